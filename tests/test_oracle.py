@@ -1,0 +1,226 @@
+"""CPU tests: pin the oracle (oracle/mmc_oracle.c) against the reference's own known
+answers, the NIST SPC/E reference energies for the bundled configurations, and the
+independent numpy restatement.  No GPU, no product code under test here."""
+import numpy as np
+import pytest
+
+from metropolismontecarlo_b200 import systems
+from oracle import numpy_ref as npr
+from oracle import oracle as ora
+from tests.util import ora_ewald, ora_system, rel
+
+
+def LennardJones(rij):  # Monatomic/mainMonatomic.jl:335-337
+    return 4 * 1 * ((1 / rij) ** 12 - (1 / rij) ** 6)
+
+
+def test_factor_constant():
+    # Ewald/constants.jl:24-28 → 167100.9566... K·Å/e²
+    assert abs(ora.factor() - 167100.95663229248) < 1e-6
+    assert ora.factor() == systems.FACTOR
+
+
+def test_vector1D_minimum_image():
+    # Ewald/boundaries.jl:8-14
+    assert ora.vector1D(0.0, 4.0, 5.0) == -1.0
+    assert ora.vector1D(4.0, 0.0, 5.0) == 1.0
+    assert ora.vector1D(0.0, 2.0, 5.0) == 2.0
+    assert ora.vector1D(1.0, 1.0, 5.0) == 0.0
+    # tie |d| == L/2 is not "<" so it wraps (c1<c2 branch: d - L)
+    assert ora.vector1D(0.0, 2.5, 5.0) == -2.5
+    assert ora.vector1D(2.5, 0.0, 5.0) == 2.5
+    rng = np.random.default_rng(1)
+    a, b = rng.random(1000) * 7, rng.random(1000) * 7
+    want = npr.vector1d(a, b, 7.0)
+    got = np.array([ora.vector1D(x, y, 7.0) for x, y in zip(a, b)])
+    assert np.array_equal(want, got)
+
+
+def test_reference_test_LJ_known_answers():
+    # Ewald/tests.jl:127-161 / Monatomic/mainMonatomic.jl:292-330
+    box, rc = 5.0, 2.5
+    r = np.array([[0, 0, 0], [0, 0, 2], [0, 1.5, 0]], dtype=np.float64)
+    e, _ = ora.LJ_dU_atom(1, r, np.ones(3), np.ones(3), box, rc)
+    assert abs(e - (-0.381860031778575)) < 1e-14
+    assert abs(e - (LennardJones(2.0) + LennardJones(1.5))) < 1e-14
+    r[1] = [0, 0, 4]
+    e, _ = ora.LJ_dU_atom(1, r, np.ones(3), np.ones(3), box, rc)
+    assert abs(e - (-0.320336594278575)) < 1e-14
+    assert abs(e - (LennardJones(1.0) + LennardJones(1.5))) < 1e-3   # the reference's own tolerance
+
+
+def test_reference_two_LJ_triangles():
+    # Ewald/tests.jl:8-82: two A&T triangles 2σ apart along z, all sites LJ(ε=σ=1), box 1000
+    alpha2 = 75.0 * np.pi / 180.0 / 2.0
+    db = np.array([[-np.sin(alpha2), 0.0, -np.cos(alpha2) / 3.0],
+                   [0.0, 0.0, 2 * np.cos(alpha2) / 3.0],
+                   [np.sin(alpha2), 0.0, -np.cos(alpha2) / 3.0]])
+    a, b = db, db + np.array([0, 0, 2.0])
+    ra = np.vstack([a, b])
+    com = np.vstack([a.mean(axis=0), b.mean(axis=0)])
+    s = ora.System(ra, np.zeros(6), np.ones(6, dtype=np.int64), [1, 4], [3, 6], com,
+                   np.ones((1, 1)), np.ones((1, 1)))
+    want = sum(LennardJones(np.sqrt(((ra[i] - ra[j]) ** 2).sum())) for i in range(3) for j in range(3, 6))
+    got, _ = ora.LJ_poly_dU(1, s, 500.0, 1000.0)
+    assert abs(got - want) < 1e-4          # the reference's own tolerance (tests.jl:72)
+    assert rel(got, want) < 1e-13
+
+
+# NIST SPC/E reference calculations (10 Å cutoff), E/k_B in K, six published digits.
+NIST = {
+    1: dict(n=100, L=20.0, fourier=6.27009e3, self_=-2.84469e6),
+    2: dict(n=200, L=20.0, fourier=6.03495e3, self_=-5.68938e6),
+    3: dict(n=300, L=20.0, fourier=5.24461e3, self_=-8.53407e6),
+    4: dict(n=750, L=30.0, fourier=7.58785e3, self_=-1.42235e7),
+}
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+def test_nist_fourier_and_self(cfg):
+    ms = systems.load_nist(cfg)
+    assert ms.n_mol == NIST[cfg]["n"] and ms.box == NIST[cfg]["L"]
+    ew = ora_ewald(ms.box)
+    assert ew.nkvecs == 337
+    e_recip = ora.RecipLong(ew, ms.coords, ms.charge, ms.box) * ew.factor
+    e_self = ora.EwaldSelf(ew, ms.charge)
+    assert abs(e_recip / NIST[cfg]["fourier"] - 1) < 5e-6
+    assert abs(e_self / NIST[cfg]["self_"] - 1) < 5e-6
+    # S(k) left in both buffers (ewalds.jl:600-601)
+    assert np.array_equal(ew.sum_old, ew.sum_new) and np.abs(ew.sum_new).max() > 0
+
+
+def test_nist_config4_atom_cutoff_contrast():
+    """Validates fixture + constants: with NIST's ATOM cutoff the numpy formulas give NIST's
+    E_disp=4.48593e5 and E_real=-3.57226e6; the reference (COM cutoff) deliberately does not."""
+    ms = systems.load_nist(4)
+    kappa, L = systems.ALPHA / ms.box, ms.box
+    O = ms.coords[0::3]
+    d = O[:, None, :] - O[None, :, :]
+    d -= L * np.rint(d / L)
+    r2 = (d * d).sum(-1)
+    iu = np.triu_indices(len(O), 1)
+    r2u = r2[iu]
+    m = r2u < 100.0
+    s6 = (systems.SPCE_SIGMA_O ** 2 / r2u[m]) ** 3
+    e_disp = (4 * systems.SPCE_EPS_O * (s6 * s6 - s6)).sum()
+    assert abs(e_disp / 4.48593e5 - 1) < 5e-6
+    from scipy.special import erfc
+    mol = np.repeat(np.arange(ms.n_mol), 3)
+    e_real = 0.0
+    for lo in range(0, ms.n_sites, 250):
+        d = ms.coords[lo:lo + 250, None, :] - ms.coords[None, :, :]
+        d -= L * np.rint(d / L)
+        r = np.sqrt((d * d).sum(-1))
+        qq = ms.charge[lo:lo + 250, None] * ms.charge[None, :]
+        ok = (r < 10.0) & (mol[lo:lo + 250, None] != mol[None, :])
+        e_real += (qq[ok] * erfc(kappa * r[ok]) / r[ok]).sum()
+    e_real *= systems.FACTOR / 2
+    assert abs(e_real / -3.57226e6 - 1) < 5e-6
+
+
+def test_kvectors_match_numpy():
+    ew = ora_ewald(30.0)
+    k, c = npr.kvectors(systems.ALPHA / 30.0, 5, 27, 30.0)
+    assert np.array_equal(k, ew.kxyz)
+    assert np.allclose(c, ew.cfac, rtol=1e-15, atol=0)
+    assert tuple(ew.kxyz[0]) == (0, -5, -1) and tuple(ew.kxyz[-1]) == (5, 1, 0)
+
+
+@pytest.mark.parametrize("cfg", [1, 4])
+def test_single_molecule_vs_numpy(cfg):
+    ms = systems.load_nist(cfg)
+    s = ora_system(ms)
+    kappa = systems.ALPHA / ms.box
+    rc = 10.0 if cfg == 4 else 9.0
+    for i in [1, 2, 17, ms.n_mol // 2, ms.n_mol]:
+        e, v = ora.LJ_poly_dU(i, s, rc, ms.box)
+        e2, v2 = npr.lj_poly(i, ms, rc, ms.box)
+        assert rel(e, e2) < 1e-12 and rel(v, v2) < 1e-11
+        p, ov = ora.EwaldReal(i, s, kappa, rc, ms.box)
+        p2, ov2 = npr.ewald_real(i, ms, kappa, rc, ms.box)
+        assert ov == ov2 and rel(p, p2) < 1e-12
+
+
+def test_recip_vs_numpy_and_delta_consistency():
+    ms = systems.load_nist(1)
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    e = ora.RecipLong(ew, ms.coords, ms.charge, ms.box)
+    S = npr.structure_factor(ew.kxyz, ms.coords, ms.charge, ms.box)
+    assert np.allclose(ew.sum_new[:, 0] + 1j * ew.sum_new[:, 1], S, rtol=0, atol=1e-11)
+    assert rel(e, npr.recip_energy(ew.cfac, S)) < 1e-12
+    # move molecule 7: delta update == fresh rebuild (ewalds.jl:434-436 comment)
+    rng = np.random.default_rng(3)
+    i = 7
+    sl = slice(3 * (i - 1), 3 * i)
+    r_old = ms.coords[sl].copy()
+    r_new = r_old + (rng.random(3) - 0.5)
+    dE = ora.RecipMove(ms.box, ew, r_old, r_new, ms.charge[sl])
+    coords2 = ms.coords.copy()
+    coords2[sl] = r_new
+    ew2 = ora_ewald(ms.box)
+    e2 = ora.RecipLong(ew2, coords2, ms.charge, ms.box)
+    assert abs(dE - (e2 - e) * ew.factor) < 1e-9 * abs(e * ew.factor)
+    assert np.allclose(ew.sum_new, ew2.sum_new, rtol=0, atol=1e-11)
+    assert not np.array_equal(ew.sum_new, ew.sum_old)
+    ora.recip_rollback(ew)
+    assert np.array_equal(ew.sum_new, ew.sum_old)
+
+
+def test_potential_coord750_reference_semantics():
+    """coord750.txt under the reference's COM-cutoff semantics (SURVEY §7 step 1 numbers)."""
+    ms = systems.load_nist(4)
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    p = ora.potential_ewald(s, ew, 10.0, 10.0, ms.box, n_threads=4)
+    assert abs(p.lj / 4.488629e5 - 1) < 2e-6
+    assert abs(p.real / -3.492756e6 - 1) < 2e-6
+    assert abs(p.recip / 7.58785e3 - 1) < 5e-6
+    assert abs(p.self_ / -1.42235e7 - 1) < 5e-6
+    assert p.overlaps == 0
+    assert rel(p.energy, p.lj + p.real + p.recip + p.self_) < 1e-14
+    assert rel(p.coulomb, p.real + p.recip + p.self_) < 1e-14
+    # threads do not change bits (rows summed in reference order)
+    p1 = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, n_threads=1)
+    assert p1.energy == p.energy and p1.virial == p.virial
+    # Wolf variant: same LJ and real parts; constants in closed form (neutral box)
+    w = ora.potential_wolf(s, ew, 10.0, 10.0, ms.box, n_threads=4)
+    assert w.lj == p.lj and w.real == p.real
+    from scipy.special import erfc
+    kappa = ew.kappa
+    qq = (ms.charge ** 2).sum()
+    closed = -(erfc(kappa * 10.0) / 20.0 + kappa / np.sqrt(np.pi)) * qq * ew.factor
+    assert rel(w.wolf_const, closed) < 1e-9
+    # Wolf potential() adds no Coulomb virial (energy.jl:905-912)
+    assert rel(w.virial, p.virial - (p.real + p.recip + p.self_) / 3.0) < 1e-9
+
+
+def test_monatomic_potential_vs_numpy():
+    at = systems.lj_lattice(343, 0.75, 2.5)
+    rng = np.random.default_rng(5)
+    at.r[:] = (at.r + rng.normal(0, 0.05, at.r.shape)) % at.box
+    e, v = ora.potential_atoms(at.r, at.eps, at.sig, at.box, at.r_cut, 2)
+    es = sum(npr.lj_atom(i, at.r, at.eps, at.sig, at.box, at.r_cut)[0] for i in range(1, at.n + 1)) / 2
+    assert rel(e, es) < 1e-12
+
+
+def test_loop_invariant_sum_of_deltas_equals_recompute():
+    """Poly/main.jl:232-235 invariant: running energy == fresh potential() after a block of moves."""
+    ms = systems.load_nist(1)           # 100 molecules, L = 20, use rc = 9 (< L/2)
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    p0 = ora.potential_ewald(s, ew, 9.0, 9.0, ms.box)
+    prm = ora.LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 9.0, 9.0, ms.box, 0, 1)
+    quat = ms.quat.copy()
+    u = np.random.default_rng(11234).random(8000)
+    rc, acc, delta, st = ora.loop(s, ew, ms.db, quat, prm, u, 500, p0.energy, p0.virial)
+    assert rc == 0 and st.n_moves == 500
+    assert 0 < st.n_accepted < 500
+    assert st.rot_attempt > 0 and st.trans_attempt > 0
+    p1 = ora.potential_ewald(s, ora_ewald(ms.box), 9.0, 9.0, ms.box)
+    assert abs(st.total_energy - p1.energy) < 1e-3          # the reference's own tolerance
+    assert rel(st.total_energy, p1.energy) < 1e-11
+    # resident S(k) after 500 delta updates == fresh rebuild
+    ew2 = ora_ewald(ms.box)
+    ora.RecipLong(ew2, s.coords, s.charge, ms.box)
+    assert np.allclose(ew.sum_old, ew2.sum_old, rtol=0, atol=1e-9)
