@@ -1,0 +1,424 @@
+// kernels_pairs.cuh — full-system pair energy for potential() / volume moves
+// (Ewald/energy.jl:946-1032 and :864-943; Ewald/volumeChange.jl:91-111), SURVEY.md §8a a9/a10/a12.
+//
+// The reference evaluates Σ_i LJ_poly_ΔU(i)/2 and Σ_i EwaldReal(i)/2: every molecule pair twice,
+// with an O(N) COM scan per molecule.  Here every unordered molecule pair is visited once:
+//   * cell mode  (box ≥ 3 r_cut): molecules are binned on their COM into cells of edge ≥ r_cut
+//     and stored cell-sorted; a work unit is (home cell, one of 14 half-shell neighbour slots);
+//   * tile mode  (small boxes):   a work unit is a (64 x 64) tile pair I ≤ J of the molecule list.
+// Units are dealt statically to persistent CTAs (no atomics → deterministic sums).  Inside a
+// unit each warp (a) runs the COM gate |COM_ij|² < r_cut² (strict, energy.jl:250, ewalds.jl:337)
+// for its share of the molecule pairs and compacts the survivors into its own shared-memory
+// queue with ballot/popc, then (b) spreads the queue's n_a·n_b site pairs over its 32 lanes, so
+// the FP64 pipe sees full warps of erfc work, and (c) runs the LJ-active site pairs (O–O only
+// for water) as a second, equally dense pass.
+//
+// Minimum image: the reference wraps every site pair separately (vector1D, boundaries.jl:8-14).
+// In cell mode the image of a surviving pair is fixed by the cell offset (shift ∈ {-L,0,+L} per
+// axis) whenever r_cut + 2·max|site-COM| < L/2; d = (x_b - x_a) ± L is then formed in the same
+// order as the reference, so the bits agree.  If that bound does not hold the kernel falls back
+// to the literal per-pair vector1D (uniform branch on a device-side flag).
+#pragma once
+#include "mmc_common.cuh"
+
+#define PAIR_BLOCK 256
+#define PAIR_WARPS (PAIR_BLOCK / 32)
+#define PAIR_TILE 64
+#define PAIR_QCAP (PAIR_TILE * PAIR_TILE / PAIR_WARPS)
+
+struct LJActive { int a, b; double eps, sig; };
+
+struct PairArgs {
+    const double4 *com;        // cell-sorted (cell mode) / original order (tile mode)
+    const double4 *site;       // S sites per molecule, site[m*S + a] = {x,y,z,q}
+    const int *cell_start;     // [ncell+1] (cell mode)
+    int ncd, S, n_mol, mode;   // mode 0: cells, 1: tiles
+    int n_tiles;
+    long long unit_begin, unit_end;
+    double L, rc_lj2, rc_qq2, kappa;
+    int want_lj, want_qq;
+    int nlj;
+    const LJActive *lj;
+    double4 *partial;          // [gridDim.x]
+    unsigned int *ovl;         // [n_mol] overlap flags (index space of `com`)
+    unsigned int *n_ovl;
+    const double *max_dev;     // max |site - COM| component, written by k_gather
+};
+
+__constant__ int c_half_shell[14][3] = {
+    {0, 0, 0},
+    {1, 0, 0},
+    {-1, 1, 0}, {0, 1, 0}, {1, 1, 0},
+    {-1, -1, 1}, {0, -1, 1}, {1, -1, 1},
+    {-1, 0, 1}, {0, 0, 1}, {1, 0, 1},
+    {-1, 1, 1}, {0, 1, 1}, {1, 1, 1}};
+
+template <int ST>   // ST = sites per molecule at compile time (0: runtime A.S)
+__global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__ PairArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = ST ? ST : A.S;
+    const int SS = S * S;
+    double4 *s_comA = reinterpret_cast<double4 *>(smem_raw);
+    double4 *s_comB = s_comA + PAIR_TILE;
+    double4 *s_siteA = s_comB + PAIR_TILE;
+    double4 *s_siteB = s_siteA + PAIR_TILE * S;
+    unsigned int *s_queue = reinterpret_cast<unsigned int *>(s_siteB + PAIR_TILE * S);
+    __shared__ LJActive s_lj[64];
+    __shared__ double s_red[3 * PAIR_WARPS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int *q = s_queue + warp * PAIR_QCAP;
+    const int nlj = min(A.nlj, 64);
+    if (tid < nlj) s_lj[tid] = A.lj[tid];
+    const double L = A.L;
+    const bool cells = (A.mode == 0);
+    double rcmax = sqrt(fmax(A.rc_lj2, A.rc_qq2));
+    const bool fast = cells && (rcmax + 2.0 * (*A.max_dev) < 0.5 * L);
+
+    // static, contiguous share of this rank's units
+    const long long n_units = A.unit_end - A.unit_begin;
+    const long long per = (n_units + gridDim.x - 1) / gridDim.x;
+    const long long u0 = A.unit_begin + per * blockIdx.x;
+    const long long u1 = (u0 + per < A.unit_end) ? u0 + per : A.unit_end;
+
+    double acc[3] = {0.0, 0.0, 0.0};   // lj_pot, lj_vir, coul
+
+    for (long long u = u0; u < u1; ++u) {
+        int a_lo, a_hi, b_lo, b_hi;
+        double shx = 0.0, shy = 0.0, shz = 0.0;
+        bool self;
+        if (cells) {
+            const int c = (int)(u / 14), slot = (int)(u - 14 * (long long)c);
+            const int n = A.ncd;
+            const int cx = c % n, cy = (c / n) % n, cz = c / (n * n);
+            int nx = cx + c_half_shell[slot][0], ny = cy + c_half_shell[slot][1],
+                nz = cz + c_half_shell[slot][2];
+            if (nx >= n) { nx -= n; shx = L; } else if (nx < 0) { nx += n; shx = -L; }
+            if (ny >= n) { ny -= n; shy = L; } else if (ny < 0) { ny += n; shy = -L; }
+            if (nz >= n) { nz -= n; shz = L; } else if (nz < 0) { nz += n; shz = -L; }
+            const int cb = nx + n * (ny + n * nz);
+            a_lo = A.cell_start[c]; a_hi = A.cell_start[c + 1];
+            b_lo = A.cell_start[cb]; b_hi = A.cell_start[cb + 1];
+            self = (slot == 0);
+        } else {
+            // unit → (I, J) with I ≤ J, row-major over the upper triangle
+            long long r = u; int I = 0, rowlen = A.n_tiles;
+            while (r >= rowlen) { r -= rowlen; ++I; --rowlen; }
+            const int J = I + (int)r;
+            a_lo = I * PAIR_TILE; a_hi = min(A.n_mol, a_lo + PAIR_TILE);
+            b_lo = J * PAIR_TILE; b_hi = min(A.n_mol, b_lo + PAIR_TILE);
+            self = (I == J);
+        }
+        for (int a0 = a_lo; a0 < a_hi; a0 += PAIR_TILE) {
+            const int nA = min(PAIR_TILE, a_hi - a0);
+            for (int b0 = b_lo; b0 < b_hi; b0 += PAIR_TILE) {
+                if (self && b0 + PAIR_TILE <= a0) continue;   // strictly lower sub-tile
+                const int nB = min(PAIR_TILE, b_hi - b0);
+                __syncthreads();
+                for (int t = tid; t < nA; t += PAIR_BLOCK) s_comA[t] = A.com[a0 + t];
+                for (int t = tid; t < nB; t += PAIR_BLOCK) s_comB[t] = A.com[b0 + t];
+                for (int t = tid; t < nA * S; t += PAIR_BLOCK) s_siteA[t] = A.site[(size_t)a0 * S + t];
+                for (int t = tid; t < nB * S; t += PAIR_BLOCK) s_siteB[t] = A.site[(size_t)b0 * S + t];
+                __syncthreads();
+                // ---- (a) COM gate, warp-private ordered compaction
+                int npairs = 0;
+                const int ntests = nA * nB;
+                for (int t0 = warp * 32; t0 < ntests; t0 += PAIR_BLOCK) {
+                    const int t = t0 + lane;
+                    int fl = 0, p = 0, qq_ = 0;
+                    if (t < ntests) {
+                        p = t / nB; qq_ = t - p * nB;
+                        if (!self || (b0 + qq_ > a0 + p)) {
+                            const double4 ca = s_comA[p], cb = s_comB[qq_];
+                            double dx, dy, dz;
+                            if (cells) {
+                                dx = (cb.x - ca.x) + shx; dy = (cb.y - ca.y) + shy; dz = (cb.z - ca.z) + shz;
+                            } else {
+                                dx = min_image(ca.x, cb.x, L); dy = min_image(ca.y, cb.y, L);
+                                dz = min_image(ca.z, cb.z, L);
+                            }
+                            const double r2 = dx * dx + dy * dy + dz * dz;
+                            if (A.want_lj && r2 < A.rc_lj2) fl |= 1;
+                            if (A.want_qq && r2 < A.rc_qq2) fl |= 2;
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, fl != 0);
+                    if (fl) q[npairs + __popc(m & ((1u << lane) - 1u))] =
+                        (unsigned)p | ((unsigned)qq_ << 8) | ((unsigned)fl << 16);
+                    npairs += __popc(m);
+                }
+                __syncwarp();
+                // ---- (b) Coulomb: all S x S site pairs of the queued molecule pairs
+                if (A.want_qq) {
+                    const int items = npairs * SS;
+                    for (int w = lane; w < items; w += 32) {
+                        const int pr = w / SS, ab = w - pr * SS;
+                        const unsigned e = q[pr];
+                        if (!(e & (2u << 16))) continue;
+                        const int p = e & 255u, qi = (e >> 8) & 255u;
+                        const int a = ab / S, b = ab - a * S;
+                        const double4 sa = s_siteA[p * S + a], sb = s_siteB[qi * S + b];
+                        double dx, dy, dz;
+                        if (fast) {
+                            dx = (sb.x - sa.x) + shx; dy = (sb.y - sa.y) + shy; dz = (sb.z - sa.z) + shz;
+                        } else {
+                            dx = min_image(sa.x, sb.x, L); dy = min_image(sa.y, sb.y, L);
+                            dz = min_image(sa.z, sb.z, L);
+                        }
+                        const double r2 = dx * dx + dy * dy + dz * dz;
+                        const double qq = sa.w * sb.w;
+                        if ((r2 < 0.5) && (qq < 0)) {                       // ewalds.jl:359
+                            if (atomicExch(&A.ovl[a0 + p], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
+                            if (atomicExch(&A.ovl[b0 + qi], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
+                        } else if (r2 < (A.rc_qq2 + 100)) {
+                            const double r = sqrt(r2);
+                            acc[2] += qq * erfc(A.kappa * r) / r;           // ewalds.jl:366-367
+                        }
+                    }
+                }
+                // ---- (c) LJ: only the site-type combinations with ε_ij > 0.001 (energy.jl:270)
+                if (A.want_lj) {
+                    const int items = npairs * nlj;
+                    for (int w = lane; w < items; w += 32) {
+                        const int pr = w / nlj, li = w - pr * nlj;
+                        const unsigned e = q[pr];
+                        if (!(e & (1u << 16))) continue;
+                        const int p = e & 255u, qi = (e >> 8) & 255u;
+                        const LJActive lj = s_lj[li];
+                        const double4 sa = s_siteA[p * S + lj.a], sb = s_siteB[qi * S + lj.b];
+                        const double4 ca = s_comA[p], cb = s_comB[qi];
+                        double dx, dy, dz, rx, ry, rz;
+                        if (cells) {
+                            rx = (cb.x - ca.x) + shx; ry = (cb.y - ca.y) + shy; rz = (cb.z - ca.z) + shz;
+                        } else {
+                            rx = min_image(ca.x, cb.x, L); ry = min_image(ca.y, cb.y, L);
+                            rz = min_image(ca.z, cb.z, L);
+                        }
+                        if (fast) {
+                            dx = (sb.x - sa.x) + shx; dy = (sb.y - sa.y) + shy; dz = (sb.z - sa.z) + shz;
+                        } else {
+                            dx = min_image(sa.x, sb.x, L); dy = min_image(sa.y, sb.y, L);
+                            dz = min_image(sa.z, sb.z, L);
+                        }
+                        const double r2 = dx * dx + dy * dy + dz * dz;
+                        if (r2 < (A.rc_lj2 + 100))
+                            lj_pair(lj.eps, lj.sig, r2, dx, dy, dz, rx, ry, rz, acc[0], acc[1]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    block_sum<3, PAIR_BLOCK>(acc, s_red);
+    if (tid == 0) A.partial[blockIdx.x] = make_double4(acc[0], acc[1], acc[2], 0.0);
+}
+
+// fold the per-CTA partials in CTA order into the head of the partial-sum vector:
+// out[0] = Σ lj_pot, out[1] = Σ lj_vir, out[2] = Σ coul (un-scaled), out[3] = #overlapped molecules
+__global__ void k_pair_reduce(const double4 *partial, int nb, const unsigned int *n_ovl, double *out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = 0; i < nb; ++i) { const double4 p = partial[i]; a += p.x; b += p.y; c += p.z; }
+    out[0] = a; out[1] = b; out[2] = c; out[3] = (double)(*n_ovl);
+}
+
+// ------------------------------------------------------------------ cell binning + gather
+struct CellArgs {
+    const double4 *com;
+    int n_mol, ncd;
+    double inv_cell;     // ncd / L
+    int *cell_of;        // [n_mol]
+    int *count;          // [ncell]  (zeroed)
+    int *start;          // [ncell+1]
+    int *fill;           // [ncell]  (zeroed)
+    int *perm;           // [n_mol] sorted position -> molecule
+};
+
+__device__ __forceinline__ int cell_coord(double x, double inv_cell, int n)
+{
+    int c = (int)floor(x * inv_cell);
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+__global__ void k_cell_count(CellArgs A)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= A.n_mol) return;
+    const double4 c = A.com[m];
+    const int cx = cell_coord(c.x, A.inv_cell, A.ncd), cy = cell_coord(c.y, A.inv_cell, A.ncd),
+              cz = cell_coord(c.z, A.inv_cell, A.ncd);
+    const int id = cx + A.ncd * (cy + A.ncd * cz);
+    A.cell_of[m] = id;
+    atomicAdd(&A.count[id], 1);
+}
+
+// exclusive scan of count[0..ncell) into start[0..ncell], single CTA
+__global__ void k_cell_scan(CellArgs A, int ncell)
+{
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int per = (ncell + nth - 1) / nth;
+    const int lo = tid * per, hi = min(ncell, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += A.count[i];
+    s_part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int t = 0; t < nth; ++t) { const int v = s_part[t]; s_part[t] = run; run += v; }
+        A.start[ncell] = run;
+    }
+    __syncthreads();
+    int run = s_part[tid];
+    for (int i = lo; i < hi; ++i) { A.start[i] = run; run += A.count[i]; }
+}
+
+__global__ void k_cell_fill(CellArgs A)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= A.n_mol) return;
+    const int id = A.cell_of[m];
+    const int pos = atomicAdd(&A.fill[id], 1);
+    A.perm[A.start[id] + pos] = m;
+}
+
+// one warp per cell: order the cell's molecules by index so that the summation order (and so
+// every bit of the result) is independent of the atomics' arrival order above
+__global__ void k_cell_sort(CellArgs A, int ncell)
+{
+    const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (cell >= ncell) return;
+    const int lo = A.start[cell], n = A.start[cell + 1] - lo;
+    // rank sort through registers: n is a few dozen
+    int mine[8], rank[8];
+    for (int u = 0; u < 8; ++u) {
+        const int t = lane + 32 * u;
+        mine[u] = t < n ? A.perm[lo + t] : 0x7fffffff;
+        rank[u] = 0;
+    }
+    if (n > 256) return;   // pathological density: keep arrival order (still correct, not bit-stable)
+    for (int j = 0; j < n; ++j) {
+        const int v = A.perm[lo + j];
+        for (int u = 0; u < 8; ++u) rank[u] += (v < mine[u]);
+    }
+    __syncwarp();
+    for (int u = 0; u < 8; ++u) {
+        const int t = lane + 32 * u;
+        if (t < n) A.perm[lo + rank[u]] = mine[u];
+    }
+}
+
+struct GatherArgs {
+    const double4 *com, *site;
+    const int *perm;        // NULL: identity
+    int n_mol, S;
+    double f;               // box_new / box (1.0: no volume change)
+    double4 *scom, *ssite;
+    unsigned long long *max_dev_bits;   // atomicMax over the bits of max |site-COM| component
+};
+
+// cell-sorted copy of the state; for a volume trial the COMs are scaled by f and the sites
+// rigidly shifted (Ewald/volumeChange.jl:62-80: coords_new = f*coords; change = coords_new -
+// coords; atom_XYZ = atom_coords + change). f == 1 reproduces the state bit for bit.
+__global__ void k_gather(GatherArgs A)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n_mol) return;
+    const int m = A.perm ? A.perm[p] : p;
+    const double4 c = A.com[m];
+    double4 cn = c;
+    cn.x = A.f * c.x; cn.y = A.f * c.y; cn.z = A.f * c.z;
+    const double chx = cn.x - c.x, chy = cn.y - c.y, chz = cn.z - c.z;
+    A.scom[p] = cn;
+    double dev = 0.0;
+    for (int a = 0; a < A.S; ++a) {
+        double4 s = A.site[(size_t)m * A.S + a];
+        dev = fmax(dev, fmax(fabs(s.x - c.x), fmax(fabs(s.y - c.y), fabs(s.z - c.z))));
+        s.x = s.x + chx; s.y = s.y + chy; s.z = s.z + chz;
+        A.ssite[(size_t)p * A.S + a] = s;
+    }
+    // warp max, then one atomic per warp (non-negative doubles order like their bit patterns)
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(A.max_dev_bits, (unsigned long long)__double_as_longlong(dev));
+}
+
+// accept of a volume move: the scaled state becomes the resident one (volumeChange.jl:141-144)
+__global__ void k_apply_scale(DevSystem S, double f)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= S.n_mol) return;
+    const double4 c = S.com[m];
+    double4 cn = c;
+    cn.x = f * c.x; cn.y = f * c.y; cn.z = f * c.z;
+    const double chx = cn.x - c.x, chy = cn.y - c.y, chz = cn.z - c.z;
+    S.com[m] = cn;
+    const int2 mi = S.mol[m];
+    for (int a = 0; a < mi.y; ++a) {
+        double4 s = S.site[mi.x + a];
+        s.x = s.x + chx; s.y = s.y + chy; s.z = s.z + chz;
+        S.site[mi.x + a] = s;
+    }
+}
+
+// Σq and Σq² (EwaldSelf ewalds.jl:829-833, Wolf constants energy.jl:924-934), single CTA, ordered
+__global__ void k_charge_sums(const double4 *site, int n, double *out)
+{
+    __shared__ double s_red[2 * 8];
+    double acc[2] = {0.0, 0.0};
+    for (int l = threadIdx.x; l < n; l += 256) { const double q = site[l].w; acc[0] += q; acc[1] += q * q; }
+    block_sum<2, 256>(acc, s_red);
+    if (threadIdx.x == 0) { out[0] = acc[0]; out[1] = acc[1]; }
+}
+
+// ------------------------------------------------------------------- monatomic potential
+// Monatomic/mainMonatomic.jl:275-289: Σ_i LJ_ΔU(i) / 2, rows over CTAs (double counted like the
+// reference: the per-j ε_j, σ_j make the (i,j) and (j,i) terms different).
+__global__ void __launch_bounds__(256) k_atoms_rows(DevAtoms S, double2 *rows)
+{
+    __shared__ double s_red[2 * 8];
+    const double L = S.box, rc2 = S.rc * S.rc;
+    for (int i = blockIdx.x; i < S.n; i += gridDim.x) {
+        const double4 r0 = S.r[i];
+        double acc[2] = {0.0, 0.0};
+        for (int j = threadIdx.x; j < S.n; j += 256) {
+            if (j == i) continue;
+            const double4 rj = S.r[j];
+            const double dx = min_image(r0.x, rj.x, L), dy = min_image(r0.y, rj.y, L),
+                         dz = min_image(r0.z, rj.z, L);
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            if (!(r2 > rc2)) {
+                const double2 es = S.es[j];
+                const double sr2 = es.y * es.y / r2, sr6 = sr2 * sr2 * sr2, sr12 = sr6 * sr6;
+                acc[0] += es.x * (sr12 - sr6);
+                acc[1] += es.x * (2 * sr12 - sr6);
+            }
+        }
+        block_sum<2, 256>(acc, s_red);
+        if (threadIdx.x == 0) rows[i] = make_double2(acc[0] * 4.0, acc[1] * 24.0 / 3.0);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_rows_sum(const double2 *rows, int n, double *out)
+{
+    __shared__ double s_red[2 * 8];
+    double acc[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += 256) { acc[0] += rows[i].x; acc[1] += rows[i].y; }
+    block_sum<2, 256>(acc, s_red);
+    if (threadIdx.x == 0) { out[0] = acc[0] / 2; out[1] = acc[1] / 2; }
+}
+
+// ------------------------------------------------------------------- FP64 peak probe
+// 8 independent DFMA chains per thread; reports 2 flop per DFMA.
+__global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 0.123) out[0] = a0;
+}

@@ -1,0 +1,1167 @@
+// mmc_api.cu — C ABI of libmmc_b200.so (include/mmc_b200.h) on top of the sm_100a kernels.
+// No CPU fallback: every energy returned here was computed by a kernel in this directory.
+#include "../../include/mmc_b200.h"
+#include "kernels_move.cuh"
+#include "kernels_pairs.cuh"
+#include "kernels_recip.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <immintrin.h>
+
+namespace {
+
+std::string g_create_error;
+
+struct Timers { cudaEvent_t ev[8]; bool on = false; float ms[4] = {0, 0, 0, 0}; };
+
+}  // namespace
+
+struct mmc_handle {
+    mmc_config cfg{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // ---- molecular system
+    bool has_system = false;
+    DevSystem S{};
+    std::vector<int2> h_mol;     // host mirror of S.mol
+    bool uniform = false;        // every molecule: same site count, same type sequence, packed
+    int US = 0;                  // uniform sites per molecule
+    std::vector<LJActive> lj;
+    LJActive *d_lj = nullptr;
+    int2 *d_mol_uniform = nullptr;
+    double sum_q = 0.0, sum_q2 = 0.0;
+    double *d_qsums = nullptr;
+
+    // ---- ewald
+    bool has_ewald = false;
+    int k_sq_max = 0;
+    std::vector<int32_t> kxyz;
+    std::vector<double> cfac;
+    int cur = 0;                 // index of the Old ρ(k) buffer
+    bool new_valid = false;
+    double2 *d_rhok_trial = nullptr;
+    double *d_cfac_trial = nullptr;
+    std::vector<double> cfac_trial;
+
+    // ---- move scratch
+    MoveScratch W{};
+    MoveOut *h_out = nullptr;
+    unsigned long long seq = 0;
+    bool trial_pending = false;
+    int trial_kind = 0;          // 1 molecule, 2 atom
+    int trial_style = 0;
+    MoveArgs last{};
+    AtomArgs last_atom{};
+    bool last_overlap = false;
+
+    // ---- full-energy scratch
+    int *d_cell_of = nullptr, *d_count = nullptr, *d_start = nullptr, *d_fill = nullptr, *d_perm = nullptr;
+    int ncell_cap = 0;
+    double4 *d_scom = nullptr, *d_ssite = nullptr;
+    double4 *d_pair_partial = nullptr;
+    int pair_grid = 0;
+    unsigned int *d_ovl = nullptr, *d_novl = nullptr;
+    double *d_maxdev = nullptr;
+    double2 *d_rhok_partial = nullptr;
+    int rhok_grid_cap = 0;
+    double *d_vec = nullptr;     // internal partial-sum vector (MMC_NSCAL + 2*NK doubles)
+    double *h_vec = nullptr;     // pinned
+    int last_mode = -1;          // 0 cells, 1 tiles, 2 rows
+    int last_ncd = 0;
+
+    // ---- volume trial
+    bool vol_pending = false;
+    double vol_box = 0, vol_kappa = 0, vol_f = 1;
+    int vol_style = 0;
+
+    // ---- atoms
+    bool has_atoms = false;
+    DevAtoms At{};
+    double2 *d_rows = nullptr;
+    double *d_atoms_out = nullptr;
+
+    int sm_count = 148;
+    mmc_counters cnt{};
+    Timers tm;
+};
+
+namespace {
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return MMC_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+#define FAIL(code, msg)                                                                       \
+    do {                                                                                      \
+        h->err = (msg);                                                                       \
+        return (code);                                                                        \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                        \
+    do {                                                                                      \
+        h->cnt.kernel_launches++;                                                             \
+        cudaError_t e_ = cudaGetLastError();                                                  \
+        if (e_ != cudaSuccess) {                                                              \
+            h->err = std::string("kernel launch: ") + cudaGetErrorString(e_);                 \
+            return MMC_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+template <typename T>
+void dfree(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void free_system(mmc_handle *h)
+{
+    dfree(h->S.site); dfree(h->S.com); dfree(h->S.mol); dfree(h->S.atype);
+    dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums);
+    dfree(h->d_cell_of); dfree(h->d_count); dfree(h->d_start); dfree(h->d_fill); dfree(h->d_perm);
+    dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl); dfree(h->d_novl);
+    dfree(h->d_maxdev); dfree(h->d_rhok_partial);
+    h->has_system = false;
+}
+
+void free_ewald(mmc_handle *h)
+{
+    dfree(h->S.kvec); dfree(h->S.cfac); dfree(h->S.rhok[0]); dfree(h->S.rhok[1]);
+    dfree(h->d_rhok_trial); dfree(h->d_cfac_trial); dfree(h->d_vec);
+    if (h->h_vec) cudaFreeHost(h->h_vec);
+    h->h_vec = nullptr;
+    h->has_ewald = false;
+}
+
+void free_atoms(mmc_handle *h)
+{
+    dfree(h->At.r); dfree(h->At.es); dfree(h->d_rows); dfree(h->d_atoms_out);
+    h->has_atoms = false;
+}
+
+int ensure_vec(mmc_handle *h)
+{
+    if (h->d_vec) return MMC_OK;
+    const size_t n = MMC_NSCAL + 2 * (size_t)std::max(h->S.nkvecs, 1);
+    CK(cudaMalloc(&h->d_vec, n * sizeof(double)));
+    CK(cudaMemsetAsync(h->d_vec, 0, n * sizeof(double), h->stream));
+    CK(cudaHostAlloc(&h->h_vec, n * sizeof(double), cudaHostAllocDefault));
+    return MMC_OK;
+}
+
+// wait for the last CTA's publication of launch `seq`
+int wait_out(mmc_handle *h)
+{
+    if (h->cfg.sync_mode == 1) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->h_out->seq != h->seq) FAIL(MMC_ECUDA, "move kernel finished without publishing its result");
+        return MMC_OK;
+    }
+    volatile unsigned long long *flag = &h->h_out->seq;
+    unsigned spins = 0;
+    while (*flag != h->seq) {
+        _mm_pause();
+        if ((++spins & 0xfffffu) == 0) {   // every ~1M polls make sure the kernel is still alive
+            cudaError_t q = cudaStreamQuery(h->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) {
+                h->err = std::string("move kernel: ") + cudaGetErrorString(q);
+                return MMC_ECUDA;
+            }
+            if (q == cudaSuccess && *flag != h->seq)
+                FAIL(MMC_ECUDA, "move kernel finished without publishing its result");
+        }
+    }
+    return MMC_OK;
+}
+
+int move_tiles(const mmc_handle *h)
+{
+    const int t = (h->S.n_mol + MOVE_BLOCK - 1) / MOVE_BLOCK;
+    return std::max(1, std::min(t, h->sm_count));
+}
+
+int launch_move(mmc_handle *h, MoveArgs &A)
+{
+    A.seq = ++h->seq;
+    const int blocks = A.n_cfg * A.tiles + A.recip_blocks;
+    if (blocks <= 0) FAIL(MMC_EINVAL, "empty move launch");
+    k_move<<<blocks, MOVE_BLOCK, 0, h->stream>>>(h->S, A, h->W);
+    LAUNCH_CHECK();
+    return wait_out(h);
+}
+
+int check_mol_index(mmc_handle *h, int64_t i)
+{
+    if (!h->has_system) FAIL(MMC_ESTATE, "no molecular system uploaded");
+    if (i < 1 || i > h->S.n_mol) FAIL(MMC_EINVAL, "molecule index out of range (1-based)");
+    return MMC_OK;
+}
+
+void fill_kvectors(int nk, int k_sq_max, std::vector<int32_t> &kxyz)
+{
+    kxyz.clear();
+    for (int kx = 0; kx <= nk; ++kx)           // Ewald/ewalds.jl:70-91 loop order
+        for (int ky = -nk; ky <= nk; ++ky)
+            for (int kz = -nk; kz <= nk; ++kz) {
+                const int k_sq = kx * kx + ky * ky + kz * kz;
+                if (k_sq < k_sq_max && k_sq != 0) { kxyz.push_back(kx); kxyz.push_back(ky); kxyz.push_back(kz); }
+            }
+}
+
+// cfac table of Ewald/ewalds.jl:52,78-83 (host-side table, uploaded once per box size)
+void fill_cfac(const std::vector<int32_t> &kxyz, double kappa, double box, std::vector<double> &cfac)
+{
+    const double b = 1.0 / 4.0 / kappa / kappa / box / box;
+    const double twopi = 2.0 * M_PI, twopi_sq = twopi * twopi;
+    const size_t n = kxyz.size() / 3;
+    cfac.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        const int kx = kxyz[3 * i], ky = kxyz[3 * i + 1], kz = kxyz[3 * i + 2];
+        const double kr_sq = twopi_sq * (double)(kx * kx + ky * ky + kz * kz);
+        double c = twopi * std::exp(-b * kr_sq) / kr_sq / box;
+        if (kx > 0) c = c * 2.0;
+        cfac[i] = c;
+    }
+}
+
+// ---------------------------------------------------------------- full-energy evaluation
+struct EvalCtx {
+    double f, box, kappa;          // scale factor, box and kappa the energy is evaluated at
+    const double *d_cfac;
+    int rank, world;
+};
+
+int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, double box, double2 *out)
+{
+    const int n = s_end - s_begin;
+    const int nkv = h->S.nkvecs;
+    int per = std::max(2 * RHOK_SITES, (n + 2 * h->sm_count - 1) / (2 * h->sm_count));
+    per = (per + RHOK_SITES - 1) / RHOK_SITES * RHOK_SITES;
+    const int nb = std::max(1, (n + per - 1) / per);
+    if (nb > h->rhok_grid_cap) {
+        dfree(h->d_rhok_partial);
+        CK(cudaMalloc(&h->d_rhok_partial, (size_t)nb * nkv * sizeof(double2)));
+        h->rhok_grid_cap = nb;
+    }
+    RhokArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->S.kvec, box, h->d_rhok_partial};
+    const int kpt = (nkv + RHOK_BLOCK - 1) / RHOK_BLOCK;
+    if (h->tm.on) cudaEventRecord(h->tm.ev[2], h->stream);
+    if (kpt <= 1) k_rhok_partial<1><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
+    else if (kpt <= 2) k_rhok_partial<2><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
+    else if (kpt <= 4) k_rhok_partial<4><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
+    else if (kpt <= 8) k_rhok_partial<8><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
+    else FAIL(MMC_EINVAL, "too many k-vectors for the rebuild kernel (nk too large)");
+    LAUNCH_CHECK();
+    if (h->tm.on) cudaEventRecord(h->tm.ev[3], h->stream);
+    k_rhok_reduce<<<(nkv + 127) / 128, 128, 0, h->stream>>>(h->d_rhok_partial, nb, nkv, out);
+    LAUNCH_CHECK();
+    return MMC_OK;
+}
+
+// Leaves this rank's partial sums in d_vec: [0] Σlj_pot [1] Σlj_vir [2] Σcoul [3] #overlap
+// [MMC_NSCAL ..) ρ(k) partial (re,im).
+int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
+{
+    if (!h->uniform) FAIL(MMC_EINVAL, "pair kernel needs a uniform topology (internal)");
+    const DevSystem &S = h->S;
+    const int US = h->US;
+    const bool want_qq = (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF);
+    const double rcmax = std::max(S.rc_lj, want_qq ? S.rc_qq : 0.0);
+    int ncd = (int)std::floor(E.box / rcmax);
+    if (ncd > 128) ncd = 128;
+    const bool cells = ncd >= 3;
+    CK(cudaMemsetAsync(d_vec, 0, (MMC_NSCAL + 2 * (size_t)std::max(S.nkvecs, 1)) * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_maxdev, 0, sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_novl, 0, sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(h->d_ovl, 0, sizeof(unsigned) * S.n_mol, h->stream));
+    if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
+    const int tb = 256, gm = (S.n_mol + tb - 1) / tb;
+    long long n_units;
+    if (cells) {
+        const int ncell = ncd * ncd * ncd;
+        if (ncell > h->ncell_cap) {
+            dfree(h->d_count); dfree(h->d_start); dfree(h->d_fill);
+            CK(cudaMalloc(&h->d_count, sizeof(int) * ncell));
+            CK(cudaMalloc(&h->d_start, sizeof(int) * (ncell + 1)));
+            CK(cudaMalloc(&h->d_fill, sizeof(int) * ncell));
+            h->ncell_cap = ncell;
+        }
+        CK(cudaMemsetAsync(h->d_count, 0, sizeof(int) * ncell, h->stream));
+        CK(cudaMemsetAsync(h->d_fill, 0, sizeof(int) * ncell, h->stream));
+        // fractional COM coordinates are invariant under the volume scaling: bin the resident state
+        CellArgs C{S.com, S.n_mol, ncd, (double)ncd / S.box, h->d_cell_of, h->d_count, h->d_start,
+                   h->d_fill, h->d_perm};
+        k_cell_count<<<gm, tb, 0, h->stream>>>(C); LAUNCH_CHECK();
+        k_cell_scan<<<1, 1024, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
+        k_cell_fill<<<gm, tb, 0, h->stream>>>(C); LAUNCH_CHECK();
+        k_cell_sort<<<(ncell * 32 + tb - 1) / tb, tb, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
+        n_units = 14LL * ncell;
+    } else {
+        const long long nt = (S.n_mol + PAIR_TILE - 1) / PAIR_TILE;
+        n_units = nt * (nt + 1) / 2;
+    }
+    GatherArgs G{S.com, S.site, cells ? h->d_perm : nullptr, S.n_mol, US, E.f, h->d_scom, h->d_ssite,
+                 reinterpret_cast<unsigned long long *>(h->d_maxdev)};
+    k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
+    if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
+
+    PairArgs P{};
+    P.com = h->d_scom; P.site = h->d_ssite; P.cell_start = h->d_start;
+    P.ncd = ncd; P.S = US; P.n_mol = S.n_mol; P.mode = cells ? 0 : 1;
+    P.n_tiles = (S.n_mol + PAIR_TILE - 1) / PAIR_TILE;
+    P.unit_begin = n_units * E.rank / E.world;
+    P.unit_end = n_units * (E.rank + 1) / E.world;
+    P.L = E.box; P.rc_lj2 = S.rc_lj * S.rc_lj; P.rc_qq2 = S.rc_qq * S.rc_qq; P.kappa = E.kappa;
+    P.want_lj = 1; P.want_qq = want_qq ? 1 : 0;
+    P.nlj = (int)h->lj.size(); P.lj = h->d_lj;
+    P.partial = h->d_pair_partial; P.ovl = h->d_ovl; P.n_ovl = h->d_novl; P.max_dev = h->d_maxdev;
+    const long long my_units = P.unit_end - P.unit_begin;
+    const int grid = (int)std::max(1LL, std::min<long long>(h->pair_grid, my_units));
+    const size_t smem = (2 * PAIR_TILE + 2 * PAIR_TILE * (size_t)US) * sizeof(double4) +
+                        (size_t)PAIR_WARPS * PAIR_QCAP * sizeof(unsigned);
+    if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
+    if (US == 3) k_pairs<3><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+    else k_pairs<0><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+    LAUNCH_CHECK();
+    if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
+    k_pair_reduce<<<1, 32, 0, h->stream>>>(h->d_pair_partial, grid, h->d_novl, d_vec); LAUNCH_CHECK();
+    h->last_mode = cells ? 0 : 1;
+    h->last_ncd = ncd;
+
+    if (style == MMC_STYLE_EWALD) {
+        const long long ns = S.n_sites;
+        const int s0 = (int)(ns * E.rank / E.world), s1 = (int)(ns * (E.rank + 1) / E.world);
+        int rc = rhok_launch(h, h->d_ssite, s0, s1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL));
+        if (rc) return rc;
+    }
+    return MMC_OK;
+}
+
+// single-molecule Coulomb row on the (scaled, sorted) evaluation copy, overlap pairs skipped
+int overlap_row(mmc_handle *h, const EvalCtx &E, int sorted_index, double *row)
+{
+    DevSystem V = h->S;
+    V.site = h->d_ssite; V.com = h->d_scom; V.mol = h->d_mol_uniform;
+    V.box = E.box; V.kappa = E.kappa;
+    MoveArgs A{};
+    A.i = sorted_index; A.n_cfg = 1; A.tiles = move_tiles(h); A.recip_blocks = 0;
+    A.want_lj = 0; A.want_qq = 1; A.ignore_overlap = 1; A.cur = h->cur;
+    A.seq = ++h->seq;
+    k_move<<<A.tiles, MOVE_BLOCK, 0, h->stream>>>(V, A, h->W);
+    LAUNCH_CHECK();
+    int rc = wait_out(h);
+    if (rc) return rc;
+    *row = h->h_out->qq[0];
+    return MMC_OK;
+}
+
+// d_vec holds the (already rank-summed) partials; computes E_recip on the device, brings the
+// scalars to the host and assembles Properties in the reference's order (energy.jl:972-1021).
+int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 *dst0, double2 *dst1,
+             mmc_properties *out)
+{
+    const DevSystem &S = h->S;
+    if (style == MMC_STYLE_EWALD) {
+        k_rhok_energy<<<1, RHOKE_BLOCK, 0, h->stream>>>(reinterpret_cast<const double2 *>(d_vec + MMC_NSCAL),
+                                                       E.d_cfac, S.nkvecs, dst0, dst1, d_vec + 4);
+        LAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(h->h_vec, d_vec, MMC_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->tm.on) cudaEventRecord(h->tm.ev[6], h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    double lj_pot = h->h_vec[0], lj_vir = h->h_vec[1], coul = h->h_vec[2];
+    const long long novl = (long long)h->h_vec[3];
+    const double recip_raw = h->h_vec[4];
+    if (novl > 0 && (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF)) {
+        // reference semantics: a molecule whose EwaldReal row hits the overlap rule contributes
+        // 0 for its whole row (ewalds.jl:359-360 inside energy.jl:991-1001): U - ½ Σ_flagged row_i
+        if (E.world > 1) FAIL(MMC_ESTATE, "overlap in a sharded evaluation: re-run unsharded (mmc_potential)");
+        std::vector<unsigned> fl(S.n_mol);
+        CK(cudaMemcpy(fl.data(), h->d_ovl, sizeof(unsigned) * S.n_mol, cudaMemcpyDeviceToHost));
+        for (int p = 0; p < S.n_mol; ++p)
+            if (fl[p]) {
+                double row;
+                int rc = overlap_row(h, E, p, &row);
+                if (rc) return rc;
+                coul -= row / 2;
+            }
+        h->cnt.overlap_events += novl;
+    }
+    std::memset(out, 0, sizeof(*out));
+    const double factor = S.factor;
+    out->lj = lj_pot * 4;                       // Σ_i(4 pot_i)/2 over unique pairs
+    const double vir_lj = lj_vir * 24 / 3.0;
+    out->energy = out->lj;
+    out->virial = vir_lj;
+    out->overlaps = novl;
+    if (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF) {
+        const double totReal = coul * factor;   // (Σ_i row_i) * factor / 2
+        out->real = totReal;
+        out->energy += totReal;
+        out->coulomb += totReal;
+        if (style == MMC_STYLE_EWALD) {
+            out->virial += totReal / 3.0;
+            const double recipEnergy = recip_raw * factor;
+            out->recip = recipEnergy;
+            out->energy += recipEnergy;
+            out->coulomb += recipEnergy;
+            out->virial += recipEnergy / 3.0;
+            const double selfEnergy = -E.kappa * h->sum_q2 / std::sqrt(M_PI) * factor;   // ewalds.jl:829-833
+            out->self_ = selfEnergy;
+            out->energy += selfEnergy;
+            out->coulomb += selfEnergy;
+            out->virial += selfEnergy / 3.0;
+        } else {
+            // energy.jl:924-934 with Σ_iΣ_j q_i q_j = (Σq)² in closed form; r_cut = LJ_rcut (:874)
+            const double r_cut = S.rc_lj;
+            const double ec = std::erfc(E.kappa * r_cut);
+            const double prefactor = -(h->sum_q * h->sum_q) * ec / r_cut;
+            const double prefactor2 = (ec / 2 / r_cut + E.kappa / std::sqrt(M_PI)) * h->sum_q2;
+            out->wolf_const = (prefactor - prefactor2) * factor;
+            out->energy += out->wolf_const;
+            out->coulomb += out->wolf_const;
+        }
+    }
+    if (h->tm.on) {
+        cudaEventElapsedTime(&h->tm.ms[0], h->tm.ev[0], h->tm.ev[1]);
+        if (style == MMC_STYLE_EWALD) cudaEventElapsedTime(&h->tm.ms[1], h->tm.ev[2], h->tm.ev[3]);
+        cudaEventElapsedTime(&h->tm.ms[2], h->tm.ev[4], h->tm.ev[5]);
+        cudaEventElapsedTime(&h->tm.ms[3], h->tm.ev[4], h->tm.ev[6]);
+    }
+    h->cnt.full_energy_evals++;
+    return MMC_OK;
+}
+
+// non-uniform topologies: literal Σ_i rows / 2 through the single-molecule kernel
+int potential_rows(mmc_handle *h, int style, mmc_properties *out)
+{
+    const DevSystem &S = h->S;
+    const bool want_qq = (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF);
+    double lj = 0, vir = 0, real = 0;
+    long long novl = 0;
+    for (int i = 0; i < S.n_mol; ++i) {
+        MoveArgs A{};
+        A.i = i; A.n_cfg = 1; A.tiles = move_tiles(h); A.want_lj = 1; A.want_qq = want_qq; A.cur = h->cur;
+        int rc = launch_move(h, A);
+        if (rc) return rc;
+        lj += h->h_out->lj_pot[0]; vir += h->h_out->lj_vir[0]; real += h->h_out->qq[0];
+        novl += h->h_out->overlap[0];
+    }
+    std::memset(out, 0, sizeof(*out));
+    out->lj = lj / 2; out->energy = lj / 2; out->virial = vir / 2; out->overlaps = novl;
+    if (want_qq) {
+        const double totReal = real * S.factor / 2;
+        out->real = totReal; out->energy += totReal; out->coulomb += totReal;
+        if (style == MMC_STYLE_EWALD) {
+            out->virial += totReal / 3.0;
+            int rc = ensure_vec(h);
+            if (rc) return rc;
+            rc = rhok_launch(h, S.site, 0, S.n_sites, S.box, reinterpret_cast<double2 *>(h->d_vec + MMC_NSCAL));
+            if (rc) return rc;
+            k_rhok_energy<<<1, RHOKE_BLOCK, 0, h->stream>>>(reinterpret_cast<const double2 *>(h->d_vec + MMC_NSCAL),
+                                                           S.cfac, S.nkvecs, S.rhok[0], S.rhok[1], h->d_vec + 4);
+            LAUNCH_CHECK();
+            CK(cudaMemcpyAsync(h->h_vec, h->d_vec, MMC_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            const double recipEnergy = h->h_vec[4] * S.factor;
+            out->recip = recipEnergy; out->energy += recipEnergy; out->coulomb += recipEnergy;
+            out->virial += recipEnergy / 3.0;
+            const double selfEnergy = -S.kappa * h->sum_q2 / std::sqrt(M_PI) * S.factor;
+            out->self_ = selfEnergy; out->energy += selfEnergy; out->coulomb += selfEnergy;
+            out->virial += selfEnergy / 3.0;
+            h->new_valid = false;
+        } else {
+            const double ec = std::erfc(S.kappa * S.rc_lj);
+            out->wolf_const = (-(h->sum_q * h->sum_q) * ec / S.rc_lj -
+                               (ec / 2 / S.rc_lj + S.kappa / std::sqrt(M_PI)) * h->sum_q2) * S.factor;
+            out->energy += out->wolf_const; out->coulomb += out->wolf_const;
+        }
+    }
+    h->cnt.full_energy_evals++;
+    return MMC_OK;
+}
+
+int style_check(mmc_handle *h, int style)
+{
+    if (style == MMC_STYLE_LJ_ATOMS) {
+        if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
+        return MMC_OK;
+    }
+    if (style != MMC_STYLE_EWALD && style != MMC_STYLE_WOLF && style != MMC_STYLE_LJ_ONLY)
+        FAIL(MMC_EINVAL, "unknown style");
+    if (!h->has_system) FAIL(MMC_ESTATE, "no molecular system uploaded");
+    if ((style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF) && !h->has_ewald)
+        FAIL(MMC_ESTATE, "mmc_ewald_prepare has not been called");
+    return MMC_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int mmc_version(void) { return MMC_VERSION; }
+
+const char *mmc_last_error(const mmc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mmc_create(const mmc_config *cfg, mmc_handle **out)
+{
+    if (!cfg || !out) { g_create_error = "null argument"; return MMC_EINVAL; }
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) { g_create_error = "bad rank/world"; return MMC_EINVAL; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (libmmc_b200 has no CPU fallback)";
+        return MMC_ECUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return MMC_EINVAL; }
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return MMC_ECUDA; }
+    mmc_handle *h = new mmc_handle();
+    h->cfg = *cfg;
+    auto fail = [&](const char *what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete h;
+        return MMC_ECUDA;
+    };
+    if (cfg->stream) h->stream = (cudaStream_t)cfg->stream;
+    else {
+        if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+        h->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail("props", e);
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaHostAlloc(&h->h_out, sizeof(MoveOut), cudaHostAllocMapped)) != cudaSuccess) return fail("hostalloc", e);
+    std::memset(h->h_out, 0, sizeof(MoveOut));
+    if ((e = cudaHostGetDevicePointer((void **)&h->W.out, h->h_out, 0)) != cudaSuccess) return fail("mapped ptr", e);
+    const int max_blocks = 2 * h->sm_count + 64 + 1024;
+    if ((e = cudaMalloc(&h->W.partial, sizeof(double4) * max_blocks)) != cudaSuccess) return fail("malloc", e);
+    if ((e = cudaMalloc(&h->W.ticket, sizeof(unsigned))) != cudaSuccess) return fail("malloc", e);
+    if ((e = cudaMemset(h->W.ticket, 0, sizeof(unsigned))) != cudaSuccess) return fail("memset", e);
+    for (auto &ev : h->tm.ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("event", e);
+    cudaFuncSetAttribute(k_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_pairs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    *out = h;
+    return MMC_OK;
+}
+
+int mmc_destroy(mmc_handle *h)
+{
+    if (!h) return MMC_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    free_system(h); free_ewald(h); free_atoms(h);
+    dfree(h->W.partial); dfree(h->W.ticket);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    for (auto &ev : h->tm.ev) cudaEventDestroy(ev);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MMC_OK;
+}
+
+int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const double *coords,
+                      const double *charge, const int64_t *atype, const int64_t *first_atom,
+                      const int64_t *last_atom, const double *com, int32_t n_types, const double *eps,
+                      const double *sig, double box, double rc_lj, double rc_qq)
+{
+    if (!h) return MMC_EINVAL;
+    if (!coords || !charge || !atype || !first_atom || !last_atom || !com || !eps || !sig) FAIL(MMC_EINVAL, "null array");
+    if (n_mol < 1 || n_sites < n_mol || n_mol > (1 << 30) || n_sites > (1LL << 30)) FAIL(MMC_EINVAL, "bad sizes");
+    if (n_types < 1 || n_types > MMC_MAX_TYPES) FAIL(MMC_EINVAL, "n_types out of range (1..8)");
+    if (!(box > 0) || !(rc_lj > 0) || !(rc_qq > 0)) FAIL(MMC_EINVAL, "box and cutoffs must be positive");
+    CK(cudaSetDevice(h->cfg.device));
+    const bool had_ewald = h->has_ewald;
+    free_system(h);
+    std::vector<double4> hs(n_sites), hc(n_mol);
+    std::vector<int2> hm(n_mol);
+    std::vector<int> ht(n_sites);
+    int max_sites = 0;
+    bool uniform = true;
+    for (int64_t m = 0; m < n_mol; ++m) {
+        const int64_t f = first_atom[m], l = last_atom[m];
+        if (f < 1 || l < f || l > n_sites) FAIL(MMC_EINVAL, "first_atom/last_atom out of range");
+        const int cnt = (int)(l - f + 1);
+        if (cnt > MMC_MAX_SITES) FAIL(MMC_EINVAL, "more than 16 sites in a molecule");
+        hm[m] = make_int2((int)(f - 1), cnt);
+        max_sites = std::max(max_sites, cnt);
+        for (int k = 0; k < 3; ++k)
+            if (!(com[3 * m + k] >= 0.0 && com[3 * m + k] <= box))
+                FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
+        hc[m] = make_double4(com[3 * m], com[3 * m + 1], com[3 * m + 2], 0.0);
+    }
+    const int US = hm[0].y;
+    for (int64_t m = 0; m < n_mol && uniform; ++m) {
+        if (hm[m].y != US || hm[m].x != (int)(m * US)) uniform = false;
+    }
+    if ((int64_t)US * n_mol != n_sites) uniform = false;
+    for (int64_t s = 0; s < n_sites; ++s) {
+        if (atype[s] < 1 || atype[s] > n_types) FAIL(MMC_EINVAL, "atype out of range (1-based)");
+        ht[s] = (int)(atype[s] - 1);
+        hs[s] = make_double4(coords[3 * s], coords[3 * s + 1], coords[3 * s + 2], charge[s]);
+        if (uniform && ht[s] != ht[s % US]) uniform = false;
+    }
+    DevSystem &S = h->S;
+    DevSystem keep = S;
+    S = DevSystem{};
+    if (had_ewald) {   // k-space tables survive a re-upload of coordinates
+        S.kappa = keep.kappa; S.factor = keep.factor; S.nk = keep.nk; S.nkvecs = keep.nkvecs;
+        S.kvec = keep.kvec; S.cfac = keep.cfac; S.rhok[0] = keep.rhok[0]; S.rhok[1] = keep.rhok[1];
+    }
+    S.n_mol = (int)n_mol; S.n_sites = (int)n_sites; S.max_sites = max_sites; S.n_types = n_types;
+    S.box = box; S.rc_lj = rc_lj; S.rc_qq = rc_qq;
+    for (int a = 0; a < n_types * n_types; ++a) { S.eps[a] = eps[a]; S.sig[a] = sig[a]; }
+    CK(cudaMalloc(&S.site, sizeof(double4) * n_sites));
+    CK(cudaMalloc(&S.com, sizeof(double4) * n_mol));
+    CK(cudaMalloc(&S.mol, sizeof(int2) * n_mol));
+    CK(cudaMalloc(&S.atype, sizeof(int) * n_sites));
+    CK(cudaMemcpyAsync(S.site, hs.data(), sizeof(double4) * n_sites, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.com, hc.data(), sizeof(double4) * n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.mol, hm.data(), sizeof(int2) * n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.atype, ht.data(), sizeof(int) * n_sites, cudaMemcpyHostToDevice, h->stream));
+    // LJ-active site-type combinations of the uniform molecule (ε_ij > 0.001, energy.jl:270)
+    h->lj.clear();
+    if (uniform)
+        for (int a = 0; a < US; ++a)
+            for (int b = 0; b < US; ++b) {
+                const double e_ = eps[ht[a] + ht[b] * n_types];
+                if (e_ > 0.001) h->lj.push_back(LJActive{a, b, e_, sig[ht[a] + ht[b] * n_types]});
+            }
+    if (h->lj.size() > 64) uniform = false;
+    h->uniform = uniform; h->US = uniform ? US : 0;
+    if (uniform) {
+        std::vector<int2> um(n_mol);
+        for (int64_t m = 0; m < n_mol; ++m) um[m] = make_int2((int)(m * US), US);
+        CK(cudaMalloc(&h->d_mol_uniform, sizeof(int2) * n_mol));
+        CK(cudaMemcpyAsync(h->d_mol_uniform, um.data(), sizeof(int2) * n_mol, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMalloc(&h->d_lj, sizeof(LJActive) * std::max<size_t>(1, h->lj.size())));
+        if (!h->lj.empty())
+            CK(cudaMemcpyAsync(h->d_lj, h->lj.data(), sizeof(LJActive) * h->lj.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMalloc(&h->d_cell_of, sizeof(int) * n_mol));
+        CK(cudaMalloc(&h->d_perm, sizeof(int) * n_mol));
+        CK(cudaMalloc(&h->d_scom, sizeof(double4) * n_mol));
+        CK(cudaMalloc(&h->d_ssite, sizeof(double4) * n_sites));
+        h->pair_grid = 2 * h->sm_count;
+        CK(cudaMalloc(&h->d_pair_partial, sizeof(double4) * h->pair_grid));
+        CK(cudaMalloc(&h->d_ovl, sizeof(unsigned) * n_mol));
+        CK(cudaMalloc(&h->d_novl, sizeof(unsigned)));
+        CK(cudaMalloc(&h->d_maxdev, sizeof(double)));
+        h->ncell_cap = 0;
+    }
+    CK(cudaMalloc(&h->d_qsums, 2 * sizeof(double)));
+    k_charge_sums<<<1, 256, 0, h->stream>>>(S.site, (int)n_sites, h->d_qsums);
+    LAUNCH_CHECK();
+    double qs[2];
+    CK(cudaMemcpyAsync(qs, h->d_qsums, sizeof(qs), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->sum_q = qs[0]; h->sum_q2 = qs[1];
+    h->rhok_grid_cap = 0;
+    h->h_mol = hm;
+    h->has_system = true;
+    h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
+    return MMC_OK;
+}
+
+int mmc_upload_atoms(mmc_handle *h, int64_t n, const double *r, const double *eps_j, const double *sig_j,
+                     double box, double r_cut)
+{
+    if (!h) return MMC_EINVAL;
+    if (!r || !eps_j || !sig_j || n < 1 || n > (1 << 30)) FAIL(MMC_EINVAL, "bad arguments");
+    if (!(box > 0) || !(r_cut > 0)) FAIL(MMC_EINVAL, "box and cutoff must be positive");
+    CK(cudaSetDevice(h->cfg.device));
+    free_atoms(h);
+    std::vector<double4> hr(n);
+    std::vector<double2> he(n);
+    for (int64_t i = 0; i < n; ++i) {
+        hr[i] = make_double4(r[3 * i], r[3 * i + 1], r[3 * i + 2], 0.0);
+        he[i] = make_double2(eps_j[i], sig_j[i]);
+    }
+    h->At.n = (int)n; h->At.box = box; h->At.rc = r_cut;
+    CK(cudaMalloc(&h->At.r, sizeof(double4) * n));
+    CK(cudaMalloc(&h->At.es, sizeof(double2) * n));
+    CK(cudaMalloc(&h->d_rows, sizeof(double2) * n));
+    CK(cudaMalloc(&h->d_atoms_out, 2 * sizeof(double)));
+    CK(cudaMemcpyAsync(h->At.r, hr.data(), sizeof(double4) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->At.es, he.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_atoms = true;
+    h->trial_pending = false;
+    return MMC_OK;
+}
+
+int mmc_download_system(mmc_handle *h, double *coords, double *com)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_system) FAIL(MMC_ESTATE, "no molecular system uploaded");
+    std::vector<double4> hs(h->S.n_sites), hc(h->S.n_mol);
+    CK(cudaMemcpyAsync(hs.data(), h->S.site, sizeof(double4) * hs.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hc.data(), h->S.com, sizeof(double4) * hc.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (coords) for (size_t s = 0; s < hs.size(); ++s) { coords[3 * s] = hs[s].x; coords[3 * s + 1] = hs[s].y; coords[3 * s + 2] = hs[s].z; }
+    if (com) for (size_t m = 0; m < hc.size(); ++m) { com[3 * m] = hc[m].x; com[3 * m + 1] = hc[m].y; com[3 * m + 2] = hc[m].z; }
+    return MMC_OK;
+}
+
+int mmc_download_atoms(mmc_handle *h, double *r)
+{
+    if (!h || !r) return MMC_EINVAL;
+    if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
+    std::vector<double4> hr(h->At.n);
+    CK(cudaMemcpyAsync(hr.data(), h->At.r, sizeof(double4) * hr.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < hr.size(); ++i) { r[3 * i] = hr[i].x; r[3 * i + 1] = hr[i].y; r[3 * i + 2] = hr[i].z; }
+    return MMC_OK;
+}
+
+int mmc_ewald_prepare(mmc_handle *h, double kappa, int32_t nk, int32_t k_sq_max, double factor, int32_t *nkvecs)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_system) FAIL(MMC_ESTATE, "upload the system before mmc_ewald_prepare (cfac depends on the box)");
+    if (!(kappa > 0) || nk < 1 || nk > MMC_MAX_NK || k_sq_max < 2) FAIL(MMC_EINVAL, "bad Ewald parameters (1 <= nk <= 8)");
+    CK(cudaSetDevice(h->cfg.device));
+    free_ewald(h);
+    fill_kvectors(nk, k_sq_max, h->kxyz);
+    const int n = (int)(h->kxyz.size() / 3);
+    if (n < 1) FAIL(MMC_EINVAL, "no k-vectors inside k_sq_max");
+    fill_cfac(h->kxyz, kappa, h->S.box, h->cfac);
+    std::vector<int4> kv(n);
+    for (int i = 0; i < n; ++i) kv[i] = make_int4(h->kxyz[3 * i], h->kxyz[3 * i + 1], h->kxyz[3 * i + 2], 0);
+    DevSystem &S = h->S;
+    S.kappa = kappa; S.factor = factor; S.nk = nk; S.nkvecs = n;
+    h->k_sq_max = k_sq_max;
+    CK(cudaMalloc(&S.kvec, sizeof(int4) * n));
+    CK(cudaMalloc(&S.cfac, sizeof(double) * n));
+    CK(cudaMalloc(&h->d_cfac_trial, sizeof(double) * n));
+    CK(cudaMalloc(&S.rhok[0], sizeof(double2) * n));
+    CK(cudaMalloc(&S.rhok[1], sizeof(double2) * n));
+    CK(cudaMalloc(&h->d_rhok_trial, sizeof(double2) * n));
+    CK(cudaMemcpyAsync(S.kvec, kv.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.cfac, h->cfac.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(S.rhok[0], 0, sizeof(double2) * n, h->stream));   // zeros(ComplexF64, NKVECS), ewalds.jl:98-99
+    CK(cudaMemsetAsync(S.rhok[1], 0, sizeof(double2) * n, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->cur = 0; h->new_valid = false; h->rhok_grid_cap = 0; dfree(h->d_rhok_partial);
+    h->has_ewald = true;
+    int rc = ensure_vec(h);
+    if (rc) return rc;
+    if (nkvecs) *nkvecs = n;
+    return MMC_OK;
+}
+
+int mmc_get_kvectors(mmc_handle *h, int32_t *kxyz, double *cfac)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_ewald) FAIL(MMC_ESTATE, "mmc_ewald_prepare has not been called");
+    if (kxyz) std::memcpy(kxyz, h->kxyz.data(), sizeof(int32_t) * h->kxyz.size());
+    if (cfac) CK(cudaMemcpy(cfac, h->S.cfac, sizeof(double) * h->S.nkvecs, cudaMemcpyDeviceToHost));
+    return MMC_OK;
+}
+
+int mmc_get_rhok(mmc_handle *h, double *sum_old, double *sum_new)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_ewald) FAIL(MMC_ESTATE, "mmc_ewald_prepare has not been called");
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t bytes = sizeof(double2) * h->S.nkvecs;
+    if (sum_old) CK(cudaMemcpy(sum_old, h->S.rhok[h->cur], bytes, cudaMemcpyDeviceToHost));
+    if (sum_new) CK(cudaMemcpy(sum_new, h->S.rhok[h->new_valid ? (h->cur ^ 1) : h->cur], bytes, cudaMemcpyDeviceToHost));
+    return MMC_OK;
+}
+
+int mmc_lj_mol(mmc_handle *h, int64_t i, double *pot, double *vir)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = check_mol_index(h, i);
+    if (rc) return rc;
+    MoveArgs A{};
+    A.i = (int)(i - 1); A.n_cfg = 1; A.tiles = move_tiles(h); A.want_lj = 1; A.cur = h->cur;
+    if ((rc = launch_move(h, A))) return rc;
+    if (pot) *pot = h->h_out->lj_pot[0];
+    if (vir) *vir = h->h_out->lj_vir[0];
+    return MMC_OK;
+}
+
+int mmc_ewald_real(mmc_handle *h, int64_t i, double *pot, int32_t *overlap)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = check_mol_index(h, i);
+    if (rc) return rc;
+    if (!h->has_ewald) FAIL(MMC_ESTATE, "mmc_ewald_prepare has not been called");
+    MoveArgs A{};
+    A.i = (int)(i - 1); A.n_cfg = 1; A.tiles = move_tiles(h); A.want_qq = 1; A.cur = h->cur;
+    if ((rc = launch_move(h, A))) return rc;
+    if (pot) *pot = h->h_out->qq[0];
+    if (overlap) *overlap = h->h_out->overlap[0];
+    return MMC_OK;
+}
+
+int mmc_ewald_short(mmc_handle *h, int64_t i, double *e, double *v, int32_t *overlap)
+{
+    double pot = 0.0;
+    int rc = mmc_ewald_real(h, i, &pot, overlap);
+    if (rc) return rc;
+    const double realEwald = pot * h->S.factor;      // ewalds.jl:905-907
+    if (e) *e = realEwald;
+    if (v) *v = realEwald / 3;
+    return MMC_OK;
+}
+
+int mmc_set_molecule(mmc_handle *h, int64_t i, const double com[3], const double *sites)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = check_mol_index(h, i);
+    if (rc) return rc;
+    if (!com || !sites) FAIL(MMC_EINVAL, "null array");
+    MoveArgs A{};
+    A.i = (int)(i - 1);
+    std::memcpy(A.site_new, sites, sizeof(double) * 3 * h->h_mol[i - 1].y);
+    k_set_molecule<<<1, 32, 0, h->stream>>>(h->S, A.i, com[0], com[1], com[2], A);
+    LAUNCH_CHECK();
+    h->trial_pending = false;
+    return MMC_OK;
+}
+
+int mmc_recip_long(mmc_handle *h, double *energy)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_system || !h->has_ewald) FAIL(MMC_ESTATE, "system and Ewald tables required");
+    int rc = rhok_launch(h, h->S.site, 0, h->S.n_sites, h->S.box, reinterpret_cast<double2 *>(h->d_vec + MMC_NSCAL));
+    if (rc) return rc;
+    k_rhok_energy<<<1, RHOKE_BLOCK, 0, h->stream>>>(reinterpret_cast<const double2 *>(h->d_vec + MMC_NSCAL),
+                                                   h->S.cfac, h->S.nkvecs, h->S.rhok[0], h->S.rhok[1], h->d_vec + 4);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(h->h_vec, h->d_vec, MMC_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->new_valid = false;
+    if (energy) *energy = h->h_vec[4];
+    return MMC_OK;
+}
+
+int mmc_recip_move(mmc_handle *h, const double *r_old, const double *r_new, const double *q, int32_t n, double *dE)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_system || !h->has_ewald) FAIL(MMC_ESTATE, "system and Ewald tables required");
+    if (!r_old || !r_new || !q || n < 1 || n > MMC_MAX_SITES) FAIL(MMC_EINVAL, "bad arguments (1 <= n <= 16)");
+    MoveArgs A{};
+    A.i = 0; A.n_cfg = 0; A.tiles = 0; A.cur = h->cur;
+    A.recip_blocks = (h->S.nkvecs + MOVE_BLOCK - 1) / MOVE_BLOCK;
+    A.recip_ns = n; A.recip_from_args = 1;
+    std::memcpy(A.site_new, r_new, sizeof(double) * 3 * n);
+    std::memcpy(A.site_old, r_old, sizeof(double) * 3 * n);
+    std::memcpy(A.q, q, sizeof(double) * n);
+    int rc = launch_move(h, A);
+    if (rc) return rc;
+    h->new_valid = true;
+    if (dE) *dE = h->h_out->d_recip;
+    return MMC_OK;
+}
+
+int mmc_recip_commit(mmc_handle *h)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_ewald) FAIL(MMC_ESTATE, "mmc_ewald_prepare has not been called");
+    if (h->new_valid) { h->cur ^= 1; h->new_valid = false; h->cnt.commits++; }
+    return MMC_OK;
+}
+
+int mmc_recip_rollback(mmc_handle *h)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_ewald) FAIL(MMC_ESTATE, "mmc_ewald_prepare has not been called");
+    h->new_valid = false;
+    return MMC_OK;
+}
+
+int mmc_ewald_self(mmc_handle *h, double *energy)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_system || !h->has_ewald) FAIL(MMC_ESTATE, "system and Ewald tables required");
+    if (energy) *energy = -h->S.kappa * h->sum_q2 / std::sqrt(M_PI) * h->S.factor;   // Σq² reduced on the device at upload
+    return MMC_OK;
+}
+
+int mmc_lj_atom(mmc_handle *h, int64_t i, double *pot, double *vir)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
+    if (i < 1 || i > h->At.n) FAIL(MMC_EINVAL, "atom index out of range (1-based)");
+    AtomArgs A{};
+    A.i = (int)(i - 1); A.n_cfg = 1;
+    A.blocks = std::max(1, std::min((h->At.n + ATOM_BLOCK - 1) / ATOM_BLOCK, 2 * h->sm_count));
+    A.seq = ++h->seq;
+    k_move_atom<<<A.blocks, ATOM_BLOCK, 0, h->stream>>>(h->At, A, h->W);
+    LAUNCH_CHECK();
+    int rc = wait_out(h);
+    if (rc) return rc;
+    if (pot) *pot = h->h_out->lj_pot[0];
+    if (vir) *vir = h->h_out->lj_vir[0];
+    return MMC_OK;
+}
+
+int mmc_set_atom(mmc_handle *h, int64_t i, const double r[3])
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
+    if (i < 1 || i > h->At.n || !r) FAIL(MMC_EINVAL, "bad arguments");
+    k_set_atom<<<1, 1, 0, h->stream>>>(h->At, (int)(i - 1), r[0], r[1], r[2]);
+    LAUNCH_CHECK();
+    h->trial_pending = false;
+    return MMC_OK;
+}
+
+int mmc_partial_count(mmc_handle *h, int64_t *n_doubles)
+{
+    if (!h || !n_doubles) return MMC_EINVAL;
+    *n_doubles = MMC_NSCAL + 2 * (int64_t)std::max(h->S.nkvecs, 1);
+    return MMC_OK;
+}
+
+int mmc_potential_partial(mmc_handle *h, int32_t style, double *d_partials)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = style_check(h, style);
+    if (rc) return rc;
+    if (style == MMC_STYLE_LJ_ATOMS || !d_partials) FAIL(MMC_EINVAL, "sharded evaluation is for molecular systems");
+    if (!h->uniform) FAIL(MMC_EINVAL, "sharded evaluation needs a uniform topology");
+    if ((rc = ensure_vec(h))) return rc;
+    EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
+    return eval_partials(h, style, E, d_partials);
+}
+
+int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partials, mmc_properties *out)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = style_check(h, style);
+    if (rc) return rc;
+    if (!d_partials || !out) FAIL(MMC_EINVAL, "null argument");
+    EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
+    rc = finalize(h, style, E, const_cast<double *>(d_partials), h->S.rhok[0], h->S.rhok[1], out);
+    if (style == MMC_STYLE_EWALD) h->new_valid = false;
+    return rc;
+}
+
+int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = style_check(h, style);
+    if (rc) return rc;
+    if (!out) FAIL(MMC_EINVAL, "null argument");
+    if (style == MMC_STYLE_LJ_ATOMS) {
+        k_atoms_rows<<<std::min(h->At.n, 8 * h->sm_count), 256, 0, h->stream>>>(h->At, h->d_rows); LAUNCH_CHECK();
+        k_rows_sum<<<1, 256, 0, h->stream>>>(h->d_rows, h->At.n, h->d_atoms_out); LAUNCH_CHECK();
+        double r[2];
+        CK(cudaMemcpyAsync(r, h->d_atoms_out, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        std::memset(out, 0, sizeof(*out));
+        out->energy = r[0]; out->lj = r[0]; out->virial = r[1];
+        h->cnt.full_energy_evals++;
+        return MMC_OK;
+    }
+    if (!h->uniform) return potential_rows(h, style, out);
+    if ((rc = ensure_vec(h))) return rc;
+    EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, 0, 1};
+    if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+    rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
+    if (style == MMC_STYLE_EWALD) h->new_valid = false;
+    return rc;
+}
+
+int mmc_trial_move(mmc_handle *h, int64_t i, const double com_new[3], const double *sites_new, int32_t style,
+                   mmc_trial_result *out)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = check_mol_index(h, i);
+    if (rc) return rc;
+    if ((rc = style_check(h, style))) return rc;
+    if (style == MMC_STYLE_LJ_ATOMS || !com_new || !sites_new || !out) FAIL(MMC_EINVAL, "bad arguments");
+    MoveArgs &A = h->last;
+    A = MoveArgs{};
+    A.i = (int)(i - 1); A.n_cfg = 2; A.tiles = move_tiles(h);
+    A.want_lj = 1; A.want_qq = (style != MMC_STYLE_LJ_ONLY);
+    A.recip_blocks = (style == MMC_STYLE_EWALD) ? (h->S.nkvecs + MOVE_BLOCK - 1) / MOVE_BLOCK : 0;
+    A.cur = h->cur;
+    A.com_new[0] = com_new[0]; A.com_new[1] = com_new[1]; A.com_new[2] = com_new[2];
+    std::memcpy(A.site_new, sites_new, sizeof(double) * 3 * h->h_mol[i - 1].y);
+    if ((rc = launch_move(h, A))) return rc;
+    const MoveOut &o = *h->h_out;
+    const double factor = h->S.factor;
+    out->lj_old = o.lj_pot[0]; out->lj_vir_old = o.lj_vir[0];
+    out->lj_new = o.lj_pot[1]; out->lj_vir_new = o.lj_vir[1];
+    out->qq_old = o.qq[0] * factor; out->qq_vir_old = out->qq_old / 3;     // ewalds.jl:905-907
+    out->qq_new = o.qq[1] * factor; out->qq_vir_new = out->qq_new / 3;
+    out->d_recip = o.d_recip;
+    out->overlap_old = o.overlap[0]; out->overlap_new = o.overlap[1];
+    h->last_overlap = o.overlap[0] || o.overlap[1];
+    h->trial_pending = true; h->trial_kind = 1; h->trial_style = style;
+    h->new_valid = (style == MMC_STYLE_EWALD) && !h->last_overlap;
+    h->cnt.trial_moves++;
+    if (h->last_overlap) h->cnt.overlap_events++;
+    return MMC_OK;
+}
+
+int mmc_trial_atom(mmc_handle *h, int64_t i, const double r_new[3], mmc_trial_result *out)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
+    if (i < 1 || i > h->At.n || !r_new || !out) FAIL(MMC_EINVAL, "bad arguments");
+    AtomArgs &A = h->last_atom;
+    A = AtomArgs{};
+    A.i = (int)(i - 1); A.n_cfg = 2;
+    A.blocks = std::max(1, std::min((h->At.n + ATOM_BLOCK - 1) / ATOM_BLOCK, 2 * h->sm_count));
+    A.r_new[0] = r_new[0]; A.r_new[1] = r_new[1]; A.r_new[2] = r_new[2];
+    A.seq = ++h->seq;
+    k_move_atom<<<A.blocks, ATOM_BLOCK, 0, h->stream>>>(h->At, A, h->W);
+    LAUNCH_CHECK();
+    int rc = wait_out(h);
+    if (rc) return rc;
+    std::memset(out, 0, sizeof(*out));
+    out->lj_old = h->h_out->lj_pot[0]; out->lj_vir_old = h->h_out->lj_vir[0];
+    out->lj_new = h->h_out->lj_pot[1]; out->lj_vir_new = h->h_out->lj_vir[1];
+    h->trial_pending = true; h->trial_kind = 2;
+    h->cnt.trial_moves++;
+    return MMC_OK;
+}
+
+int mmc_accept(mmc_handle *h)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->trial_pending) FAIL(MMC_ESTATE, "mmc_accept without a pending trial move");
+    if (h->trial_kind == 1) {
+        const MoveArgs &A = h->last;
+        k_set_molecule<<<1, 32, 0, h->stream>>>(h->S, A.i, A.com_new[0], A.com_new[1], A.com_new[2], A);
+        LAUNCH_CHECK();
+        if (h->trial_style == MMC_STYLE_EWALD && !h->last_overlap) h->cur ^= 1;   // main.jl:621 as a pointer swap
+    } else {
+        const AtomArgs &A = h->last_atom;
+        k_set_atom<<<1, 1, 0, h->stream>>>(h->At, A.i, A.r_new[0], A.r_new[1], A.r_new[2]);
+        LAUNCH_CHECK();
+    }
+    h->trial_pending = false; h->new_valid = false;
+    h->cnt.commits++;
+    return MMC_OK;
+}
+
+int mmc_reject(mmc_handle *h)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->trial_pending) FAIL(MMC_ESTATE, "mmc_reject without a pending trial move");
+    h->trial_pending = false; h->new_valid = false;    // main.jl:623-628: resident state was never touched
+    return MMC_OK;
+}
+
+int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t style, mmc_properties *out)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = style_check(h, style);
+    if (rc) return rc;
+    if (style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "volume trial is implemented for molecular systems");
+    if (!out || !(box_new > 0)) FAIL(MMC_EINVAL, "bad arguments");
+    if (!h->uniform) FAIL(MMC_EINVAL, "volume trial needs a uniform topology");
+    if ((rc = ensure_vec(h))) return rc;
+    const bool coul = (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF);
+    if (coul && !(kappa_new > 0)) FAIL(MMC_EINVAL, "kappa_new must be positive");
+    if (style == MMC_STYLE_EWALD) {
+        fill_cfac(h->kxyz, kappa_new, box_new, h->cfac_trial);          // PrepareEwaldVariables at L'
+        CK(cudaMemcpyAsync(h->d_cfac_trial, h->cfac_trial.data(), sizeof(double) * h->S.nkvecs,
+                           cudaMemcpyHostToDevice, h->stream));
+    }
+    const double f = box_new / h->S.box;                                 // volumeChange.jl:62
+    EvalCtx E{f, box_new, coul ? kappa_new : h->S.kappa, h->d_cfac_trial, 0, 1};
+    if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+    if ((rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out))) return rc;
+    h->vol_pending = true; h->vol_box = box_new; h->vol_kappa = E.kappa; h->vol_f = f; h->vol_style = style;
+    return MMC_OK;
+}
+
+int mmc_volume_accept(mmc_handle *h)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->vol_pending) FAIL(MMC_ESTATE, "mmc_volume_accept without a pending volume trial");
+    k_apply_scale<<<(h->S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->S, h->vol_f);
+    LAUNCH_CHECK();
+    h->S.box = h->vol_box;
+    if (h->vol_style == MMC_STYLE_EWALD || h->vol_style == MMC_STYLE_WOLF) h->S.kappa = h->vol_kappa;
+    if (h->vol_style == MMC_STYLE_EWALD) {
+        std::swap(h->S.cfac, h->d_cfac_trial);
+        h->cfac.swap(h->cfac_trial);
+        std::swap(h->S.rhok[h->cur], h->d_rhok_trial);
+    } else if (h->has_ewald) {
+        fill_cfac(h->kxyz, h->S.kappa, h->S.box, h->cfac);
+        CK(cudaMemcpyAsync(h->S.cfac, h->cfac.data(), sizeof(double) * h->S.nkvecs, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->vol_pending = false; h->new_valid = false; h->trial_pending = false;
+    h->cnt.commits++;
+    return MMC_OK;
+}
+
+int mmc_volume_reject(mmc_handle *h)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->vol_pending) FAIL(MMC_ESTATE, "mmc_volume_reject without a pending volume trial");
+    h->vol_pending = false;
+    return MMC_OK;
+}
+
+int mmc_get_counters(mmc_handle *h, mmc_counters *out)
+{
+    if (!h || !out) return MMC_EINVAL;
+    *out = h->cnt;
+    return MMC_OK;
+}
+
+int mmc_set_timing(mmc_handle *h, int32_t enabled)
+{
+    if (!h) return MMC_EINVAL;
+    h->tm.on = enabled != 0;
+    return MMC_OK;
+}
+
+int mmc_last_timings(mmc_handle *h, float *ms4)
+{
+    if (!h || !ms4) return MMC_EINVAL;
+    for (int i = 0; i < 4; ++i) ms4[i] = h->tm.ms[i];
+    return MMC_OK;
+}
+
+int mmc_measure_fp64_peak(mmc_handle *h, double *tflops)
+{
+    if (!h || !tflops) return MMC_EINVAL;
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double)));
+    const int blocks = h->sm_count * 8, iters = 16384;
+    k_dfma_probe<<<blocks, 256, 0, h->stream>>>(d, 256);   // warm-up
+    LAUNCH_CHECK();
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(h->tm.ev[0], h->stream);
+        k_dfma_probe<<<blocks, 256, 0, h->stream>>>(d, iters);
+        LAUNCH_CHECK();
+        cudaEventRecord(h->tm.ev[1], h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->tm.ev[0], h->tm.ev[1]);
+        best = std::min(best, ms);
+    }
+    cudaFree(d);
+    const double flop = 2.0 * 8.0 * (double)iters * 256.0 * blocks;
+    *tflops = flop / (best * 1e-3) / 1e12;
+    return MMC_OK;
+}
+
+}  // extern "C"
+
+#include "mmc_driver.inl"

@@ -1,0 +1,207 @@
+// mmc_driver.inl — host-side stand-in for the Julia move loop, built ON TOP of the C ABI.
+//
+// The north star keeps Loop() (Ewald/main.jl:460-696) in Julia; Julia is not installed where this
+// library is built and tested, so this file plays Julia's part in C++: it generates the trial
+// moves exactly as the reference does, calls mmc_trial_move / mmc_accept / mmc_reject once per
+// move (one kernel launch + one host wait each, what a ccall-driven loop would pay) and applies
+// the Metropolis rule.  Random numbers come from a caller-supplied stream of uniforms consumed
+// in the reference's draw order, so a recorded Julia stream reproduces the
+// reference trajectory.  All energies come from the CUDA kernels; nothing here evaluates one.
+
+namespace {
+
+struct UStream {
+    const double *u; int64_t n, pos; bool dry;
+    double next() { if (pos >= n) { dry = true; return 0.5; } return u[pos++]; }
+};
+
+// Ewald/boundaries.jl:16-26
+inline void pbc3(double v[3], double box)
+{
+    for (int k = 0; k < 3; ++k) {
+        if (v[k] > box) v[k] -= box;
+        if (v[k] < 0) v[k] += box;
+    }
+}
+
+// Ewald/auxillary.jl:106-114 — a uniform is drawn only when delta >= 0
+inline bool metropolis(double delta, UStream &us)
+{
+    if (delta < 0.0) return true;
+    return std::exp(-delta) > us.next();
+}
+
+// Ewald/adjust.jl:1-83 (Adjust! and Adjust_rot! share one body)
+struct MoveStat { int64_t naccepp = 0, naccept = 0, attempp = 0, attempt = 0; double set_value = 0.5, d_max = 0; };
+inline void adjust_step(MoveStat &m, double L)
+{
+    if (m.attempp == 0) { m.naccepp = m.naccept; m.attempp = m.attempt; return; }
+    const double ratio = double(m.naccept - m.naccepp) / double(m.attempt - m.attempp);
+    const double old = m.d_max;
+    m.d_max = m.d_max * ratio / m.set_value;
+    const double r = m.d_max / old;
+    if (r > 1.5) m.d_max = old * 1.5;
+    if (r < 0.5) m.d_max = old * 0.5;
+    if (m.d_max > L / 2) m.d_max = L / 2;
+    m.naccepp = m.naccept; m.attempp = m.attempt;
+}
+
+// Ewald/quaternions.jl:37-50 — rows as written in the reference, [2,3] = 2(q2 q4 + q1 q2)
+inline void quat_to_matrix(const double q[4], double a[3][3])
+{
+    const double q1 = q[0], q2 = q[1], q3 = q[2], q4 = q[3];
+    a[0][0] = q1 * q1 + q2 * q2 - q3 * q3 - q4 * q4; a[0][1] = 2 * (q2 * q3 + q1 * q4); a[0][2] = 2 * (q2 * q4 - q1 * q3);
+    a[1][0] = 2 * (q2 * q3 - q1 * q4); a[1][1] = q1 * q1 - q2 * q2 + q3 * q3 - q4 * q4; a[1][2] = 2 * (q2 * q4 + q1 * q2);
+    a[2][0] = 2 * (q2 * q4 + q1 * q3); a[2][1] = 2 * (q3 * q4 - q1 * q2); a[2][2] = q1 * q1 - q2 * q2 - q3 * q3 + q4 * q4;
+}
+
+}  // namespace
+
+extern "C" int mmc_loop_run(mmc_handle *h, const mmc_loop_params *p, double *com, double *quat, const double *db,
+                            const double *uniforms, int64_t n_uniforms, int64_t n_moves, double e0, double v0,
+                            uint8_t *accepted, double *delta_out, mmc_loop_stats *st)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_system) FAIL(MMC_ESTATE, "no molecular system uploaded");
+    if (!p || !com || !quat || !db || !uniforms || !st) FAIL(MMC_EINVAL, "null argument");
+    int rc = style_check(h, p->style);
+    if (rc) return rc;
+    const double box = h->S.box;
+    if (!(h->S.rc_lj < box / 2)) FAIL(MMC_EINVAL, "r_cut must be < box/2 (Ewald/main.jl:483)");
+    UStream us{uniforms, n_uniforms, 0, false};
+    MoveStat tr, ro;
+    tr.d_max = p->dr_max; ro.d_max = p->dphi_max;
+    double dr_max = p->dr_max, dphi_max = p->dphi_max;
+    std::memset(st, 0, sizeof(*st));
+    st->total_energy = e0; st->total_virial = v0;
+    const int n_mol = h->S.n_mol;
+    double sites[3 * MMC_MAX_SITES];
+    int ret = 0;
+    for (int64_t m = 0; m < n_moves; ++m) {
+        const int i = (int)(m % n_mol);                  // sweep order i = 1..N (main.jl:490)
+        const int2 mi = h->h_mol[i];
+        double rnew[3] = {com[3 * i], com[3 * i + 1], com[3 * i + 2]};
+        double ei[4];
+        const double chose_move = us.next();             // main.jl:516
+        bool is_trans;
+        if (chose_move < p->p_trans) {                   // main.jl:519-529, auxillary.jl:94-103
+            is_trans = true;
+            tr.attempt += 1;
+            const double z0 = us.next(), z1 = us.next(), z2 = us.next();
+            rnew[0] = rnew[0] + (z0 - 0.5) * dr_max;
+            rnew[1] = rnew[1] + (z1 - 0.5) * dr_max;
+            rnew[2] = rnew[2] + (z2 - 0.5) * dr_max;
+            pbc3(rnew, box);
+            std::memcpy(ei, quat + 4 * i, sizeof(ei));
+        } else if (chose_move <= p->p_rot) {             // main.jl:530-538, quaternions.jl:52-73,94-120,158-182
+            is_trans = false;
+            ro.attempt += 1;
+            const double *old = quat + 4 * i;
+            if (std::fabs(old[0] * old[0] + old[1] * old[1] + old[2] * old[2] + old[3] * old[3] - 1.0) > 1.e-6) { ret = 2; break; }
+            double ax[3], nrm;
+            for (;;) {
+                ax[0] = 2.0 * us.next() - 1.0; ax[1] = 2.0 * us.next() - 1.0; ax[2] = 2.0 * us.next() - 1.0;
+                nrm = ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2];
+                if (nrm < 1.0 || us.dry) break;
+            }
+            const double sn = std::sqrt(nrm);
+            ax[0] = ax[0] / sn; ax[1] = ax[1] / sn; ax[2] = ax[2] / sn;
+            const double zeta = us.next();
+            const double angle = (2.0 * zeta - 1.0) * dphi_max;
+            const double rq[4] = {std::cos(0.5 * angle), std::sin(0.5 * angle) * ax[0], std::sin(0.5 * angle) * ax[1],
+                                  std::sin(0.5 * angle) * ax[2]};
+            ei[0] = rq[0] * old[0] - rq[1] * old[1] - rq[2] * old[2] - rq[3] * old[3];   // quatmul(rot, old)
+            ei[1] = rq[1] * old[0] + rq[0] * old[1] - rq[3] * old[2] + rq[2] * old[3];
+            ei[2] = rq[2] * old[0] + rq[3] * old[1] + rq[0] * old[2] - rq[1] * old[3];
+            ei[3] = rq[3] * old[0] - rq[2] * old[1] + rq[1] * old[2] + rq[0] * old[3];
+        } else { ret = 3; break; }                       // main.jl:539-541
+        if (std::fabs(ei[0] * ei[0] + ei[1] * ei[1] + ei[2] * ei[2] + ei[3] * ei[3] - 1.0) > 1.e-6) { ret = 2; break; }
+        double a[3][3];
+        quat_to_matrix(ei, a);
+        for (int s = 0; s < mi.y; ++s) {                 // main.jl:545-548: COM + MATMUL(ai, db)
+            const double *d = db + 3 * (mi.x + s);
+            for (int c = 0; c < 3; ++c)
+                sites[3 * s + c] = rnew[c] + (d[0] * a[0][c] + d[1] * a[1][c] + d[2] * a[2][c]);
+        }
+        mmc_trial_result r;
+        if ((rc = mmc_trial_move(h, i + 1, rnew, sites, p->style, &r))) return rc;
+        double partial_old_e = r.lj_old, partial_old_v = r.lj_vir_old;
+        double partial_new_e = r.lj_new, partial_new_v = r.lj_vir_new;
+        if (p->style != MMC_STYLE_LJ_ONLY) {             // main.jl:501-505, 566-570
+            partial_old_v += r.qq_vir_old; partial_old_e += r.qq_old;
+            partial_new_v += r.qq_vir_new; partial_new_e += r.qq_new;
+        }
+        const bool overlap = r.overlap_old || r.overlap_new;
+        const double deltaRecip = r.d_recip;             // already 0 on overlap / non-Ewald
+        const double delta = (partial_new_e) - (partial_old_e) + deltaRecip;   // main.jl:593
+        if (overlap) st->n_overlap += 1;
+        const bool acc = metropolis(delta / p->temperature, us) && !overlap;   // main.jl:598
+        if (acc) {
+            st->total_energy += delta;
+            st->total_virial += (partial_new_v - partial_old_v) + deltaRecip / 3;
+            st->n_accepted += 1;
+            if (is_trans) tr.naccept += 1; else ro.naccept += 1;
+            com[3 * i] = rnew[0]; com[3 * i + 1] = rnew[1]; com[3 * i + 2] = rnew[2];
+            std::memcpy(quat + 4 * i, ei, sizeof(ei));
+            if ((rc = mmc_accept(h))) return rc;
+        } else {
+            if ((rc = mmc_reject(h))) return rc;
+        }
+        if (accepted) accepted[m] = acc ? 1 : 0;
+        if (delta_out) delta_out[m] = delta;
+        if (us.dry) { ret = 1; break; }
+        if (p->adjust && i == n_mol - 1) {               // main.jl:645-651
+            tr.d_max = dr_max; adjust_step(tr, box); dr_max = tr.d_max;
+            ro.d_max = dphi_max; adjust_step(ro, box); dphi_max = ro.d_max;
+        }
+        st->n_moves = m + 1;
+    }
+    st->uniforms_used = us.pos;
+    st->trans_attempt = tr.attempt; st->trans_accept = tr.naccept;
+    st->rot_attempt = ro.attempt; st->rot_accept = ro.naccept;
+    st->dr_max = dr_max; st->dphi_max = dphi_max;
+    return ret;
+}
+
+extern "C" int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_max, double *r,
+                                  const double *uniforms, int64_t n_uniforms, int64_t n_moves, double e0, double v0,
+                                  uint8_t *accepted, double *delta_out, mmc_loop_stats *st)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
+    if (!r || !uniforms || !st) FAIL(MMC_EINVAL, "null argument");
+    UStream us{uniforms, n_uniforms, 0, false};
+    std::memset(st, 0, sizeof(*st));
+    st->total_energy = e0; st->total_virial = v0;
+    const int n = h->At.n;
+    const double box = h->At.box;
+    int ret = 0, rc;
+    for (int64_t m = 0; m < n_moves; ++m) {              // Monatomic/mainMonatomic.jl:373-413
+        const int i = (int)(m % n);
+        double rnew[3];
+        const double z0 = us.next(), z1 = us.next(), z2 = us.next();
+        rnew[0] = r[3 * i] + (z0 - 0.5) * dr_max;
+        rnew[1] = r[3 * i + 1] + (z1 - 0.5) * dr_max;
+        rnew[2] = r[3 * i + 2] + (z2 - 0.5) * dr_max;
+        pbc3(rnew, box);
+        mmc_trial_result t;
+        if ((rc = mmc_trial_atom(h, i + 1, rnew, &t))) return rc;
+        const double delta = t.lj_new - t.lj_old;
+        const bool acc = metropolis(delta / temperature, us);
+        if (acc) {
+            st->total_energy += delta;
+            st->total_virial += (t.lj_vir_new - t.lj_vir_old);
+            st->n_accepted += 1;
+            r[3 * i] = rnew[0]; r[3 * i + 1] = rnew[1]; r[3 * i + 2] = rnew[2];
+            if ((rc = mmc_accept(h))) return rc;
+        } else if ((rc = mmc_reject(h))) return rc;
+        if (accepted) accepted[m] = acc ? 1 : 0;
+        if (delta_out) delta_out[m] = delta;
+        if (us.dry) { ret = 1; break; }
+        st->n_moves = m + 1;
+        st->trans_attempt += 1; st->trans_accept += acc ? 1 : 0;
+    }
+    st->uniforms_used = us.pos;
+    st->dr_max = dr_max;
+    return ret;
+}

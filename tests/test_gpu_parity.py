@@ -1,0 +1,344 @@
+"""GPU parity tests: every entry point of the C ABI against the CPU oracle on identical inputs.
+
+Tolerances (north star): 1e-10 relative in FP64 for energies; S(k) element-wise 1e-12·|q|·n_sites
+absolute.  Bit-exactness is not expected: sums run in parallel order and FMA contraction differs.
+"""
+import numpy as np
+import pytest
+
+from metropolismontecarlo_b200 import systems
+from oracle import oracle as ora
+from tests.util import ora_ewald, ora_system, rel
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def c750():
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.load_nist(4)
+    eng = water_engine(ms, 10.0)
+    yield ms, eng
+    eng.close()
+
+
+def test_kvectors_and_cfac(c750):
+    ms, eng = c750
+    ew = ora_ewald(ms.box)
+    k, c = eng.kvectors()
+    assert eng.nkvecs == 337
+    assert np.array_equal(k, ew.kxyz)
+    assert np.allclose(c, ew.cfac, rtol=1e-15, atol=0)
+
+
+def test_single_molecule_all_i(c750):
+    """LJ_poly_ΔU and EwaldReal for all 750 molecules of coord750.txt."""
+    ms, eng = c750
+    s = ora_system(ms)
+    kappa = systems.ALPHA / ms.box
+    worst = 0.0
+    for i in range(1, ms.n_mol + 1):
+        e, v = eng.LJ_poly_ΔU(i)
+        e0, v0 = ora.LJ_poly_dU(i, s, 10.0, ms.box)
+        p, ov = eng.EwaldReal(i)
+        p0, ov0 = ora.EwaldReal(i, s, kappa, 10.0, ms.box)
+        assert ov == ov0
+        worst = max(worst, rel(e, e0), rel(p, p0))
+        assert rel(e, e0) < 1e-12 and rel(p, p0) < 1e-11, i
+        assert abs(v - v0) < 1e-11 * max(1.0, abs(v0), abs(e0)), i
+    es, vs, ovs = eng.EwaldShort(7)
+    e0, v0, _ = ora.EwaldShort(7, s, ora_ewald(ms.box), 10.0, ms.box)
+    assert rel(es, e0) < 1e-11 and rel(vs, v0) < 1e-11 and not ovs
+    print("worst single-molecule rel err", worst)
+
+
+def test_recip_long_and_self(c750):
+    ms, eng = c750
+    ew = ora_ewald(ms.box)
+    e0 = ora.RecipLong(ew, ms.coords, ms.charge, ms.box)
+    e = eng.RecipLong()
+    assert rel(e, e0) < RTOL
+    old, new = eng.rhok()
+    want = ew.sum_new[:, 0] + 1j * ew.sum_new[:, 1]
+    tol = 1e-12 * np.abs(ms.charge).max() * ms.n_sites
+    assert np.abs(old - want).max() < tol and np.abs(new - want).max() < tol
+    assert rel(eng.EwaldSelf(), ora.EwaldSelf(ew, ms.charge)) < 1e-13
+
+
+def test_recip_move_commit_rollback(c750):
+    ms, eng = c750
+    ew = ora_ewald(ms.box)
+    ora.RecipLong(ew, ms.coords, ms.charge, ms.box)
+    eng.RecipLong()
+    rng = np.random.default_rng(7)
+    coords = ms.coords.copy()
+    for step in range(6):
+        i = int(rng.integers(1, ms.n_mol + 1))
+        sl = slice(3 * (i - 1), 3 * i)
+        r_old = coords[sl].copy()
+        r_new = r_old + (rng.random(3) - 0.5) * 0.6
+        d0 = ora.RecipMove(ms.box, ew, r_old, r_new, ms.charge[sl])
+        d = eng.RecipMove(r_old, r_new, ms.charge[sl])
+        assert abs(d - d0) < 1e-9 * max(1.0, abs(d0))
+        old, new = eng.rhok()
+        assert np.abs(new - (ew.sum_new[:, 0] + 1j * ew.sum_new[:, 1])).max() < 1e-9
+        assert np.abs(old - (ew.sum_old[:, 0] + 1j * ew.sum_old[:, 1])).max() < 1e-9
+        if step % 2 == 0:
+            ora.recip_commit(ew)
+            eng.recip_commit()
+            coords[sl] = r_new
+        else:
+            ora.recip_rollback(ew)
+            eng.recip_rollback()
+        old, new = eng.rhok()
+        assert np.array_equal(old, new)
+        assert np.abs(old - (ew.sum_old[:, 0] + 1j * ew.sum_old[:, 1])).max() < 1e-9
+
+
+def _check_props(p, q, tol=RTOL):
+    for k in ("energy", "virial", "coulomb", "lj", "real", "recip", "self_", "wolf_const"):
+        a, b = getattr(p, k), getattr(q, k)
+        assert abs(a - b) <= tol * max(abs(b), abs(q.energy) * 1e-3, 1e-30), (k, a, b)
+    assert p.overlaps == q.overlaps
+
+
+def test_potential_coord750_cell_mode(c750):
+    """Config A: potential(…, "ewald") and the Wolf variant on coord750.txt (L = 3 r_cut → 27 cells)."""
+    ms, eng = c750
+    s = ora_system(ms)
+    want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 4)
+    got = eng.potential("ewald")
+    _check_props(got, want)
+    assert abs(got.lj / 4.488629e5 - 1) < 2e-6 and abs(got.real / -3.492756e6 - 1) < 2e-6
+    assert abs(got.recip / 7.58785e3 - 1) < 5e-6 and abs(got.self_ / -1.42235e7 - 1) < 5e-6   # NIST
+    w0 = ora.potential_wolf(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 4)
+    w = eng.potential("wolf")
+    _check_props(w, w0)
+    lj = eng.potential("lj")
+    assert rel(lj.energy, want.lj) < RTOL and lj.coulomb == 0.0
+
+
+@pytest.mark.parametrize("cfg,rc", [(1, 9.0), (2, 9.5), (3, 8.0)])
+def test_potential_small_boxes_tile_mode(cfg, rc):
+    """NIST configs 1-3 (L = 20 Å < 3 r_cut): brute-force tile path with literal vector1D."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.load_nist(cfg)
+    eng = water_engine(ms, rc)
+    s = ora_system(ms)
+    want = ora.potential_ewald(s, ora_ewald(ms.box), rc, rc, ms.box, 2)
+    got = eng.potential("ewald")
+    _check_props(got, want)
+    old, _ = eng.rhok()
+    ew = ora_ewald(ms.box)
+    ora.RecipLong(ew, ms.coords, ms.charge, ms.box)
+    assert np.abs(old - (ew.sum_old[:, 0] + 1j * ew.sum_old[:, 1])).max() < 1e-10
+    eng.close()
+
+
+def test_fused_trial_move_equals_five_calls(c750):
+    ms, eng = c750
+    eng.upload_system(ms, 10.0, 10.0)
+    eng.RecipLong()
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    ora.RecipLong(ew, ms.coords, ms.charge, ms.box)
+    rng = np.random.default_rng(21)
+    for style in ("ewald", "wolf", "lj"):
+        for _ in range(8):
+            i = int(rng.integers(1, ms.n_mol + 1))
+            sl = slice(3 * (i - 1), 3 * i)
+            d = (rng.random(3) - 0.5) * 0.5
+            com_new, sites_new = s.com[i - 1] + d, s.coords[sl] + d
+            t = eng.trial_move(i, com_new, sites_new, style)
+            lo, vo = ora.LJ_poly_dU(i, s, 10.0, ms.box)
+            qo, qvo, ovo = ora.EwaldShort(i, s, ew, 10.0, ms.box)
+            r_old, com_old = s.coords[sl].copy(), s.com[i - 1].copy()
+            s.coords[sl], s.com[i - 1] = sites_new, com_new
+            ln, vn = ora.LJ_poly_dU(i, s, 10.0, ms.box)
+            qn, qvn, ovn = ora.EwaldShort(i, s, ew, 10.0, ms.box)
+            assert rel(t.lj_old, lo) < 1e-12 and rel(t.lj_new, ln) < 1e-12
+            assert abs(t.lj_vir_old - vo) < 1e-10 * max(1, abs(vo)) and abs(t.lj_vir_new - vn) < 1e-10 * max(1, abs(vn))
+            if style != "lj":
+                assert rel(t.qq_old, qo) < 1e-11 and rel(t.qq_new, qn) < 1e-11
+                assert rel(t.qq_vir_old, qvo) < 1e-11 and rel(t.qq_vir_new, qvn) < 1e-11
+                assert (t.overlap_old, t.overlap_new) == (int(ovo), int(ovn))
+            if style == "ewald":
+                d0 = ora.RecipMove(ms.box, ew, r_old, sites_new, ms.charge[sl])
+                assert abs(t.d_recip - d0) < 1e-9 * max(1.0, abs(d0))
+            else:
+                assert t.d_recip == 0.0
+            if rng.random() < 0.5:
+                eng.accept()
+                if style == "ewald":
+                    ora.recip_commit(ew)
+            else:
+                eng.reject()
+                s.coords[sl], s.com[i - 1] = r_old, com_old
+                if style == "ewald":
+                    ora.recip_rollback(ew)
+    coords, com = eng.download_system()
+    assert np.array_equal(coords, s.coords) and np.array_equal(com, s.com)
+    old, new = eng.rhok()
+    assert np.abs(old - (ew.sum_old[:, 0] + 1j * ew.sum_old[:, 1])).max() < 1e-9
+
+
+def test_overlap_rule(c750):
+    """r² < 0.5 Å² with q_a q_b < 0 → EwaldReal returns (0.0, true) (ewalds.jl:359-360);
+    potential() drops the whole row of both molecules; a trial move reports the flag."""
+    ms0, eng = c750
+    ms = ms0.copy()
+    # put molecule 2 so that its first H sits 0.3 Å from the O of molecule 1
+    shift = (ms.coords[0] + np.array([0.3, 0.0, 0.0])) - ms.coords[4]
+    ms.coords[3:6] += shift
+    ms.com[1] += shift
+    ms.com[1] = np.clip(ms.com[1], 0.0, ms.box)
+    eng.upload_system(ms, 10.0, 10.0)
+    s = ora_system(ms)
+    kappa = systems.ALPHA / ms.box
+    for i in (1, 2, 3):
+        p, ov = eng.EwaldReal(i)
+        p0, ov0 = ora.EwaldReal(i, s, kappa, 10.0, ms.box)
+        assert ov == ov0 and rel(p, p0) < 1e-11 if p0 != 0 else p == 0.0
+    assert eng.EwaldReal(1) == (0.0, True) and eng.EwaldReal(2) == (0.0, True)
+    want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 4)
+    got = eng.potential("ewald")
+    assert want.overlaps >= 2
+    _check_props(got, want)
+    t = eng.trial_move(3, ms.com[2], ms.coords[6:9], "ewald")
+    assert t.overlap_old == 0 and t.overlap_new == 0
+    t = eng.trial_move(1, ms.com[0], ms.coords[0:3], "ewald")
+    assert t.overlap_old == 1 and t.overlap_new == 1 and t.qq_old == 0.0 and t.d_recip == 0.0
+    eng.reject()
+    eng.upload_system(ms0, 10.0, 10.0)
+
+
+def test_volume_trial_matches_scaled_recompute(c750):
+    """Ewald/volumeChange.jl:50-147: scale COMs, rigid-shift sites, κ = α/L', full energy at L'."""
+    ms, eng = c750
+    eng.upload_system(ms, 10.0, 10.0)
+    e_before = eng.potential("ewald").energy
+    for box_new in (30.4, 29.8):      # 29.8 < 3 r_cut → the trial falls back to tile mode
+        s = ora_system(ms)
+        ora.volume_scale(s, ms.box, box_new)
+        ew = ora.Ewald(systems.ALPHA / box_new, 5, 27, systems.FACTOR, box_new)
+        want = ora.potential_ewald(s, ew, 10.0, 10.0, box_new, 4)
+        got = eng.volume_trial(box_new, systems.ALPHA / box_new, "ewald")
+        _check_props(got, want)
+        eng.volume_reject()
+        assert rel(eng.potential("ewald").energy, e_before) < 1e-13
+    got = eng.volume_trial(30.4, systems.ALPHA / 30.4, "ewald")
+    eng.volume_accept()
+    again = eng.potential("ewald")
+    assert rel(again.energy, got.energy) < 1e-12
+    coords, com = eng.download_system()
+    s = ora_system(ms)
+    ora.volume_scale(s, ms.box, 30.4)
+    assert np.array_equal(coords, s.coords) and np.array_equal(com, s.com)
+    # a molecule move after the accepted volume move uses the new box, κ, cfac and ρ(k)
+    ew = ora.Ewald(systems.ALPHA / 30.4, 5, 27, systems.FACTOR, 30.4)
+    ora.RecipLong(ew, s.coords, s.charge, 30.4)
+    i = 11
+    sl = slice(30, 33)
+    t = eng.trial_move(i, s.com[i - 1] + 0.2, s.coords[sl] + 0.2, "ewald")
+    d0 = ora.RecipMove(30.4, ew, s.coords[sl], s.coords[sl] + 0.2, s.charge[sl])
+    qo = ora.EwaldShort(i, s, ew, 10.0, 30.4)[0]
+    assert abs(t.d_recip - d0) < 1e-9 * max(1.0, abs(d0)) and rel(t.qq_old, qo) < 1e-11
+    eng.reject()
+    eng.upload_system(ms, 10.0, 10.0)
+    eng.PrepareEwaldVariables(systems.ALPHA / ms.box)
+
+
+def test_sharded_partials_sum_to_unsharded(c750):
+    """§8e: R ranks emulated as R handles run one after another on one GPU; partial vectors are
+    summed (what the NCCL all-reduce does) and finalised on every 'rank'."""
+    import torch
+    from metropolismontecarlo_b200.energy import water_engine
+    ms, eng = c750
+    eng.upload_system(ms, 10.0, 10.0)
+    ref = eng.potential("ewald")
+    for world in (2, 4, 8):
+        engs = [water_engine(ms, 10.0, rank=r, world=world) for r in range(world)]
+        n = engs[0].partial_count()
+        bufs = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in range(world)]
+        for e, b in zip(engs, bufs):
+            e.potential_partial("ewald", b.data_ptr())
+        torch.cuda.synchronize()
+        total = torch.stack(bufs).sum(0)
+        for e in engs:
+            buf = total.clone()
+            p = e.potential_finalize("ewald", buf.data_ptr())
+            _check_props(p, ref, 1e-12)
+            old, _ = e.rhok()
+            assert np.abs(old - eng.rhok()[0]).max() < 1e-9
+        for e in engs:
+            e.close()
+
+
+def test_config_d_4000_molecules():
+    """Config D: 4000 SPC/E on the cubic lattice with random quaternions (cell mode, 4³ cells)."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.spce_lattice(4000)
+    eng = water_engine(ms, 10.0)
+    s = ora_system(ms)
+    want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
+    got = eng.potential("ewald")
+    _check_props(got, want)
+    for i in (1, 1999, 4000):
+        assert rel(eng.LJ_poly_ΔU(i)[0], ora.LJ_poly_dU(i, s, 10.0, ms.box)[0]) < 1e-12
+    box_new = ms.box * 1.01
+    ora.volume_scale(s, ms.box, box_new)
+    w2 = ora.potential_ewald(s, ora.Ewald(systems.ALPHA / box_new, 5, 27, systems.FACTOR, box_new), 10.0, 10.0, box_new, 8)
+    _check_props(eng.volume_trial(box_new, systems.ALPHA / box_new, "ewald"), w2)
+    eng.close()
+
+
+def test_monatomic_known_answers_and_parity():
+    from metropolismontecarlo_b200.energy import Engine
+    eng = Engine()
+    # the reference's own test_LJ (Ewald/tests.jl:127-161)
+    r = np.array([[0, 0, 0], [0, 0, 2], [0, 1.5, 0]], dtype=np.float64)
+    eng.upload_atoms(systems.AtomicSystem(r, np.ones(3), np.ones(3), 5.0, 2.5))
+    assert abs(eng.LJ_ΔU(1)[0] - (-0.381860031778575)) < 1e-14
+    eng.set_atom(2, [0, 0, 4.0])
+    assert abs(eng.LJ_ΔU(1)[0] - (-0.320336594278575)) < 1e-14
+    # lattice + noise, 2197 atoms, heterogeneous eps/sig to exercise the per-j parameters
+    at = systems.lj_lattice(2197, 0.75, 2.5)
+    rng = np.random.default_rng(5)
+    at.r[:] = (at.r + rng.normal(0, 0.08, at.r.shape)) % at.box
+    at.eps[:] = 0.8 + 0.4 * rng.random(at.n)
+    at.sig[:] = 0.95 + 0.1 * rng.random(at.n)
+    eng.upload_atoms(at)
+    for i in (1, 2, 1000, 2197):
+        e, v = eng.LJ_ΔU(i)
+        e0, v0 = ora.LJ_dU_atom(i, at.r, at.eps, at.sig, at.box, at.r_cut)
+        assert rel(e, e0) < 1e-12 and rel(v, v0) < 1e-12
+    p = eng.potential("atoms")
+    e0, v0 = ora.potential_atoms(at.r, at.eps, at.sig, at.box, at.r_cut, 4)
+    assert rel(p.energy, e0) < 1e-12 and rel(p.virial, v0) < 1e-12
+    t = eng.trial_atom(17, at.r[16] + 0.05)
+    r2 = at.r.copy()
+    r2[16] += 0.05
+    assert rel(t.lj_old, ora.LJ_dU_atom(17, at.r, at.eps, at.sig, at.box, at.r_cut)[0]) < 1e-12
+    assert rel(t.lj_new, ora.LJ_dU_atom(17, r2, at.eps, at.sig, at.box, at.r_cut)[0]) < 1e-12
+    eng.accept()
+    assert np.array_equal(eng.download_atoms(), r2)
+    eng.close()
+
+
+def test_error_behaviour():
+    from metropolismontecarlo_b200.energy import Engine, MMCError
+    eng = Engine()
+    with pytest.raises(MMCError):
+        eng.potential("ewald")              # nothing uploaded
+    ms = systems.load_nist(1)
+    eng.upload_system(ms, 9.0)
+    with pytest.raises(MMCError):
+        eng.EwaldReal(1)                    # no Ewald tables yet
+    with pytest.raises(MMCError):
+        eng.LJ_poly_ΔU(0)                   # indices are 1-based
+    with pytest.raises(MMCError):
+        eng.accept()                        # no pending trial
+    assert eng.LJ_poly_ΔU(1)[0] != 0.0
+    eng.close()

@@ -1,0 +1,103 @@
+"""Trajectory parity: the library's host driver (mmc_loop_run: one fused trial-move launch +
+accept/reject per move) against the oracle's restatement of Ewald/main.jl Loop(), both fed the
+same recorded stream of uniforms in the reference's draw order.
+
+Bar (north star): identical accept/reject sequence for the first 10^4 moves; per-move deltas
+within 1e-10 relative of the energy scale; Σ accepted deltas == fresh potential() (the reference's
+own block invariant, Poly/main.jl:232-235, tolerance 1e-3 there)."""
+import numpy as np
+import pytest
+
+from metropolismontecarlo_b200 import systems
+from metropolismontecarlo_b200.energy import LoopParams
+from oracle import oracle as ora
+from tests.util import ora_ewald, ora_system, rel
+
+pytestmark = pytest.mark.gpu
+
+N_MOVES = 10_000
+
+
+@pytest.mark.parametrize("style,sid", [("ewald", 0), ("wolf", 1)])
+def test_accept_reject_sequence_coord750(style, sid):
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.load_nist(4)
+    rc, T = 10.0, 298.15
+    u = np.random.default_rng(11234).random(8 * N_MOVES)
+    # ---- oracle
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    p0 = ora.potential_ewald(s, ew, rc, rc, ms.box, 4) if sid == 0 else ora.potential_wolf(s, ew, rc, rc, ms.box, 4)
+    prm = ora.LoopParams(T, 0.316555789, 0.05, 0.5, 1.0, rc, rc, ms.box, sid, 1)
+    quat_o = ms.quat.copy()
+    rc_o, acc_o, del_o, st_o = ora.loop(s, ew, ms.db, quat_o, prm, u, N_MOVES, p0.energy, p0.virial)
+    assert rc_o == 0
+    # ---- engine
+    eng = water_engine(ms, rc)
+    g0 = eng.potential(style)
+    assert rel(g0.energy, p0.energy) < 1e-10
+    com, quat = ms.com.copy(), ms.quat.copy()
+    rc_g, acc_g, del_g, st_g = eng.loop_run(LoopParams(T, 0.316555789, 0.05, 0.5, 1.0, sid, 1), com, quat, ms.db,
+                                            u, N_MOVES, g0.energy, g0.virial)
+    assert rc_g == 0 and st_g.n_moves == N_MOVES
+    assert np.array_equal(acc_g, acc_o), f"first divergence at move {int(np.argmax(acc_g != acc_o))}"
+    assert st_g.uniforms_used == st_o.uniforms_used
+    assert st_g.n_accepted == st_o.n_accepted and st_g.rot_accept == st_o.rot_accept
+    assert st_g.dr_max == st_o.dr_max and st_g.dphi_max == st_o.dphi_max
+    scale = max(np.abs(del_o).max(), 1.0)
+    assert np.abs(del_g - del_o).max() < 1e-10 * abs(p0.energy) and np.abs(del_g - del_o).max() < 1e-6 * scale
+    assert np.array_equal(com, s.com) and np.array_equal(quat, quat_o)
+    coords, com_d = eng.download_system()
+    assert np.array_equal(coords, s.coords) and np.array_equal(com_d, s.com)
+    # running total == fresh recompute, on both sides
+    fresh = eng.potential(style)
+    assert abs(st_g.total_energy - fresh.energy) < 1e-3
+    assert rel(st_g.total_energy, fresh.energy) < 1e-10
+    assert rel(st_g.total_energy, st_o.total_energy) < 1e-11
+    if sid == 0:   # resident ρ(k) after ~5·10³ delta updates == oracle's
+        old_before = ew.sum_old[:, 0] + 1j * ew.sum_old[:, 1]
+        # potential() above rebuilt ρ(k); compare against a fresh oracle rebuild too
+        ew2 = ora_ewald(ms.box)
+        ora.RecipLong(ew2, s.coords, s.charge, ms.box)
+        assert np.abs(eng.rhok()[0] - (ew2.sum_old[:, 0] + 1j * ew2.sum_old[:, 1])).max() < 1e-9
+        assert np.abs(old_before - (ew2.sum_old[:, 0] + 1j * ew2.sum_old[:, 1])).max() < 1e-8
+    print(style, "accepted", st_g.n_accepted, "of", N_MOVES, "overlaps", st_g.n_overlap)
+    eng.close()
+
+
+def test_rhok_resident_after_moves_matches_rebuild():
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.load_nist(1)
+    eng = water_engine(ms, 9.0)
+    g0 = eng.potential("ewald")
+    u = np.random.default_rng(3).random(20000)
+    com, quat = ms.com.copy(), ms.quat.copy()
+    rc, acc, delta, st = eng.loop_run(LoopParams(298.15, 0.3, 0.05, 0.5, 1.0, 0, 1), com, quat, ms.db, u, 2000,
+                                      g0.energy, g0.virial)
+    assert rc == 0 and 0 < st.n_accepted < 2000
+    resident = eng.rhok()[0].copy()
+    eng.RecipLong()
+    assert np.abs(resident - eng.rhok()[0]).max() < 1e-9
+    eng.close()
+
+
+def test_monatomic_lj_trajectory():
+    """Monatomic/mainMonatomic.jl:373-413 with 1000 atoms, rho*=0.75, T*=1, dr_max = L/30."""
+    from metropolismontecarlo_b200.energy import Engine
+    at = systems.lj_lattice(1000, 0.75, 2.5)
+    u = np.random.default_rng(11234).random(5 * N_MOVES)
+    e0, v0 = ora.potential_atoms(at.r, at.eps, at.sig, at.box, at.r_cut, 4)
+    r_o = at.r.copy()
+    rc_o, acc_o, del_o, st_o = ora.loop_atoms(r_o, at.eps, at.sig, at.box, at.r_cut, 1.0, at.box / 30, u, N_MOVES, e0, v0)
+    eng = Engine()
+    eng.upload_atoms(at)
+    g0 = eng.potential("atoms")
+    assert rel(g0.energy, e0) < 1e-12
+    r_g = at.r.copy()
+    rc_g, acc_g, del_g, st_g = eng.loop_run_atoms(1.0, at.box / 30, r_g, u, N_MOVES, g0.energy, g0.virial)
+    assert rc_o == 0 and rc_g == 0
+    assert np.array_equal(acc_g, acc_o)
+    assert np.abs(del_g - del_o).max() < 1e-10 * max(1.0, np.abs(del_o).max())
+    assert np.array_equal(r_g, r_o) and np.array_equal(eng.download_atoms(), r_o)
+    assert rel(st_g.total_energy, eng.potential("atoms").energy) < 1e-10
+    eng.close()
