@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — full-Ewald-energy evaluations/s (BASELINE.json metric) on the synthetic 256 000-molecule
+SPC/E box (config E), sharded over N B200s, plus MC moves/s for configs A/B/C at N=1.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N>1: under torch.distributed.run)
+  python bench.py --impl reference ...                      the reference algorithm on host cores
+
+One "step" = one potential(…, "ewald") evaluation of the whole system (what every volume move
+needs): molecule-pair LJ + real-space erfc Coulomb over unique pairs + ρ(k) rebuild + E_recip
++ E_self.  `value` times the device-resident path (state already in HBM); `e2e` times the
+reference-facing call with HOST arrays (mmc_upload_system from the Julia-layout arrays +
+mmc_potential + result on the host) — see DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "full_ewald_energy_evals_per_sec"
+UNIT = "evals/s"
+N_MOL_E = 256_000
+RC = 10.0
+FLOP_PER_PAIR = 624          # 9 x 67 + 21 per in-cutoff water-water pair
+
+
+def workload_config(n_mol):
+    return {
+        "workload": f"config E: synthetic SPC/E box, {n_mol} molecules ({3 * n_mol} sites) on InitCubicGrid at "
+                    "rho=0.033101144 A^-3 with random quaternions (seed 11234); full Ewald potential(): "
+                    "r_cut=10 A COM cutoff, kappa=5.6/L, nk=5, k^2<27 (337 k-vectors)",
+        "n_molecules": n_mol,
+        "l2": "flushed between timed steps (256 MiB device write); state itself (35 MB) is L2-sized",
+        "sharding": "pair work units (cell pairs) and rho(k) sites split per rank; one NCCL all-reduce of 682 doubles",
+    }
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        self.t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- CPU baseline
+def cpu_full_energy_sample(ms, n_rows, site_frac, threads):
+    """Reference algorithm (oracle port) on a bounded sample: n_rows of the 2 x O(N^2) row loops of
+    potential() (energy.jl:972-1001) and RecipLong on 1/site_frac of the sites; extrapolated linearly."""
+    from oracle import oracle as ora
+    from metropolismontecarlo_b200 import systems
+    s = ora.System(ms.coords, ms.charge, ms.atype, ms.first_atom, ms.last_atom, ms.com, ms.eps, ms.sig)
+    kappa = systems.ALPHA / ms.box
+    rng = np.random.default_rng(1)
+    i0 = int(rng.integers(0, ms.n_mol - n_rows))
+    t0 = time.perf_counter()
+    ora.potential_rows(s, kappa, RC, RC, ms.box, i0, i0 + n_rows, threads)
+    t_rows = time.perf_counter() - t0
+    ns = ms.n_sites // site_frac
+    ew = ora.Ewald(kappa, systems.NK, systems.K_SQ_MAX, systems.FACTOR, ms.box)
+    t0 = time.perf_counter()
+    ora.RecipLong(ew, ms.coords[:ns], ms.charge[:ns], ms.box)
+    t_recip = time.perf_counter() - t0
+    t_eval = t_rows * (ms.n_mol / n_rows) + t_recip * site_frac
+    return 1.0 / t_eval, t_rows, t_recip
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU algorithm (oracle port; Julia is not installed, so
+    there is no oracle/_ref) on all host cores, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import oracle as ora
+    from metropolismontecarlo_b200 import systems
+    ora.build()
+    threads = os.cpu_count() or 1
+    ms = systems.spce_lattice(args.molecules)
+    n_rows, frac = 256, 64
+    for _ in range(args.warmup):
+        cpu_full_energy_sample(ms, 64, 256, threads)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_full_energy_sample(ms, n_rows, frac, threads)[0])
+    wall = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    sample = (f"{n_rows} of {ms.n_mol} rows of the two O(N^2) loops ({threads} OpenMP threads over rows) + RecipLong on "
+              f"1/{frac} of the sites (serial, as the reference), extrapolated linearly to one full evaluation")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(ms.n_mol),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sample_wall_s": wall,
+    }))
+
+
+# ------------------------------------------------------------------------------------ moves/s (N=1)
+def moves_benchmarks(n_moves=10_000):
+    """Configs A, B, C: moves/s through the library's host driver (one fused launch + one host wait
+    per move — the ccall protocol), and the oracle's Loop on one host core for a bounded sample."""
+    from metropolismontecarlo_b200 import systems
+    from metropolismontecarlo_b200.energy import Engine, LoopParams, water_engine
+    from oracle import oracle as ora
+    out = {}
+    ms = systems.load_nist(4)
+    u = np.random.default_rng(11234).random(8 * n_moves)
+    for name, style, sid in (("A_spce750_ewald", "ewald", 0), ("B_spce750_wolf", "wolf", 1)):
+        eng = water_engine(ms, RC)
+        p0 = eng.potential(style)
+        com, quat = ms.com.copy(), ms.quat.copy()
+        eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, sid, 1), com, quat, ms.db, u, 500, p0.energy, p0.virial)
+        eng.upload_system(ms, RC, RC)
+        p0 = eng.potential(style)
+        com, quat = ms.com.copy(), ms.quat.copy()
+        l0 = eng.counters().kernel_launches
+        t0 = time.perf_counter()
+        rc, acc, delta, st = eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, sid, 1), com, quat, ms.db,
+                                          u, n_moves, p0.energy, p0.virial)
+        dt = time.perf_counter() - t0
+        launches = eng.counters().kernel_launches - l0
+        s = ora.System(ms.coords, ms.charge, ms.atype, ms.first_atom, ms.last_atom, ms.com, ms.eps, ms.sig)
+        ew = ora.Ewald(systems.ALPHA / ms.box, 5, 27, systems.FACTOR, ms.box)
+        if sid == 0:
+            ora.RecipLong(ew, ms.coords, ms.charge, ms.box)
+        n_cpu = 2000
+        prm = ora.LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, RC, RC, ms.box, sid, 1)
+        t0 = time.perf_counter()
+        ora.loop(s, ew, ms.db, ms.quat.copy(), prm, u, n_cpu, 0.0, 0.0)
+        dtc = time.perf_counter() - t0
+        out[name] = {"moves_per_s": n_moves / dt, "us_per_move": 1e6 * dt / n_moves, "accepted": int(st.n_accepted),
+                     "gpu_launches": int(launches), "cpu_port_moves_per_s_1core": n_cpu / dtc,
+                     "flop_per_move": 2.1e5 if sid == 0 else 1.75e5}
+        eng.close()
+    at = systems.lj_lattice(32_000, 0.75, 2.5)
+    eng = Engine()
+    eng.upload_atoms(at)
+    p0 = eng.potential("atoms")
+    r = at.r.copy()
+    eng.loop_run_atoms(1.0, at.box / 30, r, u, 500, p0.energy, p0.virial)
+    eng.upload_atoms(at)
+    r = at.r.copy()
+    t0 = time.perf_counter()
+    rc, acc, delta, st = eng.loop_run_atoms(1.0, at.box / 30, r, u, n_moves, p0.energy, p0.virial)
+    dt = time.perf_counter() - t0
+    n_cpu = 500
+    t0 = time.perf_counter()
+    ora.loop_atoms(at.r.copy(), at.eps, at.sig, at.box, at.r_cut, 1.0, at.box / 30, u, n_cpu, 0.0, 0.0)
+    dtc = time.perf_counter() - t0
+    out["C_lj32000"] = {"moves_per_s": n_moves / dt, "us_per_move": 1e6 * dt / n_moves, "accepted": int(st.n_accepted),
+                        "cpu_port_moves_per_s_1core": n_cpu / dtc, "flop_per_move": 1.35e6}
+    eng.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------- ours
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from metropolismontecarlo_b200 import systems
+    from metropolismontecarlo_b200.energy import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmmc_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    eng = Engine(device=local_rank, rank=rank, world=world, stream=stream.cuda_stream)
+    ms = systems.spce_lattice(args.molecules)
+    eng.upload_system(ms, RC, RC)
+    eng.PrepareEwaldVariables(systems.ALPHA / ms.box)
+    nvec = eng.partial_count()
+    vec = torch.zeros(nvec, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step():
+        eng.potential_partial("ewald", vec.data_ptr())
+        if world > 1:
+            dist.all_reduce(vec)                       # NCCL over NVLink: 8 scalars + 337 complex rho(k)
+        return eng.potential_finalize("ewald", vec.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        props = step()
+    fp64_peak = eng.measure_fp64_peak() if rank == 0 else 0.0
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    eng.set_timing(True)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    l0 = eng.counters().kernel_launches
+    pair_ms, rhok_ms = [], []
+    barrier()
+    if sampler:
+        sampler.start()
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)                          # evict the 126 MB L2 between timed steps
+        ev0[k].record()
+        props = step()
+        ev1[k].record()
+        tm = eng.last_timings()
+        pair_ms.append(tm["pairs_ms"])
+        rhok_ms.append(tm["rhok_ms"])
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = eng.counters().kernel_launches - l0
+    eng.set_timing(False)
+    total_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)       # max over ranks, device-timed
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = 1e3 / ms_per_step
+    info = eng.last_eval_info()
+
+    # ---- e2e: host arrays in, host scalars out, every step (upload + evaluate)
+    coords_pin = ms  # the Julia-layout host arrays; the library stages them through pinned memory
+    def e2e_step():
+        eng.upload_system(coords_pin, RC, RC)
+        return step()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(n_e2e):
+        p2 = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = ms.n_sites * (32 + 4) + ms.n_mol * (32 + 8)
+    assert abs(p2.energy - props.energy) <= 1e-12 * abs(props.energy)
+
+    if rank == 0:
+        pairs = info["pairs_in_cutoff"]
+        t_pair = float(np.mean(pair_ms)) * 1e-3
+        # algorithmic FP64 flops of the dominant kernel for THIS rank's share of the pairs
+        alg_flops = FLOP_PER_PAIR * pairs / world
+        achieved = alg_flops / t_pair / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(ms.n_mol),
+            "energy_per_molecule_K": props.energy / ms.n_mol,
+            "pairs_in_cutoff": pairs, "path": info["mode"], "cells_per_dim": info["cells_per_dim"],
+            "kernel_ms": {"pairs": float(np.mean(pair_ms)), "rhok_rebuild": float(np.mean(rhok_ms))},
+            "roofline": {"bound": "fp64", "kernel": "k_pairs<3>", "achieved": achieved, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+                         "peak_source": "live DFMA-chain probe on this GPU (MEASURED_PEAKS.json has no FP64 figure); "
+                                        "nominal 37.2 TFLOP/s at 1965 MHz",
+                         "algorithmic_flop_per_launch": alg_flops, "traffic": None},
+            "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
+                    "what": "mmc_upload_system(host Julia-layout arrays) + sharded potential + Properties on host"},
+            "gpu_launches": int(launches) * world,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as ora
+            ora.build()
+            threads = os.cpu_count() or 1
+            v, t_rows, t_recip = cpu_full_energy_sample(ms, 1024, 16, threads)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"1024 of {ms.n_mol} rows of the reference's two O(N^2) loops ({threads} OpenMP threads, "
+                          f"{t_rows:.1f} s) + RecipLong on 1/16 of the sites (serial, {t_recip:.1f} s), extrapolated "
+                          "linearly; Julia is not installed, so this is the C restatement of the reference algorithm"}
+            if not args.no_moves:
+                line["moves"] = moves_benchmarks()
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--molecules", type=int, default=N_MOL_E)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-moves", action="store_true", help="skip the moves/s legs (configs A/B/C)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("for --gpus N > 1 launch under torch.distributed.run (one rank per GPU)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -203,6 +203,10 @@ int mmc_get_counters(mmc_handle *h, mmc_counters *out);
  * ms4[2] binning + gather, ms4[3] whole evaluation up to the result copy */
 int mmc_set_timing(mmc_handle *h, int32_t enabled);
 int mmc_last_timings(mmc_handle *h, float *ms4);
+/* what the last full-energy evaluation did: molecule pairs inside the cutoff (summed over ranks
+ * after finalize), path taken (0 = cell list, 1 = tile pairs, 2 = per-molecule rows) and cells per
+ * box edge */
+int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, int32_t *cells_per_dim);
 /* FP64 DFMA-chain microbenchmark: measured FP64 FMA throughput of the device [TFLOP/s] */
 int mmc_measure_fp64_peak(mmc_handle *h, double *tflops);
 

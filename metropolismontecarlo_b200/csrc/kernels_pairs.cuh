@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
     double4 *s_siteB = s_siteA + PAIR_TILE * S;
     unsigned int *s_queue = reinterpret_cast<unsigned int *>(s_siteB + PAIR_TILE * S);
     __shared__ LJActive s_lj[64];
-    __shared__ double s_red[3 * PAIR_WARPS];
+    __shared__ double s_red[4 * PAIR_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned int *q = s_queue + warp * PAIR_QCAP;
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
     const long long u1 = (u0 + per < A.unit_end) ? u0 + per : A.unit_end;
 
     double acc[3] = {0.0, 0.0, 0.0};   // lj_pot, lj_vir, coul
+    unsigned long long my_pairs = 0;   // molecule pairs that passed the gate (counted by lane 0 of each warp)
 
     for (long long u = u0; u < u1; ++u) {
         int a_lo, a_hi, b_lo, b_hi;
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
                         (unsigned)p | ((unsigned)qq_ << 8) | ((unsigned)fl << 16);
                     npairs += __popc(m);
                 }
+                if (lane == 0) my_pairs += npairs;
                 __syncwarp();
                 // ---- (b) Coulomb: all S x S site pairs of the queued molecule pairs
                 if (A.want_qq) {
@@ -210,8 +212,9 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
         }
     }
     __syncthreads();
-    block_sum<3, PAIR_BLOCK>(acc, s_red);
-    if (tid == 0) A.partial[blockIdx.x] = make_double4(acc[0], acc[1], acc[2], 0.0);
+    double accp[4] = {acc[0], acc[1], acc[2], (double)my_pairs};
+    block_sum<4, PAIR_BLOCK>(accp, s_red);
+    if (tid == 0) A.partial[blockIdx.x] = make_double4(accp[0], accp[1], accp[2], accp[3]);
 }
 
 // fold the per-CTA partials in CTA order into the head of the partial-sum vector:
@@ -219,9 +222,9 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
 __global__ void k_pair_reduce(const double4 *partial, int nb, const unsigned int *n_ovl, double *out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double a = 0.0, b = 0.0, c = 0.0;
-    for (int i = 0; i < nb; ++i) { const double4 p = partial[i]; a += p.x; b += p.y; c += p.z; }
-    out[0] = a; out[1] = b; out[2] = c; out[3] = (double)(*n_ovl);
+    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+    for (int i = 0; i < nb; ++i) { const double4 p = partial[i]; a += p.x; b += p.y; c += p.z; d += p.w; }
+    out[0] = a; out[1] = b; out[2] = c; out[3] = (double)(*n_ovl); out[5] = d;
 }
 
 // ------------------------------------------------------------------ cell binning + gather

@@ -31,6 +31,8 @@ struct mmc_handle {
     bool has_system = false;
     DevSystem S{};
     std::vector<int2> h_mol;     // host mirror of S.mol
+    unsigned char *h_stage = nullptr;   // pinned staging for uploads (repacked AoS -> device layout)
+    size_t stage_bytes = 0;
     bool uniform = false;        // every molecule: same site count, same type sequence, packed
     int US = 0;                  // uniform sites per molecule
     std::vector<LJActive> lj;
@@ -75,6 +77,7 @@ struct mmc_handle {
     double *h_vec = nullptr;     // pinned
     int last_mode = -1;          // 0 cells, 1 tiles, 2 rows
     int last_ncd = 0;
+    long long last_pairs = 0;    // molecule pairs inside the cutoff in the last evaluation (all ranks)
 
     // ---- volume trial
     bool vol_pending = false;
@@ -406,6 +409,7 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
     out->energy = out->lj;
     out->virial = vir_lj;
     out->overlaps = novl;
+    h->last_pairs = (long long)h->h_vec[5];
     if (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF) {
         const double totReal = coul * factor;   // (Σ_i row_i) * factor / 2
         out->real = totReal;
@@ -567,6 +571,7 @@ int mmc_destroy(mmc_handle *h)
     free_system(h); free_ewald(h); free_atoms(h);
     dfree(h->W.partial); dfree(h->W.ticket);
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     for (auto &ev : h->tm.ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -586,9 +591,19 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
     CK(cudaSetDevice(h->cfg.device));
     const bool had_ewald = h->has_ewald;
     free_system(h);
-    std::vector<double4> hs(n_sites), hc(n_mol);
-    std::vector<int2> hm(n_mol);
-    std::vector<int> ht(n_sites);
+    // repack straight into pinned staging memory so the H2D copies are single DMA transfers
+    const size_t need = sizeof(double4) * (size_t)(n_sites + n_mol) + sizeof(int2) * (size_t)n_mol +
+                        sizeof(int) * (size_t)n_sites;
+    if (need > h->stage_bytes) {
+        if (h->h_stage) cudaFreeHost(h->h_stage);
+        h->h_stage = nullptr; h->stage_bytes = 0;
+        CK(cudaHostAlloc((void **)&h->h_stage, need, cudaHostAllocDefault));
+        h->stage_bytes = need;
+    }
+    double4 *hs = reinterpret_cast<double4 *>(h->h_stage);
+    double4 *hc = hs + n_sites;
+    int2 *hm = reinterpret_cast<int2 *>(hc + n_mol);
+    int *ht = reinterpret_cast<int *>(hm + n_mol);
     int max_sites = 0;
     bool uniform = true;
     for (int64_t m = 0; m < n_mol; ++m) {
@@ -628,10 +643,10 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
     CK(cudaMalloc(&S.com, sizeof(double4) * n_mol));
     CK(cudaMalloc(&S.mol, sizeof(int2) * n_mol));
     CK(cudaMalloc(&S.atype, sizeof(int) * n_sites));
-    CK(cudaMemcpyAsync(S.site, hs.data(), sizeof(double4) * n_sites, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(S.com, hc.data(), sizeof(double4) * n_mol, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(S.mol, hm.data(), sizeof(int2) * n_mol, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(S.atype, ht.data(), sizeof(int) * n_sites, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.site, hs, sizeof(double4) * n_sites, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.com, hc, sizeof(double4) * n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.mol, hm, sizeof(int2) * n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.atype, ht, sizeof(int) * n_sites, cudaMemcpyHostToDevice, h->stream));
     // LJ-active site-type combinations of the uniform molecule (ε_ij > 0.001, energy.jl:270)
     h->lj.clear();
     if (uniform)
@@ -669,7 +684,7 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
     CK(cudaStreamSynchronize(h->stream));
     h->sum_q = qs[0]; h->sum_q2 = qs[1];
     h->rhok_grid_cap = 0;
-    h->h_mol = hm;
+    h->h_mol.assign(hm, hm + n_mol);
     h->has_system = true;
     h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
     return MMC_OK;
@@ -1134,6 +1149,15 @@ int mmc_last_timings(mmc_handle *h, float *ms4)
 {
     if (!h || !ms4) return MMC_EINVAL;
     for (int i = 0; i < 4; ++i) ms4[i] = h->tm.ms[i];
+    return MMC_OK;
+}
+
+int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, int32_t *cells_per_dim)
+{
+    if (!h) return MMC_EINVAL;
+    if (pairs_in_cutoff) *pairs_in_cutoff = h->last_pairs;
+    if (mode) *mode = h->last_mode;
+    if (cells_per_dim) *cells_per_dim = h->last_ncd;
     return MMC_OK;
 }
 

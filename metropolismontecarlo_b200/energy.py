@@ -272,6 +272,12 @@ class Engine:
         self._ck(self.lib.mmc_last_timings(self.h, ms))
         return {"pairs_ms": ms[0], "rhok_ms": ms[1], "bin_gather_ms": ms[2], "total_ms": ms[3]}
 
+    def last_eval_info(self):
+        n, m, c = C.c_int64(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.mmc_last_eval_info(self.h, C.byref(n), C.byref(m), C.byref(c)))
+        return {"pairs_in_cutoff": n.value, "mode": ("cells", "tiles", "rows")[m.value] if m.value >= 0 else None,
+                "cells_per_dim": c.value}
+
     def measure_fp64_peak(self) -> float:
         t = C.c_double()
         self._ck(self.lib.mmc_measure_fp64_peak(self.h, C.byref(t)))
