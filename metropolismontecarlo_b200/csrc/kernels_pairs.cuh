@@ -20,6 +20,7 @@
 // to the literal per-pair vector1D (uniform branch on a device-side flag).
 #pragma once
 #include "mmc_common.cuh"
+#include "erf_poly.h"
 
 #define PAIR_BLOCK 256
 #define PAIR_WARPS (PAIR_BLOCK / 32)
@@ -43,7 +44,35 @@ struct PairArgs {
     unsigned int *ovl;         // [n_mol] overlap flags (index space of `com`)
     unsigned int *n_ovl;
     const double *max_dev;     // max |site - COM| component, written by k_gather
+    unsigned int *err_flag;    // set when a cell does not fit the fast kernel's tile
+    const int4 *units;         // fast kernel: {a_lo, b_lo, nA | nB<<16, self | codes<<1} per unit (k_units_build)
+    long long rclj_bits, rcqq_bits, cutlj_bits, cutqq_bits;   // bit patterns of r_cut² and r_cut²+100
+    ErfPoly ep;                // smooth part of erfc(κr)/r as one polynomial (deg 0: use erfc())
 };
+
+// ---- one Coulomb site pair: q_a q_b erfc(κ r)/r with the overlap rule (ewalds.jl:359-367).
+// Comparisons of non-negative doubles are done on their bit patterns (integer pipe) so the FP64
+// pipe only sees arithmetic.  POLY: erfc(κr)/r = 1/r − κ·E(κ²r²), E from the fitted polynomial.
+template <int DEG>   // DEG > 0: padded degree of the erf polynomial (compile time → straight DFMA run); 0: erfc()
+__device__ __forceinline__ bool coul_pair(const PairArgs &A, double r2, double qq, long long cut_bits, double &acc)
+{
+    const long long r2b = __double_as_longlong(r2);
+    if (r2b < 0x3FE0000000000000LL && __double2hiint(qq) < 0 && qq != 0.0) return true;   // r² < 0.5 && qq < 0
+    if (r2b < cut_bits) {
+        if (DEG > 0) {
+            const double rinv = rsqrt(r2);
+            const double sv = fma(r2 * A.ep.kappa2, A.ep.scale, -1.0);
+            double pv = A.ep.c[DEG];
+#pragma unroll
+            for (int k = DEG - 1; k >= 0; --k) pv = fma(pv, sv, A.ep.c[k]);   // coefficients: constant-bank operands
+            acc = fma(qq, fma(-A.ep.kappa, pv, rinv), acc);
+        } else {
+            const double r = sqrt(r2);
+            acc += qq * erfc(A.kappa * r) / r;
+        }
+    }
+    return false;
+}
 
 __constant__ int c_half_shell[14][3] = {
     {0, 0, 0},
@@ -75,6 +104,7 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
     const bool cells = (A.mode == 0);
     double rcmax = sqrt(fmax(A.rc_lj2, A.rc_qq2));
     const bool fast = cells && (rcmax + 2.0 * (*A.max_dev) < 0.5 * L);
+    const long long cut_bits = A.cutqq_bits;
 
     // static, contiguous share of this rank's units
     const long long n_units = A.unit_end - A.unit_begin;
@@ -169,13 +199,9 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
                             dz = min_image(sa.z, sb.z, L);
                         }
                         const double r2 = dx * dx + dy * dy + dz * dz;
-                        const double qq = sa.w * sb.w;
-                        if ((r2 < 0.5) && (qq < 0)) {                       // ewalds.jl:359
+                        if (coul_pair<0>(A, r2, sa.w * sb.w, cut_bits, acc[2])) {           // ewalds.jl:359
                             if (atomicExch(&A.ovl[a0 + p], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
                             if (atomicExch(&A.ovl[b0 + qi], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
-                        } else if (r2 < (A.rc_qq2 + 100)) {
-                            const double r = sqrt(r2);
-                            acc[2] += qq * erfc(A.kappa * r) / r;           // ewalds.jl:366-367
                         }
                     }
                 }
@@ -217,14 +243,240 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
     if (tid == 0) A.partial[blockIdx.x] = make_double4(accp[0], accp[1], accp[2], accp[3]);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_pairs_fast — the production variant for uniform S-site molecules whose cells fit one tile.
+// Same unit → gate → queue → site-pair scheme as k_pairs, plus:
+//   * units dealt round-robin (u = blockIdx.x + k·gridDim.x): cells of unequal population
+//     (27…64 molecules on the lattice start) average out across CTAs, still deterministic;
+//   * the two tiles of the NEXT unit stream into the other shared-memory buffer with cp.async
+//     (LDGSTS, 16 B per thread) while the current unit is evaluated: one barrier per unit and
+//     no exposed L2 latency;
+//   * 16-bit queue entries, reciprocal-multiply index math, bit-pattern compares.
+// A cell with more than TILE molecules raises err_flag; the host then re-runs k_pairs.
+// ------------------------------------------------------------------------------------------
+struct UnitDesc { int a_lo, b_lo, nA, nB, self; double shx, shy, shz; };
+
+__device__ __forceinline__ void unpack_unit(const int4 d, double L, UnitDesc &U)
+{
+    U.a_lo = d.x; U.b_lo = d.y; U.nA = d.z & 0xffff; U.nB = (d.z >> 16) & 0xffff; U.self = d.w & 1;
+    const int cx = (d.w >> 1) & 3, cy = (d.w >> 3) & 3, cz = (d.w >> 5) & 3;
+    U.shx = cx == 1 ? L : (cx == 2 ? -L : 0.0);
+    U.shy = cy == 1 ? L : (cy == 2 ? -L : 0.0);
+    U.shz = cz == 1 ? L : (cz == 2 ? -L : 0.0);
+}
+
+// one thread per unit: resolves (cell, slot) / (I, J) into tile ranges and wrap codes once per binning
+__global__ void k_units_build(PairArgs A, int4 *units, long long n_units)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    int a_lo, nA, b_lo, nB, self, code = 0;
+    if (A.mode == 0) {
+        const int c = (int)(u / 14), slot = (int)(u - 14 * (long long)c);
+        const int n = A.ncd;
+        const int cx = c % n, cy = (c / n) % n, cz = c / (n * n);
+        int nx = cx + c_half_shell[slot][0], ny = cy + c_half_shell[slot][1], nz = cz + c_half_shell[slot][2];
+        if (nx >= n) { nx -= n; code |= 1 << 0; } else if (nx < 0) { nx += n; code |= 2 << 0; }
+        if (ny >= n) { ny -= n; code |= 1 << 2; } else if (ny < 0) { ny += n; code |= 2 << 2; }
+        if (nz >= n) { nz -= n; code |= 1 << 4; } else if (nz < 0) { nz += n; code |= 2 << 4; }
+        const int cb = nx + n * (ny + n * nz);
+        a_lo = A.cell_start[c]; nA = A.cell_start[c + 1] - a_lo;
+        b_lo = A.cell_start[cb]; nB = A.cell_start[cb + 1] - b_lo;
+        self = (slot == 0);
+    } else {
+        long long r = u; int I = 0, rowlen = A.n_tiles;
+        while (r >= rowlen) { r -= rowlen; ++I; --rowlen; }
+        const int J = I + (int)r;
+        a_lo = I * PAIR_TILE; nA = min(A.n_mol, a_lo + PAIR_TILE) - a_lo;
+        b_lo = J * PAIR_TILE; nB = min(A.n_mol, b_lo + PAIR_TILE) - b_lo;
+        self = (I == J);
+    }
+    units[u] = make_int4(a_lo, b_lo, nA | (nB << 16), self | (code << 1));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+
+// gate + queue + Coulomb + LJ for one unit; WRAP: the unit crosses a periodic boundary
+template <int S, int TILE, int DEG, bool WRAP>
+__device__ __forceinline__ void pair_unit_body(const PairArgs &A, const UnitDesc &U, const double4 *s_comA,
+                                               const double4 *s_comB, const double4 *s_siteA, const double4 *s_siteB,
+                                               unsigned short *q, const LJActive *s_lj, int nlj, bool cells, bool fast,
+                                               int lane, int warp, double (&acc)[3], unsigned long long &my_pairs)
+{
+    constexpr int SS = S * S;
+    const double L = A.L;
+    const int nA = U.nA, nB = U.nB;
+    const double shx = U.shx, shy = U.shy, shz = U.shz;
+    // ---- (a) COM gate, warp-private ordered compaction
+    int npairs = 0;
+    const int ntests = nA * nB;
+    const unsigned inv_nB = nB > 0 ? (0xFFFFFFFFu / (unsigned)nB) + 1u : 0u;   // t/nB = umulhi(t, inv) for t < 2^16
+    for (int t0 = warp * 32; t0 < ntests; t0 += PAIR_BLOCK) {
+        const int t = t0 + lane;
+        int fl = 0, p = 0, qq_ = 0;
+        if (t < ntests) {
+            p = (int)__umulhi((unsigned)t, inv_nB); qq_ = t - p * nB;
+            if (!U.self || (U.b_lo + qq_ > U.a_lo + p)) {
+                const double4 ca = s_comA[p], cb = s_comB[qq_];
+                double dx, dy, dz;
+                if (cells) {
+                    dx = cb.x - ca.x; dy = cb.y - ca.y; dz = cb.z - ca.z;
+                    if (WRAP) { dx += shx; dy += shy; dz += shz; }
+                } else {
+                    dx = min_image(ca.x, cb.x, L); dy = min_image(ca.y, cb.y, L); dz = min_image(ca.z, cb.z, L);
+                }
+                const long long r2b = __double_as_longlong(dx * dx + dy * dy + dz * dz);
+                if (A.want_lj && r2b < A.rclj_bits) fl |= 1;
+                if (A.want_qq && r2b < A.rcqq_bits) fl |= 2;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, fl != 0);
+        if (fl) q[npairs + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(p | (qq_ << 7) | (fl << 14));
+        npairs += __popc(m);
+    }
+    if (lane == 0) my_pairs += npairs;
+    __syncwarp();
+    // ---- (b) Coulomb: S x S site pairs of the queued molecule pairs, one per lane.
+    // item w = pr*SS + ab advances by 32 per iteration: (pr, ab) are stepped incrementally.
+    if (A.want_qq) {
+        const int items = npairs * SS;
+        int pr = lane / SS, ab = lane - pr * SS;
+        constexpr int DP = 32 / SS, DA = 32 - DP * SS;
+        for (int w = lane; w < items; w += 32) {
+            const unsigned e = q[pr];
+            const int p = e & 127u, qi = (e >> 7) & 127u;
+            const int a = (S == 3) ? ((ab * 11) >> 5) : ab / S, b = ab - a * S;
+            const bool on = (e & (2u << 14)) != 0;
+            pr += DP; ab += DA;
+            if (ab >= SS) { ab -= SS; ++pr; }
+            if (!on) continue;
+            const double4 sa = s_siteA[p * S + a], sb = s_siteB[qi * S + b];
+            double dx, dy, dz;
+            if (fast) {
+                dx = sb.x - sa.x; dy = sb.y - sa.y; dz = sb.z - sa.z;
+                if (WRAP) { dx += shx; dy += shy; dz += shz; }
+            } else {
+                dx = min_image(sa.x, sb.x, L); dy = min_image(sa.y, sb.y, L); dz = min_image(sa.z, sb.z, L);
+            }
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            if (coul_pair<DEG>(A, r2, sa.w * sb.w, A.cutqq_bits, acc[2])) {                  // ewalds.jl:359
+                if (atomicExch(&A.ovl[U.a_lo + p], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
+                if (atomicExch(&A.ovl[U.b_lo + qi], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
+            }
+        }
+    }
+    // ---- (c) LJ: only the site-type combinations with ε_ij > 0.001 (energy.jl:270)
+    if (A.want_lj) {
+        const int items = npairs * nlj;
+        for (int w = lane; w < items; w += 32) {
+            const int pr = (nlj == 1) ? w : w / nlj, li = (nlj == 1) ? 0 : w - pr * nlj;
+            const unsigned e = q[pr];
+            if (!(e & (1u << 14))) continue;
+            const int p = e & 127u, qi = (e >> 7) & 127u;
+            const LJActive lj = s_lj[li];
+            const double4 sa = s_siteA[p * S + lj.a], sb = s_siteB[qi * S + lj.b];
+            const double4 ca = s_comA[p], cb = s_comB[qi];
+            double dx, dy, dz, rx, ry, rz;
+            if (cells) {
+                rx = cb.x - ca.x; ry = cb.y - ca.y; rz = cb.z - ca.z;
+                if (WRAP) { rx += shx; ry += shy; rz += shz; }
+            } else {
+                rx = min_image(ca.x, cb.x, L); ry = min_image(ca.y, cb.y, L); rz = min_image(ca.z, cb.z, L);
+            }
+            if (fast) {
+                dx = sb.x - sa.x; dy = sb.y - sa.y; dz = sb.z - sa.z;
+                if (WRAP) { dx += shx; dy += shy; dz += shz; }
+            } else {
+                dx = min_image(sa.x, sb.x, L); dy = min_image(sa.y, sb.y, L); dz = min_image(sa.z, sb.z, L);
+            }
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            if (__double_as_longlong(r2) < A.cutlj_bits)
+                lj_pair(lj.eps, lj.sig, r2, dx, dy, dz, rx, ry, rz, acc[0], acc[1]);
+        }
+    }
+}
+
+template <int ST, int TILE, int DEG>
+__global__ void __launch_bounds__(PAIR_BLOCK, (TILE <= 64 ? 4 : 2)) k_pairs_fast(const __grid_constant__ PairArgs A)
+{
+    constexpr int S = ST;
+    constexpr int QCAP = TILE * TILE / PAIR_WARPS;
+    constexpr int TILE_D4 = 2 * TILE + 2 * TILE * S;        // double4 per buffer: comA comB siteA siteB
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double4 *s_buf = reinterpret_cast<double4 *>(smem_raw);
+    unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_buf + 2 * TILE_D4);
+    __shared__ int4 s_unit[2];
+    __shared__ LJActive s_lj[64];
+    __shared__ double s_red[4 * PAIR_WARPS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned short *q = s_queue + warp * QCAP;
+    const int nlj = min(A.nlj, 64);
+    if (tid < nlj) s_lj[tid] = A.lj[tid];
+    const bool cells = (A.mode == 0);
+    const double rcmax = sqrt(fmax(A.rc_lj2, A.rc_qq2));
+    const bool fast = cells && (rcmax + 2.0 * (*A.max_dev) < 0.5 * A.L);
+
+    auto prefetch = [&](int b, long long u) {
+        int4 d = A.units[u];
+        int nA = d.z & 0xffff, nB = (d.z >> 16) & 0xffff;
+        if (nA > TILE || nB > TILE) { if (tid == 0) atomicExch(A.err_flag, 1u); nA = 0; nB = 0; d.z = 0; }
+        if (tid == 0) s_unit[b] = d;
+        double4 *base = s_buf + b * TILE_D4;
+        // 16-byte chunks: comA | comB | siteA | siteB
+        const char *gA = reinterpret_cast<const char *>(A.com + d.x), *gB = reinterpret_cast<const char *>(A.com + d.y);
+        const char *gSA = reinterpret_cast<const char *>(A.site + (size_t)d.x * S);
+        const char *gSB = reinterpret_cast<const char *>(A.site + (size_t)d.y * S);
+        char *dA = reinterpret_cast<char *>(base), *dB = reinterpret_cast<char *>(base + TILE);
+        char *dSA = reinterpret_cast<char *>(base + 2 * TILE), *dSB = reinterpret_cast<char *>(base + 2 * TILE + TILE * S);
+        for (int t = tid; t < 2 * nA; t += PAIR_BLOCK) cp_async16(dA + 16 * t, gA + 16 * t);
+        for (int t = tid; t < 2 * nB; t += PAIR_BLOCK) cp_async16(dB + 16 * t, gB + 16 * t);
+        for (int t = tid; t < 2 * nA * S; t += PAIR_BLOCK) cp_async16(dSA + 16 * t, gSA + 16 * t);
+        for (int t = tid; t < 2 * nB * S; t += PAIR_BLOCK) cp_async16(dSB + 16 * t, gSB + 16 * t);
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    double acc[3] = {0.0, 0.0, 0.0};
+    unsigned long long my_pairs = 0;
+    long long u = A.unit_begin + blockIdx.x;
+    int it = 0;
+    if (u < A.unit_end) prefetch(0, u);
+    for (; u < A.unit_end; u += gridDim.x, it ^= 1) {
+        asm volatile("cp.async.wait_all;\n" ::);
+        __syncthreads();                       // unit u has landed; everyone is done with unit u - G
+        if (u + gridDim.x < A.unit_end) prefetch(it ^ 1, u + gridDim.x);
+        UnitDesc U;
+        unpack_unit(s_unit[it], A.L, U);
+        const double4 *s_comA = s_buf + it * TILE_D4, *s_comB = s_comA + TILE;
+        const double4 *s_siteA = s_comA + 2 * TILE, *s_siteB = s_siteA + TILE * S;
+        if ((s_unit[it].w >> 1) != 0)
+            pair_unit_body<S, TILE, DEG, true>(A, U, s_comA, s_comB, s_siteA, s_siteB, q, s_lj, nlj, cells, fast, lane, warp, acc, my_pairs);
+        else
+            pair_unit_body<S, TILE, DEG, false>(A, U, s_comA, s_comB, s_siteA, s_siteB, q, s_lj, nlj, cells, fast, lane, warp, acc, my_pairs);
+    }
+    __syncthreads();
+    double accp[4] = {acc[0], acc[1], acc[2], (double)my_pairs};
+    block_sum<4, PAIR_BLOCK>(accp, s_red);
+    if (tid == 0) A.partial[blockIdx.x] = make_double4(accp[0], accp[1], accp[2], accp[3]);
+}
+
 // fold the per-CTA partials in CTA order into the head of the partial-sum vector:
 // out[0] = Σ lj_pot, out[1] = Σ lj_vir, out[2] = Σ coul (un-scaled), out[3] = #overlapped molecules
-__global__ void k_pair_reduce(const double4 *partial, int nb, const unsigned int *n_ovl, double *out)
+__global__ void k_pair_reduce(const double4 *partial, int nb, const unsigned int *n_ovl, const int *max_count,
+                              const unsigned int *err_flag, double *out)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ double4 s_p[1024];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_p[i] = partial[i];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-    for (int i = 0; i < nb; ++i) { const double4 p = partial[i]; a += p.x; b += p.y; c += p.z; d += p.w; }
+    for (int i = 0; i < nb; ++i) { const double4 p = s_p[i]; a += p.x; b += p.y; c += p.z; d += p.w; }
     out[0] = a; out[1] = b; out[2] = c; out[3] = (double)(*n_ovl); out[5] = d;
+    out[6] = (double)(*max_count); out[7] = (double)(*err_flag);
 }
 
 // ------------------------------------------------------------------ cell binning + gather
@@ -237,6 +489,7 @@ struct CellArgs {
     int *start;          // [ncell+1]
     int *fill;           // [ncell]  (zeroed)
     int *perm;           // [n_mol] sorted position -> molecule
+    int *max_count;      // largest cell population
 };
 
 __device__ __forceinline__ int cell_coord(double x, double inv_cell, int n)
@@ -264,8 +517,9 @@ __global__ void k_cell_scan(CellArgs A, int ncell)
     const int tid = threadIdx.x, nth = blockDim.x;
     const int per = (ncell + nth - 1) / nth;
     const int lo = tid * per, hi = min(ncell, lo + per);
-    int s = 0;
-    for (int i = lo; i < hi; ++i) s += A.count[i];
+    int s = 0, mx = 0;
+    for (int i = lo; i < hi; ++i) { const int c = A.count[i]; s += c; mx = max(mx, c); }
+    if (mx > 0) atomicMax(A.max_count, mx);
     s_part[tid] = s;
     __syncthreads();
     if (tid == 0) {

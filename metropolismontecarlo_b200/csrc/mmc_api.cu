@@ -77,6 +77,13 @@ struct mmc_handle {
     double *h_vec = nullptr;     // pinned
     int last_mode = -1;          // 0 cells, 1 tiles, 2 rows
     int last_ncd = 0;
+    int max_cell_cached = -1;    // largest cell population seen at the last binning (-1: unknown)
+    int *d_maxcount = nullptr;
+    int4 *d_units = nullptr;
+    long long units_cap = 0;
+    unsigned int *d_errflag = nullptr;
+    std::vector<std::pair<double, ErfPoly>> poly_cache;
+    int last_fast = 0;           // tile size of the fast pair kernel used last (0: general kernel)
     long long last_pairs = 0;    // molecule pairs inside the cutoff in the last evaluation (all ranks)
 
     // ---- volume trial
@@ -135,7 +142,9 @@ void free_system(mmc_handle *h)
     dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums);
     dfree(h->d_cell_of); dfree(h->d_count); dfree(h->d_start); dfree(h->d_fill); dfree(h->d_perm);
     dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl); dfree(h->d_novl);
-    dfree(h->d_maxdev); dfree(h->d_rhok_partial);
+    dfree(h->d_maxdev); dfree(h->d_rhok_partial); dfree(h->d_maxcount); dfree(h->d_errflag); dfree(h->d_units);
+    h->units_cap = 0;
+    h->max_cell_cached = -1;
     h->has_system = false;
 }
 
@@ -273,9 +282,46 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
     return MMC_OK;
 }
 
+// k_pairs_fast instantiations: water (3 sites) x tile {64, 128} x padded polynomial degree
+#define MMC_FOR_DEGS(X) X(0) X(8) X(12) X(16) X(20) X(24) X(32) X(44)
+void launch_pairs_fast(int tile, int deg, int grid, size_t smem, cudaStream_t st, const PairArgs &P)
+{
+#define X(D)                                                                                   \
+    if (deg == D) {                                                                            \
+        if (tile == 64) k_pairs_fast<3, 64, D><<<grid, PAIR_BLOCK, smem, st>>>(P);             \
+        else k_pairs_fast<3, 128, D><<<grid, PAIR_BLOCK, smem, st>>>(P);                       \
+        return;                                                                                \
+    }
+    MMC_FOR_DEGS(X)
+#undef X
+}
+void pairs_fast_set_attributes()
+{
+#define X(D)                                                                                                   \
+    cudaFuncSetAttribute(k_pairs_fast<3, 64, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);      \
+    cudaFuncSetAttribute(k_pairs_fast<3, 128, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    MMC_FOR_DEGS(X)
+#undef X
+}
+
+// smooth part of erfc(κr)/r on the domain r² < r_cut²+100 the reference imposes (ewalds.jl:362);
+// fits are cached on a geometric grid of domain ends so NPT box changes reuse them
+void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P)
+{
+    const double vg = erfpoly::grid_vmax(kappa * kappa * r2_max);
+    for (auto &e : h->poly_cache)
+        if (e.first == vg) { P = e.second; P.kappa = kappa; P.kappa2 = kappa * kappa; return; }
+    ErfPoly Q{};
+    Q.kappa = kappa; Q.kappa2 = kappa * kappa;
+    erfpoly::fit(vg, Q);
+    if (h->poly_cache.size() >= 32) h->poly_cache.erase(h->poly_cache.begin());
+    h->poly_cache.emplace_back(vg, Q);
+    P = Q;
+}
+
 // Leaves this rank's partial sums in d_vec: [0] Σlj_pot [1] Σlj_vir [2] Σcoul [3] #overlap
 // [MMC_NSCAL ..) ρ(k) partial (re,im).
-int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
+int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, bool force_general = false)
 {
     if (!h->uniform) FAIL(MMC_EINVAL, "pair kernel needs a uniform topology (internal)");
     const DevSystem &S = h->S;
@@ -289,6 +335,8 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     CK(cudaMemsetAsync(h->d_maxdev, 0, sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_novl, 0, sizeof(unsigned), h->stream));
     CK(cudaMemsetAsync(h->d_ovl, 0, sizeof(unsigned) * S.n_mol, h->stream));
+    CK(cudaMemsetAsync(h->d_errflag, 0, sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(h->d_maxcount, 0, sizeof(int), h->stream));
     if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
     const int tb = 256, gm = (S.n_mol + tb - 1) / tb;
     long long n_units;
@@ -305,12 +353,18 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         CK(cudaMemsetAsync(h->d_fill, 0, sizeof(int) * ncell, h->stream));
         // fractional COM coordinates are invariant under the volume scaling: bin the resident state
         CellArgs C{S.com, S.n_mol, ncd, (double)ncd / S.box, h->d_cell_of, h->d_count, h->d_start,
-                   h->d_fill, h->d_perm};
+                   h->d_fill, h->d_perm, h->d_maxcount};
         k_cell_count<<<gm, tb, 0, h->stream>>>(C); LAUNCH_CHECK();
         k_cell_scan<<<1, 1024, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
         k_cell_fill<<<gm, tb, 0, h->stream>>>(C); LAUNCH_CHECK();
         k_cell_sort<<<(ncell * 32 + tb - 1) / tb, tb, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
         n_units = 14LL * ncell;
+        if (h->max_cell_cached < 0 || E.world > 1) {   // unknown density (or sharded: no re-run possible)
+            int mc = 0;
+            CK(cudaMemcpyAsync(&mc, h->d_maxcount, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            h->max_cell_cached = mc;
+        }
     } else {
         const long long nt = (S.n_mol + PAIR_TILE - 1) / PAIR_TILE;
         n_units = nt * (nt + 1) / 2;
@@ -330,16 +384,44 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     P.want_lj = 1; P.want_qq = want_qq ? 1 : 0;
     P.nlj = (int)h->lj.size(); P.lj = h->d_lj;
     P.partial = h->d_pair_partial; P.ovl = h->d_ovl; P.n_ovl = h->d_novl; P.max_dev = h->d_maxdev;
+    P.err_flag = h->d_errflag;
+    P.rclj_bits = 0; P.rcqq_bits = 0; P.cutlj_bits = 0; P.cutqq_bits = 0;
+    { double v;
+      v = P.rc_lj2; std::memcpy(&P.rclj_bits, &v, 8); v = P.rc_qq2; std::memcpy(&P.rcqq_bits, &v, 8);
+      v = P.rc_lj2 + 100; std::memcpy(&P.cutlj_bits, &v, 8); v = P.rc_qq2 + 100; std::memcpy(&P.cutqq_bits, &v, 8); }
+    P.ep = ErfPoly{};
+    if (want_qq) get_erf_poly(h, E.kappa, S.rc_qq * S.rc_qq + 100, P.ep);
     const long long my_units = P.unit_end - P.unit_begin;
-    const int grid = (int)std::max(1LL, std::min<long long>(h->pair_grid, my_units));
-    const size_t smem = (2 * PAIR_TILE + 2 * PAIR_TILE * (size_t)US) * sizeof(double4) +
-                        (size_t)PAIR_WARPS * PAIR_QCAP * sizeof(unsigned);
+    const int max_cell = cells ? h->max_cell_cached : PAIR_TILE;
+    const int tile = (US == 3 && !force_general) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
+    int grid;
     if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-    if (US == 3) k_pairs<3><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
-    else k_pairs<0><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+    if (tile) {
+        if (n_units > h->units_cap) {
+            dfree(h->d_units);
+            CK(cudaMalloc(&h->d_units, sizeof(int4) * n_units));
+            h->units_cap = n_units;
+        }
+        P.units = h->d_units;
+        k_units_build<<<(unsigned)((n_units + 255) / 256), 256, 0, h->stream>>>(P, h->d_units, n_units);
+        LAUNCH_CHECK();
+        if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
+        const size_t smem = 2 * (2 * (size_t)tile + 2 * (size_t)tile * US) * sizeof(double4) +
+                            (size_t)tile * tile * sizeof(unsigned short);
+        grid = (int)std::max(1LL, std::min<long long>((tile == 64 ? 4 : 2) * h->sm_count, my_units));
+        launch_pairs_fast(tile, P.ep.deg, grid, smem, h->stream, P);
+    } else {
+        const size_t smem = (2 * PAIR_TILE + 2 * PAIR_TILE * (size_t)US) * sizeof(double4) +
+                            (size_t)PAIR_WARPS * PAIR_QCAP * sizeof(unsigned);
+        grid = (int)std::max(1LL, std::min<long long>(2 * h->sm_count, my_units));
+        if (US == 3) k_pairs<3><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+        else k_pairs<0><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+    }
     LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
-    k_pair_reduce<<<1, 32, 0, h->stream>>>(h->d_pair_partial, grid, h->d_novl, d_vec); LAUNCH_CHECK();
+    k_pair_reduce<<<1, 256, 0, h->stream>>>(h->d_pair_partial, grid, h->d_novl, h->d_maxcount, h->d_errflag, d_vec);
+    LAUNCH_CHECK();
+    h->last_fast = tile;
     h->last_mode = cells ? 0 : 1;
     h->last_ncd = ncd;
 
@@ -384,6 +466,10 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
     CK(cudaMemcpyAsync(h->h_vec, d_vec, MMC_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (h->tm.on) cudaEventRecord(h->tm.ev[6], h->stream);
     CK(cudaStreamSynchronize(h->stream));
+    if (E.world == 1) {
+        if (h->last_mode == 0) h->max_cell_cached = (int)h->h_vec[6];
+        if (h->h_vec[7] != 0.0) return 1;      // a cell outgrew the fast kernel's tile: caller re-runs
+    } else if (h->h_vec[7] != 0.0) FAIL(MMC_ESTATE, "cell overflow in a sharded evaluation (internal)");
     double lj_pot = h->h_vec[0], lj_vir = h->h_vec[1], coul = h->h_vec[2];
     const long long novl = (long long)h->h_vec[3];
     const double recip_raw = h->h_vec[4];
@@ -559,6 +645,7 @@ int mmc_create(const mmc_config *cfg, mmc_handle **out)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("event", e);
     cudaFuncSetAttribute(k_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_pairs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    pairs_fast_set_attributes();
     *out = h;
     return MMC_OK;
 }
@@ -669,11 +756,13 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         CK(cudaMalloc(&h->d_perm, sizeof(int) * n_mol));
         CK(cudaMalloc(&h->d_scom, sizeof(double4) * n_mol));
         CK(cudaMalloc(&h->d_ssite, sizeof(double4) * n_sites));
-        h->pair_grid = 2 * h->sm_count;
+        h->pair_grid = 4 * h->sm_count;
         CK(cudaMalloc(&h->d_pair_partial, sizeof(double4) * h->pair_grid));
         CK(cudaMalloc(&h->d_ovl, sizeof(unsigned) * n_mol));
         CK(cudaMalloc(&h->d_novl, sizeof(unsigned)));
         CK(cudaMalloc(&h->d_maxdev, sizeof(double)));
+        CK(cudaMalloc(&h->d_maxcount, sizeof(int)));
+        CK(cudaMalloc(&h->d_errflag, sizeof(unsigned)));
         h->ncell_cap = 0;
     }
     CK(cudaMalloc(&h->d_qsums, 2 * sizeof(double)));
@@ -990,6 +1079,11 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, 0, 1};
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
     rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
+    if (rc == 1) {
+        if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+        rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
+        if (rc == 1) FAIL(MMC_ECUDA, "pair kernel tile overflow persisted (internal)");
+    }
     if (style == MMC_STYLE_EWALD) h->new_valid = false;
     return rc;
 }
@@ -1096,7 +1190,13 @@ int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t st
     const double f = box_new / h->S.box;                                 // volumeChange.jl:62
     EvalCtx E{f, box_new, coul ? kappa_new : h->S.kappa, h->d_cfac_trial, 0, 1};
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
-    if ((rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out))) return rc;
+    rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
+    if (rc == 1) {
+        if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+        rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
+        if (rc == 1) FAIL(MMC_ECUDA, "pair kernel tile overflow persisted (internal)");
+    }
+    if (rc) return rc;
     h->vol_pending = true; h->vol_box = box_new; h->vol_kappa = E.kappa; h->vol_f = f; h->vol_style = style;
     return MMC_OK;
 }

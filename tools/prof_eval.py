@@ -1,0 +1,21 @@
+"""Minimal driver for ncu: upload config E (or --molecules N) and run a few full-energy evaluations."""
+import argparse, sys, time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from metropolismontecarlo_b200 import systems
+from metropolismontecarlo_b200.energy import water_engine
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--molecules", type=int, default=256000)
+ap.add_argument("--evals", type=int, default=4)
+ap.add_argument("--style", default="ewald")
+a = ap.parse_args()
+ms = systems.spce_lattice(a.molecules) if a.molecules != 750 else systems.load_nist(4)
+eng = water_engine(ms, 10.0)
+eng.set_timing(True)
+for k in range(a.evals):
+    t0 = time.perf_counter()
+    p = eng.potential(a.style)
+    dt = time.perf_counter() - t0
+    print(k, "E/N", p.energy / ms.n_mol, "wall ms", dt * 1e3, eng.last_timings(), eng.last_eval_info())
+eng.close()
