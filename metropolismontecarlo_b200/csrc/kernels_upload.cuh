@@ -1,0 +1,72 @@
+// kernels_upload.cuh — device-side conversion of the reference's Julia array layouts
+// (xyz-interleaved coords, Float64 charges, Int64 1-based atype / firstAtom /
+// lastAtom, COM) into the engine's HBM layout (double4 {x,y,z,q} per site, double4 COM, int2
+// {first, count}, int type), with the argument validation folded in.  The raw arrays are DMA'd
+// as they are (no host-side repacking pass); this kernel touches every byte once.
+#pragma once
+#include "mmc_common.cuh"
+
+struct RepackArgs {
+    const double *coords, *charge, *com;
+    const long long *atype, *first_atom, *last_atom;
+    int n_mol, n_sites, n_types;
+    double box;
+    double4 *site, *dcom;
+    int2 *mol;
+    int *dtype;
+    int *info;     // [0] error bits, [1] max sites per molecule, [2] non-uniform flag
+};
+
+enum { REPACK_BAD_ATYPE = 1, REPACK_BAD_RANGE = 2, REPACK_TOO_MANY_SITES = 4, REPACK_COM_OUTSIDE = 8 };
+
+__global__ void k_repack(RepackArgs A)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f0 = A.first_atom[0], l0 = A.last_atom[0];
+    const int US = (int)(l0 - f0 + 1);
+    if (t < A.n_sites) {
+        const long long ty = A.atype[t];
+        if (ty < 1 || ty > A.n_types) atomicOr(&A.info[0], REPACK_BAD_ATYPE);
+        A.dtype[t] = (int)(ty - 1);
+        A.site[t] = make_double4(A.coords[3 * (size_t)t], A.coords[3 * (size_t)t + 1], A.coords[3 * (size_t)t + 2], A.charge[t]);
+        if (US > 0 && ty != A.atype[t % US]) atomicOr(&A.info[2], 1);   // type sequence differs from molecule 1
+    }
+    if (t < A.n_mol) {
+        const long long f = A.first_atom[t], l = A.last_atom[t];
+        int cnt = 0;
+        if (f < 1 || l < f || l > A.n_sites) atomicOr(&A.info[0], REPACK_BAD_RANGE);
+        else {
+            cnt = (int)(l - f + 1);
+            if (cnt > MMC_MAX_SITES) atomicOr(&A.info[0], REPACK_TOO_MANY_SITES);
+        }
+        A.mol[t] = make_int2((int)(f - 1), cnt);
+        atomicMax(&A.info[1], cnt);
+        if (cnt != US || f - 1 != (long long)t * US) atomicOr(&A.info[2], 1);
+        const double x = A.com[3 * (size_t)t], y = A.com[3 * (size_t)t + 1], z = A.com[3 * (size_t)t + 2];
+        if (!(x >= 0.0 && x <= A.box && y >= 0.0 && y <= A.box && z >= 0.0 && z <= A.box))
+            atomicOr(&A.info[0], REPACK_COM_OUTSIDE);
+        A.dcom[t] = make_double4(x, y, z, 0.0);
+    }
+}
+
+// Σq and Σq² in two deterministic stages (EwaldSelf ewalds.jl:829-833, Wolf constants energy.jl:924-934)
+__global__ void __launch_bounds__(256) k_charge_partial(const double4 *site, int n, double2 *part)
+{
+    __shared__ double s_red[2 * 8];
+    double acc[2] = {0.0, 0.0};
+    for (int l = blockIdx.x * 256 + threadIdx.x; l < n; l += gridDim.x * 256) {
+        const double q = site[l].w;
+        acc[0] += q; acc[1] += q * q;
+    }
+    block_sum<2, 256>(acc, s_red);
+    if (threadIdx.x == 0) part[blockIdx.x] = make_double2(acc[0], acc[1]);
+}
+
+__global__ void __launch_bounds__(256) k_charge_final(const double2 *part, int nb, double *out)
+{
+    __shared__ double s_red[2 * 8];
+    double acc[2] = {0.0, 0.0};
+    for (int l = threadIdx.x; l < nb; l += 256) { acc[0] += part[l].x; acc[1] += part[l].y; }
+    block_sum<2, 256>(acc, s_red);
+    if (threadIdx.x == 0) { out[0] = acc[0]; out[1] = acc[1]; }
+}

@@ -4,6 +4,7 @@
 #include "kernels_move.cuh"
 #include "kernels_pairs.cuh"
 #include "kernels_recip.cuh"
+#include "kernels_upload.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -31,8 +32,12 @@ struct mmc_handle {
     bool has_system = false;
     DevSystem S{};
     std::vector<int2> h_mol;     // host mirror of S.mol
-    unsigned char *h_stage = nullptr;   // pinned staging for uploads (repacked AoS -> device layout)
-    size_t stage_bytes = 0;
+    unsigned char *d_raw = nullptr;     // device staging for the caller's arrays in their own layout
+    size_t raw_bytes = 0;
+    int cap_mol = 0, cap_sites = 0;     // sizes the resident buffers were allocated for
+    int *d_info = nullptr;
+    double2 *d_qpart = nullptr;
+    struct UploadResult { int info[4]; double qs[2]; } *h_up = nullptr;   // pinned
     bool uniform = false;        // every molecule: same site count, same type sequence, packed
     int US = 0;                  // uniform sites per molecule
     std::vector<LJActive> lj;
@@ -139,7 +144,8 @@ void dfree(T *&p)
 void free_system(mmc_handle *h)
 {
     dfree(h->S.site); dfree(h->S.com); dfree(h->S.mol); dfree(h->S.atype);
-    dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums);
+    dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums); dfree(h->d_raw); dfree(h->d_info); dfree(h->d_qpart);
+    h->raw_bytes = 0; h->cap_mol = 0; h->cap_sites = 0;
     dfree(h->d_cell_of); dfree(h->d_count); dfree(h->d_start); dfree(h->d_fill); dfree(h->d_perm);
     dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl); dfree(h->d_novl);
     dfree(h->d_maxdev); dfree(h->d_rhok_partial); dfree(h->d_maxcount); dfree(h->d_errflag); dfree(h->d_units);
@@ -212,6 +218,11 @@ int launch_move(mmc_handle *h, MoveArgs &A)
     k_move<<<blocks, MOVE_BLOCK, 0, h->stream>>>(h->S, A, h->W);
     LAUNCH_CHECK();
     return wait_out(h);
+}
+
+inline int2 mol_of(const mmc_handle *h, int64_t i0)
+{
+    return h->uniform ? make_int2((int)(i0 * h->US), h->US) : h->h_mol[i0];
 }
 
 int check_mol_index(mmc_handle *h, int64_t i)
@@ -658,7 +669,7 @@ int mmc_destroy(mmc_handle *h)
     free_system(h); free_ewald(h); free_atoms(h);
     dfree(h->W.partial); dfree(h->W.ticket);
     if (h->h_out) cudaFreeHost(h->h_out);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_up) cudaFreeHost(h->h_up);
     for (auto &ev : h->tm.ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -676,82 +687,28 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
     if (n_types < 1 || n_types > MMC_MAX_TYPES) FAIL(MMC_EINVAL, "n_types out of range (1..8)");
     if (!(box > 0) || !(rc_lj > 0) || !(rc_qq > 0)) FAIL(MMC_EINVAL, "box and cutoffs must be positive");
     CK(cudaSetDevice(h->cfg.device));
-    const bool had_ewald = h->has_ewald;
-    free_system(h);
-    // repack straight into pinned staging memory so the H2D copies are single DMA transfers
-    const size_t need = sizeof(double4) * (size_t)(n_sites + n_mol) + sizeof(int2) * (size_t)n_mol +
-                        sizeof(int) * (size_t)n_sites;
-    if (need > h->stage_bytes) {
-        if (h->h_stage) cudaFreeHost(h->h_stage);
-        h->h_stage = nullptr; h->stage_bytes = 0;
-        CK(cudaHostAlloc((void **)&h->h_stage, need, cudaHostAllocDefault));
-        h->stage_bytes = need;
-    }
-    double4 *hs = reinterpret_cast<double4 *>(h->h_stage);
-    double4 *hc = hs + n_sites;
-    int2 *hm = reinterpret_cast<int2 *>(hc + n_mol);
-    int *ht = reinterpret_cast<int *>(hm + n_mol);
-    int max_sites = 0;
-    bool uniform = true;
-    for (int64_t m = 0; m < n_mol; ++m) {
-        const int64_t f = first_atom[m], l = last_atom[m];
-        if (f < 1 || l < f || l > n_sites) FAIL(MMC_EINVAL, "first_atom/last_atom out of range");
-        const int cnt = (int)(l - f + 1);
-        if (cnt > MMC_MAX_SITES) FAIL(MMC_EINVAL, "more than 16 sites in a molecule");
-        hm[m] = make_int2((int)(f - 1), cnt);
-        max_sites = std::max(max_sites, cnt);
-        for (int k = 0; k < 3; ++k)
-            if (!(com[3 * m + k] >= 0.0 && com[3 * m + k] <= box))
-                FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
-        hc[m] = make_double4(com[3 * m], com[3 * m + 1], com[3 * m + 2], 0.0);
-    }
-    const int US = hm[0].y;
-    for (int64_t m = 0; m < n_mol && uniform; ++m) {
-        if (hm[m].y != US || hm[m].x != (int)(m * US)) uniform = false;
-    }
-    if ((int64_t)US * n_mol != n_sites) uniform = false;
-    for (int64_t s = 0; s < n_sites; ++s) {
-        if (atype[s] < 1 || atype[s] > n_types) FAIL(MMC_EINVAL, "atype out of range (1-based)");
-        ht[s] = (int)(atype[s] - 1);
-        hs[s] = make_double4(coords[3 * s], coords[3 * s + 1], coords[3 * s + 2], charge[s]);
-        if (uniform && ht[s] != ht[s % US]) uniform = false;
-    }
     DevSystem &S = h->S;
-    DevSystem keep = S;
-    S = DevSystem{};
-    if (had_ewald) {   // k-space tables survive a re-upload of coordinates
-        S.kappa = keep.kappa; S.factor = keep.factor; S.nk = keep.nk; S.nkvecs = keep.nkvecs;
-        S.kvec = keep.kvec; S.cfac = keep.cfac; S.rhok[0] = keep.rhok[0]; S.rhok[1] = keep.rhok[1];
-    }
-    S.n_mol = (int)n_mol; S.n_sites = (int)n_sites; S.max_sites = max_sites; S.n_types = n_types;
-    S.box = box; S.rc_lj = rc_lj; S.rc_qq = rc_qq;
-    for (int a = 0; a < n_types * n_types; ++a) { S.eps[a] = eps[a]; S.sig[a] = sig[a]; }
-    CK(cudaMalloc(&S.site, sizeof(double4) * n_sites));
-    CK(cudaMalloc(&S.com, sizeof(double4) * n_mol));
-    CK(cudaMalloc(&S.mol, sizeof(int2) * n_mol));
-    CK(cudaMalloc(&S.atype, sizeof(int) * n_sites));
-    CK(cudaMemcpyAsync(S.site, hs, sizeof(double4) * n_sites, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(S.com, hc, sizeof(double4) * n_mol, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(S.mol, hm, sizeof(int2) * n_mol, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(S.atype, ht, sizeof(int) * n_sites, cudaMemcpyHostToDevice, h->stream));
-    // LJ-active site-type combinations of the uniform molecule (ε_ij > 0.001, energy.jl:270)
-    h->lj.clear();
-    if (uniform)
-        for (int a = 0; a < US; ++a)
-            for (int b = 0; b < US; ++b) {
-                const double e_ = eps[ht[a] + ht[b] * n_types];
-                if (e_ > 0.001) h->lj.push_back(LJActive{a, b, e_, sig[ht[a] + ht[b] * n_types]});
-            }
-    if (h->lj.size() > 64) uniform = false;
-    h->uniform = uniform; h->US = uniform ? US : 0;
-    if (uniform) {
-        std::vector<int2> um(n_mol);
-        for (int64_t m = 0; m < n_mol; ++m) um[m] = make_int2((int)(m * US), US);
+    const bool realloc_needed = !h->has_system || h->cap_mol != (int)n_mol || h->cap_sites != (int)n_sites;
+    if (realloc_needed) {
+        const DevSystem keep = S;
+        const bool had_ewald = h->has_ewald;
+        free_system(h);
+        S = DevSystem{};
+        if (had_ewald) {   // k-space tables survive a re-upload of coordinates
+            S.kappa = keep.kappa; S.factor = keep.factor; S.nk = keep.nk; S.nkvecs = keep.nkvecs;
+            S.kvec = keep.kvec; S.cfac = keep.cfac; S.rhok[0] = keep.rhok[0]; S.rhok[1] = keep.rhok[1];
+        }
+        CK(cudaMalloc(&S.site, sizeof(double4) * n_sites));
+        CK(cudaMalloc(&S.com, sizeof(double4) * n_mol));
+        CK(cudaMalloc(&S.mol, sizeof(int2) * n_mol));
+        CK(cudaMalloc(&S.atype, sizeof(int) * n_sites));
+        h->raw_bytes = sizeof(double) * (size_t)(4 * n_sites + 3 * n_mol) + sizeof(int64_t) * (size_t)(n_sites + 2 * n_mol);
+        CK(cudaMalloc(&h->d_raw, h->raw_bytes));
+        CK(cudaMalloc(&h->d_info, 4 * sizeof(int)));
+        CK(cudaMalloc(&h->d_qpart, 256 * sizeof(double2)));
+        CK(cudaMalloc(&h->d_qsums, 2 * sizeof(double)));
         CK(cudaMalloc(&h->d_mol_uniform, sizeof(int2) * n_mol));
-        CK(cudaMemcpyAsync(h->d_mol_uniform, um.data(), sizeof(int2) * n_mol, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMalloc(&h->d_lj, sizeof(LJActive) * std::max<size_t>(1, h->lj.size())));
-        if (!h->lj.empty())
-            CK(cudaMemcpyAsync(h->d_lj, h->lj.data(), sizeof(LJActive) * h->lj.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMalloc(&h->d_lj, sizeof(LJActive) * 64));
         CK(cudaMalloc(&h->d_cell_of, sizeof(int) * n_mol));
         CK(cudaMalloc(&h->d_perm, sizeof(int) * n_mol));
         CK(cudaMalloc(&h->d_scom, sizeof(double4) * n_mol));
@@ -763,17 +720,72 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         CK(cudaMalloc(&h->d_maxdev, sizeof(double)));
         CK(cudaMalloc(&h->d_maxcount, sizeof(int)));
         CK(cudaMalloc(&h->d_errflag, sizeof(unsigned)));
-        h->ncell_cap = 0;
+        h->ncell_cap = 0; h->rhok_grid_cap = 0;
+        h->cap_mol = (int)n_mol; h->cap_sites = (int)n_sites;
+        if (!h->h_up) CK(cudaHostAlloc((void **)&h->h_up, sizeof(*h->h_up), cudaHostAllocDefault));
     }
-    CK(cudaMalloc(&h->d_qsums, 2 * sizeof(double)));
-    k_charge_sums<<<1, 256, 0, h->stream>>>(S.site, (int)n_sites, h->d_qsums);
+    h->has_system = false;
+    // ---- DMA the caller's arrays as they are (pinned sources go at full PCIe rate), repack on the device
+    unsigned char *r = h->d_raw;
+    double *d_coords = reinterpret_cast<double *>(r); r += sizeof(double) * 3 * n_sites;
+    double *d_charge = reinterpret_cast<double *>(r); r += sizeof(double) * n_sites;
+    double *d_com = reinterpret_cast<double *>(r); r += sizeof(double) * 3 * n_mol;
+    long long *d_atype = reinterpret_cast<long long *>(r); r += sizeof(int64_t) * n_sites;
+    long long *d_first = reinterpret_cast<long long *>(r); r += sizeof(int64_t) * n_mol;
+    long long *d_last = reinterpret_cast<long long *>(r);
+    CK(cudaMemcpyAsync(d_coords, coords, sizeof(double) * 3 * n_sites, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_charge, charge, sizeof(double) * n_sites, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_atype, atype, sizeof(int64_t) * n_sites, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_first, first_atom, sizeof(int64_t) * n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_last, last_atom, sizeof(int64_t) * n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
+    RepackArgs R{d_coords, d_charge, d_com, d_atype, d_first, d_last, (int)n_mol, (int)n_sites, n_types, box,
+                 S.site, S.com, S.mol, S.atype, h->d_info};
+    k_repack<<<(unsigned)((n_sites + 255) / 256), 256, 0, h->stream>>>(R);
     LAUNCH_CHECK();
-    double qs[2];
-    CK(cudaMemcpyAsync(qs, h->d_qsums, sizeof(qs), cudaMemcpyDeviceToHost, h->stream));
+    const int qb = (int)std::min<int64_t>(256, (n_sites + 255) / 256);
+    k_charge_partial<<<qb, 256, 0, h->stream>>>(S.site, (int)n_sites, h->d_qpart); LAUNCH_CHECK();
+    k_charge_final<<<1, 256, 0, h->stream>>>(h->d_qpart, qb, h->d_qsums); LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_up->qs, h->d_qsums, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->sum_q = qs[0]; h->sum_q2 = qs[1];
-    h->rhok_grid_cap = 0;
-    h->h_mol.assign(hm, hm + n_mol);
+    const int err = h->h_up->info[0];
+    if (err & REPACK_BAD_ATYPE) FAIL(MMC_EINVAL, "atype out of range (1-based)");
+    if (err & REPACK_BAD_RANGE) FAIL(MMC_EINVAL, "first_atom/last_atom out of range");
+    if (err & REPACK_TOO_MANY_SITES) FAIL(MMC_EINVAL, "more than 16 sites in a molecule");
+    if (err & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
+    S.n_mol = (int)n_mol; S.n_sites = (int)n_sites; S.max_sites = h->h_up->info[1]; S.n_types = n_types;
+    S.box = box; S.rc_lj = rc_lj; S.rc_qq = rc_qq;
+    for (int a = 0; a < n_types * n_types; ++a) { S.eps[a] = eps[a]; S.sig[a] = sig[a]; }
+    h->sum_q = h->h_up->qs[0]; h->sum_q2 = h->h_up->qs[1];
+    bool uniform = h->h_up->info[2] == 0;
+    const int US = (int)(last_atom[0] - first_atom[0] + 1);
+    // LJ-active site-type combinations of the uniform molecule (ε_ij > 0.001, energy.jl:270)
+    h->lj.clear();
+    if (uniform)
+        for (int a = 0; a < US; ++a)
+            for (int b = 0; b < US; ++b) {
+                const int ta = (int)atype[a] - 1, tb = (int)atype[b] - 1;
+                const double e_ = eps[ta + tb * n_types];
+                if (e_ > 0.001) h->lj.push_back(LJActive{a, b, e_, sig[ta + tb * n_types]});
+            }
+    if (h->lj.size() > 64) uniform = false;
+    h->uniform = uniform; h->US = uniform ? US : 0;
+    h->h_mol.clear();
+    if (uniform) {
+        if (realloc_needed || true) {
+            // packed {m*US, US}: identical to S.mol for a uniform topology
+            CK(cudaMemcpyAsync(h->d_mol_uniform, S.mol, sizeof(int2) * n_mol, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        if (!h->lj.empty())
+            CK(cudaMemcpyAsync(h->d_lj, h->lj.data(), sizeof(LJActive) * h->lj.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } else {
+        h->h_mol.resize(n_mol);
+        for (int64_t m = 0; m < n_mol; ++m) h->h_mol[m] = make_int2((int)(first_atom[m] - 1), (int)(last_atom[m] - first_atom[m] + 1));
+    }
+    h->max_cell_cached = -1;
     h->has_system = true;
     h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
     return MMC_OK;
@@ -931,7 +943,7 @@ int mmc_set_molecule(mmc_handle *h, int64_t i, const double com[3], const double
     if (!com || !sites) FAIL(MMC_EINVAL, "null array");
     MoveArgs A{};
     A.i = (int)(i - 1);
-    std::memcpy(A.site_new, sites, sizeof(double) * 3 * h->h_mol[i - 1].y);
+    std::memcpy(A.site_new, sites, sizeof(double) * 3 * mol_of(h, i - 1).y);
     k_set_molecule<<<1, 32, 0, h->stream>>>(h->S, A.i, com[0], com[1], com[2], A);
     LAUNCH_CHECK();
     h->trial_pending = false;
@@ -1103,7 +1115,7 @@ int mmc_trial_move(mmc_handle *h, int64_t i, const double com_new[3], const doub
     A.recip_blocks = (style == MMC_STYLE_EWALD) ? (h->S.nkvecs + MOVE_BLOCK - 1) / MOVE_BLOCK : 0;
     A.cur = h->cur;
     A.com_new[0] = com_new[0]; A.com_new[1] = com_new[1]; A.com_new[2] = com_new[2];
-    std::memcpy(A.site_new, sites_new, sizeof(double) * 3 * h->h_mol[i - 1].y);
+    std::memcpy(A.site_new, sites_new, sizeof(double) * 3 * mol_of(h, i - 1).y);
     if ((rc = launch_move(h, A))) return rc;
     const MoveOut &o = *h->h_out;
     const double factor = h->S.factor;

@@ -79,7 +79,7 @@ extern "C" int mmc_loop_run(mmc_handle *h, const mmc_loop_params *p, double *com
     int ret = 0;
     for (int64_t m = 0; m < n_moves; ++m) {
         const int i = (int)(m % n_mol);                  // sweep order i = 1..N (main.jl:490)
-        const int2 mi = h->h_mol[i];
+        const int2 mi = mol_of(h, i);
         double rnew[3] = {com[3 * i], com[3 * i + 1], com[3 * i + 2]};
         double ei[4];
         const double chose_move = us.next();             // main.jl:516
