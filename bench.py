@@ -203,7 +203,11 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream()
+    # One explicit (non-default) stream for everything: the engine's kernels, torch's NCCL
+    # all-reduce and the timing events are all ordered on it.  (A NULL stream in mmc_config means
+    # "the handle's own stream", so torch's legacy default stream cannot be shared.)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng = Engine(device=local_rank, rank=rank, world=world, stream=stream.cuda_stream)
     ms = systems.spce_lattice(args.molecules)
     eng.upload_system(ms, RC, RC)
@@ -212,11 +216,10 @@ def run_ours(args, rank, world, local_rank):
     vec = torch.zeros(nvec, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def step():
-        eng.potential_partial("ewald", vec.data_ptr())
-        if world > 1:
-            dist.all_reduce(vec)                       # NCCL over NVLink: 8 scalars + 337 complex rho(k)
-        return eng.potential_finalize("ewald", vec.data_ptr())
+    from metropolismontecarlo_b200.sharding import sharded_potential
+
+    def step():   # partial -> NCCL all-reduce over NVLink (8 scalars + 337 complex rho(k)) -> finalize
+        return sharded_potential(eng, "ewald", vec, world)
 
     def barrier():
         if world > 1:

@@ -1,0 +1,120 @@
+# MMCB200.jl — Julia binding of libmmc_b200.so (include/mmc_b200.h) for the reference driver
+# (BradenDKelly/MetropolisMonteCarlo, Ewald/main.jl).  UNTESTED HERE: Julia is not installed in
+# the build image; the same C ABI is exercised through Python ctypes (metropolismontecarlo_b200/
+# _lib.py) by the parity tests.  Memory layouts are the reference's own (SURVEY.md A.6): pointers
+# to soa.coords / moa.COM (Vector{SVector{3,Float64}}) are passed as Ptr{Float64} with no copy.
+module MMCB200
+
+const LIB = get(ENV, "MMC_B200_LIB", "libmmc_b200")
+const EWALD, WOLF, LJ_ONLY, LJ_ATOMS = Cint(0), Cint(1), Cint(2), Cint(3)
+
+struct Config
+    device::Cint; rank::Cint; world::Cint; sync_mode::Cint; stream::Ptr{Cvoid}
+end
+
+mutable struct Props            # mmc_properties  (Properties of Ewald/auxillary.jl:37-45 + components)
+    energy::Cdouble; virial::Cdouble; coulomb::Cdouble
+    lj::Cdouble; real::Cdouble; recip::Cdouble; self::Cdouble; wolf_const::Cdouble
+    overlaps::Int64
+    Props() = new(0, 0, 0, 0, 0, 0, 0, 0, 0)
+end
+
+mutable struct TrialResult      # mmc_trial_result
+    lj_old::Cdouble; lj_vir_old::Cdouble; lj_new::Cdouble; lj_vir_new::Cdouble
+    qq_old::Cdouble; qq_vir_old::Cdouble; qq_new::Cdouble; qq_vir_new::Cdouble
+    d_recip::Cdouble; overlap_old::Cint; overlap_new::Cint
+    TrialResult() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+end
+
+struct Engine
+    h::Ptr{Cvoid}
+end
+
+function check(e::Engine, rc::Cint)
+    rc < 0 && error("libmmc_b200: " * unsafe_string(ccall((:mmc_last_error, LIB), Cstring, (Ptr{Cvoid},), e.h)))
+    rc
+end
+
+function Engine(; device = 0, rank = 0, world = 1, sync_mode = 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    cfg = Ref(Config(device, rank, world, sync_mode, C_NULL))
+    rc = ccall((:mmc_create, LIB), Cint, (Ref{Config}, Ref{Ptr{Cvoid}}), cfg, h)
+    rc != 0 && error("mmc_create: " * unsafe_string(ccall((:mmc_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    Engine(h[])
+end
+destroy(e::Engine) = ccall((:mmc_destroy, LIB), Cint, (Ptr{Cvoid},), e.h)
+
+# soa, moa, vdwTable exactly as main.jl holds them (MakeAtomArrays "kmc", MakeTables)
+function upload!(e::Engine, soa, moa, vdwTable, box, rc_lj, rc_qq)
+    nt = size(vdwTable.ϵᵢⱼ, 1)
+    check(e, ccall((:mmc_upload_system, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
+         Cint, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cdouble),
+        e.h, length(moa), length(soa), pointer(soa.coords), pointer(soa.charge), pointer(soa.atype),
+        pointer(moa.firstAtom), pointer(moa.lastAtom), pointer(moa.COM), nt,
+        pointer(vdwTable.ϵᵢⱼ), pointer(vdwTable.σᵢⱼ), box, rc_lj, rc_qq))
+end
+
+# PrepareEwaldVariables(ewald, box)  — Ewald/ewalds.jl:45-103
+function prepare_ewald!(e::Engine, kappa, nk, k_sq_max, factor)
+    n = Ref{Cint}(0)
+    check(e, ccall((:mmc_ewald_prepare, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cint, Cint, Cdouble, Ref{Cint}),
+                   e.h, kappa, nk, k_sq_max, factor, n))
+    Int(n[])
+end
+
+# LJ_poly_ΔU(i, moa, soa, vdwTable, r_cut, box)  — Ewald/energy.jl:209-290
+function LJ_poly_ΔU(e::Engine, i::Int)
+    p = Ref{Cdouble}(0); v = Ref{Cdouble}(0)
+    check(e, ccall((:mmc_lj_mol, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Cdouble}, Ref{Cdouble}), e.h, i, p, v))
+    p[], v[]
+end
+
+# EwaldShort(i, moa, soa, sim_props, ewald, box)  — Ewald/ewalds.jl:892-910
+function EwaldShort(e::Engine, i::Int)
+    en = Ref{Cdouble}(0); v = Ref{Cdouble}(0); o = Ref{Cint}(0)
+    check(e, ccall((:mmc_ewald_short, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Cdouble}, Ref{Cdouble}, Ref{Cint}), e.h, i, en, v, o))
+    en[], v[], o[] != 0
+end
+
+# RecipMove(box, ewald, r_old, r_new, q)  — Ewald/ewalds.jl:718-826
+function RecipMove(e::Engine, r_old::Vector, r_new::Vector, q::Vector{Float64})
+    d = Ref{Cdouble}(0)
+    check(e, ccall((:mmc_recip_move, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ref{Cdouble}),
+                   e.h, pointer(r_old), pointer(r_new), pointer(q), length(q), d))
+    d[]
+end
+recip_commit!(e::Engine) = check(e, ccall((:mmc_recip_commit, LIB), Cint, (Ptr{Cvoid},), e.h))     # main.jl:621
+recip_rollback!(e::Engine) = check(e, ccall((:mmc_recip_rollback, LIB), Cint, (Ptr{Cvoid},), e.h)) # main.jl:628
+
+# in-place writes of main.jl:527,552 / 623-624
+set_molecule!(e::Engine, i::Int, com, sites::Vector) =
+    check(e, ccall((:mmc_set_molecule, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), e.h, i, Ref(com), pointer(sites)))
+
+# potential(moa, soa, tot, ewald, vdwTable, sim_props[, "ewald"])  — Ewald/energy.jl:864-1032
+function potential(e::Engine, style::Cint = EWALD)
+    p = Props()
+    check(e, ccall((:mmc_potential, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Props}), e.h, style, p))
+    p
+end
+
+# fused fast path: the five calls of Loop (main.jl:491-590) in one launch
+function trial_move(e::Engine, i::Int, com_new, sites_new::Vector, style::Cint = EWALD)
+    r = TrialResult()
+    check(e, ccall((:mmc_trial_move, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Ref{TrialResult}),
+                   e.h, i, Ref(com_new), pointer(sites_new), style, r))
+    r
+end
+accept!(e::Engine) = check(e, ccall((:mmc_accept, LIB), Cint, (Ptr{Cvoid},), e.h))
+reject!(e::Engine) = check(e, ccall((:mmc_reject, LIB), Cint, (Ptr{Cvoid},), e.h))
+
+# Ewald/volumeChange.jl:50-147
+function volume_trial(e::Engine, box_new, kappa_new, style::Cint = EWALD)
+    p = Props()
+    check(e, ccall((:mmc_volume_trial, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cint, Ref{Props}), e.h, box_new, kappa_new, style, p))
+    p
+end
+volume_accept!(e::Engine) = check(e, ccall((:mmc_volume_accept, LIB), Cint, (Ptr{Cvoid},), e.h))
+volume_reject!(e::Engine) = check(e, ccall((:mmc_volume_reject, LIB), Cint, (Ptr{Cvoid},), e.h))
+
+end # module

@@ -1,0 +1,32 @@
+"""Host-side plumbing of the sharded full-energy path: one process per GPU,
+replicated coordinates, pair work units and ρ(k) sites split per rank, ONE all-reduce of the
+partial-sum vector, every rank finalises.
+
+Partial-sum vector layout (mmc_partial_count doubles, see csrc/mmc_common.cuh MMC_NSCAL):
+  [0] Σ lj_pot  [1] Σ lj_vir  [2] Σ coulomb (un-scaled)  [3] #overlapped molecules
+  [4] E_recip (filled by finalize)  [5] #pairs in cutoff  [6], [7] internal
+  [8 + 2k], [9 + 2k]  Re, Im of this rank's ρ(k) partial
+"""
+from __future__ import annotations
+
+NSCAL = 8
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous share [lo, hi) of n items for `rank` — the same integer formula the library uses
+    for pair units and for sites (mmc_api.cu: n * rank / world)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def partial_len(nkvecs: int) -> int:
+    return NSCAL + 2 * max(nkvecs, 1)
+
+
+def sharded_potential(eng, style, vec, world: int, group=None):
+    """partial → all-reduce (NCCL over NVLink when vec is a CUDA tensor) → finalize.
+    `vec` must live on the stream the engine was created with."""
+    eng.potential_partial(style, vec.data_ptr())
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(vec, group=group)
+    return eng.potential_finalize(style, vec.data_ptr())
