@@ -298,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
             "energy_per_molecule_K": props.energy / ms.n_mol,
             "pairs_in_cutoff": pairs, "path": info["mode"], "cells_per_dim": info["cells_per_dim"],
             "kernel_ms": {"pairs": float(np.mean(pair_ms)), "rhok_rebuild": float(np.mean(rhok_ms))},
-            "roofline": {"bound": "fp64", "kernel": "k_pairs<3>", "achieved": achieved, "peak": fp64_peak,
+            "roofline": {"bound": "fp64", "kernel": info["pair_kernel"], "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "peak_source": "live DFMA-chain probe on this GPU (MEASURED_PEAKS.json has no FP64 figure); "
                                         "nominal 37.2 TFLOP/s at 1965 MHz",

@@ -141,6 +141,10 @@ int mmc_partial_count(mmc_handle *h, int64_t *n_doubles);
 int mmc_potential_partial(mmc_handle *h, int32_t style, double *d_partials);
 int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partials,
                            mmc_properties *out);
+/* mmc_potential_finalize may return MMC_RETRY (1): the pair kernel chosen for the partial pass
+ * declined the state (e.g. a cell denser than its tile); the library has already switched to the
+ * next kernel on every rank — repeat mmc_potential_partial, the all-reduce and finalize. */
+#define MMC_RETRY 1
 
 /* ---- fused fast path: one launch, one host sync per trial move ------------------------- */
 /* Same numbers as mmc_lj_mol + mmc_ewald_short (old), mmc_set_molecule, mmc_lj_mol +
@@ -204,9 +208,10 @@ int mmc_get_counters(mmc_handle *h, mmc_counters *out);
 int mmc_set_timing(mmc_handle *h, int32_t enabled);
 int mmc_last_timings(mmc_handle *h, float *ms4);
 /* what the last full-energy evaluation did: molecule pairs inside the cutoff (summed over ranks
- * after finalize), path taken (0 = cell list, 1 = tile pairs, 2 = per-molecule rows) and cells per
- * box edge */
-int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, int32_t *cells_per_dim);
+ * after finalize), path taken (0 = cell list, 1 = tile pairs, 2 = per-molecule rows), cells per
+ * box edge, and the pair kernel used (3 = k_pairs_v3, 64/128 = k_pairs_fast tile, 0 = k_pairs) */
+int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, int32_t *cells_per_dim,
+                       int32_t *pair_kernel);
 /* FP64 DFMA-chain microbenchmark: measured FP64 FMA throughput of the device [TFLOP/s] */
 int mmc_measure_fp64_peak(mmc_handle *h, double *tflops);
 

@@ -47,6 +47,7 @@ struct PairArgs {
     unsigned int *err_flag;    // set when a cell does not fit the fast kernel's tile
     const int4 *units;         // fast kernel: {a_lo, b_lo, nA | nB<<16, self | codes<<1} per unit (k_units_build)
     long long rclj_bits, rcqq_bits, cutlj_bits, cutqq_bits;   // bit patterns of r_cut² and r_cut²+100
+    double lj_eps_tab[16], lj_sig_tab[16];   // v3: LJ table by (site a, site b) of the uniform molecule, 0 = inactive
     ErfPoly ep;                // smooth part of erfc(κr)/r as one polynomial (deg 0: use erfc())
 };
 

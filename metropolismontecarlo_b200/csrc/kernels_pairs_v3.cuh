@@ -1,0 +1,214 @@
+// kernels_pairs_v3.cuh — production pair kernel for cell mode with uniform 3-site molecules.
+//
+// Same physics and reference semantics as kernels_pairs.cuh (COM gate, 9 erfc site pairs, O–O LJ,
+// overlap flags), restructured around what the profiler showed on the first two versions: the
+// kernel is issue bound, not FP64-pipe bound, so the design minimises instructions per site pair.
+//
+//   unit   = (home cell, group of 5/5/4 half-shell slots): the home cell's ≤64 molecules (A) and
+//            the group's ≤320 neighbour molecules (B) are staged in shared memory once, B already
+//            translated by its slot's periodic shift (±L), so no wrap logic survives in the loops;
+//   gate   = warp w owns rows p ≡ w (mod 8) of A; each lane keeps one B molecule's COM in
+//            registers per 32-wide column block and tests it against the warp's rows with one
+//            broadcast shared-memory load per row: ≈0.7 instructions per COM test;
+//   queue  = survivors (p, q) go to a warp-private queue by ballot/popc (deterministic order) and
+//            are consumed in FULL rounds of 32 molecule pairs; only the last round of a unit is
+//            partial (≈94 % lane utilisation);
+//   pair   = one lane evaluates one molecule pair: 6 sites in registers, 9 site pairs unrolled —
+//            nine independent rsqrt + polynomial chains per lane (ILP instead of occupancy) and no
+//            per-site-pair index arithmetic.
+// B is stored pre-shifted: d = (x_b ± L) − x_a instead of the reference's (x_b − x_a) ± L; the two
+// differ by one rounding of a ~200 Å number (3e-14 Å), far inside the 1e-10 energy bound.
+#pragma once
+#include "kernels_pairs.cuh"
+
+#define V3_ACAP 64
+#define V3_SLOTS 5
+#define V3_BCAP (V3_SLOTS * V3_ACAP)
+#define V3_QCAP 512    // ring buffer per warp (power of two): ≤ 31 left-overs + 8 rows x 32 new entries
+#define V3_GROUPS 3
+
+__constant__ int c_v3_group_begin[V3_GROUPS + 1] = {0, 5, 10, 14};
+
+// per (cell, slot): where the neighbour cell's molecules are and how they are shifted
+__global__ void k_slots_build(PairArgs A, int4 *slots, int ncell)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell * 14) return;
+    const int c = t / 14, slot = t - 14 * c;
+    const int n = A.ncd;
+    const int cx = c % n, cy = (c / n) % n, cz = c / (n * n);
+    int nx = cx + c_half_shell[slot][0], ny = cy + c_half_shell[slot][1], nz = cz + c_half_shell[slot][2];
+    int code = 0;
+    if (nx >= n) { nx -= n; code |= 1 << 0; } else if (nx < 0) { nx += n; code |= 2 << 0; }
+    if (ny >= n) { ny -= n; code |= 1 << 2; } else if (ny < 0) { ny += n; code |= 2 << 2; }
+    if (nz >= n) { nz -= n; code |= 1 << 4; } else if (nz < 0) { nz += n; code |= 2 << 4; }
+    const int cb = nx + n * (ny + n * nz);
+    const int b_lo = A.cell_start[cb];
+    slots[t] = make_int4(b_lo, A.cell_start[cb + 1] - b_lo, code, 0);
+}
+
+// MUFU.RSQ64H seed + one cubic Newton step (relative error ≈ 1e-19·… → correctly rounded to ~1 ulp for
+// normal positive r²; r² = 0 gives +inf like 1/sqrt(0)): the CUDA rsqrt() sequence without its
+// special-value slow path, which this kernel never needs.
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(x, -(y0 * y0), 1.0);
+    return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+}
+
+// Specialisation served here (everything else goes to k_pairs_fast / k_pairs):
+//   3-site molecules whose only LJ-active site pair is (0,0) (water models: SPC/E, TIP3P),
+//   r_cut(LJ) == r_cut(qq), Coulomb on (EWALD/WOLF), a usable erf polynomial (DEG > 0), and
+//   (r_cut + 2·max|site−COM|)² < r_cut² + 100 so that the reference's `rab2 < r_cut_sq + 100`
+//   tests (energy.jl:270, ewalds.jl:362) are provably always true — the kernel re-checks this on
+//   the device and raises err_flag otherwise.
+template <int DEG>
+__global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs_v3(const __grid_constant__ PairArgs A, const int4 *__restrict__ slots)
+{
+    constexpr int S = 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double4 *s_comA = reinterpret_cast<double4 *>(smem_raw);
+    double4 *s_siteA = s_comA + V3_ACAP;
+    double4 *s_comB = s_siteA + V3_ACAP * S;
+    double4 *s_siteB = s_comB + V3_BCAP;
+    unsigned *s_queue = reinterpret_cast<unsigned *>(s_siteB + V3_BCAP * S);
+    __shared__ int s_boff[V3_SLOTS + 1], s_bglob[V3_SLOTS];
+    __shared__ double s_red[4 * PAIR_WARPS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned *q = s_queue + warp * V3_QCAP;
+    const double L = A.L;
+    {   // the always-true cut-off tests must really be always true for this state
+        const double reach = sqrt(A.rc_qq2) + 2.0 * (*A.max_dev);
+        if (!(reach * reach < A.rc_qq2 + 100.0) && tid == 0 && blockIdx.x == 0) atomicExch(A.err_flag, 1u);
+    }
+    const double lj_eps = A.lj_eps_tab[0], lj_sig2 = A.lj_sig_tab[0] * A.lj_sig_tab[0];
+
+    double acc_lj = 0.0, acc_vir = 0.0, acc_q = 0.0;
+    unsigned long long my_pairs = 0;
+
+    for (long long u = A.unit_begin + blockIdx.x; u < A.unit_end; u += gridDim.x) {
+        const int c = (int)(u / V3_GROUPS), g = (int)(u - (long long)c * V3_GROUPS);
+        const int sl0 = c_v3_group_begin[g], sl1 = c_v3_group_begin[g + 1];
+        const int a_lo = A.cell_start[c];
+        int nA = A.cell_start[c + 1] - a_lo;
+        __syncthreads();                                   // everyone is done with the previous unit's tiles
+        if (tid == 0) {
+            int off = 0;
+            for (int s = sl0; s < sl1; ++s) {
+                const int4 si = slots[c * 14 + s];
+                s_boff[s - sl0] = off; s_bglob[s - sl0] = si.x;
+                off += si.y;
+            }
+            s_boff[sl1 - sl0] = off;
+        }
+        bool bad = nA > V3_ACAP;
+        if (bad) nA = 0;
+        // ---- stage A (home cell) and B (the group's neighbour cells, translated by their shift)
+        for (int t = tid; t < nA * (1 + S); t += PAIR_BLOCK) {
+            if (t < nA) s_comA[t] = A.com[a_lo + t];
+            else s_siteA[t - nA] = A.site[(size_t)a_lo * S + (t - nA)];
+        }
+        int nB = 0;
+        for (int s = sl0; s < sl1; ++s) {
+            const int4 si = slots[c * 14 + s];
+            const int cnt = si.y;
+            if (cnt > V3_ACAP) { bad = true; continue; }
+            const int cx = si.z & 3, cy = (si.z >> 2) & 3, cz = (si.z >> 4) & 3;
+            const double shx = cx == 1 ? L : (cx == 2 ? -L : 0.0), shy = cy == 1 ? L : (cy == 2 ? -L : 0.0),
+                         shz = cz == 1 ? L : (cz == 2 ? -L : 0.0);
+            for (int t = tid; t < cnt * (1 + S); t += PAIR_BLOCK) {
+                double4 v = (t < cnt) ? A.com[si.x + t] : A.site[(size_t)si.x * S + (t - cnt)];
+                v.x += shx; v.y += shy; v.z += shz;
+                if (t < cnt) s_comB[nB + t] = v;
+                else s_siteB[(size_t)nB * S + (t - cnt)] = v;
+            }
+            nB += cnt;
+        }
+        if (bad) { if (tid == 0) atomicExch(A.err_flag, 1u); nA = 0; }
+        __syncthreads();
+        const int self_n = (g == 0) ? nA : 0;              // slot 0 of group 0 is the home cell itself: keep q > p
+        // ---- gate + consume
+        int head = 0, tail = 0;                            // warp-private queue window [head, tail)
+        auto consume = [&](int base, int count) {          // `count` queued molecule pairs, one per lane
+            if (lane == 0) my_pairs += count;
+            if (lane < count) {
+                const unsigned e = q[(base + lane) & (V3_QCAP - 1)];
+                const int p = e & 127u, qi = e >> 7;
+                double4 sa[S], sb[S];
+#pragma unroll
+                for (int k = 0; k < S; ++k) { sa[k] = s_siteA[p * S + k]; sb[k] = s_siteB[qi * S + k]; }
+                // nine site pairs in lock step: straight-line code, nine independent dependency chains
+                double r2[S * S], qq[S * S], sv[S * S], pv[S * S], ri[S * S];
+                double ddx = 0, ddy = 0, ddz = 0;            // O–O separation for the LJ term
+                unsigned ovl = 0;
+#pragma unroll
+                for (int a = 0; a < S; ++a)
+#pragma unroll
+                    for (int b = 0; b < S; ++b) {
+                        const int j = a * S + b;
+                        const double dx = sb[b].x - sa[a].x, dy = sb[b].y - sa[a].y, dz = sb[b].z - sa[a].z;
+                        if (j == 0) { ddx = dx; ddy = dy; ddz = dz; }
+                        r2[j] = dx * dx + dy * dy + dz * dz;
+                        qq[j] = sa[a].w * sb[b].w;
+                        // overlap rule r² < 0.5 && q_a q_b < 0 (ewalds.jl:359) on bit patterns
+                        if (__double_as_longlong(r2[j]) < 0x3FE0000000000000LL && qq[j] < 0.0) { ovl |= 1u << j; qq[j] = 0.0; r2[j] = 1.0; }
+                    }
+#pragma unroll
+                for (int j = 0; j < S * S; ++j) {
+                    ri[j] = fast_rsqrt(r2[j]);
+                    sv[j] = fma(r2[j] * A.ep.kappa2, A.ep.scale, -1.0);
+                    pv[j] = A.ep.c[DEG];
+                }
+#pragma unroll
+                for (int k = DEG - 1; k >= 0; --k)
+#pragma unroll
+                    for (int j = 0; j < S * S; ++j) pv[j] = fma(pv[j], sv[j], A.ep.c[k]);
+#pragma unroll
+                for (int j = 0; j < S * S; ++j) acc_q = fma(qq[j], fma(-A.ep.kappa, pv[j], ri[j]), acc_q);   // ewalds.jl:366-367
+                {   // LJ 12-6 on the O–O pair (energy.jl:270-282), virial with the COM separation
+                    const double4 ca = s_comA[p], cb = s_comB[qi];
+                    const double rx = cb.x - ca.x, ry = cb.y - ca.y, rz = cb.z - ca.z;
+                    const double rinv2 = ri[0] * ri[0];
+                    const double s2 = lj_sig2 * rinv2, s6 = s2 * s2 * s2, s12 = s6 * s6;
+                    acc_lj += lj_eps * (s12 - s6);
+                    const double w = lj_eps * (2.0 * s12 - s6) * s2;
+                    acc_vir += w * (rx * ddx + ry * ddy + rz * ddz);
+                }
+                if (ovl) {                                                           // ewalds.jl:359-360
+                    int slot_i = 0;
+                    while (slot_i + 1 < sl1 - sl0 && qi >= s_boff[slot_i + 1]) ++slot_i;
+                    const int qglob = s_bglob[slot_i] + (qi - s_boff[slot_i]);
+                    if (atomicExch(&A.ovl[a_lo + p], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
+                    if (atomicExch(&A.ovl[qglob], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
+                }
+            }
+        };
+        // warp w owns rows p ≡ w + (column block) (mod 8): the surplus rows rotate over the warps
+        for (int qb = 0, ib = 0; qb < nB; qb += 32, ++ib) {
+            const int qi = qb + lane;
+            const double4 cb = s_comB[qi < nB ? qi : 0];
+            // lanes past the end of B never pass; in the home cell itself (q < self_n) only p < q passes
+            const int p_lim = (qi >= nB) ? 0 : (qi < self_n ? qi : 0x7fffffff);
+            for (int p = (warp + ib) & (PAIR_WARPS - 1); p < nA; p += PAIR_WARPS) {
+                const double4 ca = s_comA[p];
+                const double dx = cb.x - ca.x, dy = cb.y - ca.y, dz = cb.z - ca.z;
+                const long long r2b = __double_as_longlong(dx * dx + dy * dy + dz * dz);
+                const bool pass = (r2b < A.rcqq_bits) && (p < p_lim);
+                const unsigned m = __ballot_sync(0xffffffffu, pass);
+                if (pass) q[(tail + __popc(m & ((1u << lane) - 1u))) & (V3_QCAP - 1)] = (unsigned)p | ((unsigned)qi << 7);
+                tail += __popc(m);
+            }
+            __syncwarp();
+            while (tail - head >= 32) { consume(head, 32); head += 32; }   // full rounds only
+        }
+        __syncwarp();
+        consume(head, tail - head);                        // last, partial round of the unit
+    }
+    __syncthreads();
+    double accp[4] = {acc_lj, acc_vir, acc_q, (double)my_pairs};
+    block_sum<4, PAIR_BLOCK>(accp, s_red);
+    if (tid == 0) A.partial[blockIdx.x] = make_double4(accp[0], accp[1], accp[2], accp[3]);
+}

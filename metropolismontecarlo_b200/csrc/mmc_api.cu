@@ -3,6 +3,7 @@
 #include "../../include/mmc_b200.h"
 #include "kernels_move.cuh"
 #include "kernels_pairs.cuh"
+#include "kernels_pairs_v3.cuh"
 #include "kernels_recip.cuh"
 #include "kernels_upload.cuh"
 
@@ -85,6 +86,10 @@ struct mmc_handle {
     int max_cell_cached = -1;    // largest cell population seen at the last binning (-1: unknown)
     int *d_maxcount = nullptr;
     int4 *d_units = nullptr;
+    int4 *d_slots = nullptr;
+    long long slots_cap = 0;
+    int use_v3 = 1;              // 0 disables the v3 pair kernel (A/B testing)
+    int pair_level = 0;          // 0: v3 allowed, 1: k_pairs_fast, 2: general k_pairs (raised when a kernel declines the state)
     long long units_cap = 0;
     unsigned int *d_errflag = nullptr;
     std::vector<std::pair<double, ErfPoly>> poly_cache;
@@ -148,8 +153,8 @@ void free_system(mmc_handle *h)
     h->raw_bytes = 0; h->cap_mol = 0; h->cap_sites = 0;
     dfree(h->d_cell_of); dfree(h->d_count); dfree(h->d_start); dfree(h->d_fill); dfree(h->d_perm);
     dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl); dfree(h->d_novl);
-    dfree(h->d_maxdev); dfree(h->d_rhok_partial); dfree(h->d_maxcount); dfree(h->d_errflag); dfree(h->d_units);
-    h->units_cap = 0;
+    dfree(h->d_maxdev); dfree(h->d_rhok_partial); dfree(h->d_maxcount); dfree(h->d_errflag); dfree(h->d_units); dfree(h->d_slots);
+    h->units_cap = 0; h->slots_cap = 0;
     h->max_cell_cached = -1;
     h->has_system = false;
 }
@@ -295,6 +300,7 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
 
 // k_pairs_fast instantiations: water (3 sites) x tile {64, 128} x padded polynomial degree
 #define MMC_FOR_DEGS(X) X(0) X(8) X(12) X(16) X(20) X(24) X(32) X(44)
+#define MMC_FOR_POS_DEGS(X) X(8) X(12) X(16) X(20) X(24) X(32) X(44)
 void launch_pairs_fast(int tile, int deg, int grid, size_t smem, cudaStream_t st, const PairArgs &P)
 {
 #define X(D)                                                                                   \
@@ -306,8 +312,18 @@ void launch_pairs_fast(int tile, int deg, int grid, size_t smem, cudaStream_t st
     MMC_FOR_DEGS(X)
 #undef X
 }
+constexpr size_t V3_SMEM = (V3_ACAP * 4 + V3_BCAP * 4) * sizeof(double4) + PAIR_WARPS * V3_QCAP * sizeof(unsigned);
+void launch_pairs_v3(int deg, int grid, cudaStream_t st, const PairArgs &P, const int4 *slots)
+{
+#define X(D) if (deg == D) { k_pairs_v3<D><<<grid, PAIR_BLOCK, V3_SMEM, st>>>(P, slots); return; }
+    MMC_FOR_POS_DEGS(X)
+#undef X
+}
 void pairs_fast_set_attributes()
 {
+#define X(D) cudaFuncSetAttribute(k_pairs_v3<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM);
+    MMC_FOR_POS_DEGS(X)
+#undef X
 #define X(D)                                                                                                   \
     cudaFuncSetAttribute(k_pairs_fast<3, 64, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);      \
     cudaFuncSetAttribute(k_pairs_fast<3, 128, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
@@ -332,8 +348,9 @@ void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P)
 
 // Leaves this rank's partial sums in d_vec: [0] Σlj_pot [1] Σlj_vir [2] Σcoul [3] #overlap
 // [MMC_NSCAL ..) ρ(k) partial (re,im).
-int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, bool force_general = false)
+int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
 {
+    const bool force_general = h->pair_level >= 2;
     if (!h->uniform) FAIL(MMC_EINVAL, "pair kernel needs a uniform topology (internal)");
     const DevSystem &S = h->S;
     const int US = h->US;
@@ -389,11 +406,11 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, boo
     P.com = h->d_scom; P.site = h->d_ssite; P.cell_start = h->d_start;
     P.ncd = ncd; P.S = US; P.n_mol = S.n_mol; P.mode = cells ? 0 : 1;
     P.n_tiles = (S.n_mol + PAIR_TILE - 1) / PAIR_TILE;
-    P.unit_begin = n_units * E.rank / E.world;
-    P.unit_end = n_units * (E.rank + 1) / E.world;
     P.L = E.box; P.rc_lj2 = S.rc_lj * S.rc_lj; P.rc_qq2 = S.rc_qq * S.rc_qq; P.kappa = E.kappa;
     P.want_lj = 1; P.want_qq = want_qq ? 1 : 0;
     P.nlj = (int)h->lj.size(); P.lj = h->d_lj;
+    for (int k = 0; k < 16; ++k) { P.lj_eps_tab[k] = 0.0; P.lj_sig_tab[k] = 0.0; }
+    if (US <= 4) for (const LJActive &e : h->lj) { P.lj_eps_tab[e.a * US + e.b] = e.eps; P.lj_sig_tab[e.a * US + e.b] = e.sig; }
     P.partial = h->d_pair_partial; P.ovl = h->d_ovl; P.n_ovl = h->d_novl; P.max_dev = h->d_maxdev;
     P.err_flag = h->d_errflag;
     P.rclj_bits = 0; P.rcqq_bits = 0; P.cutlj_bits = 0; P.cutqq_bits = 0;
@@ -402,12 +419,30 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, boo
       v = P.rc_lj2 + 100; std::memcpy(&P.cutlj_bits, &v, 8); v = P.rc_qq2 + 100; std::memcpy(&P.cutqq_bits, &v, 8); }
     P.ep = ErfPoly{};
     if (want_qq) get_erf_poly(h, E.kappa, S.rc_qq * S.rc_qq + 100, P.ep);
-    const long long my_units = P.unit_end - P.unit_begin;
     const int max_cell = cells ? h->max_cell_cached : PAIR_TILE;
-    const int tile = (US == 3 && !force_general) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
+    // v3 serves water-like molecules: 3 sites, LJ only on site pair (0,0), equal cut-offs, Coulomb on, polynomial erf
+    const bool v3 = cells && US == 3 && !force_general && h->use_v3 && h->pair_level == 0 && max_cell <= V3_ACAP && want_qq &&
+                    S.rc_lj == S.rc_qq && P.ep.deg > 0 && h->lj.size() == 1 && h->lj[0].a == 0 && h->lj[0].b == 0;
+    const int tile = (US == 3 && !force_general && !v3) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
+    if (v3) n_units = (long long)V3_GROUPS * ncd * ncd * ncd;
+    P.unit_begin = n_units * E.rank / E.world;
+    P.unit_end = n_units * (E.rank + 1) / E.world;
+    const long long my_units = P.unit_end - P.unit_begin;
     int grid;
     if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-    if (tile) {
+    if (v3) {
+        const long long nslots = 14LL * ncd * ncd * ncd;
+        if (nslots > h->slots_cap) {
+            dfree(h->d_slots);
+            CK(cudaMalloc(&h->d_slots, sizeof(int4) * nslots));
+            h->slots_cap = nslots;
+        }
+        k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(P, h->d_slots, ncd * ncd * ncd);
+        LAUNCH_CHECK();
+        if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
+        grid = (int)std::max(1LL, std::min<long long>(2 * h->sm_count, my_units));
+        launch_pairs_v3(P.ep.deg, grid, h->stream, P, h->d_slots);
+    } else if (tile) {
         if (n_units > h->units_cap) {
             dfree(h->d_units);
             CK(cudaMalloc(&h->d_units, sizeof(int4) * n_units));
@@ -432,7 +467,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, boo
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
     k_pair_reduce<<<1, 256, 0, h->stream>>>(h->d_pair_partial, grid, h->d_novl, h->d_maxcount, h->d_errflag, d_vec);
     LAUNCH_CHECK();
-    h->last_fast = tile;
+    h->last_fast = v3 ? 3 : tile;
     h->last_mode = cells ? 0 : 1;
     h->last_ncd = ncd;
 
@@ -480,7 +515,10 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
     if (E.world == 1) {
         if (h->last_mode == 0) h->max_cell_cached = (int)h->h_vec[6];
         if (h->h_vec[7] != 0.0) return 1;      // a cell outgrew the fast kernel's tile: caller re-runs
-    } else if (h->h_vec[7] != 0.0) FAIL(MMC_ESTATE, "cell overflow in a sharded evaluation (internal)");
+    } else if (h->h_vec[7] != 0.0) {           // summed over ranks: every rank takes the same branch
+        if (++h->pair_level > 2) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        return 1;                               // MMC_RETRY: caller repeats partial + all-reduce + finalize
+    }
     double lj_pot = h->h_vec[0], lj_vir = h->h_vec[1], coul = h->h_vec[2];
     const long long novl = (long long)h->h_vec[3];
     const double recip_raw = h->h_vec[4];
@@ -786,6 +824,7 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         for (int64_t m = 0; m < n_mol; ++m) h->h_mol[m] = make_int2((int)(first_atom[m] - 1), (int)(last_atom[m] - first_atom[m] + 1));
     }
     h->max_cell_cached = -1;
+    h->pair_level = 0;
     h->has_system = true;
     h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
     return MMC_OK;
@@ -1091,10 +1130,10 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, 0, 1};
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
     rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
-    if (rc == 1) {
+    while (rc == 1) {    // the chosen pair kernel declined this state (dense cell / wrapped molecules): next level
+        if (++h->pair_level > 2) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
-        if (rc == 1) FAIL(MMC_ECUDA, "pair kernel tile overflow persisted (internal)");
     }
     if (style == MMC_STYLE_EWALD) h->new_valid = false;
     return rc;
@@ -1203,10 +1242,10 @@ int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t st
     EvalCtx E{f, box_new, coul ? kappa_new : h->S.kappa, h->d_cfac_trial, 0, 1};
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
     rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
-    if (rc == 1) {
+    while (rc == 1) {
+        if (++h->pair_level > 2) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
-        if (rc == 1) FAIL(MMC_ECUDA, "pair kernel tile overflow persisted (internal)");
     }
     if (rc) return rc;
     h->vol_pending = true; h->vol_box = box_new; h->vol_kappa = E.kappa; h->vol_f = f; h->vol_style = style;
@@ -1264,8 +1303,10 @@ int mmc_last_timings(mmc_handle *h, float *ms4)
     return MMC_OK;
 }
 
-int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, int32_t *cells_per_dim)
+int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, int32_t *cells_per_dim,
+                       int32_t *pair_kernel)
 {
+    if (h && pair_kernel) *pair_kernel = h->last_fast;
     if (!h) return MMC_EINVAL;
     if (pairs_in_cutoff) *pairs_in_cutoff = h->last_pairs;
     if (mode) *mode = h->last_mode;

@@ -196,10 +196,11 @@ class Engine:
     def potential_partial(self, style, d_partials_ptr: int):
         self._ck(self.lib.mmc_potential_partial(self.h, _style(style), C.c_void_p(d_partials_ptr)))
 
-    def potential_finalize(self, style, d_partials_ptr: int) -> Properties:
+    def potential_finalize(self, style, d_partials_ptr: int):
+        """Returns Properties, or None when the library asks for the partial pass to be repeated (MMC_RETRY)."""
         out = Properties()
-        self._ck(self.lib.mmc_potential_finalize(self.h, _style(style), C.c_void_p(d_partials_ptr), C.byref(out)))
-        return out
+        rc = self._ck(self.lib.mmc_potential_finalize(self.h, _style(style), C.c_void_p(d_partials_ptr), C.byref(out)))
+        return None if rc == 1 else out
 
     # ---- fused trial move
     def trial_move(self, i: int, com_new, sites_new, style="ewald") -> TrialResult:
@@ -273,10 +274,11 @@ class Engine:
         return {"pairs_ms": ms[0], "rhok_ms": ms[1], "bin_gather_ms": ms[2], "total_ms": ms[3]}
 
     def last_eval_info(self):
-        n, m, c = C.c_int64(), C.c_int32(), C.c_int32()
-        self._ck(self.lib.mmc_last_eval_info(self.h, C.byref(n), C.byref(m), C.byref(c)))
+        n, m, c, k = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.mmc_last_eval_info(self.h, C.byref(n), C.byref(m), C.byref(c), C.byref(k)))
+        kern = {3: "k_pairs_v3", 64: "k_pairs_fast<64>", 128: "k_pairs_fast<128>", 0: "k_pairs"}.get(k.value, str(k.value))
         return {"pairs_in_cutoff": n.value, "mode": ("cells", "tiles", "rows")[m.value] if m.value >= 0 else None,
-                "cells_per_dim": c.value}
+                "cells_per_dim": c.value, "pair_kernel": kern}
 
     def measure_fp64_peak(self) -> float:
         t = C.c_double()

@@ -25,8 +25,12 @@ def partial_len(nkvecs: int) -> int:
 def sharded_potential(eng, style, vec, world: int, group=None):
     """partial → all-reduce (NCCL over NVLink when vec is a CUDA tensor) → finalize.
     `vec` must live on the stream the engine was created with."""
-    eng.potential_partial(style, vec.data_ptr())
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(vec, group=group)
-    return eng.potential_finalize(style, vec.data_ptr())
+    for _ in range(4):
+        eng.potential_partial(style, vec.data_ptr())
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(vec, group=group)
+        props = eng.potential_finalize(style, vec.data_ptr())
+        if props is not None:                  # None: MMC_RETRY, every rank switched to the next pair kernel
+            return props
+    raise RuntimeError("sharded potential did not converge on a pair kernel")
