@@ -87,17 +87,26 @@ __global__ void __launch_bounds__(RHOK_BLOCK) k_rhok_partial(RhokArgs A)
     }
 }
 
-// ρ(k) = Σ_b partial[b][k] in CTA order → out[k] (a slot of the partial-sum vector)
+// ρ(k) = Σ_b partial[b][k] → out[k].  blockDim = (64 k, 4 slices): each slice folds a contiguous
+// quarter of the CTAs in CTA order, the four slice sums are added in slice order (deterministic).
 __global__ void k_rhok_reduce(const double2 *partial, int nb, int nkvecs, double2 *out)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nkvecs) return;
+    __shared__ double2 s_s[4][64];
+    const int k = blockIdx.x * 64 + threadIdx.x, sl = threadIdx.y;
+    const int b0 = (int)((long long)nb * sl / 4), b1 = (int)((long long)nb * (sl + 1) / 4);
     double re = 0.0, im = 0.0;
-    for (int b = 0; b < nb; ++b) {
-        const double2 p = partial[(size_t)b * nkvecs + k];
-        re += p.x; im += p.y;
+    if (k < nkvecs)
+        for (int b = b0; b < b1; ++b) {
+            const double2 p = partial[(size_t)b * nkvecs + k];
+            re += p.x; im += p.y;
+        }
+    s_s[sl][threadIdx.x] = make_double2(re, im);
+    __syncthreads();
+    if (sl == 0 && k < nkvecs) {
+        double2 t = s_s[0][threadIdx.x];
+        for (int j = 1; j < 4; ++j) { t.x += s_s[j][threadIdx.x].x; t.y += s_s[j][threadIdx.x].y; }
+        out[k] = t;
     }
-    out[k] = make_double2(re, im);
 }
 
 // E = Σ_k cfac_k |ρ(k)|² (un-scaled, ewalds.jl:599) and ρ(k) stored to both buffers (:600-601)
@@ -116,4 +125,126 @@ k_rhok_energy(const double2 *rho, const double *cfac, int nkvecs, double2 *dst0,
     }
     block_sum<1, RHOKE_BLOCK>(acc, s_red);
     if (threadIdx.x == 0) *energy_out = acc[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// k_rhok_pairs<NK> — ρ(k) rebuild, second version (the first one was LSU bound: three LDS.128 per
+// eight FP64 instructions, 28 % FP64 pipe).
+//
+// A lane owns one (kx, |ky|) pair (28 pairs for nk = 5, k² < 27: one warp-width) and keeps the
+// accumulators of ALL its kz in registers.  Per site it forms the four products
+//   P1 = cx·cy  P2 = sx·sy  P3 = sx·cy  P4 = cx·sy   (cx, sx carry the charge, ewalds.jl:592-596)
+// → U = e^{i(kx x + ky y)} = (P1−P2, P3+P4),  V = e^{i(kx x − ky y)} = (P1+P2, P3−P4), and for every
+// kz > 0 the eight sums Σ U_r c_z, Σ U_i s_z, Σ U_r s_z, Σ U_i c_z (and the same for V), from which
+//   ρ(kx, +ky, ±kz) = (A1 ∓ A2) + i(A4 ± A3)      (negative k by conjugation, ewalds.jl:566-567)
+// are assembled once at the end: 2 DFMA per (site, k) instead of 8 FP64 instructions, and the
+// e^{ikz z} reads are warp-wide broadcasts.  Warps of a CTA take different sites of a 64-site
+// sub-chunk whose tables are built cooperatively with the reference's recurrence; per-CTA partials
+// are folded in CTA order by k_rhok_reduce as before (deterministic).
+// ------------------------------------------------------------------------------------------
+#define RHOK2_BLOCK 256
+#define RHOK2_SITES 64
+
+struct Rhok2Args {
+    const double4 *site;
+    int s_begin, s_end, per_block;
+    int nkvecs, npairs;          // lanes in use
+    const int2 *pairs;           // [npairs] {kx, |ky|}
+    const int *kindex;           // [(nk+1) x (2nk+1) x (2nk+1)] index of (kx, ky, kz) in the k list or -1
+    double box;
+    double2 *partial;            // [gridDim.x][nkvecs]
+};
+
+template <int NK>
+__global__ void __launch_bounds__(RHOK2_BLOCK) k_rhok_pairs(Rhok2Args A)
+{
+    constexpr int NW = RHOK2_BLOCK / 32;
+    constexpr int NACC = 4 + 8 * NK;
+    __shared__ double2 s_t[RHOK2_SITES][3][NK + 1];          // (cos, sin) of k·x, k·y, k·z; x carries q
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = A.s_begin + blockIdx.x * A.per_block;
+    const int c1 = min(A.s_end, c0 + A.per_block);
+    const double twopi = 2.0 * 3.141592653589793;
+    const int pl = min(lane, A.npairs - 1);
+    const int2 pr = A.pairs[pl];
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+    for (int base = c0; base < c1; base += RHOK2_SITES) {
+        __syncthreads();
+        if (tid < RHOK2_SITES * 3) {
+            const int l = tid / 3, d = tid - 3 * l;
+            double x = 0.0, q = 0.0;
+            if (base + l < c1) {
+                const double4 s = A.site[base + l];
+                x = d == 0 ? s.x : (d == 1 ? s.y : s.z);
+                q = s.w;
+            }
+            const double sc = (d == 0) ? q : 1.0;
+            cplx e1;
+            sincos(twopi * x / A.box, &e1.im, &e1.re);          // ewalds.jl:561-564
+            cplx e; e.re = 1.0; e.im = 0.0;
+            s_t[l][d][0] = make_double2(sc, 0.0);
+            e = e1;
+#pragma unroll
+            for (int k = 1; k <= NK; ++k) {
+                s_t[l][d][k] = make_double2(sc * e.re, sc * e.im);
+                e = cmul(e, e1);                                 // ewalds.jl:573-575
+            }
+        }
+        __syncthreads();
+        for (int l = warp; l < RHOK2_SITES; l += NW) {
+            const double2 ex = s_t[l][0][pr.x], ey = s_t[l][1][pr.y];
+            const double p1 = ex.x * ey.x, p2 = ex.y * ey.y, p3 = ex.y * ey.x, p4 = ex.x * ey.y;
+            const double ur = p1 - p2, ui = p3 + p4, vr = p1 + p2, vi = p3 - p4;
+            acc[0] += ur; acc[1] += ui; acc[2] += vr; acc[3] += vi;       // kz = 0
+#pragma unroll
+            for (int kz = 1; kz <= NK; ++kz) {
+                const double2 ez = s_t[l][2][kz];                          // same address in every lane: broadcast
+                double *a = acc + 4 + 8 * (kz - 1);
+                a[0] = fma(ur, ez.x, a[0]); a[1] = fma(ui, ez.y, a[1]); a[2] = fma(ur, ez.y, a[2]); a[3] = fma(ui, ez.x, a[3]);
+                a[4] = fma(vr, ez.x, a[4]); a[5] = fma(vi, ez.y, a[5]); a[6] = fma(vr, ez.y, a[6]); a[7] = fma(vi, ez.x, a[7]);
+            }
+        }
+    }
+    // ---- fold the 8 warps in warp order, then assemble ρ(k) for this lane's k-vectors
+    __syncthreads();
+    __shared__ double s_acc[NW * 32 * 4];
+    const int W = 2 * NK + 1;
+    double2 *out = A.partial + (size_t)blockIdx.x * A.nkvecs;
+    // accumulators go through shared memory four at a time
+#pragma unroll
+    for (int s0 = 0; s0 < NACC; s0 += 4) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_acc[(warp * 32 + lane) * 4 + j] = acc[s0 + j];
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double t = 0.0;
+                for (int w = 0; w < NW; ++w) t += s_acc[(w * 32 + lane) * 4 + j];
+                acc[s0 + j] = t;
+            }
+        }
+    }
+    if (warp != 0 || lane >= A.npairs) return;
+    const int kx = pr.x, ky = pr.y;
+    auto put = [&](int sy, int sz, int kz, double re, double im) {
+        const int idx = A.kindex[(kx * W + (sy * ky + NK)) * W + (sz * kz + NK)];
+        if (idx >= 0) out[idx] = make_double2(re, im);
+    };
+    put(+1, +1, 0, acc[0], acc[1]);
+    if (ky > 0) put(-1, +1, 0, acc[2], acc[3]);
+#pragma unroll
+    for (int kz = 1; kz <= NK; ++kz) {
+        const double *a = acc + 4 + 8 * (kz - 1);
+        put(+1, +1, kz, a[0] - a[1], a[2] + a[3]);
+        put(+1, -1, kz, a[0] + a[1], a[3] - a[2]);
+        if (ky > 0) {
+            put(-1, +1, kz, a[4] - a[5], a[6] + a[7]);
+            put(-1, -1, kz, a[4] + a[5], a[7] - a[6]);
+        }
+    }
 }

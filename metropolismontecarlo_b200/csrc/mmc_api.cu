@@ -55,6 +55,9 @@ struct mmc_handle {
     int cur = 0;                 // index of the Old ρ(k) buffer
     bool new_valid = false;
     double2 *d_rhok_trial = nullptr;
+    int2 *d_kpairs = nullptr;
+    int *d_kindex = nullptr;
+    int n_kpairs = 0;
     double *d_cfac_trial = nullptr;
     std::vector<double> cfac_trial;
 
@@ -88,6 +91,7 @@ struct mmc_handle {
     int4 *d_units = nullptr;
     int4 *d_slots = nullptr;
     long long slots_cap = 0;
+    int use_rhok_v2 = 1;
     int use_v3 = 1;              // 0 disables the v3 pair kernel (A/B testing)
     int pair_level = 0;          // 0: v3 allowed, 1: k_pairs_fast, 2: general k_pairs (raised when a kernel declines the state)
     long long units_cap = 0;
@@ -162,7 +166,7 @@ void free_system(mmc_handle *h)
 void free_ewald(mmc_handle *h)
 {
     dfree(h->S.kvec); dfree(h->S.cfac); dfree(h->S.rhok[0]); dfree(h->S.rhok[1]);
-    dfree(h->d_rhok_trial); dfree(h->d_cfac_trial); dfree(h->d_vec);
+    dfree(h->d_rhok_trial); dfree(h->d_cfac_trial); dfree(h->d_vec); dfree(h->d_kpairs); dfree(h->d_kindex);
     if (h->h_vec) cudaFreeHost(h->h_vec);
     h->h_vec = nullptr;
     h->has_ewald = false;
@@ -275,25 +279,39 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
 {
     const int n = s_end - s_begin;
     const int nkv = h->S.nkvecs;
-    int per = std::max(2 * RHOK_SITES, (n + 2 * h->sm_count - 1) / (2 * h->sm_count));
-    per = (per + RHOK_SITES - 1) / RHOK_SITES * RHOK_SITES;
+    const bool v2 = h->n_kpairs <= 32 && h->S.nk <= 6 && h->use_rhok_v2;
+    const int chunk = v2 ? RHOK2_SITES : RHOK_SITES;
+    int per = std::max(2 * chunk, (n + 2 * h->sm_count - 1) / (2 * h->sm_count));
+    per = (per + chunk - 1) / chunk * chunk;
     const int nb = std::max(1, (n + per - 1) / per);
     if (nb > h->rhok_grid_cap) {
         dfree(h->d_rhok_partial);
         CK(cudaMalloc(&h->d_rhok_partial, (size_t)nb * nkv * sizeof(double2)));
         h->rhok_grid_cap = nb;
     }
-    RhokArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->S.kvec, box, h->d_rhok_partial};
-    const int kpt = (nkv + RHOK_BLOCK - 1) / RHOK_BLOCK;
     if (h->tm.on) cudaEventRecord(h->tm.ev[2], h->stream);
-    if (kpt <= 1) k_rhok_partial<1><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
-    else if (kpt <= 2) k_rhok_partial<2><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
-    else if (kpt <= 4) k_rhok_partial<4><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
-    else if (kpt <= 8) k_rhok_partial<8><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
-    else FAIL(MMC_EINVAL, "too many k-vectors for the rebuild kernel (nk too large)");
+    if (v2) {
+        Rhok2Args R{site, s_begin, s_end, per, nkv, h->n_kpairs, h->d_kpairs, h->d_kindex, box, h->d_rhok_partial};
+        switch (h->S.nk) {
+            case 1: k_rhok_pairs<1><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
+            case 2: k_rhok_pairs<2><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
+            case 3: k_rhok_pairs<3><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
+            case 4: k_rhok_pairs<4><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
+            case 5: k_rhok_pairs<5><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
+            default: k_rhok_pairs<6><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
+        }
+    } else {
+        RhokArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->S.kvec, box, h->d_rhok_partial};
+        const int kpt = (nkv + RHOK_BLOCK - 1) / RHOK_BLOCK;
+        if (kpt <= 1) k_rhok_partial<1><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
+        else if (kpt <= 2) k_rhok_partial<2><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
+        else if (kpt <= 4) k_rhok_partial<4><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
+        else if (kpt <= 8) k_rhok_partial<8><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
+        else FAIL(MMC_EINVAL, "too many k-vectors for the rebuild kernel (nk too large)");
+    }
     LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[3], h->stream);
-    k_rhok_reduce<<<(nkv + 127) / 128, 128, 0, h->stream>>>(h->d_rhok_partial, nb, nkv, out);
+    k_rhok_reduce<<<(nkv + 63) / 64, dim3(64, 4), 0, h->stream>>>(h->d_rhok_partial, nb, nkv, out);
     LAUNCH_CHECK();
     return MMC_OK;
 }
@@ -905,6 +923,26 @@ int mmc_ewald_prepare(mmc_handle *h, double kappa, int32_t nk, int32_t k_sq_max,
     CK(cudaMalloc(&h->d_rhok_trial, sizeof(double2) * n));
     CK(cudaMemcpyAsync(S.kvec, kv.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(S.cfac, h->cfac.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    {   // lookup tables of the pair-wise rebuild kernel: (kx,|ky|) pairs that own at least one k-vector, index cube
+        const int W = 2 * nk + 1;
+        std::vector<int> kindex((size_t)(nk + 1) * W * W, -1);
+        std::vector<char> used((size_t)(nk + 1) * (nk + 1), 0);
+        for (int i = 0; i < n; ++i) {
+            const int kx = h->kxyz[3 * i], ky = h->kxyz[3 * i + 1], kz = h->kxyz[3 * i + 2];
+            kindex[((size_t)kx * W + (ky + nk)) * W + (kz + nk)] = i;
+            used[(size_t)kx * (nk + 1) + std::abs(ky)] = 1;
+        }
+        std::vector<int2> kp;
+        for (int kx = 0; kx <= nk; ++kx)
+            for (int ky = 0; ky <= nk; ++ky)
+                if (used[(size_t)kx * (nk + 1) + ky]) kp.push_back(make_int2(kx, ky));
+        h->n_kpairs = (int)kp.size();
+        CK(cudaMalloc(&h->d_kpairs, sizeof(int2) * kp.size()));
+        CK(cudaMalloc(&h->d_kindex, sizeof(int) * kindex.size()));
+        CK(cudaMemcpyAsync(h->d_kpairs, kp.data(), sizeof(int2) * kp.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_kindex, kindex.data(), sizeof(int) * kindex.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     CK(cudaMemsetAsync(S.rhok[0], 0, sizeof(double2) * n, h->stream));   // zeros(ComplexF64, NKVECS), ewalds.jl:98-99
     CK(cudaMemsetAsync(S.rhok[1], 0, sizeof(double2) * n, h->stream));
     CK(cudaStreamSynchronize(h->stream));
