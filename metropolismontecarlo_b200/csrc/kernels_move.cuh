@@ -4,15 +4,21 @@
 //   cfg 0: LJ_poly_ΔU + EwaldReal against the resident state        (Ewald/main.jl:491,501)
 //   cfg 1: the same with molecule i at its trial position            (Ewald/main.jl:557,566)
 //   recip: RecipMove's ρ(k) delta update and ΔE                      (Ewald/main.jl:581)
-// and the last CTA to finish folds the per-CTA partials in a fixed order and writes the
-// scalars straight into a mapped pinned host slot (one PCIe write, no memcpy, no second launch).
-//
-// Work decomposition per pair CTA: (1) one thread per partner molecule does the COM gate
-// (|COM_ij|² < rc², strict, Ewald/energy.jl:250 / ewalds.jl:337), survivors are compacted in
-// index order into shared memory; (2) the n_in × n_a × n_b site pairs are spread over all
-// threads, so the ~10³ erfc evaluations of a water move run ≈1 per thread instead of 9 in series.
-// These launches are latency-bound by construction (≈2×10⁵ flop per move at N=750).
+// These launches are latency bound by construction (≈2×10⁵ flop per move at N = 750 ≈ 6 ns of
+// FP64 peak), so everything here is about the number of DEPENDENT memory round trips:
+//   * the trial coordinates, and the previous accepted move still to be committed, travel as
+//     kernel parameters (no memcpy, no separate commit launch: every reader substitutes the
+//     pending molecule from the parameters and the last CTA writes it back to HBM);
+//   * a pair CTA loads COM + sites + types of its 128 partner molecules in ONE round trip
+//     (speculatively, before the COM gate), gates, compacts the survivors in index order into
+//     shared memory and spreads the n_in × n_a × n_b site pairs over all threads;
+//   * erfc(κr)/r uses the per-box erf polynomial (erf_poly.h) — a short dependency chain;
+//   * every CTA publishes its partial sums straight into its own 64-byte slot of a mapped pinned
+//     host array as four self-validating 16-byte {value, seq} packets; the host polls the slots
+//     and folds them in CTA order.  No tickets, no last-block pass, no fence, no D2H copy, no
+//     cudaStreamSynchronize.
 #pragma once
+#include "erf_poly.h"
 #include "mmc_common.cuh"
 
 #define MOVE_BLOCK 128
@@ -28,53 +34,88 @@ struct MoveArgs {
     unsigned long long seq;
     int recip_ns;     // sites in the ρ(k) delta (0: take molecule i's)
     int recip_from_args; // 1: old sites and charges come from site_old/q (mmc_recip_move)
+    int commit_i;     // ≥ 0: accepted move not yet written to HBM (molecule index), -1: none
+    int commit_ns;
+    int i_first, i_ns; // molecule i's first site and site count
     double com_new[3];
     double site_new[MMC_MAX_SITES * 3];
     double site_old[MMC_MAX_SITES * 3];
     double q[MMC_MAX_SITES];
+    double commit_com[3];
+    double commit_site[MMC_MAX_SITES * 3];
 };
 
-// what the last CTA writes to the host
-struct MoveOut {
-    double lj_pot[2], lj_vir[2];   // already ×4 and ×24/3
-    double qq[2];                  // EwaldReal, un-scaled, 0 if overlap
-    double d_recip;                // ×factor
-    int overlap[2];
-    unsigned long long seq;        // written last
-};
+// One 64-byte slot per CTA in mapped pinned host memory: four 16-byte packets {value, seq}.
+// A packet is ONE 16-byte store, so it reaches host memory whole: the host accepts a packet when
+// its seq matches and needs no fence between "data" and "flag" — which removes the
+// system-scope membar (≈1-2 µs over PCIe) from the critical path of every move.
+struct MovePacket { double v; unsigned long long seq; };
+struct MoveSlot { MovePacket p[4]; };   // pair CTA: lj_pot, lj_vir, coul, overlap; recip CTA: ΔE (un-scaled)
 
 struct MoveScratch {
-    double4 *partial;        // [blocks] {lj_pot, lj_vir, coul, overlap}
-    unsigned int *ticket;
-    MoveOut *out;            // mapped pinned host memory (device alias)
+    MoveSlot *slots;               // device alias of the mapped host array
 };
 
-__device__ __forceinline__ void move_pair_block(const DevSystem &S, const MoveArgs &A, int cfg,
+// lanes 0..3 of the calling warp each store one packet (one coalesced 64-byte write)
+__device__ __forceinline__ void publish(MoveSlot *slot, const double (&acc)[4], unsigned long long seq)
+{
+    const int l = threadIdx.x;
+    if (l < 4) {
+        const double v = l == 0 ? acc[0] : (l == 1 ? acc[1] : (l == 2 ? acc[2] : acc[3]));
+        const ulonglong2 pk = make_ulonglong2((unsigned long long)__double_as_longlong(v), seq);
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&slot->p[l]), "l"(pk.x), "l"(pk.y) : "memory");
+    }
+}
+
+// q_a q_b erfc(κ r)/r with the reference's overlap rule and r² < r_cut²+100 test (ewalds.jl:359-367)
+__device__ __forceinline__ void move_coul(const DevSystem &S, const ErfPoly &P, double r2, double qq, double cut2,
+                                          double (&acc)[4])
+{
+    if ((r2 < 0.5) && (qq < 0)) {
+        acc[3] = 1.0;
+    } else if (r2 < cut2) {
+        if (P.deg > 0) {
+            const double rinv = rsqrt(r2);
+            const double sv = fma(r2 * P.kappa2, P.scale, -1.0);
+            double pv = P.c[P.deg];
+#pragma unroll 1
+            for (int k = P.deg - 1; k >= 0; --k) pv = fma(pv, sv, P.c[k]);
+            acc[2] = fma(qq, fma(-P.kappa, pv, rinv), acc[2]);
+        } else {
+            const double r = sqrt(r2);
+            acc[2] += qq * erfc(S.kappa * r) / r;
+        }
+    }
+}
+
+// SP > 0: every molecule has at most SP sites and the partner sites are prefetched with the COMs
+template <int SP>
+__device__ __forceinline__ void move_pair_block(const DevSystem &S, const MoveArgs &A, const ErfPoly &P, int cfg,
                                                 int tile0, double (&acc)[4])
 {
+    constexpr int SQ = SP > 0 ? SP : 1;
     __shared__ double4 s_isite[MMC_MAX_SITES];
     __shared__ int s_itype[MMC_MAX_SITES];
     __shared__ double4 s_rij[MOVE_BLOCK];   // {rij.x, rij.y, rij.z, flags}
     __shared__ int s_j[MOVE_BLOCK];
     __shared__ int s_wcount[MOVE_BLOCK / 32];
+    __shared__ double4 s_qsite[SP > 0 ? MOVE_BLOCK * SQ : 1];
+    __shared__ int s_qtype[SP > 0 ? MOVE_BLOCK * SQ : 1];
+    __shared__ int s_qns[SP > 0 ? MOVE_BLOCK : 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = A.i;
-    const int2 mi = S.mol[i];
+    const int i = A.i, ci = A.commit_i;
+    const int2 mi = make_int2(A.i_first, A.i_ns);      // host knows molecule i's layout: no dependent load
     const int nsi = mi.y;
     const double L = S.box;
     double cx, cy, cz;
-    if (cfg == 0) {
-        const double4 c = S.com[i];
-        cx = c.x; cy = c.y; cz = c.z;
-    } else {
-        cx = A.com_new[0]; cy = A.com_new[1]; cz = A.com_new[2];
-    }
+    if (cfg == 1) { cx = A.com_new[0]; cy = A.com_new[1]; cz = A.com_new[2]; }
+    else if (i == ci) { cx = A.commit_com[0]; cy = A.commit_com[1]; cz = A.commit_com[2]; }
+    else { const double4 c = S.com[i]; cx = c.x; cy = c.y; cz = c.z; }
     if (tid < nsi) {
         double4 s = S.site[mi.x + tid];
-        if (cfg == 1) {
-            s.x = A.site_new[3 * tid]; s.y = A.site_new[3 * tid + 1]; s.z = A.site_new[3 * tid + 2];
-        }
+        if (cfg == 1) { s.x = A.site_new[3 * tid]; s.y = A.site_new[3 * tid + 1]; s.z = A.site_new[3 * tid + 2]; }
+        else if (i == ci) { s.x = A.commit_site[3 * tid]; s.y = A.commit_site[3 * tid + 1]; s.z = A.commit_site[3 * tid + 2]; }
         s_isite[tid] = s;
         s_itype[tid] = S.atype[mi.x + tid];
     }
@@ -85,13 +126,32 @@ __device__ __forceinline__ void move_pair_block(const DevSystem &S, const MoveAr
 
     for (int tile = tile0; tile * MOVE_BLOCK < S.n_mol; tile += A.tiles) {
         __syncthreads();   // s_isite ready / previous tile's queue fully consumed
-        // ---- phase 1: COM gate, ordered compaction
+        // ---- phase 1: one round trip for COM (+ sites + types), COM gate, ordered compaction
         const int j = tile * MOVE_BLOCK + tid;
         bool in = false;
         double rx = 0, ry = 0, rz = 0;
         int flags = 0;
+        double4 pre[SQ];
+        int pty[SQ];
+        int2 mj = make_int2(0, 0);
         if (j < S.n_mol && j != i) {
-            const double4 cj = S.com[j];
+            double4 cj = S.com[j];
+            if (SP > 0) {
+                mj = S.uni > 0 ? make_int2(j * S.uni, S.uni) : S.mol[j];   // uniform topology: no dependent load
+#pragma unroll
+                for (int k = 0; k < SQ; ++k) {
+                    pre[k] = (k < mj.y) ? S.site[mj.x + k] : make_double4(0, 0, 0, 0);
+                    pty[k] = (k < mj.y) ? S.atype[mj.x + k] : 0;
+                }
+            }
+            if (j == ci) {                                    // accepted move still pending in the parameters
+                cj.x = A.commit_com[0]; cj.y = A.commit_com[1]; cj.z = A.commit_com[2];
+                if (SP > 0) {
+#pragma unroll
+                    for (int k = 0; k < SQ; ++k)
+                        if (k < mj.y) { pre[k].x = A.commit_site[3 * k]; pre[k].y = A.commit_site[3 * k + 1]; pre[k].z = A.commit_site[3 * k + 2]; }
+                }
+            }
             rx = min_image(cx, cj.x, L);
             ry = min_image(cy, cj.y, L);
             rz = min_image(cz, cj.z, L);
@@ -113,6 +173,11 @@ __device__ __forceinline__ void move_pair_block(const DevSystem &S, const MoveAr
             const int p = off + __popc(m & ((1u << lane) - 1u));
             s_rij[p] = make_double4(rx, ry, rz, (double)flags);
             s_j[p] = j;
+            if (SP > 0) {
+                s_qns[p] = mj.y;
+#pragma unroll
+                for (int k = 0; k < SQ; ++k) { s_qsite[p * SQ + k] = pre[k]; s_qtype[p * SQ + k] = pty[k]; }
+            }
         }
         __syncthreads();
         // ---- phase 2: site pairs spread over the CTA
@@ -121,9 +186,20 @@ __device__ __forceinline__ void move_pair_block(const DevSystem &S, const MoveAr
             const int jj = w / per_mol;
             const int rem = w - jj * per_mol;
             const int a = rem / SM, b = rem - a * SM;
-            const int2 mj = S.mol[s_j[jj]];
-            if (b >= mj.y) continue;
-            const double4 sb = S.site[mj.x + b];
+            double4 sb;
+            int tb;
+            if (SP > 0) {
+                if (b >= s_qns[jj]) continue;
+                sb = s_qsite[jj * SQ + b];
+                tb = s_qtype[jj * SQ + b];
+            } else {
+                const int jm = s_j[jj];
+                const int2 mjj = S.mol[jm];
+                if (b >= mjj.y) continue;
+                sb = S.site[mjj.x + b];
+                tb = S.atype[mjj.x + b];
+                if (jm == ci) { sb.x = A.commit_site[3 * b]; sb.y = A.commit_site[3 * b + 1]; sb.z = A.commit_site[3 * b + 2]; }
+            }
             const double4 sa = s_isite[a];
             const double4 rij = s_rij[jj];
             const int fl = (int)rij.w;
@@ -132,20 +208,12 @@ __device__ __forceinline__ void move_pair_block(const DevSystem &S, const MoveAr
             const double dz = min_image(sa.z, sb.z, L);
             const double r2 = dx * dx + dy * dy + dz * dz;
             if (fl & 1) {
-                const int ta = s_itype[a], tb = S.atype[mj.x + b];
+                const int ta = s_itype[a];
                 const double eps = S.eps[ta + tb * nt];
                 if (r2 < (rc_lj2 + 100) && eps > 0.001)
                     lj_pair(eps, S.sig[ta + tb * nt], r2, dx, dy, dz, rij.x, rij.y, rij.z, acc[0], acc[1]);
             }
-            if (fl & 2) {
-                const double qq = sa.w * sb.w;
-                if ((r2 < 0.5) && (qq < 0)) {
-                    acc[3] = 1.0;                                    // ewalds.jl:359-360
-                } else if (r2 < (rc_qq2 + 100)) {
-                    const double r = sqrt(r2);
-                    acc[2] += qq * erfc(S.kappa * r) / r;            // ewalds.jl:366-367
-                }
-            }
+            if (fl & 2) move_coul(S, P, r2, sa.w * sb.w, rc_qq2 + 100, acc);
         }
     }
 }
@@ -160,7 +228,7 @@ __device__ __forceinline__ void move_recip_block(const DevSystem &S, const MoveA
     __shared__ double s_q[MMC_MAX_SITES];
     const int tid = threadIdx.x;
     int2 mi = make_int2(0, A.recip_ns);
-    if (!A.recip_from_args) mi = S.mol[A.i];
+    if (!A.recip_from_args) mi = make_int2(A.i_first, A.i_ns);
     const int ns = mi.y, nk = S.nk;
     const double L = S.box;
     const double twopi = 2.0 * 3.141592653589793;
@@ -173,6 +241,7 @@ __device__ __forceinline__ void move_recip_block(const DevSystem &S, const MoveA
         } else if (cfg == 0) {
             const double4 s = S.site[mi.x + l];
             x = d == 0 ? s.x : (d == 1 ? s.y : s.z);
+            if (A.i == A.commit_i) x = A.commit_site[3 * l + d];
             if (d == 0) s_q[l] = s.w;
         } else {
             x = A.site_new[3 * l + d];
@@ -207,56 +276,34 @@ __device__ __forceinline__ void move_recip_block(const DevSystem &S, const MoveA
     }
 }
 
+template <int SP>
 __global__ void __launch_bounds__(MOVE_BLOCK)
-k_move(const __grid_constant__ DevSystem S, const __grid_constant__ MoveArgs A, MoveScratch W)
+k_move(const __grid_constant__ DevSystem S, const __grid_constant__ MoveArgs A,
+       const __grid_constant__ ErfPoly P, MoveScratch W)
 {
     __shared__ double s_red[4 * (MOVE_BLOCK / 32)];
-    __shared__ bool s_last;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const int b = blockIdx.x;
     const int n_pair = A.n_cfg * A.tiles;
-    if (b < n_pair) move_pair_block(S, A, b / A.tiles, b % A.tiles, acc);
+    if (b < n_pair) move_pair_block<SP>(S, A, P, b / A.tiles, b % A.tiles, acc);
     else move_recip_block(S, A, b - n_pair, acc);
-    block_sum<4, MOVE_BLOCK>(acc, s_red);
-    if (threadIdx.x == 0) {
-        W.partial[b] = make_double4(acc[0], acc[1], acc[2], acc[3]);
-        __threadfence();
-        const unsigned t = atomicAdd(W.ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    // ---- last CTA: fold partials in block order (deterministic), publish to the host
-    __threadfence();
-    if (threadIdx.x == 0) {
-        MoveOut o;
-        bool any_ovl = false;
-        for (int cfg = 0; cfg < 2; ++cfg) {
-            double lp = 0, lv = 0, cq = 0, ov = 0;
-            if (cfg < A.n_cfg)
-                for (int t = 0; t < A.tiles; ++t) {
-                    const double4 p = ldcg4(&W.partial[cfg * A.tiles + t]);
-                    lp += p.x; lv += p.y; cq += p.z; ov += p.w;
-                }
-            const bool ovl = (ov > 0.0) && !A.ignore_overlap;
-            any_ovl |= ovl;
-            o.lj_pot[cfg] = lp * 4;              // energy.jl:289  pot * 4
-            o.lj_vir[cfg] = lv * 24 / 3.0;       //                vir * 24 / 3.0
-            o.qq[cfg] = ovl ? 0.0 : cq;          // ewalds.jl:360  return 0.0, true
-            o.overlap[cfg] = (ov > 0.0) ? 1 : 0;
+    block_sum_all<4, MOVE_BLOCK>(acc, s_red);
+    publish(&W.slots[b], acc, A.seq);
+    // the last CTA makes the pending accepted move permanent (main.jl:527,552); nobody in this
+    // launch reads these addresses: every reader took molecule commit_i from the parameters
+    if (b == gridDim.x - 1 && A.commit_i >= 0) {
+        const int2 mc = S.mol[A.commit_i];
+        const int t = threadIdx.x;
+        if (t == 0) S.com[A.commit_i] = make_double4(A.commit_com[0], A.commit_com[1], A.commit_com[2], 0.0);
+        if (t < mc.y) {
+            double4 s = S.site[mc.x + t];
+            s.x = A.commit_site[3 * t]; s.y = A.commit_site[3 * t + 1]; s.z = A.commit_site[3 * t + 2];
+            S.site[mc.x + t] = s;
         }
-        double dr = 0.0;
-        for (int t = 0; t < A.recip_blocks; ++t) dr += ldcg4(&W.partial[n_pair + t]).x;
-        o.d_recip = any_ovl ? 0.0 : dr * S.factor;   // main.jl:580-590; ewalds.jl:825
-        o.seq = 0;
-        *W.out = o;
-        *W.ticket = 0;
-        __threadfence_system();
-        *((volatile unsigned long long *)&W.out->seq) = A.seq;
     }
 }
 
-// commit of an accepted move: main.jl:527,552 made permanent (the ρ(k) part is a pointer swap)
+// explicit write of one molecule (mmc_set_molecule, and the flush of a pending accepted move)
 __global__ void k_set_molecule(DevSystem S, int i, double cx, double cy, double cz, MoveArgs A)
 {
     const int2 mi = S.mol[i];
@@ -274,8 +321,10 @@ __global__ void k_set_molecule(DevSystem S, int i, double cx, double cy, double 
 
 struct AtomArgs {
     int i, n_cfg, blocks;
+    int commit_i;                  // ≥ 0: accepted move not yet written to HBM
     unsigned long long seq;
     double r_new[3];
+    double commit_r[3];
 };
 
 // Monatomic/mainMonatomic.jl:227-272 LJ_ΔU for atom i at its resident (cfg 0) and trial (cfg 1)
@@ -284,14 +333,15 @@ __global__ void __launch_bounds__(ATOM_BLOCK)
 k_move_atom(DevAtoms S, const __grid_constant__ AtomArgs A, MoveScratch W)
 {
     __shared__ double s_red[4 * (ATOM_BLOCK / 32)];
-    __shared__ bool s_last;
-    const double4 r0 = S.r[A.i];
+    double4 r0 = S.r[A.i];
+    if (A.i == A.commit_i) { r0.x = A.commit_r[0]; r0.y = A.commit_r[1]; r0.z = A.commit_r[2]; }
     const double L = S.box, rc2 = S.rc * S.rc;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int j = blockIdx.x * ATOM_BLOCK + threadIdx.x; j < S.n; j += gridDim.x * ATOM_BLOCK) {
         if (j == A.i) continue;
-        const double4 rj = S.r[j];
+        double4 rj = S.r[j];
         const double2 es = S.es[j];
+        if (j == A.commit_i) { rj.x = A.commit_r[0]; rj.y = A.commit_r[1]; rj.z = A.commit_r[2]; }
         {
             const double dx = min_image(r0.x, rj.x, L), dy = min_image(r0.y, rj.y, L),
                          dz = min_image(r0.z, rj.z, L);
@@ -313,28 +363,10 @@ k_move_atom(DevAtoms S, const __grid_constant__ AtomArgs A, MoveScratch W)
             }
         }
     }
-    block_sum<4, ATOM_BLOCK>(acc, s_red);
-    if (threadIdx.x == 0) {
-        W.partial[blockIdx.x] = make_double4(acc[0], acc[1], acc[2], acc[3]);
-        __threadfence();
-        s_last = (atomicAdd(W.ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last || threadIdx.x != 0) return;
-    __threadfence();
-    double p0 = 0, v0 = 0, p1 = 0, v1 = 0;
-    for (int t = 0; t < (int)gridDim.x; ++t) {
-        const double4 p = ldcg4(&W.partial[t]);
-        p0 += p.x; v0 += p.y; p1 += p.z; v1 += p.w;
-    }
-    MoveOut o;
-    o.lj_pot[0] = p0 * 4.0; o.lj_vir[0] = v0 * 24.0 / 3.0;     // mainMonatomic.jl:271
-    o.lj_pot[1] = p1 * 4.0; o.lj_vir[1] = v1 * 24.0 / 3.0;
-    o.qq[0] = o.qq[1] = 0.0; o.d_recip = 0.0; o.overlap[0] = o.overlap[1] = 0; o.seq = 0;
-    *W.out = o;
-    *W.ticket = 0;
-    __threadfence_system();
-    *((volatile unsigned long long *)&W.out->seq) = A.seq;
+    block_sum_all<4, ATOM_BLOCK>(acc, s_red);
+    publish(&W.slots[blockIdx.x], acc, A.seq);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && A.commit_i >= 0)
+        S.r[A.commit_i] = make_double4(A.commit_r[0], A.commit_r[1], A.commit_r[2], 0.0);
 }
 
 __global__ void k_set_atom(DevAtoms S, int i, double x, double y, double z)

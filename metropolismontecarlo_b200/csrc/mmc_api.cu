@@ -19,6 +19,9 @@ namespace {
 
 std::string g_create_error;
 
+// host-side fold of one move launch: exactly the numbers Loop() gets from its calls
+struct MoveOut { double lj_pot[2], lj_vir[2], qq[2], d_recip; int overlap[2]; };
+
 struct Timers { cudaEvent_t ev[8]; bool on = false; float ms[4] = {0, 0, 0, 0}; };
 
 }  // namespace
@@ -63,7 +66,15 @@ struct mmc_handle {
 
     // ---- move scratch
     MoveScratch W{};
-    MoveOut *h_out = nullptr;
+    MoveSlot *h_slots = nullptr;  // mapped pinned: one slot per CTA of a move launch
+    int max_slots = 0;
+    MoveOut mout{};               // host-side fold of the slots of the last move launch
+    MoveOut *h_out = &mout;
+    ErfPoly move_poly{};          // erf polynomial of the resident box for the per-move kernels
+    int pend_kind = 0;            // accepted move not yet written to HBM: 0 none, 1 molecule, 2 atom
+    int pend_i = 0, pend_ns = 0;
+    double pend_com[3] = {0, 0, 0};
+    double pend_site[3 * MMC_MAX_SITES] = {0};
     unsigned long long seq = 0;
     bool trial_pending = false;
     int trial_kind = 0;          // 1 molecule, 2 atom
@@ -188,28 +199,32 @@ int ensure_vec(mmc_handle *h)
     return MMC_OK;
 }
 
-// wait for the last CTA's publication of launch `seq`
-int wait_out(mmc_handle *h)
+inline int2 mol_of(const mmc_handle *h, int64_t i0)
 {
-    if (h->cfg.sync_mode == 1) {
-        CK(cudaStreamSynchronize(h->stream));
-        if (h->h_out->seq != h->seq) FAIL(MMC_ECUDA, "move kernel finished without publishing its result");
-        return MMC_OK;
-    }
-    volatile unsigned long long *flag = &h->h_out->seq;
+    return h->uniform ? make_int2((int)(i0 * h->US), h->US) : h->h_mol[i0];
+}
+
+// wait until every CTA of launch `seq` has published its four packets
+int wait_slots(mmc_handle *h, int nblocks)
+{
+    if (h->cfg.sync_mode == 1) CK(cudaStreamSynchronize(h->stream));
     unsigned spins = 0;
-    while (*flag != h->seq) {
-        _mm_pause();
-        if ((++spins & 0xfffffu) == 0) {   // every ~1M polls make sure the kernel is still alive
-            cudaError_t q = cudaStreamQuery(h->stream);
-            if (q != cudaSuccess && q != cudaErrorNotReady) {
-                h->err = std::string("move kernel: ") + cudaGetErrorString(q);
-                return MMC_ECUDA;
+    for (int b = 0; b < nblocks; ++b)
+        for (int k = 0; k < 4; ++k) {
+            volatile unsigned long long *flag = &h->h_slots[b].p[k].seq;
+            while (*flag != h->seq) {
+                _mm_pause();
+                if ((++spins & 0xfffffu) == 0 || h->cfg.sync_mode == 1) {   // make sure the kernel is still alive
+                    cudaError_t q = cudaStreamQuery(h->stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) {
+                        h->err = std::string("move kernel: ") + cudaGetErrorString(q);
+                        return MMC_ECUDA;
+                    }
+                    if (q == cudaSuccess && *flag != h->seq)
+                        FAIL(MMC_ECUDA, "move kernel finished without publishing its result");
+                }
             }
-            if (q == cudaSuccess && *flag != h->seq)
-                FAIL(MMC_ECUDA, "move kernel finished without publishing its result");
         }
-    }
     return MMC_OK;
 }
 
@@ -219,19 +234,92 @@ int move_tiles(const mmc_handle *h)
     return std::max(1, std::min(t, h->sm_count));
 }
 
-int launch_move(mmc_handle *h, MoveArgs &A)
+// writes a pending accepted move to HBM with its own tiny launch (only needed when the next call
+// is not a move launch, which would carry it in its parameters)
+int flush_pending(mmc_handle *h)
 {
-    A.seq = ++h->seq;
-    const int blocks = A.n_cfg * A.tiles + A.recip_blocks;
-    if (blocks <= 0) FAIL(MMC_EINVAL, "empty move launch");
-    k_move<<<blocks, MOVE_BLOCK, 0, h->stream>>>(h->S, A, h->W);
-    LAUNCH_CHECK();
-    return wait_out(h);
+    if (h->pend_kind == 1) {
+        MoveArgs T{};
+        std::memcpy(T.site_new, h->pend_site, sizeof(double) * 3 * h->pend_ns);
+        k_set_molecule<<<1, 32, 0, h->stream>>>(h->S, h->pend_i, h->pend_com[0], h->pend_com[1], h->pend_com[2], T);
+        LAUNCH_CHECK();
+    } else if (h->pend_kind == 2) {
+        k_set_atom<<<1, 1, 0, h->stream>>>(h->At, h->pend_i, h->pend_com[0], h->pend_com[1], h->pend_com[2]);
+        LAUNCH_CHECK();
+    }
+    h->pend_kind = 0;
+    return MMC_OK;
 }
 
-inline int2 mol_of(const mmc_handle *h, int64_t i0)
+// launch k_move on system `sys`, wait for its CTAs and fold their partials in CTA order
+// (energy.jl:289 pot*4, vir*24/3; ewalds.jl:360 "return 0.0, true"; main.jl:580-590 skip on overlap)
+int launch_move_on(mmc_handle *h, const DevSystem &sys, MoveArgs &A, const ErfPoly &poly, bool carry_commit)
 {
-    return h->uniform ? make_int2((int)(i0 * h->US), h->US) : h->h_mol[i0];
+    A.seq = ++h->seq;
+    A.commit_i = -1;
+    if (carry_commit && h->pend_kind == 1) {
+        A.commit_i = h->pend_i; A.commit_ns = h->pend_ns;
+        std::memcpy(A.commit_com, h->pend_com, sizeof(A.commit_com));
+        std::memcpy(A.commit_site, h->pend_site, sizeof(double) * 3 * h->pend_ns);
+        h->pend_kind = 0;                       // this launch writes it back
+    }
+    { const int2 mi = (&sys == &h->S) ? mol_of(h, A.i) : make_int2(A.i * h->US, h->US); A.i_first = mi.x; A.i_ns = mi.y; }
+    const int blocks = A.n_cfg * A.tiles + A.recip_blocks;
+    if (blocks <= 0 || blocks > h->max_slots) FAIL(MMC_EINVAL, "bad move launch size");
+    if (sys.max_sites <= 3) k_move<3><<<blocks, MOVE_BLOCK, 0, h->stream>>>(sys, A, poly, h->W);
+    else if (sys.max_sites == 4) k_move<4><<<blocks, MOVE_BLOCK, 0, h->stream>>>(sys, A, poly, h->W);
+    else k_move<0><<<blocks, MOVE_BLOCK, 0, h->stream>>>(sys, A, poly, h->W);
+    LAUNCH_CHECK();
+    int rc = wait_slots(h, blocks);
+    if (rc) return rc;
+    MoveOut &o = h->mout;
+    bool any_ovl = false;
+    for (int cfg = 0; cfg < 2; ++cfg) {
+        double lp = 0, lv = 0, cq = 0, ov = 0;
+        if (cfg < A.n_cfg)
+            for (int t = 0; t < A.tiles; ++t) {
+                const MoveSlot &sl = h->h_slots[cfg * A.tiles + t];
+                lp += sl.p[0].v; lv += sl.p[1].v; cq += sl.p[2].v; ov += sl.p[3].v;
+            }
+        const bool ovl = (ov > 0.0) && !A.ignore_overlap;
+        any_ovl |= ovl;
+        o.lj_pot[cfg] = lp * 4;
+        o.lj_vir[cfg] = lv * 24 / 3.0;
+        o.qq[cfg] = ovl ? 0.0 : cq;
+        o.overlap[cfg] = (ov > 0.0) ? 1 : 0;
+    }
+    double dr = 0.0;
+    for (int t = 0; t < A.recip_blocks; ++t) dr += h->h_slots[A.n_cfg * A.tiles + t].p[0].v;
+    o.d_recip = any_ovl ? 0.0 : dr * sys.factor;
+    return MMC_OK;
+}
+
+int launch_move(mmc_handle *h, MoveArgs &A) { return launch_move_on(h, h->S, A, h->move_poly, true); }
+
+int launch_move_atom(mmc_handle *h, AtomArgs &A)
+{
+    A.seq = ++h->seq;
+    A.commit_i = -1;
+    if (h->pend_kind == 2) {
+        A.commit_i = h->pend_i;
+        std::memcpy(A.commit_r, h->pend_com, sizeof(A.commit_r));
+        h->pend_kind = 0;
+    }
+    if (A.blocks > h->max_slots) FAIL(MMC_EINVAL, "bad move launch size");
+    k_move_atom<<<A.blocks, ATOM_BLOCK, 0, h->stream>>>(h->At, A, h->W);
+    LAUNCH_CHECK();
+    int rc = wait_slots(h, A.blocks);
+    if (rc) return rc;
+    double p0 = 0, v0 = 0, p1 = 0, v1 = 0;
+    for (int t = 0; t < A.blocks; ++t) {
+        const MoveSlot &sl = h->h_slots[t];
+        p0 += sl.p[0].v; v0 += sl.p[1].v; p1 += sl.p[2].v; v1 += sl.p[3].v;
+    }
+    MoveOut &o = h->mout;
+    o.lj_pot[0] = p0 * 4.0; o.lj_vir[0] = v0 * 24.0 / 3.0;     // mainMonatomic.jl:271
+    o.lj_pot[1] = p1 * 4.0; o.lj_vir[1] = v1 * 24.0 / 3.0;
+    o.qq[0] = o.qq[1] = 0.0; o.d_recip = 0.0; o.overlap[0] = o.overlap[1] = 0;
+    return MMC_OK;
 }
 
 int check_mol_index(mmc_handle *h, int64_t i)
@@ -501,16 +589,14 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
 // single-molecule Coulomb row on the (scaled, sorted) evaluation copy, overlap pairs skipped
 int overlap_row(mmc_handle *h, const EvalCtx &E, int sorted_index, double *row)
 {
+    ErfPoly poly{};                      // rare path: plain erfc()
     DevSystem V = h->S;
     V.site = h->d_ssite; V.com = h->d_scom; V.mol = h->d_mol_uniform;
     V.box = E.box; V.kappa = E.kappa;
     MoveArgs A{};
     A.i = sorted_index; A.n_cfg = 1; A.tiles = move_tiles(h); A.recip_blocks = 0;
     A.want_lj = 0; A.want_qq = 1; A.ignore_overlap = 1; A.cur = h->cur;
-    A.seq = ++h->seq;
-    k_move<<<A.tiles, MOVE_BLOCK, 0, h->stream>>>(V, A, h->W);
-    LAUNCH_CHECK();
-    int rc = wait_out(h);
+    int rc = launch_move_on(h, V, A, poly, false);
     if (rc) return rc;
     *row = h->h_out->qq[0];
     return MMC_OK;
@@ -701,13 +787,10 @@ int mmc_create(const mmc_config *cfg, mmc_handle **out)
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail("props", e);
     h->sm_count = prop.multiProcessorCount;
-    if ((e = cudaHostAlloc(&h->h_out, sizeof(MoveOut), cudaHostAllocMapped)) != cudaSuccess) return fail("hostalloc", e);
-    std::memset(h->h_out, 0, sizeof(MoveOut));
-    if ((e = cudaHostGetDevicePointer((void **)&h->W.out, h->h_out, 0)) != cudaSuccess) return fail("mapped ptr", e);
-    const int max_blocks = 2 * h->sm_count + 64 + 1024;
-    if ((e = cudaMalloc(&h->W.partial, sizeof(double4) * max_blocks)) != cudaSuccess) return fail("malloc", e);
-    if ((e = cudaMalloc(&h->W.ticket, sizeof(unsigned))) != cudaSuccess) return fail("malloc", e);
-    if ((e = cudaMemset(h->W.ticket, 0, sizeof(unsigned))) != cudaSuccess) return fail("memset", e);
+    h->max_slots = 2 * h->sm_count + 64 + 1024;
+    if ((e = cudaHostAlloc((void **)&h->h_slots, sizeof(MoveSlot) * h->max_slots, cudaHostAllocMapped)) != cudaSuccess) return fail("hostalloc", e);
+    std::memset(h->h_slots, 0, sizeof(MoveSlot) * h->max_slots);
+    if ((e = cudaHostGetDevicePointer((void **)&h->W.slots, h->h_slots, 0)) != cudaSuccess) return fail("mapped ptr", e);
     for (auto &ev : h->tm.ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("event", e);
     cudaFuncSetAttribute(k_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -723,8 +806,7 @@ int mmc_destroy(mmc_handle *h)
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     free_system(h); free_ewald(h); free_atoms(h);
-    dfree(h->W.partial); dfree(h->W.ticket);
-    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_slots) cudaFreeHost(h->h_slots);
     if (h->h_up) cudaFreeHost(h->h_up);
     for (auto &ev : h->tm.ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -828,6 +910,7 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
             }
     if (h->lj.size() > 64) uniform = false;
     h->uniform = uniform; h->US = uniform ? US : 0;
+    S.uni = h->US;
     h->h_mol.clear();
     if (uniform) {
         if (realloc_needed || true) {
@@ -843,6 +926,8 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
     }
     h->max_cell_cached = -1;
     h->pair_level = 0;
+    if (h->pend_kind == 1) h->pend_kind = 0;
+    if (h->has_ewald) get_erf_poly(h, S.kappa, rc_qq * rc_qq + 100, h->move_poly);
     h->has_system = true;
     h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
     return MMC_OK;
@@ -871,6 +956,7 @@ int mmc_upload_atoms(mmc_handle *h, int64_t n, const double *r, const double *ep
     CK(cudaMemcpyAsync(h->At.es, he.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->has_atoms = true;
+    if (h->pend_kind == 2) h->pend_kind = 0;
     h->trial_pending = false;
     return MMC_OK;
 }
@@ -879,6 +965,7 @@ int mmc_download_system(mmc_handle *h, double *coords, double *com)
 {
     if (!h) return MMC_EINVAL;
     if (!h->has_system) FAIL(MMC_ESTATE, "no molecular system uploaded");
+    { int rcf = flush_pending(h); if (rcf) return rcf; }
     std::vector<double4> hs(h->S.n_sites), hc(h->S.n_mol);
     CK(cudaMemcpyAsync(hs.data(), h->S.site, sizeof(double4) * hs.size(), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(hc.data(), h->S.com, sizeof(double4) * hc.size(), cudaMemcpyDeviceToHost, h->stream));
@@ -892,6 +979,7 @@ int mmc_download_atoms(mmc_handle *h, double *r)
 {
     if (!h || !r) return MMC_EINVAL;
     if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
+    { int rcf = flush_pending(h); if (rcf) return rcf; }
     std::vector<double4> hr(h->At.n);
     CK(cudaMemcpyAsync(hr.data(), h->At.r, sizeof(double4) * hr.size(), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -948,6 +1036,7 @@ int mmc_ewald_prepare(mmc_handle *h, double kappa, int32_t nk, int32_t k_sq_max,
     CK(cudaStreamSynchronize(h->stream));
     h->cur = 0; h->new_valid = false; h->rhok_grid_cap = 0; dfree(h->d_rhok_partial);
     h->has_ewald = true;
+    get_erf_poly(h, kappa, h->S.rc_qq * h->S.rc_qq + 100, h->move_poly);
     int rc = ensure_vec(h);
     if (rc) return rc;
     if (nkvecs) *nkvecs = n;
@@ -1018,6 +1107,7 @@ int mmc_set_molecule(mmc_handle *h, int64_t i, const double com[3], const double
     int rc = check_mol_index(h, i);
     if (rc) return rc;
     if (!com || !sites) FAIL(MMC_EINVAL, "null array");
+    if ((rc = flush_pending(h))) return rc;
     MoveArgs A{};
     A.i = (int)(i - 1);
     std::memcpy(A.site_new, sites, sizeof(double) * 3 * mol_of(h, i - 1).y);
@@ -1031,6 +1121,7 @@ int mmc_recip_long(mmc_handle *h, double *energy)
 {
     if (!h) return MMC_EINVAL;
     if (!h->has_system || !h->has_ewald) FAIL(MMC_ESTATE, "system and Ewald tables required");
+    { int rcf = flush_pending(h); if (rcf) return rcf; }
     int rc = rhok_launch(h, h->S.site, 0, h->S.n_sites, h->S.box, reinterpret_cast<double2 *>(h->d_vec + MMC_NSCAL));
     if (rc) return rc;
     k_rhok_energy<<<1, RHOKE_BLOCK, 0, h->stream>>>(reinterpret_cast<const double2 *>(h->d_vec + MMC_NSCAL),
@@ -1094,10 +1185,7 @@ int mmc_lj_atom(mmc_handle *h, int64_t i, double *pot, double *vir)
     AtomArgs A{};
     A.i = (int)(i - 1); A.n_cfg = 1;
     A.blocks = std::max(1, std::min((h->At.n + ATOM_BLOCK - 1) / ATOM_BLOCK, 2 * h->sm_count));
-    A.seq = ++h->seq;
-    k_move_atom<<<A.blocks, ATOM_BLOCK, 0, h->stream>>>(h->At, A, h->W);
-    LAUNCH_CHECK();
-    int rc = wait_out(h);
+    int rc = launch_move_atom(h, A);
     if (rc) return rc;
     if (pot) *pot = h->h_out->lj_pot[0];
     if (vir) *vir = h->h_out->lj_vir[0];
@@ -1109,6 +1197,7 @@ int mmc_set_atom(mmc_handle *h, int64_t i, const double r[3])
     if (!h) return MMC_EINVAL;
     if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
     if (i < 1 || i > h->At.n || !r) FAIL(MMC_EINVAL, "bad arguments");
+    { int rc = flush_pending(h); if (rc) return rc; }
     k_set_atom<<<1, 1, 0, h->stream>>>(h->At, (int)(i - 1), r[0], r[1], r[2]);
     LAUNCH_CHECK();
     h->trial_pending = false;
@@ -1127,6 +1216,7 @@ int mmc_potential_partial(mmc_handle *h, int32_t style, double *d_partials)
     if (!h) return MMC_EINVAL;
     int rc = style_check(h, style);
     if (rc) return rc;
+    { int rcf = flush_pending(h); if (rcf) return rcf; }
     if (style == MMC_STYLE_LJ_ATOMS || !d_partials) FAIL(MMC_EINVAL, "sharded evaluation is for molecular systems");
     if (!h->uniform) FAIL(MMC_EINVAL, "sharded evaluation needs a uniform topology");
     if ((rc = ensure_vec(h))) return rc;
@@ -1151,6 +1241,7 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
     if (!h) return MMC_EINVAL;
     int rc = style_check(h, style);
     if (rc) return rc;
+    { int rcf = flush_pending(h); if (rcf) return rcf; }
     if (!out) FAIL(MMC_EINVAL, "null argument");
     if (style == MMC_STYLE_LJ_ATOMS) {
         k_atoms_rows<<<std::min(h->At.n, 8 * h->sm_count), 256, 0, h->stream>>>(h->At, h->d_rows); LAUNCH_CHECK();
@@ -1220,10 +1311,7 @@ int mmc_trial_atom(mmc_handle *h, int64_t i, const double r_new[3], mmc_trial_re
     A.i = (int)(i - 1); A.n_cfg = 2;
     A.blocks = std::max(1, std::min((h->At.n + ATOM_BLOCK - 1) / ATOM_BLOCK, 2 * h->sm_count));
     A.r_new[0] = r_new[0]; A.r_new[1] = r_new[1]; A.r_new[2] = r_new[2];
-    A.seq = ++h->seq;
-    k_move_atom<<<A.blocks, ATOM_BLOCK, 0, h->stream>>>(h->At, A, h->W);
-    LAUNCH_CHECK();
-    int rc = wait_out(h);
+    int rc = launch_move_atom(h, A);
     if (rc) return rc;
     std::memset(out, 0, sizeof(*out));
     out->lj_old = h->h_out->lj_pot[0]; out->lj_vir_old = h->h_out->lj_vir[0];
@@ -1237,15 +1325,18 @@ int mmc_accept(mmc_handle *h)
 {
     if (!h) return MMC_EINVAL;
     if (!h->trial_pending) FAIL(MMC_ESTATE, "mmc_accept without a pending trial move");
+    { int rc = flush_pending(h); if (rc) return rc; }      // at most one accepted move rides along
     if (h->trial_kind == 1) {
+        // the write-back itself is deferred: the next move launch carries it in its parameters
         const MoveArgs &A = h->last;
-        k_set_molecule<<<1, 32, 0, h->stream>>>(h->S, A.i, A.com_new[0], A.com_new[1], A.com_new[2], A);
-        LAUNCH_CHECK();
+        h->pend_kind = 1; h->pend_i = A.i; h->pend_ns = mol_of(h, A.i).y;
+        std::memcpy(h->pend_com, A.com_new, sizeof(h->pend_com));
+        std::memcpy(h->pend_site, A.site_new, sizeof(double) * 3 * h->pend_ns);
         if (h->trial_style == MMC_STYLE_EWALD && !h->last_overlap) h->cur ^= 1;   // main.jl:621 as a pointer swap
     } else {
         const AtomArgs &A = h->last_atom;
-        k_set_atom<<<1, 1, 0, h->stream>>>(h->At, A.i, A.r_new[0], A.r_new[1], A.r_new[2]);
-        LAUNCH_CHECK();
+        h->pend_kind = 2; h->pend_i = A.i;
+        std::memcpy(h->pend_com, A.r_new, sizeof(h->pend_com));
     }
     h->trial_pending = false; h->new_valid = false;
     h->cnt.commits++;
@@ -1265,6 +1356,7 @@ int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t st
     if (!h) return MMC_EINVAL;
     int rc = style_check(h, style);
     if (rc) return rc;
+    { int rcf = flush_pending(h); if (rcf) return rcf; }
     if (style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "volume trial is implemented for molecular systems");
     if (!out || !(box_new > 0)) FAIL(MMC_EINVAL, "bad arguments");
     if (!h->uniform) FAIL(MMC_EINVAL, "volume trial needs a uniform topology");
@@ -1294,6 +1386,7 @@ int mmc_volume_accept(mmc_handle *h)
 {
     if (!h) return MMC_EINVAL;
     if (!h->vol_pending) FAIL(MMC_ESTATE, "mmc_volume_accept without a pending volume trial");
+    { int rcf = flush_pending(h); if (rcf) return rcf; }
     k_apply_scale<<<(h->S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->S, h->vol_f);
     LAUNCH_CHECK();
     h->S.box = h->vol_box;
@@ -1307,6 +1400,7 @@ int mmc_volume_accept(mmc_handle *h)
         CK(cudaMemcpyAsync(h->S.cfac, h->cfac.data(), sizeof(double) * h->S.nkvecs, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    if (h->has_ewald) get_erf_poly(h, h->S.kappa, h->S.rc_qq * h->S.rc_qq + 100, h->move_poly);
     h->vol_pending = false; h->new_valid = false; h->trial_pending = false;
     h->cnt.commits++;
     return MMC_OK;

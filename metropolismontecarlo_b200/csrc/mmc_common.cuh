@@ -22,6 +22,7 @@
 // ---------------------------------------------------------------------------------------
 struct DevSystem {
     int n_mol, n_sites, max_sites, n_types;
+    int uni;                 // > 0: uniform topology, molecule m owns sites [m*uni, (m+1)*uni)
     double4 *site;
     double4 *com;
     int2 *mol;
@@ -93,6 +94,26 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch)
         }
     }
     __syncthreads();
+}
+
+// Deterministic block sum whose result is valid in EVERY thread.
+template <int NV, int BLOCK>
+__device__ __forceinline__ void block_sum_all(double (&v)[NV], double *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = BLOCK / 32;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = warp_sum(v[i]);
+        if (lane == 0) scratch[i * NW + warp] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = 0.0;
+        for (int w = 0; w < NW; ++w) s += scratch[i * NW + w];
+        v[i] = s;
+    }
 }
 
 struct cplx { double re, im; };
