@@ -575,6 +575,7 @@ struct GatherArgs {
     double f;               // box_new / box (1.0: no volume change)
     double4 *scom, *ssite;
     unsigned long long *max_dev_bits;   // atomicMax over the bits of max |site-COM| component
+    unsigned int *ovl;                  // per-molecule overlap flags, cleared here
 };
 
 // cell-sorted copy of the state; for a volume trial the COMs are scaled by f and the sites
@@ -585,6 +586,7 @@ __global__ void k_gather(GatherArgs A)
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= A.n_mol) return;
     const int m = A.perm ? A.perm[p] : p;
+    A.ovl[p] = 0u;
     const double4 c = A.com[m];
     double4 cn = c;
     cn.x = A.f * c.x; cn.y = A.f * c.y; cn.z = A.f * c.z;

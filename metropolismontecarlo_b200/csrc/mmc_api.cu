@@ -99,6 +99,7 @@ struct mmc_handle {
     int last_ncd = 0;
     int max_cell_cached = -1;    // largest cell population seen at the last binning (-1: unknown)
     int *d_maxcount = nullptr;
+    int *d_flags = nullptr;      // [maxdev(2) | novl | errflag | maxcount | 3 spare | count(ncell) | fill(ncell)]
     int4 *d_units = nullptr;
     int4 *d_slots = nullptr;
     long long slots_cap = 0;
@@ -166,9 +167,10 @@ void free_system(mmc_handle *h)
     dfree(h->S.site); dfree(h->S.com); dfree(h->S.mol); dfree(h->S.atype);
     dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums); dfree(h->d_raw); dfree(h->d_info); dfree(h->d_qpart);
     h->raw_bytes = 0; h->cap_mol = 0; h->cap_sites = 0;
-    dfree(h->d_cell_of); dfree(h->d_count); dfree(h->d_start); dfree(h->d_fill); dfree(h->d_perm);
-    dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl); dfree(h->d_novl);
-    dfree(h->d_maxdev); dfree(h->d_rhok_partial); dfree(h->d_maxcount); dfree(h->d_errflag); dfree(h->d_units); dfree(h->d_slots);
+    dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
+    h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
+    dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl);
+    dfree(h->d_rhok_partial); dfree(h->d_units); dfree(h->d_slots);
     h->units_cap = 0; h->slots_cap = 0;
     h->max_cell_cached = -1;
     h->has_system = false;
@@ -437,6 +439,16 @@ void pairs_fast_set_attributes()
 #undef X
 }
 
+void bind_flags(mmc_handle *h, int ncell)
+{
+    h->d_maxdev = reinterpret_cast<double *>(h->d_flags);
+    h->d_novl = reinterpret_cast<unsigned *>(h->d_flags + 2);
+    h->d_errflag = reinterpret_cast<unsigned *>(h->d_flags + 3);
+    h->d_maxcount = h->d_flags + 4;
+    h->d_count = h->d_flags + 8;
+    h->d_fill = h->d_flags + 8 + ncell;
+}
+
 // smooth part of erfc(κr)/r on the domain r² < r_cut²+100 the reference imposes (ewalds.jl:362);
 // fits are cached on a geometric grid of domain ends so NPT box changes reuse them
 void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P)
@@ -466,25 +478,20 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     if (ncd > 128) ncd = 128;
     const bool cells = ncd >= 3;
     CK(cudaMemsetAsync(d_vec, 0, (MMC_NSCAL + 2 * (size_t)std::max(S.nkvecs, 1)) * sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->d_maxdev, 0, sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->d_novl, 0, sizeof(unsigned), h->stream));
-    CK(cudaMemsetAsync(h->d_ovl, 0, sizeof(unsigned) * S.n_mol, h->stream));
-    CK(cudaMemsetAsync(h->d_errflag, 0, sizeof(unsigned), h->stream));
-    CK(cudaMemsetAsync(h->d_maxcount, 0, sizeof(int), h->stream));
     if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
     const int tb = 256, gm = (S.n_mol + tb - 1) / tb;
     long long n_units;
     if (cells) {
         const int ncell = ncd * ncd * ncd;
         if (ncell > h->ncell_cap) {
-            dfree(h->d_count); dfree(h->d_start); dfree(h->d_fill);
-            CK(cudaMalloc(&h->d_count, sizeof(int) * ncell));
+            // one block: [flags(8 ints) | count(ncell) | fill(ncell)] so that one memset clears it all
+            dfree(h->d_flags); dfree(h->d_start);
+            CK(cudaMalloc(&h->d_flags, sizeof(int) * (8 + 2 * (size_t)ncell)));
             CK(cudaMalloc(&h->d_start, sizeof(int) * (ncell + 1)));
-            CK(cudaMalloc(&h->d_fill, sizeof(int) * ncell));
             h->ncell_cap = ncell;
         }
-        CK(cudaMemsetAsync(h->d_count, 0, sizeof(int) * ncell, h->stream));
-        CK(cudaMemsetAsync(h->d_fill, 0, sizeof(int) * ncell, h->stream));
+        bind_flags(h, ncell);
+        CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * (8 + 2 * (size_t)ncell), h->stream));
         // fractional COM coordinates are invariant under the volume scaling: bin the resident state
         CellArgs C{S.com, S.n_mol, ncd, (double)ncd / S.box, h->d_cell_of, h->d_count, h->d_start,
                    h->d_fill, h->d_perm, h->d_maxcount};
@@ -493,18 +500,21 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         k_cell_fill<<<gm, tb, 0, h->stream>>>(C); LAUNCH_CHECK();
         k_cell_sort<<<(ncell * 32 + tb - 1) / tb, tb, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
         n_units = 14LL * ncell;
-        if (h->max_cell_cached < 0 || E.world > 1) {   // unknown density (or sharded: no re-run possible)
+        if (h->max_cell_cached < 0) {   // unknown density: one synchronous read-back, cached afterwards
             int mc = 0;
             CK(cudaMemcpyAsync(&mc, h->d_maxcount, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             h->max_cell_cached = mc;
         }
     } else {
+        if (!h->d_flags) CK(cudaMalloc(&h->d_flags, sizeof(int) * 8));
+        bind_flags(h, 0);
+        CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 8, h->stream));
         const long long nt = (S.n_mol + PAIR_TILE - 1) / PAIR_TILE;
         n_units = nt * (nt + 1) / 2;
     }
     GatherArgs G{S.com, S.site, cells ? h->d_perm : nullptr, S.n_mol, US, E.f, h->d_scom, h->d_ssite,
-                 reinterpret_cast<unsigned long long *>(h->d_maxdev)};
+                 reinterpret_cast<unsigned long long *>(h->d_maxdev), h->d_ovl};
     k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
 
@@ -621,6 +631,7 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
         if (h->h_vec[7] != 0.0) return 1;      // a cell outgrew the fast kernel's tile: caller re-runs
     } else if (h->h_vec[7] != 0.0) {           // summed over ranks: every rank takes the same branch
         if (++h->pair_level > 2) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        h->max_cell_cached = -1;
         return 1;                               // MMC_RETRY: caller repeats partial + all-reduce + finalize
     }
     double lj_pot = h->h_vec[0], lj_vir = h->h_vec[1], coul = h->h_vec[2];
@@ -854,10 +865,6 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         h->pair_grid = 4 * h->sm_count;
         CK(cudaMalloc(&h->d_pair_partial, sizeof(double4) * h->pair_grid));
         CK(cudaMalloc(&h->d_ovl, sizeof(unsigned) * n_mol));
-        CK(cudaMalloc(&h->d_novl, sizeof(unsigned)));
-        CK(cudaMalloc(&h->d_maxdev, sizeof(double)));
-        CK(cudaMalloc(&h->d_maxcount, sizeof(int)));
-        CK(cudaMalloc(&h->d_errflag, sizeof(unsigned)));
         h->ncell_cap = 0; h->rhok_grid_cap = 0;
         h->cap_mol = (int)n_mol; h->cap_sites = (int)n_sites;
         if (!h->h_up) CK(cudaHostAlloc((void **)&h->h_up, sizeof(*h->h_up), cudaHostAllocDefault));
