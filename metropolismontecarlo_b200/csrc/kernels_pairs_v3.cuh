@@ -192,14 +192,24 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs_v3(const __grid_constan
             const double4 cb = s_comB[qi < nB ? qi : 0];
             // lanes past the end of B never pass; in the home cell itself (q < self_n) only p < q passes
             const int p_lim = (qi >= nB) ? 0 : (qi < self_n ? qi : 0x7fffffff);
-            for (int p = (warp + ib) & (PAIR_WARPS - 1); p < nA; p += PAIR_WARPS) {
+            // two rows per iteration: two independent load → distance → ballot chains in flight
+            for (int p = (warp + ib) & (PAIR_WARPS - 1); p < nA; p += 2 * PAIR_WARPS) {
+                const int p2 = p + PAIR_WARPS;
                 const double4 ca = s_comA[p];
+                const double4 ca2 = s_comA[p2 < nA ? p2 : p];
                 const double dx = cb.x - ca.x, dy = cb.y - ca.y, dz = cb.z - ca.z;
+                const double ex = cb.x - ca2.x, ey = cb.y - ca2.y, ez = cb.z - ca2.z;
                 const long long r2b = __double_as_longlong(dx * dx + dy * dy + dz * dz);
+                const long long s2b = __double_as_longlong(ex * ex + ey * ey + ez * ez);
                 const bool pass = (r2b < A.rcqq_bits) && (p < p_lim);
+                const bool pass2 = (s2b < A.rcqq_bits) && (p2 < p_lim) && (p2 < nA);
                 const unsigned m = __ballot_sync(0xffffffffu, pass);
-                if (pass) q[(tail + __popc(m & ((1u << lane) - 1u))) & (V3_QCAP - 1)] = (unsigned)p | ((unsigned)qi << 7);
+                const unsigned m2 = __ballot_sync(0xffffffffu, pass2);
+                const unsigned lt = (1u << lane) - 1u;
+                if (pass) q[(tail + __popc(m & lt)) & (V3_QCAP - 1)] = (unsigned)p | ((unsigned)qi << 7);
                 tail += __popc(m);
+                if (pass2) q[(tail + __popc(m2 & lt)) & (V3_QCAP - 1)] = (unsigned)p2 | ((unsigned)qi << 7);
+                tail += __popc(m2);
             }
             __syncwarp();
             while (tail - head >= 32) { consume(head, 32); head += 32; }   // full rounds only

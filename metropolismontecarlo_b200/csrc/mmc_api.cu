@@ -104,6 +104,7 @@ struct mmc_handle {
     int4 *d_slots = nullptr;
     long long slots_cap = 0;
     int use_rhok_v2 = 1;
+    int v3_ctas_per_sm = 2;
     int use_v3 = 1;              // 0 disables the v3 pair kernel (A/B testing)
     int pair_level = 0;          // 0: v3 allowed, 1: k_pairs_fast, 2: general k_pairs (raised when a kernel declines the state)
     long long units_cap = 0;
@@ -556,7 +557,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(P, h->d_slots, ncd * ncd * ncd);
         LAUNCH_CHECK();
         if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-        grid = (int)std::max(1LL, std::min<long long>(2 * h->sm_count, my_units));
+        grid = (int)std::max(1LL, std::min<long long>(h->v3_ctas_per_sm * h->sm_count, my_units));
         launch_pairs_v3(P.ep.deg, grid, h->stream, P, h->d_slots);
     } else if (tile) {
         if (n_units > h->units_cap) {
