@@ -196,6 +196,14 @@ int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_max, double 
                        double e0, double v0, uint8_t *accepted, double *delta,
                        mmc_loop_stats *stats);
 
+/* The reference's random stream without Julia: the first `n` values, after skipping `skip`, that
+ * `Random.seed!(seed); rand()` yields in the Julia the reference targets (1.x <= 1.6, global
+ * MersenneTwister = dSFMT-19937 seeded by init_by_array(make_seed(seed))); `rand(Float64,3)`
+ * (Ewald/auxillary.jl:99, quaternions.jl:64) consumes three consecutive values of the same
+ * stream.  seed = 11234 is the reference's own (Ewald/main.jl:36, Monatomic/mainMonatomic.jl:15).
+ * Host code; feeds mmc_loop_run / mmc_loop_run_atoms. */
+int mmc_julia_rand(uint64_t seed, int64_t skip, double *out, int64_t n);
+
 /* ---- instrumentation ------------------------------------------------------------------- */
 typedef struct {
     int64_t kernel_launches;     /* kernels of this library launched on this handle */

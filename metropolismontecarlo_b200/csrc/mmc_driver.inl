@@ -8,6 +8,8 @@
 // in the reference's draw order, so a recorded Julia stream reproduces the
 // reference trajectory.  All energies come from the CUDA kernels; nothing here evaluates one.
 
+#include "julia_mt.h"
+
 namespace {
 
 struct UStream {
@@ -204,4 +206,14 @@ extern "C" int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_m
     st->uniforms_used = us.pos;
     st->dr_max = dr_max;
     return ret;
+}
+
+extern "C" int mmc_julia_rand(uint64_t seed, int64_t skip, double *out, int64_t n)
+{
+    if (skip < 0 || n < 0 || (n > 0 && !out)) return MMC_EINVAL;
+    julia_mt::State s;
+    julia_mt::seed(s, seed);
+    for (int64_t k = 0; k < skip; ++k) (void)julia_mt::next(s);
+    for (int64_t k = 0; k < n; ++k) out[k] = julia_mt::next(s);
+    return MMC_OK;
 }

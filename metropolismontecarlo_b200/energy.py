@@ -286,6 +286,16 @@ class Engine:
         return t.value
 
 
+def julia_rand(seed: int, n: int, skip: int = 0) -> np.ndarray:
+    """`Random.seed!(seed); [rand() for _ in 1:n]` of the reference's Julia (MersenneTwister /
+    dSFMT-19937) via mmc_julia_rand — the uniform stream Loop() consumes (Ewald/main.jl:36,516)."""
+    out = np.empty(n, dtype=np.float64)
+    rc = _lib.load().mmc_julia_rand(C.c_uint64(seed), C.c_int64(skip), out.ctypes.data_as(_lib.c_double_p), C.c_int64(n))
+    if rc:
+        raise _lib.MMCError(rc, "mmc_julia_rand: bad arguments")
+    return out
+
+
 def water_engine(ms: MolecularSystem, r_cut: float = 10.0, alpha: float = ALPHA, nk: int = NK,
                  k_sq_max: int = K_SQ_MAX, **kw) -> Engine:
     """Engine set up like Ewald/main.jl:285-303: kappa = alpha/box, nk = 5, k² < 27."""

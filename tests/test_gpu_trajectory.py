@@ -1,6 +1,8 @@
 """Trajectory parity: the library's host driver (mmc_loop_run: one fused trial-move launch +
 accept/reject per move) against the oracle's restatement of Ewald/main.jl Loop(), both fed the
-same recorded stream of uniforms in the reference's draw order.
+same stream of uniforms in the reference's draw order.  The stream is the
+reference's own: Julia's MersenneTwister seeded with 11234 (Ewald/main.jl:36), reproduced by
+mmc_julia_rand and, independently, by oracle/julia_rng.py (pinned to Julia's printed values).
 
 Bar (north star): identical accept/reject sequence for the first 10^4 moves; per-move deltas
 within 1e-10 relative of the energy scale; Σ accepted deltas == fresh potential() (the reference's
@@ -9,7 +11,7 @@ import numpy as np
 import pytest
 
 from metropolismontecarlo_b200 import systems
-from metropolismontecarlo_b200.energy import LoopParams
+from metropolismontecarlo_b200.energy import LoopParams, julia_rand
 from oracle import oracle as ora
 from tests.util import ora_ewald, ora_system, rel
 
@@ -23,7 +25,9 @@ def test_accept_reject_sequence_coord750(style, sid):
     from metropolismontecarlo_b200.energy import water_engine
     ms = systems.load_nist(4)
     rc, T = 10.0, 298.15
-    u = np.random.default_rng(11234).random(8 * N_MOVES)
+    u = julia_rand(11234, 8 * N_MOVES)              # Random.seed!(11234), Ewald/main.jl:36
+    from oracle.julia_rng import julia_rand as ora_rand
+    assert np.array_equal(u[:2000], ora_rand(11234, 2000))
     # ---- oracle
     s = ora_system(ms)
     ew = ora_ewald(ms.box)
@@ -85,7 +89,7 @@ def test_monatomic_lj_trajectory():
     """Monatomic/mainMonatomic.jl:373-413 with 1000 atoms, rho*=0.75, T*=1, dr_max = L/30."""
     from metropolismontecarlo_b200.energy import Engine
     at = systems.lj_lattice(1000, 0.75, 2.5)
-    u = np.random.default_rng(11234).random(5 * N_MOVES)
+    u = julia_rand(11234, 5 * N_MOVES)              # Random.seed!(11234), mainMonatomic.jl:15
     e0, v0 = ora.potential_atoms(at.r, at.eps, at.sig, at.box, at.r_cut, 4)
     r_o = at.r.copy()
     rc_o, acc_o, del_o, st_o = ora.loop_atoms(r_o, at.eps, at.sig, at.box, at.r_cut, 1.0, at.box / 30, u, N_MOVES, e0, v0)

@@ -224,3 +224,28 @@ def test_loop_invariant_sum_of_deltas_equals_recompute():
     ew2 = ora_ewald(ms.box)
     ora.RecipLong(ew2, s.coords, s.charge, ms.box)
     assert np.allclose(ew.sum_old, ew2.sum_old, rtol=0, atol=1e-9)
+
+
+# ---- the reference's random stream (Julia MersenneTwister = dSFMT-19937) -------------------
+
+def test_julia_rng_known_answers():
+    """Values Julia (1.x <= 1.6) prints: the manual's `rand(MersenneTwister(1234), 2)` and
+    `Random.seed!(0); rand(4)`.  One matching Float64 already fixes seeding, recursion and masks."""
+    from oracle.julia_rng import julia_rand
+    assert julia_rand(1234, 3).tolist() == [0.5908446386657102, 0.7667970365022592, 0.5662374165061859]
+    assert julia_rand(0, 4).tolist() == [0.8236475079774124, 0.9103565379264364, 0.16456579813368521,
+                                         0.17732884646626457]
+
+
+def test_julia_rng_library_matches_oracle():
+    """mmc_julia_rand (host C in the library's driver stand-in) == the oracle's Python restatement,
+    across several state regenerations (382 doubles each), a 64-bit seed, and with `skip`."""
+    from metropolismontecarlo_b200.energy import julia_rand as lib_rand
+    from oracle.julia_rng import julia_rand
+    for seed in (0, 1234, 11234, (1 << 32) + 5, (1 << 63) + 12345):
+        want = julia_rand(seed, 1500)
+        got = lib_rand(seed, 1500)
+        assert np.array_equal(want, got), seed
+        assert np.array_equal(lib_rand(seed, 400, skip=381), want[381:781])
+    u = lib_rand(11234, 200000)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3
