@@ -220,6 +220,10 @@ int mmc_last_timings(mmc_handle *h, float *ms4);
  * box edge, and the pair kernel used (3 = k_pairs_v3, 64/128 = k_pairs_fast tile, 0 = k_pairs) */
 int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, int32_t *cells_per_dim,
                        int32_t *pair_kernel);
+/* test/profiling knobs. key "pair_level": first full-energy pair kernel the fallback chain may use
+ * (0 = k_pairs_v4, 1 = k_pairs_v3, 2 = k_pairs_fast, 3 = general k_pairs); results are identical
+ * within rounding, only speed differs. */
+int mmc_debug_set(mmc_handle *h, const char *key, int64_t value);
 /* FP64 DFMA-chain microbenchmark: measured FP64 FMA throughput of the device [TFLOP/s] */
 int mmc_measure_fp64_peak(mmc_handle *h, double *tflops);
 

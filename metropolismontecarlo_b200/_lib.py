@@ -110,6 +110,7 @@ SIGNATURES = {
     "mmc_set_timing": (C.c_int, [H, C.c_int32]),
     "mmc_last_timings": (C.c_int, [H, c_float_p]),
     "mmc_last_eval_info": (C.c_int, [H, c_int64_p, c_int32_p, c_int32_p, c_int32_p]),
+    "mmc_debug_set": (C.c_int, [H, C.c_char_p, C.c_int64]),
     "mmc_measure_fp64_peak": (C.c_int, [H, c_double_p]),
 }
 

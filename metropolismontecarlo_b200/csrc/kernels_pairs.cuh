@@ -48,6 +48,9 @@ struct PairArgs {
     const int4 *units;         // fast kernel: {a_lo, b_lo, nA | nB<<16, self | codes<<1} per unit (k_units_build)
     long long rclj_bits, rcqq_bits, cutlj_bits, cutqq_bits;   // bit patterns of r_cut² and r_cut²+100
     double lj_eps_tab[16], lj_sig_tab[16];   // v3: LJ table by (site a, site b) of the uniform molecule, 0 = inactive
+    double qq_tab[9];          // v4: q_a q_b of the uniform 3-site molecule (launch constants)
+    unsigned qq_negmask;       // v4: bit j set when qq_tab[j] < 0 (the overlap rule only fires there)
+    float gate_rc2f;           // v4: conservative FP32 COM-gate threshold (>= r_cut² + worst-case FP32 error)
     ErfPoly ep;                // smooth part of erfc(κr)/r as one polynomial (deg 0: use erfc())
 };
 

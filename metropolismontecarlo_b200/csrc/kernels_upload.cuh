@@ -14,7 +14,7 @@ struct RepackArgs {
     double4 *site, *dcom;
     int2 *mol;
     int *dtype;
-    int *info;     // [0] error bits, [1] max sites per molecule, [2] non-uniform flag
+    int *info;     // [0] error bits, [1] max sites per molecule, [2] non-uniform flag, [3] charges differ between molecules
 };
 
 enum { REPACK_BAD_ATYPE = 1, REPACK_BAD_RANGE = 2, REPACK_TOO_MANY_SITES = 4, REPACK_COM_OUTSIDE = 8 };
@@ -30,6 +30,7 @@ __global__ void k_repack(RepackArgs A)
         A.dtype[t] = (int)(ty - 1);
         A.site[t] = make_double4(A.coords[3 * (size_t)t], A.coords[3 * (size_t)t + 1], A.coords[3 * (size_t)t + 2], A.charge[t]);
         if (US > 0 && ty != A.atype[t % US]) atomicOr(&A.info[2], 1);   // type sequence differs from molecule 1
+        if (US > 0 && A.charge[t] != A.charge[t % US]) atomicOr(&A.info[3], 1);
     }
     if (t < A.n_mol) {
         const long long f = A.first_atom[t], l = A.last_atom[t];

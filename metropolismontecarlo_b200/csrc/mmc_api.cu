@@ -4,6 +4,7 @@
 #include "kernels_move.cuh"
 #include "kernels_pairs.cuh"
 #include "kernels_pairs_v3.cuh"
+#include "kernels_pairs_v4.cuh"
 #include "kernels_recip.cuh"
 #include "kernels_upload.cuh"
 
@@ -106,7 +107,11 @@ struct mmc_handle {
     int use_rhok_v2 = 1;
     int v3_ctas_per_sm = 2;
     int use_v3 = 1;              // 0 disables the v3 pair kernel (A/B testing)
-    int pair_level = 0;          // 0: v3 allowed, 1: k_pairs_fast, 2: general k_pairs (raised when a kernel declines the state)
+    int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v4, 1 k_pairs_v3, 2 k_pairs_fast, 3 general k_pairs
+                                 // (raised when a kernel declines the state)
+    int pair_floor = 0;          // lowest level the chain may start from (mmc_debug_set "pair_level": A/B tests)
+    bool uniform_q = false;      // every molecule carries the charges of molecule 1 (per site index)
+    double q_site[MMC_MAX_SITES] = {0};
     long long units_cap = 0;
     unsigned int *d_errflag = nullptr;
     std::vector<std::pair<double, ErfPoly>> poly_cache;
@@ -428,8 +433,17 @@ void launch_pairs_v3(int deg, int grid, cudaStream_t st, const PairArgs &P, cons
     MMC_FOR_POS_DEGS(X)
 #undef X
 }
+void launch_pairs_v4(int deg, int grid, cudaStream_t st, const PairArgs &P, const int4 *slots)
+{
+#define X(D) if (deg == D) { k_pairs_v4<D><<<grid, V4_BLOCK, V4_SMEM, st>>>(P, slots); return; }
+    MMC_FOR_POS_DEGS(X)
+#undef X
+}
 void pairs_fast_set_attributes()
 {
+#define X(D) cudaFuncSetAttribute(k_pairs_v4<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM);
+    MMC_FOR_POS_DEGS(X)
+#undef X
 #define X(D) cudaFuncSetAttribute(k_pairs_v3<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM);
     MMC_FOR_POS_DEGS(X)
 #undef X
@@ -469,7 +483,7 @@ void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P)
 // [MMC_NSCAL ..) ρ(k) partial (re,im).
 int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
 {
-    const bool force_general = h->pair_level >= 2;
+    const bool force_general = h->pair_level >= 3;
     if (!h->uniform) FAIL(MMC_EINVAL, "pair kernel needs a uniform topology (internal)");
     const DevSystem &S = h->S;
     const int US = h->US;
@@ -538,16 +552,32 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     if (want_qq) get_erf_poly(h, E.kappa, S.rc_qq * S.rc_qq + 100, P.ep);
     const int max_cell = cells ? h->max_cell_cached : PAIR_TILE;
     // v3 serves water-like molecules: 3 sites, LJ only on site pair (0,0), equal cut-offs, Coulomb on, polynomial erf
-    const bool v3 = cells && US == 3 && !force_general && h->use_v3 && h->pair_level == 0 && max_cell <= V3_ACAP && want_qq &&
-                    S.rc_lj == S.rc_qq && P.ep.deg > 0 && h->lj.size() == 1 && h->lj[0].a == 0 && h->lj[0].b == 0;
-    const int tile = (US == 3 && !force_general && !v3) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
-    if (v3) n_units = (long long)V3_GROUPS * ncd * ncd * ncd;
+    const bool water = cells && US == 3 && !force_general && h->pair_level <= 1 && max_cell <= V3_ACAP && want_qq &&
+                       S.rc_lj == S.rc_qq && P.ep.deg > 0 && h->lj.size() == 1 && h->lj[0].a == 0 && h->lj[0].b == 0;
+    // v4 additionally needs identical per-site charges (they become launch constants)
+    const bool v4 = water && h->pair_level == 0 && h->uniform_q;
+    const bool v3 = water && !v4 && h->use_v3;
+    const int tile = (US == 3 && !force_general && !v3 && !v4) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
+    if (v3 || v4) n_units = (long long)V3_GROUPS * ncd * ncd * ncd;
+    if (v4) {
+        P.qq_negmask = 0;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                P.qq_tab[a * 3 + b] = h->q_site[a] * h->q_site[b];
+                if (P.qq_tab[a * 3 + b] < 0.0) P.qq_negmask |= 1u << (a * 3 + b);
+            }
+        // conservative FP32 gate: |d²_f32 - d²| <= 2*sqrt(3)*rc*delta + 3*delta² + 3*2^-23*rc², delta = 6*2^-24*edge
+        // (two roundings to float of coordinates <= 2*edge, one float subtraction of <= 3*edge); 4x safety
+        const double edge = E.box / ncd, rc = S.rc_qq, delta = 6.0 * edge / 16777216.0;
+        const double margin = 4.0 * (2.0 * 1.7320508075688772 * rc * delta + 3.0 * delta * delta + 3.6e-7 * rc * rc);
+        P.gate_rc2f = std::nextafterf((float)(rc * rc + margin), INFINITY);
+    }
     P.unit_begin = n_units * E.rank / E.world;
     P.unit_end = n_units * (E.rank + 1) / E.world;
     const long long my_units = P.unit_end - P.unit_begin;
     int grid;
     if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-    if (v3) {
+    if (v3 || v4) {
         const long long nslots = 14LL * ncd * ncd * ncd;
         if (nslots > h->slots_cap) {
             dfree(h->d_slots);
@@ -557,8 +587,13 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(P, h->d_slots, ncd * ncd * ncd);
         LAUNCH_CHECK();
         if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-        grid = (int)std::max(1LL, std::min<long long>(h->v3_ctas_per_sm * h->sm_count, my_units));
-        launch_pairs_v3(P.ep.deg, grid, h->stream, P, h->d_slots);
+        if (v4) {
+            grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
+            launch_pairs_v4(P.ep.deg, grid, h->stream, P, h->d_slots);
+        } else {
+            grid = (int)std::max(1LL, std::min<long long>(h->v3_ctas_per_sm * h->sm_count, my_units));
+            launch_pairs_v3(P.ep.deg, grid, h->stream, P, h->d_slots);
+        }
     } else if (tile) {
         if (n_units > h->units_cap) {
             dfree(h->d_units);
@@ -584,7 +619,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
     k_pair_reduce<<<1, 256, 0, h->stream>>>(h->d_pair_partial, grid, h->d_novl, h->d_maxcount, h->d_errflag, d_vec);
     LAUNCH_CHECK();
-    h->last_fast = v3 ? 3 : tile;
+    h->last_fast = v4 ? 4 : (v3 ? 3 : tile);
     h->last_mode = cells ? 0 : 1;
     h->last_ncd = ncd;
 
@@ -631,7 +666,7 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
         if (h->last_mode == 0) h->max_cell_cached = (int)h->h_vec[6];
         if (h->h_vec[7] != 0.0) return 1;      // a cell outgrew the fast kernel's tile: caller re-runs
     } else if (h->h_vec[7] != 0.0) {           // summed over ranks: every rank takes the same branch
-        if (++h->pair_level > 2) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        if (++h->pair_level > 3) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         h->max_cell_cached = -1;
         return 1;                               // MMC_RETRY: caller repeats partial + all-reduce + finalize
     }
@@ -907,6 +942,8 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
     h->sum_q = h->h_up->qs[0]; h->sum_q2 = h->h_up->qs[1];
     bool uniform = h->h_up->info[2] == 0;
     const int US = (int)(last_atom[0] - first_atom[0] + 1);
+    h->uniform_q = uniform && h->h_up->info[3] == 0 && US <= MMC_MAX_SITES;
+    if (h->uniform_q) for (int a = 0; a < US; ++a) h->q_site[a] = charge[a];
     // LJ-active site-type combinations of the uniform molecule (ε_ij > 0.001, energy.jl:270)
     h->lj.clear();
     if (uniform)
@@ -933,7 +970,7 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         for (int64_t m = 0; m < n_mol; ++m) h->h_mol[m] = make_int2((int)(first_atom[m] - 1), (int)(last_atom[m] - first_atom[m] + 1));
     }
     h->max_cell_cached = -1;
-    h->pair_level = 0;
+    h->pair_level = h->pair_floor;
     if (h->pend_kind == 1) h->pend_kind = 0;
     if (h->has_ewald) get_erf_poly(h, S.kappa, rc_qq * rc_qq + 100, h->move_poly);
     h->has_system = true;
@@ -1268,7 +1305,7 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
     rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
     while (rc == 1) {    // the chosen pair kernel declined this state (dense cell / wrapped molecules): next level
-        if (++h->pair_level > 2) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        if (++h->pair_level > 3) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
     }
@@ -1381,7 +1418,7 @@ int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t st
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
     rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
     while (rc == 1) {
-        if (++h->pair_level > 2) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        if (++h->pair_level > 3) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
     }
@@ -1452,6 +1489,18 @@ int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, i
     if (mode) *mode = h->last_mode;
     if (cells_per_dim) *cells_per_dim = h->last_ncd;
     return MMC_OK;
+}
+
+int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
+{
+    if (!h || !key) return MMC_EINVAL;
+    const std::string k(key);
+    if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v4 .. 3 general)
+        if (value < 0 || value > 3) FAIL(MMC_EINVAL, "pair_level must be 0..3");
+        h->pair_floor = (int)value; h->pair_level = (int)value;
+        return MMC_OK;
+    }
+    FAIL(MMC_EINVAL, "unknown debug key");
 }
 
 int mmc_measure_fp64_peak(mmc_handle *h, double *tflops)

@@ -300,6 +300,18 @@ def test_config_d_4000_molecules():
     eng.close()
 
 
+def npr_pairs_in_cutoff(com, box, rc):
+    """unordered molecule pairs with |COM_ij|² < rc² under the reference's minimum image (numpy, O(N²) in blocks)"""
+    from oracle import numpy_ref as npr
+    n, tot = len(com), 0
+    for lo in range(0, n, 256):
+        d = npr.vector1d(com[lo:lo + 256, None, :], com[None, :, :], box)
+        r2 = (d * d).sum(-1)
+        idx = np.arange(lo, min(lo + 256, n))[:, None]
+        tot += int(((r2 < rc * rc) & (np.arange(n)[None, :] > idx)).sum())
+    return tot
+
+
 def test_pair_kernel_variants_agree_with_oracle():
     """Every pair kernel (v3 water kernel, k_pairs_fast tiles, general k_pairs) on a disordered box:
     2197 SPC/E molecules, lattice COMs displaced by up to 1.2 Å, so cells are unevenly filled."""
@@ -312,11 +324,17 @@ def test_pair_kernel_variants_agree_with_oracle():
     ms.com = newcom
     s = ora_system(ms)
     want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
+    want_pairs = npr_pairs_in_cutoff(ms.com, ms.box, 10.0)
     eng = water_engine(ms, 10.0)
-    got = eng.potential("ewald")
-    assert eng.last_eval_info()["pair_kernel"] == "k_pairs_v3", eng.last_eval_info()
-    _check_props(got, want)
-    _check_props(eng.potential("wolf"), ora.potential_wolf(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8))
+    want_wolf = ora.potential_wolf(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
+    for level, name in ((0, "k_pairs_v4"), (1, "k_pairs_v3"), (2, "k_pairs_fast<64>"), (3, "k_pairs")):
+        eng.debug_set("pair_level", level)
+        got = eng.potential("ewald")
+        assert eng.last_eval_info()["pair_kernel"] == name, (level, eng.last_eval_info())
+        assert eng.last_eval_info()["pairs_in_cutoff"] == want_pairs
+        _check_props(got, want)
+        _check_props(eng.potential("wolf"), want_wolf)
+    eng.debug_set("pair_level", 0)
     lj = eng.potential("lj")                       # no Coulomb: served by k_pairs_fast
     assert eng.last_eval_info()["pair_kernel"].startswith("k_pairs_fast") and rel(lj.energy, want.lj) < RTOL
     eng.close()
