@@ -15,12 +15,18 @@
 #include <vector>
 
 #define MMC_ERF_MAXDEG 44
+#define MMC_ERF_DIRECT_MAXDEG 12
 
 struct ErfPoly {
     int deg;                 // 0: no usable fit, kernels fall back to erfc()
     double kappa, kappa2;    // κ, κ²
     double scale;            // 2 / v_max
     double c[MMC_ERF_MAXDEG + 1];
+    // "direct" form for small domains (big boxes: v_max = κ²(r_cut²+100) ≲ 3): E(v) ≈ Σ a_k v^k by
+    // plain Horner in v, so a kernel can fold κ into the coefficients and run Horner in r² itself
+    // (no mapped variable, exact degree, no padding).  ddeg = 0: not accurate enough, use c[].
+    int ddeg;
+    double a[MMC_ERF_DIRECT_MAXDEG + 1];
 };
 
 namespace erfpoly {
@@ -69,6 +75,42 @@ inline double eval(const ErfPoly &P, double v)
     return p;
 }
 
+inline double eval_direct(const ErfPoly &P, double v)
+{
+    double p = P.a[P.ddeg];
+    for (int k = P.ddeg - 1; k >= 0; --k) p = std::fma(p, v, P.a[k]);
+    return p;
+}
+
+// Direct (monomial-in-v) form: the degree-D Chebyshev interpolant re-expanded from s = σv − 1 to v in
+// long double; accepted when the double-precision Horner in v meets `tol` on the dense grid.
+inline void fit_direct(long double vmax, ErfPoly &P, const std::vector<double> &vs, const std::vector<long double> &ref,
+                       double tol)
+{
+    P.ddeg = 0;
+    const long double sigma = 2.0L / vmax;
+    std::vector<long double> mono;
+    for (int D = 3; D <= MMC_ERF_DIRECT_MAXDEG; ++D) {
+        cheb_fit(D, vmax, mono);
+        ErfPoly Q = P;
+        Q.ddeg = D;
+        for (int k = 0; k <= D; ++k) {
+            long double acc = 0.0L, binom = 1.0L;      // C(i, k) for i = k, k+1, ...
+            for (int i = k; i <= D; ++i) {
+                acc += mono[i] * binom * (((i - k) & 1) ? -1.0L : 1.0L);
+                binom = binom * (long double)(i + 1) / (long double)(i + 1 - k);
+            }
+            Q.a[k] = (double)(acc * powl(sigma, (long double)k));
+        }
+        double err = 0.0;
+        for (size_t i = 0; i < vs.size(); ++i) {
+            const double e = std::fabs((double)((long double)eval_direct(Q, vs[i]) - ref[i]));
+            if (e > err) err = e;
+        }
+        if (err <= tol) { for (int k = 0; k <= D; ++k) P.a[k] = Q.a[k]; P.ddeg = D; return; }
+    }
+}
+
 // Picks the smallest degree whose measured max |E_poly − E| is below `tol`; returns that error.
 // vmax is the upper end of the fitted domain in v = κ² r² (the coefficients depend on vmax only).
 inline double fit(double vmax_d, ErfPoly &P, double tol = 2.5e-16)
@@ -107,6 +149,7 @@ inline double fit(double vmax_d, ErfPoly &P, double tol = 2.5e-16)
         for (int i = P.deg + 1; i <= padded; ++i) P.c[i] = 0.0;
         P.deg = padded;
     }
+    fit_direct(vmax, P, vs, ref, tol);
     return best;
 }
 

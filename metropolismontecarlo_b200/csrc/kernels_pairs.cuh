@@ -52,6 +52,8 @@ struct PairArgs {
     unsigned qq_negmask;       // v4: bit j set when qq_tab[j] < 0 (the overlap rule only fires there)
     float gate_rc2f;           // v4: conservative FP32 COM-gate threshold (>= r_cut² + worst-case FP32 error)
     ErfPoly ep;                // smooth part of erfc(κr)/r as one polynomial (deg 0: use erfc())
+    double pc[MMC_ERF_MAXDEG + 1];   // v5: −κ·(coefficients), in r² (DIRECT, κ^2k folded) or in s = pk2s·r² − 1
+    double pk2s;               // v5: σ κ²
 };
 
 // ---- one Coulomb site pair: q_a q_b erfc(κ r)/r with the overlap rule (ewalds.jl:359-367).

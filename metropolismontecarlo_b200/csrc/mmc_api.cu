@@ -5,6 +5,7 @@
 #include "kernels_pairs.cuh"
 #include "kernels_pairs_v3.cuh"
 #include "kernels_pairs_v4.cuh"
+#include "kernels_pairs_v5.cuh"
 #include "kernels_recip.cuh"
 #include "kernels_upload.cuh"
 
@@ -107,7 +108,7 @@ struct mmc_handle {
     int use_rhok_v2 = 1;
     int v3_ctas_per_sm = 2;
     int use_v3 = 1;              // 0 disables the v3 pair kernel (A/B testing)
-    int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v4, 1 k_pairs_v3, 2 k_pairs_fast, 3 general k_pairs
+    int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v5, 1 k_pairs_v4, 2 k_pairs_v3, 3 k_pairs_fast, 4 general k_pairs
                                  // (raised when a kernel declines the state)
     int pair_floor = 0;          // lowest level the chain may start from (mmc_debug_set "pair_level": A/B tests)
     bool uniform_q = false;      // every molecule carries the charges of molecule 1 (per site index)
@@ -439,8 +440,27 @@ void launch_pairs_v4(int deg, int grid, cudaStream_t st, const PairArgs &P, cons
     MMC_FOR_POS_DEGS(X)
 #undef X
 }
+#define MMC_FOR_DIRECT_DEGS(X) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+void launch_pairs_v5(int deg, bool direct, int grid, cudaStream_t st, const PairArgs &P, const int4 *slots)
+{
+    if (direct) {
+#define X(D) if (deg == D) { k_pairs_v5<D, true><<<grid, V5_BLOCK, V5_SMEM, st>>>(P, slots); return; }
+        MMC_FOR_DIRECT_DEGS(X)
+#undef X
+    } else {
+#define X(D) if (deg == D) { k_pairs_v5<D, false><<<grid, V5_BLOCK, V5_SMEM, st>>>(P, slots); return; }
+        MMC_FOR_POS_DEGS(X)
+#undef X
+    }
+}
 void pairs_fast_set_attributes()
 {
+#define X(D) cudaFuncSetAttribute(k_pairs_v5<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V5_SMEM);
+    MMC_FOR_DIRECT_DEGS(X)
+#undef X
+#define X(D) cudaFuncSetAttribute(k_pairs_v5<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V5_SMEM);
+    MMC_FOR_POS_DEGS(X)
+#undef X
 #define X(D) cudaFuncSetAttribute(k_pairs_v4<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM);
     MMC_FOR_POS_DEGS(X)
 #undef X
@@ -483,7 +503,7 @@ void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P)
 // [MMC_NSCAL ..) ρ(k) partial (re,im).
 int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
 {
-    const bool force_general = h->pair_level >= 3;
+    const bool force_general = h->pair_level >= 4;
     if (!h->uniform) FAIL(MMC_EINVAL, "pair kernel needs a uniform topology (internal)");
     const DevSystem &S = h->S;
     const int US = h->US;
@@ -552,14 +572,15 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     if (want_qq) get_erf_poly(h, E.kappa, S.rc_qq * S.rc_qq + 100, P.ep);
     const int max_cell = cells ? h->max_cell_cached : PAIR_TILE;
     // v3 serves water-like molecules: 3 sites, LJ only on site pair (0,0), equal cut-offs, Coulomb on, polynomial erf
-    const bool water = cells && US == 3 && !force_general && h->pair_level <= 1 && max_cell <= V3_ACAP && want_qq &&
+    const bool water = cells && US == 3 && !force_general && h->pair_level <= 2 && max_cell <= V3_ACAP && want_qq &&
                        S.rc_lj == S.rc_qq && P.ep.deg > 0 && h->lj.size() == 1 && h->lj[0].a == 0 && h->lj[0].b == 0;
     // v4 additionally needs identical per-site charges (they become launch constants)
-    const bool v4 = water && h->pair_level == 0 && h->uniform_q;
-    const bool v3 = water && !v4 && h->use_v3;
-    const int tile = (US == 3 && !force_general && !v3 && !v4) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
-    if (v3 || v4) n_units = (long long)V3_GROUPS * ncd * ncd * ncd;
-    if (v4) {
+    const bool v5 = water && h->pair_level == 0 && h->uniform_q;
+    const bool v4 = water && !v5 && h->pair_level <= 1 && h->uniform_q;
+    const bool v3 = water && !v4 && !v5 && h->use_v3;
+    const int tile = (US == 3 && !force_general && !v3 && !v4 && !v5) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
+    if (v3 || v4 || v5) n_units = (long long)V3_GROUPS * ncd * ncd * ncd;
+    if (v4 || v5) {
         P.qq_negmask = 0;
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) {
@@ -572,12 +593,24 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         const double margin = 4.0 * (2.0 * 1.7320508075688772 * rc * delta + 3.0 * delta * delta + 3.6e-7 * rc * rc);
         P.gate_rc2f = std::nextafterf((float)(rc * rc + margin), INFINITY);
     }
+    bool v5_direct = false;
+    int v5_deg = 0;
+    if (v5) {   // −κ folded into the coefficients; DIRECT: also κ^2k, so the kernel runs Horner in r² itself
+        v5_direct = P.ep.ddeg > 0;
+        v5_deg = v5_direct ? P.ep.ddeg : P.ep.deg;
+        double k2k = 1.0;
+        for (int k = 0; k <= v5_deg; ++k) {
+            P.pc[k] = v5_direct ? -E.kappa * P.ep.a[k] * k2k : -E.kappa * P.ep.c[k];
+            k2k *= E.kappa * E.kappa;
+        }
+        P.pk2s = P.ep.kappa2 * P.ep.scale;
+    }
     P.unit_begin = n_units * E.rank / E.world;
     P.unit_end = n_units * (E.rank + 1) / E.world;
     const long long my_units = P.unit_end - P.unit_begin;
     int grid;
     if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-    if (v3 || v4) {
+    if (v3 || v4 || v5) {
         const long long nslots = 14LL * ncd * ncd * ncd;
         if (nslots > h->slots_cap) {
             dfree(h->d_slots);
@@ -587,7 +620,10 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(P, h->d_slots, ncd * ncd * ncd);
         LAUNCH_CHECK();
         if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-        if (v4) {
+        if (v5) {
+            grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
+            launch_pairs_v5(v5_deg, v5_direct, grid, h->stream, P, h->d_slots);
+        } else if (v4) {
             grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
             launch_pairs_v4(P.ep.deg, grid, h->stream, P, h->d_slots);
         } else {
@@ -619,7 +655,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
     k_pair_reduce<<<1, 256, 0, h->stream>>>(h->d_pair_partial, grid, h->d_novl, h->d_maxcount, h->d_errflag, d_vec);
     LAUNCH_CHECK();
-    h->last_fast = v4 ? 4 : (v3 ? 3 : tile);
+    h->last_fast = v5 ? 5 : (v4 ? 4 : (v3 ? 3 : tile));
     h->last_mode = cells ? 0 : 1;
     h->last_ncd = ncd;
 
@@ -666,7 +702,7 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
         if (h->last_mode == 0) h->max_cell_cached = (int)h->h_vec[6];
         if (h->h_vec[7] != 0.0) return 1;      // a cell outgrew the fast kernel's tile: caller re-runs
     } else if (h->h_vec[7] != 0.0) {           // summed over ranks: every rank takes the same branch
-        if (++h->pair_level > 3) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        if (++h->pair_level > 4) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         h->max_cell_cached = -1;
         return 1;                               // MMC_RETRY: caller repeats partial + all-reduce + finalize
     }
@@ -1305,7 +1341,7 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
     rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
     while (rc == 1) {    // the chosen pair kernel declined this state (dense cell / wrapped molecules): next level
-        if (++h->pair_level > 3) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        if (++h->pair_level > 4) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
     }
@@ -1418,7 +1454,7 @@ int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t st
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
     rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
     while (rc == 1) {
-        if (++h->pair_level > 3) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        if (++h->pair_level > 4) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
     }
@@ -1495,8 +1531,8 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
 {
     if (!h || !key) return MMC_EINVAL;
     const std::string k(key);
-    if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v4 .. 3 general)
-        if (value < 0 || value > 3) FAIL(MMC_EINVAL, "pair_level must be 0..3");
+    if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v5 .. 4 general)
+        if (value < 0 || value > 4) FAIL(MMC_EINVAL, "pair_level must be 0..4");
         h->pair_floor = (int)value; h->pair_level = (int)value;
         return MMC_OK;
     }
