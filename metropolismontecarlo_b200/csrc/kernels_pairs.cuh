@@ -581,6 +581,12 @@ struct GatherArgs {
     double4 *scom, *ssite;
     unsigned long long *max_dev_bits;   // atomicMax over the bits of max |site-COM| component
     unsigned int *ovl;                  // per-molecule overlap flags, cleared here
+    // optional (k_pairs_v6): the same state as 96-byte rows {site xyz x3, COM xyz} + cell-local float gate coordinates
+    double *rows;
+    float4 *gf;
+    const int *cell_of;     // [n_mol] cell of each molecule (original index)
+    int ncd;
+    double edge;            // box_new / ncd
 };
 
 // cell-sorted copy of the state; for a volume trial the COMs are scaled by f and the sites
@@ -603,6 +609,14 @@ __global__ void k_gather(GatherArgs A)
         dev = fmax(dev, fmax(fabs(s.x - c.x), fmax(fabs(s.y - c.y), fabs(s.z - c.z))));
         s.x = s.x + chx; s.y = s.y + chy; s.z = s.z + chz;
         A.ssite[(size_t)p * A.S + a] = s;
+        if (A.rows) { double *r = A.rows + (size_t)p * 12 + 3 * a; r[0] = s.x; r[1] = s.y; r[2] = s.z; }
+    }
+    if (A.rows) {
+        double *r = A.rows + (size_t)p * 12 + 9;
+        r[0] = cn.x; r[1] = cn.y; r[2] = cn.z;
+        const int id = A.cell_of[m], n = A.ncd;
+        A.gf[p] = make_float4((float)(cn.x - (double)(id % n) * A.edge), (float)(cn.y - (double)((id / n) % n) * A.edge),
+                              (float)(cn.z - (double)(id / (n * n)) * A.edge), 0.f);
     }
     // warp max, then one atomic per warp (non-negative doubles order like their bit patterns)
     for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));

@@ -6,6 +6,7 @@
 #include "kernels_pairs_v3.cuh"
 #include "kernels_pairs_v4.cuh"
 #include "kernels_pairs_v5.cuh"
+#include "kernels_pairs_v6.cuh"
 #include "kernels_recip.cuh"
 #include "kernels_upload.cuh"
 
@@ -89,6 +90,8 @@ struct mmc_handle {
     int *d_cell_of = nullptr, *d_count = nullptr, *d_start = nullptr, *d_fill = nullptr, *d_perm = nullptr;
     int ncell_cap = 0;
     double4 *d_scom = nullptr, *d_ssite = nullptr;
+    double *d_mrows = nullptr;   // k_pairs_v6: cell-sorted state as rows of 12 doubles
+    float4 *d_gf = nullptr;      //             and cell-local float COMs
     double4 *d_pair_partial = nullptr;
     int pair_grid = 0;
     unsigned int *d_ovl = nullptr, *d_novl = nullptr;
@@ -108,7 +111,7 @@ struct mmc_handle {
     int use_rhok_v2 = 1;
     int v3_ctas_per_sm = 2;
     int use_v3 = 1;              // 0 disables the v3 pair kernel (A/B testing)
-    int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v5, 1 k_pairs_v4, 2 k_pairs_v3, 3 k_pairs_fast, 4 general k_pairs
+    int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v6, 1 k_pairs_v5, 2 k_pairs_v4, 3 k_pairs_v3, 4 k_pairs_fast, 5 general k_pairs
                                  // (raised when a kernel declines the state)
     int pair_floor = 0;          // lowest level the chain may start from (mmc_debug_set "pair_level": A/B tests)
     bool uniform_q = false;      // every molecule carries the charges of molecule 1 (per site index)
@@ -176,6 +179,7 @@ void free_system(mmc_handle *h)
     h->raw_bytes = 0; h->cap_mol = 0; h->cap_sites = 0;
     dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
     h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
+    dfree(h->d_mrows); dfree(h->d_gf);
     dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl);
     dfree(h->d_rhok_partial); dfree(h->d_units); dfree(h->d_slots);
     h->units_cap = 0; h->slots_cap = 0;
@@ -453,8 +457,26 @@ void launch_pairs_v5(int deg, bool direct, int grid, cudaStream_t st, const Pair
 #undef X
     }
 }
+void launch_pairs_v6(int deg, bool direct, int grid, cudaStream_t st, const PairArgs &P, const int4 *slots, const V6Extra &X)
+{
+    if (direct) {
+#define X_(D) if (deg == D) { k_pairs_v6<D, true><<<grid, V6_BLOCK, V6_SMEM, st>>>(P, slots, X); return; }
+        MMC_FOR_DIRECT_DEGS(X_)
+#undef X_
+    } else {
+#define X_(D) if (deg == D) { k_pairs_v6<D, false><<<grid, V6_BLOCK, V6_SMEM, st>>>(P, slots, X); return; }
+        MMC_FOR_POS_DEGS(X_)
+#undef X_
+    }
+}
 void pairs_fast_set_attributes()
 {
+#define X(D) cudaFuncSetAttribute(k_pairs_v6<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6_SMEM);
+    MMC_FOR_DIRECT_DEGS(X)
+#undef X
+#define X(D) cudaFuncSetAttribute(k_pairs_v6<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6_SMEM);
+    MMC_FOR_POS_DEGS(X)
+#undef X
 #define X(D) cudaFuncSetAttribute(k_pairs_v5<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V5_SMEM);
     MMC_FOR_DIRECT_DEGS(X)
 #undef X
@@ -499,11 +521,20 @@ void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P)
     P = Q;
 }
 
+// A pair kernel declined the state.  The water kernels (levels 0-3: v6, v5, v4, v3) share their
+// preconditions (cell population <= 64, site reach inside the reference's +100 window), so a decline
+// by one of them goes straight to k_pairs_fast; after that one level at a time.
+bool escalate_pair_level(mmc_handle *h)
+{
+    h->pair_level = h->pair_level < 4 ? 4 : h->pair_level + 1;
+    return h->pair_level <= 5;
+}
+
 // Leaves this rank's partial sums in d_vec: [0] Σlj_pot [1] Σlj_vir [2] Σcoul [3] #overlap
 // [MMC_NSCAL ..) ρ(k) partial (re,im).
 int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
 {
-    const bool force_general = h->pair_level >= 4;
+    const bool force_general = h->pair_level >= 5;
     if (!h->uniform) FAIL(MMC_EINVAL, "pair kernel needs a uniform topology (internal)");
     const DevSystem &S = h->S;
     const int US = h->US;
@@ -548,8 +579,15 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         const long long nt = (S.n_mol + PAIR_TILE - 1) / PAIR_TILE;
         n_units = nt * (nt + 1) / 2;
     }
+    // k_pairs_v6 reads the state as 96-byte rows + float gate coordinates (written by the same gather)
+    const bool want_rows = cells && US == 3 && h->pair_level == 0 && h->uniform_q && want_qq;
+    if (want_rows && !h->d_mrows) {
+        CK(cudaMalloc(&h->d_mrows, sizeof(double) * 12 * (size_t)S.n_mol));
+        CK(cudaMalloc(&h->d_gf, sizeof(float4) * (size_t)S.n_mol));
+    }
     GatherArgs G{S.com, S.site, cells ? h->d_perm : nullptr, S.n_mol, US, E.f, h->d_scom, h->d_ssite,
-                 reinterpret_cast<unsigned long long *>(h->d_maxdev), h->d_ovl};
+                 reinterpret_cast<unsigned long long *>(h->d_maxdev), h->d_ovl,
+                 want_rows ? h->d_mrows : nullptr, want_rows ? h->d_gf : nullptr, h->d_cell_of, ncd, E.box / ncd};
     k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
 
@@ -572,15 +610,16 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     if (want_qq) get_erf_poly(h, E.kappa, S.rc_qq * S.rc_qq + 100, P.ep);
     const int max_cell = cells ? h->max_cell_cached : PAIR_TILE;
     // v3 serves water-like molecules: 3 sites, LJ only on site pair (0,0), equal cut-offs, Coulomb on, polynomial erf
-    const bool water = cells && US == 3 && !force_general && h->pair_level <= 2 && max_cell <= V3_ACAP && want_qq &&
+    const bool water = cells && US == 3 && !force_general && h->pair_level <= 3 && max_cell <= V3_ACAP && want_qq &&
                        S.rc_lj == S.rc_qq && P.ep.deg > 0 && h->lj.size() == 1 && h->lj[0].a == 0 && h->lj[0].b == 0;
     // v4 additionally needs identical per-site charges (they become launch constants)
-    const bool v5 = water && h->pair_level == 0 && h->uniform_q;
-    const bool v4 = water && !v5 && h->pair_level <= 1 && h->uniform_q;
-    const bool v3 = water && !v4 && !v5 && h->use_v3;
-    const int tile = (US == 3 && !force_general && !v3 && !v4 && !v5) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
-    if (v3 || v4 || v5) n_units = (long long)V3_GROUPS * ncd * ncd * ncd;
-    if (v4 || v5) {
+    const bool v6 = water && h->pair_level == 0 && h->uniform_q && want_rows;
+    const bool v5 = water && !v6 && h->pair_level <= 1 && h->uniform_q;
+    const bool v4 = water && !v5 && !v6 && h->pair_level <= 2 && h->uniform_q;
+    const bool v3 = water && !v4 && !v5 && !v6 && h->use_v3;
+    const int tile = (US == 3 && !force_general && !v3 && !v4 && !v5 && !v6) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
+    if (v3 || v4 || v5 || v6) n_units = (long long)V3_GROUPS * ncd * ncd * ncd;
+    if (v4 || v5 || v6) {
         P.qq_negmask = 0;
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) {
@@ -588,14 +627,15 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
                 if (P.qq_tab[a * 3 + b] < 0.0) P.qq_negmask |= 1u << (a * 3 + b);
             }
         // conservative FP32 gate: |d²_f32 - d²| <= 2*sqrt(3)*rc*delta + 3*delta² + 3*2^-23*rc², delta = 6*2^-24*edge
-        // (two roundings to float of coordinates <= 2*edge, one float subtraction of <= 3*edge); 4x safety
-        const double edge = E.box / ncd, rc = S.rc_qq, delta = 6.0 * edge / 16777216.0;
+        // (roundings to float of cell-local coordinates < edge, of their sum with the slot offset <= 2*edge, one
+        // float subtraction of <= 3*edge: 7 half-ulps of edge at most); 4x safety
+        const double edge = E.box / ncd, rc = S.rc_qq, delta = 8.0 * edge / 16777216.0;
         const double margin = 4.0 * (2.0 * 1.7320508075688772 * rc * delta + 3.0 * delta * delta + 3.6e-7 * rc * rc);
         P.gate_rc2f = std::nextafterf((float)(rc * rc + margin), INFINITY);
     }
     bool v5_direct = false;
     int v5_deg = 0;
-    if (v5) {   // −κ folded into the coefficients; DIRECT: also κ^2k, so the kernel runs Horner in r² itself
+    if (v5 || v6) {   // −κ folded into the coefficients; DIRECT: also κ^2k, so the kernel runs Horner in r² itself
         v5_direct = P.ep.ddeg > 0;
         v5_deg = v5_direct ? P.ep.ddeg : P.ep.deg;
         double k2k = 1.0;
@@ -610,7 +650,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     const long long my_units = P.unit_end - P.unit_begin;
     int grid;
     if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-    if (v3 || v4 || v5) {
+    if (v3 || v4 || v5 || v6) {
         const long long nslots = 14LL * ncd * ncd * ncd;
         if (nslots > h->slots_cap) {
             dfree(h->d_slots);
@@ -620,7 +660,10 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(P, h->d_slots, ncd * ncd * ncd);
         LAUNCH_CHECK();
         if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-        if (v5) {
+        if (v6) {
+            grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
+            launch_pairs_v6(v5_deg, v5_direct, grid, h->stream, P, h->d_slots, V6Extra{h->d_mrows, h->d_gf});
+        } else if (v5) {
             grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
             launch_pairs_v5(v5_deg, v5_direct, grid, h->stream, P, h->d_slots);
         } else if (v4) {
@@ -655,7 +698,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
     k_pair_reduce<<<1, 256, 0, h->stream>>>(h->d_pair_partial, grid, h->d_novl, h->d_maxcount, h->d_errflag, d_vec);
     LAUNCH_CHECK();
-    h->last_fast = v5 ? 5 : (v4 ? 4 : (v3 ? 3 : tile));
+    h->last_fast = v6 ? 6 : (v5 ? 5 : (v4 ? 4 : (v3 ? 3 : tile)));
     h->last_mode = cells ? 0 : 1;
     h->last_ncd = ncd;
 
@@ -702,7 +745,7 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
         if (h->last_mode == 0) h->max_cell_cached = (int)h->h_vec[6];
         if (h->h_vec[7] != 0.0) return 1;      // a cell outgrew the fast kernel's tile: caller re-runs
     } else if (h->h_vec[7] != 0.0) {           // summed over ranks: every rank takes the same branch
-        if (++h->pair_level > 4) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         h->max_cell_cached = -1;
         return 1;                               // MMC_RETRY: caller repeats partial + all-reduce + finalize
     }
@@ -1341,7 +1384,7 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
     rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
     while (rc == 1) {    // the chosen pair kernel declined this state (dense cell / wrapped molecules): next level
-        if (++h->pair_level > 4) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
     }
@@ -1454,7 +1497,7 @@ int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t st
     if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
     rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
     while (rc == 1) {
-        if (++h->pair_level > 4) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
     }
@@ -1531,8 +1574,8 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
 {
     if (!h || !key) return MMC_EINVAL;
     const std::string k(key);
-    if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v5 .. 4 general)
-        if (value < 0 || value > 4) FAIL(MMC_EINVAL, "pair_level must be 0..4");
+    if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v6 .. 5 general)
+        if (value < 0 || value > 5) FAIL(MMC_EINVAL, "pair_level must be 0..5");
         h->pair_floor = (int)value; h->pair_level = (int)value;
         return MMC_OK;
     }

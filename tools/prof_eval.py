@@ -9,7 +9,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--molecules", type=int, default=256000)
 ap.add_argument("--evals", type=int, default=4)
 ap.add_argument("--style", default="ewald")
-ap.add_argument("--pair-level", type=int, default=0, help="0 v5, 1 v4, 2 v3, 3 fast, 4 general")
+ap.add_argument("--pair-level", type=int, default=0, help="0 v6, 1 v5, 2 v4, 3 v3, 4 fast, 5 general")
 a = ap.parse_args()
 ms = systems.spce_lattice(a.molecules) if a.molecules != 750 else systems.load_nist(4)
 eng = water_engine(ms, 10.0)
