@@ -19,9 +19,9 @@
 #define V6_WARPS (V6_BLOCK / 32)
 #define V6_ACAP 64
 #define V6_SLOTS 5
-#define V6_BCAP (V6_SLOTS * V6_ACAP)
+#define V6_BCAP 256    // B tile: the group's ≤5 neighbour cells normally fit (5 x 37 at liquid density); else two passes
 #define V6_ROW 12
-#define V6_QCAP 1024
+#define V6_QCAP 512    // 16-bit entries per warp (power of two); drained when fewer than V6_BCAP are free
 
 constexpr size_t V6_SMEM = (size_t)(V6_ACAP + V6_BCAP) * V6_ROW * sizeof(double) +
                            (size_t)(V6_ACAP + V6_BCAP) * sizeof(float4) +
@@ -58,7 +58,7 @@ struct V6Extra {
 };
 
 template <int DEG, bool DIRECT>
-__global__ void __launch_bounds__(V6_BLOCK, 4) k_pairs_v6(const __grid_constant__ PairArgs A, const int4 *__restrict__ slots,
+__global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant__ PairArgs A, const int4 *__restrict__ slots,
                                                            const V6Extra X)
 {
     constexpr int S = 3;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(V6_BLOCK, 4) k_pairs_v6(const __grid_constant_
     float4 *s_fA = reinterpret_cast<float4 *>(s_rowB + V6_BCAP * V6_ROW);
     float4 *s_fB = s_fA + V6_ACAP;
     unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_fB + V6_BCAP);
-    __shared__ int s_boff[V6_SLOTS + 1], s_bglob[V6_SLOTS], s_code[V6_SLOTS], s_nA;
+    __shared__ int s_boff[V6_SLOTS + 1], s_bglob[V6_SLOTS], s_code[V6_SLOTS], s_nA, s_nB, s_pass_end;
     __shared__ double s_red[4 * V6_WARPS];
     __shared__ __align__(8) unsigned long long s_mbar;
 
@@ -106,42 +106,50 @@ __global__ void __launch_bounds__(V6_BLOCK, 4) k_pairs_v6(const __grid_constant_
     for (; u < A.unit_end; u += gridDim.x) {
         const int c = (int)(u / V3_GROUPS), g = (int)(u - (long long)c * V3_GROUPS);
         const int sl0 = c_v3_group_begin[g], nsl = c_v3_group_begin[g + 1] - sl0;
+      // a group whose neighbour cells hold more than V6_BCAP molecules together is evaluated in two passes
+      for (int s_begin = 0, s_end = 0; s_begin < nsl; s_begin = s_end) {
         fence_proxy_async_smem();                          // our generic-proxy writes (fix-up) before the engine overwrites
-        __syncthreads();                                   // everyone is done with the previous unit's tiles
+        __syncthreads();                                   // everyone is done with the previous tiles
         if (warp == 0) {
             const int cnt = desc.y;
-            int incl = (lane < V6_SLOTS) ? cnt : 0;        // inclusive prefix of the B counts over lanes 0..4
+            int incl = (lane >= s_begin && lane < V6_SLOTS) ? cnt : 0;   // inclusive prefix of the B counts from s_begin on
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            const int nBt = __shfl_sync(0xffffffffu, incl, V6_SLOTS - 1);
+            // slots [s_begin, se) fit the B tile (every count is <= V6_ACAP, so at least four do)
+            const int se = min(nsl, __popc(__ballot_sync(0xffffffffu, lane < V6_SLOTS && incl <= V6_BCAP)));
+            const int nBt = __shfl_sync(0xffffffffu, incl, se - 1);
             const int nAt = __shfl_sync(0xffffffffu, cnt, 5);
             const bool bad = __any_sync(0xffffffffu, lane < 6 && cnt > V6_ACAP);
+            const bool mine = (lane >= s_begin && lane < se) || (lane == 5 && s_begin == 0);
             if (lane < V6_SLOTS) { s_boff[lane] = incl - cnt; s_bglob[lane] = desc.x; s_code[lane] = desc.z; }
             __syncwarp();
             if (lane == 0) {
-                s_boff[V6_SLOTS] = bad ? 0 : nBt;
+                s_boff[se] = bad ? 0 : nBt;                // one past the pass's last slot
                 s_nA = bad ? 0 : nAt;
+                s_nB = bad ? 0 : nBt;
+                s_pass_end = bad ? nsl : se;
                 if (bad) atomicExch(A.err_flag, 1u);
-                mbar_arrive_expect_tx(&s_mbar, bad ? 0u : (unsigned)(nBt + nAt) * (V6_ROW * 8 + 16));
+                mbar_arrive_expect_tx(&s_mbar, bad ? 0u : (unsigned)(nBt + (s_begin == 0 ? nAt : 0)) * (V6_ROW * 8 + 16));
             }
-            if (!bad && lane < 6 && cnt > 0) {
+            if (!bad && mine && cnt > 0) {
                 const int off = incl - cnt;
                 double *drow = (lane == 5) ? s_rowA : s_rowB + off * V6_ROW;
                 float4 *dgf = (lane == 5) ? s_fA : s_fB + off;
                 bulk_g2s(drow, X.rows + (size_t)desc.x * V6_ROW, (unsigned)cnt * V6_ROW * 8, &s_mbar);
                 bulk_g2s(dgf, X.gf + desc.x, (unsigned)cnt * 16, &s_mbar);
             }
-            desc = fetch_desc(u + gridDim.x);              // next unit's descriptors travel while this one is evaluated
+            if (bad || se == nsl) desc = fetch_desc(u + gridDim.x);   // next unit's descriptors travel while this one is evaluated
         }
         mbar_wait(&s_mbar, phase);
         phase ^= 1u;
-        const int nA = s_nA, nB = s_boff[V6_SLOTS];
+        s_end = s_pass_end;
+        const int nA = s_nA, nB = s_nB;
         // ---- fix-up: B gate coordinates get the slot's cell offset; rows of wrapped slots get ±L
         for (int t = tid; t < ((nB + 63) & ~63); t += V6_BLOCK) {
             if (t < nB) {
-                int sl = 0;
+                int sl = s_begin;
 #pragma unroll
-                for (int k = 1; k < V6_SLOTS; ++k) sl += (k < nsl && t >= s_boff[k]) ? 1 : 0;
+                for (int k = 1; k < V6_SLOTS; ++k) sl += (k > s_begin && k < s_end && t >= s_boff[k]) ? 1 : 0;
                 float4 f = s_fB[t];
                 f.x += (float)c_half_shell[sl0 + sl][0] * edge_f;
                 f.y += (float)c_half_shell[sl0 + sl][1] * edge_f;
@@ -151,21 +159,21 @@ __global__ void __launch_bounds__(V6_BLOCK, 4) k_pairs_v6(const __grid_constant_
                 s_fB[t] = make_float4(1e18f, 1e18f, 1e18f, 0.f);   // sentinels: the gate walks B in steps of 64
             }
         }
-        for (int sl = 0; sl < nsl; ++sl) {
+        for (int sl = s_begin; sl < s_end; ++sl) {
             const int code = s_code[sl];
             if (code == 0) continue;                       // uniform branch: only cells on the box faces
             const int cx = code & 3, cy = (code >> 2) & 3, cz = (code >> 4) & 3;
             const double sh[3] = {cx == 1 ? L : (cx == 2 ? -L : 0.0), cy == 1 ? L : (cy == 2 ? -L : 0.0),
                                   cz == 1 ? L : (cz == 2 ? -L : 0.0)};
             double *base = s_rowB + s_boff[sl] * V6_ROW;
-            const int nval = (s_boff[sl + 1 < nsl ? sl + 1 : V6_SLOTS] - s_boff[sl]) * V6_ROW;
+            const int nval = (s_boff[sl + 1] - s_boff[sl]) * V6_ROW;
             for (int t = tid; t < nval; t += V6_BLOCK) {
                 const int k = t % 3;
                 base[t] = base[t] + (k == 0 ? sh[0] : (k == 1 ? sh[1] : sh[2]));
             }
         }
         __syncthreads();
-        const int self_n = (g == 0) ? nA : 0;              // slot 0 of group 0 is the home cell itself: keep q > p
+        const int self_n = (g == 0 && s_begin == 0) ? nA : 0;   // slot 0 of group 0 is the home cell itself: keep q > p
 
         int head = 0, tail = 0;                            // warp-private ring window [head, tail)
         auto consume = [&](int base, int count) {          // `count` queued molecule pairs, one per lane
@@ -226,8 +234,8 @@ __global__ void __launch_bounds__(V6_BLOCK, 4) k_pairs_v6(const __grid_constant_
                     f_one = fast_rsqrt(1.0) + f_one;
 #pragma unroll
                     for (int j = 0; j < S * S; ++j) if ((ovl >> j) & 1u) acc_q = fma(-A.qq_tab[j], f_one, acc_q);
-                    int slot_i = 0;
-                    while (slot_i + 1 < nsl && qi >= s_boff[slot_i + 1]) ++slot_i;
+                    int slot_i = s_begin;
+                    while (slot_i + 1 < s_end && qi >= s_boff[slot_i + 1]) ++slot_i;
                     const int qglob = s_bglob[slot_i] + (qi - s_boff[slot_i]);
                     if (atomicExch(&A.ovl[A.cell_start[c] + p], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
                     if (atomicExch(&A.ovl[qglob], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
@@ -272,6 +280,7 @@ __global__ void __launch_bounds__(V6_BLOCK, 4) k_pairs_v6(const __grid_constant_
             }
             if (last) break;
         }
+      }
     }
     __syncthreads();
     double accp[4] = {acc_lj, acc_vir, acc_q, (double)my_pairs};

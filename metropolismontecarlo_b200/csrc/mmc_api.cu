@@ -110,6 +110,7 @@ struct mmc_handle {
     long long slots_cap = 0;
     int use_rhok_v2 = 1;
     int v3_ctas_per_sm = 2;
+    int v6_ctas_per_sm = 5;
     int use_v3 = 1;              // 0 disables the v3 pair kernel (A/B testing)
     int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v6, 1 k_pairs_v5, 2 k_pairs_v4, 3 k_pairs_v3, 4 k_pairs_fast, 5 general k_pairs
                                  // (raised when a kernel declines the state)
@@ -661,7 +662,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         LAUNCH_CHECK();
         if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
         if (v6) {
-            grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
+            grid = (int)std::max(1LL, std::min<long long>(h->v6_ctas_per_sm * h->sm_count, my_units));
             launch_pairs_v6(v5_deg, v5_direct, grid, h->stream, P, h->d_slots, V6Extra{h->d_mrows, h->d_gf});
         } else if (v5) {
             grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
@@ -977,7 +978,7 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         CK(cudaMalloc(&h->d_perm, sizeof(int) * n_mol));
         CK(cudaMalloc(&h->d_scom, sizeof(double4) * n_mol));
         CK(cudaMalloc(&h->d_ssite, sizeof(double4) * n_sites));
-        h->pair_grid = 4 * h->sm_count;
+        h->pair_grid = 5 * h->sm_count;
         CK(cudaMalloc(&h->d_pair_partial, sizeof(double4) * h->pair_grid));
         CK(cudaMalloc(&h->d_ovl, sizeof(unsigned) * n_mol));
         h->ncell_cap = 0; h->rhok_grid_cap = 0;
@@ -1574,6 +1575,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
 {
     if (!h || !key) return MMC_EINVAL;
     const std::string k(key);
+    if (k == "v6_ctas_per_sm") { if (value < 1 || value > 5) FAIL(MMC_EINVAL, "v6_ctas_per_sm must be 1..5"); h->v6_ctas_per_sm = (int)value; return MMC_OK; }
     if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v6 .. 5 general)
         if (value < 0 || value > 5) FAIL(MMC_EINVAL, "pair_level must be 0..5");
         h->pair_floor = (int)value; h->pair_level = (int)value;
