@@ -32,6 +32,10 @@ UNIT = "evals/s"
 N_MOL_E = 256_000
 RC = 10.0
 FLOP_PER_PAIR = 624          # 9 x 67 + 21 per in-cutoff water-water pair
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on config E at N=1, from the
+# `ncu --set full` capture summarised in profiles/r01_v6_ncu_full_pairs_and_rhok.txt (a profiler number is never
+# taken inside bench.py; the algorithmic bytes are the 35 MB of state, read once)
+NCU_DRAM_BYTES = {"k_pairs_v6": 30264320, "k_pairs_v5": 34369280, "k_pairs_v4": 34369280}
 
 
 def workload_config(n_mol):
@@ -302,7 +306,9 @@ def run_ours(args, rank, world, local_rank):
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "peak_source": "live DFMA-chain probe on this GPU (MEASURED_PEAKS.json has no FP64 figure); "
                                         "nominal 37.2 TFLOP/s at 1965 MHz",
-                         "algorithmic_flop_per_launch": alg_flops, "traffic": None},
+                         "algorithmic_flop_per_launch": alg_flops,
+                         "traffic": NCU_DRAM_BYTES.get(info["pair_kernel"]) if world == 1 and ms.n_mol == N_MOL_E else None,
+                         "traffic_unit": "bytes of DRAM per launch (ncu, profiles/r01_v6_ncu_full_pairs_and_rhok.txt)"},
             "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
                     "what": "mmc_upload_system(host Julia-layout arrays) + sharded potential + Properties on host"},
             "gpu_launches": int(launches) * world,
