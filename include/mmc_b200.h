@@ -190,6 +190,16 @@ typedef struct {
 int mmc_loop_run(mmc_handle *h, const mmc_loop_params *p, double *com, double *quat,
                  const double *db, const double *uniforms, int64_t n_uniforms, int64_t n_moves,
                  double e0, double v0, uint8_t *accepted, double *delta, mmc_loop_stats *stats);
+/* The same block of moves evaluated on the device in ONE launch (csrc/kernels_chain.cuh): the state of a
+ * small system (uniform topology, <= 4 sites per molecule, fits one SM's shared memory: up to ~1600
+ * three-site molecules) stays on chip, the uniform stream is consumed in the same order, and the
+ * accept/reject record, deltas, statistics, com/quat and the library's resident state (sites, COMs,
+ * rho(k)) come back when the block is done.  What a Julia Loop() would call once per sweep/block
+ * instead of five times per move (Ewald/main.jl:487-651).  Same arguments and return codes as
+ * mmc_loop_run; MMC_EINVAL when the system does not qualify. */
+int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, double *com, double *quat,
+                        const double *db, const double *uniforms, int64_t n_uniforms, int64_t n_moves,
+                        double e0, double v0, uint8_t *accepted, double *delta, mmc_loop_stats *stats);
 /* Monatomic/mainMonatomic.jl:373-413 */
 int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_max, double *r,
                        const double *uniforms, int64_t n_uniforms, int64_t n_moves,

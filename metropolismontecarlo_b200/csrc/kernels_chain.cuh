@@ -1,0 +1,477 @@
+// kernels_chain.cuh — a block of trial moves evaluated back to back on the device.
+//
+// The per-move entry points (kernels_move.cuh) pay one kernel launch and one PCIe round trip per
+// trial move: ≈12 µs for ≈2×10⁵ flop.  A Markov chain is sequential, so the only way to take that
+// latency out is to keep the WHOLE accept/reject loop of Ewald/main.jl:487-651 next to the data for
+// a block of moves: the caller hands over the stretch of its uniform random stream that the block
+// will consume (the reference's own draw order) and gets back the accept/reject
+// record, the per-move deltas and the final state — one launch per block (e.g. per sweep) instead
+// of one per move.  Same decisions, same order, same stream.
+//
+//   one CTA of 512 threads, one SM; the state of the (small) system lives in SHARED memory:
+//     site[N·S] double4, com[N] double4, ρ(k) Old/New, k-vectors, cfac        (N = 750: 127 KB)
+//   per move:
+//     step 0  lane 0 of warp 0 draws the move exactly like the host driver (mmc_driver.inl; every
+//             product and sum rounded separately, as the reference's Julia does), from a ring of
+//             uniforms that warp 0 prefetches one move ahead;
+//     step 1  all threads: COM gate of molecule i at its old AND trial position against all j,
+//             ordered compaction (ballot/popc) of the partners inside either cut-off; the last warp
+//             builds the 2·S·3 e^{ik·r} recurrence tables of RecipMove (ewalds.jl:770-795);
+//     step 2  all threads: (partner, old/new, site a) items, S site pairs each in lock-step
+//             (LJ energy.jl:270-282, erfc Coulomb ewalds.jl:359-367 via the erf polynomial), and the
+//             ρ(k) delta update ewalds.jl:804-821 for k = tid;
+//     step 3  ordered block reduction, Metropolis (auxillary.jl:106-114) and, on accept, the state
+//             update + ρ(k) Old/New flip (main.jl:599-629) by lane 0.
+//   5 block barriers per move; nothing leaves the SM until the block of moves is done.
+#pragma once
+#include "kernels_move.cuh"
+
+#define CHAIN_THREADS 512
+#define CHAIN_WARPS (CHAIN_THREADS / 32)
+#define CHAIN_MAXIT 4            // N <= CHAIN_MAXIT * CHAIN_THREADS
+#define CHAIN_RING 64
+
+struct ChainOut {                // mirrors mmc_loop_stats + return code + final ρ(k) index
+    long long n_moves, n_accepted, n_overlap, uniforms_used;
+    long long trans_attempt, trans_accept, rot_attempt, rot_accept;
+    double dr_max, dphi_max, total_energy, total_virial;
+    int ret, cur;
+};
+
+struct ChainArgs {
+    long long n_moves, n_uniforms;
+    int style_qq, style_recip;   // Coulomb on (EWALD/WOLF); ρ(k) on (EWALD)
+    int adjust, cur;
+    double temperature, dr_max, dphi_max, p_trans, p_rot, e0, v0;
+    const double *uniforms;      // [n_uniforms]
+    double *quat;                // [N][4]
+    const double *db;            // [n_sites][3] body-fixed site vectors
+    unsigned char *accepted;     // [n_moves] or NULL
+    double *delta;               // [n_moves] or NULL
+    ChainOut *out;
+};
+
+__host__ __device__ inline size_t chain_smem_bytes(int n_mol, int S, int nk)
+{
+    return sizeof(double4) * ((size_t)n_mol * S + n_mol) + (size_t)nk * (2 * sizeof(double2) + sizeof(int4) + sizeof(double)) +
+           sizeof(int2) * (size_t)n_mol;
+}
+
+namespace chain {
+// separately rounded arithmetic: what the host driver (no FMA contraction) and Julia compute
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+
+// Ewald/adjust.jl:1-83
+struct MoveStat { long long naccepp, naccept, attempp, attempt; double set_value, d_max; };
+__device__ inline void adjust_step(MoveStat &m, double L)
+{
+    if (m.attempp == 0) { m.naccepp = m.naccept; m.attempp = m.attempt; return; }
+    const double ratio = __ddiv_rn((double)(m.naccept - m.naccepp), (double)(m.attempt - m.attempp));
+    const double old = m.d_max;
+    m.d_max = __ddiv_rn(mul(m.d_max, ratio), m.set_value);
+    const double r = __ddiv_rn(m.d_max, old);
+    if (r > 1.5) m.d_max = mul(old, 1.5);
+    if (r < 0.5) m.d_max = mul(old, 0.5);
+    if (m.d_max > __ddiv_rn(L, 2.0)) m.d_max = __ddiv_rn(L, 2.0);
+    m.naccepp = m.naccept; m.attempp = m.attempt;
+}
+}  // namespace chain
+
+template <int S>
+__global__ void __launch_bounds__(CHAIN_THREADS, 1)
+k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs A, const __grid_constant__ ErfPoly P)
+{
+    using namespace chain;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = Sy.n_mol, NK = A.style_recip ? Sy.nkvecs : 0;
+    double4 *s_site = reinterpret_cast<double4 *>(smem_raw);
+    double4 *s_com = s_site + (size_t)N * S;
+    double2 *s_rhok[2];
+    s_rhok[0] = reinterpret_cast<double2 *>(s_com + N);
+    s_rhok[1] = s_rhok[0] + NK;
+    int4 *s_kvec = reinterpret_cast<int4 *>(s_rhok[1] + NK);
+    double *s_cfac = reinterpret_cast<double *>(s_kvec + NK);
+    int2 *s_list = reinterpret_cast<int2 *>(s_cfac + NK);
+
+    __shared__ cplx s_tab[2][S][3][MMC_MAX_NK + 1];
+    __shared__ int s_type[S];
+    __shared__ int s_wcount[CHAIN_MAXIT * CHAIN_WARPS];
+    __shared__ double s_red[9 * CHAIN_WARPS];
+    __shared__ double s_u[CHAIN_RING];
+    __shared__ double s_tcom[3], s_tsite[S][3];
+    __shared__ int s_stop;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const double L = Sy.box;
+    const double rc_lj2 = Sy.rc_lj * Sy.rc_lj, rc_qq2 = Sy.rc_qq * Sy.rc_qq;
+    const int nt = Sy.n_types, nk = Sy.nk;
+    const int nit = (N + CHAIN_THREADS - 1) / CHAIN_THREADS;
+    const double twopi = 2.0 * 3.141592653589793;
+
+    // ---- the resident state comes on chip once
+    for (int t = tid; t < N * S; t += CHAIN_THREADS) s_site[t] = Sy.site[t];
+    for (int t = tid; t < N; t += CHAIN_THREADS) s_com[t] = Sy.com[t];
+    for (int t = tid; t < NK; t += CHAIN_THREADS) {
+        s_rhok[A.cur][t] = Sy.rhok[A.cur][t]; s_rhok[A.cur ^ 1][t] = Sy.rhok[A.cur][t];
+        s_kvec[t] = Sy.kvec[t]; s_cfac[t] = Sy.cfac[t];
+    }
+    if (tid < S) s_type[tid] = Sy.atype[tid];
+    if (tid == 0) s_stop = 0;
+
+    // ---- driver state (meaningful in lane 0 of warp 0 only)
+    long long pos = 0, ring_end = 0;
+    bool dry = false;
+    double pre0 = 0.0, pre1 = 0.0; int pre_cnt = 0;
+    MoveStat tr{0, 0, 0, 0, 0.5, A.dr_max}, ro{0, 0, 0, 0, 0.5, A.dphi_max};
+    double dr_max = A.dr_max, dphi_max = A.dphi_max;
+    double tot_e = A.e0, tot_v = A.v0;
+    long long n_acc = 0, n_ovl = 0, n_done = 0;
+    int cur = A.cur, ret = 0;
+    double ei[4] = {1, 0, 0, 0};
+    bool is_trans = true;
+    double nq[4] = {0, 0, 0, 0}, ndb[S * 3];    // quaternion and body frame of the NEXT molecule, prefetched
+#pragma unroll
+    for (int k = 0; k < S * 3; ++k) ndb[k] = 0.0;
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nq[k] = A.quat[k];
+#pragma unroll
+        for (int k = 0; k < S * 3; ++k) ndb[k] = A.db[k];
+    }
+    if (warp == 0) {                                        // first fill of the uniform ring
+        const long long lim = A.n_uniforms < CHAIN_RING ? A.n_uniforms : CHAIN_RING;
+        if (lane < lim) s_u[lane] = A.uniforms[lane];
+        if (lane + 32 < lim) s_u[lane + 32] = A.uniforms[lane + 32];
+        ring_end = lim;
+    }
+    __syncthreads();
+
+    auto next_u = [&]() -> double {                         // UStream::next of the host driver
+        if (pos >= A.n_uniforms) { dry = true; return 0.5; }
+        const double v = (pos < ring_end) ? s_u[pos & (CHAIN_RING - 1)] : A.uniforms[pos];
+        ++pos;
+        return v;
+    };
+
+    for (long long m = 0; m < A.n_moves; ++m) {
+        const int i = (int)(m % N);                         // sweep order i = 1..N (main.jl:490)
+        // ================= step 0: the trial move (main.jl:514-552), lane 0 of warp 0
+        if (warp == 0) {
+            if (pre_cnt > 0) {                              // uniforms requested during the previous move have landed
+                if (lane < pre_cnt) s_u[(ring_end + lane) & (CHAIN_RING - 1)] = pre0;
+                if (lane + 32 < pre_cnt) s_u[(ring_end + 32 + lane) & (CHAIN_RING - 1)] = pre1;
+                pre_cnt = __shfl_sync(0xffffffffu, pre_cnt, 0);
+                ring_end += pre_cnt;
+                pre_cnt = 0;
+                __syncwarp();
+            }
+            if (lane == 0) {
+                const double4 c0 = s_com[i];
+                double rnew[3] = {c0.x, c0.y, c0.z};
+                const double chose = next_u();              // main.jl:516
+                if (chose < A.p_trans) {                    // main.jl:519-529, auxillary.jl:94-103
+                    is_trans = true; tr.attempt += 1;
+                    const double z0 = next_u(), z1 = next_u(), z2 = next_u();
+                    rnew[0] = add(rnew[0], mul(sub(z0, 0.5), dr_max));
+                    rnew[1] = add(rnew[1], mul(sub(z1, 0.5), dr_max));
+                    rnew[2] = add(rnew[2], mul(sub(z2, 0.5), dr_max));
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {           // boundaries.jl:16-26
+                        if (rnew[k] > L) rnew[k] = sub(rnew[k], L);
+                        if (rnew[k] < 0) rnew[k] = add(rnew[k], L);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ei[k] = nq[k];
+                } else if (chose <= A.p_rot) {              // main.jl:530-538, quaternions.jl:52-73,94-120,158-182
+                    is_trans = false; ro.attempt += 1;
+                    if (fabs(sub(add(add(add(mul(nq[0], nq[0]), mul(nq[1], nq[1])), mul(nq[2], nq[2])), mul(nq[3], nq[3])), 1.0)) > 1.e-6) ret = 2;
+                    double ax[3], nrm;
+                    for (;;) {
+                        ax[0] = sub(mul(2.0, next_u()), 1.0); ax[1] = sub(mul(2.0, next_u()), 1.0); ax[2] = sub(mul(2.0, next_u()), 1.0);
+                        nrm = add(add(mul(ax[0], ax[0]), mul(ax[1], ax[1])), mul(ax[2], ax[2]));
+                        if (nrm < 1.0 || dry) break;
+                    }
+                    const double sn = __dsqrt_rn(nrm);
+                    ax[0] = __ddiv_rn(ax[0], sn); ax[1] = __ddiv_rn(ax[1], sn); ax[2] = __ddiv_rn(ax[2], sn);
+                    const double zeta = next_u();
+                    const double angle = mul(sub(mul(2.0, zeta), 1.0), dphi_max);
+                    const double ch = cos(mul(0.5, angle)), sh = sin(mul(0.5, angle));
+                    const double rq[4] = {ch, mul(sh, ax[0]), mul(sh, ax[1]), mul(sh, ax[2])};
+                    ei[0] = sub(sub(sub(mul(rq[0], nq[0]), mul(rq[1], nq[1])), mul(rq[2], nq[2])), mul(rq[3], nq[3]));   // quatmul(rot, old)
+                    ei[1] = add(sub(add(mul(rq[1], nq[0]), mul(rq[0], nq[1])), mul(rq[3], nq[2])), mul(rq[2], nq[3]));
+                    ei[2] = sub(add(add(mul(rq[2], nq[0]), mul(rq[3], nq[1])), mul(rq[0], nq[2])), mul(rq[1], nq[3]));
+                    ei[3] = add(add(sub(mul(rq[3], nq[0]), mul(rq[2], nq[1])), mul(rq[1], nq[2])), mul(rq[0], nq[3]));
+                } else ret = 3;                             // main.jl:539-541
+                if (ret == 0 && fabs(sub(add(add(add(mul(ei[0], ei[0]), mul(ei[1], ei[1])), mul(ei[2], ei[2])), mul(ei[3], ei[3])), 1.0)) > 1.e-6) ret = 2;
+                // quaternions.jl:37-50 — rows as written in the reference, [2,3] = 2(q2 q4 + q1 q2)
+                const double q1 = ei[0], q2 = ei[1], q3 = ei[2], q4 = ei[3];
+                double a[3][3];
+                a[0][0] = sub(sub(add(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
+                a[0][1] = mul(2, add(mul(q2, q3), mul(q1, q4))); a[0][2] = mul(2, sub(mul(q2, q4), mul(q1, q3)));
+                a[1][0] = mul(2, sub(mul(q2, q3), mul(q1, q4)));
+                a[1][1] = sub(add(sub(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
+                a[1][2] = mul(2, add(mul(q2, q4), mul(q1, q2)));
+                a[2][0] = mul(2, add(mul(q2, q4), mul(q1, q3))); a[2][1] = mul(2, sub(mul(q3, q4), mul(q1, q2)));
+                a[2][2] = add(sub(sub(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
+#pragma unroll
+                for (int s = 0; s < S; ++s)                 // main.jl:545-548: COM + MATMUL(ai, db)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        s_tsite[s][c] = add(rnew[c], add(add(mul(ndb[3 * s], a[0][c]), mul(ndb[3 * s + 1], a[1][c])), mul(ndb[3 * s + 2], a[2][c])));
+                s_tcom[0] = rnew[0]; s_tcom[1] = rnew[1]; s_tcom[2] = rnew[2];
+                if (ret) s_stop = ret;
+                // prefetch the next molecule's orientation and body frame (move m cannot change them)
+                const int inx = (i + 1 == N) ? 0 : i + 1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) nq[k] = A.quat[4 * inx + k];
+#pragma unroll
+                for (int k = 0; k < S * 3; ++k) ndb[k] = A.db[(size_t)inx * S * 3 + k];
+            }
+            {   // request the uniforms of the next move now; they are stored at the top of the next step 0
+                const long long p0 = __shfl_sync(0xffffffffu, pos, 0);
+                long long lim = p0 + CHAIN_RING;            // slot x may be overwritten once x - RING < pos
+                if (lim > A.n_uniforms) lim = A.n_uniforms;
+                const long long want = lim - ring_end;
+                pre_cnt = want > 0 ? (int)want : 0;
+                if (lane < pre_cnt) pre0 = A.uniforms[ring_end + lane];
+                if (lane + 32 < pre_cnt) pre1 = A.uniforms[ring_end + 32 + lane];
+            }
+        }
+        __syncthreads();                                    // B1
+        if (s_stop) break;
+
+        // ================= step 1: COM gate for the old and the trial position
+        const double4 co = s_com[i];
+        const double cnx = s_tcom[0], cny = s_tcom[1], cnz = s_tcom[2];
+        int myfl[CHAIN_MAXIT]; unsigned mymask[CHAIN_MAXIT];
+#pragma unroll
+        for (int it = 0; it < CHAIN_MAXIT; ++it) {
+            myfl[it] = 0; mymask[it] = 0;
+            if (it < nit) {
+                const int j = it * CHAIN_THREADS + tid;
+                int fl = 0;
+                if (j < N && j != i) {
+                    const double4 cj = s_com[j];
+                    {
+                        const double rx = min_image(co.x, cj.x, L), ry = min_image(co.y, cj.y, L), rz = min_image(co.z, cj.z, L);
+                        const double r2 = add(add(mul(rx, rx), mul(ry, ry)), mul(rz, rz));
+                        if (r2 < rc_lj2) fl |= 1;
+                        if (A.style_qq && r2 < rc_qq2) fl |= 2;
+                    }
+                    {
+                        const double rx = min_image(cnx, cj.x, L), ry = min_image(cny, cj.y, L), rz = min_image(cnz, cj.z, L);
+                        const double r2 = add(add(mul(rx, rx), mul(ry, ry)), mul(rz, rz));
+                        if (r2 < rc_lj2) fl |= 4;
+                        if (A.style_qq && r2 < rc_qq2) fl |= 8;
+                    }
+                }
+                const unsigned mk = __ballot_sync(0xffffffffu, fl != 0);
+                if (lane == 0) s_wcount[it * CHAIN_WARPS + warp] = __popc(mk);
+                myfl[it] = fl; mymask[it] = mk;
+            }
+        }
+        if (A.style_recip && warp == CHAIN_WARPS - 1 && lane < 2 * S * 3) {   // ewalds.jl:770-795
+            const int cfg = lane / (S * 3), rem = lane - cfg * S * 3, l = rem / 3, d = rem - 3 * l;
+            double x;
+            if (cfg == 0) { const double4 s = s_site[i * S + l]; x = d == 0 ? s.x : (d == 1 ? s.y : s.z); }
+            else x = s_tsite[l][d];
+            cplx e1;
+            sincos(twopi * x / L, &e1.im, &e1.re);
+            cplx e; e.re = 1.0; e.im = 0.0;
+            s_tab[cfg][l][d][0] = e;
+            e = e1;
+            s_tab[cfg][l][d][1] = e;
+            for (int k = 2; k <= nk; ++k) { e = cmul(e, e1); s_tab[cfg][l][d][k] = e; }
+        }
+        __syncthreads();                                    // B2
+        int n_in;
+        {   // exclusive prefix of the per-(iteration, warp) counts, in index order
+            const int nidx = nit * CHAIN_WARPS;
+            const int c0 = lane < nidx ? s_wcount[lane] : 0, c1 = lane + 32 < nidx ? s_wcount[lane + 32] : 0;
+            int i0 = c0, i1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v0 = __shfl_up_sync(0xffffffffu, i0, o), v1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if (lane >= o) { i0 += v0; i1 += v1; }
+            }
+            const int t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
+            n_in = t0 + t1;
+            const int e0 = i0 - c0, e1 = t0 + i1 - c1;       // exclusive prefixes of entries lane and lane+32
+#pragma unroll
+            for (int it = 0; it < CHAIN_MAXIT; ++it) {
+                if (it < nit) {
+                    const int idx = it * CHAIN_WARPS + warp;
+                    const int b0 = __shfl_sync(0xffffffffu, e0, idx & 31), b1 = __shfl_sync(0xffffffffu, e1, idx & 31);
+                    const int base = idx < 32 ? b0 : b1;
+                    if (myfl[it]) s_list[base + __popc(mymask[it] & lt)] = make_int2(it * CHAIN_THREADS + tid, myfl[it]);
+                }
+            }
+        }
+        __syncthreads();                                    // B3
+
+        // ================= step 2: site pairs of (partner, cfg, site a) items + ρ(k) delta
+        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const int items = n_in * 2 * S;
+        for (int w = tid; w < items; w += CHAIN_THREADS) {
+            const int jj = w / (2 * S), rem = w - jj * 2 * S, cfg = rem / S, a = rem - cfg * S;
+            const int2 e = s_list[jj];
+            const int j = e.x, fl = (e.y >> (2 * cfg)) & 3;
+            if (!fl) continue;
+            double4 sa = s_site[i * S + a];
+            double cix = co.x, ciy = co.y, ciz = co.z;
+            if (cfg) { sa.x = s_tsite[a][0]; sa.y = s_tsite[a][1]; sa.z = s_tsite[a][2]; cix = cnx; ciy = cny; ciz = cnz; }
+            const double4 cj = s_com[j];
+            const double rijx = min_image(cix, cj.x, L), rijy = min_image(ciy, cj.y, L), rijz = min_image(ciz, cj.z, L);
+            double r2[S], dx[S], dy[S], dz[S], qq[S];
+#pragma unroll
+            for (int b = 0; b < S; ++b) {
+                const double4 sb = s_site[j * S + b];
+                dx[b] = min_image(sa.x, sb.x, L); dy[b] = min_image(sa.y, sb.y, L); dz[b] = min_image(sa.z, sb.z, L);
+                r2[b] = dx[b] * dx[b] + dy[b] * dy[b] + dz[b] * dz[b];
+                qq[b] = sa.w * sb.w;
+            }
+            double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+            if (fl & 1) {                                   // energy.jl:270-282
+                const int ta = s_type[a];
+#pragma unroll
+                for (int b = 0; b < S; ++b) {
+                    const int tb = s_type[b];
+                    const double eps = Sy.eps[ta + tb * nt];
+                    if (r2[b] < (rc_lj2 + 100) && eps > 0.001)
+                        lj_pair(eps, Sy.sig[ta + tb * nt], r2[b], dx[b], dy[b], dz[b], rijx, rijy, rijz, l0, l1);
+                }
+            }
+            if (fl & 2) {                                   // ewalds.jl:359-367
+                bool use[S];
+#pragma unroll
+                for (int b = 0; b < S; ++b) {
+                    use[b] = false;
+                    if ((r2[b] < 0.5) && (qq[b] < 0)) l3 = 1.0;
+                    else if (r2[b] < rc_qq2 + 100) use[b] = true;
+                }
+                if (P.deg > 0) {                            // erfc(κr)/r = 1/r − κ·E(κ²r²), S chains in lock-step
+                    double sv[S], pv[S];
+#pragma unroll
+                    for (int b = 0; b < S; ++b) { sv[b] = fma(r2[b] * P.kappa2, P.scale, -1.0); pv[b] = P.c[P.deg]; }
+#pragma unroll 1
+                    for (int k = P.deg - 1; k >= 0; --k) {
+                        const double ck = P.c[k];
+#pragma unroll
+                        for (int b = 0; b < S; ++b) pv[b] = fma(pv[b], sv[b], ck);
+                    }
+#pragma unroll
+                    for (int b = 0; b < S; ++b) if (use[b]) l2 = fma(qq[b], fma(-P.kappa, pv[b], rsqrt(r2[b])), l2);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < S; ++b) if (use[b]) { const double r = sqrt(r2[b]); l2 += qq[b] * erfc(Sy.kappa * r) / r; }
+                }
+            }
+            if (cfg) { acc[4] += l0; acc[5] += l1; acc[6] += l2; acc[7] += l3; }
+            else { acc[0] += l0; acc[1] += l1; acc[2] += l2; acc[3] += l3; }
+        }
+        if (A.style_recip) {                                // ewalds.jl:804-821
+            const double2 *Sold = s_rhok[cur];
+            double2 *Snew = s_rhok[cur ^ 1];
+            for (int k = tid; k < NK; k += CHAIN_THREADS) {
+                const int4 kv = s_kvec[k];
+                const int aky = abs(kv.y), akz = abs(kv.z);
+                const bool ny = kv.y < 0, nz = kv.z < 0;
+                const double2 so = Sold[k];
+                double nr = so.x, ni = so.y;
+#pragma unroll
+                for (int l = 0; l < S; ++l) {
+                    const cplx tn = cmul(cmul(s_tab[1][l][0][kv.x], cconj_if(s_tab[1][l][1][aky], ny)), cconj_if(s_tab[1][l][2][akz], nz));
+                    const cplx to = cmul(cmul(s_tab[0][l][0][kv.x], cconj_if(s_tab[0][l][1][aky], ny)), cconj_if(s_tab[0][l][2][akz], nz));
+                    const double q = s_site[i * S + l].w;
+                    nr += q * (tn.re - to.re);
+                    ni += q * (tn.im - to.im);
+                }
+                Snew[k] = make_double2(nr, ni);
+                acc[8] += s_cfac[k] * ((nr * nr + ni * ni) - (so.x * so.x + so.y * so.y));
+            }
+        }
+        // ================= step 3: ordered reduction, decision, state update
+#pragma unroll
+        for (int v = 0; v < 9; ++v) {
+            acc[v] = warp_sum(acc[v]);
+            if (lane == 0) s_red[v * CHAIN_WARPS + warp] = acc[v];
+        }
+        __syncthreads();                                    // B4
+        if (warp == 0) {
+            double tot[9];
+#pragma unroll
+            for (int v = 0; v < 9; ++v) {
+                double x = lane < CHAIN_WARPS ? s_red[v * CHAIN_WARPS + lane] : 0.0;
+#pragma unroll
+                for (int o = CHAIN_WARPS / 2; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+                tot[v] = x;
+            }
+            if (lane == 0) {
+                // launch_move_on's folding (energy.jl:289 pot*4, vir*24/3; ewalds.jl:360; main.jl:580-590) + mmc_trial_move
+                const bool ovl0 = tot[3] > 0.0, ovl1 = tot[7] > 0.0, overlap = ovl0 || ovl1;
+                const double lj_old = mul(tot[0], 4), ljv_old = __ddiv_rn(mul(tot[1], 24), 3.0);
+                const double lj_new = mul(tot[4], 4), ljv_new = __ddiv_rn(mul(tot[5], 24), 3.0);
+                const double qq_old = mul(ovl0 ? 0.0 : tot[2], Sy.factor), qq_new = mul(ovl1 ? 0.0 : tot[6], Sy.factor);
+                const double d_recip = (overlap || !A.style_recip) ? 0.0 : mul(tot[8], Sy.factor);
+                double old_e = lj_old, old_v = ljv_old, new_e = lj_new, new_v = ljv_new;
+                if (A.style_qq) {                           // main.jl:501-505, 566-570
+                    old_v = add(old_v, __ddiv_rn(qq_old, 3)); old_e = add(old_e, qq_old);
+                    new_v = add(new_v, __ddiv_rn(qq_new, 3)); new_e = add(new_e, qq_new);
+                }
+                const double delta = add(sub(new_e, old_e), d_recip);                 // main.jl:593
+                if (overlap) n_ovl += 1;
+                const double x = __ddiv_rn(delta, A.temperature);
+                bool okm = true;
+                if (!(x < 0.0)) okm = exp(-x) > next_u();                            // auxillary.jl:106-114
+                const bool accd = okm && !overlap;                                    // main.jl:598
+                if (accd) {
+                    tot_e = add(tot_e, delta);
+                    tot_v = add(tot_v, add(sub(new_v, old_v), __ddiv_rn(d_recip, 3)));
+                    n_acc += 1;
+                    if (is_trans) tr.naccept += 1; else ro.naccept += 1;
+                    s_com[i] = make_double4(s_tcom[0], s_tcom[1], s_tcom[2], 0.0);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        double4 t = s_site[i * S + s];
+                        t.x = s_tsite[s][0]; t.y = s_tsite[s][1]; t.z = s_tsite[s][2];
+                        s_site[i * S + s] = t;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) A.quat[4 * i + k] = ei[k];
+                    if (A.style_recip && !overlap) cur ^= 1;                          // main.jl:621 as an index flip
+                }
+                if (A.accepted) A.accepted[m] = accd ? 1 : 0;
+                if (A.delta) A.delta[m] = delta;
+                if (dry) { ret = 1; s_stop = 1; }
+                else {
+                    if (A.adjust && i == N - 1) {                                     // main.jl:645-651
+                        tr.d_max = dr_max; adjust_step(tr, L); dr_max = tr.d_max;
+                        ro.d_max = dphi_max; adjust_step(ro, L); dphi_max = ro.d_max;
+                    }
+                    n_done = m + 1;
+                }
+            }
+            cur = __shfl_sync(0xffffffffu, cur, 0);
+            s_wcount[0] = cur;                               // everybody needs the Old/New index for the next move
+        }
+        __syncthreads();                                    // B5
+        cur = s_wcount[0];
+        if (s_stop) break;
+    }
+    __syncthreads();
+    // ---- the state goes back to HBM; ρ(k) Old of the final state into BOTH buffers' Old slot
+    for (int t = tid; t < N * S; t += CHAIN_THREADS) Sy.site[t] = s_site[t];
+    for (int t = tid; t < N; t += CHAIN_THREADS) Sy.com[t] = s_com[t];
+    for (int t = tid; t < NK; t += CHAIN_THREADS) Sy.rhok[cur][t] = s_rhok[cur][t];
+    if (tid == 0) {
+        ChainOut o;
+        o.n_moves = n_done; o.n_accepted = n_acc; o.n_overlap = n_ovl; o.uniforms_used = pos;
+        o.trans_attempt = tr.attempt; o.trans_accept = tr.naccept; o.rot_attempt = ro.attempt; o.rot_accept = ro.naccept;
+        o.dr_max = dr_max; o.dphi_max = dphi_max; o.total_energy = tot_e; o.total_virial = tot_v;
+        o.ret = ret; o.cur = cur;
+        *A.out = o;
+    }
+}

@@ -2,6 +2,7 @@
 // No CPU fallback: every energy returned here was computed by a kernel in this directory.
 #include "../../include/mmc_b200.h"
 #include "kernels_move.cuh"
+#include "kernels_chain.cuh"
 #include "kernels_pairs.cuh"
 #include "kernels_pairs_v3.cuh"
 #include "kernels_pairs_v4.cuh"
@@ -74,6 +75,9 @@ struct mmc_handle {
     MoveOut mout{};               // host-side fold of the slots of the last move launch
     MoveOut *h_out = &mout;
     ErfPoly move_poly{};          // erf polynomial of the resident box for the per-move kernels
+    // ---- device-resident block of moves (mmc_loop_run_device)
+    unsigned char *d_chain = nullptr;   // [uniforms | quat | db | delta | out | accepted]
+    size_t chain_bytes = 0;
     int pend_kind = 0;            // accepted move not yet written to HBM: 0 none, 1 molecule, 2 atom
     int pend_i = 0, pend_ns = 0;
     double pend_com[3] = {0, 0, 0};
@@ -180,7 +184,7 @@ void free_system(mmc_handle *h)
     h->raw_bytes = 0; h->cap_mol = 0; h->cap_sites = 0;
     dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
     h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
-    dfree(h->d_mrows); dfree(h->d_gf);
+    dfree(h->d_mrows); dfree(h->d_gf); dfree(h->d_chain); h->chain_bytes = 0;
     dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl);
     dfree(h->d_rhok_partial); dfree(h->d_units); dfree(h->d_slots);
     h->units_cap = 0; h->slots_cap = 0;

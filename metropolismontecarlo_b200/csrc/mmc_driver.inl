@@ -165,6 +165,88 @@ extern "C" int mmc_loop_run(mmc_handle *h, const mmc_loop_params *p, double *com
     return ret;
 }
 
+// The same loop, evaluated on the device for the whole block of moves (kernels_chain.cuh): one launch,
+// the system's state in one SM's shared memory.  Arguments, draw order, return codes and statistics are
+// those of mmc_loop_run; energies are summed in a different (fixed) order than the per-move kernels, so
+// deltas agree to rounding (≈1e-13 relative) and the accept/reject record is the same.
+extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, double *com, double *quat, const double *db,
+                                   const double *uniforms, int64_t n_uniforms, int64_t n_moves, double e0, double v0,
+                                   uint8_t *accepted, double *delta_out, mmc_loop_stats *st)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_system) FAIL(MMC_ESTATE, "no molecular system uploaded");
+    if (!p || !com || !quat || !db || !uniforms || !st || n_moves < 0 || n_uniforms < 0) FAIL(MMC_EINVAL, "bad argument");
+    int rc = style_check(h, p->style);
+    if (rc) return rc;
+    if (p->style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "mmc_loop_run_device is for molecular systems");
+    if (h->trial_pending || h->vol_pending) FAIL(MMC_ESTATE, "a trial move is pending");
+    const DevSystem &S = h->S;
+    if (!(S.rc_lj < S.box / 2)) FAIL(MMC_EINVAL, "r_cut must be < box/2 (Ewald/main.jl:483)");
+    if (!h->uniform || h->US < 1 || h->US > 4) FAIL(MMC_EINVAL, "device loop needs a uniform topology with 1..4 sites per molecule");
+    if (S.n_mol < 2 || S.n_mol > CHAIN_MAXIT * CHAIN_THREADS) FAIL(MMC_EINVAL, "device loop: 2 <= n_mol <= 2048");
+    const bool recip = p->style == MMC_STYLE_EWALD;
+    const size_t smem = chain_smem_bytes(S.n_mol, h->US, recip ? S.nkvecs : 0);
+    int dev = 0, max_optin = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem + 8 * 1024 > (size_t)max_optin) FAIL(MMC_EINVAL, "device loop: the system does not fit one SM's shared memory; use mmc_loop_run");
+    if ((rc = flush_pending(h))) return rc;
+    // one device block: [uniforms | quat | db | delta | out | accepted]
+    const size_t n_q = 4 * (size_t)S.n_mol, n_db = 3 * (size_t)S.n_sites;
+    const size_t off_q = (size_t)n_uniforms, off_db = off_q + n_q, off_delta = off_db + n_db, off_out = off_delta + (size_t)n_moves;
+    const size_t out_doubles = (sizeof(ChainOut) + 7) / 8;
+    const size_t bytes = (off_out + out_doubles) * sizeof(double) + (size_t)n_moves + 16;
+    if (bytes > h->chain_bytes) {
+        dfree(h->d_chain);
+        CK(cudaMalloc(&h->d_chain, bytes));
+        h->chain_bytes = bytes;
+    }
+    double *d = reinterpret_cast<double *>(h->d_chain);
+    unsigned char *d_acc = reinterpret_cast<unsigned char *>(d + off_out + out_doubles);
+    CK(cudaMemcpyAsync(d, uniforms, sizeof(double) * (size_t)n_uniforms, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + off_q, quat, sizeof(double) * n_q, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + off_db, db, sizeof(double) * n_db, cudaMemcpyHostToDevice, h->stream));
+    ChainArgs A{};
+    A.n_moves = n_moves; A.n_uniforms = n_uniforms;
+    A.style_qq = p->style != MMC_STYLE_LJ_ONLY; A.style_recip = recip;
+    A.adjust = p->adjust; A.cur = h->cur;
+    A.temperature = p->temperature; A.dr_max = p->dr_max; A.dphi_max = p->dphi_max;
+    A.p_trans = p->p_trans; A.p_rot = p->p_rot; A.e0 = e0; A.v0 = v0;
+    A.uniforms = d; A.quat = d + off_q; A.db = d + off_db; A.delta = d + off_delta;
+    A.out = reinterpret_cast<ChainOut *>(d + off_out); A.accepted = d_acc;
+#define MMC_CHAIN_LAUNCH(SS)                                                                                         \
+    {                                                                                                                \
+        CK(cudaFuncSetAttribute(k_chain<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+        k_chain<SS><<<1, CHAIN_THREADS, smem, h->stream>>>(h->S, A, h->move_poly);                                   \
+    }
+    switch (h->US) {
+        case 1: MMC_CHAIN_LAUNCH(1) break;
+        case 2: MMC_CHAIN_LAUNCH(2) break;
+        case 3: MMC_CHAIN_LAUNCH(3) break;
+        default: MMC_CHAIN_LAUNCH(4) break;
+    }
+#undef MMC_CHAIN_LAUNCH
+    LAUNCH_CHECK();
+    ChainOut o{};
+    std::vector<double4> hc(S.n_mol);
+    CK(cudaMemcpyAsync(&o, A.out, sizeof(o), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hc.data(), S.com, sizeof(double4) * S.n_mol, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(quat, A.quat, sizeof(double) * n_q, cudaMemcpyDeviceToHost, h->stream));
+    if (accepted && n_moves) CK(cudaMemcpyAsync(accepted, d_acc, (size_t)n_moves, cudaMemcpyDeviceToHost, h->stream));
+    if (delta_out && n_moves) CK(cudaMemcpyAsync(delta_out, A.delta, sizeof(double) * (size_t)n_moves, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int m = 0; m < S.n_mol; ++m) { com[3 * m] = hc[m].x; com[3 * m + 1] = hc[m].y; com[3 * m + 2] = hc[m].z; }
+    h->cur = o.cur;
+    h->new_valid = false;
+    h->cnt.trial_moves += o.n_moves; h->cnt.commits += o.n_accepted; h->cnt.overlap_events += o.n_overlap;
+    std::memset(st, 0, sizeof(*st));
+    st->n_moves = o.n_moves; st->n_accepted = o.n_accepted; st->n_overlap = o.n_overlap; st->uniforms_used = o.uniforms_used;
+    st->trans_attempt = o.trans_attempt; st->trans_accept = o.trans_accept;
+    st->rot_attempt = o.rot_attempt; st->rot_accept = o.rot_accept;
+    st->dr_max = o.dr_max; st->dphi_max = o.dphi_max; st->total_energy = o.total_energy; st->total_virial = o.total_virial;
+    return o.ret;
+}
+
 extern "C" int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_max, double *r,
                                   const double *uniforms, int64_t n_uniforms, int64_t n_moves, double e0, double v0,
                                   uint8_t *accepted, double *delta_out, mmc_loop_stats *st)

@@ -235,7 +235,10 @@ class Engine:
         self._ck(self.lib.mmc_volume_reject(self.h))
 
     # ---- the Loop stand-in (Ewald/main.jl:487-651) in the library's C++ host driver
-    def loop_run(self, params: LoopParams, com, quat, db, uniforms, n_moves, e0=0.0, v0=0.0):
+    def loop_run(self, params: LoopParams, com, quat, db, uniforms, n_moves, e0=0.0, v0=0.0, device=False):
+        """Loop() of Ewald/main.jl:487-651 over the C ABI: one fused launch per move (device=False, the
+        ccall protocol) or the whole block of moves in one launch with the state on chip (device=True)."""
+        fn = self.lib.mmc_loop_run_device if device else self.lib.mmc_loop_run
         assert com.dtype == np.float64 and com.flags.c_contiguous
         assert quat.dtype == np.float64 and quat.flags.c_contiguous
         db = np.ascontiguousarray(db, dtype=np.float64)
@@ -243,7 +246,7 @@ class Engine:
         acc = np.zeros(n_moves, dtype=np.uint8)
         delta = np.zeros(n_moves)
         st = LoopStats()
-        rc = self._ck(self.lib.mmc_loop_run(self.h, C.byref(params), _dp(com), _dp(quat), _dp(db), _dp(uniforms),
+        rc = self._ck(fn(self.h, C.byref(params), _dp(com), _dp(quat), _dp(db), _dp(uniforms),
                                             uniforms.shape[0], n_moves, e0, v0,
                                             acc.ctypes.data_as(_lib.c_uint8_p), _dp(delta), C.byref(st)))
         return rc, acc, delta, st

@@ -105,3 +105,66 @@ def test_monatomic_lj_trajectory():
     assert np.array_equal(r_g, r_o) and np.array_equal(eng.download_atoms(), r_o)
     assert rel(st_g.total_energy, eng.potential("atoms").energy) < 1e-10
     eng.close()
+
+
+@pytest.mark.parametrize("style,sid", [("ewald", 0), ("wolf", 1)])
+def test_device_loop_matches_oracle_and_host_driver(style, sid):
+    """mmc_loop_run_device: the whole block of 10^4 moves in one launch (state in shared memory).
+    Same accept/reject record, uniform consumption and step-size adaptation as the oracle's Loop();
+    deltas to rounding; the state it leaves in the library equals the host-driven run's."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.load_nist(4)
+    rc, T = 10.0, 298.15
+    u = julia_rand(11234, 8 * N_MOVES)
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    p0 = ora.potential_ewald(s, ew, rc, rc, ms.box, 4) if sid == 0 else ora.potential_wolf(s, ew, rc, rc, ms.box, 4)
+    prm = ora.LoopParams(T, 0.316555789, 0.05, 0.5, 1.0, rc, rc, ms.box, sid, 1)
+    quat_o = ms.quat.copy()
+    rc_o, acc_o, del_o, st_o = ora.loop(s, ew, ms.db, quat_o, prm, u, N_MOVES, p0.energy, p0.virial)
+    eng = water_engine(ms, rc)
+    g0 = eng.potential(style)
+    com, quat = ms.com.copy(), ms.quat.copy()
+    rc_g, acc_g, del_g, st_g = eng.loop_run(LoopParams(T, 0.316555789, 0.05, 0.5, 1.0, sid, 1), com, quat, ms.db,
+                                            u, N_MOVES, g0.energy, g0.virial, device=True)
+    assert rc_g == 0 and st_g.n_moves == N_MOVES
+    assert np.array_equal(acc_g, acc_o), f"first divergence at move {int(np.argmax(acc_g != acc_o))}"
+    assert st_g.uniforms_used == st_o.uniforms_used
+    assert st_g.n_accepted == st_o.n_accepted and st_g.rot_accept == st_o.rot_accept and st_g.n_overlap == st_o.n_overlap
+    assert abs(st_g.dr_max - st_o.dr_max) < 1e-12 and abs(st_g.dphi_max - st_o.dphi_max) < 1e-12
+    scale = max(np.abs(del_o).max(), 1.0)
+    assert np.abs(del_g - del_o).max() < 1e-10 * abs(p0.energy) and np.abs(del_g - del_o).max() < 1e-6 * scale
+    # device cos/sin may differ from libm in the last bit: positions to 1e-12 Å instead of bit equality
+    assert np.abs(com - s.com).max() < 1e-12 and np.abs(quat - quat_o).max() < 1e-12
+    coords, com_d = eng.download_system()
+    assert np.abs(coords - s.coords).max() < 1e-11 and np.array_equal(com_d, com)
+    fresh = eng.potential(style)                    # running total == fresh recompute (Poly/main.jl:232-235)
+    assert rel(st_g.total_energy, fresh.energy) < 1e-10
+    assert rel(st_g.total_energy, st_o.total_energy) < 1e-11
+    # the per-move entry points continue from the state the block left behind
+    i = 7
+    t = eng.trial_move(i, com[i - 1] + 0.05, coords[3 * (i - 1):3 * i] + 0.05, style)
+    e_old = ora.LJ_poly_dU(i, s, rc, ms.box)[0] + ora.EwaldShort(i, s, ew, rc, ms.box)[0]
+    assert rel(t.lj_old + t.qq_old, e_old) < 1e-9
+    eng.reject()
+    eng.close()
+
+
+def test_device_loop_short_stream_and_small_system():
+    """Return code 1 when the uniform stream runs dry, exactly where the host driver stops; 100-molecule box."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.load_nist(1)
+    u = np.random.default_rng(5).random(1500)
+    outs = []
+    for device in (False, True):
+        eng = water_engine(ms, 9.0)
+        g0 = eng.potential("ewald")
+        com, quat = ms.com.copy(), ms.quat.copy()
+        rc, acc, delta, st = eng.loop_run(LoopParams(298.15, 0.3, 0.05, 0.5, 1.0, 0, 1), com, quat, ms.db, u, 2000,
+                                          g0.energy, g0.virial, device=device)
+        outs.append((rc, acc.copy(), st.n_moves, st.uniforms_used, st.n_accepted, com.copy()))
+        eng.close()
+    assert outs[0][0] == 1 and outs[1][0] == 1
+    assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3] == 1500 and outs[0][4] == outs[1][4]
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.abs(outs[0][5] - outs[1][5]).max() < 1e-12
