@@ -36,6 +36,7 @@ struct ChainOut {                // mirrors mmc_loop_stats + return code + final
     long long trans_attempt, trans_accept, rot_attempt, rot_accept;
     double dr_max, dphi_max, total_energy, total_virial;
     int ret, cur;
+    long long phase_cycles[6];   // lane 0 of warp 0: step 0, step 1 + B2, compaction + B3, step 2, warp sums + B4 wait, reduce + decision + B5
 };
 
 struct ChainArgs {
@@ -79,7 +80,27 @@ __device__ inline void adjust_step(MoveStat &m, double L)
 }
 }  // namespace chain
 
-template <int S>
+// Driver state of the block (what Loop() keeps in local variables): lives in shared memory and is touched
+// by lane 0 of warp 0 only, so that it costs the 511 other threads no registers in the pair loops.
+struct ChainDriver {
+    long long n_acc, n_ovl, n_done;
+    chain::MoveStat tr, ro;
+    double dr_max, dphi_max, tot_e, tot_v;
+    double ei[4], nq[4], ndb[4 * 3];
+    int ret, is_trans, cur;
+};
+
+// MUFU.RSQ64H seed + one cubic Newton step (see kernels_pairs_v3.cuh fast_rsqrt)
+__device__ __forceinline__ double chain_rsqrt(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(x, -(y0 * y0), 1.0);
+    return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+}
+
+// DEG > 0: padded degree of the erf polynomial at compile time; 0: erfc(); -1: run-time degree
+template <int S, int DEG>
 __global__ void __launch_bounds__(CHAIN_THREADS, 1)
 k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs A, const __grid_constant__ ErfPoly P)
 {
@@ -101,7 +122,8 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
     __shared__ double s_red[9 * CHAIN_WARPS];
     __shared__ double s_u[CHAIN_RING];
     __shared__ double s_tcom[3], s_tsite[S][3];
-    __shared__ int s_stop;
+    __shared__ int s_stop, s_cur;
+    __shared__ ChainDriver D;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -119,61 +141,63 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
         s_kvec[t] = Sy.kvec[t]; s_cfac[t] = Sy.cfac[t];
     }
     if (tid < S) s_type[tid] = Sy.atype[tid];
-    if (tid == 0) s_stop = 0;
-
-    // ---- driver state (meaningful in lane 0 of warp 0 only)
-    long long pos = 0, ring_end = 0;
-    bool dry = false;
-    double pre0 = 0.0, pre1 = 0.0; int pre_cnt = 0;
-    MoveStat tr{0, 0, 0, 0, 0.5, A.dr_max}, ro{0, 0, 0, 0, 0.5, A.dphi_max};
-    double dr_max = A.dr_max, dphi_max = A.dphi_max;
-    double tot_e = A.e0, tot_v = A.v0;
-    long long n_acc = 0, n_ovl = 0, n_done = 0;
-    int cur = A.cur, ret = 0;
-    double ei[4] = {1, 0, 0, 0};
-    bool is_trans = true;
-    double nq[4] = {0, 0, 0, 0}, ndb[S * 3];    // quaternion and body frame of the NEXT molecule, prefetched
-#pragma unroll
-    for (int k = 0; k < S * 3; ++k) ndb[k] = 0.0;
     if (tid == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) nq[k] = A.quat[k];
-#pragma unroll
-        for (int k = 0; k < S * 3; ++k) ndb[k] = A.db[k];
+        s_stop = 0; s_cur = A.cur;
+        D.n_acc = 0; D.n_ovl = 0; D.n_done = 0;
+        D.tr = MoveStat{0, 0, 0, 0, 0.5, A.dr_max}; D.ro = MoveStat{0, 0, 0, 0, 0.5, A.dphi_max};
+        D.dr_max = A.dr_max; D.dphi_max = A.dphi_max; D.tot_e = A.e0; D.tot_v = A.v0;
+        D.ret = 0; D.is_trans = 1; D.cur = A.cur;
+        for (int k = 0; k < 4; ++k) { D.ei[k] = 0.0; D.nq[k] = A.quat[k]; }
+        for (int k = 0; k < S * 3; ++k) D.ndb[k] = A.db[k];
     }
     if (warp == 0) {                                        // first fill of the uniform ring
         const long long lim = A.n_uniforms < CHAIN_RING ? A.n_uniforms : CHAIN_RING;
         if (lane < lim) s_u[lane] = A.uniforms[lane];
         if (lane + 32 < lim) s_u[lane + 32] = A.uniforms[lane + 32];
-        ring_end = lim;
     }
+    // prefetch registers of warp 0: uniforms (two per lane) and the next molecule's quaternion / body frame (one per lane)
+    double pre0 = 0.0, pre1 = 0.0, pfq = 0.0;
+    int pre_cnt = 0, pf_on = 0;
+    long long pos = 0, ring_end = A.n_uniforms < CHAIN_RING ? A.n_uniforms : CHAIN_RING;   // stream position (lane 0), ring fill (warp 0)
+    bool dry = false;
     __syncthreads();
 
-    auto next_u = [&]() -> double {                         // UStream::next of the host driver
+    auto next_u = [&]() -> double {                         // UStream::next of the host driver (lane 0 of warp 0)
         if (pos >= A.n_uniforms) { dry = true; return 0.5; }
         const double v = (pos < ring_end) ? s_u[pos & (CHAIN_RING - 1)] : A.uniforms[pos];
         ++pos;
         return v;
     };
 
+    long long pc[6] = {0, 0, 0, 0, 0, 0};
+    int cur = A.cur;
     for (long long m = 0; m < A.n_moves; ++m) {
         const int i = (int)(m % N);                         // sweep order i = 1..N (main.jl:490)
+        long long tc0 = clock64();
         // ================= step 0: the trial move (main.jl:514-552), lane 0 of warp 0
         if (warp == 0) {
             if (pre_cnt > 0) {                              // uniforms requested during the previous move have landed
                 if (lane < pre_cnt) s_u[(ring_end + lane) & (CHAIN_RING - 1)] = pre0;
                 if (lane + 32 < pre_cnt) s_u[(ring_end + 32 + lane) & (CHAIN_RING - 1)] = pre1;
-                pre_cnt = __shfl_sync(0xffffffffu, pre_cnt, 0);
                 ring_end += pre_cnt;
                 pre_cnt = 0;
-                __syncwarp();
             }
+            if (pf_on) {                                    // ... and so have the next molecule's quaternion and body frame
+                if (lane >= 1 && lane <= 4) D.nq[lane - 1] = pfq;
+                if (lane >= 5 && lane < 5 + S * 3) D.ndb[lane - 5] = pfq;
+                pf_on = 0;
+            }
+            __syncwarp();
             if (lane == 0) {
+                const double dr_max = D.dr_max, dphi_max = D.dphi_max;
+                const double nq0 = D.nq[0], nq1 = D.nq[1], nq2 = D.nq[2], nq3 = D.nq[3];
                 const double4 c0 = s_com[i];
                 double rnew[3] = {c0.x, c0.y, c0.z};
+                double e0 = nq0, e1 = nq1, e2 = nq2, e3 = nq3;
+                int ret = 0;
                 const double chose = next_u();              // main.jl:516
                 if (chose < A.p_trans) {                    // main.jl:519-529, auxillary.jl:94-103
-                    is_trans = true; tr.attempt += 1;
+                    D.is_trans = 1; D.tr.attempt += 1;
                     const double z0 = next_u(), z1 = next_u(), z2 = next_u();
                     rnew[0] = add(rnew[0], mul(sub(z0, 0.5), dr_max));
                     rnew[1] = add(rnew[1], mul(sub(z1, 0.5), dr_max));
@@ -183,31 +207,31 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                         if (rnew[k] > L) rnew[k] = sub(rnew[k], L);
                         if (rnew[k] < 0) rnew[k] = add(rnew[k], L);
                     }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) ei[k] = nq[k];
                 } else if (chose <= A.p_rot) {              // main.jl:530-538, quaternions.jl:52-73,94-120,158-182
-                    is_trans = false; ro.attempt += 1;
-                    if (fabs(sub(add(add(add(mul(nq[0], nq[0]), mul(nq[1], nq[1])), mul(nq[2], nq[2])), mul(nq[3], nq[3])), 1.0)) > 1.e-6) ret = 2;
-                    double ax[3], nrm;
+                    D.is_trans = 0; D.ro.attempt += 1;
+                    if (fabs(sub(add(add(add(mul(nq0, nq0), mul(nq1, nq1)), mul(nq2, nq2)), mul(nq3, nq3)), 1.0)) > 1.e-6) ret = 2;
+                    double ax0, ax1, ax2, nrm;
                     for (;;) {
-                        ax[0] = sub(mul(2.0, next_u()), 1.0); ax[1] = sub(mul(2.0, next_u()), 1.0); ax[2] = sub(mul(2.0, next_u()), 1.0);
-                        nrm = add(add(mul(ax[0], ax[0]), mul(ax[1], ax[1])), mul(ax[2], ax[2]));
+                        ax0 = sub(mul(2.0, next_u()), 1.0); ax1 = sub(mul(2.0, next_u()), 1.0); ax2 = sub(mul(2.0, next_u()), 1.0);
+                        nrm = add(add(mul(ax0, ax0), mul(ax1, ax1)), mul(ax2, ax2));
                         if (nrm < 1.0 || dry) break;
                     }
                     const double sn = __dsqrt_rn(nrm);
-                    ax[0] = __ddiv_rn(ax[0], sn); ax[1] = __ddiv_rn(ax[1], sn); ax[2] = __ddiv_rn(ax[2], sn);
+                    ax0 = __ddiv_rn(ax0, sn); ax1 = __ddiv_rn(ax1, sn); ax2 = __ddiv_rn(ax2, sn);
                     const double zeta = next_u();
                     const double angle = mul(sub(mul(2.0, zeta), 1.0), dphi_max);
-                    const double ch = cos(mul(0.5, angle)), sh = sin(mul(0.5, angle));
-                    const double rq[4] = {ch, mul(sh, ax[0]), mul(sh, ax[1]), mul(sh, ax[2])};
-                    ei[0] = sub(sub(sub(mul(rq[0], nq[0]), mul(rq[1], nq[1])), mul(rq[2], nq[2])), mul(rq[3], nq[3]));   // quatmul(rot, old)
-                    ei[1] = add(sub(add(mul(rq[1], nq[0]), mul(rq[0], nq[1])), mul(rq[3], nq[2])), mul(rq[2], nq[3]));
-                    ei[2] = sub(add(add(mul(rq[2], nq[0]), mul(rq[3], nq[1])), mul(rq[0], nq[2])), mul(rq[1], nq[3]));
-                    ei[3] = add(add(sub(mul(rq[3], nq[0]), mul(rq[2], nq[1])), mul(rq[1], nq[2])), mul(rq[0], nq[3]));
+                    double sh, ch;
+                    sincos(mul(0.5, angle), &sh, &ch);
+                    const double r0 = ch, r1 = mul(sh, ax0), r2q = mul(sh, ax1), r3 = mul(sh, ax2);
+                    e0 = sub(sub(sub(mul(r0, nq0), mul(r1, nq1)), mul(r2q, nq2)), mul(r3, nq3));   // quatmul(rot, old)
+                    e1 = add(sub(add(mul(r1, nq0), mul(r0, nq1)), mul(r3, nq2)), mul(r2q, nq3));
+                    e2 = sub(add(add(mul(r2q, nq0), mul(r3, nq1)), mul(r0, nq2)), mul(r1, nq3));
+                    e3 = add(add(sub(mul(r3, nq0), mul(r2q, nq1)), mul(r1, nq2)), mul(r0, nq3));
                 } else ret = 3;                             // main.jl:539-541
-                if (ret == 0 && fabs(sub(add(add(add(mul(ei[0], ei[0]), mul(ei[1], ei[1])), mul(ei[2], ei[2])), mul(ei[3], ei[3])), 1.0)) > 1.e-6) ret = 2;
+                if (ret == 0 && fabs(sub(add(add(add(mul(e0, e0), mul(e1, e1)), mul(e2, e2)), mul(e3, e3)), 1.0)) > 1.e-6) ret = 2;
+                D.ei[0] = e0; D.ei[1] = e1; D.ei[2] = e2; D.ei[3] = e3;
                 // quaternions.jl:37-50 — rows as written in the reference, [2,3] = 2(q2 q4 + q1 q2)
-                const double q1 = ei[0], q2 = ei[1], q3 = ei[2], q4 = ei[3];
+                const double q1 = e0, q2 = e1, q3 = e2, q4 = e3;
                 double a[3][3];
                 a[0][0] = sub(sub(add(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
                 a[0][1] = mul(2, add(mul(q2, q3), mul(q1, q4))); a[0][2] = mul(2, sub(mul(q2, q4), mul(q1, q3)));
@@ -217,29 +241,31 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                 a[2][0] = mul(2, add(mul(q2, q4), mul(q1, q3))); a[2][1] = mul(2, sub(mul(q3, q4), mul(q1, q2)));
                 a[2][2] = add(sub(sub(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
 #pragma unroll
-                for (int s = 0; s < S; ++s)                 // main.jl:545-548: COM + MATMUL(ai, db)
+                for (int s = 0; s < S; ++s) {               // main.jl:545-548: COM + MATMUL(ai, db)
+                    const double d0 = D.ndb[3 * s], d1 = D.ndb[3 * s + 1], d2 = D.ndb[3 * s + 2];
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        s_tsite[s][c] = add(rnew[c], add(add(mul(ndb[3 * s], a[0][c]), mul(ndb[3 * s + 1], a[1][c])), mul(ndb[3 * s + 2], a[2][c])));
+                        s_tsite[s][c] = add(rnew[c], add(add(mul(d0, a[0][c]), mul(d1, a[1][c])), mul(d2, a[2][c])));
+                }
                 s_tcom[0] = rnew[0]; s_tcom[1] = rnew[1]; s_tcom[2] = rnew[2];
-                if (ret) s_stop = ret;
-                // prefetch the next molecule's orientation and body frame (move m cannot change them)
-                const int inx = (i + 1 == N) ? 0 : i + 1;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) nq[k] = A.quat[4 * inx + k];
-#pragma unroll
-                for (int k = 0; k < S * 3; ++k) ndb[k] = A.db[(size_t)inx * S * 3 + k];
+                if (ret) { D.ret = ret; s_stop = ret; }
             }
-            {   // request the uniforms of the next move now; they are stored at the top of the next step 0
-                const long long p0 = __shfl_sync(0xffffffffu, pos, 0);
+            __syncwarp();
+            {   // requests for the NEXT move, consumed at the top of its step 0: uniforms, quaternion, body frame
+                const long long p0 = __shfl_sync(0xffffffffu, pos, 0), re = ring_end;
                 long long lim = p0 + CHAIN_RING;            // slot x may be overwritten once x - RING < pos
                 if (lim > A.n_uniforms) lim = A.n_uniforms;
-                const long long want = lim - ring_end;
+                const long long want = lim - re;
                 pre_cnt = want > 0 ? (int)want : 0;
-                if (lane < pre_cnt) pre0 = A.uniforms[ring_end + lane];
-                if (lane + 32 < pre_cnt) pre1 = A.uniforms[ring_end + 32 + lane];
+                if (lane < pre_cnt) pre0 = A.uniforms[re + lane];
+                if (lane + 32 < pre_cnt) pre1 = A.uniforms[re + 32 + lane];
+                const int inx = (i + 1 == N) ? 0 : i + 1;   // move m cannot change molecule i+1
+                if (lane >= 1 && lane <= 4) pfq = A.quat[4 * inx + lane - 1];
+                if (lane >= 5 && lane < 5 + S * 3) pfq = A.db[(size_t)inx * S * 3 + lane - 5];
+                pf_on = 1;
             }
         }
+        { const long long t = clock64(); pc[0] += t - tc0; tc0 = t; }
         __syncthreads();                                    // B1
         if (s_stop) break;
 
@@ -287,6 +313,7 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
             for (int k = 2; k <= nk; ++k) { e = cmul(e, e1); s_tab[cfg][l][d][k] = e; }
         }
         __syncthreads();                                    // B2
+        { const long long t = clock64(); pc[1] += t - tc0; tc0 = t; }
         int n_in;
         {   // exclusive prefix of the per-(iteration, warp) counts, in index order
             const int nidx = nit * CHAIN_WARPS;
@@ -311,6 +338,7 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
             }
         }
         __syncthreads();                                    // B3
+        { const long long t = clock64(); pc[2] += t - tc0; tc0 = t; }
 
         // ================= step 2: site pairs of (partner, cfg, site a) items + ρ(k) delta
         double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -323,8 +351,6 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
             double4 sa = s_site[i * S + a];
             double cix = co.x, ciy = co.y, ciz = co.z;
             if (cfg) { sa.x = s_tsite[a][0]; sa.y = s_tsite[a][1]; sa.z = s_tsite[a][2]; cix = cnx; ciy = cny; ciz = cnz; }
-            const double4 cj = s_com[j];
-            const double rijx = min_image(cix, cj.x, L), rijy = min_image(ciy, cj.y, L), rijz = min_image(ciz, cj.z, L);
             double r2[S], dx[S], dy[S], dz[S], qq[S];
 #pragma unroll
             for (int b = 0; b < S; ++b) {
@@ -336,6 +362,8 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
             double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
             if (fl & 1) {                                   // energy.jl:270-282
                 const int ta = s_type[a];
+                const double4 cj = s_com[j];
+                const double rijx = min_image(cix, cj.x, L), rijy = min_image(ciy, cj.y, L), rijz = min_image(ciz, cj.z, L);
 #pragma unroll
                 for (int b = 0; b < S; ++b) {
                     const int tb = s_type[b];
@@ -352,18 +380,26 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                     if ((r2[b] < 0.5) && (qq[b] < 0)) l3 = 1.0;
                     else if (r2[b] < rc_qq2 + 100) use[b] = true;
                 }
-                if (P.deg > 0) {                            // erfc(κr)/r = 1/r − κ·E(κ²r²), S chains in lock-step
+                if (DEG != 0) {                             // erfc(κr)/r = 1/r − κ·E(κ²r²), S chains in lock-step
                     double sv[S], pv[S];
+                    const int deg = DEG > 0 ? DEG : P.deg;
 #pragma unroll
-                    for (int b = 0; b < S; ++b) { sv[b] = fma(r2[b] * P.kappa2, P.scale, -1.0); pv[b] = P.c[P.deg]; }
+                    for (int b = 0; b < S; ++b) { sv[b] = fma(r2[b] * P.kappa2, P.scale, -1.0); pv[b] = P.c[deg]; }
+                    if (DEG > 0) {
+#pragma unroll
+                        for (int k = DEG - 1; k >= 0; --k)
+#pragma unroll
+                            for (int b = 0; b < S; ++b) pv[b] = fma(pv[b], sv[b], P.c[k]);
+                    } else {
 #pragma unroll 1
-                    for (int k = P.deg - 1; k >= 0; --k) {
-                        const double ck = P.c[k];
+                        for (int k = deg - 1; k >= 0; --k) {
+                            const double ck = P.c[k];
 #pragma unroll
-                        for (int b = 0; b < S; ++b) pv[b] = fma(pv[b], sv[b], ck);
+                            for (int b = 0; b < S; ++b) pv[b] = fma(pv[b], sv[b], ck);
+                        }
                     }
 #pragma unroll
-                    for (int b = 0; b < S; ++b) if (use[b]) l2 = fma(qq[b], fma(-P.kappa, pv[b], rsqrt(r2[b])), l2);
+                    for (int b = 0; b < S; ++b) if (use[b]) l2 = fma(qq[b], fma(-P.kappa, pv[b], chain_rsqrt(r2[b])), l2);
                 } else {
 #pragma unroll
                     for (int b = 0; b < S; ++b) if (use[b]) { const double r = sqrt(r2[b]); l2 += qq[b] * erfc(Sy.kappa * r) / r; }
@@ -375,7 +411,7 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
         if (A.style_recip) {                                // ewalds.jl:804-821
             const double2 *Sold = s_rhok[cur];
             double2 *Snew = s_rhok[cur ^ 1];
-            for (int k = tid; k < NK; k += CHAIN_THREADS) {
+            for (int k = CHAIN_THREADS - 1 - tid; k < NK; k += CHAIN_THREADS) {   // from the far end: the low warps carry more pair items
                 const int4 kv = s_kvec[k];
                 const int aky = abs(kv.y), akz = abs(kv.z);
                 const bool ny = kv.y < 0, nz = kv.z < 0;
@@ -393,6 +429,7 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                 acc[8] += s_cfac[k] * ((nr * nr + ni * ni) - (so.x * so.x + so.y * so.y));
             }
         }
+        { const long long t = clock64(); pc[3] += t - tc0; tc0 = t; }
         // ================= step 3: ordered reduction, decision, state update
 #pragma unroll
         for (int v = 0; v < 9; ++v) {
@@ -400,6 +437,7 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
             if (lane == 0) s_red[v * CHAIN_WARPS + warp] = acc[v];
         }
         __syncthreads();                                    // B4
+        { const long long t = clock64(); pc[4] += t - tc0; tc0 = t; }
         if (warp == 0) {
             double tot[9];
 #pragma unroll
@@ -409,29 +447,41 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                 for (int o = CHAIN_WARPS / 2; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
                 tot[v] = x;
             }
+            // launch_move_on's folding (energy.jl:289 pot*4, vir*24/3; ewalds.jl:360; main.jl:580-590) + mmc_trial_move.
+            // Every lane holds the totals; the six divisions run in six lanes at once, lane 0 keeps the critical path
+            // delta → delta/T → exp.
+#pragma unroll
+            for (int v = 0; v < 9; ++v) tot[v] = __shfl_sync(0xffffffffu, tot[v], 0);
+            const bool ovl0 = tot[3] > 0.0, ovl1 = tot[7] > 0.0, overlap = ovl0 || ovl1;
+            const double lj_old = mul(tot[0], 4), lj_new = mul(tot[4], 4);
+            const double qq_old = mul(ovl0 ? 0.0 : tot[2], Sy.factor), qq_new = mul(ovl1 ? 0.0 : tot[6], Sy.factor);
+            const double d_recip = (overlap || !A.style_recip) ? 0.0 : mul(tot[8], Sy.factor);
+            double old_e = lj_old, new_e = lj_new;
+            if (A.style_qq) { old_e = add(old_e, qq_old); new_e = add(new_e, qq_new); }     // main.jl:501-505, 566-570
+            const double delta = add(sub(new_e, old_e), d_recip);                             // main.jl:593
+            double num = delta, den = A.temperature;                                          // lane 0: delta / T
+            if (lane == 1) { num = mul(tot[1], 24); den = 3.0; }                              // lj_vir_old
+            if (lane == 2) { num = mul(tot[5], 24); den = 3.0; }                              // lj_vir_new
+            if (lane == 3) { num = qq_old; den = 3.0; }                                       // ewalds.jl:907 virial = E/3
+            if (lane == 4) { num = qq_new; den = 3.0; }
+            if (lane == 5) { num = d_recip; den = 3.0; }
+            const double quo = __ddiv_rn(num, den);
+            const double ljv_old = __shfl_sync(0xffffffffu, quo, 1), ljv_new = __shfl_sync(0xffffffffu, quo, 2);
+            const double qqv_old = __shfl_sync(0xffffffffu, quo, 3), qqv_new = __shfl_sync(0xffffffffu, quo, 4);
+            const double recv = __shfl_sync(0xffffffffu, quo, 5);
             if (lane == 0) {
-                // launch_move_on's folding (energy.jl:289 pot*4, vir*24/3; ewalds.jl:360; main.jl:580-590) + mmc_trial_move
-                const bool ovl0 = tot[3] > 0.0, ovl1 = tot[7] > 0.0, overlap = ovl0 || ovl1;
-                const double lj_old = mul(tot[0], 4), ljv_old = __ddiv_rn(mul(tot[1], 24), 3.0);
-                const double lj_new = mul(tot[4], 4), ljv_new = __ddiv_rn(mul(tot[5], 24), 3.0);
-                const double qq_old = mul(ovl0 ? 0.0 : tot[2], Sy.factor), qq_new = mul(ovl1 ? 0.0 : tot[6], Sy.factor);
-                const double d_recip = (overlap || !A.style_recip) ? 0.0 : mul(tot[8], Sy.factor);
-                double old_e = lj_old, old_v = ljv_old, new_e = lj_new, new_v = ljv_new;
-                if (A.style_qq) {                           // main.jl:501-505, 566-570
-                    old_v = add(old_v, __ddiv_rn(qq_old, 3)); old_e = add(old_e, qq_old);
-                    new_v = add(new_v, __ddiv_rn(qq_new, 3)); new_e = add(new_e, qq_new);
-                }
-                const double delta = add(sub(new_e, old_e), d_recip);                 // main.jl:593
-                if (overlap) n_ovl += 1;
-                const double x = __ddiv_rn(delta, A.temperature);
+                double old_v = ljv_old, new_v = ljv_new;
+                if (A.style_qq) { old_v = add(old_v, qqv_old); new_v = add(new_v, qqv_new); }
+                const double x = quo;
+                if (overlap) D.n_ovl += 1;
                 bool okm = true;
                 if (!(x < 0.0)) okm = exp(-x) > next_u();                            // auxillary.jl:106-114
                 const bool accd = okm && !overlap;                                    // main.jl:598
                 if (accd) {
-                    tot_e = add(tot_e, delta);
-                    tot_v = add(tot_v, add(sub(new_v, old_v), __ddiv_rn(d_recip, 3)));
-                    n_acc += 1;
-                    if (is_trans) tr.naccept += 1; else ro.naccept += 1;
+                    D.tot_e = add(D.tot_e, delta);
+                    D.tot_v = add(D.tot_v, add(sub(new_v, old_v), recv));
+                    D.n_acc += 1;
+                    if (D.is_trans) D.tr.naccept += 1; else D.ro.naccept += 1;
                     s_com[i] = make_double4(s_tcom[0], s_tcom[1], s_tcom[2], 0.0);
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
@@ -440,38 +490,38 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                         s_site[i * S + s] = t;
                     }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) A.quat[4 * i + k] = ei[k];
-                    if (A.style_recip && !overlap) cur ^= 1;                          // main.jl:621 as an index flip
+                    for (int k = 0; k < 4; ++k) A.quat[4 * i + k] = D.ei[k];
+                    if (A.style_recip && !overlap) s_cur = cur ^ 1;                   // main.jl:621 as an index flip
                 }
                 if (A.accepted) A.accepted[m] = accd ? 1 : 0;
                 if (A.delta) A.delta[m] = delta;
-                if (dry) { ret = 1; s_stop = 1; }
+                if (dry) { D.ret = 1; s_stop = 1; }
                 else {
                     if (A.adjust && i == N - 1) {                                     // main.jl:645-651
-                        tr.d_max = dr_max; adjust_step(tr, L); dr_max = tr.d_max;
-                        ro.d_max = dphi_max; adjust_step(ro, L); dphi_max = ro.d_max;
+                        D.tr.d_max = D.dr_max; adjust_step(D.tr, L); D.dr_max = D.tr.d_max;
+                        D.ro.d_max = D.dphi_max; adjust_step(D.ro, L); D.dphi_max = D.ro.d_max;
                     }
-                    n_done = m + 1;
+                    D.n_done = m + 1;
                 }
             }
-            cur = __shfl_sync(0xffffffffu, cur, 0);
-            s_wcount[0] = cur;                               // everybody needs the Old/New index for the next move
         }
         __syncthreads();                                    // B5
-        cur = s_wcount[0];
+        { const long long t = clock64(); pc[5] += t - tc0; tc0 = t; }
+        cur = s_cur;
         if (s_stop) break;
     }
     __syncthreads();
-    // ---- the state goes back to HBM; ρ(k) Old of the final state into BOTH buffers' Old slot
+    // ---- the state goes back to HBM; ρ(k) of the final state into the buffer the handle will call "Old"
     for (int t = tid; t < N * S; t += CHAIN_THREADS) Sy.site[t] = s_site[t];
     for (int t = tid; t < N; t += CHAIN_THREADS) Sy.com[t] = s_com[t];
     for (int t = tid; t < NK; t += CHAIN_THREADS) Sy.rhok[cur][t] = s_rhok[cur][t];
     if (tid == 0) {
         ChainOut o;
-        o.n_moves = n_done; o.n_accepted = n_acc; o.n_overlap = n_ovl; o.uniforms_used = pos;
-        o.trans_attempt = tr.attempt; o.trans_accept = tr.naccept; o.rot_attempt = ro.attempt; o.rot_accept = ro.naccept;
-        o.dr_max = dr_max; o.dphi_max = dphi_max; o.total_energy = tot_e; o.total_virial = tot_v;
-        o.ret = ret; o.cur = cur;
+        o.n_moves = D.n_done; o.n_accepted = D.n_acc; o.n_overlap = D.n_ovl; o.uniforms_used = pos;
+        o.trans_attempt = D.tr.attempt; o.trans_accept = D.tr.naccept; o.rot_attempt = D.ro.attempt; o.rot_accept = D.ro.naccept;
+        o.dr_max = D.dr_max; o.dphi_max = D.dphi_max; o.total_energy = D.tot_e; o.total_virial = D.tot_v;
+        o.ret = D.ret; o.cur = cur;
+        for (int k = 0; k < 6; ++k) o.phase_cycles[k] = pc[k];
         *A.out = o;
     }
 }

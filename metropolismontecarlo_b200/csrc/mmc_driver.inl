@@ -214,16 +214,35 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     A.p_trans = p->p_trans; A.p_rot = p->p_rot; A.e0 = e0; A.v0 = v0;
     A.uniforms = d; A.quat = d + off_q; A.db = d + off_db; A.delta = d + off_delta;
     A.out = reinterpret_cast<ChainOut *>(d + off_out); A.accepted = d_acc;
-#define MMC_CHAIN_LAUNCH(SS)                                                                                         \
+#define MMC_CHAIN_LAUNCH(SS, DD)                                                                                     \
     {                                                                                                                \
-        CK(cudaFuncSetAttribute(k_chain<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
-        k_chain<SS><<<1, CHAIN_THREADS, smem, h->stream>>>(h->S, A, h->move_poly);                                   \
+        CK(cudaFuncSetAttribute(k_chain<SS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        k_chain<SS, DD><<<1, CHAIN_THREADS, smem, h->stream>>>(h->S, A, h->move_poly);                               \
     }
-    switch (h->US) {
-        case 1: MMC_CHAIN_LAUNCH(1) break;
-        case 2: MMC_CHAIN_LAUNCH(2) break;
-        case 3: MMC_CHAIN_LAUNCH(3) break;
-        default: MMC_CHAIN_LAUNCH(4) break;
+    const int deg = A.style_qq ? h->move_poly.deg : 0;
+    if (h->US == 3) {          // water-like: erf polynomial degree at compile time
+        switch (deg) {
+            case 0: MMC_CHAIN_LAUNCH(3, 0) break;
+            case 8: MMC_CHAIN_LAUNCH(3, 8) break;
+            case 12: MMC_CHAIN_LAUNCH(3, 12) break;
+            case 16: MMC_CHAIN_LAUNCH(3, 16) break;
+            case 20: MMC_CHAIN_LAUNCH(3, 20) break;
+            case 24: MMC_CHAIN_LAUNCH(3, 24) break;
+            case 32: MMC_CHAIN_LAUNCH(3, 32) break;
+            default: MMC_CHAIN_LAUNCH(3, -1) break;
+        }
+    } else if (deg == 0) {
+        switch (h->US) {
+            case 1: MMC_CHAIN_LAUNCH(1, 0) break;
+            case 2: MMC_CHAIN_LAUNCH(2, 0) break;
+            default: MMC_CHAIN_LAUNCH(4, 0) break;
+        }
+    } else {
+        switch (h->US) {
+            case 1: MMC_CHAIN_LAUNCH(1, -1) break;
+            case 2: MMC_CHAIN_LAUNCH(2, -1) break;
+            default: MMC_CHAIN_LAUNCH(4, -1) break;
+        }
     }
 #undef MMC_CHAIN_LAUNCH
     LAUNCH_CHECK();
@@ -238,6 +257,10 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     for (int m = 0; m < S.n_mol; ++m) { com[3 * m] = hc[m].x; com[3 * m + 1] = hc[m].y; com[3 * m + 2] = hc[m].z; }
     h->cur = o.cur;
     h->new_valid = false;
+    if (std::getenv("MMC_CHAIN_DEBUG") && o.n_moves > 0)
+        std::fprintf(stderr, "k_chain cycles/move: step0 %.0f  gate %.0f  compact %.0f  pairs %.0f  B4wait %.0f  decide %.0f\n",
+                     (double)o.phase_cycles[0] / o.n_moves, (double)o.phase_cycles[1] / o.n_moves, (double)o.phase_cycles[2] / o.n_moves,
+                     (double)o.phase_cycles[3] / o.n_moves, (double)o.phase_cycles[4] / o.n_moves, (double)o.phase_cycles[5] / o.n_moves);
     h->cnt.trial_moves += o.n_moves; h->cnt.commits += o.n_accepted; h->cnt.overlap_events += o.n_overlap;
     std::memset(st, 0, sizeof(*st));
     st->n_moves = o.n_moves; st->n_accepted = o.n_accepted; st->n_overlap = o.n_overlap; st->uniforms_used = o.uniforms_used;
