@@ -169,9 +169,21 @@ def moves_benchmarks(n_moves=10_000):
         t0 = time.perf_counter()
         ora.loop(s, ew, ms.db, ms.quat.copy(), prm, u, n_cpu, 0.0, 0.0)
         dtc = time.perf_counter() - t0
+        # the same block of moves in ONE launch (mmc_loop_run_device: state in shared memory)
+        eng.upload_system(ms, RC, RC)
+        p0 = eng.potential(style)
+        com, quat = ms.com.copy(), ms.quat.copy()
+        t0 = time.perf_counter()
+        rc_d, acc_d, delta_d, st_d = eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, sid, 1), com, quat, ms.db,
+                                                   u, n_moves, p0.energy, p0.virial, device=True)
+        dt_dev = time.perf_counter() - t0
+        assert np.array_equal(acc, acc_d), "device block of moves diverged from the per-move protocol"
         out[name] = {"moves_per_s": n_moves / dt, "us_per_move": 1e6 * dt / n_moves, "accepted": int(st.n_accepted),
                      "gpu_launches": int(launches), "cpu_port_moves_per_s_1core": n_cpu / dtc,
-                     "flop_per_move": 2.1e5 if sid == 0 else 1.75e5}
+                     "flop_per_move": 2.1e5 if sid == 0 else 1.75e5,
+                     "block_offload": {"moves_per_s": n_moves / dt_dev, "us_per_move": 1e6 * dt_dev / n_moves,
+                                       "gpu_launches": 1, "what": "mmc_loop_run_device: 10^4 moves in one launch, "
+                                       "uniforms H2D + results D2H inside the timed region, same accept/reject record"}}
         eng.close()
     at = systems.lj_lattice(32_000, 0.75, 2.5)
     eng = Engine()

@@ -117,4 +117,29 @@ end
 volume_accept!(e::Engine) = check(e, ccall((:mmc_volume_accept, LIB), Cint, (Ptr{Cvoid},), e.h))
 volume_reject!(e::Engine) = check(e, ccall((:mmc_volume_reject, LIB), Cint, (Ptr{Cvoid},), e.h))
 
+# Loop() for a whole block of moves in one launch (Ewald/main.jl:487-651); include/mmc_b200.h mmc_loop_run_device.
+# com::Vector{SVector{3,Float64}} (moa.COM), quat::Vector{SVector{4,Float64}}, db: body-fixed site vectors (n_sites x 3),
+# u: the stretch of the caller's uniform stream this block may consume (st.uniforms_used tells how much it did).
+struct LoopParams
+    temperature::Cdouble; dr_max::Cdouble; dphi_max::Cdouble
+    p_trans::Cdouble; p_rot::Cdouble
+    style::Cint; adjust::Cint
+end
+mutable struct LoopStats
+    n_moves::Int64; n_accepted::Int64; n_overlap::Int64; uniforms_used::Int64
+    trans_attempt::Int64; trans_accept::Int64; rot_attempt::Int64; rot_accept::Int64
+    dr_max::Cdouble; dphi_max::Cdouble; total_energy::Cdouble; total_virial::Cdouble
+    LoopStats() = new(0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0)
+end
+function loop_run_device!(e::Engine, p::LoopParams, com, quat, db, u::Vector{Float64}, n_moves::Int, e0, v0;
+                          accepted::Vector{UInt8} = Vector{UInt8}(undef, n_moves), delta::Vector{Float64} = Vector{Float64}(undef, n_moves))
+    st = LoopStats()
+    rc = ccall((:mmc_loop_run_device, LIB), Cint,
+               (Ptr{Cvoid}, Ref{LoopParams}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Cdouble, Cdouble,
+                Ptr{UInt8}, Ptr{Float64}, Ref{LoopStats}),
+               e.h, p, pointer(com), pointer(quat), pointer(db), pointer(u), length(u), n_moves, e0, v0, pointer(accepted), pointer(delta), st)
+    rc < 0 && check(e, rc)          # 1 = stream ran dry, 2 = quaternion-norm error (quaternions.jl:22-25), 3 = no move selected
+    st, accepted, delta, rc
+end
+
 end # module
