@@ -222,7 +222,7 @@ def run_ours(args, rank, world, local_rank):
     # One explicit (non-default) stream for everything: the engine's kernels, torch's NCCL
     # all-reduce and the timing events are all ordered on it.  (A NULL stream in mmc_config means
     # "the handle's own stream", so torch's legacy default stream cannot be shared.)
-    stream = torch.cuda.Stream(device=dev)
+    stream = torch.cuda.Stream(device=dev, priority=-1)   # high priority: the library's side stream (rho(k) rebuild) runs below it
     torch.cuda.set_stream(stream)
     eng = Engine(device=local_rank, rank=rank, world=world, stream=stream.cuda_stream)
     ms = systems.spce_lattice(args.molecules)

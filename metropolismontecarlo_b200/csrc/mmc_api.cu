@@ -35,6 +35,9 @@ struct mmc_handle {
     mmc_config cfg{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;         // the ρ(k) rebuild of a full evaluation runs here, beside binning + pair kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int overlap_rhok = 1;                // mmc_debug_set "overlap_rhok": 0 = everything on one stream
     std::string err;
 
     // ---- molecular system
@@ -382,8 +385,9 @@ struct EvalCtx {
     int rank, world;
 };
 
-int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, double box, double2 *out)
+int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, double box, double2 *out, cudaStream_t st = nullptr)
 {
+    if (!st) st = h->stream;
     const int n = s_end - s_begin;
     const int nkv = h->S.nkvecs;
     const bool v2 = h->n_kpairs <= 32 && h->S.nk <= 6 && h->use_rhok_v2;
@@ -396,29 +400,29 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
         CK(cudaMalloc(&h->d_rhok_partial, (size_t)nb * nkv * sizeof(double2)));
         h->rhok_grid_cap = nb;
     }
-    if (h->tm.on) cudaEventRecord(h->tm.ev[2], h->stream);
+    if (h->tm.on) cudaEventRecord(h->tm.ev[2], st);
     if (v2) {
         Rhok2Args R{site, s_begin, s_end, per, nkv, h->n_kpairs, h->d_kpairs, h->d_kindex, box, h->d_rhok_partial};
         switch (h->S.nk) {
-            case 1: k_rhok_pairs<1><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
-            case 2: k_rhok_pairs<2><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
-            case 3: k_rhok_pairs<3><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
-            case 4: k_rhok_pairs<4><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
-            case 5: k_rhok_pairs<5><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
-            default: k_rhok_pairs<6><<<nb, RHOK2_BLOCK, 0, h->stream>>>(R); break;
+            case 1: k_rhok_pairs<1><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
+            case 2: k_rhok_pairs<2><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
+            case 3: k_rhok_pairs<3><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
+            case 4: k_rhok_pairs<4><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
+            case 5: k_rhok_pairs<5><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
+            default: k_rhok_pairs<6><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
         }
     } else {
         RhokArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->S.kvec, box, h->d_rhok_partial};
         const int kpt = (nkv + RHOK_BLOCK - 1) / RHOK_BLOCK;
-        if (kpt <= 1) k_rhok_partial<1><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
-        else if (kpt <= 2) k_rhok_partial<2><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
-        else if (kpt <= 4) k_rhok_partial<4><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
-        else if (kpt <= 8) k_rhok_partial<8><<<nb, RHOK_BLOCK, 0, h->stream>>>(R);
+        if (kpt <= 1) k_rhok_partial<1><<<nb, RHOK_BLOCK, 0, st>>>(R);
+        else if (kpt <= 2) k_rhok_partial<2><<<nb, RHOK_BLOCK, 0, st>>>(R);
+        else if (kpt <= 4) k_rhok_partial<4><<<nb, RHOK_BLOCK, 0, st>>>(R);
+        else if (kpt <= 8) k_rhok_partial<8><<<nb, RHOK_BLOCK, 0, st>>>(R);
         else FAIL(MMC_EINVAL, "too many k-vectors for the rebuild kernel (nk too large)");
     }
     LAUNCH_CHECK();
-    if (h->tm.on) cudaEventRecord(h->tm.ev[3], h->stream);
-    k_rhok_reduce<<<(nkv + 63) / 64, dim3(64, 4), 0, h->stream>>>(h->d_rhok_partial, nb, nkv, out);
+    if (h->tm.on) cudaEventRecord(h->tm.ev[3], st);
+    k_rhok_reduce<<<(nkv + 63) / 64, dim3(64, 4), 0, st>>>(h->d_rhok_partial, nb, nkv, out);
     LAUNCH_CHECK();
     return MMC_OK;
 }
@@ -551,6 +555,20 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     const bool cells = ncd >= 3;
     CK(cudaMemsetAsync(d_vec, 0, (MMC_NSCAL + 2 * (size_t)std::max(S.nkvecs, 1)) * sizeof(double), h->stream));
     if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
+    // The ρ(k) rebuild (RecipLong) depends on nothing the pair path produces when the box is unchanged (f == 1): it
+    // reads the resident sites in their own order and runs on the side stream while binning, gather and the pair
+    // kernel run here.  For a volume trial it needs the scaled sites and forks after the gather instead.
+    const long long ns_all = S.n_sites;
+    const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
+    bool rhok_forked = false;
+    if (style == MMC_STYLE_EWALD && h->overlap_rhok && E.f == 1.0) {
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        int rcr = rhok_launch(h, S.site, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL), h->side);
+        if (rcr) return rcr;
+        CK(cudaEventRecord(h->ev_join, h->side));
+        rhok_forked = true;
+    }
     const int tb = 256, gm = (S.n_mol + tb - 1) / tb;
     long long n_units;
     if (cells) {
@@ -596,6 +614,14 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
                  want_rows ? h->d_mrows : nullptr, want_rows ? h->d_gf : nullptr, h->d_cell_of, ncd, E.box / ncd};
     k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
+    if (style == MMC_STYLE_EWALD && h->overlap_rhok && !rhok_forked) {      // volume trial: scaled, sorted sites
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        int rcr = rhok_launch(h, h->d_ssite, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL), h->side);
+        if (rcr) return rcr;
+        CK(cudaEventRecord(h->ev_join, h->side));
+        rhok_forked = true;
+    }
 
     PairArgs P{};
     P.com = h->d_scom; P.site = h->d_ssite; P.cell_start = h->d_start;
@@ -709,10 +735,11 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     h->last_ncd = ncd;
 
     if (style == MMC_STYLE_EWALD) {
-        const long long ns = S.n_sites;
-        const int s0 = (int)(ns * E.rank / E.world), s1 = (int)(ns * (E.rank + 1) / E.world);
-        int rc = rhok_launch(h, h->d_ssite, s0, s1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL));
-        if (rc) return rc;
+        if (rhok_forked) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        else {
+            int rc = rhok_launch(h, h->d_ssite, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL));
+            if (rc) return rc;
+        }
     }
     return MMC_OK;
 }
@@ -913,7 +940,9 @@ int mmc_create(const mmc_config *cfg, mmc_handle **out)
     };
     if (cfg->stream) h->stream = (cudaStream_t)cfg->stream;
     else {
-        if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+        int prio_lo = 0, prio_hi = 0;                       // main stream at the highest priority, side stream at the lowest:
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // the ρ(k) rebuild fills what binning/gather/pairs leave free
+        if ((e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("stream", e);
         h->own_stream = true;
     }
     cudaDeviceProp prop;
@@ -925,6 +954,13 @@ int mmc_create(const mmc_config *cfg, mmc_handle **out)
     if ((e = cudaHostGetDevicePointer((void **)&h->W.slots, h->h_slots, 0)) != cudaSuccess) return fail("mapped ptr", e);
     for (auto &ev : h->tm.ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("event", e);
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if ((e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("side stream", e);
+    }
+    if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     cudaFuncSetAttribute(k_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_pairs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     pairs_fast_set_attributes();
@@ -941,6 +977,9 @@ int mmc_destroy(mmc_handle *h)
     if (h->h_slots) cudaFreeHost(h->h_slots);
     if (h->h_up) cudaFreeHost(h->h_up);
     for (auto &ev : h->tm.ev) cudaEventDestroy(ev);
+    if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return MMC_OK;
@@ -1580,6 +1619,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
 {
     if (!h || !key) return MMC_EINVAL;
     const std::string k(key);
+    if (k == "overlap_rhok") { h->overlap_rhok = value != 0; return MMC_OK; }
     if (k == "v6_ctas_per_sm") { if (value < 1 || value > 5) FAIL(MMC_EINVAL, "v6_ctas_per_sm must be 1..5"); h->v6_ctas_per_sm = (int)value; return MMC_OK; }
     if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v6 .. 5 general)
         if (value < 0 || value > 5) FAIL(MMC_EINVAL, "pair_level must be 0..5");
