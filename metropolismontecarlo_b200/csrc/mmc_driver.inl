@@ -191,8 +191,10 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (smem + 8 * 1024 > (size_t)max_optin) FAIL(MMC_EINVAL, "device loop: the system does not fit one SM's shared memory; use mmc_loop_run");
     if ((rc = flush_pending(h))) return rc;
-    // one device block: [uniforms | quat | db | delta | out | accepted]
-    const size_t n_q = 4 * (size_t)S.n_mol, n_db = 3 * (size_t)S.n_sites;
+    // thread-block cluster version: C CTAs on C SMs share the partner molecules and the k-vectors
+    const int C = (h->chain_cluster > 1 && S.n_mol >= 64) ? std::min(h->chain_cluster, CHAINC_MAXC) : 1;
+    // one device block: [uniforms | quat (C replicas) | db | delta | out | accepted]
+    const size_t n_q1 = 4 * (size_t)S.n_mol, n_q = n_q1 * C, n_db = 3 * (size_t)S.n_sites;
     const size_t off_q = (size_t)n_uniforms, off_db = off_q + n_q, off_delta = off_db + n_db, off_out = off_delta + (size_t)n_moves;
     const size_t out_doubles = (sizeof(ChainOut) + 7) / 8;
     const size_t bytes = (off_out + out_doubles) * sizeof(double) + (size_t)n_moves + 16;
@@ -204,7 +206,8 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     double *d = reinterpret_cast<double *>(h->d_chain);
     unsigned char *d_acc = reinterpret_cast<unsigned char *>(d + off_out + out_doubles);
     CK(cudaMemcpyAsync(d, uniforms, sizeof(double) * (size_t)n_uniforms, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d + off_q, quat, sizeof(double) * n_q, cudaMemcpyHostToDevice, h->stream));
+    for (int r = 0; r < C; ++r)
+        CK(cudaMemcpyAsync(d + off_q + r * n_q1, quat, sizeof(double) * n_q1, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d + off_db, db, sizeof(double) * n_db, cudaMemcpyHostToDevice, h->stream));
     ChainArgs A{};
     A.n_moves = n_moves; A.n_uniforms = n_uniforms;
@@ -215,7 +218,16 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     A.uniforms = d; A.quat = d + off_q; A.db = d + off_db; A.delta = d + off_delta;
     A.out = reinterpret_cast<ChainOut *>(d + off_out); A.accepted = d_acc;
 #define MMC_CHAIN_LAUNCH(SS, DD)                                                                                     \
-    {                                                                                                                \
+    if (C > 1) {                                                                                                     \
+        CK(cudaFuncSetAttribute(k_chainc<SS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        cudaLaunchConfig_t lc{};                                                                                     \
+        lc.gridDim = dim3(C); lc.blockDim = dim3(CHAINC_THREADS); lc.dynamicSmemBytes = smem; lc.stream = h->stream; \
+        cudaLaunchAttribute at[1];                                                                                   \
+        at[0].id = cudaLaunchAttributeClusterDimension;                                                              \
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                          \
+        lc.attrs = at; lc.numAttrs = 1;                                                                              \
+        CK(cudaLaunchKernelEx(&lc, k_chainc<SS, DD>, h->S, A, h->move_poly));                                        \
+    } else {                                                                                                         \
         CK(cudaFuncSetAttribute(k_chain<SS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         k_chain<SS, DD><<<1, CHAIN_THREADS, smem, h->stream>>>(h->S, A, h->move_poly);                               \
     }
@@ -250,7 +262,7 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     std::vector<double4> hc(S.n_mol);
     CK(cudaMemcpyAsync(&o, A.out, sizeof(o), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(hc.data(), S.com, sizeof(double4) * S.n_mol, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(quat, A.quat, sizeof(double) * n_q, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(quat, A.quat, sizeof(double) * n_q1, cudaMemcpyDeviceToHost, h->stream));
     if (accepted && n_moves) CK(cudaMemcpyAsync(accepted, d_acc, (size_t)n_moves, cudaMemcpyDeviceToHost, h->stream));
     if (delta_out && n_moves) CK(cudaMemcpyAsync(delta_out, A.delta, sizeof(double) * (size_t)n_moves, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

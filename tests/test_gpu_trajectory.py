@@ -107,8 +107,8 @@ def test_monatomic_lj_trajectory():
     eng.close()
 
 
-@pytest.mark.parametrize("style,sid", [("ewald", 0), ("wolf", 1)])
-def test_device_loop_matches_oracle_and_host_driver(style, sid):
+@pytest.mark.parametrize("style,sid,cluster", [("ewald", 0, 8), ("wolf", 1, 8), ("ewald", 0, 1), ("wolf", 1, 4)])
+def test_device_loop_matches_oracle_and_host_driver(style, sid, cluster):
     """mmc_loop_run_device: the whole block of 10^4 moves in one launch (state in shared memory).
     Same accept/reject record, uniform consumption and step-size adaptation as the oracle's Loop();
     deltas to rounding; the state it leaves in the library equals the host-driven run's."""
@@ -123,6 +123,7 @@ def test_device_loop_matches_oracle_and_host_driver(style, sid):
     quat_o = ms.quat.copy()
     rc_o, acc_o, del_o, st_o = ora.loop(s, ew, ms.db, quat_o, prm, u, N_MOVES, p0.energy, p0.virial)
     eng = water_engine(ms, rc)
+    eng.debug_set("chain_cluster", cluster)         # 1: one CTA (k_chain); > 1: thread-block cluster (k_chainc)
     g0 = eng.potential(style)
     com, quat = ms.com.copy(), ms.quat.copy()
     rc_g, acc_g, del_g, st_g = eng.loop_run(LoopParams(T, 0.316555789, 0.05, 0.5, 1.0, sid, 1), com, quat, ms.db,
