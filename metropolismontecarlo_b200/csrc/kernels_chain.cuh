@@ -43,7 +43,7 @@ struct ChainArgs {
     long long n_moves, n_uniforms;
     int style_qq, style_recip;   // Coulomb on (EWALD/WOLF); ρ(k) on (EWALD)
     int adjust, cur;
-    double temperature, dr_max, dphi_max, p_trans, p_rot, e0, v0;
+    double temperature, inv_temperature, dr_max, dphi_max, p_trans, p_rot, e0, v0;
     const double *uniforms;      // [n_uniforms]
     double *quat;                // [N][4]
     const double *db;            // [n_sites][3] body-fixed site vectors
@@ -351,13 +351,14 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
             double4 sa = s_site[i * S + a];
             double cix = co.x, ciy = co.y, ciz = co.z;
             if (cfg) { sa.x = s_tsite[a][0]; sa.y = s_tsite[a][1]; sa.z = s_tsite[a][2]; cix = cnx; ciy = cny; ciz = cnz; }
-            double r2[S], dx[S], dy[S], dz[S], qq[S];
+            double r2[S], dx[S], dy[S], dz[S], qq[S], ri[S];
 #pragma unroll
             for (int b = 0; b < S; ++b) {
                 const double4 sb = s_site[j * S + b];
                 dx[b] = min_image(sa.x, sb.x, L); dy[b] = min_image(sa.y, sb.y, L); dz[b] = min_image(sa.z, sb.z, L);
                 r2[b] = dx[b] * dx[b] + dy[b] * dy[b] + dz[b] * dz[b];
                 qq[b] = sa.w * sb.w;
+                ri[b] = chain_rsqrt(r2[b]);
             }
             double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
             if (fl & 1) {                                   // energy.jl:270-282
@@ -368,8 +369,13 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                 for (int b = 0; b < S; ++b) {
                     const int tb = s_type[b];
                     const double eps = Sy.eps[ta + tb * nt];
-                    if (r2[b] < (rc_lj2 + 100) && eps > 0.001)
-                        lj_pair(eps, Sy.sig[ta + tb * nt], r2[b], dx[b], dy[b], dz[b], rijx, rijy, rijz, l0, l1);
+                    if (r2[b] < (rc_lj2 + 100) && eps > 0.001) {          // σ²/r² formed as σ²·(1/√r²)²: no division on the critical path
+                        const double sig = Sy.sig[ta + tb * nt];
+                        const double s2 = sig * sig * (ri[b] * ri[b]), s6 = s2 * s2 * s2, s12 = s6 * s6;
+                        l0 += eps * (s12 - s6);
+                        const double virab = eps * (2.0 * s12 - s6) * s2;
+                        l1 += rijx * (dx[b] * virab) + rijy * (dy[b] * virab) + rijz * (dz[b] * virab);
+                    }
                 }
             }
             if (fl & 2) {                                   // ewalds.jl:359-367
@@ -399,7 +405,7 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                         }
                     }
 #pragma unroll
-                    for (int b = 0; b < S; ++b) if (use[b]) l2 = fma(qq[b], fma(-P.kappa, pv[b], chain_rsqrt(r2[b])), l2);
+                    for (int b = 0; b < S; ++b) if (use[b]) l2 = fma(qq[b], fma(-P.kappa, pv[b], ri[b]), l2);
                 } else {
 #pragma unroll
                     for (int b = 0; b < S; ++b) if (use[b]) { const double r = sqrt(r2[b]); l2 += qq[b] * erfc(Sy.kappa * r) / r; }
@@ -527,6 +533,7 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
 }
 
 #include <cooperative_groups.h>
+#include <cstdio>
 #define CHAINC_THREADS 256
 #define CHAINC_WARPS (CHAINC_THREADS / 32)
 #define CHAINC_MAXC 8
@@ -565,7 +572,7 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
     __shared__ double s_tcom[3], s_tsite[S][3];
     __shared__ int s_stop, s_cur;
     __shared__ ChainDriver D;
-    __shared__ double s_xchg[2][CHAINC_MAXC][9];              // [move parity][source rank][value], written remotely
+    __shared__ double s_xchg[2][9][CHAINC_MAXC];              // [move parity][value][source rank], written remotely; unused ranks stay 0
     __shared__ double s_tot[9];
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -589,6 +596,7 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
         s_kvec[t] = Sy.kvec[t]; s_cfac[t] = Sy.cfac[t];
     }
     if (tid < S) s_type[tid] = Sy.atype[tid];
+    for (int k = tid; k < 2 * 9 * CHAINC_MAXC; k += CHAINC_THREADS) (&s_xchg[0][0][0])[k] = 0.0;
     if (tid == 0) {
         s_stop = 0; s_cur = A.cur;
         D.n_acc = 0; D.n_ovl = 0; D.n_done = 0;
@@ -618,6 +626,7 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
     };
 
     long long pc[6] = {0, 0, 0, 0, 0, 0};
+    long long pd[6] = {0, 0, 0, 0, 0, 0};
     int cur = A.cur;
     for (long long m = 0; m < A.n_moves; ++m) {
         const int i = (int)(m % N);                         // sweep order i = 1..N (main.jl:490)
@@ -637,6 +646,7 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
             }
             __syncwarp();
             if (lane == 0) {
+                const long long tg0 = clock64();
                 const double dr_max = D.dr_max, dphi_max = D.dphi_max;
                 const double nq0 = D.nq[0], nq1 = D.nq[1], nq2 = D.nq[2], nq3 = D.nq[3];
                 const double4 c0 = s_com[i];
@@ -697,6 +707,7 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                 }
                 s_tcom[0] = rnew[0]; s_tcom[1] = rnew[1]; s_tcom[2] = rnew[2];
                 if (ret) { D.ret = ret; s_stop = ret; }
+                if (D.is_trans) { pd[0] += clock64() - tg0; pd[1] += 1; } else pd[2] += clock64() - tg0;
             }
             __syncwarp();
             {   // requests for the NEXT move, consumed at the top of its step 0: uniforms, quaternion, body frame
@@ -777,13 +788,14 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
             double4 sa = s_site[i * S + a];
             double cix = co.x, ciy = co.y, ciz = co.z;
             if (cfg) { sa.x = s_tsite[a][0]; sa.y = s_tsite[a][1]; sa.z = s_tsite[a][2]; cix = cnx; ciy = cny; ciz = cnz; }
-            double r2[S], dx[S], dy[S], dz[S], qq[S];
+            double r2[S], dx[S], dy[S], dz[S], qq[S], ri[S];
 #pragma unroll
             for (int b = 0; b < S; ++b) {
                 const double4 sb = s_site[j * S + b];
                 dx[b] = min_image(sa.x, sb.x, L); dy[b] = min_image(sa.y, sb.y, L); dz[b] = min_image(sa.z, sb.z, L);
                 r2[b] = dx[b] * dx[b] + dy[b] * dy[b] + dz[b] * dz[b];
                 qq[b] = sa.w * sb.w;
+                ri[b] = chain_rsqrt(r2[b]);
             }
             double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
             if (fl & 1) {                                   // energy.jl:270-282
@@ -794,8 +806,13 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                 for (int b = 0; b < S; ++b) {
                     const int tb = s_type[b];
                     const double eps = Sy.eps[ta + tb * nt];
-                    if (r2[b] < (rc_lj2 + 100) && eps > 0.001)
-                        lj_pair(eps, Sy.sig[ta + tb * nt], r2[b], dx[b], dy[b], dz[b], rijx, rijy, rijz, l0, l1);
+                    if (r2[b] < (rc_lj2 + 100) && eps > 0.001) {          // σ²/r² formed as σ²·(1/√r²)²: no division on the critical path
+                        const double sig = Sy.sig[ta + tb * nt];
+                        const double s2 = sig * sig * (ri[b] * ri[b]), s6 = s2 * s2 * s2, s12 = s6 * s6;
+                        l0 += eps * (s12 - s6);
+                        const double virab = eps * (2.0 * s12 - s6) * s2;
+                        l1 += rijx * (dx[b] * virab) + rijy * (dy[b] * virab) + rijz * (dz[b] * virab);
+                    }
                 }
             }
             if (fl & 2) {                                   // ewalds.jl:359-367
@@ -825,7 +842,7 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                         }
                     }
 #pragma unroll
-                    for (int b = 0; b < S; ++b) if (use[b]) l2 = fma(qq[b], fma(-P.kappa, pv[b], chain_rsqrt(r2[b])), l2);
+                    for (int b = 0; b < S; ++b) if (use[b]) l2 = fma(qq[b], fma(-P.kappa, pv[b], ri[b]), l2);
                 } else {
 #pragma unroll
                     for (int b = 0; b < S; ++b) if (use[b]) { const double r = sqrt(r2[b]); l2 += qq[b] * erfc(Sy.kappa * r) / r; }
@@ -864,25 +881,41 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
         }
         __syncthreads();                                    // B4
         { const long long t = clock64(); pc[4] += t - tc0; tc0 = t; }
+        long long td0 = clock64();
         if (warp == 0) {
             double tot[9];
-            {   // this CTA's partial sums, folded in warp order, into slot `rank` of every CTA's exchange buffer
-                double mine = 0.0;
-                if (lane < 9) for (int w = 0; w < CHAINC_WARPS; ++w) mine += s_red[lane * CHAINC_WARPS + w];
-                const int par = (int)(m & 1);
-                for (int d = 0; d < C; ++d) {
-                    double *dst = cluster.map_shared_rank(&s_xchg[par][rank][0], d);
-                    if (lane < 9) dst[lane] = mine;
+            {   // this CTA's partial sums (s_red[v][warp], 8 warps) folded by a fixed shuffle tree over groups of 8 lanes,
+                // then into slot `rank` of every CTA's exchange buffer
+                double x0 = s_red[lane], x1 = s_red[lane + 32], x2 = lane < 8 ? s_red[lane + 64] : 0.0;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o); x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+                }
+                const int par = (int)(m & 1), v0 = lane >> 3;
+                if ((lane & 7) == 0) {
+                    for (int d = 0; d < C; ++d) {
+                        double *dst = cluster.map_shared_rank(&s_xchg[par][0][0], d);
+                        dst[v0 * CHAINC_MAXC + rank] = x0;
+                        dst[(4 + v0) * CHAINC_MAXC + rank] = x1;
+                        if (lane == 0) dst[8 * CHAINC_MAXC + rank] = x2;
+                    }
                 }
             }
         }
+        { const long long tt = clock64(); pd[3] += tt - td0; td0 = tt; }
         cluster.sync();                                     // every CTA's nine sums are in every CTA's buffer
+        { const long long tt = clock64(); pd[4] += tt - td0; td0 = tt; }
         if (warp == 0) {
             double tot[9];
-            {
+            {   // add the C slots of every value with the same fixed tree in every CTA: bit-identical totals everywhere
                 const int par = (int)(m & 1);
-                double t = 0.0;
-                if (lane < 9) { for (int r = 0; r < C; ++r) t += s_xchg[par][r][lane]; s_tot[lane] = t; }
+                const double *xb = &s_xchg[par][0][0];
+                double x0 = xb[lane], x1 = xb[lane + 32], x2 = lane < 8 ? xb[lane + 64] : 0.0;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o); x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+                }
+                if ((lane & 7) == 0) { s_tot[lane >> 3] = x0; s_tot[4 + (lane >> 3)] = x1; if (lane == 0) s_tot[8] = x2; }
                 __syncwarp();
 #pragma unroll
                 for (int v = 0; v < 9; ++v) tot[v] = s_tot[v];
@@ -898,13 +931,16 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
             double old_e = lj_old, new_e = lj_new;
             if (A.style_qq) { old_e = add(old_e, qq_old); new_e = add(new_e, qq_new); }     // main.jl:501-505, 566-570
             const double delta = add(sub(new_e, old_e), d_recip);                             // main.jl:593
-            double num = delta, den = A.temperature;                                          // lane 0: delta / T
-            if (lane == 1) { num = mul(tot[1], 24); den = 3.0; }                              // lj_vir_old
-            if (lane == 2) { num = mul(tot[5], 24); den = 3.0; }                              // lj_vir_new
-            if (lane == 3) { num = qq_old; den = 3.0; }                                       // ewalds.jl:907 virial = E/3
-            if (lane == 4) { num = qq_new; den = 3.0; }
-            if (lane == 5) { num = d_recip; den = 3.0; }
-            const double quo = __ddiv_rn(num, den);
+            double num = delta, den = A.temperature, rden = A.inv_temperature;                // lane 0: delta / T
+            if (lane == 1) { num = mul(tot[1], 24); den = 3.0; rden = 1.0 / 3.0; }            // lj_vir_old
+            if (lane == 2) { num = mul(tot[5], 24); den = 3.0; rden = 1.0 / 3.0; }            // lj_vir_new
+            if (lane == 3) { num = qq_old; den = 3.0; rden = 1.0 / 3.0; }                     // ewalds.jl:907 virial = E/3
+            if (lane == 4) { num = qq_new; den = 3.0; rden = 1.0 / 3.0; }
+            if (lane == 5) { num = d_recip; den = 3.0; rden = 1.0 / 3.0; }
+            // num / den by the correctly rounded reciprocal and one exact-remainder correction (Markstein): the
+            // rounded quotient without the ~15-deep generic division sequence on the decision's critical path
+            const double q0 = mul(num, rden);
+            const double quo = fma(fma(-q0, den, num), rden, q0);
             const double ljv_old = __shfl_sync(0xffffffffu, quo, 1), ljv_new = __shfl_sync(0xffffffffu, quo, 2);
             const double qqv_old = __shfl_sync(0xffffffffu, quo, 3), qqv_new = __shfl_sync(0xffffffffu, quo, 4);
             const double recv = __shfl_sync(0xffffffffu, quo, 5);
@@ -944,6 +980,7 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                 }
             }
         }
+        pd[5] += clock64() - td0;
         __syncthreads();                                    // B5
         { const long long t = clock64(); pc[5] += t - tc0; tc0 = t; }
         cur = s_cur;
@@ -964,6 +1001,9 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
         o.dr_max = D.dr_max; o.dphi_max = D.dphi_max; o.total_energy = D.tot_e; o.total_virial = D.tot_v;
         o.ret = D.ret; o.cur = cur;
         for (int k = 0; k < 6; ++k) o.phase_cycles[k] = pc[k];
+        if (rank == 0) printf("k_chainc detail (cycles): translation %.0f  rotation %.0f  fold+store %.0f  cluster.sync %.0f  sum+decide %.0f per move\n",
+                              (double)pd[0] / (double)(pd[1] > 0 ? pd[1] : 1), (double)pd[2] / (double)(D.n_done - pd[1] > 0 ? D.n_done - pd[1] : 1),
+                              (double)pd[3] / (double)D.n_done, (double)pd[4] / (double)D.n_done, (double)pd[5] / (double)D.n_done);
         *A.out = o;
     }
 }

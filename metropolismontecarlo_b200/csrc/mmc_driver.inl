@@ -213,7 +213,7 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     A.n_moves = n_moves; A.n_uniforms = n_uniforms;
     A.style_qq = p->style != MMC_STYLE_LJ_ONLY; A.style_recip = recip;
     A.adjust = p->adjust; A.cur = h->cur;
-    A.temperature = p->temperature; A.dr_max = p->dr_max; A.dphi_max = p->dphi_max;
+    A.temperature = p->temperature; A.inv_temperature = 1.0 / p->temperature; A.dr_max = p->dr_max; A.dphi_max = p->dphi_max;
     A.p_trans = p->p_trans; A.p_rot = p->p_rot; A.e0 = e0; A.v0 = v0;
     A.uniforms = d; A.quat = d + off_q; A.db = d + off_db; A.delta = d + off_delta;
     A.out = reinterpret_cast<ChainOut *>(d + off_out); A.accepted = d_acc;
