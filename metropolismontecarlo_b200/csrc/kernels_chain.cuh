@@ -539,20 +539,44 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
 #define CHAINC_MAXC 8
 
 // ---------------------------------------------------------------------------------------------------------
-// k_chainc — the same block of moves on a thread-block CLUSTER (one CTA per SM, distributed shared memory).
+// k_chains — the same block of moves on a thread-block CLUSTER (one CTA per SM, distributed shared memory).
 // Every CTA keeps a full replica of the state and runs the (cheap, deterministic) driver redundantly: same
 // uniforms, same trial move, same decision, same state update — so nothing but nine partial sums per move ever
 // crosses between SMs.  What is split is the work that made the single-CTA kernel slow: CTA r gates and evaluates
 // only the partner molecules j in its slice [r·N/C, (r+1)·N/C) and owns the slice [r·NK/C, (r+1)·NK/C) of ρ(k).
 // Per move: the CTA's ordered partial sums go into slot r of every CTA's exchange buffer (st.shared::cluster),
-// one cluster barrier (barrier.cluster arrive.release / wait.acquire), then every CTA adds the C slots in rank
-// order — bit-identical totals everywhere — and decides.  The exchange buffer is double-buffered by move parity,
-// so one cluster barrier per move is enough.  Rank 0 alone writes the accept/reject record and the quaternions.
+// one cluster barrier (barrier.cluster arrive.release / wait.acquire), then every CTA adds the C slots by the same
+// fixed tree — bit-identical totals everywhere — and decides.  The exchange buffer is double-buffered by move
+// parity, so one cluster barrier per move is enough.  Rank 0 alone writes the accept/reject record.
+//
+// The trial move is off the critical path.  Per-phase counters of the first cluster version: drawing the move
+// (lane 0: 930 cycles for a translation, 2400 for a quaternion rotation, plus the e^{ik·r} tables) was the
+// largest serial piece of a move.  The trial move of move
+// m+1 depends on nothing move m decides except (a) whether Metropolis(m) consumed a uniform — the stream position
+// is P or P+1 — and (b) the step sizes, which only change at the end of a sweep.  So two generator warps (6, 7)
+// build BOTH candidates for move m+1 (stream position P and P+1, trial coordinates and tables) while the six
+// worker warps evaluate move m; the decision of move m selects one.  At a sweep end with step-size adaptation,
+// and for move 0, the move is drawn after the decision instead (one candidate, exact position).  Everything a
+// candidate needs comes from data move m cannot change (molecule i+1's COM, sites, quaternion, body frame).
+// Cluster barrier: generators arrive as soon as the move starts (they publish nothing) and wait at its end.
+#define CHAINS_WORKERS 192
+#define CHAINS_WWARPS (CHAINS_WORKERS / 32)
+
+template <int S>
+struct ChainCand {
+    double com[3], site[S][3], ei[4];
+    long long pos_end;
+    int is_trans, ret, dry, pad;
+};
+
+__device__ __forceinline__ void chain_worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CHAINS_WORKERS) : "memory"); }
+
 template <int S, int DEG>
 __global__ void __launch_bounds__(CHAINC_THREADS, 1)
-k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs A, const __grid_constant__ ErfPoly P)
+k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs A, const __grid_constant__ ErfPoly P)
 {
     using namespace chain;
+    namespace cg = cooperative_groups;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = Sy.n_mol, NK = A.style_recip ? Sy.nkvecs : 0;
     double4 *s_site = reinterpret_cast<double4 *>(smem_raw);
@@ -564,31 +588,34 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
     double *s_cfac = reinterpret_cast<double *>(s_kvec + NK);
     int2 *s_list = reinterpret_cast<int2 *>(s_cfac + NK);
 
-    __shared__ cplx s_tab[2][S][3][MMC_MAX_NK + 1];
+    __shared__ ChainCand<S> s_cand[2][2];                              // [move parity][candidate]
+    __shared__ cplx s_tabc[2][2][2][S][3][MMC_MAX_NK + 1];             // [move parity][candidate][old/new][site][xyz][power]
+    __shared__ double s_ug[2][32], s_gq[2][4], s_gdb[2][S * 3];        // per generator: uniform window, quaternion, body frame
     __shared__ int s_type[S];
-    __shared__ int s_wcount[CHAIN_MAXIT * CHAINC_WARPS];
-    __shared__ double s_red[9 * CHAINC_WARPS];
-    __shared__ double s_u[CHAIN_RING];
-    __shared__ double s_tcom[3], s_tsite[S][3];
-    __shared__ int s_stop, s_cur;
-    __shared__ ChainDriver D;
-    __shared__ double s_xchg[2][9][CHAINC_MAXC];              // [move parity][value][source rank], written remotely; unused ranks stay 0
+    __shared__ int s_wcount[2 * CHAINS_WWARPS];
+    __shared__ double s_red[9 * 8];
+    __shared__ double s_xchg[2][9][CHAINC_MAXC];                       // [move parity][value][source rank], written remotely
     __shared__ double s_tot[9];
-    namespace cg = cooperative_groups;
+    __shared__ int s_stop, s_cur, s_sel;
+    __shared__ ChainDriver D;
+    __shared__ long long s_pos;                                        // stream position after the last decision
+
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    double *myquat = A.quat + (size_t)rank * 4 * Sy.n_mol;   // A.quat holds C replicas of the quaternion array
+    double *myquat = A.quat + (size_t)rank * 4 * Sy.n_mol;             // this CTA's replica of the quaternion array
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool worker = warp < CHAINS_WWARPS;
+    const int gen = warp - CHAINS_WWARPS;                              // 0, 1 for the generator warps
     const unsigned lt = (1u << lane) - 1u;
     const double L = Sy.box;
     const double rc_lj2 = Sy.rc_lj * Sy.rc_lj, rc_qq2 = Sy.rc_qq * Sy.rc_qq;
     const int nt = Sy.n_types, nk = Sy.nk;
-    const int j_lo = (int)((long long)N * rank / C), j_hi = (int)((long long)N * (rank + 1) / C);      // this CTA's partners
-    const int k_lo = (int)((long long)NK * rank / C), k_hi = (int)((long long)NK * (rank + 1) / C);    // this CTA's k-vectors
+    const int j_lo = (int)((long long)N * rank / C), j_hi = (int)((long long)N * (rank + 1) / C);
+    const int k_lo = (int)((long long)NK * rank / C), k_hi = (int)((long long)NK * (rank + 1) / C);
+    const int n_loc = j_hi - j_lo;
     const double twopi = 2.0 * 3.141592653589793;
 
-    // ---- the resident state comes on chip once
     for (int t = tid; t < N * S; t += CHAINC_THREADS) s_site[t] = Sy.site[t];
     for (int t = tid; t < N; t += CHAINC_THREADS) s_com[t] = Sy.com[t];
     for (int t = tid; t < NK; t += CHAINC_THREADS) {
@@ -597,397 +624,393 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
     }
     if (tid < S) s_type[tid] = Sy.atype[tid];
     for (int k = tid; k < 2 * 9 * CHAINC_MAXC; k += CHAINC_THREADS) (&s_xchg[0][0][0])[k] = 0.0;
+    if (tid < 9 * 8) s_red[tid] = 0.0;
     if (tid == 0) {
-        s_stop = 0; s_cur = A.cur;
+        s_stop = 0; s_cur = A.cur; s_sel = 0; s_pos = 0;
         D.n_acc = 0; D.n_ovl = 0; D.n_done = 0;
         D.tr = MoveStat{0, 0, 0, 0, 0.5, A.dr_max}; D.ro = MoveStat{0, 0, 0, 0, 0.5, A.dphi_max};
         D.dr_max = A.dr_max; D.dphi_max = A.dphi_max; D.tot_e = A.e0; D.tot_v = A.v0;
         D.ret = 0; D.is_trans = 1; D.cur = A.cur;
-        for (int k = 0; k < 4; ++k) { D.ei[k] = 0.0; D.nq[k] = myquat[k]; }
-        for (int k = 0; k < S * 3; ++k) D.ndb[k] = A.db[k];
     }
-    if (warp == 0) {                                        // first fill of the uniform ring
-        const long long lim = A.n_uniforms < CHAIN_RING ? A.n_uniforms : CHAIN_RING;
-        if (lane < lim) s_u[lane] = A.uniforms[lane];
-        if (lane + 32 < lim) s_u[lane + 32] = A.uniforms[lane + 32];
-    }
-    // prefetch registers of warp 0: uniforms (two per lane) and the next molecule's quaternion / body frame (one per lane)
-    double pre0 = 0.0, pre1 = 0.0, pfq = 0.0;
-    int pre_cnt = 0, pf_on = 0;
-    long long pos = 0, ring_end = A.n_uniforms < CHAIN_RING ? A.n_uniforms : CHAIN_RING;   // stream position (lane 0), ring fill (warp 0)
-    bool dry = false;
     __syncthreads();
 
-    auto next_u = [&]() -> double {                         // UStream::next of the host driver (lane 0 of warp 0)
-        if (pos >= A.n_uniforms) { dry = true; return 0.5; }
-        const double v = (pos < ring_end) ? s_u[pos & (CHAIN_RING - 1)] : A.uniforms[pos];
-        ++pos;
-        return v;
-    };
-
-    long long pc[6] = {0, 0, 0, 0, 0, 0};
-    long long pd[6] = {0, 0, 0, 0, 0, 0};
-    int cur = A.cur;
-    for (long long m = 0; m < A.n_moves; ++m) {
-        const int i = (int)(m % N);                         // sweep order i = 1..N (main.jl:490)
-        long long tc0 = clock64();
-        // ================= step 0: the trial move (main.jl:514-552), lane 0 of warp 0
-        if (warp == 0) {
-            if (pre_cnt > 0) {                              // uniforms requested during the previous move have landed
-                if (lane < pre_cnt) s_u[(ring_end + lane) & (CHAIN_RING - 1)] = pre0;
-                if (lane + 32 < pre_cnt) s_u[(ring_end + 32 + lane) & (CHAIN_RING - 1)] = pre1;
-                ring_end += pre_cnt;
-                pre_cnt = 0;
-            }
-            if (pf_on) {                                    // ... and so have the next molecule's quaternion and body frame
-                if (lane >= 1 && lane <= 4) D.nq[lane - 1] = pfq;
-                if (lane >= 5 && lane < 5 + S * 3) D.ndb[lane - 5] = pfq;
-                pf_on = 0;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                const long long tg0 = clock64();
-                const double dr_max = D.dr_max, dphi_max = D.dphi_max;
-                const double nq0 = D.nq[0], nq1 = D.nq[1], nq2 = D.nq[2], nq3 = D.nq[3];
-                const double4 c0 = s_com[i];
-                double rnew[3] = {c0.x, c0.y, c0.z};
-                double e0 = nq0, e1 = nq1, e2 = nq2, e3 = nq3;
-                int ret = 0;
-                const double chose = next_u();              // main.jl:516
-                if (chose < A.p_trans) {                    // main.jl:519-529, auxillary.jl:94-103
-                    D.is_trans = 1; D.tr.attempt += 1;
-                    const double z0 = next_u(), z1 = next_u(), z2 = next_u();
-                    rnew[0] = add(rnew[0], mul(sub(z0, 0.5), dr_max));
-                    rnew[1] = add(rnew[1], mul(sub(z1, 0.5), dr_max));
-                    rnew[2] = add(rnew[2], mul(sub(z2, 0.5), dr_max));
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {           // boundaries.jl:16-26
-                        if (rnew[k] > L) rnew[k] = sub(rnew[k], L);
-                        if (rnew[k] < 0) rnew[k] = add(rnew[k], L);
-                    }
-                } else if (chose <= A.p_rot) {              // main.jl:530-538, quaternions.jl:52-73,94-120,158-182
-                    D.is_trans = 0; D.ro.attempt += 1;
-                    if (fabs(sub(add(add(add(mul(nq0, nq0), mul(nq1, nq1)), mul(nq2, nq2)), mul(nq3, nq3)), 1.0)) > 1.e-6) ret = 2;
-                    double ax0, ax1, ax2, nrm;
-                    for (;;) {
-                        ax0 = sub(mul(2.0, next_u()), 1.0); ax1 = sub(mul(2.0, next_u()), 1.0); ax2 = sub(mul(2.0, next_u()), 1.0);
-                        nrm = add(add(mul(ax0, ax0), mul(ax1, ax1)), mul(ax2, ax2));
-                        if (nrm < 1.0 || dry) break;
-                    }
-                    const double sn = __dsqrt_rn(nrm);
-                    ax0 = __ddiv_rn(ax0, sn); ax1 = __ddiv_rn(ax1, sn); ax2 = __ddiv_rn(ax2, sn);
-                    const double zeta = next_u();
-                    const double angle = mul(sub(mul(2.0, zeta), 1.0), dphi_max);
-                    double sh, ch;
-                    sincos(mul(0.5, angle), &sh, &ch);
-                    const double r0 = ch, r1 = mul(sh, ax0), r2q = mul(sh, ax1), r3 = mul(sh, ax2);
-                    e0 = sub(sub(sub(mul(r0, nq0), mul(r1, nq1)), mul(r2q, nq2)), mul(r3, nq3));   // quatmul(rot, old)
-                    e1 = add(sub(add(mul(r1, nq0), mul(r0, nq1)), mul(r3, nq2)), mul(r2q, nq3));
-                    e2 = sub(add(add(mul(r2q, nq0), mul(r3, nq1)), mul(r0, nq2)), mul(r1, nq3));
-                    e3 = add(add(sub(mul(r3, nq0), mul(r2q, nq1)), mul(r1, nq2)), mul(r0, nq3));
-                } else ret = 3;                             // main.jl:539-541
-                if (ret == 0 && fabs(sub(add(add(add(mul(e0, e0), mul(e1, e1)), mul(e2, e2)), mul(e3, e3)), 1.0)) > 1.e-6) ret = 2;
-                D.ei[0] = e0; D.ei[1] = e1; D.ei[2] = e2; D.ei[3] = e3;
-                // quaternions.jl:37-50 — rows as written in the reference, [2,3] = 2(q2 q4 + q1 q2)
-                const double q1 = e0, q2 = e1, q3 = e2, q4 = e3;
-                double a[3][3];
-                a[0][0] = sub(sub(add(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
-                a[0][1] = mul(2, add(mul(q2, q3), mul(q1, q4))); a[0][2] = mul(2, sub(mul(q2, q4), mul(q1, q3)));
-                a[1][0] = mul(2, sub(mul(q2, q3), mul(q1, q4)));
-                a[1][1] = sub(add(sub(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
-                a[1][2] = mul(2, add(mul(q2, q4), mul(q1, q2)));
-                a[2][0] = mul(2, add(mul(q2, q4), mul(q1, q3))); a[2][1] = mul(2, sub(mul(q3, q4), mul(q1, q2)));
-                a[2][2] = add(sub(sub(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
-#pragma unroll
-                for (int s = 0; s < S; ++s) {               // main.jl:545-548: COM + MATMUL(ai, db)
-                    const double d0 = D.ndb[3 * s], d1 = D.ndb[3 * s + 1], d2 = D.ndb[3 * s + 2];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        s_tsite[s][c] = add(rnew[c], add(add(mul(d0, a[0][c]), mul(d1, a[1][c])), mul(d2, a[2][c])));
-                }
-                s_tcom[0] = rnew[0]; s_tcom[1] = rnew[1]; s_tcom[2] = rnew[2];
-                if (ret) { D.ret = ret; s_stop = ret; }
-                if (D.is_trans) { pd[0] += clock64() - tg0; pd[1] += 1; } else pd[2] += clock64() - tg0;
-            }
-            __syncwarp();
-            {   // requests for the NEXT move, consumed at the top of its step 0: uniforms, quaternion, body frame
-                const long long p0 = __shfl_sync(0xffffffffu, pos, 0), re = ring_end;
-                long long lim = p0 + CHAIN_RING;            // slot x may be overwritten once x - RING < pos
-                if (lim > A.n_uniforms) lim = A.n_uniforms;
-                const long long want = lim - re;
-                pre_cnt = want > 0 ? (int)want : 0;
-                if (lane < pre_cnt) pre0 = A.uniforms[re + lane];
-                if (lane + 32 < pre_cnt) pre1 = A.uniforms[re + 32 + lane];
-                const int inx = (i + 1 == N) ? 0 : i + 1;   // move m cannot change molecule i+1
-                if (lane >= 1 && lane <= 4) pfq = myquat[4 * inx + lane - 1];
-                if (lane >= 5 && lane < 5 + S * 3) pfq = A.db[(size_t)inx * S * 3 + lane - 5];
-                pf_on = 1;
-            }
+    // ---- one candidate for move `mv`, drawn from stream position `p0` (one warp; SURVEY A.5, mmc_driver.inl)
+    auto generate = [&](int g, long long mv, long long p0, int par) {
+        const int i = (int)(mv % N);
+        {   // everything this candidate reads from HBM in one round trip: 32 uniforms, the quaternion, the body frame
+            const long long x = p0 + lane;
+            const double uv = x < A.n_uniforms ? A.uniforms[x] : 0.5;
+            double qv = 0.0;
+            if (lane < 4) qv = myquat[4 * i + lane];
+            else if (lane < 4 + S * 3) qv = A.db[(size_t)i * S * 3 + lane - 4];
+            s_ug[g][lane] = uv;
+            if (lane < 4) s_gq[g][lane] = qv;
+            else if (lane < 4 + S * 3) s_gdb[g][lane - 4] = qv;
         }
-        { const long long t = clock64(); pc[0] += t - tc0; tc0 = t; }
-        __syncthreads();                                    // B1
-        if (s_stop) break;
-
-        // ================= step 1: COM gate for the old and the trial position
-        const double4 co = s_com[i];
-        const double cnx = s_tcom[0], cny = s_tcom[1], cnz = s_tcom[2];
-        int myfl = 0; unsigned mymask;
-        {
-            const int j = j_lo + tid;
-            if (j < j_hi && j != i) {
-                const double4 cj = s_com[j];
-                {
-                    const double rx = min_image(co.x, cj.x, L), ry = min_image(co.y, cj.y, L), rz = min_image(co.z, cj.z, L);
-                    const double r2 = add(add(mul(rx, rx), mul(ry, ry)), mul(rz, rz));
-                    if (r2 < rc_lj2) myfl |= 1;
-                    if (A.style_qq && r2 < rc_qq2) myfl |= 2;
+        __syncwarp();
+        ChainCand<S> &T = s_cand[par][g];
+        if (lane == 0) {
+            long long pos = p0;
+            bool dry = false;
+            auto next_u = [&]() -> double {                 // UStream::next of the host driver
+                if (pos >= A.n_uniforms) { dry = true; return 0.5; }
+                const long long k = pos - p0;
+                const double v = k < 32 ? s_ug[g][k] : A.uniforms[pos];
+                ++pos;
+                return v;
+            };
+            const double dr_max = D.dr_max, dphi_max = D.dphi_max;
+            const double nq0 = s_gq[g][0], nq1 = s_gq[g][1], nq2 = s_gq[g][2], nq3 = s_gq[g][3];
+            const double4 c0 = s_com[i];
+            double rnew[3] = {c0.x, c0.y, c0.z};
+            double e0 = nq0, e1 = nq1, e2 = nq2, e3 = nq3;
+            int ret = 0, is_trans = 1;
+            const double chose = next_u();                  // main.jl:516
+            if (chose < A.p_trans) {                        // main.jl:519-529, auxillary.jl:94-103
+                const double z0 = next_u(), z1 = next_u(), z2 = next_u();
+                rnew[0] = add(rnew[0], mul(sub(z0, 0.5), dr_max));
+                rnew[1] = add(rnew[1], mul(sub(z1, 0.5), dr_max));
+                rnew[2] = add(rnew[2], mul(sub(z2, 0.5), dr_max));
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {               // boundaries.jl:16-26
+                    if (rnew[k] > L) rnew[k] = sub(rnew[k], L);
+                    if (rnew[k] < 0) rnew[k] = add(rnew[k], L);
                 }
-                {
-                    const double rx = min_image(cnx, cj.x, L), ry = min_image(cny, cj.y, L), rz = min_image(cnz, cj.z, L);
-                    const double r2 = add(add(mul(rx, rx), mul(ry, ry)), mul(rz, rz));
-                    if (r2 < rc_lj2) myfl |= 4;
-                    if (A.style_qq && r2 < rc_qq2) myfl |= 8;
+            } else if (chose <= A.p_rot) {                  // main.jl:530-538, quaternions.jl:52-73,94-120,158-182
+                is_trans = 0;
+                if (fabs(sub(add(add(add(mul(nq0, nq0), mul(nq1, nq1)), mul(nq2, nq2)), mul(nq3, nq3)), 1.0)) > 1.e-6) ret = 2;
+                double ax0, ax1, ax2, nrm;
+                for (;;) {
+                    ax0 = sub(mul(2.0, next_u()), 1.0); ax1 = sub(mul(2.0, next_u()), 1.0); ax2 = sub(mul(2.0, next_u()), 1.0);
+                    nrm = add(add(mul(ax0, ax0), mul(ax1, ax1)), mul(ax2, ax2));
+                    if (nrm < 1.0 || dry) break;
                 }
+                const double sn = __dsqrt_rn(nrm);
+                ax0 = __ddiv_rn(ax0, sn); ax1 = __ddiv_rn(ax1, sn); ax2 = __ddiv_rn(ax2, sn);
+                const double zeta = next_u();
+                const double angle = mul(sub(mul(2.0, zeta), 1.0), dphi_max);
+                double sh, ch;
+                sincos(mul(0.5, angle), &sh, &ch);
+                const double r0 = ch, r1 = mul(sh, ax0), r2q = mul(sh, ax1), r3 = mul(sh, ax2);
+                e0 = sub(sub(sub(mul(r0, nq0), mul(r1, nq1)), mul(r2q, nq2)), mul(r3, nq3));   // quatmul(rot, old)
+                e1 = add(sub(add(mul(r1, nq0), mul(r0, nq1)), mul(r3, nq2)), mul(r2q, nq3));
+                e2 = sub(add(add(mul(r2q, nq0), mul(r3, nq1)), mul(r0, nq2)), mul(r1, nq3));
+                e3 = add(add(sub(mul(r3, nq0), mul(r2q, nq1)), mul(r1, nq2)), mul(r0, nq3));
+            } else ret = 3;                                 // main.jl:539-541
+            if (ret == 0 && fabs(sub(add(add(add(mul(e0, e0), mul(e1, e1)), mul(e2, e2)), mul(e3, e3)), 1.0)) > 1.e-6) ret = 2;
+            T.ei[0] = e0; T.ei[1] = e1; T.ei[2] = e2; T.ei[3] = e3;
+            // quaternions.jl:37-50 — rows as written in the reference, [2,3] = 2(q2 q4 + q1 q2)
+            const double q1 = e0, q2 = e1, q3 = e2, q4 = e3;
+            double a[3][3];
+            a[0][0] = sub(sub(add(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
+            a[0][1] = mul(2, add(mul(q2, q3), mul(q1, q4))); a[0][2] = mul(2, sub(mul(q2, q4), mul(q1, q3)));
+            a[1][0] = mul(2, sub(mul(q2, q3), mul(q1, q4)));
+            a[1][1] = sub(add(sub(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
+            a[1][2] = mul(2, add(mul(q2, q4), mul(q1, q2)));
+            a[2][0] = mul(2, add(mul(q2, q4), mul(q1, q3))); a[2][1] = mul(2, sub(mul(q3, q4), mul(q1, q2)));
+            a[2][2] = add(sub(sub(mul(q1, q1), mul(q2, q2)), mul(q3, q3)), mul(q4, q4));
+#pragma unroll
+            for (int s = 0; s < S; ++s) {                   // main.jl:545-548: COM + MATMUL(ai, db)
+                const double d0 = s_gdb[g][3 * s], d1 = s_gdb[g][3 * s + 1], d2 = s_gdb[g][3 * s + 2];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    T.site[s][c] = add(rnew[c], add(add(mul(d0, a[0][c]), mul(d1, a[1][c])), mul(d2, a[2][c])));
             }
-            mymask = __ballot_sync(0xffffffffu, myfl != 0);
-            if (lane == 0) s_wcount[warp] = __popc(mymask);
+            T.com[0] = rnew[0]; T.com[1] = rnew[1]; T.com[2] = rnew[2];
+            T.pos_end = pos; T.is_trans = is_trans; T.ret = ret; T.dry = dry ? 1 : 0;
         }
-        if (A.style_recip && warp == CHAINC_WARPS - 1 && lane < 2 * S * 3) {   // ewalds.jl:770-795
+        __syncwarp();
+        if (A.style_recip && lane < 2 * S * 3) {            // ewalds.jl:770-795 for the old and the trial sites
             const int cfg = lane / (S * 3), rem = lane - cfg * S * 3, l = rem / 3, d = rem - 3 * l;
             double x;
             if (cfg == 0) { const double4 s = s_site[i * S + l]; x = d == 0 ? s.x : (d == 1 ? s.y : s.z); }
-            else x = s_tsite[l][d];
+            else x = T.site[l][d];
             cplx e1;
             sincos(twopi * x / L, &e1.im, &e1.re);
             cplx e; e.re = 1.0; e.im = 0.0;
-            s_tab[cfg][l][d][0] = e;
+            s_tabc[par][g][cfg][l][d][0] = e;
             e = e1;
-            s_tab[cfg][l][d][1] = e;
-            for (int k = 2; k <= nk; ++k) { e = cmul(e, e1); s_tab[cfg][l][d][k] = e; }
+            s_tabc[par][g][cfg][l][d][1] = e;
+            for (int k = 2; k <= nk; ++k) { e = cmul(e, e1); s_tabc[par][g][cfg][l][d][k] = e; }
         }
-        __syncthreads();                                    // B2
-        { const long long t = clock64(); pc[1] += t - tc0; tc0 = t; }
-        int n_in = 0;
-        {   // exclusive prefix of the per-warp counts, in index order
-            int base = 0;
-#pragma unroll
-            for (int w = 0; w < CHAINC_WARPS; ++w) { const int c = s_wcount[w]; if (w < warp) base += c; n_in += c; }
-            if (myfl) s_list[base + __popc(mymask & lt)] = make_int2(j_lo + tid, myfl);
-        }
-        __syncthreads();                                    // B3
-        { const long long t = clock64(); pc[2] += t - tc0; tc0 = t; }
+    };
 
-        // ================= step 2: site pairs of (partner, cfg, site a) items + ρ(k) delta
-        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        const int items = n_in * 2 * S;
-        for (int w = tid; w < items; w += CHAINC_THREADS) {
-            const int jj = w / (2 * S), rem = w - jj * 2 * S, cfg = rem / S, a = rem - cfg * S;
-            const int2 e = s_list[jj];
-            const int j = e.x, fl = (e.y >> (2 * cfg)) & 3;
-            if (!fl) continue;
-            double4 sa = s_site[i * S + a];
-            double cix = co.x, ciy = co.y, ciz = co.z;
-            if (cfg) { sa.x = s_tsite[a][0]; sa.y = s_tsite[a][1]; sa.z = s_tsite[a][2]; cix = cnx; ciy = cny; ciz = cnz; }
-            double r2[S], dx[S], dy[S], dz[S], qq[S], ri[S];
+    if (A.n_moves > 0 && gen == 0) generate(0, 0, 0, 0);    // move 0: one candidate at the exact position
+    __syncthreads();
+
+    int cur = A.cur;
+    for (long long m = 0; m < A.n_moves; ++m) {
+        const int i = (int)(m % N), par = (int)(m & 1), sel = s_sel;
+        const ChainCand<S> &T = s_cand[par][sel];
+        if (tid == 0 && T.ret != 3) { if (T.is_trans) D.tr.attempt += 1; else D.ro.attempt += 1; }
+        if (T.ret) { if (tid == 0) { D.ret = T.ret; s_pos = T.pos_end; } break; }   // quaternion-norm error / no move selected: stop before the move
+        // the move after this one is drawn while this one is evaluated, unless the step sizes may change in between
+        const bool have_next = m + 1 < A.n_moves;
+        const bool late = A.adjust && i == N - 1;
+        double u_metro = 0.5;                                // the uniform Metropolis(m) would draw: requested now, used at the decision
+        if (tid == 0) {
+            D.is_trans = T.is_trans;
+            if (T.pos_end < A.n_uniforms) u_metro = A.uniforms[T.pos_end];
+        }
+        if (!worker) {
+            cluster.barrier_arrive();                        // generators publish nothing across SMs
+            if (have_next && !late) generate(gen, m + 1, T.pos_end + gen, par ^ 1);
+            cluster.barrier_wait();
+        } else {
+            // ================= step 1: COM gate for the old and the trial position (this CTA's partners)
+            const double4 co = s_com[i];
+            const double cnx = T.com[0], cny = T.com[1], cnz = T.com[2];
+            int myfl[2]; unsigned mymask[2];
 #pragma unroll
-            for (int b = 0; b < S; ++b) {
-                const double4 sb = s_site[j * S + b];
-                dx[b] = min_image(sa.x, sb.x, L); dy[b] = min_image(sa.y, sb.y, L); dz[b] = min_image(sa.z, sb.z, L);
-                r2[b] = dx[b] * dx[b] + dy[b] * dy[b] + dz[b] * dz[b];
-                qq[b] = sa.w * sb.w;
-                ri[b] = chain_rsqrt(r2[b]);
-            }
-            double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
-            if (fl & 1) {                                   // energy.jl:270-282
-                const int ta = s_type[a];
-                const double4 cj = s_com[j];
-                const double rijx = min_image(cix, cj.x, L), rijy = min_image(ciy, cj.y, L), rijz = min_image(ciz, cj.z, L);
-#pragma unroll
-                for (int b = 0; b < S; ++b) {
-                    const int tb = s_type[b];
-                    const double eps = Sy.eps[ta + tb * nt];
-                    if (r2[b] < (rc_lj2 + 100) && eps > 0.001) {          // σ²/r² formed as σ²·(1/√r²)²: no division on the critical path
-                        const double sig = Sy.sig[ta + tb * nt];
-                        const double s2 = sig * sig * (ri[b] * ri[b]), s6 = s2 * s2 * s2, s12 = s6 * s6;
-                        l0 += eps * (s12 - s6);
-                        const double virab = eps * (2.0 * s12 - s6) * s2;
-                        l1 += rijx * (dx[b] * virab) + rijy * (dy[b] * virab) + rijz * (dz[b] * virab);
-                    }
-                }
-            }
-            if (fl & 2) {                                   // ewalds.jl:359-367
-                bool use[S];
-#pragma unroll
-                for (int b = 0; b < S; ++b) {
-                    use[b] = false;
-                    if ((r2[b] < 0.5) && (qq[b] < 0)) l3 = 1.0;
-                    else if (r2[b] < rc_qq2 + 100) use[b] = true;
-                }
-                if (DEG != 0) {                             // erfc(κr)/r = 1/r − κ·E(κ²r²), S chains in lock-step
-                    double sv[S], pv[S];
-                    const int deg = DEG > 0 ? DEG : P.deg;
-#pragma unroll
-                    for (int b = 0; b < S; ++b) { sv[b] = fma(r2[b] * P.kappa2, P.scale, -1.0); pv[b] = P.c[deg]; }
-                    if (DEG > 0) {
-#pragma unroll
-                        for (int k = DEG - 1; k >= 0; --k)
-#pragma unroll
-                            for (int b = 0; b < S; ++b) pv[b] = fma(pv[b], sv[b], P.c[k]);
-                    } else {
-#pragma unroll 1
-                        for (int k = deg - 1; k >= 0; --k) {
-                            const double ck = P.c[k];
-#pragma unroll
-                            for (int b = 0; b < S; ++b) pv[b] = fma(pv[b], sv[b], ck);
+            for (int it = 0; it < 2; ++it) {
+                myfl[it] = 0; mymask[it] = 0;
+                if (it * CHAINS_WORKERS < n_loc) {
+                    const int j = j_lo + it * CHAINS_WORKERS + tid;
+                    int fl = 0;
+                    if (j < j_hi && j != i) {
+                        const double4 cj = s_com[j];
+                        {
+                            const double rx = min_image(co.x, cj.x, L), ry = min_image(co.y, cj.y, L), rz = min_image(co.z, cj.z, L);
+                            const double r2 = add(add(mul(rx, rx), mul(ry, ry)), mul(rz, rz));
+                            if (r2 < rc_lj2) fl |= 1;
+                            if (A.style_qq && r2 < rc_qq2) fl |= 2;
+                        }
+                        {
+                            const double rx = min_image(cnx, cj.x, L), ry = min_image(cny, cj.y, L), rz = min_image(cnz, cj.z, L);
+                            const double r2 = add(add(mul(rx, rx), mul(ry, ry)), mul(rz, rz));
+                            if (r2 < rc_lj2) fl |= 4;
+                            if (A.style_qq && r2 < rc_qq2) fl |= 8;
                         }
                     }
+                    const unsigned mk = __ballot_sync(0xffffffffu, fl != 0);
+                    if (lane == 0) s_wcount[it * CHAINS_WWARPS + warp] = __popc(mk);
+                    myfl[it] = fl; mymask[it] = mk;
+                } else if (lane == 0) s_wcount[it * CHAINS_WWARPS + warp] = 0;
+            }
+            chain_worker_bar();
+            int n_in = 0;
+            {   // exclusive prefix of the per-(iteration, warp) counts, in index order
+                int base[2] = {0, 0};
 #pragma unroll
-                    for (int b = 0; b < S; ++b) if (use[b]) l2 = fma(qq[b], fma(-P.kappa, pv[b], ri[b]), l2);
-                } else {
+                for (int k = 0; k < 2 * CHAINS_WWARPS; ++k) {
+                    const int c = s_wcount[k];
+                    if (k < warp) base[0] += c;
+                    if (k < CHAINS_WWARPS + warp) base[1] += c;
+                    n_in += c;
+                }
 #pragma unroll
-                    for (int b = 0; b < S; ++b) if (use[b]) { const double r = sqrt(r2[b]); l2 += qq[b] * erfc(Sy.kappa * r) / r; }
+                for (int it = 0; it < 2; ++it)
+                    if (myfl[it]) s_list[base[it] + __popc(mymask[it] & lt)] = make_int2(j_lo + it * CHAINS_WORKERS + tid, myfl[it]);
+            }
+            chain_worker_bar();
+
+            // ================= step 2: site pairs of (partner, cfg, site a) items + ρ(k) delta of this CTA's k-vectors
+            double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            const int items = n_in * 2 * S;
+            for (int w = tid; w < items; w += CHAINS_WORKERS) {
+                const int jj = w / (2 * S), rem = w - jj * 2 * S, cfg = rem / S, a = rem - cfg * S;
+                const int2 e = s_list[jj];
+                const int j = e.x, fl = (e.y >> (2 * cfg)) & 3;
+                if (!fl) continue;
+                double4 sa = s_site[i * S + a];
+                double cix = co.x, ciy = co.y, ciz = co.z;
+                if (cfg) { sa.x = T.site[a][0]; sa.y = T.site[a][1]; sa.z = T.site[a][2]; cix = cnx; ciy = cny; ciz = cnz; }
+                double r2[S], dx[S], dy[S], dz[S], qq[S], ri[S];
+#pragma unroll
+                for (int b = 0; b < S; ++b) {
+                    const double4 sb = s_site[j * S + b];
+                    dx[b] = min_image(sa.x, sb.x, L); dy[b] = min_image(sa.y, sb.y, L); dz[b] = min_image(sa.z, sb.z, L);
+                    r2[b] = dx[b] * dx[b] + dy[b] * dy[b] + dz[b] * dz[b];
+                    qq[b] = sa.w * sb.w;
+                    ri[b] = chain_rsqrt(r2[b]);
+                }
+                double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+                if (fl & 1) {                               // energy.jl:270-282
+                    const int ta = s_type[a];
+                    const double4 cj = s_com[j];
+                    const double rijx = min_image(cix, cj.x, L), rijy = min_image(ciy, cj.y, L), rijz = min_image(ciz, cj.z, L);
+#pragma unroll
+                    for (int b = 0; b < S; ++b) {
+                        const int tb = s_type[b];
+                        const double eps = Sy.eps[ta + tb * nt];
+                        if (r2[b] < (rc_lj2 + 100) && eps > 0.001) {      // σ²/r² formed as σ²·(1/√r²)²: no division
+                            const double sig = Sy.sig[ta + tb * nt];
+                            const double s2 = sig * sig * (ri[b] * ri[b]), s6 = s2 * s2 * s2, s12 = s6 * s6;
+                            l0 += eps * (s12 - s6);
+                            const double virab = eps * (2.0 * s12 - s6) * s2;
+                            l1 += rijx * (dx[b] * virab) + rijy * (dy[b] * virab) + rijz * (dz[b] * virab);
+                        }
+                    }
+                }
+                if (fl & 2) {                               // ewalds.jl:359-367
+                    bool use[S];
+#pragma unroll
+                    for (int b = 0; b < S; ++b) {
+                        use[b] = false;
+                        if ((r2[b] < 0.5) && (qq[b] < 0)) l3 = 1.0;
+                        else if (r2[b] < rc_qq2 + 100) use[b] = true;
+                    }
+                    if (DEG != 0) {                         // erfc(κr)/r = 1/r − κ·E(κ²r²), S chains in lock-step
+                        double sv[S], pv[S];
+                        const int deg = DEG > 0 ? DEG : P.deg;
+#pragma unroll
+                        for (int b = 0; b < S; ++b) { sv[b] = fma(r2[b] * P.kappa2, P.scale, -1.0); pv[b] = P.c[deg]; }
+                        if (DEG > 0) {
+#pragma unroll
+                            for (int k = DEG - 1; k >= 0; --k)
+#pragma unroll
+                                for (int b = 0; b < S; ++b) pv[b] = fma(pv[b], sv[b], P.c[k]);
+                        } else {
+#pragma unroll 1
+                            for (int k = deg - 1; k >= 0; --k) {
+                                const double ck = P.c[k];
+#pragma unroll
+                                for (int b = 0; b < S; ++b) pv[b] = fma(pv[b], sv[b], ck);
+                            }
+                        }
+#pragma unroll
+                        for (int b = 0; b < S; ++b) if (use[b]) l2 = fma(qq[b], fma(-P.kappa, pv[b], ri[b]), l2);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < S; ++b) if (use[b]) { const double r = sqrt(r2[b]); l2 += qq[b] * erfc(Sy.kappa * r) / r; }
+                    }
+                }
+                if (cfg) { acc[4] += l0; acc[5] += l1; acc[6] += l2; acc[7] += l3; }
+                else { acc[0] += l0; acc[1] += l1; acc[2] += l2; acc[3] += l3; }
+            }
+            if (A.style_recip) {                            // ewalds.jl:804-821
+                const double2 *Sold = s_rhok[cur];
+                double2 *Snew = s_rhok[cur ^ 1];
+                for (int k = k_lo + (CHAINS_WORKERS - 1 - tid); k < k_hi; k += CHAINS_WORKERS) {   // from the far end: the low warps carry the pair items
+                    const int4 kv = s_kvec[k];
+                    const int aky = abs(kv.y), akz = abs(kv.z);
+                    const bool ny = kv.y < 0, nz = kv.z < 0;
+                    const double2 so = Sold[k];
+                    double nr = so.x, ni = so.y;
+#pragma unroll
+                    for (int l = 0; l < S; ++l) {
+                        const cplx tn = cmul(cmul(s_tabc[par][sel][1][l][0][kv.x], cconj_if(s_tabc[par][sel][1][l][1][aky], ny)), cconj_if(s_tabc[par][sel][1][l][2][akz], nz));
+                        const cplx to = cmul(cmul(s_tabc[par][sel][0][l][0][kv.x], cconj_if(s_tabc[par][sel][0][l][1][aky], ny)), cconj_if(s_tabc[par][sel][0][l][2][akz], nz));
+                        const double q = s_site[i * S + l].w;
+                        nr += q * (tn.re - to.re);
+                        ni += q * (tn.im - to.im);
+                    }
+                    Snew[k] = make_double2(nr, ni);
+                    acc[8] += s_cfac[k] * ((nr * nr + ni * ni) - (so.x * so.x + so.y * so.y));
                 }
             }
-            if (cfg) { acc[4] += l0; acc[5] += l1; acc[6] += l2; acc[7] += l3; }
-            else { acc[0] += l0; acc[1] += l1; acc[2] += l2; acc[3] += l3; }
-        }
-        if (A.style_recip) {                                // ewalds.jl:804-821
-            const double2 *Sold = s_rhok[cur];
-            double2 *Snew = s_rhok[cur ^ 1];
-            for (int k = k_lo + (CHAINC_THREADS - 1 - tid); k < k_hi; k += CHAINC_THREADS) {   // from the far end: the low warps carry the pair items
-                const int4 kv = s_kvec[k];
-                const int aky = abs(kv.y), akz = abs(kv.z);
-                const bool ny = kv.y < 0, nz = kv.z < 0;
-                const double2 so = Sold[k];
-                double nr = so.x, ni = so.y;
+            // ================= step 3: ordered reduction, exchange, decision, state update
 #pragma unroll
-                for (int l = 0; l < S; ++l) {
-                    const cplx tn = cmul(cmul(s_tab[1][l][0][kv.x], cconj_if(s_tab[1][l][1][aky], ny)), cconj_if(s_tab[1][l][2][akz], nz));
-                    const cplx to = cmul(cmul(s_tab[0][l][0][kv.x], cconj_if(s_tab[0][l][1][aky], ny)), cconj_if(s_tab[0][l][2][akz], nz));
-                    const double q = s_site[i * S + l].w;
-                    nr += q * (tn.re - to.re);
-                    ni += q * (tn.im - to.im);
-                }
-                Snew[k] = make_double2(nr, ni);
-                acc[8] += s_cfac[k] * ((nr * nr + ni * ni) - (so.x * so.x + so.y * so.y));
+            for (int v = 0; v < 9; ++v) {
+                acc[v] = warp_sum(acc[v]);
+                if (lane == 0) s_red[v * 8 + warp] = acc[v];
             }
-        }
-        { const long long t = clock64(); pc[3] += t - tc0; tc0 = t; }
-        // ================= step 3: ordered reduction, decision, state update
-#pragma unroll
-        for (int v = 0; v < 9; ++v) {
-            acc[v] = warp_sum(acc[v]);
-            if (lane == 0) s_red[v * CHAINC_WARPS + warp] = acc[v];
-        }
-        __syncthreads();                                    // B4
-        { const long long t = clock64(); pc[4] += t - tc0; tc0 = t; }
-        long long td0 = clock64();
-        if (warp == 0) {
-            double tot[9];
-            {   // this CTA's partial sums (s_red[v][warp], 8 warps) folded by a fixed shuffle tree over groups of 8 lanes,
-                // then into slot `rank` of every CTA's exchange buffer
+            chain_worker_bar();
+            if (warp == 0) {   // partial sums (s_red[v][warp], slots 6, 7 are zero) folded by a fixed shuffle tree, then into every CTA's buffer
                 double x0 = s_red[lane], x1 = s_red[lane + 32], x2 = lane < 8 ? s_red[lane + 64] : 0.0;
 #pragma unroll
                 for (int o = 1; o < 8; o <<= 1) {
                     x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o); x2 += __shfl_xor_sync(0xffffffffu, x2, o);
                 }
-                const int par = (int)(m & 1), v0 = lane >> 3;
-                if ((lane & 7) == 0) {
-                    for (int d = 0; d < C; ++d) {
-                        double *dst = cluster.map_shared_rank(&s_xchg[par][0][0], d);
-                        dst[v0 * CHAINC_MAXC + rank] = x0;
-                        dst[(4 + v0) * CHAINC_MAXC + rank] = x1;
-                        if (lane == 0) dst[8 * CHAINC_MAXC + rank] = x2;
+                const int v0 = lane >> 3, d = lane & 7;       // every lane of a group holds the group's sum: lane (v0, d) serves CTA d
+                if (d < C) {
+                    double *dst = cluster.map_shared_rank(&s_xchg[par][0][0], d);
+                    dst[v0 * CHAINC_MAXC + rank] = x0;
+                    dst[(4 + v0) * CHAINC_MAXC + rank] = x1;
+                    if (v0 == 0) dst[8 * CHAINC_MAXC + rank] = x2;
+                }
+            }
+            cluster.barrier_arrive();
+            cluster.barrier_wait();                          // every CTA's nine sums are in every CTA's buffer
+            if (warp == 0) {
+                double tot[9];
+                {   // the C slots of every value added by the same fixed tree in every CTA: bit-identical totals everywhere
+                    const double *xb = &s_xchg[par][0][0];
+                    double x0 = xb[lane], x1 = xb[lane + 32], x2 = lane < 8 ? xb[lane + 64] : 0.0;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o); x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+                    }
+                    if ((lane & 7) == 0) { s_tot[lane >> 3] = x0; s_tot[4 + (lane >> 3)] = x1; if (lane == 0) s_tot[8] = x2; }
+                    __syncwarp();
+#pragma unroll
+                    for (int v = 0; v < 9; ++v) tot[v] = s_tot[v];
+                    __syncwarp();
+                }
+                // launch_move_on's folding (energy.jl:289 pot*4, vir*24/3; ewalds.jl:360; main.jl:580-590) + mmc_trial_move
+                const bool ovl0 = tot[3] > 0.0, ovl1 = tot[7] > 0.0, overlap = ovl0 || ovl1;
+                const double lj_old = mul(tot[0], 4), lj_new = mul(tot[4], 4);
+                const double qq_old = mul(ovl0 ? 0.0 : tot[2], Sy.factor), qq_new = mul(ovl1 ? 0.0 : tot[6], Sy.factor);
+                const double d_recip = (overlap || !A.style_recip) ? 0.0 : mul(tot[8], Sy.factor);
+                double old_e = lj_old, new_e = lj_new;
+                if (A.style_qq) { old_e = add(old_e, qq_old); new_e = add(new_e, qq_new); }     // main.jl:501-505, 566-570
+                const double delta = add(sub(new_e, old_e), d_recip);                             // main.jl:593
+                double num = delta, den = A.temperature, rden = A.inv_temperature;                // lane 0: delta / T
+                if (lane == 1) { num = mul(tot[1], 24); den = 3.0; rden = 1.0 / 3.0; }            // lj_vir_old
+                if (lane == 2) { num = mul(tot[5], 24); den = 3.0; rden = 1.0 / 3.0; }            // lj_vir_new
+                if (lane == 3) { num = qq_old; den = 3.0; rden = 1.0 / 3.0; }                     // ewalds.jl:907 virial = E/3
+                if (lane == 4) { num = qq_new; den = 3.0; rden = 1.0 / 3.0; }
+                if (lane == 5) { num = d_recip; den = 3.0; rden = 1.0 / 3.0; }
+                const double q0 = mul(num, rden);                                                 // rounded quotient via the rounded reciprocal
+                const double quo = fma(fma(-q0, den, num), rden, q0);                             // and one exact-remainder correction
+                const double ljv_old = __shfl_sync(0xffffffffu, quo, 1), ljv_new = __shfl_sync(0xffffffffu, quo, 2);
+                const double qqv_old = __shfl_sync(0xffffffffu, quo, 3), qqv_new = __shfl_sync(0xffffffffu, quo, 4);
+                const double recv = __shfl_sync(0xffffffffu, quo, 5);
+                if (lane == 0) {
+                    double old_v = ljv_old, new_v = ljv_new;
+                    if (A.style_qq) { old_v = add(old_v, qqv_old); new_v = add(new_v, qqv_new); }
+                    const double x = quo;
+                    if (overlap) D.n_ovl += 1;
+                    long long pos = T.pos_end;
+                    bool dry = T.dry != 0;
+                    bool okm = true;
+                    int drew = 0;
+                    if (!(x < 0.0)) {                                                         // auxillary.jl:106-114
+                        if (pos >= A.n_uniforms) { dry = true; u_metro = 0.5; } else { ++pos; drew = 1; }
+                        okm = exp(-x) > u_metro;
+                    }
+                    const bool accd = okm && !overlap;                                        // main.jl:598
+                    if (accd) {
+                        D.tot_e = add(D.tot_e, delta);
+                        D.tot_v = add(D.tot_v, add(sub(new_v, old_v), recv));
+                        D.n_acc += 1;
+                        if (T.is_trans) D.tr.naccept += 1; else D.ro.naccept += 1;
+                        s_com[i] = make_double4(T.com[0], T.com[1], T.com[2], 0.0);
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            double4 t = s_site[i * S + s];
+                            t.x = T.site[s][0]; t.y = T.site[s][1]; t.z = T.site[s][2];
+                            s_site[i * S + s] = t;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) myquat[4 * i + k] = T.ei[k];                  // this CTA's own replica
+                        if (A.style_recip && !overlap) s_cur = cur ^ 1;                           // main.jl:621 as an index flip
+                    }
+                    if (A.accepted && rank == 0) A.accepted[m] = accd ? 1 : 0;
+                    if (A.delta && rank == 0) A.delta[m] = delta;
+                    s_pos = pos;
+                    s_sel = drew;                                                             // which candidate of move m+1 is the real one
+                    if (dry) { D.ret = 1; s_stop = 1; }
+                    else {
+                        if (late) {                                                           // main.jl:645-651
+                            D.tr.d_max = D.dr_max; adjust_step(D.tr, L); D.dr_max = D.tr.d_max;
+                            D.ro.d_max = D.dphi_max; adjust_step(D.ro, L); D.dphi_max = D.ro.d_max;
+                        }
+                        D.n_done = m + 1;
                     }
                 }
             }
         }
-        { const long long tt = clock64(); pd[3] += tt - td0; td0 = tt; }
-        cluster.sync();                                     // every CTA's nine sums are in every CTA's buffer
-        { const long long tt = clock64(); pd[4] += tt - td0; td0 = tt; }
-        if (warp == 0) {
-            double tot[9];
-            {   // add the C slots of every value with the same fixed tree in every CTA: bit-identical totals everywhere
-                const int par = (int)(m & 1);
-                const double *xb = &s_xchg[par][0][0];
-                double x0 = xb[lane], x1 = xb[lane + 32], x2 = lane < 8 ? xb[lane + 64] : 0.0;
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o); x2 += __shfl_xor_sync(0xffffffffu, x2, o);
-                }
-                if ((lane & 7) == 0) { s_tot[lane >> 3] = x0; s_tot[4 + (lane >> 3)] = x1; if (lane == 0) s_tot[8] = x2; }
-                __syncwarp();
-#pragma unroll
-                for (int v = 0; v < 9; ++v) tot[v] = s_tot[v];
-                __syncwarp();
-            }
-            // launch_move_on's folding (energy.jl:289 pot*4, vir*24/3; ewalds.jl:360; main.jl:580-590) + mmc_trial_move.
-            // Every lane holds the totals; the six divisions run in six lanes at once, lane 0 keeps the critical path
-            // delta → delta/T → exp.
-            const bool ovl0 = tot[3] > 0.0, ovl1 = tot[7] > 0.0, overlap = ovl0 || ovl1;
-            const double lj_old = mul(tot[0], 4), lj_new = mul(tot[4], 4);
-            const double qq_old = mul(ovl0 ? 0.0 : tot[2], Sy.factor), qq_new = mul(ovl1 ? 0.0 : tot[6], Sy.factor);
-            const double d_recip = (overlap || !A.style_recip) ? 0.0 : mul(tot[8], Sy.factor);
-            double old_e = lj_old, new_e = lj_new;
-            if (A.style_qq) { old_e = add(old_e, qq_old); new_e = add(new_e, qq_new); }     // main.jl:501-505, 566-570
-            const double delta = add(sub(new_e, old_e), d_recip);                             // main.jl:593
-            double num = delta, den = A.temperature, rden = A.inv_temperature;                // lane 0: delta / T
-            if (lane == 1) { num = mul(tot[1], 24); den = 3.0; rden = 1.0 / 3.0; }            // lj_vir_old
-            if (lane == 2) { num = mul(tot[5], 24); den = 3.0; rden = 1.0 / 3.0; }            // lj_vir_new
-            if (lane == 3) { num = qq_old; den = 3.0; rden = 1.0 / 3.0; }                     // ewalds.jl:907 virial = E/3
-            if (lane == 4) { num = qq_new; den = 3.0; rden = 1.0 / 3.0; }
-            if (lane == 5) { num = d_recip; den = 3.0; rden = 1.0 / 3.0; }
-            // num / den by the correctly rounded reciprocal and one exact-remainder correction (Markstein): the
-            // rounded quotient without the ~15-deep generic division sequence on the decision's critical path
-            const double q0 = mul(num, rden);
-            const double quo = fma(fma(-q0, den, num), rden, q0);
-            const double ljv_old = __shfl_sync(0xffffffffu, quo, 1), ljv_new = __shfl_sync(0xffffffffu, quo, 2);
-            const double qqv_old = __shfl_sync(0xffffffffu, quo, 3), qqv_new = __shfl_sync(0xffffffffu, quo, 4);
-            const double recv = __shfl_sync(0xffffffffu, quo, 5);
-            if (lane == 0) {
-                double old_v = ljv_old, new_v = ljv_new;
-                if (A.style_qq) { old_v = add(old_v, qqv_old); new_v = add(new_v, qqv_new); }
-                const double x = quo;
-                if (overlap) D.n_ovl += 1;
-                bool okm = true;
-                if (!(x < 0.0)) okm = exp(-x) > next_u();                            // auxillary.jl:106-114
-                const bool accd = okm && !overlap;                                    // main.jl:598
-                if (accd) {
-                    D.tot_e = add(D.tot_e, delta);
-                    D.tot_v = add(D.tot_v, add(sub(new_v, old_v), recv));
-                    D.n_acc += 1;
-                    if (D.is_trans) D.tr.naccept += 1; else D.ro.naccept += 1;
-                    s_com[i] = make_double4(s_tcom[0], s_tcom[1], s_tcom[2], 0.0);
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        double4 t = s_site[i * S + s];
-                        t.x = s_tsite[s][0]; t.y = s_tsite[s][1]; t.z = s_tsite[s][2];
-                        s_site[i * S + s] = t;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) myquat[4 * i + k] = D.ei[k];      // this CTA's own replica (L1 is not coherent across SMs)
-                    if (A.style_recip && !overlap) s_cur = cur ^ 1;                   // main.jl:621 as an index flip
-                }
-                if (A.accepted && rank == 0) A.accepted[m] = accd ? 1 : 0;
-                if (A.delta && rank == 0) A.delta[m] = delta;
-                if (dry) { D.ret = 1; s_stop = 1; }
-                else {
-                    if (A.adjust && i == N - 1) {                                     // main.jl:645-651
-                        D.tr.d_max = D.dr_max; adjust_step(D.tr, L); D.dr_max = D.tr.d_max;
-                        D.ro.d_max = D.dphi_max; adjust_step(D.ro, L); D.dphi_max = D.ro.d_max;
-                    }
-                    D.n_done = m + 1;
-                }
-            }
-        }
-        pd[5] += clock64() - td0;
-        __syncthreads();                                    // B5
-        { const long long t = clock64(); pc[5] += t - tc0; tc0 = t; }
+        __syncthreads();                                    // B5: decision, state and (speculative) candidates are in place
         cur = s_cur;
         if (s_stop) break;
+        if (have_next && late) {                            // step sizes may have changed: draw move m+1 now, at the exact position
+            if (gen == 0) generate(0, m + 1, s_pos, par ^ 1);
+            if (tid == 0) s_sel = 0;
+            __syncthreads();
+        }
     }
     __syncthreads();
-    // ---- the state goes back to HBM; ρ(k) of the final state into the buffer the handle will call "Old"
     if (rank == 0) {
         for (int t = tid; t < N * S; t += CHAINC_THREADS) Sy.site[t] = s_site[t];
         for (int t = tid; t < N; t += CHAINC_THREADS) Sy.com[t] = s_com[t];
@@ -996,14 +1019,11 @@ k_chainc(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
     cluster.sync();                                         // nobody leaves while a neighbour may still write into its buffer
     if (tid == 0 && rank == 0) {
         ChainOut o;
-        o.n_moves = D.n_done; o.n_accepted = D.n_acc; o.n_overlap = D.n_ovl; o.uniforms_used = pos;
+        o.n_moves = D.n_done; o.n_accepted = D.n_acc; o.n_overlap = D.n_ovl; o.uniforms_used = s_pos;
         o.trans_attempt = D.tr.attempt; o.trans_accept = D.tr.naccept; o.rot_attempt = D.ro.attempt; o.rot_accept = D.ro.naccept;
         o.dr_max = D.dr_max; o.dphi_max = D.dphi_max; o.total_energy = D.tot_e; o.total_virial = D.tot_v;
         o.ret = D.ret; o.cur = cur;
-        for (int k = 0; k < 6; ++k) o.phase_cycles[k] = pc[k];
-        if (rank == 0) printf("k_chainc detail (cycles): translation %.0f  rotation %.0f  fold+store %.0f  cluster.sync %.0f  sum+decide %.0f per move\n",
-                              (double)pd[0] / (double)(pd[1] > 0 ? pd[1] : 1), (double)pd[2] / (double)(D.n_done - pd[1] > 0 ? D.n_done - pd[1] : 1),
-                              (double)pd[3] / (double)D.n_done, (double)pd[4] / (double)D.n_done, (double)pd[5] / (double)D.n_done);
+        for (int k = 0; k < 6; ++k) o.phase_cycles[k] = 0;
         *A.out = o;
     }
 }

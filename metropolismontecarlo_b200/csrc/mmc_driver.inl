@@ -189,7 +189,7 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     int dev = 0, max_optin = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (smem + 8 * 1024 > (size_t)max_optin) FAIL(MMC_EINVAL, "device loop: the system does not fit one SM's shared memory; use mmc_loop_run");
+    if (smem + 16 * 1024 > (size_t)max_optin) FAIL(MMC_EINVAL, "device loop: the system does not fit one SM's shared memory; use mmc_loop_run");
     if ((rc = flush_pending(h))) return rc;
     // thread-block cluster version: C CTAs on C SMs share the partner molecules and the k-vectors
     const int C = (h->chain_cluster > 1 && S.n_mol >= 64) ? std::min(h->chain_cluster, CHAINC_MAXC) : 1;
@@ -219,14 +219,14 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     A.out = reinterpret_cast<ChainOut *>(d + off_out); A.accepted = d_acc;
 #define MMC_CHAIN_LAUNCH(SS, DD)                                                                                     \
     if (C > 1) {                                                                                                     \
-        CK(cudaFuncSetAttribute(k_chainc<SS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        CK(cudaFuncSetAttribute(k_chains<SS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
         cudaLaunchConfig_t lc{};                                                                                     \
         lc.gridDim = dim3(C); lc.blockDim = dim3(CHAINC_THREADS); lc.dynamicSmemBytes = smem; lc.stream = h->stream; \
         cudaLaunchAttribute at[1];                                                                                   \
         at[0].id = cudaLaunchAttributeClusterDimension;                                                              \
         at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                          \
         lc.attrs = at; lc.numAttrs = 1;                                                                              \
-        CK(cudaLaunchKernelEx(&lc, k_chainc<SS, DD>, h->S, A, h->move_poly));                                        \
+        CK(cudaLaunchKernelEx(&lc, k_chains<SS, DD>, h->S, A, h->move_poly));                                        \
     } else {                                                                                                         \
         CK(cudaFuncSetAttribute(k_chain<SS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         k_chain<SS, DD><<<1, CHAIN_THREADS, smem, h->stream>>>(h->S, A, h->move_poly);                               \
