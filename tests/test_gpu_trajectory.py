@@ -169,3 +169,51 @@ def test_device_loop_short_stream_and_small_system():
     assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3] == 1500 and outs[0][4] == outs[1][4]
     assert np.array_equal(outs[0][1], outs[1][1])
     assert np.abs(outs[0][5] - outs[1][5]).max() < 1e-12
+
+
+def _resite(ms, keep):
+    """A uniform system with other site counts, derived from an SPC/E box: keep = list of (source site, charge scale)
+    per molecule; a fourth site copies H2 with a small opposite charge so the box stays neutral-ish (the engine does
+    not need neutrality).  Body frames and COMs stay those of the water molecules."""
+    n = ms.n_mol
+    S = len(keep)
+    idx = np.array([[3 * m + a for a, _ in keep] for m in range(n)]).reshape(-1)
+    sc = np.tile(np.array([s for _, s in keep]), n)
+    out = ms.copy()
+    out.coords = ms.coords[idx].copy()
+    out.charge = ms.charge[idx] * sc
+    out.atype = ms.atype[idx].copy()
+    out.db = ms.db[idx].copy()
+    out.first_atom = (np.arange(n) * S + 1).astype(np.int64)
+    out.last_atom = (np.arange(n) * S + S).astype(np.int64)
+    return out
+
+
+@pytest.mark.parametrize("keep,style,sid", [
+    ([(0, 1.0)], "lj", 2),                                        # one LJ site per molecule
+    ([(0, 1.0), (1, 2.0)], "wolf", 1),                            # two sites (O, H with doubled charge)
+    ([(0, 1.0), (1, 1.0), (2, 0.5), (2, 0.5)], "ewald", 0),       # four sites (second H split in two)
+])
+def test_device_loop_other_site_counts_match_host_driver(keep, style, sid):
+    """k_chains<S> / k_chain<S> for S = 1, 2, 4 against the per-move protocol (which is oracle-tested)."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = _resite(systems.load_nist(1), keep)
+    u = julia_rand(11234, 8 * 3000)
+    outs = []
+    for device, cluster in ((False, 1), (True, 1), (True, 8)):
+        eng = water_engine(ms, 9.0)
+        eng.debug_set("chain_cluster", cluster)
+        g0 = eng.potential(style)
+        com, quat = ms.com.copy(), ms.quat.copy()
+        rc, acc, delta, st = eng.loop_run(LoopParams(298.15, 0.4, 0.08, 0.5, 1.0, sid, 1), com, quat, ms.db, u, 3000,
+                                          g0.energy, g0.virial, device=device)
+        assert rc == 0
+        fresh = eng.potential(style)
+        assert rel(st.total_energy, fresh.energy) < 1e-9
+        outs.append((acc.copy(), delta.copy(), st.uniforms_used, st.dr_max, com.copy()))
+        eng.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0])
+        assert o[2] == outs[0][2] and abs(o[3] - outs[0][3]) < 1e-12
+        assert np.abs(o[1] - outs[0][1]).max() < 1e-6 * max(1.0, np.abs(outs[0][1]).max())
+        assert np.abs(o[4] - outs[0][4]).max() < 1e-11
