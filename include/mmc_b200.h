@@ -206,6 +206,13 @@ int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_max, double 
                        double e0, double v0, uint8_t *accepted, double *delta,
                        mmc_loop_stats *stats);
 
+/* mmc_loop_run_atoms for a block of moves in one launch (csrc/kernels_chain.cuh k_chain_atoms: the atoms are
+ * sliced over the CTAs of an 8-SM cluster, FP32 distance gate on chip, FP64 evaluation of what passes). */
+int mmc_loop_run_atoms_device(mmc_handle *h, double temperature, double dr_max, double *r,
+                              const double *uniforms, int64_t n_uniforms, int64_t n_moves,
+                              double e0, double v0, uint8_t *accepted, double *delta,
+                              mmc_loop_stats *stats);
+
 /* The reference's random stream without Julia: the first `n` values, after skipping `skip`, that
  * `Random.seed!(seed); rand()` yields in the Julia the reference targets (1.x <= 1.6, global
  * MersenneTwister = dSFMT-19937 seeded by init_by_array(make_seed(seed))); `rand(Float64,3)`

@@ -1027,3 +1027,211 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
         *A.out = o;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// k_chain_atoms — Monatomic/mainMonatomic.jl:373-413 for a block of moves on a thread-block cluster.
+// The reference scans all N atoms twice per move (LJ_ΔU old, LJ_ΔU new).  Here CTA r of the cluster keeps a FLOAT
+// copy of its slice of the positions in shared memory (16 B per atom: 32 000 atoms = 64 KB per CTA at C = 8) and
+// scans it with a conservative FP32 distance gate for the old and the trial position at once (min-image by rintf);
+// the few atoms that pass (≈50 of 32 000) are re-tested and evaluated in FP64 from the resident arrays (exact rule
+// `!(r² > r_cut²)`, σ_j²/r² by division as in the reference).  Four partial sums per CTA cross the cluster through
+// DSMEM; one cluster barrier per move; every CTA takes the same decision redundantly; the owner of atom i updates
+// the resident position (L2) and its float copy.  r_old(i+1) and the uniforms are requested one move ahead.
+#define CHAINA_THREADS 512
+#define CHAINA_WARPS (CHAINA_THREADS / 32)
+
+struct ChainAtomArgs {
+    long long n_moves, n_uniforms;
+    double temperature, inv_temperature, dr_max, e0, v0;
+    float gate_rc2f;             // r_cut² + 4× the worst-case FP32 error of the gate
+    const double *uniforms;
+    unsigned char *accepted;     // [n_moves] or NULL
+    double *delta;               // [n_moves] or NULL
+    ChainOut *out;
+};
+
+__global__ void __launch_bounds__(CHAINA_THREADS, 1)
+k_chain_atoms(DevAtoms At, const __grid_constant__ ChainAtomArgs A)
+{
+    using namespace chain;
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_f = reinterpret_cast<float4 *>(smem_raw);                  // float copy of this CTA's slice
+    __shared__ double s_red[4 * CHAINA_WARPS];
+    __shared__ double s_xchg[2][4][CHAINC_MAXC];                         // [move parity][value][source rank]
+    __shared__ double s_tot[4];
+    __shared__ double s_u[CHAIN_RING];
+    __shared__ double s_r0[3], s_rn[3];
+    __shared__ int s_stop;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = At.n;
+    const int a_lo = (int)((long long)N * rank / C), a_hi = (int)((long long)N * (rank + 1) / C), n_loc = a_hi - a_lo;
+    const double L = At.box, rc2 = At.rc * At.rc;
+    const float Lf = (float)L, invLf = (float)(1.0 / L), rc2f = A.gate_rc2f;
+
+    for (int t = tid; t < n_loc; t += CHAINA_THREADS) {
+        const double4 r = At.r[a_lo + t];
+        s_f[t] = make_float4((float)r.x, (float)r.y, (float)r.z, 0.f);
+    }
+    for (int k = tid; k < 2 * 4 * CHAINC_MAXC; k += CHAINA_THREADS) (&s_xchg[0][0][0])[k] = 0.0;
+    if (tid == 0) s_stop = 0;
+
+    // driver state: lane 0 of warp 0 (a handful of registers)
+    long long pos = 0, ring_end = A.n_uniforms < CHAIN_RING ? A.n_uniforms : CHAIN_RING;
+    bool dry = false;
+    double tot_e = A.e0, tot_v = A.v0;
+    long long n_acc = 0, n_tacc = 0, n_done = 0;
+    int ret = 0;
+    double pre0 = 0.0, pre1 = 0.0; int pre_cnt = 0;
+    double4 rnext = make_double4(0, 0, 0, 0);                              // position of the next move's atom, requested a move ahead
+    if (warp == 0) {
+        const long long lim = ring_end;
+        if (lane < lim) s_u[lane] = A.uniforms[lane];
+        if (lane + 32 < lim) s_u[lane + 32] = A.uniforms[lane + 32];
+        if (lane == 0 && A.n_moves > 0) rnext = ldcg4(&At.r[0]);
+    }
+    __syncthreads();
+    auto next_u = [&]() -> double {
+        if (pos >= A.n_uniforms) { dry = true; return 0.5; }
+        const double v = (pos < ring_end) ? s_u[pos & (CHAIN_RING - 1)] : A.uniforms[pos];
+        ++pos;
+        return v;
+    };
+
+    for (long long m = 0; m < A.n_moves; ++m) {
+        const int i = (int)(m % N), par = (int)(m & 1);
+        // ================= step 0: the trial position (mainMonatomic.jl:375-380), lane 0 of warp 0
+        if (warp == 0) {
+            if (pre_cnt > 0) {
+                if (lane < pre_cnt) s_u[(ring_end + lane) & (CHAIN_RING - 1)] = pre0;
+                if (lane + 32 < pre_cnt) s_u[(ring_end + 32 + lane) & (CHAIN_RING - 1)] = pre1;
+                ring_end += pre_cnt;
+                pre_cnt = 0;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const double z0 = next_u(), z1 = next_u(), z2 = next_u();
+                double rn[3] = {add(rnext.x, mul(sub(z0, 0.5), A.dr_max)), add(rnext.y, mul(sub(z1, 0.5), A.dr_max)),
+                                add(rnext.z, mul(sub(z2, 0.5), A.dr_max))};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (rn[k] > L) rn[k] = sub(rn[k], L);
+                    if (rn[k] < 0) rn[k] = add(rn[k], L);
+                }
+                s_r0[0] = rnext.x; s_r0[1] = rnext.y; s_r0[2] = rnext.z;
+                s_rn[0] = rn[0]; s_rn[1] = rn[1]; s_rn[2] = rn[2];
+                const int inx = (i + 1 == N) ? 0 : i + 1;   // move m cannot change atom i+1; L2 load: its owner is another SM
+                rnext = ldcg4(&At.r[inx]);
+            }
+            {
+                const long long p0 = __shfl_sync(0xffffffffu, pos, 0);
+                long long lim = p0 + CHAIN_RING;
+                if (lim > A.n_uniforms) lim = A.n_uniforms;
+                const long long want = lim - ring_end;
+                pre_cnt = want > 0 ? (int)want : 0;
+                if (lane < pre_cnt) pre0 = A.uniforms[ring_end + lane];
+                if (lane + 32 < pre_cnt) pre1 = A.uniforms[ring_end + 32 + lane];
+            }
+        }
+        __syncthreads();
+        // ================= step 1: FP32 gate over this CTA's slice, FP64 evaluation of what passes
+        const double x0 = s_r0[0], y0 = s_r0[1], z0 = s_r0[2], xn = s_rn[0], yn = s_rn[1], zn = s_rn[2];
+        const float fx0 = (float)x0, fy0 = (float)y0, fz0 = (float)z0, fxn = (float)xn, fyn = (float)yn, fzn = (float)zn;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int t = tid; t < n_loc; t += CHAINA_THREADS) {
+            const float4 f = s_f[t];
+            float dx = f.x - fx0, dy = f.y - fy0, dz = f.z - fz0;
+            dx -= Lf * rintf(dx * invLf); dy -= Lf * rintf(dy * invLf); dz -= Lf * rintf(dz * invLf);
+            const float d2o = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            float ex = f.x - fxn, ey = f.y - fyn, ez = f.z - fzn;
+            ex -= Lf * rintf(ex * invLf); ey -= Lf * rintf(ey * invLf); ez -= Lf * rintf(ez * invLf);
+            const float d2n = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+            if ((d2o <= rc2f || d2n <= rc2f) && a_lo + t != i) {
+                const double4 rj = At.r[a_lo + t];
+                const double2 es = At.es[a_lo + t];
+                {
+                    const double ax = min_image(x0, rj.x, L), ay = min_image(y0, rj.y, L), az = min_image(z0, rj.z, L);
+                    const double r2 = ax * ax + ay * ay + az * az;
+                    if (!(r2 > rc2)) {                       // mainMonatomic.jl:249
+                        const double sr2 = es.y * es.y / r2, sr6 = sr2 * sr2 * sr2, sr12 = sr6 * sr6;
+                        acc[0] += es.x * (sr12 - sr6);
+                        acc[1] += es.x * (2 * sr12 - sr6);
+                    }
+                }
+                {
+                    const double ax = min_image(xn, rj.x, L), ay = min_image(yn, rj.y, L), az = min_image(zn, rj.z, L);
+                    const double r2 = ax * ax + ay * ay + az * az;
+                    if (!(r2 > rc2)) {
+                        const double sr2 = es.y * es.y / r2, sr6 = sr2 * sr2 * sr2, sr12 = sr6 * sr6;
+                        acc[2] += es.x * (sr12 - sr6);
+                        acc[3] += es.x * (2 * sr12 - sr6);
+                    }
+                }
+            }
+        }
+        // ================= step 2: ordered reduction, exchange, decision
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            acc[v] = warp_sum(acc[v]);
+            if (lane == 0) s_red[v * CHAINA_WARPS + warp] = acc[v];
+        }
+        __syncthreads();
+        if (warp == 0) {   // s_red[v][16 warps]: fixed shuffle tree over groups of 16 lanes, then into every CTA's buffer
+            double xa = s_red[lane], xb = s_red[lane + 32];
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) { xa += __shfl_xor_sync(0xffffffffu, xa, o); xb += __shfl_xor_sync(0xffffffffu, xb, o); }
+            const int d = lane & 15, vh = lane >> 4;          // lane (vh, d): values vh and 2 + vh for CTA d
+            if (d < C) {
+                double *dst = cluster.map_shared_rank(&s_xchg[par][0][0], d);
+                dst[vh * CHAINC_MAXC + rank] = xa;
+                dst[(2 + vh) * CHAINC_MAXC + rank] = xb;
+            }
+        }
+        cluster.sync();
+        if (warp == 0) {
+            double x = (&s_xchg[par][0][0])[lane];            // 4 values x 8 ranks = 32 doubles: groups of 8 lanes
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((lane & 7) == 0) s_tot[lane >> 3] = x;
+            __syncwarp();
+            if (lane == 0) {
+                // launch_move_atom's folding (mainMonatomic.jl:271): pot*4, vir*24/3
+                const double lj_old = mul(s_tot[0], 4.0), v_old = __ddiv_rn(mul(s_tot[1], 24.0), 3.0);
+                const double lj_new = mul(s_tot[2], 4.0), v_new = __ddiv_rn(mul(s_tot[3], 24.0), 3.0);
+                const double delta = sub(lj_new, lj_old);
+                const double q0 = mul(delta, A.inv_temperature);
+                const double x = fma(fma(-q0, A.temperature, delta), A.inv_temperature, q0);   // delta / T
+                bool okm = true;
+                if (!(x < 0.0)) okm = exp(-x) > next_u();    // Metropolis
+                if (okm) {
+                    tot_e = add(tot_e, delta);
+                    tot_v = add(tot_v, sub(v_new, v_old));
+                    n_acc += 1;
+                    if (i >= a_lo && i < a_hi) {             // the owner of atom i updates the resident position and its float copy
+                        At.r[i] = make_double4(s_rn[0], s_rn[1], s_rn[2], 0.0);
+                        s_f[i - a_lo] = make_float4((float)s_rn[0], (float)s_rn[1], (float)s_rn[2], 0.f);
+                    }
+                }
+                if (A.accepted && rank == 0) A.accepted[m] = okm ? 1 : 0;
+                if (A.delta && rank == 0) A.delta[m] = delta;
+                if (dry) { ret = 1; s_stop = 1; } else { n_done = m + 1; if (okm) n_tacc += 1; }
+            }
+        }
+        __syncthreads();
+        if (s_stop) break;
+    }
+    __threadfence();
+    cluster.sync();
+    if (tid == 0 && rank == 0) {
+        ChainOut o;
+        o.n_moves = n_done; o.n_accepted = n_acc; o.n_overlap = 0; o.uniforms_used = pos;
+        o.trans_attempt = n_done; o.trans_accept = n_tacc; o.rot_attempt = 0; o.rot_accept = 0;
+        o.dr_max = A.dr_max; o.dphi_max = 0.0; o.total_energy = tot_e; o.total_virial = tot_v;
+        o.ret = ret; o.cur = 0;
+        for (int k = 0; k < 6; ++k) o.phase_cycles[k] = 0;
+        *A.out = o;
+    }
+}

@@ -325,6 +325,71 @@ extern "C" int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_m
     return ret;
 }
 
+// Monatomic/mainMonatomic.jl:373-413 for a block of moves in one launch on a thread-block cluster
+// (kernels_chain.cuh k_chain_atoms).  Arguments, draw order, return codes and statistics of mmc_loop_run_atoms.
+extern "C" int mmc_loop_run_atoms_device(mmc_handle *h, double temperature, double dr_max, double *r,
+                                         const double *uniforms, int64_t n_uniforms, int64_t n_moves, double e0, double v0,
+                                         uint8_t *accepted, double *delta_out, mmc_loop_stats *st)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
+    if (!r || !uniforms || !st || n_moves < 0 || n_uniforms < 0) FAIL(MMC_EINVAL, "bad argument");
+    if (h->trial_pending) FAIL(MMC_ESTATE, "a trial move is pending");
+    const int n = h->At.n;
+    const int C = CHAINC_MAXC;
+    if (n < 64) FAIL(MMC_EINVAL, "device loop: at least 64 atoms");
+    const size_t smem = sizeof(float4) * (size_t)((n + C - 1) / C + 1);
+    int dev = 0, max_optin = 0, rc;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem + 8 * 1024 > (size_t)max_optin) FAIL(MMC_EINVAL, "device loop: the slice of atoms does not fit one SM's shared memory; use mmc_loop_run_atoms");
+    if ((rc = flush_pending(h))) return rc;
+    const size_t off_delta = (size_t)n_uniforms, off_out = off_delta + (size_t)n_moves;
+    const size_t out_doubles = (sizeof(ChainOut) + 7) / 8;
+    const size_t bytes = (off_out + out_doubles) * sizeof(double) + (size_t)n_moves + 16;
+    if (bytes > h->chain_bytes) {
+        dfree(h->d_chain);
+        CK(cudaMalloc(&h->d_chain, bytes));
+        h->chain_bytes = bytes;
+    }
+    double *d = reinterpret_cast<double *>(h->d_chain);
+    unsigned char *d_acc = reinterpret_cast<unsigned char *>(d + off_out + out_doubles);
+    CK(cudaMemcpyAsync(d, uniforms, sizeof(double) * (size_t)n_uniforms, cudaMemcpyHostToDevice, h->stream));
+    ChainAtomArgs A{};
+    A.n_moves = n_moves; A.n_uniforms = n_uniforms;
+    A.temperature = temperature; A.inv_temperature = 1.0 / temperature; A.dr_max = dr_max; A.e0 = e0; A.v0 = v0;
+    {   // conservative FP32 gate: |d²_f32 − d²| <= 2·sqrt(3)·rc·δ + 3δ² with δ = 5·L·2^-24 (float positions <= L + dr,
+        // their difference, the ±L image shift); 4x safety, and one ulp for the `!(r² > r_cut²)` equality
+        const double L = h->At.box, rcut = h->At.rc, del = 5.0 * (L + dr_max) / 16777216.0;
+        const double margin = 4.0 * (2.0 * 1.7320508075688772 * rcut * del + 3.0 * del * del + 3.6e-7 * rcut * rcut);
+        A.gate_rc2f = std::nextafterf((float)(rcut * rcut + margin), INFINITY);
+    }
+    A.uniforms = d; A.delta = d + off_delta; A.out = reinterpret_cast<ChainOut *>(d + off_out); A.accepted = d_acc;
+    CK(cudaFuncSetAttribute(k_chain_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(C); lc.blockDim = dim3(CHAINA_THREADS); lc.dynamicSmemBytes = smem; lc.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&lc, k_chain_atoms, h->At, A));
+    LAUNCH_CHECK();
+    ChainOut o{};
+    std::vector<double4> hr(n);
+    CK(cudaMemcpyAsync(&o, A.out, sizeof(o), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hr.data(), h->At.r, sizeof(double4) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (accepted && n_moves) CK(cudaMemcpyAsync(accepted, d_acc, (size_t)n_moves, cudaMemcpyDeviceToHost, h->stream));
+    if (delta_out && n_moves) CK(cudaMemcpyAsync(delta_out, A.delta, sizeof(double) * (size_t)n_moves, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < n; ++k) { r[3 * k] = hr[k].x; r[3 * k + 1] = hr[k].y; r[3 * k + 2] = hr[k].z; }
+    h->cnt.trial_moves += o.n_moves; h->cnt.commits += o.n_accepted;
+    std::memset(st, 0, sizeof(*st));
+    st->n_moves = o.n_moves; st->n_accepted = o.n_accepted; st->uniforms_used = o.uniforms_used;
+    st->trans_attempt = o.trans_attempt; st->trans_accept = o.trans_accept;
+    st->dr_max = o.dr_max; st->total_energy = o.total_energy; st->total_virial = o.total_virial;
+    return o.ret;
+}
+
 extern "C" int mmc_julia_rand(uint64_t seed, int64_t skip, double *out, int64_t n)
 {
     if (skip < 0 || n < 0 || (n > 0 && !out)) return MMC_EINVAL;

@@ -251,13 +251,14 @@ class Engine:
                                             acc.ctypes.data_as(_lib.c_uint8_p), _dp(delta), C.byref(st)))
         return rc, acc, delta, st
 
-    def loop_run_atoms(self, temperature, dr_max, r, uniforms, n_moves, e0=0.0, v0=0.0):
+    def loop_run_atoms(self, temperature, dr_max, r, uniforms, n_moves, e0=0.0, v0=0.0, device=False):
+        fn = self.lib.mmc_loop_run_atoms_device if device else self.lib.mmc_loop_run_atoms
         assert r.dtype == np.float64 and r.flags.c_contiguous
         uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
         acc = np.zeros(n_moves, dtype=np.uint8)
         delta = np.zeros(n_moves)
         st = LoopStats()
-        rc = self._ck(self.lib.mmc_loop_run_atoms(self.h, temperature, dr_max, _dp(r), _dp(uniforms),
+        rc = self._ck(fn(self.h, temperature, dr_max, _dp(r), _dp(uniforms),
                                                   uniforms.shape[0], n_moves, e0, v0,
                                                   acc.ctypes.data_as(_lib.c_uint8_p), _dp(delta), C.byref(st)))
         return rc, acc, delta, st

@@ -217,3 +217,28 @@ def test_device_loop_other_site_counts_match_host_driver(keep, style, sid):
         assert o[2] == outs[0][2] and abs(o[3] - outs[0][3]) < 1e-12
         assert np.abs(o[1] - outs[0][1]).max() < 1e-6 * max(1.0, np.abs(outs[0][1]).max())
         assert np.abs(o[4] - outs[0][4]).max() < 1e-11
+
+
+@pytest.mark.parametrize("n_atoms,dr_div", [(1000, 30.0), (4096, 150.0)])
+def test_monatomic_device_loop(n_atoms, dr_div):
+    """mmc_loop_run_atoms_device (k_chain_atoms: atoms sliced over an 8-SM cluster, FP32 gate + FP64 evaluation)
+    against the oracle's loop: identical accept/reject record and positions; dr_max = L/150 gives ~50 % acceptance."""
+    from metropolismontecarlo_b200.energy import Engine
+    at = systems.lj_lattice(n_atoms, 0.75, 2.5)
+    u = julia_rand(11234, 5 * N_MOVES)
+    e0, v0 = ora.potential_atoms(at.r, at.eps, at.sig, at.box, at.r_cut, 4)
+    r_o = at.r.copy()
+    rc_o, acc_o, del_o, st_o = ora.loop_atoms(r_o, at.eps, at.sig, at.box, at.r_cut, 1.0, at.box / dr_div, u, N_MOVES, e0, v0)
+    eng = Engine()
+    eng.upload_atoms(at)
+    g0 = eng.potential("atoms")
+    r_g = at.r.copy()
+    rc_g, acc_g, del_g, st_g = eng.loop_run_atoms(1.0, at.box / dr_div, r_g, u, N_MOVES, g0.energy, g0.virial, device=True)
+    assert rc_o == 0 and rc_g == 0 and st_g.n_moves == N_MOVES
+    assert np.array_equal(acc_g, acc_o), f"first divergence at move {int(np.argmax(acc_g != acc_o))}"
+    assert st_g.uniforms_used == st_o.uniforms_used and st_g.n_accepted == st_o.n_accepted
+    assert np.abs(del_g - del_o).max() < 1e-10 * max(1.0, np.abs(del_o).max())
+    assert np.array_equal(r_g, r_o) and np.array_equal(eng.download_atoms(), r_o)
+    assert rel(st_g.total_energy, eng.potential("atoms").energy) < 1e-10
+    print("atoms", n_atoms, "accepted", st_g.n_accepted)
+    eng.close()
