@@ -126,14 +126,14 @@ def run_reference(args, rank):
     v = float(np.mean(vals))
     sample = (f"{n_rows} of {ms.n_mol} rows of the two O(N^2) loops ({threads} OpenMP threads over rows) + RecipLong on "
               f"1/{frac} of the sites (serial, as the reference), extrapolated linearly to one full evaluation")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(ms.n_mol),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sample_wall_s": wall,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------ moves/s (N=1)
@@ -347,13 +347,34 @@ def run_ours(args, rank, world, local_rank):
                           "linearly; Julia is not installed, so this is the C restatement of the reference algorithm"}
             if not args.no_moves:
                 line["moves"] = moves_benchmarks()
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # exactly ONE line on stdout (the JSON): libraries that print banners there (NCCL's version line under
+    # NCCL_DEBUG=VERSION) are sent to stderr while the benchmark runs
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        if _RESULT_LINES:
+            os.write(1, ("\n".join(_RESULT_LINES) + "\n").encode())
+
+
+_RESULT_LINES = []
+
+
+def emit(line: dict):
+    _RESULT_LINES.append(json.dumps(line))
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
