@@ -88,6 +88,11 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites,
                       const int64_t *first_atom, const int64_t *last_atom, const double *com,
                       int32_t n_types, const double *eps, const double *sig,
                       double box, double rc_lj, double rc_qq);
+/* All positions of an uploaded system at once (pointer(soa.coords), pointer(moa.COM) after the caller changed
+ * them itself): the bulk form of mmc_set_molecule (Ewald/main.jl:527,552).  Charges, types and topology stay; the
+ * resident rho(k) is not rebuilt (mmc_recip_long / mmc_potential do that, as after mmc_upload_system). */
+int mmc_upload_positions(mmc_handle *h, const double *coords, const double *com);
+
 /* Monatomic/mainMonatomic.jl:140-146 Requirements(r, eps, sig, box, r_cut) */
 int mmc_upload_atoms(mmc_handle *h, int64_t n, const double *r, const double *eps_j,
                      const double *sig_j, double box, double r_cut);

@@ -91,6 +91,10 @@ recip_rollback!(e::Engine) = check(e, ccall((:mmc_recip_rollback, LIB), Cint, (P
 set_molecule!(e::Engine, i::Int, com, sites::Vector) =
     check(e, ccall((:mmc_set_molecule, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), e.h, i, Ref(com), pointer(sites)))
 
+# all positions at once (bulk form of set_molecule!): pointer(soa.coords), pointer(moa.COM)
+upload_positions!(e::Engine, coords, com) =
+    check(e, ccall((:mmc_upload_positions, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), e.h, pointer(coords), pointer(com)))
+
 # potential(moa, soa, tot, ewald, vdwTable, sim_props[, "ewald"])  — Ewald/energy.jl:864-1032
 function potential(e::Engine, style::Cint = EWALD)
     p = Props()

@@ -100,6 +100,7 @@ SIGNATURES = {
     "mmc_volume_trial": (C.c_int, [H, C.c_double, C.c_double, C.c_int32, C.POINTER(Properties)]),
     "mmc_volume_accept": (C.c_int, [H]),
     "mmc_volume_reject": (C.c_int, [H]),
+    "mmc_upload_positions": (C.c_int, [H, c_double_p, c_double_p]),
     "mmc_loop_run": (C.c_int, [H, C.POINTER(LoopParams), c_double_p, c_double_p, c_double_p, c_double_p,
                                C.c_int64, C.c_int64, C.c_double, C.c_double, c_uint8_p, c_double_p,
                                C.POINTER(LoopStats)]),

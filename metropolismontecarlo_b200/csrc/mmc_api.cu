@@ -562,7 +562,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     const long long ns_all = S.n_sites;
     const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
     bool rhok_forked = false;
-    if (style == MMC_STYLE_EWALD && h->overlap_rhok && E.f == 1.0) {
+    if (style == MMC_STYLE_EWALD && h->overlap_rhok == 1 && E.f == 1.0) {
         CK(cudaEventRecord(h->ev_fork, h->stream));
         CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         int rcr = rhok_launch(h, S.site, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL), h->side);
@@ -1131,6 +1131,33 @@ int mmc_upload_atoms(mmc_handle *h, int64_t n, const double *r, const double *ep
     return MMC_OK;
 }
 
+// All positions of an uploaded system at once (soa.coords, moa.COM after the caller changed them itself: a
+// checkpoint, its own volume scaling, ...): the bulk form of mmc_set_molecule (Ewald/main.jl:527,552).  Charges,
+// types and topology stay; the resident ρ(k) is NOT rebuilt (call mmc_recip_long / mmc_potential as after an upload).
+int mmc_upload_positions(mmc_handle *h, const double *coords, const double *com)
+{
+    if (!h) return MMC_EINVAL;
+    if (!h->has_system) FAIL(MMC_ESTATE, "no molecular system uploaded");
+    if (!coords || !com) FAIL(MMC_EINVAL, "null array");
+    CK(cudaSetDevice(h->cfg.device));
+    DevSystem &S = h->S;
+    double *d_coords = reinterpret_cast<double *>(h->d_raw);
+    double *d_com = d_coords + 4 * (size_t)S.n_sites;      // same slots as in mmc_upload_system's staging block
+    CK(cudaMemcpyAsync(d_coords, coords, sizeof(double) * 3 * S.n_sites, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * S.n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
+    k_repack_positions<<<(unsigned)((S.n_sites + 255) / 256), 256, 0, h->stream>>>(d_coords, d_com, S.n_mol, S.n_sites, S.box,
+                                                                                  S.site, S.com, h->d_info);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
+    h->pair_level = h->pair_floor;
+    if (h->pend_kind == 1) h->pend_kind = 0;
+    h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
+    return MMC_OK;
+}
+
 int mmc_download_system(mmc_handle *h, double *coords, double *com)
 {
     if (!h) return MMC_EINVAL;
@@ -1621,7 +1648,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     if (!h || !key) return MMC_EINVAL;
     const std::string k(key);
     if (k == "chain_cluster") { if (value < 1 || value > CHAINC_MAXC) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
-    if (k == "overlap_rhok") { h->overlap_rhok = value != 0; return MMC_OK; }
+    if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
     if (k == "v6_ctas_per_sm") { if (value < 1 || value > 5) FAIL(MMC_EINVAL, "v6_ctas_per_sm must be 1..5"); h->v6_ctas_per_sm = (int)value; return MMC_OK; }
     if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v6 .. 5 general)
         if (value < 0 || value > 5) FAIL(MMC_EINVAL, "pair_level must be 0..5");

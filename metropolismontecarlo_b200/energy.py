@@ -75,6 +75,13 @@ class Engine:
         self.box = float(ms.box)
         self.n_mol, self.n_sites = ms.n_mol, ms.n_sites
 
+    def upload_positions(self, coords, com):
+        """All site coordinates and COMs of the uploaded system at once (bulk mmc_set_molecule, main.jl:527,552)."""
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        com = np.ascontiguousarray(com, dtype=np.float64)
+        assert coords.shape == (self.n_sites, 3) and com.shape == (self.n_mol, 3)
+        self._ck(self.lib.mmc_upload_positions(self.h, _dp(coords), _dp(com)))
+
     def upload_atoms(self, at: AtomicSystem):
         r = np.ascontiguousarray(at.r, dtype=np.float64)
         e = np.ascontiguousarray(at.eps, dtype=np.float64)

@@ -395,3 +395,25 @@ def test_error_behaviour():
         eng.accept()                        # no pending trial
     assert eng.LJ_poly_ΔU(1)[0] != 0.0
     eng.close()
+
+
+def test_upload_positions_equals_full_upload(c750):
+    """mmc_upload_positions (bulk set_molecule) leaves the same state as a full mmc_upload_system of the moved system."""
+    ms, eng = c750
+    eng.upload_system(ms, 10.0, 10.0)
+    rng = np.random.default_rng(4)
+    ms2 = ms.copy()
+    d = rng.uniform(-0.2, 0.2, ms.com.shape)
+    ms2.com = np.clip(ms.com + d, 0.0, ms.box)
+    ms2.coords = ms.coords + np.repeat(ms2.com - ms.com, 3, axis=0)
+    eng.upload_positions(ms2.coords, ms2.com)
+    got = eng.potential("ewald")
+    coords, com = eng.download_system()
+    assert np.array_equal(coords, ms2.coords) and np.array_equal(com, ms2.com)
+    eng.upload_system(ms2, 10.0, 10.0)
+    want = eng.potential("ewald")
+    _check_props(got, want, 1e-13)
+    bad = ms2.com.copy(); bad[3, 0] = ms.box + 1.0
+    with pytest.raises(Exception):
+        eng.upload_positions(ms2.coords, bad)
+    eng.upload_system(ms, 10.0, 10.0)

@@ -10,11 +10,13 @@ ap.add_argument("--molecules", type=int, default=256000)
 ap.add_argument("--evals", type=int, default=4)
 ap.add_argument("--style", default="ewald")
 ap.add_argument("--pair-level", type=int, default=0, help="0 v6, 1 v5, 2 v4, 3 v3, 4 fast, 5 general")
+ap.add_argument("--overlap", type=int, default=1)
 a = ap.parse_args()
 ms = systems.spce_lattice(a.molecules) if a.molecules != 750 else systems.load_nist(4)
 eng = water_engine(ms, 10.0)
 eng.set_timing(True)
 eng.debug_set("pair_level", a.pair_level)
+eng.debug_set("overlap_rhok", a.overlap)
 for k in range(a.evals):
     t0 = time.perf_counter()
     p = eng.potential(a.style)
