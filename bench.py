@@ -45,7 +45,8 @@ def workload_config(n_mol):
                     "r_cut=10 A COM cutoff, kappa=5.6/L, nk=5, k^2<27 (337 k-vectors)",
         "n_molecules": n_mol,
         "l2": "flushed between timed steps (256 MiB device write); state itself (35 MB) is L2-sized",
-        "sharding": "pair work units (cell pairs) and rho(k) sites split per rank; one NCCL all-reduce of 682 doubles",
+        "sharding": "pair work units (cell pairs) and rho(k) sites split per rank; the 682-double partial vectors are exchanged "
+                    "peer to peer over NVLink (CUDA IPC buffers, k_peer_push/k_peer_sum) or, with --collective nccl, by one all-reduce",
     }
 
 
@@ -241,9 +242,16 @@ def run_ours(args, rank, world, local_rank):
     vec = torch.zeros(nvec, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    from metropolismontecarlo_b200.sharding import sharded_potential
+    from metropolismontecarlo_b200.sharding import setup_peer_exchange, sharded_potential
 
-    def step():   # partial -> NCCL all-reduce over NVLink (8 scalars + 337 complex rho(k)) -> finalize
+    p2p = world > 1 and args.collective == "p2p"
+    if p2p:        # every rank maps every rank's exchange buffer (CUDA IPC); NCCL only carries the 64-byte handles
+        setup_peer_exchange(eng, world)
+
+    def step():
+        if p2p:    # partial -> each rank stores its 682 doubles into every peer's buffer over NVLink -> ordered sum -> finalize
+            return eng.potential_sharded("ewald")
+        # partial -> NCCL all-reduce over NVLink (8 scalars + 337 complex rho(k)) -> finalize
         return sharded_potential(eng, "ewald", vec, world)
 
     def barrier():
@@ -333,6 +341,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
                     "what": "mmc_upload_positions(pinned host soa.coords + moa.COM, Julia layout) + sharded potential + Properties on host"},
             "gpu_launches": int(launches) * world,
+            "collective": (args.collective if world > 1 else None),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -381,6 +390,8 @@ def _main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--molecules", type=int, default=N_MOL_E)
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="exchange of the partial sums at N > 1: NVLink peer-memory kernels (default) or an NCCL all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-moves", action="store_true", help="skip the moves/s legs (configs A/B/C)")
     args = ap.parse_args()

@@ -151,6 +151,23 @@ int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partial
  * next kernel on every rank — repeat mmc_potential_partial, the all-reduce and finalize. */
 #define MMC_RETRY 1
 
+/* ---- the same exchange over NVLink peer memory instead of a library all-reduce ------------ */
+/* Every rank owns an exchange buffer that its peers map through CUDA IPC (one process per GPU on one node).
+ * mmc_peer_export: allocate it and return its 64-byte cudaIpcMemHandle_t; pass every rank's handle to every
+ * other rank (any transport: torch.distributed all_gather_object, MPI, a file) and mmc_peer_import them.
+ * mmc_potential_sharded (all ranks together) = partial sums -> each rank stores its vector into slot `rank` of
+ * every rank's buffer + an epoch flag (k_peer_push) -> wait for the `world` flags, add the slots in rank order
+ * (k_peer_sum) -> finalise.  Same Properties on every rank, bit-identical totals; no collective library call.
+ * _begin/_end are the two halves (begin returns after the launches); mmc_peer_import_ptr/mmc_peer_buffer are
+ * the same-process form used to emulate ranks in one process (tests). */
+int mmc_peer_export(mmc_handle *h, void *ipc_handle_64_bytes);
+int mmc_peer_import(mmc_handle *h, int32_t peer_rank, const void *ipc_handle_64_bytes);
+int mmc_peer_import_ptr(mmc_handle *h, int32_t peer_rank, void *peer_buffer);
+int mmc_peer_buffer(mmc_handle *h, void **buffer);
+int mmc_potential_sharded_begin(mmc_handle *h, int32_t style);
+int mmc_potential_sharded_end(mmc_handle *h, mmc_properties *out);
+int mmc_potential_sharded(mmc_handle *h, int32_t style, mmc_properties *out);
+
 /* ---- fused fast path: one launch, one host sync per trial move ------------------------- */
 /* Same numbers as mmc_lj_mol + mmc_ewald_short (old), mmc_set_molecule, mmc_lj_mol +
  * mmc_ewald_short (new), mmc_recip_move — Ewald/main.jl:491-590. The resident state is not

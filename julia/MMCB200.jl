@@ -121,6 +121,20 @@ end
 volume_accept!(e::Engine) = check(e, ccall((:mmc_volume_accept, LIB), Cint, (Ptr{Cvoid},), e.h))
 volume_reject!(e::Engine) = check(e, ccall((:mmc_volume_reject, LIB), Cint, (Ptr{Cvoid},), e.h))
 
+# sharded full energy with the exchange over NVLink peer memory (one process per GPU; include/mmc_b200.h mmc_peer_*)
+function peer_export(e::Engine)
+    hd = Vector{UInt8}(undef, 64)
+    check(e, ccall((:mmc_peer_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), e.h, hd))
+    hd
+end
+peer_import!(e::Engine, rank::Integer, hd::Vector{UInt8}) =
+    check(e, ccall((:mmc_peer_import, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}), e.h, rank, hd))
+function potential_sharded(e::Engine, style::Cint = EWALD)
+    p = Props()
+    check(e, ccall((:mmc_potential_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Props}), e.h, style, p))
+    p
+end
+
 # Loop() for a whole block of moves in one launch (Ewald/main.jl:487-651); include/mmc_b200.h mmc_loop_run_device.
 # com::Vector{SVector{3,Float64}} (moa.COM), quat::Vector{SVector{4,Float64}}, db: body-fixed site vectors (n_sites x 3),
 # u: the stretch of the caller's uniform stream this block may consume (st.uniforms_used tells how much it did).

@@ -100,6 +100,13 @@ SIGNATURES = {
     "mmc_volume_trial": (C.c_int, [H, C.c_double, C.c_double, C.c_int32, C.POINTER(Properties)]),
     "mmc_volume_accept": (C.c_int, [H]),
     "mmc_volume_reject": (C.c_int, [H]),
+    "mmc_peer_export": (C.c_int, [H, C.c_void_p]),
+    "mmc_peer_import": (C.c_int, [H, C.c_int32, C.c_void_p]),
+    "mmc_peer_import_ptr": (C.c_int, [H, C.c_int32, C.c_void_p]),
+    "mmc_peer_buffer": (C.c_int, [H, C.POINTER(C.c_void_p)]),
+    "mmc_potential_sharded_begin": (C.c_int, [H, C.c_int32]),
+    "mmc_potential_sharded_end": (C.c_int, [H, C.POINTER(Properties)]),
+    "mmc_potential_sharded": (C.c_int, [H, C.c_int32, C.POINTER(Properties)]),
     "mmc_upload_positions": (C.c_int, [H, c_double_p, c_double_p]),
     "mmc_loop_run": (C.c_int, [H, C.POINTER(LoopParams), c_double_p, c_double_p, c_double_p, c_double_p,
                                C.c_int64, C.c_int64, C.c_double, C.c_double, c_uint8_p, c_double_p,

@@ -8,6 +8,7 @@
 #include "kernels_pairs_v4.cuh"
 #include "kernels_pairs_v5.cuh"
 #include "kernels_pairs_v6.cuh"
+#include "kernels_peer.cuh"
 #include "kernels_recip.cuh"
 #include "kernels_upload.cuh"
 
@@ -79,6 +80,18 @@ struct mmc_handle {
     MoveOut mout{};               // host-side fold of the slots of the last move launch
     MoveOut *h_out = &mout;
     ErfPoly move_poly{};          // erf polynomial of the resident box for the per-move kernels
+    // ---- sharded evaluation over peer memory (mmc_peer_*, mmc_potential_sharded_begin/end)
+    double *d_peer_buf = nullptr;                 // [2][world][peer_nvec_cap] doubles, then [2][world] flags
+    size_t peer_nvec_cap = 0;
+    void *peer_base[MMC_PEER_MAX] = {nullptr};    // mapped exchange buffers of all ranks (own: d_peer_buf)
+    bool peer_opened[MMC_PEER_MAX] = {false};     // opened through cudaIpcOpenMemHandle (to be closed)
+    int peer_ready = 0;                           // number of imported ranks
+    unsigned long long peer_epoch = 0;
+    double *d_peer_total = nullptr;               // summed vector
+    int *h_peer_status = nullptr;                 // mapped pinned host word written by k_peer_sum (no extra copy to read it)
+    int *d_peer_status = nullptr;                 // its device alias
+    bool sharded_pending = false;
+    int sharded_style = 0;
     // ---- device-resident block of moves (mmc_loop_run_device)
     unsigned char *d_chain = nullptr;   // [uniforms | quat | db | delta | out | accepted]
     int chain_cluster = 8;              // CTAs (SMs) per cluster for mmc_loop_run_device; 1 = single-CTA kernel
@@ -978,6 +991,9 @@ int mmc_destroy(mmc_handle *h)
     if (h->h_slots) cudaFreeHost(h->h_slots);
     if (h->h_up) cudaFreeHost(h->h_up);
     for (auto &ev : h->tm.ev) cudaEventDestroy(ev);
+    for (int q = 0; q < MMC_PEER_MAX; ++q) if (h->peer_opened[q] && h->peer_base[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
+    dfree(h->d_peer_buf); dfree(h->d_peer_total);
+    if (h->h_peer_status) cudaFreeHost(h->h_peer_status);
     if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -1431,6 +1447,136 @@ int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partial
     rc = finalize(h, style, E, const_cast<double *>(d_partials), h->S.rhok[0], h->S.rhok[1], out);
     if (style == MMC_STYLE_EWALD) h->new_valid = false;
     return rc;
+}
+
+// ---- sharded evaluation with the exchange over NVLink peer memory (kernels_peer.cuh) ----------------------
+static size_t peer_flag_offset_doubles(const mmc_handle *h) { return 2 * (size_t)h->cfg.world * h->peer_nvec_cap; }
+
+int mmc_peer_export(mmc_handle *h, void *handle64)
+{
+    if (!h || !handle64) return MMC_EINVAL;
+    if (h->cfg.world < 1 || h->cfg.world > MMC_PEER_MAX) FAIL(MMC_EINVAL, "peer exchange supports up to 8 ranks");
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->d_peer_buf) {
+        h->peer_nvec_cap = MMC_NSCAL + 2 * 4096;
+        const size_t doubles = peer_flag_offset_doubles(h) + 2 * (size_t)h->cfg.world;
+        CK(cudaMalloc(&h->d_peer_buf, doubles * sizeof(double)));
+        CK(cudaMemset(h->d_peer_buf, 0, doubles * sizeof(double)));
+        CK(cudaMalloc(&h->d_peer_total, h->peer_nvec_cap * sizeof(double)));
+        CK(cudaHostAlloc((void **)&h->h_peer_status, sizeof(int), cudaHostAllocMapped));
+        *h->h_peer_status = 0;
+        CK(cudaHostGetDevicePointer((void **)&h->d_peer_status, h->h_peer_status, 0));
+        h->peer_base[h->cfg.rank] = h->d_peer_buf;
+        h->peer_ready = 1;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t ih;
+    CK(cudaIpcGetMemHandle(&ih, h->d_peer_buf));
+    std::memcpy(handle64, &ih, 64);
+    return MMC_OK;
+}
+
+int mmc_peer_import(mmc_handle *h, int32_t peer_rank, const void *handle64)
+{
+    if (!h || !handle64) return MMC_EINVAL;
+    if (!h->d_peer_buf) FAIL(MMC_ESTATE, "mmc_peer_export first");
+    if (peer_rank < 0 || peer_rank >= h->cfg.world) FAIL(MMC_EINVAL, "peer rank out of range");
+    if (peer_rank == h->cfg.rank || h->peer_base[peer_rank]) return MMC_OK;
+    CK(cudaSetDevice(h->cfg.device));
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, handle64, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_base[peer_rank] = p; h->peer_opened[peer_rank] = true;
+    h->peer_ready += 1;
+    return MMC_OK;
+}
+
+// same-process form (emulated ranks in one process, tests): the peer's buffer by device pointer
+int mmc_peer_import_ptr(mmc_handle *h, int32_t peer_rank, void *peer_buffer)
+{
+    if (!h || !peer_buffer) return MMC_EINVAL;
+    if (!h->d_peer_buf) FAIL(MMC_ESTATE, "mmc_peer_export first");
+    if (peer_rank < 0 || peer_rank >= h->cfg.world) FAIL(MMC_EINVAL, "peer rank out of range");
+    if (peer_rank == h->cfg.rank || h->peer_base[peer_rank]) return MMC_OK;
+    h->peer_base[peer_rank] = peer_buffer;
+    h->peer_ready += 1;
+    return MMC_OK;
+}
+
+int mmc_peer_buffer(mmc_handle *h, void **buffer)
+{
+    if (!h || !buffer) return MMC_EINVAL;
+    if (!h->d_peer_buf) FAIL(MMC_ESTATE, "mmc_peer_export first");
+    *buffer = h->d_peer_buf;
+    return MMC_OK;
+}
+
+static PeerArgs peer_args(mmc_handle *h)
+{
+    PeerArgs P{};
+    const size_t fo = peer_flag_offset_doubles(h);
+    for (int q = 0; q < h->cfg.world; ++q) {
+        P.slot[q] = reinterpret_cast<double *>(h->peer_base[q]);
+        P.flag[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(h->peer_base[q]) + fo);
+    }
+    P.world = h->cfg.world; P.rank = h->cfg.rank;
+    P.nvec = (int)(MMC_NSCAL + 2 * (size_t)std::max(h->S.nkvecs, 1)); P.nvec_cap = (int)h->peer_nvec_cap;
+    P.epoch = h->peer_epoch; P.parity = (int)(h->peer_epoch & 1);
+    return P;
+}
+
+// this rank's partial sums, pushed into every rank's exchange buffer (asynchronous: returns after the launches)
+int mmc_potential_sharded_begin(mmc_handle *h, int32_t style)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = style_check(h, style);
+    if (rc) return rc;
+    if (style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "sharded evaluation is for molecular systems");
+    if (!h->uniform) FAIL(MMC_EINVAL, "sharded evaluation needs a uniform topology");
+    if (h->peer_ready != h->cfg.world) FAIL(MMC_ESTATE, "peer exchange not set up: mmc_peer_export / mmc_peer_import for every rank");
+    if (h->sharded_pending) FAIL(MMC_ESTATE, "mmc_potential_sharded_end has not been called");
+    if ((size_t)(MMC_NSCAL + 2 * std::max(h->S.nkvecs, 1)) > h->peer_nvec_cap) FAIL(MMC_EINVAL, "too many k-vectors for the exchange buffer");
+    { int rcf = flush_pending(h); if (rcf) return rcf; }
+    if ((rc = ensure_vec(h))) return rc;
+    EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
+    if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+    h->peer_epoch += 1;
+    const PeerArgs P = peer_args(h);
+    k_peer_push<<<h->cfg.world, 256, 0, h->stream>>>(P, h->d_vec);
+    LAUNCH_CHECK();
+    h->sharded_pending = true; h->sharded_style = style;
+    return MMC_OK;
+}
+
+// wait for every rank's push, add the slots in rank order, finalise.  MMC_RETRY as mmc_potential_finalize.
+int mmc_potential_sharded_end(mmc_handle *h, mmc_properties *out)
+{
+    if (!h || !out) return MMC_EINVAL;
+    if (!h->sharded_pending) FAIL(MMC_ESTATE, "mmc_potential_sharded_begin first");
+    h->sharded_pending = false;
+    const int style = h->sharded_style;
+    const PeerArgs P = peer_args(h);
+    k_peer_sum<<<1, 256, 0, h->stream>>>(P, h->d_peer_total, h->d_peer_status);
+    LAUNCH_CHECK();
+    EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
+    int rc = finalize(h, style, E, h->d_peer_total, h->S.rhok[0], h->S.rhok[1], out);
+    if (style == MMC_STYLE_EWALD) h->new_valid = false;
+    if (rc < 0) return rc;
+    if (*(volatile int *)h->h_peer_status) FAIL(MMC_ENCCL, "peer exchange: a rank's partial sums did not arrive");   // finalize synchronised the stream
+    return rc;
+}
+
+// all ranks call this together: begin + end, repeated while the pair kernel chain escalates (MMC_RETRY)
+int mmc_potential_sharded(mmc_handle *h, int32_t style, mmc_properties *out)
+{
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int rc = mmc_potential_sharded_begin(h, style);
+        if (rc) return rc;
+        rc = mmc_potential_sharded_end(h, out);
+        if (rc != MMC_RETRY) return rc;
+    }
+    FAIL(MMC_ECUDA, "sharded potential did not converge on a pair kernel (internal)");
 }
 
 int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)

@@ -209,6 +209,37 @@ class Engine:
         rc = self._ck(self.lib.mmc_potential_finalize(self.h, _style(style), C.c_void_p(d_partials_ptr), C.byref(out)))
         return None if rc == 1 else out
 
+    # ---- the sharded evaluation with the exchange over NVLink peer memory (include/mmc_b200.h mmc_peer_*)
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.mmc_peer_export(self.h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def peer_import(self, rank: int, handle: bytes):
+        buf = C.create_string_buffer(handle, 64)
+        self._ck(self.lib.mmc_peer_import(self.h, rank, C.cast(buf, C.c_void_p)))
+
+    def peer_buffer(self) -> int:
+        p = C.c_void_p()
+        self._ck(self.lib.mmc_peer_buffer(self.h, C.byref(p)))
+        return p.value
+
+    def peer_import_ptr(self, rank: int, ptr: int):
+        self._ck(self.lib.mmc_peer_import_ptr(self.h, rank, C.c_void_p(ptr)))
+
+    def potential_sharded_begin(self, style):
+        self._ck(self.lib.mmc_potential_sharded_begin(self.h, _style(style)))
+
+    def potential_sharded_end(self):
+        out = Properties()
+        rc = self._ck(self.lib.mmc_potential_sharded_end(self.h, C.byref(out)))
+        return None if rc == 1 else out
+
+    def potential_sharded(self, style) -> Properties:
+        out = Properties()
+        self._ck(self.lib.mmc_potential_sharded(self.h, _style(style), C.byref(out)))
+        return out
+
     # ---- fused trial move
     def trial_move(self, i: int, com_new, sites_new, style="ewald") -> TrialResult:
         com_new = np.ascontiguousarray(com_new, dtype=np.float64)

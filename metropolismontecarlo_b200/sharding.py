@@ -34,3 +34,15 @@ def sharded_potential(eng, style, vec, world: int, group=None):
         if props is not None:                  # None: MMC_RETRY, every rank switched to the next pair kernel
             return props
     raise RuntimeError("sharded potential did not converge on a pair kernel")
+
+
+def setup_peer_exchange(eng, world: int, group=None):
+    """One process per GPU on one node: every rank exports the CUDA IPC handle of its exchange buffer, the handles
+    travel through torch.distributed (any transport would do), every rank maps every peer's buffer.  After this
+    eng.potential_sharded(style) needs no collective library: partial sums go peer to peer over NVLink."""
+    import torch.distributed as dist
+    mine = eng.peer_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    for r, hd in enumerate(handles):
+        eng.peer_import(r, hd)
