@@ -475,13 +475,14 @@ __global__ void __launch_bounds__(PAIR_BLOCK, (TILE <= 64 ? 4 : 2)) k_pairs_fast
 __global__ void k_pair_reduce(const double4 *partial, int nb, const unsigned int *n_ovl, const int *max_count,
                               const unsigned int *err_flag, double *out)
 {
-    __shared__ double4 s_p[1024];
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_p[i] = partial[i];
-    __syncthreads();
+    // fixed order: thread t adds partials t, t+256, ... ; then the 256 thread sums are folded by block_sum (warp
+    // shuffles, then warp order) — the same tree every run, so the result is reproducible
+    __shared__ double s_red[4 * 8];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < nb; i += 256) { const double4 p = partial[i]; v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w; }
+    block_sum<4, 256>(v, s_red);
     if (threadIdx.x != 0) return;
-    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-    for (int i = 0; i < nb; ++i) { const double4 p = s_p[i]; a += p.x; b += p.y; c += p.z; d += p.w; }
-    out[0] = a; out[1] = b; out[2] = c; out[3] = (double)(*n_ovl); out[5] = d;
+    out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; out[3] = (double)(*n_ovl); out[5] = v[3];
     out[6] = (double)(*max_count); out[7] = (double)(*err_flag);
 }
 
@@ -496,6 +497,7 @@ struct CellArgs {
     int *fill;           // [ncell]  (zeroed)
     int *perm;           // [n_mol] sorted position -> molecule
     int *max_count;      // largest cell population
+    int zl_lo, zl_cnt;   // sharded evaluation: only the z-layers [zl_lo, zl_lo + zl_cnt) (mod ncd) are needed by this rank
 };
 
 __device__ __forceinline__ int cell_coord(double x, double inv_cell, int n)
@@ -519,22 +521,31 @@ __global__ void k_cell_count(CellArgs A)
 // exclusive scan of count[0..ncell) into start[0..ncell], single CTA
 __global__ void k_cell_scan(CellArgs A, int ncell)
 {
-    __shared__ int s_part[1024];
-    const int tid = threadIdx.x, nth = blockDim.x;
+    __shared__ int s_warp[32];
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int per = (ncell + nth - 1) / nth;
     const int lo = tid * per, hi = min(ncell, lo + per);
     int s = 0, mx = 0;
     for (int i = lo; i < hi; ++i) { const int c = A.count[i]; s += c; mx = max(mx, c); }
-    if (mx > 0) atomicMax(A.max_count, mx);
-    s_part[tid] = s;
+    // block-wide exclusive scan of the per-thread sums: shuffle scan inside each warp, then across the warp totals
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0 && mx > 0) atomicMax(A.max_count, mx);
     __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int t = 0; t < nth; ++t) { const int v = s_part[t]; s_part[t] = run; run += v; }
-        A.start[ncell] = run;
+    if (warp == 0) {
+        const int nw = nth >> 5;
+        int w = lane < nw ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+        s_warp[lane] = wi - w;                               // exclusive prefix of the warp totals
+        if (lane == 31) A.start[ncell] = wi;
     }
     __syncthreads();
-    int run = s_part[tid];
+    int run = s_warp[warp] + incl - s;
     for (int i = lo; i < hi; ++i) { A.start[i] = run; run += A.count[i]; }
 }
 
@@ -553,6 +564,11 @@ __global__ void k_cell_sort(CellArgs A, int ncell)
 {
     const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (cell >= ncell) return;
+    {   // a rank of a sharded evaluation only orders the cells it will read
+        const int z = cell / (A.ncd * A.ncd);
+        int dz = z - A.zl_lo; if (dz < 0) dz += A.ncd;
+        if (dz >= A.zl_cnt) return;
+    }
     const int lo = A.start[cell], n = A.start[cell + 1] - lo;
     // rank sort through registers: n is a few dozen
     int mine[8], rank[8];
@@ -587,6 +603,7 @@ struct GatherArgs {
     const int *cell_of;     // [n_mol] cell of each molecule (original index)
     int ncd;
     double edge;            // box_new / ncd
+    int zl_lo, zl_cnt;      // cell mode: gather only molecules whose cell lies in z-layers [zl_lo, zl_lo + zl_cnt) (mod ncd)
 };
 
 // cell-sorted copy of the state; for a volume trial the COMs are scaled by f and the sites
@@ -597,6 +614,11 @@ __global__ void k_gather(GatherArgs A)
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= A.n_mol) return;
     const int m = A.perm ? A.perm[p] : p;
+    if (A.perm && A.zl_cnt < A.ncd) {      // sharded evaluation: this rank reads its unit range and one layer above it
+        const int z = A.cell_of[m] / (A.ncd * A.ncd);
+        int dz = z - A.zl_lo; if (dz < 0) dz += A.ncd;
+        if (dz >= A.zl_cnt) return;
+    }
     A.ovl[p] = 0u;
     const double4 c = A.com[m];
     double4 cn = c;

@@ -87,13 +87,14 @@ __global__ void __launch_bounds__(RHOK_BLOCK) k_rhok_partial(RhokArgs A)
     }
 }
 
-// ρ(k) = Σ_b partial[b][k] → out[k].  blockDim = (64 k, 4 slices): each slice folds a contiguous
-// quarter of the CTAs in CTA order, the four slice sums are added in slice order (deterministic).
+// ρ(k) = Σ_b partial[b][k] → out[k].  blockDim = (32 k, 32 slices): each slice folds a contiguous 1/32 of the
+// CTAs in CTA order, the 32 slice sums are added in slice order (deterministic); many short dependent chains
+// instead of four long ones (the kernel is pure load latency).
 __global__ void k_rhok_reduce(const double2 *partial, int nb, int nkvecs, double2 *out)
 {
-    __shared__ double2 s_s[4][64];
-    const int k = blockIdx.x * 64 + threadIdx.x, sl = threadIdx.y;
-    const int b0 = (int)((long long)nb * sl / 4), b1 = (int)((long long)nb * (sl + 1) / 4);
+    __shared__ double2 s_s[32][33];
+    const int k = blockIdx.x * 32 + threadIdx.x, sl = threadIdx.y;
+    const int b0 = (int)((long long)nb * sl / 32), b1 = (int)((long long)nb * (sl + 1) / 32);
     double re = 0.0, im = 0.0;
     if (k < nkvecs)
         for (int b = b0; b < b1; ++b) {
@@ -104,7 +105,7 @@ __global__ void k_rhok_reduce(const double2 *partial, int nb, int nkvecs, double
     __syncthreads();
     if (sl == 0 && k < nkvecs) {
         double2 t = s_s[0][threadIdx.x];
-        for (int j = 1; j < 4; ++j) { t.x += s_s[j][threadIdx.x].x; t.y += s_s[j][threadIdx.x].y; }
+        for (int j = 1; j < 32; ++j) { t.x += s_s[j][threadIdx.x].x; t.y += s_s[j][threadIdx.x].y; }
         out[k] = t;
     }
 }

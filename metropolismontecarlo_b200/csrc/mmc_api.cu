@@ -436,7 +436,7 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
     }
     LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[3], st);
-    k_rhok_reduce<<<(nkv + 63) / 64, dim3(64, 4), 0, st>>>(h->d_rhok_partial, nb, nkv, out);
+    k_rhok_reduce<<<(nkv + 31) / 32, dim3(32, 32), 0, st>>>(h->d_rhok_partial, nb, nkv, out);
     LAUNCH_CHECK();
     return MMC_OK;
 }
@@ -585,6 +585,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     }
     const int tb = 256, gm = (S.n_mol + tb - 1) / tb;
     long long n_units;
+    int zl_lo = 0, zl_cnt = 1 << 30;
     if (cells) {
         const int ncell = ncd * ncd * ncd;
         if (ncell > h->ncell_cap) {
@@ -597,8 +598,21 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         bind_flags(h, ncell);
         CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * (8 + 2 * (size_t)ncell), h->stream));
         // fractional COM coordinates are invariant under the volume scaling: bin the resident state
+        // a rank of a sharded evaluation reads the home cells of its unit range and their half-shell neighbours: z-layers
+        // [z(first home cell), z(last home cell) + 1]; only those are ordered and gathered (units are (cell, group) triples)
+        // Units are (cell, group) or (cell, slot) tuples, U per cell, dealt in contiguous ranges: for every U the first home
+        // cell of rank r is floor(ncell·r/world) and the last one is at most ceil(ncell·(r+1)/world) − 1.
+        zl_lo = 0; zl_cnt = ncd;
+        if (E.world > 1 && E.f == 1.0) {
+            const int c0 = (int)((long long)ncell * E.rank / E.world);
+            const int c1 = (int)(((long long)ncell * (E.rank + 1) + E.world - 1) / E.world) - 1;
+            if (c1 >= c0) {
+                zl_lo = c0 / (ncd * ncd);
+                zl_cnt = std::min(ncd, c1 / (ncd * ncd) - zl_lo + 2);
+            }
+        }
         CellArgs C{S.com, S.n_mol, ncd, (double)ncd / S.box, h->d_cell_of, h->d_count, h->d_start,
-                   h->d_fill, h->d_perm, h->d_maxcount};
+                   h->d_fill, h->d_perm, h->d_maxcount, zl_lo, zl_cnt};
         k_cell_count<<<gm, tb, 0, h->stream>>>(C); LAUNCH_CHECK();
         k_cell_scan<<<1, 1024, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
         k_cell_fill<<<gm, tb, 0, h->stream>>>(C); LAUNCH_CHECK();
@@ -625,7 +639,8 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     }
     GatherArgs G{S.com, S.site, cells ? h->d_perm : nullptr, S.n_mol, US, E.f, h->d_scom, h->d_ssite,
                  reinterpret_cast<unsigned long long *>(h->d_maxdev), h->d_ovl,
-                 want_rows ? h->d_mrows : nullptr, want_rows ? h->d_gf : nullptr, h->d_cell_of, ncd, E.box / ncd};
+                 want_rows ? h->d_mrows : nullptr, want_rows ? h->d_gf : nullptr, h->d_cell_of, ncd, E.box / ncd,
+                 zl_lo, std::min(zl_cnt, ncd)};
     k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
     if (style == MMC_STYLE_EWALD && h->overlap_rhok && !rhok_forked) {      // volume trial: scaled, sorted sites
