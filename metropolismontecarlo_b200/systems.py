@@ -190,6 +190,93 @@ def spce_lattice(n_mol: int, rho: float = 0.033101144, seed: int = 11234) -> Mol
     return MolecularSystem(coords, charge, atype, first, last, com, eps, sig, float(L), db, quat)
 
 
+# ------------------------------------------------------------------ GROMACS .top / .pdb subset (input formats)
+R_GAS = 8.3144621e-3      # kJ mol^-1 K^-1, Ewald/constants.jl:11 (ε[kJ/mol] / R → K, main.jl:185)
+
+
+def read_top(path) -> dict:
+    """The subset of a GROMACS topology the reference's ReadTopFile uses (Ewald/setup.jl:30-390) for rigid
+    molecules: [ atomtypes ] (name, mass, charge, σ [nm], ε [kJ/mol]) and, per [ moleculetype ], its [ atoms ]
+    (type, charge, mass) and the [ molecules ] counts.  Comments (;) and preprocessor lines (#) are skipped."""
+    section, types, mols, counts, cur = None, {}, {}, [], None
+    for raw in Path(path).read_text().splitlines():
+        line = raw.split(";", 1)[0].strip()
+        if not line or line.startswith("#"):
+            continue
+        if line.startswith("["):
+            section = line.strip("[] \t").lower()
+            continue
+        t = line.split()
+        if section == "atomtypes":            # name bond_type mass charge ptype sigma epsilon   (7 columns, as water.top)
+            types[t[0]] = {"mass": float(t[-5]), "charge": float(t[-4]), "sigma_nm": float(t[-2]), "eps_kj": float(t[-1])}
+        elif section == "moleculetype":
+            cur = t[0]
+            mols[cur] = []
+        elif section == "atoms" and cur is not None:   # nr type resnr residue atom cgnr charge mass
+            mols[cur].append({"type": t[1], "name": t[4], "charge": float(t[6]), "mass": float(t[7])})
+        elif section == "molecules":
+            counts.append((t[0], int(t[1])))
+    return {"atomtypes": types, "molecules": mols, "counts": counts}
+
+
+def read_pdb(path) -> np.ndarray:
+    """ATOM/HETATM coordinates [Å] of a PDB file (columns 31-54), as the reference's ReadPDB (Ewald/setup.jl) uses them."""
+    xyz = []
+    for line in Path(path).read_text().splitlines():
+        if line.startswith(("ATOM", "HETATM")):
+            xyz.append([float(line[30:38]), float(line[38:46]), float(line[46:54])])
+    return np.array(xyz, dtype=np.float64)
+
+
+def tables_from_types(eps_kj, sig_nm):
+    """vdwTable of Ewald/main.jl:183-186: geometric ε, arithmetic σ (structs.jl:342-346), then ε/R → K, σ·10 → Å."""
+    e = np.asarray(eps_kj, dtype=np.float64)
+    g = np.asarray(sig_nm, dtype=np.float64)
+    eps = np.sqrt(e[:, None] * e[None, :]) / R_GAS
+    sig = (g[:, None] + g[None, :]) / 2 * 10.0
+    return eps, sig
+
+
+def rigid_lattice(model: dict, n_mol: int, rho: float = 0.033101144, seed: int = 11234) -> MolecularSystem:
+    """A box of one rigid molecule type the way the reference's "crystal" start builds it (Ewald/main.jl:156-189):
+    body frame = PDB coordinates shifted to the COM (main.jl:163-164), COMs on InitCubicGrid, random quaternions,
+    sites = COM + MATMUL(A(q), db).  `model`: {"types": [names], "eps_kj", "sig_nm" per type, "atoms": [(type
+    index, charge, mass)], "xyz": body coordinates in Å}."""
+    rng = np.random.default_rng(seed)
+    atoms = model["atoms"]
+    S = len(atoms)
+    mass = np.array([a[2] for a in atoms])
+    xyz = np.asarray(model["xyz"], dtype=np.float64)
+    dbm = xyz - (xyz * mass[:, None]).sum(axis=0) / mass.sum()
+    com, L = init_cubic_grid(n_mol, rho)
+    quat = random_quaternions(n_mol, rng)
+    coords = np.empty((n_mol * S, 3))
+    for m in range(n_mol):
+        coords[S * m:S * m + S] = com[m] + matmul_ref(q_to_a(quat[m]), dbm)
+    charge = np.tile(np.array([a[1] for a in atoms]), n_mol)
+    atype = np.tile(np.array([a[0] + 1 for a in atoms], dtype=np.int64), n_mol)
+    first = np.arange(n_mol, dtype=np.int64) * S + 1
+    eps, sig = tables_from_types(model["eps_kj"], model["sig_nm"])
+    return MolecularSystem(coords, charge, atype, first, first + S - 1, com, eps, sig, float(L), np.tile(dbm, (n_mol, 1)), quat)
+
+
+def model_from_files(top_path, pdb_path, molname=None) -> dict:
+    """{types, eps_kj, sig_nm, atoms, xyz} of one molecule type from a .top and its .pdb (what main.jl:156-171 reads)."""
+    top = read_top(top_path)
+    molname = molname or next(iter(top["molecules"]))
+    names = list(top["atomtypes"])
+    atoms = [(names.index(a["type"]), a["charge"], a["mass"]) for a in top["molecules"][molname]]
+    return {"types": names, "eps_kj": [top["atomtypes"][n]["eps_kj"] for n in names],
+            "sig_nm": [top["atomtypes"][n]["sigma_nm"] for n in names], "atoms": atoms,
+            "xyz": read_pdb(pdb_path)[:len(atoms)].tolist()}
+
+
+def tip3p_model() -> dict:
+    """TIP3P as the reference ships it (water.top + tip3p.pdb at the repository root), from the committed fixture."""
+    import json
+    return json.loads((Path(__file__).resolve().parent.parent / "tests" / "golden" / "tip3p_model.json").read_text())
+
+
 @dataclass
 class AtomicSystem:
     """Monatomic/mainMonatomic.jl Requirements(r, ϵ, σ, box, r_cut)."""

@@ -45,6 +45,14 @@ def main():
     assert box == out["box4"] and np.array_equal(xyz, out["xyz4"]), "coord750 != config 4"
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, {k: getattr(v, "shape", None) for k, v in out.items()})
+    # TIP3P model parameters, parsed from the reference's own input files (repository root: water.top, tip3p.pdb —
+    # what Ewald/main.jl:156-157 opens) by the product's readers; numbers only, no reference text is copied
+    import json
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
+    from metropolismontecarlo_b200.systems import model_from_files
+    model = model_from_files(REF.parent / "water.top", REF.parent / "tip3p.pdb", "WAT")
+    (OUT.parent / "tip3p_model.json").write_text(json.dumps(model, indent=1) + "\n")
+    print("wrote tip3p_model.json", model)
 
 
 if __name__ == "__main__":

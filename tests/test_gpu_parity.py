@@ -453,3 +453,38 @@ def test_peer_exchange_emulated_ranks(c750):
                 assert p.energy == props[0].energy and p.recip == props[0].recip     # same order of summation on every rank
         for e in engs:
             e.close()
+
+
+def test_tip3p_1000_molecules_reference_run():
+    """The reference's own shipped run (Ewald/main.jl "crystal" branch): 1000 TIP3P molecules (water.top + tip3p.pdb) on
+    InitCubicGrid at rho = 0.033101144, random orientations, r_cut = 10, kappa = 5.6/L, 337 k-vectors."""
+    from metropolismontecarlo_b200.energy import LoopParams, julia_rand, water_engine
+    ms = systems.rigid_lattice(systems.tip3p_model(), 1000)
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    eng = water_engine(ms, 10.0)
+    for style, want in (("ewald", ora.potential_ewald(s, ew, 10.0, 10.0, ms.box, 8)),
+                        ("wolf", ora.potential_wolf(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8))):
+        _check_props(eng.potential(style), want)
+    for i in (1, 17, 500, 1000):
+        lj, vir = eng.LJ_poly_ΔU(i)
+        e, v, ovl = eng.EwaldShort(i)
+        wl = ora.LJ_poly_dU(i, s, 10.0, ms.box)
+        we = ora.EwaldShort(i, s, ew, 10.0, ms.box)
+        assert rel(lj, wl[0]) < 1e-12 and rel(vir, wl[1]) < 1e-11 and rel(e, we[0]) < 1e-12 and bool(ovl) == bool(we[2])
+    # 3000 moves of the reference loop: per-move protocol, block offload and oracle agree move by move
+    u = julia_rand(11234, 8 * 3000)
+    p0 = ora.potential_ewald(s, ew, 10.0, 10.0, ms.box, 8)
+    prm = ora.LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 10.0, 10.0, ms.box, 0, 1)
+    quat_o = ms.quat.copy()
+    rc_o, acc_o, del_o, st_o = ora.loop(s, ew, ms.db, quat_o, prm, u, 3000, p0.energy, p0.virial)
+    for device in (False, True):
+        eng.upload_system(ms, 10.0, 10.0)
+        g0 = eng.potential("ewald")
+        com, quat = ms.com.copy(), ms.quat.copy()
+        rc_g, acc_g, del_g, st_g = eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 0, 1), com, quat, ms.db, u, 3000,
+                                                g0.energy, g0.virial, device=device)
+        assert rc_g == 0 and np.array_equal(acc_g, acc_o) and st_g.uniforms_used == st_o.uniforms_used
+        assert np.abs(com - s.com).max() < 1e-11
+        assert rel(st_g.total_energy, eng.potential("ewald").energy) < 1e-10
+    eng.close()
