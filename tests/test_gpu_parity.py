@@ -488,3 +488,20 @@ def test_tip3p_1000_molecules_reference_run():
         assert np.abs(com - s.com).max() < 1e-11
         assert rel(st_g.total_energy, eng.potential("ewald").energy) < 1e-10
     eng.close()
+
+
+def test_pairs_v6_two_pass_groups():
+    """k_pairs_v6's two-pass path: 3200 SPC/E molecules on the 15³ lattice give 4 cells of 11.5 Å per edge holding
+    27 … 64 molecules (3 or 4 lattice planes per cell and direction), so 5-slot groups of up to 288 molecules exceed the
+    256-row B tile and are evaluated in two passes.  Totals and pair count against the oracle."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.spce_lattice(3200)
+    eng = water_engine(ms, 10.0)
+    got = eng.potential("ewald")
+    info = eng.last_eval_info()
+    assert info["pair_kernel"] == "k_pairs_v6" and info["cells_per_dim"] == 4, info
+    s = ora_system(ms)
+    want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
+    _check_props(got, want)
+    assert info["pairs_in_cutoff"] == npr_pairs_in_cutoff(ms.com, ms.box, 10.0)
+    eng.close()
