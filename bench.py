@@ -186,6 +186,39 @@ def moves_benchmarks(n_moves=10_000):
                                        "gpu_launches": 1, "what": "mmc_loop_run_device: 10^4 moves in one launch, "
                                        "uniforms H2D + results D2H inside the timed region, same accept/reject record"}}
         eng.close()
+    # ---- config D: 4000 SPC/E, NPT with Ewald — a volume trial is one full pair + k-space recompute at the new box
+    # (Ewald/volumeChange.jl:50-147: scale COMs, kappa = 5.6/L', cfac and rho(k) rebuilt); molecule moves in between go
+    # through the per-move protocol (4000 molecules do not fit one SM's shared memory)
+    ms_d = systems.spce_lattice(4000)
+    eng = water_engine(ms_d, RC)
+    p0 = eng.potential("ewald")
+    rng = np.random.default_rng(11234)
+    vol0 = ms_d.box ** 3
+    boxes = [(vol0 + (rng.random() - 0.5) * 0.01 * vol0) ** (1.0 / 3.0) for _ in range(60)]   # vmax = 0.01 V
+    for L in boxes[:10]:
+        eng.volume_trial(L, systems.ALPHA / L, "ewald"); eng.volume_reject()
+    l0 = eng.counters().kernel_launches
+    t0 = time.perf_counter()
+    for L in boxes[10:]:
+        pv = eng.volume_trial(L, systems.ALPHA / L, "ewald")
+        eng.volume_reject()
+    dt_v = (time.perf_counter() - t0) / 50
+    launches_v = (eng.counters().kernel_launches - l0) / 50
+    info_d = eng.last_eval_info()
+    com, quat = ms_d.com.copy(), ms_d.quat.copy()
+    n_d = 2000
+    t0 = time.perf_counter()
+    rc, acc, delta, st = eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 0, 1), com, quat, ms_d.db, u, n_d,
+                                      p0.energy, p0.virial)
+    dt_m = (time.perf_counter() - t0) / n_d
+    sweep = ms_d.n_mol * dt_m + dt_v                      # one NPT cycle: N molecule moves + one volume trial
+    out["D_spce4000_npt_ewald"] = {"volume_trial_evals_per_s": 1.0 / dt_v, "ms_per_volume_trial": 1e3 * dt_v,
+                                   "gpu_launches_per_volume_trial": launches_v, "pair_kernel": info_d["pair_kernel"],
+                                   "moves_per_s": 1.0 / dt_m, "us_per_move": 1e6 * dt_m,
+                                   "blended_moves_per_s": (ms_d.n_mol + 1) / sweep,
+                                   "what": "volume trial = host call to result on host (scale + full Ewald energy at the new box, "
+                                           "random box per trial, vmax = 0.01 V); blended = 4000 molecule moves + 1 volume trial"}
+    eng.close()
     at = systems.lj_lattice(32_000, 0.75, 2.5)
     eng = Engine()
     eng.upload_atoms(at)
