@@ -211,11 +211,28 @@ def moves_benchmarks(n_moves=10_000):
     rc, acc, delta, st = eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 0, 1), com, quat, ms_d.db, u, n_d,
                                       p0.energy, p0.virial)
     dt_m = (time.perf_counter() - t0) / n_d
+    # block offload: one sweep (4000 moves) per launch; 4000 molecules are sliced over the cluster's 8 SMs
+    eng.upload_system(ms_d, RC, RC)
+    p0 = eng.potential("ewald")
+    com, quat = ms_d.com.copy(), ms_d.quat.copy()
+    eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 0, 1), com, quat, ms_d.db, u, 500, p0.energy, p0.virial, device=True)
+    eng.upload_system(ms_d, RC, RC)
+    p0 = eng.potential("ewald")
+    com, quat = ms_d.com.copy(), ms_d.quat.copy()
+    t0 = time.perf_counter()
+    rc_b, acc_b, delta_b, st_b = eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 0, 1), com, quat, ms_d.db, u, n_moves,
+                                              p0.energy, p0.virial, device=True)
+    dt_b = (time.perf_counter() - t0) / n_moves
+    assert np.array_equal(acc, acc_b[:n_d]), "device block of moves diverged from the per-move protocol"
     sweep = ms_d.n_mol * dt_m + dt_v                      # one NPT cycle: N molecule moves + one volume trial
+    sweep_b = ms_d.n_mol * dt_b + dt_v
     out["D_spce4000_npt_ewald"] = {"volume_trial_evals_per_s": 1.0 / dt_v, "ms_per_volume_trial": 1e3 * dt_v,
                                    "gpu_launches_per_volume_trial": launches_v, "pair_kernel": info_d["pair_kernel"],
                                    "moves_per_s": 1.0 / dt_m, "us_per_move": 1e6 * dt_m,
                                    "blended_moves_per_s": (ms_d.n_mol + 1) / sweep,
+                                   "block_offload": {"moves_per_s": 1.0 / dt_b, "us_per_move": 1e6 * dt_b,
+                                                     "blended_moves_per_s": (ms_d.n_mol + 1) / sweep_b,
+                                                     "what": "mmc_loop_run_device, state sliced over the 8 CTAs of the cluster"},
                                    "what": "volume trial = host call to result on host (scale + full Ewald energy at the new box, "
                                            "random box per trial, vmax = 0.01 V); blended = 4000 molecule moves + 1 volume trial"}
     eng.close()

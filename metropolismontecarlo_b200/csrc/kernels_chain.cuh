@@ -52,6 +52,7 @@ struct ChainArgs {
     ChainOut *out;
 };
 
+// n_mol: molecules held by ONE CTA (all of them for k_chain, a slice's capacity (N + C - 1) / C + 1 for k_chains)
 __host__ __device__ inline size_t chain_smem_bytes(int n_mol, int S, int nk)
 {
     return sizeof(double4) * ((size_t)n_mol * S + n_mol) + (size_t)nk * (2 * sizeof(double2) + sizeof(int4) + sizeof(double)) +
@@ -561,17 +562,20 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
 // Cluster barrier: generators arrive as soon as the move starts (they publish nothing) and wait at its end.
 #define CHAINS_WORKERS 192
 #define CHAINS_WWARPS (CHAINS_WORKERS / 32)
+#define CHAINS_MAXIT 8      // partner molecules per CTA <= CHAINS_MAXIT * CHAINS_WORKERS
 
 template <int S>
 struct ChainCand {
-    double com[3], site[S][3], ei[4];
+    double com[3], site[S][3], ei[4];            // trial COM, trial sites, trial quaternion
+    double ocom[3], osite[S][3], q[S];           // molecule's resident COM, sites and charges (from L2: its owner is another SM)
     long long pos_end;
     int is_trans, ret, dry, pad;
 };
 
 __device__ __forceinline__ void chain_worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CHAINS_WORKERS) : "memory"); }
 
-template <int S, int DEG>
+// SLICED = false: every CTA holds the whole system (fastest: the molecule about to move is on chip); true: a slice per CTA
+template <int S, int DEG, bool SLICED>
 __global__ void __launch_bounds__(CHAINC_THREADS, 1)
 k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs A, const __grid_constant__ ErfPoly P)
 {
@@ -579,10 +583,13 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
     namespace cg = cooperative_groups;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = Sy.n_mol, NK = A.style_recip ? Sy.nkvecs : 0;
-    double4 *s_site = reinterpret_cast<double4 *>(smem_raw);
-    double4 *s_com = s_site + (size_t)N * S;
+    namespace cgx = cooperative_groups;
+    const int C0 = (int)cgx::this_cluster().num_blocks();
+    const int n_cap = SLICED ? (N + C0 - 1) / C0 + 1 : N;               // molecules held by this CTA (chain_smem_bytes: same formula)
+    double4 *s_site = reinterpret_cast<double4 *>(smem_raw);            // SLICED: this CTA's slice of the molecules only
+    double4 *s_com = s_site + (size_t)n_cap * S;
     double2 *s_rhok[2];
-    s_rhok[0] = reinterpret_cast<double2 *>(s_com + N);
+    s_rhok[0] = reinterpret_cast<double2 *>(s_com + n_cap);
     s_rhok[1] = s_rhok[0] + NK;
     int4 *s_kvec = reinterpret_cast<int4 *>(s_rhok[1] + NK);
     double *s_cfac = reinterpret_cast<double *>(s_kvec + NK);
@@ -592,7 +599,7 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
     __shared__ cplx s_tabc[2][2][2][S][3][MMC_MAX_NK + 1];             // [move parity][candidate][old/new][site][xyz][power]
     __shared__ double s_ug[2][32], s_gq[2][4], s_gdb[2][S * 3];        // per generator: uniform window, quaternion, body frame
     __shared__ int s_type[S];
-    __shared__ int s_wcount[2 * CHAINS_WWARPS];
+    __shared__ int s_wcount[CHAINS_MAXIT * CHAINS_WWARPS];
     __shared__ double s_red[9 * 8];
     __shared__ double s_xchg[2][9][CHAINC_MAXC];                       // [move parity][value][source rank], written remotely
     __shared__ double s_tot[9];
@@ -614,10 +621,14 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
     const int j_lo = (int)((long long)N * rank / C), j_hi = (int)((long long)N * (rank + 1) / C);
     const int k_lo = (int)((long long)NK * rank / C), k_hi = (int)((long long)NK * (rank + 1) / C);
     const int n_loc = j_hi - j_lo;
+    const int s_lo = SLICED ? j_lo : 0;                                 // first molecule held in shared memory
     const double twopi = 2.0 * 3.141592653589793;
 
-    for (int t = tid; t < N * S; t += CHAINC_THREADS) s_site[t] = Sy.site[t];
-    for (int t = tid; t < N; t += CHAINC_THREADS) s_com[t] = Sy.com[t];
+    {
+        const int n_hold = SLICED ? n_loc : N;
+        for (int t = tid; t < n_hold * S; t += CHAINC_THREADS) s_site[t] = Sy.site[(size_t)s_lo * S + t];
+        for (int t = tid; t < n_hold; t += CHAINC_THREADS) s_com[t] = Sy.com[s_lo + t];
+    }
     for (int t = tid; t < NK; t += CHAINC_THREADS) {
         s_rhok[A.cur][t] = Sy.rhok[A.cur][t]; s_rhok[A.cur ^ 1][t] = Sy.rhok[A.cur][t];
         s_kvec[t] = Sy.kvec[t]; s_cfac[t] = Sy.cfac[t];
@@ -643,9 +654,16 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
             double qv = 0.0;
             if (lane < 4) qv = myquat[4 * i + lane];
             else if (lane < 4 + S * 3) qv = A.db[(size_t)i * S * 3 + lane - 4];
+            // the molecule's resident COM and sites come from L2 (its owner is another SM): lanes 16..16+S
+            double4 rv = make_double4(0, 0, 0, 0);
+            if (lane == 16) rv = SLICED ? ldcg4(&Sy.com[i]) : s_com[i];
+            else if (lane > 16 && lane <= 16 + S) rv = SLICED ? ldcg4(&Sy.site[(size_t)i * S + lane - 17]) : s_site[i * S + lane - 17];
             s_ug[g][lane] = uv;
             if (lane < 4) s_gq[g][lane] = qv;
             else if (lane < 4 + S * 3) s_gdb[g][lane - 4] = qv;
+            ChainCand<S> &T0 = s_cand[par][g];
+            if (lane == 16) { T0.ocom[0] = rv.x; T0.ocom[1] = rv.y; T0.ocom[2] = rv.z; }
+            else if (lane > 16 && lane <= 16 + S) { T0.osite[lane - 17][0] = rv.x; T0.osite[lane - 17][1] = rv.y; T0.osite[lane - 17][2] = rv.z; T0.q[lane - 17] = rv.w; }
         }
         __syncwarp();
         ChainCand<S> &T = s_cand[par][g];
@@ -661,7 +679,7 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
             };
             const double dr_max = D.dr_max, dphi_max = D.dphi_max;
             const double nq0 = s_gq[g][0], nq1 = s_gq[g][1], nq2 = s_gq[g][2], nq3 = s_gq[g][3];
-            const double4 c0 = s_com[i];
+            const double4 c0 = make_double4(T.ocom[0], T.ocom[1], T.ocom[2], 0.0);
             double rnew[3] = {c0.x, c0.y, c0.z};
             double e0 = nq0, e1 = nq1, e2 = nq2, e3 = nq3;
             int ret = 0, is_trans = 1;
@@ -723,7 +741,7 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
         if (A.style_recip && lane < 2 * S * 3) {            // ewalds.jl:770-795 for the old and the trial sites
             const int cfg = lane / (S * 3), rem = lane - cfg * S * 3, l = rem / 3, d = rem - 3 * l;
             double x;
-            if (cfg == 0) { const double4 s = s_site[i * S + l]; x = d == 0 ? s.x : (d == 1 ? s.y : s.z); }
+            if (cfg == 0) x = T.osite[l][d];
             else x = T.site[l][d];
             cplx e1;
             sincos(twopi * x / L, &e1.im, &e1.re);
@@ -758,17 +776,17 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
             cluster.barrier_wait();
         } else {
             // ================= step 1: COM gate for the old and the trial position (this CTA's partners)
-            const double4 co = s_com[i];
+            const double4 co = make_double4(T.ocom[0], T.ocom[1], T.ocom[2], 0.0);
             const double cnx = T.com[0], cny = T.com[1], cnz = T.com[2];
-            int myfl[2]; unsigned mymask[2];
+            int myfl[CHAINS_MAXIT]; unsigned mymask[CHAINS_MAXIT];
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
+            for (int it = 0; it < CHAINS_MAXIT; ++it) {
                 myfl[it] = 0; mymask[it] = 0;
                 if (it * CHAINS_WORKERS < n_loc) {
                     const int j = j_lo + it * CHAINS_WORKERS + tid;
                     int fl = 0;
                     if (j < j_hi && j != i) {
-                        const double4 cj = s_com[j];
+                        const double4 cj = s_com[j - s_lo];
                         {
                             const double rx = min_image(co.x, cj.x, L), ry = min_image(co.y, cj.y, L), rz = min_image(co.z, cj.z, L);
                             const double r2 = add(add(mul(rx, rx), mul(ry, ry)), mul(rz, rz));
@@ -789,18 +807,17 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
             }
             chain_worker_bar();
             int n_in = 0;
-            {   // exclusive prefix of the per-(iteration, warp) counts, in index order
-                int base[2] = {0, 0};
+            {   // ordered compaction: survivors of iteration `it`, warp `warp` go after everything with a smaller (it, warp)
 #pragma unroll
-                for (int k = 0; k < 2 * CHAINS_WWARPS; ++k) {
-                    const int c = s_wcount[k];
-                    if (k < warp) base[0] += c;
-                    if (k < CHAINS_WWARPS + warp) base[1] += c;
-                    n_in += c;
+                for (int it = 0; it < CHAINS_MAXIT; ++it) {
+                    if (it * CHAINS_WORKERS < n_loc) {
+                        int below = 0, tot = 0;
+#pragma unroll
+                        for (int w = 0; w < CHAINS_WWARPS; ++w) { const int c = s_wcount[it * CHAINS_WWARPS + w]; tot += c; if (w < warp) below += c; }
+                        if (myfl[it]) s_list[n_in + below + __popc(mymask[it] & lt)] = make_int2(j_lo + it * CHAINS_WORKERS + tid, myfl[it]);
+                        n_in += tot;
+                    }
                 }
-#pragma unroll
-                for (int it = 0; it < 2; ++it)
-                    if (myfl[it]) s_list[base[it] + __popc(mymask[it] & lt)] = make_int2(j_lo + it * CHAINS_WORKERS + tid, myfl[it]);
             }
             chain_worker_bar();
 
@@ -812,13 +829,13 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                 const int2 e = s_list[jj];
                 const int j = e.x, fl = (e.y >> (2 * cfg)) & 3;
                 if (!fl) continue;
-                double4 sa = s_site[i * S + a];
+                double4 sa = make_double4(T.osite[a][0], T.osite[a][1], T.osite[a][2], T.q[a]);
                 double cix = co.x, ciy = co.y, ciz = co.z;
                 if (cfg) { sa.x = T.site[a][0]; sa.y = T.site[a][1]; sa.z = T.site[a][2]; cix = cnx; ciy = cny; ciz = cnz; }
                 double r2[S], dx[S], dy[S], dz[S], qq[S], ri[S];
 #pragma unroll
                 for (int b = 0; b < S; ++b) {
-                    const double4 sb = s_site[j * S + b];
+                    const double4 sb = s_site[(j - s_lo) * S + b];
                     dx[b] = min_image(sa.x, sb.x, L); dy[b] = min_image(sa.y, sb.y, L); dz[b] = min_image(sa.z, sb.z, L);
                     r2[b] = dx[b] * dx[b] + dy[b] * dy[b] + dz[b] * dz[b];
                     qq[b] = sa.w * sb.w;
@@ -827,7 +844,7 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                 double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
                 if (fl & 1) {                               // energy.jl:270-282
                     const int ta = s_type[a];
-                    const double4 cj = s_com[j];
+                    const double4 cj = s_com[j - s_lo];
                     const double rijx = min_image(cix, cj.x, L), rijy = min_image(ciy, cj.y, L), rijz = min_image(ciz, cj.z, L);
 #pragma unroll
                     for (int b = 0; b < S; ++b) {
@@ -891,7 +908,7 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                     for (int l = 0; l < S; ++l) {
                         const cplx tn = cmul(cmul(s_tabc[par][sel][1][l][0][kv.x], cconj_if(s_tabc[par][sel][1][l][1][aky], ny)), cconj_if(s_tabc[par][sel][1][l][2][akz], nz));
                         const cplx to = cmul(cmul(s_tabc[par][sel][0][l][0][kv.x], cconj_if(s_tabc[par][sel][0][l][1][aky], ny)), cconj_if(s_tabc[par][sel][0][l][2][akz], nz));
-                        const double q = s_site[i * S + l].w;
+                        const double q = T.q[l];
                         nr += q * (tn.re - to.re);
                         ni += q * (tn.im - to.im);
                     }
@@ -975,12 +992,18 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                         D.tot_v = add(D.tot_v, add(sub(new_v, old_v), recv));
                         D.n_acc += 1;
                         if (T.is_trans) D.tr.naccept += 1; else D.ro.naccept += 1;
-                        s_com[i] = make_double4(T.com[0], T.com[1], T.com[2], 0.0);
+                        const bool owner = i >= j_lo && i < j_hi;
+                        if (!SLICED || owner) {           // on-chip copy: every replica, or the owner's slice
+                            s_com[i - s_lo] = make_double4(T.com[0], T.com[1], T.com[2], 0.0);
 #pragma unroll
-                        for (int s = 0; s < S; ++s) {
-                            double4 t = s_site[i * S + s];
-                            t.x = T.site[s][0]; t.y = T.site[s][1]; t.z = T.site[s][2];
-                            s_site[i * S + s] = t;
+                            for (int s = 0; s < S; ++s) s_site[(i - s_lo) * S + s] = make_double4(T.site[s][0], T.site[s][1], T.site[s][2], T.q[s]);
+                        }
+                        if (owner) {                      // the resident arrays (L2) are kept current by the owner of molecule i
+                            Sy.com[i] = make_double4(T.com[0], T.com[1], T.com[2], 0.0);
+#pragma unroll
+                            for (int s = 0; s < S; ++s) Sy.site[(size_t)i * S + s] = make_double4(T.site[s][0], T.site[s][1], T.site[s][2], T.q[s]);
+                            // no fence here: the readers are generator warps of this cluster, at least N-1 moves later, and every
+                            // move passes barrier.cluster arrive(release) / wait(acquire), which orders these stores for them
                         }
 #pragma unroll
                         for (int k = 0; k < 4; ++k) myquat[4 * i + k] = T.ei[k];                  // this CTA's own replica
@@ -1011,11 +1034,9 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
         }
     }
     __syncthreads();
-    if (rank == 0) {
-        for (int t = tid; t < N * S; t += CHAINC_THREADS) Sy.site[t] = s_site[t];
-        for (int t = tid; t < N; t += CHAINC_THREADS) Sy.com[t] = s_com[t];
-    }
+    // sites and COMs: the owners kept the resident arrays current; ρ(k): every CTA writes its slice
     for (int t = k_lo + tid; t < k_hi; t += CHAINC_THREADS) Sy.rhok[cur][t] = s_rhok[cur][t];
+    __threadfence();
     cluster.sync();                                         // nobody leaves while a neighbour may still write into its buffer
     if (tid == 0 && rank == 0) {
         ChainOut o;

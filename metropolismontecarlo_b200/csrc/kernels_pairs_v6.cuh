@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant_
                 s_fB[t] = make_float4(1e18f, 1e18f, 1e18f, 0.f);   // sentinels: the gate walks B in steps of 64
             }
         }
-        for (int sl = s_begin; sl < s_end; ++sl) {
+        for (int sl = s_begin; sl < s_end && nB > 0; ++sl) {   // (nB == 0: the unit was declined — offsets are not meaningful)
             const int code = s_code[sl];
             if (code == 0) continue;                       // uniform branch: only cells on the box faces
             const int cx = code & 3, cy = (code >> 2) & 3, cz = (code >> 4) & 3;

@@ -183,16 +183,26 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     const DevSystem &S = h->S;
     if (!(S.rc_lj < S.box / 2)) FAIL(MMC_EINVAL, "r_cut must be < box/2 (Ewald/main.jl:483)");
     if (!h->uniform || h->US < 1 || h->US > 4) FAIL(MMC_EINVAL, "device loop needs a uniform topology with 1..4 sites per molecule");
-    if (S.n_mol < 2 || S.n_mol > CHAIN_MAXIT * CHAIN_THREADS) FAIL(MMC_EINVAL, "device loop: 2 <= n_mol <= 2048");
     const bool recip = p->style == MMC_STYLE_EWALD;
-    const size_t smem = chain_smem_bytes(S.n_mol, h->US, recip ? S.nkvecs : 0);
     int dev = 0, max_optin = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (smem + 16 * 1024 > (size_t)max_optin) FAIL(MMC_EINVAL, "device loop: the system does not fit one SM's shared memory; use mmc_loop_run");
+    // thread-block cluster version (k_chains): C CTAs on C SMs, each holding a slice of the molecules and of the k-vectors;
+    // one CTA (k_chain) holds the whole system
+    int C = (h->chain_cluster > 1 && S.n_mol >= 64) ? std::min(h->chain_cluster, CHAINC_MAXC) : 1;
+    bool sliced = false;
+    size_t smem = chain_smem_bytes(S.n_mol, h->US, recip ? S.nkvecs : 0);             // every CTA holds the whole system
+    const bool whole_fits = smem + 16 * 1024 <= (size_t)max_optin && S.n_mol <= CHAIN_MAXIT * CHAIN_THREADS;
+    if (!whole_fits) {                                                                  // a slice per CTA of an 8-SM cluster
+        if (S.n_mol < 64) FAIL(MMC_EINVAL, "device loop: the system does not fit one SM's shared memory; use mmc_loop_run");
+        C = CHAINC_MAXC; sliced = true;
+        const int held = (S.n_mol + C - 1) / C + 1;
+        smem = chain_smem_bytes(held, h->US, recip ? S.nkvecs : 0);
+        if (smem + 16 * 1024 > (size_t)max_optin || held > CHAINS_MAXIT * CHAINS_WORKERS)
+            FAIL(MMC_EINVAL, "device loop: the system does not fit the cluster's shared memory; use mmc_loop_run");
+    } else if (C > 1 && (S.n_mol + C - 1) / C > CHAINS_MAXIT * CHAINS_WORKERS) C = 1;
+    if (S.n_mol < 2) FAIL(MMC_EINVAL, "device loop: at least 2 molecules");
     if ((rc = flush_pending(h))) return rc;
-    // thread-block cluster version: C CTAs on C SMs share the partner molecules and the k-vectors
-    const int C = (h->chain_cluster > 1 && S.n_mol >= 64) ? std::min(h->chain_cluster, CHAINC_MAXC) : 1;
     // one device block: [uniforms | quat (C replicas) | db | delta | out | accepted]
     const size_t n_q1 = 4 * (size_t)S.n_mol, n_q = n_q1 * C, n_db = 3 * (size_t)S.n_sites;
     const size_t off_q = (size_t)n_uniforms, off_db = off_q + n_q, off_delta = off_db + n_db, off_out = off_delta + (size_t)n_moves;
@@ -219,14 +229,15 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     A.out = reinterpret_cast<ChainOut *>(d + off_out); A.accepted = d_acc;
 #define MMC_CHAIN_LAUNCH(SS, DD)                                                                                     \
     if (C > 1) {                                                                                                     \
-        CK(cudaFuncSetAttribute(k_chains<SS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        auto kern = sliced ? k_chains<SS, DD, true> : k_chains<SS, DD, false>;                                        \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
         cudaLaunchConfig_t lc{};                                                                                     \
         lc.gridDim = dim3(C); lc.blockDim = dim3(CHAINC_THREADS); lc.dynamicSmemBytes = smem; lc.stream = h->stream; \
         cudaLaunchAttribute at[1];                                                                                   \
         at[0].id = cudaLaunchAttributeClusterDimension;                                                              \
         at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                          \
         lc.attrs = at; lc.numAttrs = 1;                                                                              \
-        CK(cudaLaunchKernelEx(&lc, k_chains<SS, DD>, h->S, A, h->move_poly));                                        \
+        CK(cudaLaunchKernelEx(&lc, kern, h->S, A, h->move_poly));                                                    \
     } else {                                                                                                         \
         CK(cudaFuncSetAttribute(k_chain<SS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         k_chain<SS, DD><<<1, CHAIN_THREADS, smem, h->stream>>>(h->S, A, h->move_poly);                               \

@@ -505,3 +505,29 @@ def test_pairs_v6_two_pass_groups():
     _check_props(got, want)
     assert info["pairs_in_cutoff"] == npr_pairs_in_cutoff(ms.com, ms.box, 10.0)
     eng.close()
+
+
+def test_pair_kernel_declines_dense_cells_with_stale_density():
+    """A cell above 64 molecules that the cached density does not know about (positions re-sent with
+    mmc_upload_positions): k_pairs_v6 must decline cleanly (regression: its boundary fix-up ran on a declined unit)
+    and the chain must end on a kernel that gives the oracle's answer."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.spce_lattice(4000)                 # 4 cells per edge, full cells hold exactly 64 molecules
+    eng = water_engine(ms, 10.0)
+    eng.potential("ewald")
+    assert eng.last_eval_info()["pair_kernel"] == "k_pairs_v6"
+    rng = np.random.default_rng(2)
+    newcom = np.clip(ms.com + rng.uniform(-1.5, 1.5, ms.com.shape), 0.0, ms.box)
+    ms2 = ms.copy()
+    ms2.coords = ms.coords + np.repeat(newcom - ms.com, 3, axis=0)
+    ms2.com = newcom
+    s = ora_system(ms2)
+    want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
+    for rep in range(3):
+        eng.upload_system(ms, 10.0, 10.0)
+        eng.potential("ewald")
+        eng.upload_positions(ms2.coords, ms2.com)
+        got = eng.potential("ewald")
+        assert eng.last_eval_info()["pair_kernel"] != "k_pairs_v6"
+        _check_props(got, want)
+    eng.close()

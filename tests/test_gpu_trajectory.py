@@ -242,3 +242,28 @@ def test_monatomic_device_loop(n_atoms, dr_div):
     assert rel(st_g.total_energy, eng.potential("atoms").energy) < 1e-10
     print("atoms", n_atoms, "accepted", st_g.n_accepted)
     eng.close()
+
+
+def test_device_loop_config_d_4000_molecules():
+    """4000 SPC/E molecules do not fit one SM: k_chains keeps a slice per CTA (the resident arrays in L2 are the truth for
+    the molecule about to move).  Same record as the per-move protocol; running total == fresh potential()."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.spce_lattice(4000)
+    u = julia_rand(11234, 8 * 6000)
+    outs = []
+    for device in (False, True):
+        eng = water_engine(ms, 10.0)
+        g0 = eng.potential("ewald")
+        com, quat = ms.com.copy(), ms.quat.copy()
+        rc, acc, delta, st = eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 0, 1), com, quat, ms.db, u, 6000,
+                                          g0.energy, g0.virial, device=device)
+        assert rc == 0 and st.n_moves == 6000
+        fresh = eng.potential("ewald")
+        assert rel(st.total_energy, fresh.energy) < 1e-10
+        coords, com_d = eng.download_system()
+        assert np.array_equal(com_d, com)
+        outs.append((acc.copy(), delta.copy(), st.uniforms_used, st.dr_max, com.copy(), coords.copy()))
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][2] == outs[1][2] and abs(outs[0][3] - outs[1][3]) < 1e-12
+    assert np.abs(outs[0][1] - outs[1][1]).max() < 1e-6 * max(1.0, np.abs(outs[0][1]).max())
+    assert np.abs(outs[0][4] - outs[1][4]).max() < 1e-11 and np.abs(outs[0][5] - outs[1][5]).max() < 1e-11
