@@ -531,3 +531,27 @@ def test_pair_kernel_declines_dense_cells_with_stale_density():
         assert eng.last_eval_info()["pair_kernel"] != "k_pairs_v6"
         _check_props(got, want)
     eng.close()
+
+
+def test_pairs_v6_sparse_box_with_empty_cells():
+    """Low density: 6 cells per edge with a handful of molecules each and some empty ones (zero-size tiles), molecules
+    clustered in one corner so that whole neighbour cells are empty."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.spce_lattice(600, rho=0.0025)
+    rng = np.random.default_rng(8)
+    newcom = ms.com.copy()
+    newcom[:200] = rng.uniform(0.0, 0.3 * ms.box, (200, 3))       # a dense corner ...
+    newcom[200:] = np.clip(ms.com[200:] + rng.uniform(-2, 2, (400, 3)), 0.0, ms.box)
+    ms.coords = ms.coords + np.repeat(newcom - ms.com, 3, axis=0)
+    ms.com = newcom
+    eng = water_engine(ms, 10.0)
+    got = eng.potential("ewald")
+    info = eng.last_eval_info()
+    assert info["pair_kernel"] == "k_pairs_v6" and info["cells_per_dim"] >= 5, info
+    s = ora_system(ms)
+    want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
+    assert info["pairs_in_cutoff"] == npr_pairs_in_cutoff(ms.com, ms.box, 10.0)
+    assert got.overlaps == want.overlaps
+    if want.overlaps == 0:
+        _check_props(got, want)
+    eng.close()
