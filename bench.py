@@ -323,7 +323,17 @@ def run_ours(args, rank, world, local_rank):
 
     p2p = world > 1 and args.collective == "p2p"
     if p2p:        # every rank maps every rank's exchange buffer (CUDA IPC); NCCL only carries the 64-byte handles
-        setup_peer_exchange(eng, world)
+        ok = 1
+        try:
+            setup_peer_exchange(eng, world)
+        except Exception as e:            # no CUDA IPC between these processes: all ranks fall back to the NCCL all-reduce
+            print(f"rank {rank}: peer exchange unavailable ({e}); using the NCCL all-reduce", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        p2p = bool(flag.item())
+        if not p2p:
+            args.collective = "nccl"
 
     def step():
         if p2p:    # partial -> each rank stores its 682 doubles into every peer's buffer over NVLink -> ordered sum -> finalize

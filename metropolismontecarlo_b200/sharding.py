@@ -41,8 +41,13 @@ def setup_peer_exchange(eng, world: int, group=None):
     travel through torch.distributed (any transport would do), every rank maps every peer's buffer.  After this
     eng.potential_sharded(style) needs no collective library: partial sums go peer to peer over NVLink."""
     import torch.distributed as dist
-    mine = eng.peer_export()
+    try:
+        mine = eng.peer_export()
+    except Exception:
+        mine = None
     handles = [None] * world
-    dist.all_gather_object(handles, mine, group=group)
+    dist.all_gather_object(handles, mine, group=group)      # every rank takes part even if its export failed
+    if any(hd is None for hd in handles):
+        raise RuntimeError("a rank could not export its exchange buffer (CUDA IPC unavailable)")
     for r, hd in enumerate(handles):
         eng.peer_import(r, hd)
