@@ -575,7 +575,9 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     const long long ns_all = S.n_sites;
     const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
     bool rhok_forked = false;
-    if (style == MMC_STYLE_EWALD && h->overlap_rhok == 1 && E.f == 1.0) {
+    // (small systems: the rebuild is a few µs of work, the fork/join events would cost more than they hide)
+    const bool rhok_side = h->overlap_rhok && (long long)(rs1 - rs0) * S.nkvecs > 10000000LL;
+    if (style == MMC_STYLE_EWALD && rhok_side && h->overlap_rhok == 1 && E.f == 1.0) {
         CK(cudaEventRecord(h->ev_fork, h->stream));
         CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         int rcr = rhok_launch(h, S.site, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL), h->side);
@@ -643,7 +645,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
                  zl_lo, std::min(zl_cnt, ncd)};
     k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
-    if (style == MMC_STYLE_EWALD && h->overlap_rhok && !rhok_forked) {      // volume trial: scaled, sorted sites
+    if (style == MMC_STYLE_EWALD && rhok_side && !rhok_forked) {      // volume trial: scaled, sorted sites
         CK(cudaEventRecord(h->ev_fork, h->stream));
         CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         int rcr = rhok_launch(h, h->d_ssite, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL), h->side);
@@ -712,15 +714,17 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     int grid;
     if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
     if (v3 || v4 || v5 || v6) {
-        const long long nslots = 14LL * ncd * ncd * ncd;
-        if (nslots > h->slots_cap) {
-            dfree(h->d_slots);
-            CK(cudaMalloc(&h->d_slots, sizeof(int4) * nslots));
-            h->slots_cap = nslots;
+        {
+            const long long nslots = 14LL * ncd * ncd * ncd;
+            if (nslots > h->slots_cap) {
+                dfree(h->d_slots);
+                CK(cudaMalloc(&h->d_slots, sizeof(int4) * nslots));
+                h->slots_cap = nslots;
+            }
+            k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(P, h->d_slots, ncd * ncd * ncd);
+            LAUNCH_CHECK();
+            if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
         }
-        k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(P, h->d_slots, ncd * ncd * ncd);
-        LAUNCH_CHECK();
-        if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
         if (v6) {
             grid = (int)std::max(1LL, std::min<long long>(h->v6_ctas_per_sm * h->sm_count, my_units));
             launch_pairs_v6(v5_deg, v5_direct, grid, h->stream, P, h->d_slots, V6Extra{h->d_mrows, h->d_gf});
@@ -765,8 +769,8 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
 
     if (style == MMC_STYLE_EWALD) {
         if (rhok_forked) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        else {
-            int rc = rhok_launch(h, h->d_ssite, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL));
+        else {   // same stream: resident sites when the box is unchanged (a sharded rank gathers only its layers), scaled copy otherwise
+            int rc = rhok_launch(h, E.f == 1.0 ? S.site : h->d_ssite, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL));
             if (rc) return rc;
         }
     }
