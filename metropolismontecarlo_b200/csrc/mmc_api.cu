@@ -577,13 +577,18 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     bool rhok_forked = false;
     // (small systems: the rebuild is a few µs of work, the fork/join events would cost more than they hide)
     const bool rhok_side = h->overlap_rhok && (long long)(rs1 - rs0) * S.nkvecs > 10000000LL;
-    if (style == MMC_STYLE_EWALD && rhok_side && h->overlap_rhok == 1 && E.f == 1.0) {
+    auto fork_rhok_resident = [&]() -> int {
         CK(cudaEventRecord(h->ev_fork, h->stream));
         CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         int rcr = rhok_launch(h, S.site, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL), h->side);
         if (rcr) return rcr;
         CK(cudaEventRecord(h->ev_join, h->side));
         rhok_forked = true;
+        return MMC_OK;
+    };
+    if (style == MMC_STYLE_EWALD && rhok_side && h->overlap_rhok == 1 && E.f == 1.0) {
+        int rcr = fork_rhok_resident();
+        if (rcr) return rcr;
     }
     const int tb = 256, gm = (S.n_mol + tb - 1) / tb;
     long long n_units;
@@ -619,6 +624,10 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         k_cell_scan<<<1, 1024, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
         k_cell_fill<<<gm, tb, 0, h->stream>>>(C); LAUNCH_CHECK();
         k_cell_sort<<<(ncell * 32 + tb - 1) / tb, tb, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
+        if (style == MMC_STYLE_EWALD && rhok_side && h->overlap_rhok == 3 && E.f == 1.0) {   // fork after the (tiny, launch-bound) binning kernels
+            int rcr = fork_rhok_resident();
+            if (rcr) return rcr;
+        }
         n_units = 14LL * ncell;
         if (h->max_cell_cached < 0) {   // unknown density: one synchronous read-back, cached afterwards
             int mc = 0;
