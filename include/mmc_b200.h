@@ -229,7 +229,7 @@ int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_max, double 
                        mmc_loop_stats *stats);
 
 /* mmc_loop_run_atoms for a block of moves in one launch (csrc/kernels_chain.cuh k_chain_atoms: the atoms are
- * sliced over the CTAs of an 8-SM cluster, FP32 distance gate on chip, FP64 evaluation of what passes). */
+ * sliced over the CTAs of a 16-SM (or 8-SM) cluster, FP32 distance gate on chip, FP64 evaluation of what passes). */
 int mmc_loop_run_atoms_device(mmc_handle *h, double temperature, double dr_max, double *r,
                               const double *uniforms, int64_t n_uniforms, int64_t n_moves,
                               double e0, double v0, uint8_t *accepted, double *delta,

@@ -1060,6 +1060,7 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
 // the resident position (L2) and its float copy.  r_old(i+1) and the uniforms are requested one move ahead.
 #define CHAINA_THREADS 512
 #define CHAINA_WARPS (CHAINA_THREADS / 32)
+#define CHAINA_MAXC 16       // CTAs per cluster (16 is the non-portable maximum of sm_100; 8 is the fallback)
 
 struct ChainAtomArgs {
     long long n_moves, n_uniforms;
@@ -1079,7 +1080,7 @@ k_chain_atoms(DevAtoms At, const __grid_constant__ ChainAtomArgs A)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_f = reinterpret_cast<float4 *>(smem_raw);                  // float copy of this CTA's slice
     __shared__ double s_red[4 * CHAINA_WARPS];
-    __shared__ double s_xchg[2][4][CHAINC_MAXC];                         // [move parity][value][source rank]
+    __shared__ double s_xchg[2][4][CHAINA_MAXC];                         // [move parity][value][source rank]; unused ranks stay 0
     __shared__ double s_tot[4];
     __shared__ double s_u[CHAIN_RING];
     __shared__ double s_r0[3], s_rn[3];
@@ -1097,7 +1098,7 @@ k_chain_atoms(DevAtoms At, const __grid_constant__ ChainAtomArgs A)
         const double4 r = At.r[a_lo + t];
         s_f[t] = make_float4((float)r.x, (float)r.y, (float)r.z, 0.f);
     }
-    for (int k = tid; k < 2 * 4 * CHAINC_MAXC; k += CHAINA_THREADS) (&s_xchg[0][0][0])[k] = 0.0;
+    for (int k = tid; k < 2 * 4 * CHAINA_MAXC; k += CHAINA_THREADS) (&s_xchg[0][0][0])[k] = 0.0;
     if (tid == 0) s_stop = 0;
 
     // driver state: lane 0 of warp 0 (a handful of registers)
@@ -1207,16 +1208,17 @@ k_chain_atoms(DevAtoms At, const __grid_constant__ ChainAtomArgs A)
             const int d = lane & 15, vh = lane >> 4;          // lane (vh, d): values vh and 2 + vh for CTA d
             if (d < C) {
                 double *dst = cluster.map_shared_rank(&s_xchg[par][0][0], d);
-                dst[vh * CHAINC_MAXC + rank] = xa;
-                dst[(2 + vh) * CHAINC_MAXC + rank] = xb;
+                dst[vh * CHAINA_MAXC + rank] = xa;
+                dst[(2 + vh) * CHAINA_MAXC + rank] = xb;
             }
         }
         cluster.sync();
         if (warp == 0) {
-            double x = (&s_xchg[par][0][0])[lane];            // 4 values x 8 ranks = 32 doubles: groups of 8 lanes
+            // 4 values x 16 rank slots = 64 doubles: two per lane, groups of 16 lanes (same fixed tree in every CTA)
+            double x0 = (&s_xchg[par][0][0])[lane], x1 = (&s_xchg[par][0][0])[lane + 32];
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if ((lane & 7) == 0) s_tot[lane >> 3] = x;
+            for (int o = 1; o < 16; o <<= 1) { x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o); }
+            if ((lane & 15) == 0) { s_tot[lane >> 4] = x0; s_tot[2 + (lane >> 4)] = x1; }
             __syncwarp();
             if (lane == 0) {
                 // launch_move_atom's folding (mainMonatomic.jl:271): pot*4, vir*24/3

@@ -95,6 +95,7 @@ struct mmc_handle {
     // ---- device-resident block of moves (mmc_loop_run_device)
     unsigned char *d_chain = nullptr;   // [uniforms | quat | db | delta | out | accepted]
     int chain_cluster = 8;              // CTAs (SMs) per cluster for mmc_loop_run_device; 1 = single-CTA kernel
+    int chain_cluster_atoms = 16;       // ... for mmc_loop_run_atoms_device (16 = non-portable cluster size, falls back to 8)
     size_t chain_bytes = 0;
     int pend_kind = 0;            // accepted move not yet written to HBM: 0 none, 1 molecule, 2 atom
     int pend_i = 0, pend_ns = 0;
@@ -1821,6 +1822,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
 {
     if (!h || !key) return MMC_EINVAL;
     const std::string k(key);
+    if (k == "chain_cluster_atoms") { h->chain_cluster_atoms = (int)value; return MMC_OK; }
     if (k == "chain_cluster") { if (value < 1 || value > CHAINC_MAXC) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
     if (k == "v6_ctas_per_sm") { if (value < 1 || value > 5) FAIL(MMC_EINVAL, "v6_ctas_per_sm must be 1..5"); h->v6_ctas_per_sm = (int)value; return MMC_OK; }

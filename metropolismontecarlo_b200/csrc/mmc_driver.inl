@@ -347,9 +347,9 @@ extern "C" int mmc_loop_run_atoms_device(mmc_handle *h, double temperature, doub
     if (!r || !uniforms || !st || n_moves < 0 || n_uniforms < 0) FAIL(MMC_EINVAL, "bad argument");
     if (h->trial_pending) FAIL(MMC_ESTATE, "a trial move is pending");
     const int n = h->At.n;
-    const int C = CHAINC_MAXC;
+    int C = (n >= 4096 && h->chain_cluster_atoms > 8) ? CHAINA_MAXC : CHAINC_MAXC;      // 16 CTAs need the non-portable cluster size
     if (n < 64) FAIL(MMC_EINVAL, "device loop: at least 64 atoms");
-    const size_t smem = sizeof(float4) * (size_t)((n + C - 1) / C + 1);
+    size_t smem = sizeof(float4) * (size_t)((n + CHAINC_MAXC - 1) / CHAINC_MAXC + 1);     // sized for the 8-CTA fallback
     int dev = 0, max_optin = 0, rc;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -377,13 +377,24 @@ extern "C" int mmc_loop_run_atoms_device(mmc_handle *h, double temperature, doub
     }
     A.uniforms = d; A.delta = d + off_delta; A.out = reinterpret_cast<ChainOut *>(d + off_out); A.accepted = d_acc;
     CK(cudaFuncSetAttribute(k_chain_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(C); lc.blockDim = dim3(CHAINA_THREADS); lc.dynamicSmemBytes = smem; lc.stream = h->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    lc.attrs = at; lc.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&lc, k_chain_atoms, h->At, A));
+    if (C > 8 && cudaFuncSetAttribute(k_chain_atoms, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        C = CHAINC_MAXC;
+    }
+    for (;;) {
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(C); lc.blockDim = dim3(CHAINA_THREADS); lc.dynamicSmemBytes = smem; lc.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&lc, k_chain_atoms, h->At, A);
+        if (le == cudaSuccess) break;
+        cudaGetLastError();
+        if (C > 8) { C = CHAINC_MAXC; continue; }            // 16-CTA cluster not schedulable here: portable size
+        h->err = std::string("k_chain_atoms launch: ") + cudaGetErrorString(le);
+        return MMC_ECUDA;
+    }
     LAUNCH_CHECK();
     ChainOut o{};
     std::vector<double4> hr(n);
