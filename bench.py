@@ -197,7 +197,12 @@ def moves_benchmarks(n_moves=10_000):
         t0 = time.perf_counter()
         ora.loop(s, ew, ms.db, ms.quat.copy(), prm, u, n_cpu, 0.0, 0.0)
         dtc = time.perf_counter() - t0
-        # the same block of moves in ONE launch (mmc_loop_run_device: state in shared memory)
+        # the same block of moves in ONE launch (mmc_loop_run_device: state in shared memory); one untimed block first
+        # (first use loads the kernel and allocates the block's device buffers)
+        eng.upload_system(ms, RC, RC)
+        p0 = eng.potential(style)
+        com, quat = ms.com.copy(), ms.quat.copy()
+        eng.loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, sid, 1), com, quat, ms.db, u, 500, p0.energy, p0.virial, device=True)
         eng.upload_system(ms, RC, RC)
         p0 = eng.potential(style)
         com, quat = ms.com.copy(), ms.quat.copy()
@@ -279,6 +284,9 @@ def moves_benchmarks(n_moves=10_000):
     t0 = time.perf_counter()
     ora.loop_atoms(at.r.copy(), at.eps, at.sig, at.box, at.r_cut, 1.0, at.box / 30, u, n_cpu, 0.0, 0.0)
     dtc = time.perf_counter() - t0
+    eng.upload_atoms(at)
+    r = at.r.copy()
+    eng.loop_run_atoms(1.0, at.box / 30, r, u, 500, p0.energy, p0.virial, device=True)      # untimed first block
     eng.upload_atoms(at)
     r = at.r.copy()
     t0 = time.perf_counter()

@@ -208,10 +208,12 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     const size_t off_q = (size_t)n_uniforms, off_db = off_q + n_q, off_delta = off_db + n_db, off_out = off_delta + (size_t)n_moves;
     const size_t out_doubles = (sizeof(ChainOut) + 7) / 8;
     const size_t bytes = (off_out + out_doubles) * sizeof(double) + (size_t)n_moves + 16;
-    if (bytes > h->chain_bytes) {
+    if (bytes > h->chain_bytes) {            // grown in powers of two from 4 MiB: a cudaFree + cudaMalloc between two blocks can cost
+        size_t cap = 4u << 20;               // more than the block itself
+        while (cap < bytes) cap <<= 1;
         dfree(h->d_chain);
-        CK(cudaMalloc(&h->d_chain, bytes));
-        h->chain_bytes = bytes;
+        CK(cudaMalloc(&h->d_chain, cap));
+        h->chain_bytes = cap;
     }
     double *d = reinterpret_cast<double *>(h->d_chain);
     unsigned char *d_acc = reinterpret_cast<unsigned char *>(d + off_out + out_doubles);
@@ -358,10 +360,12 @@ extern "C" int mmc_loop_run_atoms_device(mmc_handle *h, double temperature, doub
     const size_t off_delta = (size_t)n_uniforms, off_out = off_delta + (size_t)n_moves;
     const size_t out_doubles = (sizeof(ChainOut) + 7) / 8;
     const size_t bytes = (off_out + out_doubles) * sizeof(double) + (size_t)n_moves + 16;
-    if (bytes > h->chain_bytes) {
+    if (bytes > h->chain_bytes) {            // grown in powers of two from 4 MiB: a cudaFree + cudaMalloc between two blocks can cost
+        size_t cap = 4u << 20;               // more than the block itself
+        while (cap < bytes) cap <<= 1;
         dfree(h->d_chain);
-        CK(cudaMalloc(&h->d_chain, bytes));
-        h->chain_bytes = bytes;
+        CK(cudaMalloc(&h->d_chain, cap));
+        h->chain_bytes = cap;
     }
     double *d = reinterpret_cast<double *>(h->d_chain);
     unsigned char *d_acc = reinterpret_cast<unsigned char *>(d + off_out + out_doubles);
