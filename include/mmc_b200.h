@@ -92,6 +92,10 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites,
  * them itself): the bulk form of mmc_set_molecule (Ewald/main.jl:527,552).  Charges, types and topology stay; the
  * resident rho(k) is not rebuilt (mmc_recip_long / mmc_potential do that, as after mmc_upload_system). */
 int mmc_upload_positions(mmc_handle *h, const double *coords, const double *com);
+/* mmc_upload_positions + mmc_potential in one call with the host->device copies overlapped with the work that does
+ * not need them yet (COMs first: cell binning; sites in chunks on a side stream, each fed to the rho(k) rebuild as it
+ * lands; gather + pair kernel when the last chunk is in).  Host arrays in, Properties out. */
+int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, int32_t style, mmc_properties *out);
 
 /* Monatomic/mainMonatomic.jl:140-146 Requirements(r, eps, sig, box, r_cut) */
 int mmc_upload_atoms(mmc_handle *h, int64_t n, const double *r, const double *eps_j,

@@ -95,6 +95,14 @@ set_molecule!(e::Engine, i::Int, com, sites::Vector) =
 upload_positions!(e::Engine, coords, com) =
     check(e, ccall((:mmc_upload_positions, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), e.h, pointer(coords), pointer(com)))
 
+# host arrays in, Properties out: upload_positions! + potential with the copies overlapped with compute
+function potential_host(e::Engine, coords, com, style::Cint = EWALD)
+    p = Props()
+    check(e, ccall((:mmc_potential_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ref{Props}),
+                   e.h, pointer(coords), pointer(com), style, p))
+    p
+end
+
 # potential(moa, soa, tot, ewald, vdwTable, sim_props[, "ewald"])  — Ewald/energy.jl:864-1032
 function potential(e::Engine, style::Cint = EWALD)
     p = Props()

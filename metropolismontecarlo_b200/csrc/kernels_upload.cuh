@@ -67,6 +67,26 @@ __global__ void k_repack_positions(const double *coords, const double *com, int 
     }
 }
 
+// the two halves of k_repack_positions, for the pipelined end-to-end path (mmc_potential_host): COMs first (binning
+// needs nothing else), sites chunk by chunk as their copies land
+__global__ void k_repack_com(const double *com, int n_mol, double box, double4 *dcom, int *info)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_mol) return;
+    const double x = com[3 * (size_t)t], y = com[3 * (size_t)t + 1], z = com[3 * (size_t)t + 2];
+    if (!(x >= 0.0 && x <= box && y >= 0.0 && y <= box && z >= 0.0 && z <= box)) atomicOr(&info[0], REPACK_COM_OUTSIDE);
+    dcom[t] = make_double4(x, y, z, 0.0);
+}
+
+__global__ void k_repack_sites(const double *coords, int s0, int s1, double4 *site)
+{
+    const int t = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= s1) return;
+    double4 s = site[t];
+    s.x = coords[3 * (size_t)t]; s.y = coords[3 * (size_t)t + 1]; s.z = coords[3 * (size_t)t + 2];
+    site[t] = s;
+}
+
 // Σq and Σq² in two deterministic stages (EwaldSelf ewalds.jl:829-833, Wolf constants energy.jl:924-934)
 __global__ void __launch_bounds__(256) k_charge_partial(const double4 *site, int n, double2 *part)
 {

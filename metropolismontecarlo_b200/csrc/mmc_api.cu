@@ -37,7 +37,9 @@ struct mmc_handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t side = nullptr;         // the ρ(k) rebuild of a full evaluation runs here, beside binning + pair kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sites = nullptr;
+    cudaStream_t copy = nullptr;         // mmc_potential_host: host->device chunks + repack; ρ(k) partials follow on `side`
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
     int overlap_rhok = 1;                // mmc_debug_set "overlap_rhok": 0 = everything on one stream
     std::string err;
 
@@ -398,9 +400,13 @@ struct EvalCtx {
     double f, box, kappa;          // scale factor, box and kappa the energy is evaluated at
     const double *d_cfac;
     int rank, world;
+    cudaEvent_t wait_sites = nullptr;   // mmc_potential_host: the sites arrive on the side stream; wait for them before the gather
+    bool rhok_external = false;         //                     ... and the ρ(k) partials are produced there, chunk by chunk
 };
 
-int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, double box, double2 *out, cudaStream_t st = nullptr)
+// out == nullptr: partials only, written from block `block0` on (the caller reduces all blocks later); *nb_out = blocks used
+int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, double box, double2 *out, cudaStream_t st = nullptr,
+                int block0 = 0, int *nb_out = nullptr, int cap_blocks = 0)
 {
     if (!st) st = h->stream;
     const int n = s_end - s_begin;
@@ -410,14 +416,18 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
     int per = std::max(2 * chunk, (n + 2 * h->sm_count - 1) / (2 * h->sm_count));
     per = (per + chunk - 1) / chunk * chunk;
     const int nb = std::max(1, (n + per - 1) / per);
-    if (nb > h->rhok_grid_cap) {
+    if (nb_out) *nb_out = nb;
+    const int need = std::max(block0 + nb, cap_blocks);
+    if (need > h->rhok_grid_cap) {
+        if (block0 > 0) FAIL(MMC_ECUDA, "rho(k) partial buffer too small for a chunked rebuild (internal)");
         dfree(h->d_rhok_partial);
-        CK(cudaMalloc(&h->d_rhok_partial, (size_t)nb * nkv * sizeof(double2)));
-        h->rhok_grid_cap = nb;
+        CK(cudaMalloc(&h->d_rhok_partial, (size_t)need * nkv * sizeof(double2)));
+        h->rhok_grid_cap = need;
     }
+    double2 *part = h->d_rhok_partial + (size_t)block0 * nkv;
     if (h->tm.on) cudaEventRecord(h->tm.ev[2], st);
     if (v2) {
-        Rhok2Args R{site, s_begin, s_end, per, nkv, h->n_kpairs, h->d_kpairs, h->d_kindex, box, h->d_rhok_partial};
+        Rhok2Args R{site, s_begin, s_end, per, nkv, h->n_kpairs, h->d_kpairs, h->d_kindex, box, part};
         switch (h->S.nk) {
             case 1: k_rhok_pairs<1><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
             case 2: k_rhok_pairs<2><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
@@ -427,7 +437,7 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
             default: k_rhok_pairs<6><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
         }
     } else {
-        RhokArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->S.kvec, box, h->d_rhok_partial};
+        RhokArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->S.kvec, box, part};
         const int kpt = (nkv + RHOK_BLOCK - 1) / RHOK_BLOCK;
         if (kpt <= 1) k_rhok_partial<1><<<nb, RHOK_BLOCK, 0, st>>>(R);
         else if (kpt <= 2) k_rhok_partial<2><<<nb, RHOK_BLOCK, 0, st>>>(R);
@@ -437,8 +447,10 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
     }
     LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[3], st);
-    k_rhok_reduce<<<(nkv + 31) / 32, dim3(32, 32), 0, st>>>(h->d_rhok_partial, nb, nkv, out);
-    LAUNCH_CHECK();
+    if (out) {
+        k_rhok_reduce<<<(nkv + 31) / 32, dim3(32, 32), 0, st>>>(h->d_rhok_partial, nb, nkv, out);
+        LAUNCH_CHECK();
+    }
     return MMC_OK;
 }
 
@@ -577,7 +589,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
     bool rhok_forked = false;
     // (small systems: the rebuild is a few µs of work, the fork/join events would cost more than they hide)
-    const bool rhok_side = h->overlap_rhok && (long long)(rs1 - rs0) * S.nkvecs > 10000000LL;
+    const bool rhok_side = h->overlap_rhok && !E.rhok_external && (long long)(rs1 - rs0) * S.nkvecs > 10000000LL;
     auto fork_rhok_resident = [&]() -> int {
         CK(cudaEventRecord(h->ev_fork, h->stream));
         CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
@@ -653,6 +665,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
                  reinterpret_cast<unsigned long long *>(h->d_maxdev), h->d_ovl,
                  want_rows ? h->d_mrows : nullptr, want_rows ? h->d_gf : nullptr, h->d_cell_of, ncd, E.box / ncd,
                  zl_lo, std::min(zl_cnt, ncd)};
+    if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
     k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
     if (style == MMC_STYLE_EWALD && rhok_side && !rhok_forked) {      // volume trial: scaled, sorted sites
@@ -777,7 +790,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     h->last_mode = cells ? 0 : 1;
     h->last_ncd = ncd;
 
-    if (style == MMC_STYLE_EWALD) {
+    if (style == MMC_STYLE_EWALD && !E.rhok_external) {
         if (rhok_forked) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         else {   // same stream: resident sites when the box is unchanged (a sharded rank gathers only its layers), scaled copy otherwise
             int rc = rhok_launch(h, E.f == 1.0 ? S.site : h->d_ssite, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL));
@@ -1004,6 +1017,10 @@ int mmc_create(const mmc_config *cfg, mmc_handle **out)
     }
     if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_sites, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return fail("copy stream", e);
+    for (auto &ev : h->ev_chunk)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     cudaFuncSetAttribute(k_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_pairs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     pairs_fast_set_attributes();
@@ -1026,6 +1043,9 @@ int mmc_destroy(mmc_handle *h)
     if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_sites) cudaEventDestroy(h->ev_sites);
+    if (h->copy) { cudaStreamSynchronize(h->copy); cudaStreamDestroy(h->copy); }
+    for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return MMC_OK;
@@ -1637,6 +1657,83 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
         rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
     }
     if (style == MMC_STYLE_EWALD) h->new_valid = false;
+    return rc;
+}
+
+// End to end in one call: positions from HOST arrays (pointer(soa.coords), pointer(moa.COM)) → Properties on the host, with the
+// copies overlapped with the work that does not need them yet.  COMs go first (the cell binning needs nothing else); the sites
+// follow in chunks on the side stream, each chunk repacked and fed to the ρ(k) rebuild as it lands; the gather and the pair kernel
+// start when the last chunk is in.  Same result as mmc_upload_positions + mmc_potential.
+int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, int32_t style, mmc_properties *out)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = style_check(h, style);
+    if (rc) return rc;
+    if (!coords || !com || !out || style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "bad arguments");
+    DevSystem &S = h->S;
+    const int nchunk = 4;
+    if (!h->uniform || h->cfg.world != 1 || S.n_sites < 64 * nchunk) {          // small or general systems: the plain sequence
+        if ((rc = mmc_upload_positions(h, coords, com))) return rc;
+        return mmc_potential(h, style, out);
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    if ((rc = ensure_vec(h))) return rc;
+    h->pair_level = h->pair_floor;
+    if (h->pend_kind == 1) h->pend_kind = 0;
+    h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
+    double *d_coords = reinterpret_cast<double *>(h->d_raw);
+    double *d_com = d_coords + 4 * (size_t)S.n_sites;
+    const bool ewald = style == MMC_STYLE_EWALD;
+    // main stream: COMs
+    CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * S.n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
+    k_repack_com<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(d_com, S.n_mol, S.box, S.com, h->d_info); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    // copy stream: site chunks, each repacked as it lands; side stream: (Ewald) ρ(k) partials of a chunk as soon as it is in
+    CK(cudaStreamWaitEvent(h->copy, h->ev_fork, 0));
+    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    int blocks = 0, cap = 0;
+    if (ewald) {   // blocks a chunk needs (same formula as rhok_launch), to size the partial buffer once
+        const bool v2 = h->n_kpairs <= 32 && S.nk <= 6 && h->use_rhok_v2;
+        const int ck = v2 ? RHOK2_SITES : RHOK_SITES;
+        for (int c = 0; c < nchunk; ++c) {
+            const int n = (int)((long long)S.n_sites * (c + 1) / nchunk) - (int)((long long)S.n_sites * c / nchunk);
+            int per = std::max(2 * ck, (n + 2 * h->sm_count - 1) / (2 * h->sm_count));
+            per = (per + ck - 1) / ck * ck;
+            cap += std::max(1, (n + per - 1) / per);
+        }
+    }
+    for (int c = 0; c < nchunk; ++c) {
+        const int s0 = (int)((long long)S.n_sites * c / nchunk), s1 = (int)((long long)S.n_sites * (c + 1) / nchunk);
+        CK(cudaMemcpyAsync(d_coords + 3 * (size_t)s0, coords + 3 * (size_t)s0, sizeof(double) * 3 * (size_t)(s1 - s0), cudaMemcpyHostToDevice, h->copy));
+        k_repack_sites<<<(s1 - s0 + 255) / 256, 256, 0, h->copy>>>(d_coords, s0, s1, S.site); LAUNCH_CHECK();
+        CK(cudaEventRecord(c == nchunk - 1 ? h->ev_sites : h->ev_chunk[c], h->copy));
+        if (ewald) {
+            CK(cudaStreamWaitEvent(h->side, c == nchunk - 1 ? h->ev_sites : h->ev_chunk[c], 0));
+            int nb = 0;
+            if ((rc = rhok_launch(h, S.site, s0, s1, S.box, nullptr, h->side, blocks, &nb, cap))) return rc;
+            blocks += nb;
+        }
+    }
+    CK(cudaEventRecord(h->ev_join, h->side));
+    EvalCtx E{1.0, S.box, S.kappa, S.cfac, 0, 1};
+    E.wait_sites = h->ev_sites; E.rhok_external = true;
+    for (;;) {
+        if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        if (ewald) {
+            k_rhok_reduce<<<(S.nkvecs + 31) / 32, dim3(32, 32), 0, h->stream>>>(h->d_rhok_partial, blocks, S.nkvecs,
+                                                                               reinterpret_cast<double2 *>(h->d_vec + MMC_NSCAL));
+            LAUNCH_CHECK();
+        }
+        CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        rc = finalize(h, style, E, h->d_vec, S.rhok[0], S.rhok[1], out);
+        if (rc != 1) break;
+        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        E.wait_sites = nullptr;                                  // the state is on the device now
+    }
+    if (rc < 0) return rc;
+    if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
     return rc;
 }
 

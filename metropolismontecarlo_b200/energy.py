@@ -82,6 +82,15 @@ class Engine:
         assert coords.shape == (self.n_sites, 3) and com.shape == (self.n_mol, 3)
         self._ck(self.lib.mmc_upload_positions(self.h, _dp(coords), _dp(com)))
 
+    def potential_host(self, coords, com, style="ewald") -> Properties:
+        """upload_positions + potential in one call, copies overlapped with compute (mmc_potential_host)."""
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        com = np.ascontiguousarray(com, dtype=np.float64)
+        assert coords.shape == (self.n_sites, 3) and com.shape == (self.n_mol, 3)
+        out = Properties()
+        self._ck(self.lib.mmc_potential_host(self.h, _dp(coords), _dp(com), _style(style), C.byref(out)))
+        return out
+
     def upload_atoms(self, at: AtomicSystem):
         r = np.ascontiguousarray(at.r, dtype=np.float64)
         e = np.ascontiguousarray(at.eps, dtype=np.float64)

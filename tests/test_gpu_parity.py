@@ -555,3 +555,29 @@ def test_pairs_v6_sparse_box_with_empty_cells():
     if want.overlaps == 0:
         _check_props(got, want)
     eng.close()
+
+
+def test_potential_host_pipelined_equals_upload_then_potential():
+    """mmc_potential_host (COMs first, sites in chunks on the side stream feeding the rho(k) rebuild, gather + pairs last)
+    against mmc_upload_positions + mmc_potential, Ewald / Wolf / LJ, twice (the state it leaves is the uploaded one)."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.spce_lattice(8000)
+    eng = water_engine(ms, 10.0)
+    eng.potential("ewald")
+    rng = np.random.default_rng(12)
+    for rep in range(2):
+        newcom = np.clip(ms.com + rng.uniform(-0.3, 0.3, ms.com.shape), 0.0, ms.box)
+        coords = ms.coords + np.repeat(newcom - ms.com, 3, axis=0)
+        for style in ("ewald", "wolf", "lj"):
+            got = eng.potential_host(coords, newcom, style)
+            c2, m2 = eng.download_system()
+            assert np.array_equal(c2, coords) and np.array_equal(m2, newcom)
+            eng.upload_positions(coords, newcom)
+            want = eng.potential(style)
+            _check_props(got, want, 1e-13)
+        if rep == 0:
+            assert np.abs(eng.rhok()[0]).max() > 0
+    bad = newcom.copy(); bad[7, 2] = -1.0
+    with pytest.raises(Exception):
+        eng.potential_host(coords, bad, "ewald")
+    eng.close()
