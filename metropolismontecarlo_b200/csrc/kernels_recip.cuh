@@ -157,7 +157,7 @@ struct Rhok2Args {
 };
 
 template <int NK>
-__global__ void __launch_bounds__(RHOK2_BLOCK) k_rhok_pairs(Rhok2Args A)
+__global__ void __launch_bounds__(RHOK2_BLOCK, 2) k_rhok_pairs(Rhok2Args A)
 {
     constexpr int NW = RHOK2_BLOCK / 32;
     constexpr int NACC = 4 + 8 * NK;
