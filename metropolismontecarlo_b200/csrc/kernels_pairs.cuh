@@ -54,6 +54,7 @@ struct PairArgs {
     ErfPoly ep;                // smooth part of erfc(κr)/r as one polynomial (deg 0: use erfc())
     double pc[MMC_ERF_MAXDEG + 1];   // v5: −κ·(coefficients), in r² (DIRECT, κ^2k folded) or in s = pk2s·r² − 1
     double pk2s;               // v5: σ κ²
+    double *per_mol;           // k_pairs<ST, true>: [n_mol x 3] per-molecule rows {Σlj_pot, Σlj_vir, Σcoul} (index space of `com`)
 };
 
 // ---- one Coulomb site pair: q_a q_b erfc(κ r)/r with the overlap rule (ewalds.jl:359-367).
@@ -88,7 +89,9 @@ __constant__ int c_half_shell[14][3] = {
     {-1, 0, 1}, {0, 0, 1}, {1, 0, 1},
     {-1, 1, 1}, {0, 1, 1}, {1, 1, 1}};
 
-template <int ST>   // ST = sites per molecule at compile time (0: runtime A.S)
+// PM: every evaluated molecule pair is also credited to the rows of BOTH molecules (mmc_energy_all: LJ_poly_ΔU(i) and
+// EwaldReal(i) for all i from one pass over the unique pairs; FP64 atomics, so the row sums are order-free to ~1e-13).
+template <int ST, bool PM>   // ST = sites per molecule at compile time (0: runtime A.S)
 __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__ PairArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -205,9 +208,15 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
                             dz = min_image(sa.z, sb.z, L);
                         }
                         const double r2 = dx * dx + dy * dy + dz * dz;
-                        if (coul_pair<0>(A, r2, sa.w * sb.w, cut_bits, acc[2])) {           // ewalds.jl:359
+                        double c1 = 0.0;
+                        if (coul_pair<0>(A, r2, sa.w * sb.w, cut_bits, PM ? c1 : acc[2])) {           // ewalds.jl:359
                             if (atomicExch(&A.ovl[a0 + p], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
                             if (atomicExch(&A.ovl[b0 + qi], 1u) == 0u) atomicAdd(A.n_ovl, 1u);
+                        }
+                        if (PM && c1 != 0.0) {
+                            acc[2] += c1;
+                            atomicAdd(&A.per_mol[3 * (size_t)(a0 + p) + 2], c1);
+                            atomicAdd(&A.per_mol[3 * (size_t)(b0 + qi) + 2], c1);
                         }
                     }
                 }
@@ -236,8 +245,16 @@ __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__
                             dz = min_image(sa.z, sb.z, L);
                         }
                         const double r2 = dx * dx + dy * dy + dz * dz;
-                        if (r2 < (A.rc_lj2 + 100))
-                            lj_pair(lj.eps, lj.sig, r2, dx, dy, dz, rx, ry, rz, acc[0], acc[1]);
+                        if (r2 < (A.rc_lj2 + 100)) {
+                            if (PM) {
+                                double l0 = 0.0, l1 = 0.0;
+                                lj_pair(lj.eps, lj.sig, r2, dx, dy, dz, rx, ry, rz, l0, l1);
+                                acc[0] += l0; acc[1] += l1;
+                                atomicAdd(&A.per_mol[3 * (size_t)(a0 + p)], l0); atomicAdd(&A.per_mol[3 * (size_t)(a0 + p) + 1], l1);
+                                atomicAdd(&A.per_mol[3 * (size_t)(b0 + qi)], l0); atomicAdd(&A.per_mol[3 * (size_t)(b0 + qi) + 1], l1);
+                            } else
+                                lj_pair(lj.eps, lj.sig, r2, dx, dy, dz, rx, ry, rz, acc[0], acc[1]);
+                        }
                     }
                 }
             }
