@@ -142,6 +142,13 @@ int mmc_set_atom(mmc_handle *h, int64_t i, const double r[3]);
  * EWALD also rebuilds S(k) into both buffers like RecipLong does. Unsharded handles only. */
 int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out);
 
+/* LJ_poly_ΔU(i) (Ewald/energy.jl:209-290) and EwaldShort(i) (Ewald/ewalds.jl:892-910) for EVERY molecule i from one
+ * evaluation — the rows that potential() sums at energy.jl:966-1001, kept per molecule.  Arrays of n_mol
+ * entries in molecule order, any of them may be NULL: lj_pot[i] = 4·pot, lj_vir[i] = 24·vir/3, coul[i] = pot·factor
+ * (0 with overlap[i] = 1 when the overlap rule of ewalds.jl:359 fires for molecule i; coul is 0 for LJ_ONLY).  Uniform
+ * topologies, unsharded handles.  Row sums are accumulated with FP64 atomics: equal to the per-i calls to ~1e-13 relative. */
+int mmc_energy_all(mmc_handle *h, int32_t style, double *lj_pot, double *lj_vir, double *coul, int32_t *overlap);
+
 /* sharded variant (world > 1): each rank evaluates its share of the molecule-pair work and of
  * the sites of S(k) and leaves MMC_NPARTIAL doubles in device memory at d_partials; the caller
  * sums that buffer across ranks (NCCL all-reduce over NVLink) and calls finalize on every rank.

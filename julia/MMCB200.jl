@@ -103,6 +103,14 @@ function potential_host(e::Engine, coords, com, style::Cint = EWALD)
     p
 end
 
+# LJ_poly_ΔU(i, …) and EwaldShort(i, …)[1] for every molecule i from one evaluation (the rows potential() sums)
+function energy_all(e::Engine, n_mol::Integer, style::Cint = EWALD)
+    lj = Vector{Float64}(undef, n_mol); vir = similar(lj); qq = similar(lj); ov = Vector{Int32}(undef, n_mol)
+    check(e, ccall((:mmc_energy_all, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                   e.h, style, lj, vir, qq, ov))
+    lj, vir, qq, ov
+end
+
 # potential(moa, soa, tot, ewald, vdwTable, sim_props[, "ewald"])  — Ewald/energy.jl:864-1032
 function potential(e::Engine, style::Cint = EWALD)
     p = Props()

@@ -504,6 +504,27 @@ __global__ void k_pair_reduce(const double4 *partial, int nb, const unsigned int
 }
 
 // ------------------------------------------------------------------ cell binning + gather
+// per-molecule rows (evaluation order) → the caller's arrays in molecule order, scaled as LJ_poly_ΔU (energy.jl:289:
+// 4·pot, 24·vir/3) and EwaldShort (ewalds.jl:905: pot·factor) return them; a flagged molecule reports (0, overlap)
+// like EwaldReal's early return (ewalds.jl:359-360)
+struct PerMolArgs {
+    const double *rows; const int *perm; const unsigned int *ovl;
+    int n_mol, want_qq; double factor;
+    double *lj_pot, *lj_vir, *coul; int *overlap;
+};
+
+__global__ void k_permol_scatter(PerMolArgs A)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n_mol) return;
+    const int m = A.perm ? A.perm[p] : p;
+    A.lj_pot[m] = 4 * A.rows[3 * (size_t)p];
+    A.lj_vir[m] = 24 * A.rows[3 * (size_t)p + 1] / 3;
+    const bool ov = A.want_qq && A.ovl[p] != 0u;
+    A.coul[m] = (A.want_qq && !ov) ? A.rows[3 * (size_t)p + 2] * A.factor : 0.0;
+    A.overlap[m] = ov ? 1 : 0;
+}
+
 struct CellArgs {
     const double4 *com;
     int n_mol, ncd;

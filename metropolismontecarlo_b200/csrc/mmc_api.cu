@@ -116,6 +116,7 @@ struct mmc_handle {
     int ncell_cap = 0;
     double4 *d_scom = nullptr, *d_ssite = nullptr;
     double *d_mrows = nullptr;   // k_pairs_v6: cell-sorted state as rows of 12 doubles
+    double *d_permol = nullptr, *d_permol_out = nullptr;   // mmc_energy_all: per-molecule rows (evaluation order) and the scaled output arrays
     float4 *d_gf = nullptr;      //             and cell-local float COMs
     double4 *d_pair_partial = nullptr;
     int pair_grid = 0;
@@ -206,6 +207,7 @@ void free_system(mmc_handle *h)
     dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
     h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
     dfree(h->d_mrows); dfree(h->d_gf); dfree(h->d_chain); h->chain_bytes = 0;
+    dfree(h->d_permol); dfree(h->d_permol_out);
     dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl);
     dfree(h->d_rhok_partial); dfree(h->d_units); dfree(h->d_slots);
     h->units_cap = 0; h->slots_cap = 0;
@@ -402,6 +404,7 @@ struct EvalCtx {
     int rank, world;
     cudaEvent_t wait_sites = nullptr;   // mmc_potential_host: the sites arrive on the side stream; wait for them before the gather
     bool rhok_external = false;         //                     ... and the ρ(k) partials are produced there, chunk by chunk
+    double *per_mol = nullptr;          // mmc_energy_all: [n_mol x 3] per-molecule rows (general kernel, evaluation order)
 };
 
 // out == nullptr: partials only, written from block `block0` on (the caller reduces all blocks later); *nb_out = blocks used
@@ -571,7 +574,7 @@ bool escalate_pair_level(mmc_handle *h)
 // [MMC_NSCAL ..) ρ(k) partial (re,im).
 int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
 {
-    const bool force_general = h->pair_level >= 5;
+    const bool force_general = h->pair_level >= 5 || E.per_mol != nullptr;
     if (!h->uniform) FAIL(MMC_EINVAL, "pair kernel needs a uniform topology (internal)");
     const DevSystem &S = h->S;
     const int US = h->US;
@@ -688,6 +691,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     if (US <= 4) for (const LJActive &e : h->lj) { P.lj_eps_tab[e.a * US + e.b] = e.eps; P.lj_sig_tab[e.a * US + e.b] = e.sig; }
     P.partial = h->d_pair_partial; P.ovl = h->d_ovl; P.n_ovl = h->d_novl; P.max_dev = h->d_maxdev;
     P.err_flag = h->d_errflag;
+    P.per_mol = E.per_mol;
     P.rclj_bits = 0; P.rcqq_bits = 0; P.cutlj_bits = 0; P.cutqq_bits = 0;
     { double v;
       v = P.rc_lj2; std::memcpy(&P.rclj_bits, &v, 8); v = P.rc_qq2; std::memcpy(&P.rcqq_bits, &v, 8);
@@ -779,8 +783,11 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         const size_t smem = (2 * PAIR_TILE + 2 * PAIR_TILE * (size_t)US) * sizeof(double4) +
                             (size_t)PAIR_WARPS * PAIR_QCAP * sizeof(unsigned);
         grid = (int)std::max(1LL, std::min<long long>(2 * h->sm_count, my_units));
-        if (US == 3) k_pairs<3><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
-        else k_pairs<0><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+        if (P.per_mol) {
+            if (US == 3) k_pairs<3, true><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+            else k_pairs<0, true><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+        } else if (US == 3) k_pairs<3, false><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+        else k_pairs<0, false><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
     }
     LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
@@ -1021,8 +1028,10 @@ int mmc_create(const mmc_config *cfg, mmc_handle **out)
     if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return fail("copy stream", e);
     for (auto &ev : h->ev_chunk)
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
-    cudaFuncSetAttribute(k_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_pairs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_pairs<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_pairs<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_pairs<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_pairs<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     pairs_fast_set_attributes();
     *out = h;
     return MMC_OK;
@@ -1658,6 +1667,41 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
     }
     if (style == MMC_STYLE_EWALD) h->new_valid = false;
     return rc;
+}
+
+// a2 + a3/a4 for EVERY molecule in one evaluation: what Σ_i in potential() iterates over (energy.jl:966-1001), kept per i.
+// One pass over the unique in-cutoff pairs (cell lists), each pair credited to both molecules.
+int mmc_energy_all(mmc_handle *h, int32_t style, double *lj_pot, double *lj_vir, double *coul, int32_t *overlap)
+{
+    if (!h) return MMC_EINVAL;
+    int rc = style_check(h, style);
+    if (rc) return rc;
+    if (style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "mmc_energy_all is for molecular systems");
+    if (!h->uniform) FAIL(MMC_EINVAL, "mmc_energy_all needs a uniform topology");
+    { int rcf = flush_pending(h); if (rcf) return rcf; }
+    if ((rc = ensure_vec(h))) return rc;
+    const DevSystem &S = h->S;
+    const size_t n = (size_t)S.n_mol;
+    if (!h->d_permol) {
+        CK(cudaMalloc(&h->d_permol, sizeof(double) * 3 * n));
+        CK(cudaMalloc(&h->d_permol_out, sizeof(double) * 3 * n + sizeof(int) * n));
+    }
+    CK(cudaMemsetAsync(h->d_permol, 0, sizeof(double) * 3 * n, h->stream));
+    EvalCtx E{1.0, S.box, S.kappa, S.cfac, 0, 1};
+    E.rhok_external = true;          // pair part only: ρ(k) is not a per-molecule quantity
+    E.per_mol = h->d_permol;
+    if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+    const bool want_qq = (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF);
+    double *o = h->d_permol_out;
+    PerMolArgs A{h->d_permol, h->last_mode == 0 ? h->d_perm : nullptr, h->d_ovl, S.n_mol, want_qq ? 1 : 0, S.factor,
+                 o, o + n, o + 2 * n, reinterpret_cast<int *>(o + 3 * n)};
+    k_permol_scatter<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(A); LAUNCH_CHECK();
+    if (lj_pot) CK(cudaMemcpyAsync(lj_pot, o, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (lj_vir) CK(cudaMemcpyAsync(lj_vir, o + n, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (coul) CK(cudaMemcpyAsync(coul, o + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (overlap) CK(cudaMemcpyAsync(overlap, o + 3 * n, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MMC_OK;
 }
 
 // End to end in one call: positions from HOST arrays (pointer(soa.coords), pointer(moa.COM)) → Properties on the host, with the

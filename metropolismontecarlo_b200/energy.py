@@ -204,6 +204,16 @@ class Engine:
         self._ck(self.lib.mmc_potential(self.h, _style(style), C.byref(out)))
         return out
 
+    def energy_all(self, style="ewald"):
+        """LJ_poly_ΔU(i) (energy.jl:209-290) and EwaldShort(i)[1] (ewalds.jl:892-910) for every molecule at once:
+        (lj_pot[n_mol], lj_vir[n_mol], coul[n_mol], overlap[n_mol]) in molecule order."""
+        n = self.n_mol
+        lj, vir, qq = (np.empty(n) for _ in range(3))
+        ov = np.empty(n, dtype=np.int32)
+        self._ck(self.lib.mmc_energy_all(self.h, _style(style), _dp(lj), _dp(vir), _dp(qq),
+                                         ov.ctypes.data_as(C.POINTER(C.c_int32))))
+        return lj, vir, qq, ov
+
     def partial_count(self) -> int:
         n = C.c_int64()
         self._ck(self.lib.mmc_partial_count(self.h, C.byref(n)))

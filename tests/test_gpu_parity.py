@@ -581,3 +581,57 @@ def test_potential_host_pipelined_equals_upload_then_potential():
     with pytest.raises(Exception):
         eng.potential_host(coords, bad, "ewald")
     eng.close()
+
+
+def test_energy_all_rows_equal_per_molecule_calls(c750):
+    """mmc_energy_all: LJ_poly_ΔU(i) and EwaldShort(i) for every i from ONE pass over the unique pairs,
+    against the oracle's per-molecule functions (energy.jl:209-290, ewalds.jl:293-376, 892-910) on coord750 (cell mode),
+    on a small NIST box (tile mode), with the overlap rule, and for the Wolf / LJ-only styles."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms, eng = c750
+    for rc, m in ((10.0, ms), (9.0, systems.load_nist(1))):      # cell mode (3^3 cells) and tile mode (L = 20)
+        eng.upload_system(m, rc, rc)
+        eng.PrepareEwaldVariables(systems.ALPHA / m.box)
+        s = ora_system(m)
+        ew = ora_ewald(m.box)
+        lj, vir, qq, ov = eng.energy_all("ewald")
+        assert not ov.any()
+        for i in range(1, m.n_mol + 1):
+            e0, v0 = ora.LJ_poly_dU(i, s, rc, m.box)
+            c0, _, ov0 = ora.EwaldShort(i, s, ew, rc, m.box)
+            assert not ov0
+            assert rel(lj[i - 1], e0) < 1e-11 and rel(qq[i - 1], c0) < 1e-10, (rc, i)
+            assert abs(vir[i - 1] - v0) < 1e-10 * max(1.0, abs(v0), abs(e0)), (rc, i)
+        # Σ_i rows / 2 is what potential() reports (energy.jl:966-1001)
+        p = eng.potential("ewald")
+        assert rel(lj.sum() / 2, p.lj) < 1e-11 and rel(qq.sum() / 2, p.real) < 1e-11
+        ljw, _, qqw, _ = eng.energy_all("wolf")
+        assert np.allclose(ljw, lj, rtol=1e-12) and np.allclose(qqw, qq, rtol=1e-12)
+        ljo, _, qqo, ovo = eng.energy_all("lj")
+        assert np.allclose(ljo, lj, rtol=1e-12) and not qqo.any() and not ovo.any()
+    # overlap: both molecules of the offending pair report (0, overlap) like EwaldReal's early return
+    mo = ms.copy()
+    shift = (mo.coords[0] + np.array([0.3, 0.0, 0.0])) - mo.coords[4]
+    mo.coords[3:6] += shift
+    mo.com[1] = np.clip(mo.com[1] + shift, 0.0, mo.box)
+    eng.upload_system(mo, 10.0, 10.0)
+    eng.PrepareEwaldVariables(systems.ALPHA / mo.box)
+    s = ora_system(mo)
+    ew = ora_ewald(mo.box)
+    lj, vir, qq, ov = eng.energy_all("ewald")
+    assert ov[0] == 1 and ov[1] == 1 and ov.sum() == 2 and qq[0] == 0.0 and qq[1] == 0.0
+    for i in (1, 2, 3, 17, 400):
+        c0, _, ov0 = ora.EwaldShort(i, s, ew, 10.0, mo.box)
+        assert bool(ov[i - 1]) == bool(ov0) and (rel(qq[i - 1], c0) < 1e-10 if c0 != 0 else qq[i - 1] == 0.0)
+    eng.upload_system(ms, 10.0, 10.0)
+    # config D (4000 molecules, 4^3+ cells): rows against the engine's own per-molecule kernel
+    md = systems.spce_lattice(4000)
+    ed = water_engine(md, 10.0)
+    lj, vir, qq, ov = ed.energy_all("ewald")
+    for i in (1, 2, 1999, 4000):
+        e, v = ed.LJ_poly_ΔU(i)
+        c, _, o = ed.EwaldShort(i)
+        assert rel(lj[i - 1], e) < 1e-11 and rel(qq[i - 1], c) < 1e-10 and abs(vir[i - 1] - v) < 1e-9 * max(1.0, abs(v))
+    p = ed.potential("ewald")
+    assert rel(lj.sum() / 2, p.lj) < 1e-11 and rel(qq.sum() / 2, p.real) < 1e-10
+    ed.close()
