@@ -1,0 +1,125 @@
+"""Config E at BASELINE.json's full size (256 000 SPC/E molecules, 768 000 sites, L = 197.757 Å) on one B200.
+
+The oracle's potential() is O(N²) (about a minute on 16 host cores), so the full-size checks are the size-independent
+properties of the path plus every oracle piece that is O(N) or O(n_s · NK):
+  * per-molecule rows: mmc_energy_all against the oracle's LJ_poly_ΔU(i) / EwaldShort(i) for sampled i (each is one
+    O(N) scan, energy.jl:209-290, ewalds.jl:293-376), and Σ_i rows / 2 == potential()'s LJ and real-space terms
+    (energy.jl:966-1001) — together these pin the pair part of the full evaluation to the oracle;
+  * RecipLong and EwaldSelf against the oracle directly (ewalds.jl:538-604, 829-833);
+  * all six pair kernels (v6 … general) agree; sharded partial sums over 8 emulated ranks == unsharded;
+  * a volume trial at f = 1 reproduces potential(); ρ(k) after delta updates == a fresh rebuild.
+Tolerance 1e-10 relative (north star), stated per assertion.
+"""
+import numpy as np
+import pytest
+
+from metropolismontecarlo_b200 import systems
+from oracle import oracle as ora
+from tests.util import ora_ewald, ora_system, rel
+
+pytestmark = pytest.mark.gpu
+
+N_E = 256000
+
+
+@pytest.fixture(scope="module")
+def cfg_e():
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.spce_lattice(N_E)
+    eng = water_engine(ms, 10.0)
+    yield ms, eng
+    eng.close()
+
+
+def test_full_size_rows_and_totals_against_oracle(cfg_e):
+    ms, eng = cfg_e
+    assert ms.n_sites == 768000 and abs(ms.box - 197.757) < 1e-2
+    p = eng.potential("ewald")
+    info = eng.last_eval_info()
+    assert info["mode"] == "cells" and info["cells_per_dim"] == 19 and info["pair_kernel"] == "k_pairs_v6"
+    lj, vir, qq, ov = eng.energy_all("ewald")
+    assert not ov.any() and p.overlaps == 0
+    assert rel(lj.sum() / 2, p.lj) < 1e-10 and rel(qq.sum() / 2, p.real) < 1e-10
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    rng = np.random.default_rng(11234)
+    sample = np.unique(np.concatenate([[1, 2, N_E - 1, N_E], rng.integers(1, N_E + 1, 60)]))
+    for i in sample:
+        e0, v0 = ora.LJ_poly_dU(int(i), s, 10.0, ms.box)
+        c0, _, ov0 = ora.EwaldShort(int(i), s, ew, 10.0, ms.box)
+        assert not ov0
+        assert rel(lj[i - 1], e0) < 1e-10 and rel(qq[i - 1], c0) < 1e-10, i
+        assert abs(vir[i - 1] - v0) < 1e-10 * max(1.0, abs(v0), abs(e0)), i
+    # k-space and self term: the oracle itself at full size
+    e_recip = ora.RecipLong(ew, ms.coords, ms.charge, ms.box) * systems.FACTOR
+    assert rel(p.recip, e_recip) < 1e-10
+    assert rel(p.self_, ora.EwaldSelf(ew, ms.charge)) < 1e-10     # Σq² over 768 000 sites: serial (oracle) vs tree order
+    assert rel(p.energy, p.lj + p.real + p.recip + p.self_) < 1e-14
+    assert rel(p.virial, vir.sum() / 2 + (p.real + p.recip + p.self_) / 3) < 1e-10       # energy.jl:1019-1021
+    old, new = eng.rhok()
+    assert np.array_equal(old, new)                       # RecipLong writes both buffers (ewalds.jl:598-599)
+    assert abs(old - (ew.sum_new[:, 0] + 1j * ew.sum_new[:, 1])).max() < 1e-12 * 0.8476 * ms.n_sites
+
+
+def test_full_size_pair_kernels_agree(cfg_e):
+    ms, eng = cfg_e
+    ref = None
+    for level in (0, 1, 2, 3, 4, 5):
+        eng.debug_set("pair_level", level)
+        p = eng.potential("ewald")
+        assert eng.last_eval_info()["pair_kernel"] == ("k_pairs_v6", "k_pairs_v5", "k_pairs_v4", "k_pairs_v3",
+                                                      "k_pairs_fast<64>", "k_pairs")[level]
+        if ref is None:
+            ref = p
+            assert eng.last_eval_info()["pairs_in_cutoff"] > 17_000_000
+        else:
+            assert rel(p.lj, ref.lj) < 1e-11 and rel(p.real, ref.real) < 1e-11 and rel(p.virial, ref.virial) < 1e-11, level
+            assert p.recip == ref.recip
+    eng.debug_set("pair_level", 0)
+
+
+def test_full_size_sharded_sum_equals_unsharded(cfg_e):
+    import torch
+    from metropolismontecarlo_b200.energy import water_engine
+    ms, eng = cfg_e
+    ref = eng.potential("ewald")
+    world = 8
+    engs = [water_engine(ms, 10.0, rank=r, world=world) for r in range(world)]
+    n = engs[0].partial_count()
+    bufs = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in range(world)]
+    for e, b in zip(engs, bufs):
+        e.potential_partial("ewald", b.data_ptr())
+    torch.cuda.synchronize()
+    total = torch.stack(bufs).sum(0)
+    got = engs[3].potential_finalize("ewald", total.clone().data_ptr())
+    assert got is not None
+    for f in ("energy", "virial", "coulomb", "lj", "real", "recip", "self_"):
+        assert rel(getattr(got, f), getattr(ref, f)) < 1e-11, f
+    for e in engs:
+        e.close()
+
+
+def test_full_size_volume_identity_and_rhok_delta(cfg_e):
+    ms, eng = cfg_e
+    ref = eng.potential("ewald")
+    v = eng.volume_trial(ms.box, systems.ALPHA / ms.box, "ewald")
+    for f in ("energy", "virial", "coulomb", "lj", "real", "recip"):
+        assert rel(getattr(v, f), getattr(ref, f)) < 1e-12, f
+    eng.volume_reject()
+    # 20 accepted single-molecule moves through the delta update, then a fresh rebuild
+    rng = np.random.default_rng(5)
+    coords, com = ms.coords.copy(), ms.com.copy()
+    for k in range(20):
+        i = int(rng.integers(1, N_E + 1))
+        d = rng.uniform(-0.3, 0.3, 3)
+        a = 3 * (i - 1)
+        t = eng.trial_move(i, com[i - 1] + d, coords[a:a + 3] + d, "ewald")
+        assert not t.overlap_new
+        eng.accept()
+        coords[a:a + 3] += d
+        com[i - 1] += d
+    old_delta, _ = eng.rhok()
+    eng.RecipLong()
+    fresh, _ = eng.rhok()
+    assert abs(old_delta - fresh).max() < 1e-12 * 0.8476 * ms.n_sites
+    eng.upload_system(ms, 10.0, 10.0)
