@@ -201,7 +201,9 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
         if (smem + 16 * 1024 > (size_t)max_optin || held > CHAINS_MAXIT * CHAINS_WORKERS)
             FAIL(MMC_EINVAL, "device loop: the system does not fit the cluster's shared memory; use mmc_loop_run");
     } else if (C > 1 && (S.n_mol + C - 1) / C > CHAINS_MAXIT * CHAINS_WORKERS) C = 1;
-    if (S.n_mol < 2) FAIL(MMC_EINVAL, "device loop: at least 2 molecules");
+    // a lone molecule: the block kernels prepare the next trial while the current one is evaluated, which presumes another
+    // molecule to move next; the per-move kernels give the same record (and there is no pair work to batch)
+    if (S.n_mol < 2) return mmc_loop_run(h, p, com, quat, db, uniforms, n_uniforms, n_moves, e0, v0, accepted, delta_out, st);
     if ((rc = flush_pending(h))) return rc;
     // one device block: [uniforms | quat (C replicas) | db | delta | out | accepted]
     const size_t n_q1 = 4 * (size_t)S.n_mol, n_q = n_q1 * C, n_db = 3 * (size_t)S.n_sites;

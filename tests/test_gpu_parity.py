@@ -635,3 +635,62 @@ def test_energy_all_rows_equal_per_molecule_calls(c750):
     p = ed.potential("ewald")
     assert rel(lj.sum() / 2, p.lj) < 1e-11 and rel(qq.sum() / 2, p.real) < 1e-10
     ed.close()
+
+
+def _subsystem(ms, n):
+    out = ms.copy()
+    out.coords, out.charge, out.atype = ms.coords[:3 * n].copy(), ms.charge[:3 * n].copy(), ms.atype[:3 * n].copy()
+    out.first_atom, out.last_atom, out.com = ms.first_atom[:n].copy(), ms.last_atom[:n].copy(), ms.com[:n].copy()
+    out.db, out.quat = ms.db[:3 * n].copy(), ms.quat[:n].copy()
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
+def test_tiny_systems(n):
+    """Ragged / minimum sizes: 1–5 molecules (a lone molecule has no pair term at all; fewer molecules than lanes, than
+    CTAs of the move kernel, than k-space site chunks) through every entry point that takes the system as a whole, in a
+    cell-mode box (L = 30) and a tile-mode box (L = 20)."""
+    from metropolismontecarlo_b200.energy import LoopParams, water_engine
+    for cfg, rc in ((4, 10.0), (1, 9.0)):
+        ms = _subsystem(systems.load_nist(cfg), n)
+        s = ora_system(ms)
+        ew = ora_ewald(ms.box)
+        eng = water_engine(ms, rc)
+        want = ora.potential_ewald(s, ew, rc, rc, ms.box, 1)
+        _check_props(eng.potential("ewald"), want)
+        _check_props(eng.potential("wolf"), ora.potential_wolf(s, ew, rc, rc, ms.box, 1))
+        if n == 1:
+            assert want.lj == 0.0 and want.real == 0.0 and want.recip != 0.0
+        lj, vir, qq, ov = eng.energy_all("ewald")
+        for i in range(1, n + 1):
+            e0, v0 = ora.LJ_poly_dU(i, s, rc, ms.box)
+            c0, _, _ = ora.EwaldShort(i, s, ew, rc, ms.box)
+            assert abs(lj[i - 1] - e0) <= 1e-11 * abs(e0) and abs(qq[i - 1] - c0) <= 1e-10 * abs(c0)
+            assert abs(eng.LJ_poly_ΔU(i)[0] - e0) <= 1e-12 * abs(e0)
+            assert abs(eng.EwaldShort(i)[0] - c0) <= 1e-11 * abs(c0)
+        # a trial move of the last molecule: ΔU == U(new) − U(old) from two full evaluations
+        d = np.array([0.11, -0.07, 0.05])
+        t = eng.trial_move(n, ms.com[n - 1] + d, ms.coords[3 * (n - 1):] + d, "ewald")
+        eng.accept()
+        s.coords[3 * (n - 1):] += d
+        s.com[n - 1] += d
+        after = ora.potential_ewald(s, ora_ewald(ms.box), rc, rc, ms.box, 1)
+        du = (t.lj_new - t.lj_old) + (t.qq_new - t.qq_old) + t.d_recip
+        assert abs(du - (after.energy - want.energy)) < 1e-9 * max(1.0, abs(want.energy) * 1e-3)
+        _check_props(eng.potential("ewald"), after)
+        # block of moves on the device == the per-move protocol on the same uniforms
+        u = np.random.default_rng(n).random(4000)
+        outs = []
+        for device in (False, True):
+            e2 = water_engine(ms, rc)
+            g0 = e2.potential("ewald")
+            com, quat = ms.com.copy(), ms.quat.copy()
+            r, acc, delta, st = e2.loop_run(LoopParams(298.15, 0.3, 0.05, 0.5, 1.0, 0, 1), com, quat, ms.db, u, 300,
+                                            g0.energy, g0.virial, device=device)
+            fresh = e2.potential("ewald")
+            assert r == 0 and abs(st.total_energy - fresh.energy) < 1e-9 * abs(fresh.energy)
+            outs.append((acc.copy(), st.uniforms_used, com.copy()))
+            e2.close()
+        assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+        assert np.abs(outs[0][2] - outs[1][2]).max() < 1e-12
+        eng.close()
