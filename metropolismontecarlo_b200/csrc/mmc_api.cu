@@ -140,6 +140,7 @@ struct mmc_handle {
     int use_v3 = 1;              // 0 disables the v3 pair kernel (A/B testing)
     int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v6, 1 k_pairs_v5, 2 k_pairs_v4, 3 k_pairs_v3, 4 k_pairs_fast, 5 general k_pairs
                                  // (raised when a kernel declines the state)
+    int rhok_split = 1;          // ρ(k) rebuild: CTAs per resident slot (short CTAs let higher-priority kernels in between)
     int pair_floor = 0;          // lowest level the chain may start from (mmc_debug_set "pair_level": A/B tests)
     bool uniform_q = false;      // every molecule carries the charges of molecule 1 (per site index)
     double q_site[MMC_MAX_SITES] = {0};
@@ -416,7 +417,8 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
     const int nkv = h->S.nkvecs;
     const bool v2 = h->n_kpairs <= 32 && h->S.nk <= 6 && h->use_rhok_v2;
     const int chunk = v2 ? RHOK2_SITES : RHOK_SITES;
-    int per = std::max(2 * chunk, (n + 2 * h->sm_count - 1) / (2 * h->sm_count));
+    const int waves = 2 * h->sm_count * std::max(1, h->rhok_split);
+    int per = std::max(2 * chunk, (n + waves - 1) / waves);
     per = (per + chunk - 1) / chunk * chunk;
     const int nb = std::max(1, (n + per - 1) / per);
     if (nb_out) *nb_out = nb;
@@ -1967,6 +1969,11 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     if (k == "chain_cluster") { if (value < 1 || value > CHAINC_MAXC) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
     if (k == "v6_ctas_per_sm") { if (value < 1 || value > 5) FAIL(MMC_EINVAL, "v6_ctas_per_sm must be 1..5"); h->v6_ctas_per_sm = (int)value; return MMC_OK; }
+    if (k == "rhok_split") {
+        if (value < 1 || value > 64) FAIL(MMC_EINVAL, "rhok_split must be 1..64");
+        h->rhok_split = (int)value;
+        return MMC_OK;
+    }
     if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v6 .. 5 general)
         if (value < 0 || value > 5) FAIL(MMC_EINVAL, "pair_level must be 0..5");
         h->pair_floor = (int)value; h->pair_level = (int)value;
