@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(RHOK2_BLOCK, 2) k_rhok_pairs(Rhok2Args A)
 {
     constexpr int NW = RHOK2_BLOCK / 32;
     constexpr int NACC = 4 + 8 * NK;
-    __shared__ double2 s_t[RHOK2_SITES][3][NK + 1];          // (cos, sin) of k·x, k·y, k·z; x carries q
+    // (cos, sin) of k·x, k·y, k·z; x carries q.  Row stride 16·(NK+1 | 1) bytes: an odd number of 16-byte words, so the table
+    // build (one row per thread, 16-byte stores) is free of bank conflicts (a 96-byte stride is 8-way conflicted)
+    __shared__ double2 s_t[RHOK2_SITES][3][(NK + 1) | 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c0 = A.s_begin + blockIdx.x * A.per_block;
     const int c1 = min(A.s_end, c0 + A.per_block);
