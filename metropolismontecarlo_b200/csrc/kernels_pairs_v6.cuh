@@ -55,6 +55,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 struct V6Extra {
     const double *rows;     // [n_mol][12], cell-sorted
     const float4 *gf;       // [n_mol], COM relative to its own cell's origin
+    // dynamic unit scheduling (NULL: units dealt round-robin, one partial per CTA).  Cells hold 9..64 molecules on the lattice
+    // start, units differ 10x in cost, and a static deal leaves the slowest CTA 8 % (one GPU) to 50 % (one rank of eight: 3.5
+    // units per CTA) behind the mean.  With tickets a CTA takes the next unit when it is done with its own; every unit's sums
+    // are written per (unit, warp) and folded in unit order afterwards, so the result does not depend on which CTA ran what.
+    unsigned int *ticket;   // zeroed before the launch
+    double4 *unit_partial;  // [units of this rank][V6_WARPS]
 };
 
 template <int DEG, bool DIRECT>
@@ -71,6 +77,7 @@ __global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant_
     __shared__ int s_boff[V6_SLOTS + 1], s_bglob[V6_SLOTS], s_code[V6_SLOTS], s_nA, s_nB, s_pass_end;
     __shared__ double s_red[4 * V6_WARPS];
     __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ long long s_unext;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned short *q = s_queue + warp * V6_QCAP;
@@ -102,8 +109,13 @@ __global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant_
     };
     long long u = A.unit_begin + blockIdx.x;
     int4 desc = fetch_desc(u);
+    const bool dyn = X.ticket != nullptr;
+    // one ticket is always in flight (drawn a unit ahead), so the atomic's round trip is never waited for
+    unsigned tk_pending = 0;
+    if (dyn && tid == 0) tk_pending = atomicAdd(X.ticket, 1u);
+    long long u_next = u + gridDim.x;
 
-    for (; u < A.unit_end; u += gridDim.x) {
+    for (; u < A.unit_end; u = u_next) {
         const int c = (int)(u / V3_GROUPS), g = (int)(u - (long long)c * V3_GROUPS);
         const int sl0 = c_v3_group_begin[g], nsl = c_v3_group_begin[g + 1] - sl0;
       // a group whose neighbour cells hold more than V6_BCAP molecules together is evaluated in two passes
@@ -138,7 +150,16 @@ __global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant_
                 bulk_g2s(drow, X.rows + (size_t)desc.x * V6_ROW, (unsigned)cnt * V6_ROW * 8, &s_mbar);
                 bulk_g2s(dgf, X.gf + desc.x, (unsigned)cnt * 16, &s_mbar);
             }
-            if (bad || se == nsl) desc = fetch_desc(u + gridDim.x);   // next unit's descriptors travel while this one is evaluated
+            if (bad || se == nsl) {                        // next unit's descriptors travel while this one is evaluated
+                long long un = u + gridDim.x;
+                if (dyn) {
+                    const unsigned tk = __shfl_sync(0xffffffffu, tk_pending, 0);
+                    un = A.unit_begin + (long long)gridDim.x + tk;
+                    if (lane == 0 && un < A.unit_end) tk_pending = atomicAdd(X.ticket, 1u);
+                }
+                if (lane == 0) s_unext = un;
+                desc = fetch_desc(un);
+            }
         }
         mbar_wait(&s_mbar, phase);
         phase ^= 1u;
@@ -173,6 +194,7 @@ __global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant_
             }
         }
         __syncthreads();
+        u_next = s_unext;                                  // written by warp 0 in the unit's last pass (earlier passes: stale, unused)
         const int self_n = (g == 0 && s_begin == 0) ? nA : 0;   // slot 0 of group 0 is the home cell itself: keep q > p
 
         int head = 0, tail = 0;                            // warp-private ring window [head, tail)
@@ -281,9 +303,27 @@ __global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant_
             if (last) break;
         }
       }
+      if (dyn) {   // this unit's sums, per warp, at a place that depends on the unit only
+          const double w0 = warp_sum(acc_lj), w1 = warp_sum(acc_vir), w2 = warp_sum(acc_q);
+          if (lane == 0) X.unit_partial[(size_t)(u - A.unit_begin) * V6_WARPS + warp] = make_double4(w0, w1, w2, (double)my_pairs);
+          acc_lj = 0.0; acc_vir = 0.0; acc_q = 0.0; my_pairs = 0;
+      }
     }
+    if (dyn) return;
     __syncthreads();
     double accp[4] = {acc_lj, acc_vir, acc_q, (double)my_pairs};
     block_sum<4, V6_BLOCK>(accp, s_red);
     if (tid == 0) A.partial[blockIdx.x] = make_double4(accp[0], accp[1], accp[2], accp[3]);
+}
+
+// stage 1 of the fold of the per-(unit, warp) sums: CTA b adds its contiguous share in a fixed order
+__global__ void __launch_bounds__(256) k_unit_fold(const double4 *__restrict__ unit_partial, long long n, double4 *out)
+{
+    __shared__ double s_red[4 * 8];
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long lo = per * blockIdx.x, hi = (lo + per < n) ? lo + per : n;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) { const double4 p = unit_partial[i]; v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w; }
+    block_sum<4, 256>(v, s_red);
+    if (threadIdx.x == 0) out[blockIdx.x] = make_double4(v[0], v[1], v[2], v[3]);
 }

@@ -140,6 +140,9 @@ struct mmc_handle {
     int use_v3 = 1;              // 0 disables the v3 pair kernel (A/B testing)
     int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v6, 1 k_pairs_v5, 2 k_pairs_v4, 3 k_pairs_v3, 4 k_pairs_fast, 5 general k_pairs
                                  // (raised when a kernel declines the state)
+    int v6_dynamic = 1;          // k_pairs_v6 draws units by ticket (0: static round-robin deal)
+    double4 *d_unit_partial = nullptr;
+    size_t unit_partial_cap = 0;
     int rhok_split = 1;          // ρ(k) rebuild: CTAs per resident slot (short CTAs let higher-priority kernels in between)
     int pair_floor = 0;          // lowest level the chain may start from (mmc_debug_set "pair_level": A/B tests)
     bool uniform_q = false;      // every molecule carries the charges of molecule 1 (per site index)
@@ -208,7 +211,7 @@ void free_system(mmc_handle *h)
     dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
     h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
     dfree(h->d_mrows); dfree(h->d_gf); dfree(h->d_chain); h->chain_bytes = 0;
-    dfree(h->d_permol); dfree(h->d_permol_out);
+    dfree(h->d_permol); dfree(h->d_permol_out); dfree(h->d_unit_partial); h->unit_partial_cap = 0;
     dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl);
     dfree(h->d_rhok_partial); dfree(h->d_units); dfree(h->d_slots);
     h->units_cap = 0; h->slots_cap = 0;
@@ -741,6 +744,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     P.unit_end = n_units * (E.rank + 1) / E.world;
     const long long my_units = P.unit_end - P.unit_begin;
     int grid;
+    long long v6_units = 0;      // > 0: k_pairs_v6 ran with tickets and left per-(unit, warp) sums
     if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
     if (v3 || v4 || v5 || v6) {
         {
@@ -756,7 +760,20 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         }
         if (v6) {
             grid = (int)std::max(1LL, std::min<long long>(h->v6_ctas_per_sm * h->sm_count, my_units));
-            launch_pairs_v6(v5_deg, v5_direct, grid, h->stream, P, h->d_slots, V6Extra{h->d_mrows, h->d_gf});
+            V6Extra X{h->d_mrows, h->d_gf, nullptr, nullptr};
+            if (h->v6_dynamic && E.world == 1) {   // measured on config E: -2.3 % on one GPU, but +5..25 µs on a rank's share of a 2..8-rank
+                                                    // evaluation (few units per CTA: the greedy order ends on expensive units), so ranks keep the static deal
+                const size_t need = (size_t)my_units * V6_WARPS;
+                if (need > h->unit_partial_cap) {
+                    dfree(h->d_unit_partial);
+                    CK(cudaMalloc(&h->d_unit_partial, sizeof(double4) * need));
+                    h->unit_partial_cap = need;
+                }
+                X.ticket = reinterpret_cast<unsigned int *>(h->d_flags + 5);      // cleared with the flags at the start of the evaluation
+                X.unit_partial = h->d_unit_partial;
+                v6_units = my_units;
+            }
+            launch_pairs_v6(v5_deg, v5_direct, grid, h->stream, P, h->d_slots, X);
         } else if (v5) {
             grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
             launch_pairs_v5(v5_deg, v5_direct, grid, h->stream, P, h->d_slots);
@@ -793,6 +810,10 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     }
     LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
+    if (v6_units > 0) {          // fold the unit sums in unit order: 64 contiguous shares, then the usual final fold
+        grid = (int)std::min<long long>(64, h->pair_grid);
+        k_unit_fold<<<grid, 256, 0, h->stream>>>(h->d_unit_partial, v6_units * V6_WARPS, h->d_pair_partial); LAUNCH_CHECK();
+    }
     k_pair_reduce<<<1, 256, 0, h->stream>>>(h->d_pair_partial, grid, h->d_novl, h->d_maxcount, h->d_errflag, d_vec);
     LAUNCH_CHECK();
     h->last_fast = v6 ? 6 : (v5 ? 5 : (v4 ? 4 : (v3 ? 3 : tile)));
@@ -1969,6 +1990,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     if (k == "chain_cluster") { if (value < 1 || value > CHAINC_MAXC) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
     if (k == "v6_ctas_per_sm") { if (value < 1 || value > 5) FAIL(MMC_EINVAL, "v6_ctas_per_sm must be 1..5"); h->v6_ctas_per_sm = (int)value; return MMC_OK; }
+    if (k == "v6_dynamic") { h->v6_dynamic = value != 0; return MMC_OK; }
     if (k == "rhok_split") {
         if (value < 1 || value > 64) FAIL(MMC_EINVAL, "rhok_split must be 1..64");
         h->rhok_split = (int)value;
