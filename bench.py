@@ -35,7 +35,7 @@ FLOP_PER_PAIR = 624          # 9 x 67 + 21 per in-cutoff water
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on config E at N=1, from the
 # `ncu --set full` capture summarised in profiles/r01_v6_ncu_full_pairs_and_rhok.txt (a profiler number is never
 # taken inside bench.py; the algorithmic bytes are the 35 MB of state, read once)
-NCU_DRAM_BYTES = {"k_pairs_v6": 30264320, "k_pairs_v5": 34369280, "k_pairs_v4": 34369280}
+NCU_DRAM_BYTES = {"k_pairs_v6": 30271488, "k_pairs_v5": 34369280, "k_pairs_v4": 34369280}
 
 
 def workload_config(n_mol):
@@ -478,7 +478,7 @@ def run_ours(args, rank, world, local_rank):
                          "isolated": {"ms": pair_ms_isolated, "achieved": alg_flops / (pair_ms_isolated * 1e-3) / 1e12,
                                       "frac": (alg_flops / (pair_ms_isolated * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None},
                          "traffic": NCU_DRAM_BYTES.get(info["pair_kernel"]) if world == 1 and ms.n_mol == N_MOL_E else None,
-                         "traffic_unit": "bytes of DRAM per launch (ncu, profiles/r01_v6_ncu_full_pairs_and_rhok.txt)"},
+                         "traffic_unit": "bytes of DRAM per launch (ncu, profiles/r01_v6c_ncu_full_pairs_tickets.txt)"},
             "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
                     "what": "N=1: mmc_potential_host (pinned host soa.coords + moa.COM in, Properties out, copies overlapped with compute); "
                             "N>1: mmc_upload_positions + sharded potential"},
