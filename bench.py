@@ -477,6 +477,8 @@ def run_ours(args, rank, world, local_rank):
                          "note": "achieved/frac are in situ (timed region, rho(k) rebuild running beside the pair kernel on a side stream)",
                          "isolated": {"ms": pair_ms_isolated, "achieved": alg_flops / (pair_ms_isolated * 1e-3) / 1e12,
                                       "frac": (alg_flops / (pair_ms_isolated * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None},
+                         "executed": {"fp64_instructions_per_pair": 204, "fp64_pipe_busy_pct": 41.6, "issue_slots_busy_pct": 64.4,
+                                      "source": "ncu --set full, profiles/r01_v6c_ncu_full_pairs_tickets.txt (static, not re-measured per run)"},
                          "traffic": NCU_DRAM_BYTES.get(info["pair_kernel"]) if world == 1 and ms.n_mol == N_MOL_E else None,
                          "traffic_unit": "bytes of DRAM per launch (ncu, profiles/r01_v6c_ncu_full_pairs_tickets.txt)"},
             "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
