@@ -21,6 +21,7 @@
  */
 #ifndef MMC_B200_H
 #define MMC_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -253,6 +254,13 @@ int mmc_loop_run_atoms_device(mmc_handle *h, double temperature, double dr_max, 
  * stream.  seed = 11234 is the reference's own (Ewald/main.jl:36, Monatomic/mainMonatomic.jl:15).
  * Host code; feeds mmc_loop_run / mmc_loop_run_atoms. */
 int mmc_julia_rand(uint64_t seed, int64_t skip, double *out, int64_t n);
+
+/* Page-lock caller-owned host arrays (e.g. the storage behind soa.coords and moa.COM, Ewald/main.jl:306-330) so that
+ * mmc_upload_positions / mmc_potential_host DMA them at full PCIe rate and really asynchronously; pageable memory is
+ * staged by the driver at a fraction of that.  Register once after the arrays are allocated, unregister before they
+ * are freed or resized.  Thin wrappers over cudaHostRegister / cudaHostUnregister; no handle needed. */
+int mmc_host_register(void *ptr, size_t bytes);
+int mmc_host_unregister(void *ptr);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 typedef struct {

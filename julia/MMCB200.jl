@@ -91,6 +91,12 @@ recip_rollback!(e::Engine) = check(e, ccall((:mmc_recip_rollback, LIB), Cint, (P
 set_molecule!(e::Engine, i::Int, com, sites::Vector) =
     check(e, ccall((:mmc_set_molecule, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), e.h, i, Ref(com), pointer(sites)))
 
+# page-lock long-lived host arrays (soa.coords, moa.COM) once, so uploads from them are true asynchronous DMA at full PCIe rate
+host_register(a::Array) = ccall((:mmc_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), pointer(a), sizeof(a)) == 0 ||
+    error("mmc_host_register failed")
+host_unregister(a::Array) = ccall((:mmc_host_unregister, LIB), Cint, (Ptr{Cvoid},), pointer(a)) == 0 ||
+    error("mmc_host_unregister failed")
+
 # all positions at once (bulk form of set_molecule!): pointer(soa.coords), pointer(moa.COM)
 upload_positions!(e::Engine, coords, com) =
     check(e, ccall((:mmc_upload_positions, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), e.h, pointer(coords), pointer(com)))

@@ -120,6 +120,8 @@ SIGNATURES = {
                                      C.c_double, C.c_double, c_uint8_p, c_double_p, C.POINTER(LoopStats)]),
     "mmc_loop_run_atoms_device": (C.c_int, [H, C.c_double, C.c_double, c_double_p, c_double_p, C.c_int64, C.c_int64,
                                             C.c_double, C.c_double, c_uint8_p, c_double_p, C.POINTER(LoopStats)]),
+    "mmc_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "mmc_host_unregister": (C.c_int, [C.c_void_p]),
     "mmc_julia_rand": (C.c_int, [C.c_uint64, C.c_int64, c_double_p, C.c_int64]),
     "mmc_get_counters": (C.c_int, [H, C.POINTER(Counters)]),
     "mmc_set_timing": (C.c_int, [H, C.c_int32]),

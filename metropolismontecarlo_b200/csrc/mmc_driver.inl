@@ -418,6 +418,23 @@ extern "C" int mmc_loop_run_atoms_device(mmc_handle *h, double temperature, doub
     return o.ret;
 }
 
+extern "C" int mmc_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0) return MMC_EINVAL;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return MMC_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return MMC_ECUDA; }
+    return MMC_OK;
+}
+
+extern "C" int mmc_host_unregister(void *ptr)
+{
+    if (!ptr) return MMC_EINVAL;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorHostMemoryNotRegistered ? MMC_ESTATE : MMC_ECUDA; }
+    return MMC_OK;
+}
+
 extern "C" int mmc_julia_rand(uint64_t seed, int64_t skip, double *out, int64_t n)
 {
     if (skip < 0 || n < 0 || (n > 0 && !out)) return MMC_EINVAL;

@@ -350,6 +350,19 @@ class Engine:
         return t.value
 
 
+def host_register(a: np.ndarray):
+    """Page-lock a caller-owned array (mmc_host_register) so uploads from it run at full PCIe rate."""
+    rc = _lib.load().mmc_host_register(C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes))
+    if rc < 0:
+        raise _lib.MMCError(rc, "mmc_host_register failed")
+
+
+def host_unregister(a: np.ndarray):
+    rc = _lib.load().mmc_host_unregister(C.c_void_p(a.ctypes.data))
+    if rc < 0:
+        raise _lib.MMCError(rc, "mmc_host_unregister failed")
+
+
 def julia_rand(seed: int, n: int, skip: int = 0) -> np.ndarray:
     """`Random.seed!(seed); [rand() for _ in 1:n]` of the reference's Julia (MersenneTwister /
     dSFMT-19937) via mmc_julia_rand — the uniform stream Loop() consumes (Ewald/main.jl:36,516)."""

@@ -694,3 +694,20 @@ def test_tiny_systems(n):
         assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
         assert np.abs(outs[0][2] - outs[1][2]).max() < 1e-12
         eng.close()
+
+
+def test_host_register_pins_caller_arrays():
+    """mmc_host_register / mmc_host_unregister: a caller's pageable arrays page-locked in place; uploads from them give
+    the same result; registering twice is accepted, unregistering an unknown pointer is MMC_ESTATE."""
+    from metropolismontecarlo_b200.energy import MMCError, host_register, host_unregister, water_engine
+    ms = systems.spce_lattice(8000)
+    eng = water_engine(ms, 10.0)
+    ref = eng.potential("ewald")
+    coords, com = ms.coords.copy(), ms.com.copy()
+    host_register(coords); host_register(com); host_register(com)
+    got = eng.potential_host(coords, com, "ewald")
+    _check_props(got, ref, 1e-13)
+    host_unregister(coords); host_unregister(com)
+    with pytest.raises(MMCError):
+        host_unregister(com)
+    eng.close()
