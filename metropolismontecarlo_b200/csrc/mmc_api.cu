@@ -39,7 +39,8 @@ struct mmc_handle {
     cudaStream_t side = nullptr;         // the ρ(k) rebuild of a full evaluation runs here, beside binning + pair kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sites = nullptr;
     cudaStream_t copy = nullptr;         // mmc_potential_host: host->device chunks + repack; ρ(k) partials follow on `side`
-    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int host_chunks = 4;                 // mmc_potential_host: pieces the site array is uploaded in (mmc_debug_set "host_chunks", 1..8)
     int overlap_rhok = 1;                // mmc_debug_set "overlap_rhok": 0 = everything on one stream
     std::string err;
 
@@ -1738,7 +1739,7 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     if (rc) return rc;
     if (!coords || !com || !out || style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "bad arguments");
     DevSystem &S = h->S;
-    const int nchunk = 4;
+    const int nchunk = h->host_chunks;
     if (!h->uniform || h->cfg.world != 1 || S.n_sites < 64 * nchunk) {          // small or general systems: the plain sequence
         if ((rc = mmc_upload_positions(h, coords, com))) return rc;
         return mmc_potential(h, style, out);
@@ -1990,6 +1991,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     if (k == "chain_cluster") { if (value < 1 || value > CHAINC_MAXC) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
     if (k == "v6_ctas_per_sm") { if (value < 1 || value > 5) FAIL(MMC_EINVAL, "v6_ctas_per_sm must be 1..5"); h->v6_ctas_per_sm = (int)value; return MMC_OK; }
+    if (k == "host_chunks") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "host_chunks must be 1..8"); h->host_chunks = (int)value; return MMC_OK; }
     if (k == "v6_dynamic") { h->v6_dynamic = value != 0; return MMC_OK; }
     if (k == "rhok_split") {
         if (value < 1 || value > 64) FAIL(MMC_EINVAL, "rhok_split must be 1..64");
