@@ -108,3 +108,20 @@ __global__ void __launch_bounds__(256) k_charge_final(const double2 *part, int n
     block_sum<2, 256>(acc, s_red);
     if (threadIdx.x == 0) { out[0] = acc[0]; out[1] = acc[1]; }
 }
+
+// mmc_potential_host, windowed pair evaluation: need[w] = the last site chunk that holds a molecule of window w's layers
+// (home layers [ncd·w/nwin, ncd·(w+1)/nwin) plus the layer above them, periodic).  Chunk c = sites [n_sites·c/n_chunks, n_sites·(c+1)/n_chunks).
+__global__ void k_window_need(const int *__restrict__ cell_of, int n_mol, int S, int ncd, int nwin, int n_sites, int n_chunks, int *need)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mol) return;
+    const int z = cell_of[m] / (ncd * ncd);
+    const long long last_site = (long long)m * S + S - 1;
+    int c = (int)(last_site * n_chunks / n_sites);
+    while (c + 1 < n_chunks && (long long)n_sites * (c + 1) / n_chunks <= last_site) ++c;
+    while (c > 0 && (long long)n_sites * c / n_chunks > last_site) --c;
+    for (int w = 0; w < nwin; ++w) {
+        const int zlo = (int)((long long)ncd * w / nwin), zhi = (int)((long long)ncd * (w + 1) / nwin);
+        if ((z >= zlo && z < zhi) || z == zhi % ncd) atomicMax(&need[w], c);
+    }
+}

@@ -40,7 +40,10 @@ struct mmc_handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sites = nullptr;
     cudaStream_t copy = nullptr;         // mmc_potential_host: host->device chunks + repack; ρ(k) partials follow on `side`
     cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int host_chunks = 4;                 // mmc_potential_host: pieces the site array is uploaded in (mmc_debug_set "host_chunks", 1..8)
+    int host_windows = 3;                // ... and z-layer windows the pair evaluation is cut into while they arrive (1: wait for all sites)
+    int *d_winneed = nullptr;
+    cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int host_chunks = 6;                 // mmc_potential_host: pieces the site array is uploaded in (mmc_debug_set "host_chunks", 1..8)
     int overlap_rhok = 1;                // mmc_debug_set "overlap_rhok": 0 = everything on one stream
     std::string err;
 
@@ -212,7 +215,7 @@ void free_system(mmc_handle *h)
     dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
     h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
     dfree(h->d_mrows); dfree(h->d_gf); dfree(h->d_chain); h->chain_bytes = 0;
-    dfree(h->d_permol); dfree(h->d_permol_out); dfree(h->d_unit_partial); h->unit_partial_cap = 0;
+    dfree(h->d_winneed); dfree(h->d_permol); dfree(h->d_permol_out); dfree(h->d_unit_partial); h->unit_partial_cap = 0;
     dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl);
     dfree(h->d_rhok_partial); dfree(h->d_units); dfree(h->d_slots);
     h->units_cap = 0; h->slots_cap = 0;
@@ -410,6 +413,8 @@ struct EvalCtx {
     cudaEvent_t wait_sites = nullptr;   // mmc_potential_host: the sites arrive on the side stream; wait for them before the gather
     bool rhok_external = false;         //                     ... and the ρ(k) partials are produced there, chunk by chunk
     double *per_mol = nullptr;          // mmc_energy_all: [n_mol x 3] per-molecule rows (general kernel, evaluation order)
+    const cudaEvent_t *chunk_ev = nullptr;   // mmc_potential_host: event of every site chunk, in upload order (the last one == wait_sites)
+    int n_chunks = 0;
 };
 
 // out == nullptr: partials only, written from block `block0` on (the caller reduces all blocks later); *nb_out = blocks used
@@ -674,8 +679,34 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
                  reinterpret_cast<unsigned long long *>(h->d_maxdev), h->d_ovl,
                  want_rows ? h->d_mrows : nullptr, want_rows ? h->d_gf : nullptr, h->d_cell_of, ncd, E.box / ncd,
                  zl_lo, std::min(zl_cnt, ncd)};
-    if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
-    k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
+    // Sites still arriving from the host (mmc_potential_host): the home cells are cut into z-layer windows; a window's gather and its
+    // share of the pair kernel start as soon as the chunk that completes its layers (+ one layer above, the half shell) has landed,
+    // while later chunks are still on the bus.  Which chunk that is comes from the cell of every molecule (known: the COMs are in).
+    int nwin = 1, win_need[4] = {0, 0, 0, 0};
+    auto win_z = [&](int w) { return (int)((long long)ncd * w / nwin); };
+    auto gather_window = [&](int w) -> int {          // layers not gathered by an earlier window: [zlo + (w > 0), zhi], zhi wraps to 0 for the last
+        const int lo = win_z(w) + (w > 0 ? 1 : 0), hi = std::min(win_z(w + 1), ncd - 1);
+        if (hi < lo) return MMC_OK;
+        GatherArgs Gw = G; Gw.zl_lo = lo; Gw.zl_cnt = hi - lo + 1;
+        k_gather<<<gm, tb, 0, h->stream>>>(Gw); LAUNCH_CHECK();
+        return MMC_OK;
+    };
+    if (E.chunk_ev && E.n_chunks > 1 && cells && want_rows && E.world == 1 && E.f == 1.0 && h->v6_dynamic && h->host_windows > 1 &&
+        ncd >= 4 * h->host_windows) {
+        nwin = std::min(4, h->host_windows);
+        if (!h->d_winneed) CK(cudaMalloc(&h->d_winneed, 4 * sizeof(int)));
+        CK(cudaMemsetAsync(h->d_winneed, 0, 4 * sizeof(int), h->stream));
+        k_window_need<<<gm, tb, 0, h->stream>>>(h->d_cell_of, S.n_mol, US, ncd, nwin, S.n_sites, E.n_chunks, h->d_winneed); LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(win_need, h->d_winneed, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));          // ~0.15 ms into the call; the site chunks are in flight on the copy stream meanwhile
+        for (int w = 0; w < nwin; ++w) win_need[w] = std::max(0, std::min(win_need[w], E.n_chunks - 1));
+        for (int w = 1; w < nwin; ++w) win_need[w] = std::max(win_need[w], win_need[w - 1]);
+        CK(cudaStreamWaitEvent(h->stream, E.chunk_ev[win_need[0]], 0));
+        { int rcw = gather_window(0); if (rcw) return rcw; }
+    } else {
+        if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
+        k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
+    }
     if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
     if (style == MMC_STYLE_EWALD && rhok_side && !rhok_forked) {      // volume trial: scaled, sorted sites
         CK(cudaEventRecord(h->ev_fork, h->stream));
@@ -713,6 +744,11 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     const bool v5 = water && !v6 && h->pair_level <= 1 && h->uniform_q;
     const bool v4 = water && !v5 && !v6 && h->pair_level <= 2 && h->uniform_q;
     const bool v3 = water && !v4 && !v5 && !v6 && h->use_v3;
+    if (nwin > 1 && !v6) {       // another kernel serves this state: it wants the whole gathered copy
+        if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));
+        k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
+        nwin = 1;
+    }
     const int tile = (US == 3 && !force_general && !v3 && !v4 && !v5 && !v6) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
     if (v3 || v4 || v5 || v6) n_units = (long long)V3_GROUPS * ncd * ncd * ncd;
     if (v4 || v5 || v6) {
@@ -774,6 +810,21 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
                 X.unit_partial = h->d_unit_partial;
                 v6_units = my_units;
             }
+            if (nwin > 1) {          // one launch per z-layer window, each as soon as its sites are in
+                const long long per_layer = (long long)V3_GROUPS * ncd * ncd;
+                for (int w = 0; w < nwin; ++w) {
+                    if (w > 0) {
+                        CK(cudaStreamWaitEvent(h->stream, E.chunk_ev[win_need[w]], 0));
+                        int rcw = gather_window(w); if (rcw) return rcw;
+                        CK(cudaMemsetAsync(X.ticket, 0, sizeof(unsigned int), h->stream));
+                    }
+                    PairArgs Pw = P;
+                    Pw.unit_begin = per_layer * win_z(w); Pw.unit_end = per_layer * win_z(w + 1);
+                    V6Extra Xw = X; Xw.unit_partial = X.unit_partial + (size_t)Pw.unit_begin * V6_WARPS;
+                    const int gw = (int)std::max(1LL, std::min<long long>(h->v6_ctas_per_sm * h->sm_count, Pw.unit_end - Pw.unit_begin));
+                    launch_pairs_v6(v5_deg, v5_direct, gw, h->stream, Pw, h->d_slots, Xw);
+                }
+            } else
             launch_pairs_v6(v5_deg, v5_direct, grid, h->stream, P, h->d_slots, X);
         } else if (v5) {
             grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
@@ -1052,6 +1103,8 @@ int mmc_create(const mmc_config *cfg, mmc_handle **out)
     if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return fail("copy stream", e);
     for (auto &ev : h->ev_chunk)
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    for (auto &ev : h->ev_copy)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     cudaFuncSetAttribute(k_pairs<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_pairs<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_pairs<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -1079,6 +1132,7 @@ int mmc_destroy(mmc_handle *h)
     if (h->ev_sites) cudaEventDestroy(h->ev_sites);
     if (h->copy) { cudaStreamSynchronize(h->copy); cudaStreamDestroy(h->copy); }
     for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->ev_copy) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return MMC_OK;
@@ -1773,11 +1827,14 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     }
     for (int c = 0; c < nchunk; ++c) {
         const int s0 = (int)((long long)S.n_sites * c / nchunk), s1 = (int)((long long)S.n_sites * (c + 1) / nchunk);
+        // the copy stream carries nothing but copies: a repack kernel in it would hold the next copy back whenever the SMs are
+        // taken by a window of the pair kernel (persistent CTAs).  Repack + ρ(k) partials of the chunk follow on the side stream.
         CK(cudaMemcpyAsync(d_coords + 3 * (size_t)s0, coords + 3 * (size_t)s0, sizeof(double) * 3 * (size_t)(s1 - s0), cudaMemcpyHostToDevice, h->copy));
-        k_repack_sites<<<(s1 - s0 + 255) / 256, 256, 0, h->copy>>>(d_coords, s0, s1, S.site); LAUNCH_CHECK();
-        CK(cudaEventRecord(c == nchunk - 1 ? h->ev_sites : h->ev_chunk[c], h->copy));
+        CK(cudaEventRecord(h->ev_copy[c], h->copy));
+        CK(cudaStreamWaitEvent(h->side, h->ev_copy[c], 0));
+        k_repack_sites<<<(s1 - s0 + 255) / 256, 256, 0, h->side>>>(d_coords, s0, s1, S.site); LAUNCH_CHECK();
+        CK(cudaEventRecord(c == nchunk - 1 ? h->ev_sites : h->ev_chunk[c], h->side));
         if (ewald) {
-            CK(cudaStreamWaitEvent(h->side, c == nchunk - 1 ? h->ev_sites : h->ev_chunk[c], 0));
             int nb = 0;
             if ((rc = rhok_launch(h, S.site, s0, s1, S.box, nullptr, h->side, blocks, &nb, cap))) return rc;
             blocks += nb;
@@ -1786,6 +1843,9 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     CK(cudaEventRecord(h->ev_join, h->side));
     EvalCtx E{1.0, S.box, S.kappa, S.cfac, 0, 1};
     E.wait_sites = h->ev_sites; E.rhok_external = true;
+    cudaEvent_t chunk_events[8];
+    for (int c = 0; c < nchunk; ++c) chunk_events[c] = (c == nchunk - 1) ? h->ev_sites : h->ev_chunk[c];
+    E.chunk_ev = chunk_events; E.n_chunks = nchunk;
     for (;;) {
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
@@ -1798,7 +1858,7 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
         rc = finalize(h, style, E, h->d_vec, S.rhok[0], S.rhok[1], out);
         if (rc != 1) break;
         if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
-        E.wait_sites = nullptr;                                  // the state is on the device now
+        E.wait_sites = nullptr; E.chunk_ev = nullptr;            // the state is on the device now
     }
     if (rc < 0) return rc;
     if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
@@ -1991,6 +2051,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     if (k == "chain_cluster") { if (value < 1 || value > CHAINC_MAXC) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
     if (k == "v6_ctas_per_sm") { if (value < 1 || value > 5) FAIL(MMC_EINVAL, "v6_ctas_per_sm must be 1..5"); h->v6_ctas_per_sm = (int)value; return MMC_OK; }
+    if (k == "host_windows") { if (value < 1 || value > 4) FAIL(MMC_EINVAL, "host_windows must be 1..4"); h->host_windows = (int)value; return MMC_OK; }
     if (k == "host_chunks") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "host_chunks must be 1..8"); h->host_chunks = (int)value; return MMC_OK; }
     if (k == "v6_dynamic") { h->v6_dynamic = value != 0; return MMC_OK; }
     if (k == "rhok_split") {

@@ -123,3 +123,37 @@ def test_full_size_volume_identity_and_rhok_delta(cfg_e):
     fresh, _ = eng.rhok()
     assert abs(old_delta - fresh).max() < 1e-12 * 0.8476 * ms.n_sites
     eng.upload_system(ms, 10.0, 10.0)
+
+
+def test_full_size_potential_host_windows(cfg_e):
+    """mmc_potential_host at full size: the pair evaluation is cut into z-layer windows that start while later site chunks
+    are still on the bus.  Same Properties as upload + potential() for the lattice order (chunks = z-slabs: windows really
+    overlap the copies), for a random molecule order (every window needs the last chunk), with 1..4 windows and 1..8 chunks."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms, eng = cfg_e
+    ref = eng.potential("ewald")
+    fields = ("energy", "virial", "coulomb", "lj", "real", "recip", "self_")
+    for windows, chunks in ((4, 4), (1, 4), (4, 8), (3, 5), (2, 2), (4, 1)):
+        eng.debug_set("host_windows", windows)
+        eng.debug_set("host_chunks", chunks)
+        for style in ("ewald", "wolf"):
+            got = eng.potential_host(ms.coords, ms.com, style)
+            want = ref if style == "ewald" else eng.potential("wolf")
+            for f in fields:
+                assert rel(getattr(got, f), getattr(want, f)) < 1e-12, (windows, chunks, style, f)
+            assert got.overlaps == 0
+    eng.debug_set("host_windows", 3)
+    eng.debug_set("host_chunks", 6)
+    # a random molecule order: same energy (to summation order), every window waits for the last chunk
+    perm = np.random.default_rng(3).permutation(N_E)
+    mp = ms.copy()
+    mp.com = ms.com[perm].copy()
+    mp.coords = ms.coords.reshape(N_E, 3, 3)[perm].reshape(-1, 3).copy()
+    e2 = water_engine(mp, 10.0)
+    got = e2.potential_host(mp.coords, mp.com, "ewald")
+    for f in fields:
+        assert rel(getattr(got, f), getattr(ref, f)) < 1e-11, f
+    want = e2.potential("ewald")
+    for f in fields:
+        assert rel(getattr(got, f), getattr(want, f)) < 1e-12, f
+    e2.close()
