@@ -275,11 +275,11 @@ int mmc_set_timing(mmc_handle *h, int32_t enabled);
 int mmc_last_timings(mmc_handle *h, float *ms4);
 /* what the last full-energy evaluation did: molecule pairs inside the cutoff (summed over ranks
  * after finalize), path taken (0 = cell list, 1 = tile pairs, 2 = per-molecule rows), cells per
- * box edge, and the pair kernel used (6 = k_pairs_v6, 5 = k_pairs_v5, 4 = k_pairs_v4, 3 = k_pairs_v3, 64/128 = k_pairs_fast tile, 0 = k_pairs) */
+ * box edge, and the pair kernel used (6 = k_pairs_v6, 5 = k_pairs_v5, 64/128 = k_pairs_fast tile, 0 = k_pairs) */
 int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, int32_t *cells_per_dim,
                        int32_t *pair_kernel);
 /* test/profiling knobs. key "pair_level": first full-energy pair kernel the fallback chain may use
- * (0 = k_pairs_v6, 1 = k_pairs_v5, 2 = k_pairs_v4, 3 = k_pairs_v3, 4 = k_pairs_fast, 5 = general k_pairs); results are identical
+ * (0 = k_pairs_v6, 1 = k_pairs_v5, 2 = k_pairs_fast, 3 = general k_pairs); results are identical
  * within rounding, only speed differs. */
 int mmc_debug_set(mmc_handle *h, const char *key, int64_t value);
 /* FP64 DFMA-chain microbenchmark: measured FP64 FMA throughput of the device [TFLOP/s] */

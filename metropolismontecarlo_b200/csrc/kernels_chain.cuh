@@ -102,7 +102,7 @@ __device__ __forceinline__ double chain_rsqrt(double x)
 
 // DEG > 0: padded degree of the erf polynomial at compile time; 0: erfc(); -1: run-time degree
 template <int S, int DEG>
-__global__ void __launch_bounds__(CHAIN_THREADS, 1)
+static __global__ void __launch_bounds__(CHAIN_THREADS, 1)
 k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs A, const __grid_constant__ ErfPoly P)
 {
     using namespace chain;
@@ -576,7 +576,7 @@ __device__ __forceinline__ void chain_worker_bar() { asm volatile("bar.sync 1, %
 
 // SLICED = false: every CTA holds the whole system (fastest: the molecule about to move is on chip); true: a slice per CTA
 template <int S, int DEG, bool SLICED>
-__global__ void __launch_bounds__(CHAINC_THREADS, 1)
+static __global__ void __launch_bounds__(CHAINC_THREADS, 1)
 k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs A, const __grid_constant__ ErfPoly P)
 {
     using namespace chain;
@@ -1072,7 +1072,7 @@ struct ChainAtomArgs {
     ChainOut *out;
 };
 
-__global__ void __launch_bounds__(CHAINA_THREADS, 1)
+static __global__ void __launch_bounds__(CHAINA_THREADS, 1)
 k_chain_atoms(DevAtoms At, const __grid_constant__ ChainAtomArgs A)
 {
     using namespace chain;

@@ -277,7 +277,7 @@ __device__ __forceinline__ void move_recip_block(const DevSystem &S, const MoveA
 }
 
 template <int SP>
-__global__ void __launch_bounds__(MOVE_BLOCK)
+static __global__ void __launch_bounds__(MOVE_BLOCK)
 k_move(const __grid_constant__ DevSystem S, const __grid_constant__ MoveArgs A,
        const __grid_constant__ ErfPoly P, MoveScratch W)
 {
@@ -304,7 +304,7 @@ k_move(const __grid_constant__ DevSystem S, const __grid_constant__ MoveArgs A,
 }
 
 // explicit write of one molecule (mmc_set_molecule, and the flush of a pending accepted move)
-__global__ void k_set_molecule(DevSystem S, int i, double cx, double cy, double cz, MoveArgs A)
+static __global__ void k_set_molecule(DevSystem S, int i, double cx, double cy, double cz, MoveArgs A)
 {
     const int2 mi = S.mol[i];
     const int t = threadIdx.x;
@@ -329,7 +329,7 @@ struct AtomArgs {
 
 // Monatomic/mainMonatomic.jl:227-272 LJ_ΔU for atom i at its resident (cfg 0) and trial (cfg 1)
 // position in one pass over the partner atoms: r_j, ε_j, σ_j are loaded once for both.
-__global__ void __launch_bounds__(ATOM_BLOCK)
+static __global__ void __launch_bounds__(ATOM_BLOCK)
 k_move_atom(DevAtoms S, const __grid_constant__ AtomArgs A, MoveScratch W)
 {
     __shared__ double s_red[4 * (ATOM_BLOCK / 32)];
@@ -369,7 +369,7 @@ k_move_atom(DevAtoms S, const __grid_constant__ AtomArgs A, MoveScratch W)
         S.r[A.commit_i] = make_double4(A.commit_r[0], A.commit_r[1], A.commit_r[2], 0.0);
 }
 
-__global__ void k_set_atom(DevAtoms S, int i, double x, double y, double z)
+static __global__ void k_set_atom(DevAtoms S, int i, double x, double y, double z)
 {
     S.r[i] = make_double4(x, y, z, 0.0);
 }

@@ -27,8 +27,6 @@
 #define PAIR_TILE 64
 #define PAIR_QCAP (PAIR_TILE * PAIR_TILE / PAIR_WARPS)
 
-struct LJActive { int a, b; double eps, sig; };
-
 struct PairArgs {
     const double4 *com;        // cell-sorted (cell mode) / original order (tile mode)
     const double4 *site;       // S sites per molecule, site[m*S + a] = {x,y,z,q}
@@ -81,7 +79,7 @@ __device__ __forceinline__ bool coul_pair(const PairArgs &A, double r2, double q
     return false;
 }
 
-__constant__ int c_half_shell[14][3] = {
+static __constant__ int c_half_shell[14][3] = {
     {0, 0, 0},
     {1, 0, 0},
     {-1, 1, 0}, {0, 1, 0}, {1, 1, 0},
@@ -92,7 +90,7 @@ __constant__ int c_half_shell[14][3] = {
 // PM: every evaluated molecule pair is also credited to the rows of BOTH molecules (mmc_energy_all: LJ_poly_ΔU(i) and
 // EwaldReal(i) for all i from one pass over the unique pairs; FP64 atomics, so the row sums are order-free to ~1e-13).
 template <int ST, bool PM>   // ST = sites per molecule at compile time (0: runtime A.S)
-__global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__ PairArgs A)
+static __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_constant__ PairArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = ST ? ST : A.S;
@@ -289,7 +287,7 @@ __device__ __forceinline__ void unpack_unit(const int4 d, double L, UnitDesc &U)
 }
 
 // one thread per unit: resolves (cell, slot) / (I, J) into tile ranges and wrap codes once per binning
-__global__ void k_units_build(PairArgs A, int4 *units, long long n_units)
+static __global__ void k_units_build(PairArgs A, int4 *units, long long n_units)
 {
     const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
@@ -424,7 +422,7 @@ __device__ __forceinline__ void pair_unit_body(const PairArgs &A, const UnitDesc
 }
 
 template <int ST, int TILE, int DEG>
-__global__ void __launch_bounds__(PAIR_BLOCK, (TILE <= 64 ? 4 : 2)) k_pairs_fast(const __grid_constant__ PairArgs A)
+static __global__ void __launch_bounds__(PAIR_BLOCK, (TILE <= 64 ? 4 : 2)) k_pairs_fast(const __grid_constant__ PairArgs A)
 {
     constexpr int S = ST;
     constexpr int QCAP = TILE * TILE / PAIR_WARPS;
@@ -489,7 +487,7 @@ __global__ void __launch_bounds__(PAIR_BLOCK, (TILE <= 64 ? 4 : 2)) k_pairs_fast
 
 // fold the per-CTA partials in CTA order into the head of the partial-sum vector:
 // out[0] = Σ lj_pot, out[1] = Σ lj_vir, out[2] = Σ coul (un-scaled), out[3] = #overlapped molecules
-__global__ void k_pair_reduce(const double4 *partial, int nb, const unsigned int *n_ovl, const int *max_count,
+static __global__ void k_pair_reduce(const double4 *partial, int nb, const unsigned int *n_ovl, const int *max_count,
                               const unsigned int *err_flag, double *out)
 {
     // fixed order: thread t adds partials t, t+256, ... ; then the 256 thread sums are folded by block_sum (warp
@@ -513,7 +511,7 @@ struct PerMolArgs {
     double *lj_pot, *lj_vir, *coul; int *overlap;
 };
 
-__global__ void k_permol_scatter(PerMolArgs A)
+static __global__ void k_permol_scatter(PerMolArgs A)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= A.n_mol) return;
@@ -544,7 +542,7 @@ __device__ __forceinline__ int cell_coord(double x, double inv_cell, int n)
     return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
-__global__ void k_cell_count(CellArgs A)
+static __global__ void k_cell_count(CellArgs A)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= A.n_mol) return;
@@ -557,7 +555,7 @@ __global__ void k_cell_count(CellArgs A)
 }
 
 // exclusive scan of count[0..ncell) into start[0..ncell], single CTA
-__global__ void k_cell_scan(CellArgs A, int ncell)
+static __global__ void k_cell_scan(CellArgs A, int ncell)
 {
     __shared__ int s_warp[32];
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -587,7 +585,7 @@ __global__ void k_cell_scan(CellArgs A, int ncell)
     for (int i = lo; i < hi; ++i) { A.start[i] = run; run += A.count[i]; }
 }
 
-__global__ void k_cell_fill(CellArgs A)
+static __global__ void k_cell_fill(CellArgs A)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= A.n_mol) return;
@@ -598,7 +596,7 @@ __global__ void k_cell_fill(CellArgs A)
 
 // one warp per cell: order the cell's molecules by index so that the summation order (and so
 // every bit of the result) is independent of the atomics' arrival order above
-__global__ void k_cell_sort(CellArgs A, int ncell)
+static __global__ void k_cell_sort(CellArgs A, int ncell)
 {
     const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (cell >= ncell) return;
@@ -647,7 +645,7 @@ struct GatherArgs {
 // cell-sorted copy of the state; for a volume trial the COMs are scaled by f and the sites
 // rigidly shifted (Ewald/volumeChange.jl:62-80: coords_new = f*coords; change = coords_new -
 // coords; atom_XYZ = atom_coords + change). f == 1 reproduces the state bit for bit.
-__global__ void k_gather(GatherArgs A)
+static __global__ void k_gather(GatherArgs A)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= A.n_mol) return;
@@ -684,7 +682,7 @@ __global__ void k_gather(GatherArgs A)
 }
 
 // accept of a volume move: the scaled state becomes the resident one (volumeChange.jl:141-144)
-__global__ void k_apply_scale(DevSystem S, double f)
+static __global__ void k_apply_scale(DevSystem S, double f)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= S.n_mol) return;
@@ -702,7 +700,7 @@ __global__ void k_apply_scale(DevSystem S, double f)
 }
 
 // Σq and Σq² (EwaldSelf ewalds.jl:829-833, Wolf constants energy.jl:924-934), single CTA, ordered
-__global__ void k_charge_sums(const double4 *site, int n, double *out)
+static __global__ void k_charge_sums(const double4 *site, int n, double *out)
 {
     __shared__ double s_red[2 * 8];
     double acc[2] = {0.0, 0.0};
@@ -714,7 +712,7 @@ __global__ void k_charge_sums(const double4 *site, int n, double *out)
 // ------------------------------------------------------------------- monatomic potential
 // Monatomic/mainMonatomic.jl:275-289: Σ_i LJ_ΔU(i) / 2, rows over CTAs (double counted like the
 // reference: the per-j ε_j, σ_j make the (i,j) and (j,i) terms different).
-__global__ void __launch_bounds__(256) k_atoms_rows(DevAtoms S, double2 *rows)
+static __global__ void __launch_bounds__(256) k_atoms_rows(DevAtoms S, double2 *rows)
 {
     __shared__ double s_red[2 * 8];
     const double L = S.box, rc2 = S.rc * S.rc;
@@ -739,7 +737,7 @@ __global__ void __launch_bounds__(256) k_atoms_rows(DevAtoms S, double2 *rows)
     }
 }
 
-__global__ void __launch_bounds__(256) k_rows_sum(const double2 *rows, int n, double *out)
+static __global__ void __launch_bounds__(256) k_rows_sum(const double2 *rows, int n, double *out)
 {
     __shared__ double s_red[2 * 8];
     double acc[2] = {0.0, 0.0};
@@ -750,7 +748,7 @@ __global__ void __launch_bounds__(256) k_rows_sum(const double2 *rows, int n, do
 
 // ------------------------------------------------------------------- FP64 peak probe
 // 8 independent DFMA chains per thread; reports 2 flop per DFMA.
-__global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters)
+static __global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters)
 {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
            a6 = a0 + 6, a7 = a0 + 7;

@@ -1,8 +1,8 @@
 // kernels_pairs_v5.cuh — production pair kernel for cell mode, 3-site molecules with identical
-// per-site charges (SPC/E, TIP3P).  Same reference semantics as k_pairs_v4 (COM gate energy.jl:250 /
+// per-site charges (SPC/E, TIP3P).  Reference semantics: (COM gate energy.jl:250 /
 // ewalds.jl:337, nine erfc site pairs ewalds.jl:359-367, O–O LJ energy.jl:270-282, overlap flags)
-// and the same unit / queue / row layout; what changed is what the ncu source page of v4 showed
-// (profiles/r01_ncu_full_pairs_v4.txt): only 31 % of its 480 M warp instructions were FP64
+// and the unit / queue / row layout of its predecessors (round 1: k_pairs_v3/v4, removed); what changed is what the ncu
+// source page of v4 showed (profiles/r01_v4_ncu_full_pairs.txt): only 31 % of its 480 M warp instructions were FP64
 // arithmetic — the COM gate took ≈80 instructions per 64 tests and the consume phase ≈100
 // non-FP64 instructions per round of 32 molecule pairs.
 //
@@ -18,7 +18,46 @@
 //              7 DFMA per site pair at config E instead of 2 + 8 + 1; otherwise the mapped
 //              Chebyshev form with σκ² folded into one constant.
 #pragma once
-#include "kernels_pairs_v4.cuh"
+#include "kernels_pairs.cuh"
+
+// ---- shared by the cell-mode water kernels: unit = (home cell, group of 5/5/4 half-shell slots)
+#define V3_ACAP 64
+#define V3_SLOTS 5
+#define V3_BCAP (V3_SLOTS * V3_ACAP)
+#define V3_QCAP 512    // ring buffer per warp (power of two): ≤ 31 left-overs + 8 rows x 32 new entries
+#define V3_GROUPS 3
+
+static __constant__ int c_v3_group_begin[V3_GROUPS + 1] = {0, 5, 10, 14};
+
+// per (cell, slot): where the neighbour cell's molecules are and how they are shifted
+static __global__ void k_slots_build(PairArgs A, int4 *slots, int ncell)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell * 14) return;
+    const int c = t / 14, slot = t - 14 * c;
+    const int n = A.ncd;
+    const int cx = c % n, cy = (c / n) % n, cz = c / (n * n);
+    int nx = cx + c_half_shell[slot][0], ny = cy + c_half_shell[slot][1], nz = cz + c_half_shell[slot][2];
+    int code = 0;
+    if (nx >= n) { nx -= n; code |= 1 << 0; } else if (nx < 0) { nx += n; code |= 2 << 0; }
+    if (ny >= n) { ny -= n; code |= 1 << 2; } else if (ny < 0) { ny += n; code |= 2 << 2; }
+    if (nz >= n) { nz -= n; code |= 1 << 4; } else if (nz < 0) { nz += n; code |= 2 << 4; }
+    const int cb = nx + n * (ny + n * nz);
+    const int b_lo = A.cell_start[cb];
+    slots[t] = make_int4(b_lo, A.cell_start[cb + 1] - b_lo, code, 0);
+}
+
+// MUFU.RSQ64H seed + one cubic Newton step (relative error ≈ 1e-19·… → correctly rounded to ~1 ulp for
+// normal positive r²; r² = 0 gives +inf like 1/sqrt(0)): the CUDA rsqrt() sequence without its
+// special-value slow path, which this kernel never needs.
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(x, -(y0 * y0), 1.0);
+    return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+}
+
 
 #define V5_BLOCK 128
 #define V5_WARPS (V5_BLOCK / 32)
@@ -49,7 +88,7 @@ __device__ __forceinline__ void v5_poly9(const PairArgs &A, const double (&r2)[9
 }
 
 template <int DEG, bool DIRECT>
-__global__ void __launch_bounds__(V5_BLOCK, 4) k_pairs_v5(const __grid_constant__ PairArgs A, const int4 *__restrict__ slots)
+static __global__ void __launch_bounds__(V5_BLOCK, 4) k_pairs_v5(const __grid_constant__ PairArgs A, const int4 *__restrict__ slots)
 {
     constexpr int S = 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];

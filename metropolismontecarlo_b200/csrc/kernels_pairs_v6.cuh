@@ -64,7 +64,7 @@ struct V6Extra {
 };
 
 template <int DEG, bool DIRECT>
-__global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant__ PairArgs A, const int4 *__restrict__ slots,
+static __global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant__ PairArgs A, const int4 *__restrict__ slots,
                                                            const V6Extra X)
 {
     constexpr int S = 3;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(V6_BLOCK, 5) k_pairs_v6(const __grid_constant_
 }
 
 // stage 1 of the fold of the per-(unit, warp) sums: CTA b adds its contiguous share in a fixed order
-__global__ void __launch_bounds__(256) k_unit_fold(const double4 *__restrict__ unit_partial, long long n, double4 *out)
+static __global__ void __launch_bounds__(256) k_unit_fold(const double4 *__restrict__ unit_partial, long long n, double4 *out)
 {
     __shared__ double s_red[4 * 8];
     const long long per = (n + gridDim.x - 1) / gridDim.x;

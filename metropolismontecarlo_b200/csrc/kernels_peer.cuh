@@ -25,7 +25,7 @@ struct PeerArgs {
     unsigned long long epoch;
 };
 
-__global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerArgs P, const double *__restrict__ vec)
+static __global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerArgs P, const double *__restrict__ vec)
 {
     const int d = blockIdx.x;                   // destination rank
     double *dst = P.slot[d] + ((size_t)P.parity * P.world + P.rank) * P.nvec_cap;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerA
 }
 
 // out[0 .. nvec): Σ_ranks slot; status[0] = 1 when a peer's flag did not arrive within the spin limit
-__global__ void __launch_bounds__(256) k_peer_sum(const __grid_constant__ PeerArgs P, double *__restrict__ out, int *status)
+static __global__ void __launch_bounds__(256) k_peer_sum(const __grid_constant__ PeerArgs P, double *__restrict__ out, int *status)
 {
     __shared__ int s_bad;
     if (threadIdx.x == 0) s_bad = 0;

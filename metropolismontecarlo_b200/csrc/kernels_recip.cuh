@@ -26,7 +26,7 @@ struct RhokArgs {
 };
 
 template <int KPT>
-__global__ void __launch_bounds__(RHOK_BLOCK) k_rhok_partial(RhokArgs A)
+static __global__ void __launch_bounds__(RHOK_BLOCK) k_rhok_partial(RhokArgs A)
 {
     __shared__ cplx s_e[RHOK_SITES][3][MMC_MAX_NK + 1];
     const int tid = threadIdx.x;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(RHOK_BLOCK) k_rhok_partial(RhokArgs A)
 // ρ(k) = Σ_b partial[b][k] → out[k].  blockDim = (32 k, 32 slices): each slice folds a contiguous 1/32 of the
 // CTAs in CTA order, the 32 slice sums are added in slice order (deterministic); many short dependent chains
 // instead of four long ones (the kernel is pure load latency).
-__global__ void k_rhok_reduce(const double2 *partial, int nb, int nkvecs, double2 *out)
+static __global__ void k_rhok_reduce(const double2 *partial, int nb, int nkvecs, double2 *out)
 {
     __shared__ double2 s_s[32][33];
     const int k = blockIdx.x * 32 + threadIdx.x, sl = threadIdx.y;
@@ -112,7 +112,7 @@ __global__ void k_rhok_reduce(const double2 *partial, int nb, int nkvecs, double
 
 // E = Σ_k cfac_k |ρ(k)|² (un-scaled, ewalds.jl:599) and ρ(k) stored to both buffers (:600-601)
 #define RHOKE_BLOCK 256
-__global__ void __launch_bounds__(RHOKE_BLOCK)
+static __global__ void __launch_bounds__(RHOKE_BLOCK)
 k_rhok_energy(const double2 *rho, const double *cfac, int nkvecs, double2 *dst0, double2 *dst1,
               double *energy_out)
 {
@@ -157,7 +157,7 @@ struct Rhok2Args {
 };
 
 template <int NK>
-__global__ void __launch_bounds__(RHOK2_BLOCK, 2) k_rhok_pairs(Rhok2Args A)
+static __global__ void __launch_bounds__(RHOK2_BLOCK, 2) k_rhok_pairs(Rhok2Args A)
 {
     constexpr int NW = RHOK2_BLOCK / 32;
     constexpr int NACC = 4 + 8 * NK;

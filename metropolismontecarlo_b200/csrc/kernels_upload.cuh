@@ -19,7 +19,7 @@ struct RepackArgs {
 
 enum { REPACK_BAD_ATYPE = 1, REPACK_BAD_RANGE = 2, REPACK_TOO_MANY_SITES = 4, REPACK_COM_OUTSIDE = 8 };
 
-__global__ void k_repack(RepackArgs A)
+static __global__ void k_repack(RepackArgs A)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const long long f0 = A.first_atom[0], l0 = A.last_atom[0];
@@ -51,7 +51,7 @@ __global__ void k_repack(RepackArgs A)
 }
 
 // positions only (mmc_upload_positions): coords and COM of an already uploaded system, charges/topology untouched
-__global__ void k_repack_positions(const double *coords, const double *com, int n_mol, int n_sites, double box,
+static __global__ void k_repack_positions(const double *coords, const double *com, int n_mol, int n_sites, double box,
                                    double4 *site, double4 *dcom, int *info)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,7 +69,7 @@ __global__ void k_repack_positions(const double *coords, const double *com, int 
 
 // the two halves of k_repack_positions, for the pipelined end-to-end path (mmc_potential_host): COMs first (binning
 // needs nothing else), sites chunk by chunk as their copies land
-__global__ void k_repack_com(const double *com, int n_mol, double box, double4 *dcom, int *info)
+static __global__ void k_repack_com(const double *com, int n_mol, double box, double4 *dcom, int *info)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_mol) return;
@@ -78,7 +78,7 @@ __global__ void k_repack_com(const double *com, int n_mol, double box, double4 *
     dcom[t] = make_double4(x, y, z, 0.0);
 }
 
-__global__ void k_repack_sites(const double *coords, int s0, int s1, double4 *site)
+static __global__ void k_repack_sites(const double *coords, int s0, int s1, double4 *site)
 {
     const int t = s0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= s1) return;
@@ -88,7 +88,7 @@ __global__ void k_repack_sites(const double *coords, int s0, int s1, double4 *si
 }
 
 // Σq and Σq² in two deterministic stages (EwaldSelf ewalds.jl:829-833, Wolf constants energy.jl:924-934)
-__global__ void __launch_bounds__(256) k_charge_partial(const double4 *site, int n, double2 *part)
+static __global__ void __launch_bounds__(256) k_charge_partial(const double4 *site, int n, double2 *part)
 {
     __shared__ double s_red[2 * 8];
     double acc[2] = {0.0, 0.0};
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_charge_partial(const double4 *site, int
     if (threadIdx.x == 0) part[blockIdx.x] = make_double2(acc[0], acc[1]);
 }
 
-__global__ void __launch_bounds__(256) k_charge_final(const double2 *part, int nb, double *out)
+static __global__ void __launch_bounds__(256) k_charge_final(const double2 *part, int nb, double *out)
 {
     __shared__ double s_red[2 * 8];
     double acc[2] = {0.0, 0.0};
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_charge_final(const double2 *part, int n
 
 // mmc_potential_host, windowed pair evaluation: need[w] = the last site chunk that holds a molecule of window w's layers
 // (home layers [ncd·w/nwin, ncd·(w+1)/nwin) plus the layer above them, periodic).  Chunk c = sites [n_sites·c/n_chunks, n_sites·(c+1)/n_chunks).
-__global__ void k_window_need(const int *__restrict__ cell_of, int n_mol, int S, int ncd, int nwin, int n_sites, int n_chunks, int *need)
+static __global__ void k_window_need(const int *__restrict__ cell_of, int n_mol, int S, int ncd, int nwin, int n_sites, int n_chunks, int *need)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_mol) return;

@@ -37,6 +37,9 @@ struct DevSystem {
     double2 *rhok[2];
 };
 
+// LJ-active site pair (a, b) of the uniform molecule (eps_ab > 0.001, Ewald/energy.jl:270)
+struct LJActive { int a, b; double eps, sig; };
+
 struct DevAtoms {
     int n;
     double4 *r;      // {x, y, z, -}

@@ -1,0 +1,208 @@
+// mmc_handle.h — internal: the state behind an mmc_handle and the helpers shared by the translation units of
+// libmmc_b200.so (mmc_api.cu: lifetime, upload, per-move entry points; mmc_eval.cu: full-energy evaluation, sharding,
+// volume moves; mmc_loop.cu: the Loop() stand-in and the block-of-moves kernels).  Not part of the public ABI.
+#pragma once
+#include "../../include/mmc_b200.h"
+#include "erf_poly.h"
+#include "kernels_move.cuh"
+#include "kernels_peer.cuh"
+#include "mmc_common.cuh"
+
+#include <string>
+#include <utility>
+#include <vector>
+
+// host-side fold of one move launch: exactly the numbers Loop() gets from its calls
+struct MoveOut { double lj_pot[2], lj_vir[2], qq[2], d_recip; int overlap[2]; };
+struct Timers { cudaEvent_t ev[8]; bool on = false; float ms[4] = {0, 0, 0, 0}; };
+
+struct mmc_handle {
+    mmc_config cfg{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t side = nullptr;         // the ρ(k) rebuild of a full evaluation runs here, beside binning + pair kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sites = nullptr;
+    cudaStream_t copy = nullptr;         // mmc_potential_host: host->device chunks + repack; ρ(k) partials follow on `side`
+    cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int host_windows = 3;                // ... and z-layer windows the pair evaluation is cut into while they arrive (1: wait for all sites)
+    int *d_winneed = nullptr;
+    cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int host_chunks = 6;                 // mmc_potential_host: pieces the site array is uploaded in (mmc_debug_set "host_chunks", 1..8)
+    int overlap_rhok = 1;                // mmc_debug_set "overlap_rhok": 0 = everything on one stream
+    std::string err;
+
+    // ---- molecular system
+    bool has_system = false;
+    DevSystem S{};
+    std::vector<int2> h_mol;     // host mirror of S.mol
+    unsigned char *d_raw = nullptr;     // device staging for the caller's arrays in their own layout
+    size_t raw_bytes = 0;
+    int cap_mol = 0, cap_sites = 0;     // sizes the resident buffers were allocated for
+    int *d_info = nullptr;
+    double2 *d_qpart = nullptr;
+    struct UploadResult { int info[4]; double qs[2]; } *h_up = nullptr;   // pinned
+    bool uniform = false;        // every molecule: same site count, same type sequence, packed
+    int US = 0;                  // uniform sites per molecule
+    std::vector<LJActive> lj;
+    LJActive *d_lj = nullptr;
+    int2 *d_mol_uniform = nullptr;
+    double sum_q = 0.0, sum_q2 = 0.0;
+    double *d_qsums = nullptr;
+
+    // ---- ewald
+    bool has_ewald = false;
+    int k_sq_max = 0;
+    std::vector<int32_t> kxyz;
+    std::vector<double> cfac;
+    int cur = 0;                 // index of the Old ρ(k) buffer
+    bool new_valid = false;
+    double2 *d_rhok_trial = nullptr;
+    int2 *d_kpairs = nullptr;
+    int *d_kindex = nullptr;
+    int n_kpairs = 0;
+    double *d_cfac_trial = nullptr;
+    std::vector<double> cfac_trial;
+
+    // ---- move scratch
+    MoveScratch W{};
+    MoveSlot *h_slots = nullptr;  // mapped pinned: one slot per CTA of a move launch
+    int max_slots = 0;
+    MoveOut mout{};               // host-side fold of the slots of the last move launch
+    MoveOut *h_out = &mout;
+    ErfPoly move_poly{};          // erf polynomial of the resident box for the per-move kernels
+    // ---- sharded evaluation over peer memory (mmc_peer_*, mmc_potential_sharded_begin/end)
+    double *d_peer_buf = nullptr;                 // [2][world][peer_nvec_cap] doubles, then [2][world] flags
+    size_t peer_nvec_cap = 0;
+    void *peer_base[MMC_PEER_MAX] = {nullptr};    // mapped exchange buffers of all ranks (own: d_peer_buf)
+    bool peer_opened[MMC_PEER_MAX] = {false};     // opened through cudaIpcOpenMemHandle (to be closed)
+    int peer_ready = 0;                           // number of imported ranks
+    unsigned long long peer_epoch = 0;
+    double *d_peer_total = nullptr;               // summed vector
+    int *h_peer_status = nullptr;                 // mapped pinned host word written by k_peer_sum (no extra copy to read it)
+    int *d_peer_status = nullptr;                 // its device alias
+    bool sharded_pending = false;
+    int sharded_style = 0;
+    // ---- device-resident block of moves (mmc_loop_run_device)
+    unsigned char *d_chain = nullptr;   // [uniforms | quat | db | delta | out | accepted]
+    int chain_cluster = 8;              // CTAs (SMs) per cluster for mmc_loop_run_device; 1 = single-CTA kernel
+    int chain_cluster_atoms = 16;       // ... for mmc_loop_run_atoms_device (16 = non-portable cluster size, falls back to 8)
+    size_t chain_bytes = 0;
+    int pend_kind = 0;            // accepted move not yet written to HBM: 0 none, 1 molecule, 2 atom
+    int pend_i = 0, pend_ns = 0;
+    double pend_com[3] = {0, 0, 0};
+    double pend_site[3 * MMC_MAX_SITES] = {0};
+    unsigned long long seq = 0;
+    bool trial_pending = false;
+    int trial_kind = 0;          // 1 molecule, 2 atom
+    int trial_style = 0;
+    MoveArgs last{};
+    AtomArgs last_atom{};
+    bool last_overlap = false;
+
+    // ---- full-energy scratch
+    int *d_cell_of = nullptr, *d_count = nullptr, *d_start = nullptr, *d_fill = nullptr, *d_perm = nullptr;
+    int ncell_cap = 0;
+    double4 *d_scom = nullptr, *d_ssite = nullptr;
+    double *d_mrows = nullptr;   // k_pairs_v6: cell-sorted state as rows of 12 doubles
+    double *d_permol = nullptr, *d_permol_out = nullptr;   // mmc_energy_all: per-molecule rows (evaluation order) and the scaled output arrays
+    float4 *d_gf = nullptr;      //             and cell-local float COMs
+    double4 *d_pair_partial = nullptr;
+    int pair_grid = 0;
+    unsigned int *d_ovl = nullptr, *d_novl = nullptr;
+    double *d_maxdev = nullptr;
+    double2 *d_rhok_partial = nullptr;
+    int rhok_grid_cap = 0;
+    double *d_vec = nullptr;     // internal partial-sum vector (MMC_NSCAL + 2*NK doubles)
+    double *h_vec = nullptr;     // pinned
+    int last_mode = -1;          // 0 cells, 1 tiles, 2 rows
+    int last_ncd = 0;
+    int max_cell_cached = -1;    // largest cell population seen at the last binning (-1: unknown)
+    int *d_maxcount = nullptr;
+    int *d_flags = nullptr;      // [maxdev(2) | novl | errflag | maxcount | 3 spare | count(ncell) | fill(ncell)]
+    int4 *d_units = nullptr;
+    int4 *d_slots = nullptr;
+    long long slots_cap = 0;
+    int use_rhok_v2 = 1;
+    int v6_ctas_per_sm = 5;
+    int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v6, 1 k_pairs_v5, 2 k_pairs_fast, 3 general k_pairs
+                                 // (raised when a kernel declines the state)
+    int v6_dynamic = 1;          // k_pairs_v6 draws units by ticket (0: static round-robin deal)
+    double4 *d_unit_partial = nullptr;
+    size_t unit_partial_cap = 0;
+    int rhok_split = 1;          // ρ(k) rebuild: CTAs per resident slot (short CTAs let higher-priority kernels in between)
+    int pair_floor = 0;          // lowest level the chain may start from (mmc_debug_set "pair_level": A/B tests)
+    bool uniform_q = false;      // every molecule carries the charges of molecule 1 (per site index)
+    double q_site[MMC_MAX_SITES] = {0};
+    long long units_cap = 0;
+    unsigned int *d_errflag = nullptr;
+    std::vector<std::pair<double, ErfPoly>> poly_cache;
+    int last_fast = 0;           // tile size of the fast pair kernel used last (0: general kernel)
+    long long last_pairs = 0;    // molecule pairs inside the cutoff in the last evaluation (all ranks)
+
+    // ---- volume trial
+    bool vol_pending = false;
+    double vol_box = 0, vol_kappa = 0, vol_f = 1;
+    int vol_style = 0;
+
+    // ---- atoms
+    bool has_atoms = false;
+    DevAtoms At{};
+    double2 *d_rows = nullptr;
+    double *d_atoms_out = nullptr;
+
+    int sm_count = 148;
+    mmc_counters cnt{};
+    Timers tm;
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return MMC_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+#define FAIL(code, msg)                                                                       \
+    do {                                                                                      \
+        h->err = (msg);                                                                       \
+        return (code);                                                                        \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                        \
+    do {                                                                                      \
+        h->cnt.kernel_launches++;                                                             \
+        cudaError_t e_ = cudaGetLastError();                                                  \
+        if (e_ != cudaSuccess) {                                                              \
+            h->err = std::string("kernel launch: ") + cudaGetErrorString(e_);                 \
+            return MMC_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+template <typename T>
+inline void dfree(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+inline int2 mol_of(const mmc_handle *h, int64_t i0)
+{
+    return h->uniform ? make_int2((int)(i0 * h->US), h->US) : h->h_mol[i0];
+}
+
+namespace mmc_detail {
+// mmc_api.cu
+int ensure_vec(mmc_handle *h);
+int move_tiles(const mmc_handle *h);
+int flush_pending(mmc_handle *h);
+int launch_move_on(mmc_handle *h, const DevSystem &sys, MoveArgs &A, const ErfPoly &poly, bool carry_commit);
+int style_check(mmc_handle *h, int style);
+void fill_cfac(const std::vector<int32_t> &kxyz, double kappa, double box, std::vector<double> &cfac);
+void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P);
+// mmc_eval.cu
+void eval_set_attributes();
+int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, double box, double2 *out, cudaStream_t st = nullptr,
+                int block0 = 0, int *nb_out = nullptr, int cap_blocks = 0);
+}  // namespace mmc_detail

@@ -1,4 +1,4 @@
-// mmc_driver.inl — host-side stand-in for the Julia move loop, built ON TOP of the C ABI.
+// mmc_loop.cu — host-side stand-in for the Julia move loop, built ON TOP of the C ABI.
 //
 // The north star keeps Loop() (Ewald/main.jl:460-696) in Julia; Julia is not installed where this
 // library is built and tested, so this file plays Julia's part in C++: it generates the trial
@@ -8,7 +8,17 @@
 // in the reference's draw order, so a recorded Julia stream reproduces the
 // reference trajectory.  All energies come from the CUDA kernels; nothing here evaluates one.
 
+#include "mmc_handle.h"
 #include "julia_mt.h"
+#include "kernels_chain.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+using namespace mmc_detail;
 
 namespace {
 

@@ -327,7 +327,7 @@ def test_pair_kernel_variants_agree_with_oracle():
     want_pairs = npr_pairs_in_cutoff(ms.com, ms.box, 10.0)
     eng = water_engine(ms, 10.0)
     want_wolf = ora.potential_wolf(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
-    for level, name in ((0, "k_pairs_v6"), (1, "k_pairs_v5"), (2, "k_pairs_v4"), (3, "k_pairs_v3"), (4, "k_pairs_fast<64>"), (5, "k_pairs")):
+    for level, name in ((0, "k_pairs_v6"), (1, "k_pairs_v5"), (2, "k_pairs_fast<64>"), (3, "k_pairs")):
         eng.debug_set("pair_level", level)
         got = eng.potential("ewald")
         assert eng.last_eval_info()["pair_kernel"] == name, (level, eng.last_eval_info())
