@@ -172,9 +172,11 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
 
     long long pc[6] = {0, 0, 0, 0, 0, 0};
     int cur = A.cur;
+    long long pos_m = 0;                                    // stream position at the start of the current move (lane 0 of warp 0)
     for (long long m = 0; m < A.n_moves; ++m) {
         const int i = (int)(m % N);                         // sweep order i = 1..N (main.jl:490)
         long long tc0 = clock64();
+        pos_m = pos;
         // ================= step 0: the trial move (main.jl:514-552), lane 0 of warp 0
         if (warp == 0) {
             if (pre_cnt > 0) {                              // uniforms requested during the previous move have landed
@@ -483,7 +485,9 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                 if (overlap) D.n_ovl += 1;
                 bool okm = true;
                 if (!(x < 0.0)) okm = exp(-x) > next_u();                            // auxillary.jl:106-114
-                const bool accd = okm && !overlap;                                    // main.jl:598
+                // a move whose draws ran past the end of the caller's stream never happened: nothing is committed or recorded,
+                // its counters are taken back and the stream position returns to the start of the move (resume point)
+                const bool accd = okm && !overlap && !dry;                            // main.jl:598
                 if (accd) {
                     D.tot_e = add(D.tot_e, delta);
                     D.tot_v = add(D.tot_v, add(sub(new_v, old_v), recv));
@@ -500,10 +504,13 @@ k_chain(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs 
                     for (int k = 0; k < 4; ++k) A.quat[4 * i + k] = D.ei[k];
                     if (A.style_recip && !overlap) s_cur = cur ^ 1;                   // main.jl:621 as an index flip
                 }
-                if (A.accepted) A.accepted[m] = accd ? 1 : 0;
-                if (A.delta) A.delta[m] = delta;
-                if (dry) { D.ret = 1; s_stop = 1; }
-                else {
+                if (dry) {
+                    D.ret = 1; s_stop = 1; pos = pos_m;
+                    if (D.is_trans) D.tr.attempt -= 1; else D.ro.attempt -= 1;
+                    if (overlap) D.n_ovl -= 1;
+                } else {
+                    if (A.accepted) A.accepted[m] = accd ? 1 : 0;
+                    if (A.delta) A.delta[m] = delta;
                     if (A.adjust && i == N - 1) {                                     // main.jl:645-651
                         D.tr.d_max = D.dr_max; adjust_step(D.tr, L); D.dr_max = D.tr.d_max;
                         D.ro.d_max = D.dphi_max; adjust_step(D.ro, L); D.dphi_max = D.ro.d_max;
@@ -568,7 +575,7 @@ template <int S>
 struct ChainCand {
     double com[3], site[S][3], ei[4];            // trial COM, trial sites, trial quaternion
     double ocom[3], osite[S][3], q[S];           // molecule's resident COM, sites and charges (from L2: its owner is another SM)
-    long long pos_end;
+    long long pos_begin, pos_end;                // stream position before / after drawing this candidate
     int is_trans, ret, dry, pad;
 };
 
@@ -735,7 +742,7 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                     T.site[s][c] = add(rnew[c], add(add(mul(d0, a[0][c]), mul(d1, a[1][c])), mul(d2, a[2][c])));
             }
             T.com[0] = rnew[0]; T.com[1] = rnew[1]; T.com[2] = rnew[2];
-            T.pos_end = pos; T.is_trans = is_trans; T.ret = ret; T.dry = dry ? 1 : 0;
+            T.pos_begin = p0; T.pos_end = pos; T.is_trans = is_trans; T.ret = ret; T.dry = dry ? 1 : 0;
         }
         __syncwarp();
         if (A.style_recip && lane < 2 * S * 3) {            // ewalds.jl:770-795 for the old and the trial sites
@@ -986,7 +993,8 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                         if (pos >= A.n_uniforms) { dry = true; u_metro = 0.5; } else { ++pos; drew = 1; }
                         okm = exp(-x) > u_metro;
                     }
-                    const bool accd = okm && !overlap;                                        // main.jl:598
+                    // a move whose draws ran past the end of the stream never happened (see k_chain)
+                    const bool accd = okm && !overlap && !dry;                                // main.jl:598
                     if (accd) {
                         D.tot_e = add(D.tot_e, delta);
                         D.tot_v = add(D.tot_v, add(sub(new_v, old_v), recv));
@@ -1009,12 +1017,15 @@ k_chains(const __grid_constant__ DevSystem Sy, const __grid_constant__ ChainArgs
                         for (int k = 0; k < 4; ++k) myquat[4 * i + k] = T.ei[k];                  // this CTA's own replica
                         if (A.style_recip && !overlap) s_cur = cur ^ 1;                           // main.jl:621 as an index flip
                     }
-                    if (A.accepted && rank == 0) A.accepted[m] = accd ? 1 : 0;
-                    if (A.delta && rank == 0) A.delta[m] = delta;
                     s_pos = pos;
                     s_sel = drew;                                                             // which candidate of move m+1 is the real one
-                    if (dry) { D.ret = 1; s_stop = 1; }
-                    else {
+                    if (dry) {
+                        D.ret = 1; s_stop = 1; s_pos = T.pos_begin;
+                        if (T.is_trans) D.tr.attempt -= 1; else D.ro.attempt -= 1;
+                        if (overlap) D.n_ovl -= 1;
+                    } else {
+                        if (A.accepted && rank == 0) A.accepted[m] = accd ? 1 : 0;
+                        if (A.delta && rank == 0) A.delta[m] = delta;
                         if (late) {                                                           // main.jl:645-651
                             D.tr.d_max = D.dr_max; adjust_step(D.tr, L); D.dr_max = D.tr.d_max;
                             D.ro.d_max = D.dphi_max; adjust_step(D.ro, L); D.dphi_max = D.ro.d_max;
@@ -1123,8 +1134,10 @@ k_chain_atoms(DevAtoms At, const __grid_constant__ ChainAtomArgs A)
         return v;
     };
 
+    long long pos_m = 0;                                     // stream position at the start of the current move
     for (long long m = 0; m < A.n_moves; ++m) {
         const int i = (int)(m % N), par = (int)(m & 1);
+        pos_m = pos;
         // ================= step 0: the trial position (mainMonatomic.jl:375-380), lane 0 of warp 0
         if (warp == 0) {
             if (pre_cnt > 0) {
@@ -1229,6 +1242,7 @@ k_chain_atoms(DevAtoms At, const __grid_constant__ ChainAtomArgs A)
                 const double x = fma(fma(-q0, A.temperature, delta), A.inv_temperature, q0);   // delta / T
                 bool okm = true;
                 if (!(x < 0.0)) okm = exp(-x) > next_u();    // Metropolis
+                if (dry) okm = false;                        // the stream ran dry inside this move: it never happened
                 if (okm) {
                     tot_e = add(tot_e, delta);
                     tot_v = add(tot_v, sub(v_new, v_old));
@@ -1238,9 +1252,12 @@ k_chain_atoms(DevAtoms At, const __grid_constant__ ChainAtomArgs A)
                         s_f[i - a_lo] = make_float4((float)s_rn[0], (float)s_rn[1], (float)s_rn[2], 0.f);
                     }
                 }
-                if (A.accepted && rank == 0) A.accepted[m] = okm ? 1 : 0;
-                if (A.delta && rank == 0) A.delta[m] = delta;
-                if (dry) { ret = 1; s_stop = 1; } else { n_done = m + 1; if (okm) n_tacc += 1; }
+                if (dry) { ret = 1; s_stop = 1; pos = pos_m; }
+                else {
+                    if (A.accepted && rank == 0) A.accepted[m] = okm ? 1 : 0;
+                    if (A.delta && rank == 0) A.delta[m] = delta;
+                    n_done = m + 1; if (okm) n_tacc += 1;
+                }
             }
         }
         __syncthreads();

@@ -648,20 +648,22 @@ struct GatherArgs {
 static __global__ void k_gather(GatherArgs A)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.n_mol) return;
-    const int m = A.perm ? A.perm[p] : p;
-    if (A.perm && A.zl_cnt < A.ncd) {      // sharded evaluation: this rank reads its unit range and one layer above it
+    // no early return: every lane takes part in the warp reduction of max |site - COM| below (inactive lanes contribute 0)
+    bool active = p < A.n_mol;
+    const int m = active ? (A.perm ? A.perm[p] : p) : 0;
+    if (active && A.perm && A.zl_cnt < A.ncd) {      // sharded evaluation: this rank reads its unit range and one layer above it
         const int z = A.cell_of[m] / (A.ncd * A.ncd);
         int dz = z - A.zl_lo; if (dz < 0) dz += A.ncd;
-        if (dz >= A.zl_cnt) return;
+        if (dz >= A.zl_cnt) active = false;
     }
+    double dev = 0.0;
+    if (active) {
     A.ovl[p] = 0u;
     const double4 c = A.com[m];
     double4 cn = c;
     cn.x = A.f * c.x; cn.y = A.f * c.y; cn.z = A.f * c.z;
     const double chx = cn.x - c.x, chy = cn.y - c.y, chz = cn.z - c.z;
     A.scom[p] = cn;
-    double dev = 0.0;
     for (int a = 0; a < A.S; ++a) {
         double4 s = A.site[(size_t)m * A.S + a];
         dev = fmax(dev, fmax(fabs(s.x - c.x), fmax(fabs(s.y - c.y), fabs(s.z - c.z))));
@@ -675,6 +677,7 @@ static __global__ void k_gather(GatherArgs A)
         const int id = A.cell_of[m], n = A.ncd;
         A.gf[p] = make_float4((float)(cn.x - (double)(id % n) * A.edge), (float)(cn.y - (double)((id / n) % n) * A.edge),
                               (float)(cn.z - (double)(id / (n * n)) * A.edge), 0.f);
+    }
     }
     // warp max, then one atomic per warp (non-negative doubles order like their bit patterns)
     for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));

@@ -1,0 +1,595 @@
+// kernels_pairs_v7.cuh — full pair energy for potential() / volume moves (Ewald/energy.jl:946-1032, :864-943;
+// Ewald/volumeChange.jl:91-111), cell mode, 3-site molecules with identical per-site charges (SPC/E, TIP3P).
+// Reference semantics as before: COM gate |COM_ij|² < r_cut² (strict, energy.jl:250 / ewalds.jl:337), nine
+// q_a q_b erfc(κr)/r site pairs (ewalds.jl:359-367), O–O LJ with the COM-separation virial (energy.jl:270-282),
+// every unordered molecule pair once.
+//
+// What changed against k_pairs_v6 and why (ncu source page of v6, profiles/r02_v6_sass_regions.txt: 405 M warp
+// instructions per launch, of which 31 % FP64 arithmetic, 38 % the COM gate, 17 % consume bookkeeping, 14 % per-unit
+// staging / fix-up / spin):
+//
+//   state   = a GHOST-EXTENDED cell grid in a fixed-capacity layout.  k_bin7 drops every molecule into the bucket of
+//             its cell (64 slots per cell, one atomic per molecule, no prefix sum); k_gather7 (one warp per cell of the
+//             (ncd+2) x (ncd+2) x (ncd+1) extended grid) orders a cell's members by molecule index and writes 96-byte rows
+//             {3 sites xyz, COM xyz} + cell-local FP32 gate coordinates, the ghost cells already translated by ±L.  The
+//             pair kernel therefore has no periodic-wrap logic, no slot descriptors to build (a neighbour is `cell + const`)
+//             and nothing to fix up after a tile has landed.
+//   gate    = a lane OWNS B molecules (one per 32-wide chunk of the B tile, coordinates in registers) and walks the
+//             warp's A rows, which arrive by shared-memory broadcast as {−2a, r_c² − |a|²}:
+//                 |a − b|² < r_c²   ⇔   |b|² − 2a·b < r_c² − |a|²          3 FFMA + 1 FSETP + 1 predicated LOP per test
+//             into a per-lane 16-bit row mask — no ballot, no popc, no store per test: 6 instructions per 32 tests
+//             instead of 26.  (FP32, conservative: the threshold carries the worst-case rounding error; the exact FP64
+//             test on the same doubles as the reference is repeated on the survivors.)
+//   queue   = once per unit: popc over the masks, one warp scan, every lane appends its own survivors.
+//   pipeline= a fifth PRODUCER warp runs the unit sequence ahead of the four consumer warps: it draws the ticket, reads
+//             the cell populations, and issues the cp.async.bulk copies — gate coordinates of unit j+1 (two-stage ring)
+//             while unit j is evaluated, the rows of unit j while unit j is being gated.  Consumers never execute a
+//             CTA-wide barrier and only ever wait on an mbarrier whose copy was issued a phase earlier.
+#pragma once
+#include "kernels_pairs.cuh"
+
+// ---- unit = (home cell, group of 5/5/4 half-shell slots)
+#define V3_GROUPS 3
+static __constant__ int c_v3_group_begin[V3_GROUPS + 1] = {0, 5, 10, 14};
+
+// MUFU.RSQ64H seed + one cubic Newton step (relative error ≈ 1e-19·… → correctly rounded to ~1 ulp for
+// normal positive r²; r² = 0 gives +inf like 1/sqrt(0)): the CUDA rsqrt() sequence without its
+// special-value slow path, which this kernel never needs.
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(x, -(y0 * y0), 1.0);
+    return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+}
+
+// ---- mbarrier / bulk-copy (TMA engine, SASS UBLKCP) primitives
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+#define V7_CONSUMERS 4
+#define V7_BLOCK (32 * (V7_CONSUMERS + 1))
+#define V7_CAP 64          // molecules per cell (fixed-capacity layout); a denser cell makes the path decline
+#define V7_BCAP 256        // rows of the B tile; a group with more neighbours is split into two sub-units
+#define V7_ROW 12
+#define V7_QCAP 1024       // queue entries per consumer warp
+#define V7_MAXCH (V7_BCAP / 32)
+
+constexpr size_t V7_SMEM = (size_t)(V7_CAP + V7_BCAP) * V7_ROW * sizeof(double) +        // rows: A | B
+                           2 * (size_t)(V7_CAP + V7_BCAP) * sizeof(float4) +              // gate coordinates, two stages
+                           (size_t)V7_CONSUMERS * V7_QCAP * sizeof(unsigned short);
+
+// ---- extended grid: real cell (cx, cy, cz) is extended cell (cx+1, cy+1, cz); ghosts at x,y = 0 / ncd+1 and z = ncd
+struct V7Grid {
+    int ncd, EX, EY;       // EX = EY = ncd + 2; extended layers ez = 0 .. ncd
+    int z0, z1;            // this rank's home layers [z0, z1); it reads layers z0 .. z1 (z1 == ncd: the ghost of layer 0)
+    double edge;           // box_new / ncd
+    double box_new;
+};
+__host__ __device__ __forceinline__ int v7_ext_cells(const V7Grid &G) { return G.EX * G.EY * (G.ncd + 1); }
+
+struct Bin7Args {
+    const double4 *com;
+    int n_mol;
+    double inv_cell;       // ncd / box (of the resident coordinates: fractional positions do not change with the box)
+    V7Grid G;
+    int *count;            // [ncd³] (zeroed)
+    int *bucket;           // [ncd³][V7_CAP]
+};
+
+// one thread per molecule: cell of its COM, slot by arrival (k_gather7 orders the members afterwards)
+static __global__ void k_bin7(Bin7Args A)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= A.n_mol) return;
+    const double4 c = A.com[m];
+    const int n = A.G.ncd;
+    const int cx = cell_coord(c.x, A.inv_cell, n), cy = cell_coord(c.y, A.inv_cell, n), cz = cell_coord(c.z, A.inv_cell, n);
+    const bool needed = (cz >= A.G.z0 && cz <= A.G.z1) || (A.G.z1 == n && cz == 0);
+    if (!needed) return;
+    const int id = cx + n * (cy + n * cz);
+    const int pos = atomicAdd(&A.count[id], 1);
+    if (pos < V7_CAP) A.bucket[(size_t)id * V7_CAP + pos] = m;
+}
+
+struct Gather7Args {
+    const double4 *com, *site;     // resident state (3 sites per molecule)
+    const int *count, *bucket;
+    V7Grid G;
+    double f;                      // box_new / box (1.0: no volume change)
+    double *rows;                  // [ext cells][V7_CAP][12]
+    float4 *gf;                    // [ext cells][V7_CAP]
+    int *ecount;                   // [ext cells]
+    unsigned long long *max_dev_bits;
+    unsigned int *err_flag;
+    int *max_count;
+};
+
+// one warp per extended cell: members ordered by molecule index (so every sum downstream is independent of the
+// atomics' arrival order), scaled for a volume trial (volumeChange.jl:62-80: COM' = f·COM, sites shifted rigidly),
+// ghosts translated by ±L'
+static __global__ void __launch_bounds__(256) k_gather7(Gather7Args A)
+{
+    const int lane = threadIdx.x & 31;
+    const int wcell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const V7Grid &G = A.G;
+    const int per_layer = G.EX * G.EY;
+    const int n_layers = G.z1 - G.z0 + 1;
+    if (wcell >= per_layer * n_layers) return;
+    const int ez = G.z0 + wcell / per_layer, rem = wcell - (wcell / per_layer) * per_layer;
+    const int ey = rem / G.EX, ex = rem - ey * G.EX;
+    const int e = ex + G.EX * (ey + G.EY * ez);
+    const int n = G.ncd;
+    int rx = ex - 1, ry = ey - 1, rz = ez;
+    double shx = 0.0, shy = 0.0, shz = 0.0;
+    if (rx < 0) { rx += n; shx = -G.box_new; } else if (rx >= n) { rx -= n; shx = G.box_new; }
+    if (ry < 0) { ry += n; shy = -G.box_new; } else if (ry >= n) { ry -= n; shy = G.box_new; }
+    if (rz >= n) { rz -= n; shz = G.box_new; }
+    const int c = rx + n * (ry + n * rz);
+    int cnt = A.count[c];
+    if (lane == 0) atomicMax(A.max_count, cnt);
+    if (cnt > V7_CAP) { if (lane == 0) atomicExch(A.err_flag, 1u); cnt = 0; }
+    if (lane == 0) A.ecount[e] = cnt;
+    const int *b = A.bucket + (size_t)c * V7_CAP;
+    const int v0 = lane < cnt ? b[lane] : 0x7fffffff, v1 = lane + 32 < cnt ? b[lane + 32] : 0x7fffffff;
+    int r0 = 0, r1 = 0;
+    for (int t = 0; t < cnt; ++t) {
+        const int v = t < 32 ? __shfl_sync(0xffffffffu, v0, t) : __shfl_sync(0xffffffffu, v1, t - 32);
+        r0 += v < v0; r1 += v < v1;
+    }
+    const double ox = (double)rx * G.edge, oy = (double)ry * G.edge, oz = (double)rz * G.edge;
+    double dev = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int m = h ? v1 : v0, r = h ? r1 : r0;
+        if (m == 0x7fffffff) continue;
+        const double4 cm = A.com[m];
+        const double cnx = A.f * cm.x, cny = A.f * cm.y, cnz = A.f * cm.z;
+        const double chx = cnx - cm.x, chy = cny - cm.y, chz = cnz - cm.z;
+        double v[12];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double4 s = A.site[(size_t)m * 3 + a];
+            dev = fmax(dev, fmax(fabs(s.x - cm.x), fmax(fabs(s.y - cm.y), fabs(s.z - cm.z))));
+            v[3 * a] = (s.x + chx) + shx; v[3 * a + 1] = (s.y + chy) + shy; v[3 * a + 2] = (s.z + chz) + shz;
+        }
+        v[9] = cnx + shx; v[10] = cny + shy; v[11] = cnz + shz;
+        double2 *dst = reinterpret_cast<double2 *>(A.rows + ((size_t)e * V7_CAP + r) * V7_ROW);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dst[k] = make_double2(v[2 * k], v[2 * k + 1]);
+        A.gf[(size_t)e * V7_CAP + r] = make_float4((float)(cnx - ox), (float)(cny - oy), (float)(cnz - oz), 0.f);
+    }
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    if (lane == 0) atomicMax(A.max_dev_bits, (unsigned long long)__double_as_longlong(dev));
+}
+
+struct V7Args {
+    V7Grid G;
+    int units;                     // 3 groups x ncd² x (z1 − z0) home cells
+    const double *rows;
+    const float4 *gf;
+    const int *ecount;
+    float gate_rc2f;               // conservative FP32 gate threshold (>= r_cut² + worst-case rounding of the dot form)
+    double rc_qq2;
+    long long rcqq_bits;
+    double qq_tab[9];
+    unsigned qq_negmask;
+    double lj_eps, lj_sig2;
+    double pc[MMC_ERF_MAXDEG + 1];
+    double pk2s;
+    const double *max_dev;
+    unsigned int *err_flag;
+    unsigned int *n_ovl;
+    unsigned int *ticket;          // zeroed before the launch
+    double4 *unit_partial;         // [units][2 sub-units][V7_CONSUMERS]
+};
+
+// what the producer publishes per sub-unit (ring of four, guarded by the gate-coordinate barriers)
+struct V7Desc {
+    int valid;                     // 0: this CTA's unit sequence has ended
+    int nA, nB, nsl;
+    int self_n;                    // nA when slot 0 of this sub-unit is the home cell itself (keep q > p), else 0
+    int rot;                       // row rotation of the unit (spreads the remainder rows over the warps)
+    int boff[6];                   // first B row of slot k; entries from nsl on hold nB
+    float4 off[5];                 // slot offset of slot k in Å (FP32): gate coordinates are relative to the home cell
+    long long sub;                 // partial slot of this sub-unit: unit * 2 + pass
+};
+
+template <int DEG, bool DIRECT>
+static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_constant__ V7Args A)
+{
+    constexpr int S = 3;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_rowA = reinterpret_cast<double *>(smem_raw);
+    double *s_rowB = s_rowA + V7_CAP * V7_ROW;
+    float4 *s_gf = reinterpret_cast<float4 *>(s_rowB + V7_BCAP * V7_ROW);          // [2][V7_CAP + V7_BCAP]
+    unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_gf + 2 * (V7_CAP + V7_BCAP));
+    __shared__ V7Desc s_desc[4];
+    __shared__ float4 s_a2[V7_CONSUMERS][16];
+    __shared__ __align__(8) unsigned long long s_full_gf[2], s_empty_gf[2], s_full_rows, s_empty_rows;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&s_full_gf[0], 1); mbar_init(&s_full_gf[1], 1);
+        mbar_init(&s_empty_gf[0], V7_CONSUMERS); mbar_init(&s_empty_gf[1], V7_CONSUMERS);
+        mbar_init(&s_full_rows, 1); mbar_init(&s_empty_rows, V7_CONSUMERS);
+        // the always-true cut-off tests (energy.jl:270, ewalds.jl:362) must really be always true for this state
+        const double reach = sqrt(A.rc_qq2) + 2.0 * (*A.max_dev);
+        if (!(reach * reach < A.rc_qq2 + 100.0) && blockIdx.x == 0) atomicExch(A.err_flag, 1u);
+    }
+    __syncthreads();                                       // the only CTA-wide barrier of the kernel
+
+    if (warp == V7_CONSUMERS) {
+        // ======================================================================== producer warp
+        const int n = A.G.ncd, EX = A.G.EX, EY = A.G.EY;
+        const float edge_f = (float)A.G.edge;
+        long long u = blockIdx.x;
+        unsigned tk_pending = 0;
+        if (lane == 0) tk_pending = atomicAdd(A.ticket, 1u);       // one ticket is always in flight: drawn a unit ahead
+        unsigned seq = 0;
+        while (u < A.units) {
+            const int ci = (int)(u / V3_GROUPS), g = (int)(u - (long long)ci * V3_GROUPS);
+            const int lz = ci / (n * n), r2 = ci - lz * n * n, cy = r2 / n, cx = r2 - cy * n;
+            const int e = (cx + 1) + EX * ((cy + 1) + EY * (A.G.z0 + lz));
+            const int sl0 = c_v3_group_begin[g], nsl_all = c_v3_group_begin[g + 1] - sl0;
+            int en = e, cnt = 0;
+            if (lane < nsl_all) {
+                const int s = sl0 + lane;
+                en = e + c_half_shell[s][0] + EX * (c_half_shell[s][1] + EY * c_half_shell[s][2]);
+                cnt = A.ecount[en];
+            } else if (lane == 5) cnt = A.ecount[e];
+            const unsigned tk = __shfl_sync(FULL, tk_pending, 0);
+            const long long u_next = (long long)gridDim.x + tk;
+            if (lane == 0 && u_next < A.units) tk_pending = atomicAdd(A.ticket, 1u);
+            // both sub-unit slots of the unit start at zero (a unit is skipped when a tile is empty; most units have one pass)
+            if (lane < 2 * V7_CONSUMERS) A.unit_partial[(size_t)u * 2 * V7_CONSUMERS + lane] = make_double4(0.0, 0.0, 0.0, 0.0);
+            const int nA = __shfl_sync(FULL, cnt, 5);
+            int pass = 0;
+            for (int s_begin = 0; s_begin < nsl_all && nA > 0; ++pass) {
+                int incl = (lane >= s_begin && lane < nsl_all) ? cnt : 0;          // inclusive prefix of the B counts from s_begin on
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                // slots [s_begin, se) fit the B tile (every count is <= V7_CAP, so at least four do)
+                const int se = min(nsl_all, __popc(__ballot_sync(FULL, lane < 5 && incl <= V7_BCAP)));
+                const int nB = __shfl_sync(FULL, incl, se - 1);
+                if (nB > 0) {
+                    const int sg = seq & 1;
+                    V7Desc &D = s_desc[seq & 3];
+                    mbar_wait(&s_empty_gf[sg], ((seq >> 1) & 1u) ^ 1u);              // consumers are done gating sub-unit seq − 2
+                    const bool mine = lane >= s_begin && lane < se;
+                    if (mine) {
+                        const int k = lane - s_begin, s = sl0 + lane;
+                        D.boff[k] = incl - cnt;
+                        D.off[k] = make_float4((float)c_half_shell[s][0] * edge_f, (float)c_half_shell[s][1] * edge_f,
+                                               (float)c_half_shell[s][2] * edge_f, 0.f);
+                    }
+                    if (lane >= se - s_begin && lane < 6) D.boff[lane] = nB;
+                    if (lane == 0) {
+                        D.valid = 1; D.nA = nA; D.nB = nB; D.nsl = se - s_begin;
+                        D.self_n = (g == 0 && s_begin == 0) ? nA : 0;
+                        D.rot = (int)(u & 3); D.sub = u * 2 + pass;
+                    }
+                    __syncwarp();
+                    float4 *gfA = s_gf + sg * (V7_CAP + V7_BCAP), *gfB = gfA + V7_CAP;
+                    if (lane == 0) mbar_arrive_expect_tx(&s_full_gf[sg], (unsigned)(nA + nB) * 16u);
+                    __syncwarp();
+                    if (mine && cnt > 0) bulk_g2s(gfB + (incl - cnt), A.gf + (size_t)en * V7_CAP, (unsigned)cnt * 16u, &s_full_gf[sg]);
+                    if (lane == 5) bulk_g2s(gfA, A.gf + (size_t)e * V7_CAP, (unsigned)nA * 16u, &s_full_gf[sg]);
+                    // the rows follow as soon as the consumers have left the previous sub-unit: they land while this one is gated
+                    mbar_wait(&s_empty_rows, (seq & 1u) ^ 1u);
+                    if (lane == 0) mbar_arrive_expect_tx(&s_full_rows, (unsigned)(nA + nB) * (V7_ROW * 8u));
+                    __syncwarp();
+                    if (mine && cnt > 0)
+                        bulk_g2s(s_rowB + (size_t)(incl - cnt) * V7_ROW, A.rows + (size_t)en * V7_CAP * V7_ROW, (unsigned)cnt * (V7_ROW * 8u), &s_full_rows);
+                    if (lane == 5) bulk_g2s(s_rowA, A.rows + (size_t)e * V7_CAP * V7_ROW, (unsigned)nA * (V7_ROW * 8u), &s_full_rows);
+                    ++seq;
+                }
+                s_begin = se;
+            }
+            u = u_next;
+        }
+        // end marker
+        const int sg = seq & 1;
+        mbar_wait(&s_empty_gf[sg], ((seq >> 1) & 1u) ^ 1u);
+        if (lane == 0) { s_desc[seq & 3].valid = 0; mbar_arrive(&s_full_gf[sg]); }
+        return;
+    }
+
+    // ============================================================================ consumer warps
+    unsigned short *q = s_queue + warp * V7_QCAP;
+    float4 *a2 = s_a2[warp];
+    const float rc2f = A.gate_rc2f;
+    const double lj_eps = A.lj_eps, lj_sig2 = A.lj_sig2;
+    double acc_lj = 0.0, acc_vir = 0.0, acc_q = 0.0;
+    unsigned long long my_pairs = 0;
+
+    auto consume = [&](unsigned e, bool have) {          // one queued molecule pair per lane
+        const int p = e & 63u, qi = e >> 6;
+        const double2 *ra = reinterpret_cast<const double2 *>(s_rowA + p * V7_ROW);
+        const double2 *rb = reinterpret_cast<const double2 *>(s_rowB + qi * V7_ROW);
+        const double2 a4 = ra[4], a5 = ra[5], b4 = rb[4], b5 = rb[5];
+        // exact gate on the FP64 COMs (strict <, energy.jl:250 / ewalds.jl:337); un-contracted, left to right, like Julia
+        // evaluates rij[1]*rij[1] + rij[2]*rij[2] + rij[3]*rij[3]
+        const double rx = b4.y - a4.y, ry = b5.x - a5.x, rz = b5.y - a5.y;
+        const double r2com = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+        const bool act = have && (__double_as_longlong(r2com) < A.rcqq_bits);
+        const unsigned am = __ballot_sync(FULL, act);
+        if (lane == 0) my_pairs += __popc(am);
+        if (act) {
+            const double2 a0 = ra[0], a1 = ra[1], a2r = ra[2], a3 = ra[3];
+            const double2 b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3];
+            const double ax[S] = {a0.x, a1.y, a3.x}, ay[S] = {a0.y, a2r.x, a3.y}, az[S] = {a1.x, a2r.y, a4.x};
+            const double bx[S] = {b0.x, b1.y, b3.x}, by[S] = {b0.y, b2.x, b3.y}, bz[S] = {b1.x, b2.y, b4.x};
+            double r2[S * S], pv[S * S], ri[S * S];
+            double ddx = 0, ddy = 0, ddz = 0;            // O–O separation for the LJ term
+            int hmin = 0x7fffffff;
+#pragma unroll
+            for (int a = 0; a < S; ++a)
+#pragma unroll
+                for (int b = 0; b < S; ++b) {
+                    const int j = a * S + b;
+                    const double dx = bx[b] - ax[a], dy = by[b] - ay[a], dz = bz[b] - az[a];
+                    if (j == 0) { ddx = dx; ddy = dy; ddz = dz; }
+                    r2[j] = dx * dx + dy * dy + dz * dz;
+                    hmin = min(hmin, __double2hiint(r2[j]));
+                }
+            if (hmin < 0x3FE00000) {   // some site pair has r² < 0.5: the sign rule q_a q_b < 0 (ewalds.jl:359) decides
+                bool ov = false;
+#pragma unroll
+                for (int j = 0; j < S * S; ++j) ov |= ((A.qq_negmask >> j) & 1u) && __double2hiint(r2[j]) < 0x3FE00000;
+                if (ov) atomicAdd(A.n_ovl, 1u);   // the overlap rule zeroes whole rows: the host re-evaluates on the general path
+            }
+#pragma unroll
+            for (int j = 0; j < S * S; ++j) ri[j] = fast_rsqrt(r2[j]);
+            {   // smooth part of erfc(κr)/r as one polynomial: Horner in r² (DIRECT) or in s = σκ²r² − 1
+                double x[S * S];
+#pragma unroll
+                for (int j = 0; j < S * S; ++j) { x[j] = DIRECT ? r2[j] : fma(r2[j], A.pk2s, -1.0); pv[j] = A.pc[DEG]; }
+#pragma unroll
+                for (int k = DEG - 1; k >= 0; --k)
+#pragma unroll
+                    for (int j = 0; j < S * S; ++j) pv[j] = fma(pv[j], x[j], A.pc[k]);
+            }
+#pragma unroll
+            for (int j = 0; j < S * S; ++j) acc_q = fma(A.qq_tab[j], ri[j] + pv[j], acc_q);   // ewalds.jl:366-367
+            {   // LJ 12-6 on the O–O pair (energy.jl:270-282), virial with the COM separation
+                const double rinv2 = ri[0] * ri[0];
+                const double s2 = lj_sig2 * rinv2, s6 = s2 * s2 * s2, s12 = s6 * s6;
+                acc_lj += lj_eps * (s12 - s6);
+                const double wv = lj_eps * (2.0 * s12 - s6) * s2;
+                acc_vir += wv * (rx * ddx + ry * ddy + rz * ddz);
+            }
+        }
+    };
+
+    for (unsigned seq = 0;; ++seq) {
+        const int sg = seq & 1;
+        mbar_wait(&s_full_gf[sg], (seq >> 1) & 1u);
+        const V7Desc &D = s_desc[seq & 3];
+        if (!D.valid) break;
+        const int nA = D.nA, nB = D.nB, self_n = D.self_n;
+        const int p0 = (warp + D.rot) & (V7_CONSUMERS - 1);
+        const int nr = nA > p0 ? (nA - p0 + V7_CONSUMERS - 1) / V7_CONSUMERS : 0;      // rows p0, p0+4, ... of the home cell
+        const float4 *gfA = s_gf + sg * (V7_CAP + V7_BCAP), *gfB = gfA + V7_CAP;
+        // ---- this warp's A rows as {−2a, r_c² − |a|²}; the tail of the table never passes
+        if (lane < 16) {
+            float4 t = make_float4(0.f, 0.f, 0.f, -INFINITY);
+            if (lane < nr) {
+                const float4 a = gfA[p0 + V7_CONSUMERS * lane];
+                t = make_float4(-2.f * a.x, -2.f * a.y, -2.f * a.z, rc2f - fmaf(a.z, a.z, fmaf(a.y, a.y, a.x * a.x)));
+            }
+            a2[lane] = t;
+        }
+        __syncwarp();
+        // ---- gate: lane owns B molecule t = 32 j + lane of every chunk j; 16-bit mask over the warp's rows
+        unsigned m[V7_MAXCH];
+        const int b1 = D.boff[1], b2 = D.boff[2], b3 = D.boff[3], b4 = D.boff[4];
+#pragma unroll
+        for (int j = 0; j < V7_MAXCH; ++j) {
+            m[j] = 0u;
+            if (32 * j < nB && nr > 0) {
+                const int t = 32 * j + lane;
+                const bool valid = t < nB;
+                const float4 g = gfB[valid ? t : 0];
+                const int sl = (t >= b1) + (t >= b2) + (t >= b3) + (t >= b4);
+                const float4 o = D.off[sl];
+                const float bx = g.x + o.x, by = g.y + o.y, bz = g.z + o.z;
+                const float bw = valid ? fmaf(bz, bz, fmaf(by, by, bx * bx)) : INFINITY;
+                unsigned mask = 0u;
+#pragma unroll
+                for (int r4 = 0; r4 < 16; r4 += 4) {
+                    if (r4 < nr) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 a = a2[r4 + k];
+                            const float tt = fmaf(a.z, bz, fmaf(a.y, by, fmaf(a.x, bx, bw)));
+                            if (tt < a.w) mask |= 1u << (r4 + k);
+                        }
+                    }
+                }
+                if (t < self_n) {   // home cell against itself: keep q > p with p = p0 + 4 r  ⇔  r < ceil((t − p0) / 4)
+                    const int nv = t > p0 ? (t - p0 + V7_CONSUMERS - 1) / V7_CONSUMERS : 0;
+                    mask &= nv >= 16 ? 0xffffu : ((1u << nv) - 1u);
+                }
+                m[j] = mask;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty_gf[sg]);           // the producer may refill this gate stage
+        // ---- queue: every lane appends its own survivors behind those of the lanes below it
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < V7_MAXCH; ++j) cnt += __popc(m[j]);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total <= V7_QCAP) {
+            int base = incl - cnt;
+#pragma unroll
+            for (int j = 0; j < V7_MAXCH; ++j) {
+                if (32 * j < nB) {
+                    unsigned mm = m[j];
+                    const unsigned eb = ((unsigned)(32 * j + lane) << 6) | (unsigned)p0;
+                    while (mm) {
+                        const int r = __ffs(mm) - 1;
+                        mm &= mm - 1u;
+                        q[base++] = (unsigned short)(eb + (unsigned)(V7_CONSUMERS * r));
+                    }
+                }
+            }
+            __syncwarp();
+            mbar_wait(&s_full_rows, seq & 1u);
+            for (int b = 0; b < total; b += 32) {
+                const bool have = b + lane < total;
+                consume(have ? q[b + lane] : 0u, have);
+            }
+        } else {
+            // a unit with more survivors than the queue holds (far denser than a liquid): chunk by chunk
+            mbar_wait(&s_full_rows, seq & 1u);
+#pragma unroll
+            for (int j = 0; j < V7_MAXCH; ++j) {
+                if (32 * j < nB) {
+                    unsigned mm = m[j];
+                    const int c = __popc(mm);
+                    int ic = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, ic, o); if (lane >= o) ic += v; }
+                    const int tot = __shfl_sync(FULL, ic, 31);
+                    int base = ic - c;
+                    const unsigned eb = ((unsigned)(32 * j + lane) << 6) | (unsigned)p0;
+                    while (mm) {
+                        const int r = __ffs(mm) - 1;
+                        mm &= mm - 1u;
+                        q[base++] = (unsigned short)(eb + (unsigned)(V7_CONSUMERS * r));
+                    }
+                    __syncwarp();
+                    for (int b = 0; b < tot; b += 32) {
+                        const bool have = b + lane < tot;
+                        consume(have ? q[b + lane] : 0u, have);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        // ---- this sub-unit's sums, per warp, at a place that depends on the unit only (folded in unit order afterwards)
+        const double w0 = warp_sum(acc_lj), w1 = warp_sum(acc_vir), w2 = warp_sum(acc_q);
+        if (lane == 0) A.unit_partial[(size_t)D.sub * V7_CONSUMERS + warp] = make_double4(w0, w1, w2, (double)my_pairs);
+        acc_lj = 0.0; acc_vir = 0.0; acc_q = 0.0; my_pairs = 0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty_rows);             // the producer may refill the rows
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_eval_tail — everything after the two big kernels in one launch.  Block b folds its contiguous share of the
+// per-(unit, warp) pair sums (fixed order) and its share of the k-vectors of the ρ(k) partials (CTA order); the last
+// block to finish (ticket) adds the block sums in block order, forms E_recip = Σ cfac |ρ(k)|² (ewalds.jl:599),
+// stores ρ(k) to the resident buffers (:600-601), and either publishes the scalars to the host (one rank) or pushes
+// this rank's vector into every peer's exchange buffer (sharded evaluation, kernels_peer.cuh).
+// ------------------------------------------------------------------------------------------------------------
+#define TAIL_BLOCKS 64
+#define TAIL_THREADS 256
+
+struct TailArgs {
+    const double4 *unit_partial; long long n_partial;   // pair sums
+    const double2 *rhok_partial; int rhok_blocks, nkvecs;   // ρ(k) partials [rhok_blocks][nkvecs] (nkvecs == 0: no k-space)
+    double4 *block_sums;           // [TAIL_BLOCKS]
+    unsigned int *done;            // ticket of the tail blocks (zeroed)
+    const unsigned int *n_ovl, *err_flag; const int *max_count;
+    double *vec;                   // [MMC_NSCAL + 2 nkvecs]: the rank's partial-sum vector (sharding.py layout)
+    // one rank: finish here
+    int finish;                    // 1: E_recip, resident ρ(k), host result
+    const double *cfac; double2 *dst0, *dst1;
+    double *host_out;              // mapped pinned: [0..7] vec head, [8] sequence number (written last)
+    unsigned long long seq;
+};
+
+static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_constant__ TailArgs A)
+{
+    __shared__ double s_red[4 * (TAIL_THREADS / 32)];
+    __shared__ double2 s_s[8][33];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, b = blockIdx.x;
+    {   // pair sums: contiguous share, thread-strided, fixed tree
+        const long long per = (A.n_partial + gridDim.x - 1) / gridDim.x;
+        const long long lo = per * b, hi = lo + per < A.n_partial ? lo + per : A.n_partial;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        for (long long i = lo + tid; i < hi; i += TAIL_THREADS) { const double4 p = A.unit_partial[i]; v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w; }
+        block_sum<4, TAIL_THREADS>(v, s_red);
+        if (tid == 0) A.block_sums[b] = make_double4(v[0], v[1], v[2], v[3]);
+    }
+    // ρ(k): block b owns k-vectors [32 b, 32 b + 32); 8 slices of the CTA partials per k, added in slice order
+    for (int k0 = 32 * b; k0 < A.nkvecs; k0 += 32 * gridDim.x) {
+        const int k = k0 + (tid & 31), sl = tid >> 5;
+        const int c0 = (int)((long long)A.rhok_blocks * sl / 8), c1 = (int)((long long)A.rhok_blocks * (sl + 1) / 8);
+        double re = 0.0, im = 0.0;
+        if (k < A.nkvecs)
+            for (int c = c0; c < c1; ++c) { const double2 p = A.rhok_partial[(size_t)c * A.nkvecs + k]; re += p.x; im += p.y; }
+        __syncthreads();
+        s_s[sl][tid & 31] = make_double2(re, im);
+        __syncthreads();
+        if (sl == 0 && k < A.nkvecs) {
+            double2 t = s_s[0][tid];
+            for (int j = 1; j < 8; ++j) { t.x += s_s[j][tid].x; t.y += s_s[j][tid].y; }
+            A.vec[MMC_NSCAL + 2 * k] = t.x; A.vec[MMC_NSCAL + 2 * k + 1] = t.y;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(A.done, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (tid < (int)gridDim.x) { const double4 p = ldcg4(&A.block_sums[tid]); v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; }
+    block_sum<4, TAIL_THREADS>(v, s_red);
+    double er[1] = {0.0};
+    if (A.finish && A.nkvecs > 0) {
+        for (int k = tid; k < A.nkvecs; k += TAIL_THREADS) {
+            const double2 s = make_double2(__ldcg(&A.vec[MMC_NSCAL + 2 * k]), __ldcg(&A.vec[MMC_NSCAL + 2 * k + 1]));
+            er[0] += A.cfac[k] * (s.x * s.x + s.y * s.y);
+            if (A.dst0) A.dst0[k] = s;
+            if (A.dst1) A.dst1[k] = s;
+        }
+        block_sum<1, TAIL_THREADS>(er, s_red);
+    }
+    if (tid == 0) {
+        double h[MMC_NSCAL];
+        h[0] = v[0]; h[1] = v[1]; h[2] = v[2]; h[3] = (double)(*A.n_ovl); h[4] = er[0]; h[5] = v[3];
+        h[6] = (double)(*A.max_count); h[7] = (double)(*A.err_flag);
+        for (int i = 0; i < MMC_NSCAL; ++i) A.vec[i] = h[i];
+        if (A.finish && A.host_out) {
+            for (int i = 0; i < MMC_NSCAL; ++i) A.host_out[i] = h[i];
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(A.host_out + MMC_NSCAL) = A.seq;
+        }
+        *A.done = 0u;                                     // ready for the next evaluation
+    }
+}

@@ -23,7 +23,24 @@ struct RhokArgs {
     const int4 *kvec;
     double box;
     double2 *partial;        // [gridDim.x][nkvecs]
+    // volume trial on the resident (unscaled) state: site' = site + (f·COM − COM) of its molecule (volumeChange.jl:62-80);
+    // com == NULL: the sites are used as they are
+    const double4 *com;
+    double f;
+    int US;                  // sites per molecule (uniform topology)
 };
+
+// coordinate d of site l as the k-space sum sees it
+__device__ __forceinline__ double rhok_coord(const double4 &s, int d, const double4 *com, double f, int US, int l)
+{
+    double x = d == 0 ? s.x : (d == 1 ? s.y : s.z);
+    if (com) {
+        const double4 c = com[l / US];
+        const double cd = d == 0 ? c.x : (d == 1 ? c.y : c.z);
+        x = x + (f * cd - cd);
+    }
+    return x;
+}
 
 template <int KPT>
 static __global__ void __launch_bounds__(RHOK_BLOCK) k_rhok_partial(RhokArgs A)
@@ -52,7 +69,7 @@ static __global__ void __launch_bounds__(RHOK_BLOCK) k_rhok_partial(RhokArgs A)
             double x = 0.0, q = 0.0;
             if (base + l < c1) {
                 const double4 s = A.site[base + l];
-                x = d == 0 ? s.x : (d == 1 ? s.y : s.z);
+                x = rhok_coord(s, d, A.com, A.f, A.US, base + l);
                 q = s.w;
             }
             const double sc = (d == 0) ? q : 1.0;      // charge folded into the x table: (q*ex)*ey*ez
@@ -154,6 +171,9 @@ struct Rhok2Args {
     const int *kindex;           // [(nk+1) x (2nk+1) x (2nk+1)] index of (kx, ky, kz) in the k list or -1
     double box;
     double2 *partial;            // [gridDim.x][nkvecs]
+    const double4 *com;          // as RhokArgs: volume trial on the resident state (NULL: sites as they are)
+    double f;
+    int US;
 };
 
 template <int NK>
@@ -181,7 +201,7 @@ static __global__ void __launch_bounds__(RHOK2_BLOCK, 2) k_rhok_pairs(Rhok2Args 
             double x = 0.0, q = 0.0;
             if (base + l < c1) {
                 const double4 s = A.site[base + l];
-                x = d == 0 ? s.x : (d == 1 ? s.y : s.z);
+                x = rhok_coord(s, d, A.com, A.f, A.US, base + l);
                 q = s.w;
             }
             const double sc = (d == 0) ? q : 1.0;

@@ -21,11 +21,14 @@ void free_system(mmc_handle *h)
     h->raw_bytes = 0; h->cap_mol = 0; h->cap_sites = 0;
     dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
     h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
-    dfree(h->d_mrows); dfree(h->d_gf); dfree(h->d_chain); h->chain_bytes = 0;
-    dfree(h->d_winneed); dfree(h->d_permol); dfree(h->d_permol_out); dfree(h->d_unit_partial); h->unit_partial_cap = 0;
+    dfree(h->d_chain); h->chain_bytes = 0;
+    dfree(h->d_permol); dfree(h->d_permol_out);
     dfree(h->d_scom); dfree(h->d_ssite); dfree(h->d_pair_partial); dfree(h->d_ovl);
-    dfree(h->d_rhok_partial); dfree(h->d_units); dfree(h->d_slots);
-    h->units_cap = 0; h->slots_cap = 0;
+    dfree(h->d_rhok_partial); dfree(h->d_units);
+    h->units_cap = 0;
+    dfree(h->d7_flags); dfree(h->d7_count); dfree(h->d7_bucket); dfree(h->d7_ecount); dfree(h->d7_rows); dfree(h->d7_gf);
+    dfree(h->d7_unit_partial); dfree(h->d7_block_sums);
+    h->d7_ncd = 0; h->d7_partial_cap = 0; h->bin_version = 0;
     h->max_cell_cached = -1;
     h->has_system = false;
 }
@@ -287,6 +290,9 @@ int mmc_create(const mmc_config *cfg, mmc_handle **out)
     if ((e = cudaHostAlloc((void **)&h->h_slots, sizeof(MoveSlot) * h->max_slots, cudaHostAllocMapped)) != cudaSuccess) return fail("hostalloc", e);
     std::memset(h->h_slots, 0, sizeof(MoveSlot) * h->max_slots);
     if ((e = cudaHostGetDevicePointer((void **)&h->W.slots, h->h_slots, 0)) != cudaSuccess) return fail("mapped ptr", e);
+    if ((e = cudaHostAlloc((void **)&h->h7_res, sizeof(double) * (MMC_NSCAL + 8), cudaHostAllocMapped)) != cudaSuccess) return fail("hostalloc", e);
+    std::memset(h->h7_res, 0, sizeof(double) * (MMC_NSCAL + 8));
+    if ((e = cudaHostGetDevicePointer((void **)&h->d7_res, h->h7_res, 0)) != cudaSuccess) return fail("mapped ptr", e);
     for (auto &ev : h->tm.ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("event", e);
     {
@@ -314,6 +320,7 @@ int mmc_destroy(mmc_handle *h)
     cudaStreamSynchronize(h->stream);
     free_system(h); free_ewald(h); free_atoms(h);
     if (h->h_slots) cudaFreeHost(h->h_slots);
+    if (h->h7_res) cudaFreeHost(h->h7_res);
     if (h->h_up) cudaFreeHost(h->h_up);
     for (auto &ev : h->tm.ev) cudaEventDestroy(ev);
     for (int q = 0; q < MMC_PEER_MAX; ++q) if (h->peer_opened[q] && h->peer_base[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
@@ -343,6 +350,7 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
     if (!(box > 0) || !(rc_lj > 0) || !(rc_qq > 0)) FAIL(MMC_EINVAL, "box and cutoffs must be positive");
     CK(cudaSetDevice(h->cfg.device));
     DevSystem &S = h->S;
+    const double box_before = h->has_system ? S.box : 0.0;
     const bool realloc_needed = !h->has_system || h->cap_mol != (int)n_mol || h->cap_sites != (int)n_sites;
     if (realloc_needed) {
         const DevSystem keep = S;
@@ -442,8 +450,23 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
     h->max_cell_cached = -1;
     h->pair_level = h->pair_floor;
     if (h->pend_kind == 1) h->pend_kind = 0;
-    if (h->has_ewald) get_erf_poly(h, S.kappa, rc_qq * rc_qq + 100, h->move_poly);
+    if (h->has_ewald) {
+        get_erf_poly(h, S.kappa, rc_qq * rc_qq + 100, h->move_poly);
+        if (box != box_before) {
+            // the k-space tables survive a re-upload, but cfac depends on the box (PrepareEwaldVariables, ewalds.jl:52,78-83):
+            // rebuilt here for the new box with the resident kappa, and the resident rho(k) (a sum over the old positions)
+            // is cleared like after mmc_ewald_prepare.  A caller that follows the reference's kappa = alpha/box convention
+            // calls mmc_ewald_prepare again for the new kappa.
+            fill_cfac(h->kxyz, S.kappa, box, h->cfac);
+            CK(cudaMemcpyAsync(S.cfac, h->cfac.data(), sizeof(double) * S.nkvecs, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemsetAsync(S.rhok[0], 0, sizeof(double2) * S.nkvecs, h->stream));
+            CK(cudaMemsetAsync(S.rhok[1], 0, sizeof(double2) * S.nkvecs, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            h->cur = 0;
+        }
+    }
     h->has_system = true;
+    h->state_version++;
     h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
     return MMC_OK;
 }
@@ -494,6 +517,7 @@ int mmc_upload_positions(mmc_handle *h, const double *coords, const double *com)
     k_repack_positions<<<(unsigned)((S.n_sites + 255) / 256), 256, 0, h->stream>>>(d_coords, d_com, S.n_mol, S.n_sites, S.box,
                                                                                   S.site, S.com, h->d_info);
     LAUNCH_CHECK();
+    h->state_version++;
     CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
@@ -655,6 +679,7 @@ int mmc_set_molecule(mmc_handle *h, int64_t i, const double com[3], const double
     std::memcpy(A.site_new, sites, sizeof(double) * 3 * mol_of(h, i - 1).y);
     k_set_molecule<<<1, 32, 0, h->stream>>>(h->S, A.i, com[0], com[1], com[2], A);
     LAUNCH_CHECK();
+    h->state_version++;
     h->trial_pending = false;
     return MMC_OK;
 }
@@ -790,6 +815,7 @@ int mmc_accept(mmc_handle *h)
     if (h->trial_kind == 1) {
         // the write-back itself is deferred: the next move launch carries it in its parameters
         const MoveArgs &A = h->last;
+        h->state_version++;
         h->pend_kind = 1; h->pend_i = A.i; h->pend_ns = mol_of(h, A.i).y;
         std::memcpy(h->pend_com, A.com_new, sizeof(h->pend_com));
         std::memcpy(h->pend_site, A.site_new, sizeof(double) * 3 * h->pend_ns);
@@ -851,17 +877,15 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     if (k == "chain_cluster_atoms") { h->chain_cluster_atoms = (int)value; return MMC_OK; }
     if (k == "chain_cluster") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
-    if (k == "v6_ctas_per_sm") { if (value < 1 || value > 5) FAIL(MMC_EINVAL, "v6_ctas_per_sm must be 1..5"); h->v6_ctas_per_sm = (int)value; return MMC_OK; }
-    if (k == "host_windows") { if (value < 1 || value > 4) FAIL(MMC_EINVAL, "host_windows must be 1..4"); h->host_windows = (int)value; return MMC_OK; }
+    if (k == "v7_ctas_per_sm") { if (value < 1 || value > 4) FAIL(MMC_EINVAL, "v7_ctas_per_sm must be 1..4"); h->v7_ctas_per_sm = (int)value; return MMC_OK; }
     if (k == "host_chunks") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "host_chunks must be 1..8"); h->host_chunks = (int)value; return MMC_OK; }
-    if (k == "v6_dynamic") { h->v6_dynamic = value != 0; return MMC_OK; }
     if (k == "rhok_split") {
         if (value < 1 || value > 64) FAIL(MMC_EINVAL, "rhok_split must be 1..64");
         h->rhok_split = (int)value;
         return MMC_OK;
     }
-    if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v6, 1 v5, 2 fast, 3 general)
-        if (value < 0 || value > 3) FAIL(MMC_EINVAL, "pair_level must be 0..3");
+    if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v7, 1 fast, 2 general)
+        if (value < 0 || value > 2) FAIL(MMC_EINVAL, "pair_level must be 0..2");
         h->pair_floor = (int)value; h->pair_level = (int)value;
         return MMC_OK;
     }

@@ -1,10 +1,10 @@
 // mmc_eval.cu — C ABI of libmmc_b200.so, part 2: the full-system energy (potential(), Ewald/energy.jl:946-1032 and
 // :864-943), its sharded forms, the host-array form and the volume move (Ewald/volumeChange.jl:50-147) on top of the
-// pair kernels (kernels_pairs*.cuh), the rho(k) rebuild (kernels_recip.cuh) and the peer exchange (kernels_peer.cuh).
+// pair kernels (kernels_pairs_v7.cuh; kernels_pairs.cuh for general topologies), the rho(k) rebuild (kernels_recip.cuh)
+// and the peer exchange (kernels_peer.cuh).
 #include "mmc_handle.h"
 #include "kernels_pairs.cuh"
-#include "kernels_pairs_v5.cuh"
-#include "kernels_pairs_v6.cuh"
+#include "kernels_pairs_v7.cuh"
 #include "kernels_recip.cuh"
 #include "kernels_upload.cuh"
 
@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <immintrin.h>
 
 using namespace mmc_detail;
 
@@ -26,10 +27,9 @@ struct EvalCtx {
     cudaEvent_t wait_sites = nullptr;   // mmc_potential_host: the sites arrive on the side stream; wait for them before the gather
     bool rhok_external = false;         //                     ... and the ρ(k) partials are produced there, chunk by chunk
     double *per_mol = nullptr;          // mmc_energy_all: [n_mol x 3] per-molecule rows (general kernel, evaluation order)
-    const cudaEvent_t *chunk_ev = nullptr;   // mmc_potential_host: event of every site chunk, in upload order (the last one == wait_sites)
-    int n_chunks = 0;
+    int rhok_blocks = 0;                // rhok_external: CTAs whose partials sit in d_rhok_partial ...
+    cudaEvent_t rhok_done = nullptr;    //                ... once this event has fired
 };
-
 
 }  // namespace
 
@@ -37,7 +37,7 @@ namespace mmc_detail {
 
 // out == nullptr: partials only, written from block `block0` on (the caller reduces all blocks later); *nb_out = blocks used
 int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, double box, double2 *out, cudaStream_t st,
-                int block0, int *nb_out, int cap_blocks)
+                int block0, int *nb_out, int cap_blocks, const double4 *com, double f)
 {
     if (!st) st = h->stream;
     const int n = s_end - s_begin;
@@ -57,9 +57,10 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
         h->rhok_grid_cap = need;
     }
     double2 *part = h->d_rhok_partial + (size_t)block0 * nkv;
+    const int US = h->US > 0 ? h->US : 1;
     if (h->tm.on) cudaEventRecord(h->tm.ev[2], st);
     if (v2) {
-        Rhok2Args R{site, s_begin, s_end, per, nkv, h->n_kpairs, h->d_kpairs, h->d_kindex, box, part};
+        Rhok2Args R{site, s_begin, s_end, per, nkv, h->n_kpairs, h->d_kpairs, h->d_kindex, box, part, com, f, US};
         switch (h->S.nk) {
             case 1: k_rhok_pairs<1><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
             case 2: k_rhok_pairs<2><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
@@ -69,7 +70,7 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
             default: k_rhok_pairs<6><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
         }
     } else {
-        RhokArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->S.kvec, box, part};
+        RhokArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->S.kvec, box, part, com, f, US};
         const int kpt = (nkv + RHOK_BLOCK - 1) / RHOK_BLOCK;
         if (kpt <= 1) k_rhok_partial<1><<<nb, RHOK_BLOCK, 0, st>>>(R);
         else if (kpt <= 2) k_rhok_partial<2><<<nb, RHOK_BLOCK, 0, st>>>(R);
@@ -93,6 +94,7 @@ namespace {
 // k_pairs_fast instantiations: water (3 sites) x tile {64, 128} x padded polynomial degree
 #define MMC_FOR_DEGS(X) X(0) X(8) X(12) X(16) X(20) X(24) X(32) X(44)
 #define MMC_FOR_POS_DEGS(X) X(8) X(12) X(16) X(20) X(24) X(32) X(44)
+#define MMC_FOR_DIRECT_DEGS(X) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
 void launch_pairs_fast(int tile, int deg, int grid, size_t smem, cudaStream_t st, const PairArgs &P)
 {
 #define X(D)                                                                                   \
@@ -104,29 +106,16 @@ void launch_pairs_fast(int tile, int deg, int grid, size_t smem, cudaStream_t st
     MMC_FOR_DEGS(X)
 #undef X
 }
-#define MMC_FOR_DIRECT_DEGS(X) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
-void launch_pairs_v5(int deg, bool direct, int grid, cudaStream_t st, const PairArgs &P, const int4 *slots)
+void launch_pairs_v7(int deg, bool direct, int grid, cudaStream_t st, const V7Args &A)
 {
     if (direct) {
-#define X(D) if (deg == D) { k_pairs_v5<D, true><<<grid, V5_BLOCK, V5_SMEM, st>>>(P, slots); return; }
+#define X(D) if (deg == D) { k_pairs_v7<D, true><<<grid, V7_BLOCK, V7_SMEM, st>>>(A); return; }
         MMC_FOR_DIRECT_DEGS(X)
 #undef X
     } else {
-#define X(D) if (deg == D) { k_pairs_v5<D, false><<<grid, V5_BLOCK, V5_SMEM, st>>>(P, slots); return; }
+#define X(D) if (deg == D) { k_pairs_v7<D, false><<<grid, V7_BLOCK, V7_SMEM, st>>>(A); return; }
         MMC_FOR_POS_DEGS(X)
 #undef X
-    }
-}
-void launch_pairs_v6(int deg, bool direct, int grid, cudaStream_t st, const PairArgs &P, const int4 *slots, const V6Extra &X)
-{
-    if (direct) {
-#define X_(D) if (deg == D) { k_pairs_v6<D, true><<<grid, V6_BLOCK, V6_SMEM, st>>>(P, slots, X); return; }
-        MMC_FOR_DIRECT_DEGS(X_)
-#undef X_
-    } else {
-#define X_(D) if (deg == D) { k_pairs_v6<D, false><<<grid, V6_BLOCK, V6_SMEM, st>>>(P, slots, X); return; }
-        MMC_FOR_POS_DEGS(X_)
-#undef X_
     }
 }
 }  // namespace
@@ -137,16 +126,10 @@ void mmc_detail::eval_set_attributes()
     cudaFuncSetAttribute(k_pairs<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_pairs<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_pairs<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-#define X(D) cudaFuncSetAttribute(k_pairs_v6<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6_SMEM);
+#define X(D) cudaFuncSetAttribute(k_pairs_v7<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V7_SMEM);
     MMC_FOR_DIRECT_DEGS(X)
 #undef X
-#define X(D) cudaFuncSetAttribute(k_pairs_v6<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6_SMEM);
-    MMC_FOR_POS_DEGS(X)
-#undef X
-#define X(D) cudaFuncSetAttribute(k_pairs_v5<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V5_SMEM);
-    MMC_FOR_DIRECT_DEGS(X)
-#undef X
-#define X(D) cudaFuncSetAttribute(k_pairs_v5<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V5_SMEM);
+#define X(D) cudaFuncSetAttribute(k_pairs_v7<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V7_SMEM);
     MMC_FOR_POS_DEGS(X)
 #undef X
 #define X(D)                                                                                                   \
@@ -168,51 +151,210 @@ void bind_flags(mmc_handle *h, int ncell)
     h->d_fill = h->d_flags + 8 + ncell;
 }
 
-// A pair kernel declined the state.  The water kernels (levels 0-1: v6, v5) share their preconditions (cell
-// population <= 64, site reach inside the reference's +100 window), so a decline by one of them goes straight to
-// k_pairs_fast (level 2); after that the general kernel (level 3).
+// A pair kernel declined the state (level 0 k_pairs_v7: a cell with more than 64 molecules, a molecule reaching outside
+// the reference's +100 window, or an overlap — whose whole-row rule the general path implements; level 1 k_pairs_fast: a
+// cell that does not fit its tile): next level.
 bool escalate_pair_level(mmc_handle *h)
 {
-    h->pair_level = h->pair_level < 2 ? 2 : h->pair_level + 1;
-    return h->pair_level <= 3;
+    h->pair_level += 1;
+    return h->pair_level <= 2;
 }
 
+int grid_cells(const mmc_handle *h, int style, double box)
+{
+    const bool want_qq = (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF);
+    const double rcmax = std::max(h->S.rc_lj, want_qq ? h->S.rc_qq : 0.0);
+    int ncd = (int)std::floor(box / rcmax);
+    return ncd > 128 ? 128 : ncd;
+}
+
+// ---------------------------------------------------------------------------------------------------- k_pairs_v7 path
+// Serves: cell mode (box >= 3 r_cut), uniform 3-site molecules with identical per-site charges, LJ on site pair (0,0) only,
+// equal cut-offs, Coulomb on (EWALD / WOLF), a usable erf polynomial.
+bool v7_eligible(mmc_handle *h, int style, const EvalCtx &E, ErfPoly &ep)
+{
+    const DevSystem &S = h->S;
+    const bool want_qq = (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF);
+    if (h->pair_level != 0 || E.per_mol || !h->uniform || h->US != 3 || !h->uniform_q || !want_qq) return false;
+    if (S.rc_lj != S.rc_qq || h->lj.size() != 1 || h->lj[0].a != 0 || h->lj[0].b != 0) return false;
+    if (grid_cells(h, style, E.box) < 3) return false;
+    get_erf_poly(h, E.kappa, S.rc_qq * S.rc_qq + 100, ep);
+    return ep.deg > 0;
+}
+
+// this rank's home layers of the cell grid: contiguous z-slabs (every rank bins, gathers and reads only its slab + the
+// layer above it)
+void v7_slab(int ncd, int rank, int world, int &z0, int &z1)
+{
+    z0 = (int)((long long)ncd * rank / world);
+    z1 = (int)((long long)ncd * (rank + 1) / world);
+}
+
+int v7_alloc(mmc_handle *h, const V7Grid &G, long long units)
+{
+    if (!h->d7_flags) {
+        CK(cudaMalloc(&h->d7_flags, 8 * sizeof(int)));
+        CK(cudaMalloc(&h->d7_block_sums, TAIL_BLOCKS * sizeof(double4)));
+    }
+    if (G.ncd != h->d7_ncd) {
+        dfree(h->d7_count); dfree(h->d7_bucket); dfree(h->d7_ecount); dfree(h->d7_rows); dfree(h->d7_gf);
+        const size_t ncell = (size_t)G.ncd * G.ncd * G.ncd, next = (size_t)v7_ext_cells(G);
+        CK(cudaMalloc(&h->d7_count, ncell * sizeof(int)));
+        CK(cudaMalloc(&h->d7_bucket, ncell * V7_CAP * sizeof(int)));
+        CK(cudaMalloc(&h->d7_ecount, next * sizeof(int)));
+        CK(cudaMalloc(&h->d7_rows, next * V7_CAP * V7_ROW * sizeof(double)));
+        CK(cudaMalloc(&h->d7_gf, next * V7_CAP * sizeof(float4)));
+        h->d7_ncd = G.ncd;
+        h->bin_version = 0;
+    }
+    const size_t need = (size_t)std::max(1LL, units) * 2 * V7_CONSUMERS;
+    if (need > h->d7_partial_cap) {
+        dfree(h->d7_unit_partial);
+        CK(cudaMalloc(&h->d7_unit_partial, need * sizeof(double4)));
+        h->d7_partial_cap = need;
+    }
+    return MMC_OK;
+}
+
+// Enqueues one evaluation on the v7 path and leaves this rank's partial-sum vector in d_vec.  finish: one rank — E_recip,
+// resident ρ(k) and the scalars in the mapped host slot come out of the same tail kernel.
+int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, double *d_vec, bool finish, double2 *dst0, double2 *dst1)
+{
+    const DevSystem &S = h->S;
+    const bool ewald = style == MMC_STYLE_EWALD;
+    V7Grid G{};
+    G.ncd = grid_cells(h, style, E.box); G.EX = G.ncd + 2; G.EY = G.ncd + 2;
+    v7_slab(G.ncd, E.rank, E.world, G.z0, G.z1);
+    G.edge = E.box / G.ncd; G.box_new = E.box;
+    const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * (G.z1 - G.z0);
+    int rc = v7_alloc(h, G, units);
+    if (rc) return rc;
+    if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
+    // ---- ρ(k) rebuild (RecipLong, ewalds.jl:538-604) of this rank's share of the sites: depends on nothing the pair path
+    // produces (a volume trial scales the resident sites inside the kernel), so it runs beside it on the side stream
+    const long long ns_all = S.n_sites;
+    const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
+    int rhok_blocks = E.rhok_blocks;
+    bool forked = false;
+    if (ewald && !E.rhok_external) {
+        const bool side = h->overlap_rhok && (long long)(rs1 - rs0) * S.nkvecs > 10000000LL;
+        cudaStream_t st = side ? h->side : h->stream;
+        if (side) {
+            CK(cudaEventRecord(h->ev_fork, h->stream));
+            CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        }
+        rc = rhok_launch(h, S.site, rs0, rs1, E.box, nullptr, st, 0, &rhok_blocks, 0, E.f == 1.0 ? nullptr : S.com, E.f);
+        if (rc) return rc;
+        if (side) { CK(cudaEventRecord(h->ev_join, h->side)); forked = true; }
+    }
+    // ---- binning (fractional COM coordinates do not change with the box: the buckets of an unchanged state are reused,
+    // e.g. by consecutive volume trials) and the gather into the extended grid
+    CK(cudaMemsetAsync(h->d7_flags, 0, 8 * sizeof(int), h->stream));
+    const int tb = 256;
+    if (h->bin_version != h->state_version || h->bin_ncd != G.ncd || h->bin_z0 != G.z0 || h->bin_z1 != G.z1) {
+        CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)G.ncd * G.ncd * G.ncd, h->stream));
+        Bin7Args B{S.com, S.n_mol, (double)G.ncd / S.box, G, h->d7_count, h->d7_bucket};
+        k_bin7<<<(S.n_mol + tb - 1) / tb, tb, 0, h->stream>>>(B); LAUNCH_CHECK();
+        h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_z0 = G.z0; h->bin_z1 = G.z1;
+    }
+    if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
+    unsigned int *fl = reinterpret_cast<unsigned int *>(h->d7_flags);
+    {
+        Gather7Args A{S.com, S.site, h->d7_count, h->d7_bucket, G, E.f, h->d7_rows, h->d7_gf, h->d7_ecount,
+                      reinterpret_cast<unsigned long long *>(h->d7_flags), fl + 3, h->d7_flags + 4};
+        const int warps = G.EX * G.EY * (G.z1 - G.z0 + 1);
+        k_gather7<<<(warps + 7) / 8, 256, 0, h->stream>>>(A); LAUNCH_CHECK();
+    }
+    if (h->tm.on) { cudaEventRecord(h->tm.ev[5], h->stream); cudaEventRecord(h->tm.ev[0], h->stream); }
+    // ---- pairs
+    if (units > 0) {
+        V7Args A{};
+        A.G = G; A.units = (int)units;
+        A.rows = h->d7_rows; A.gf = h->d7_gf; A.ecount = h->d7_ecount;
+        const double rcut = S.rc_qq, edge = G.edge;
+        // conservative FP32 gate in the dot form |b|² − 2a·b < r_c² − |a|² on coordinates relative to the home cell
+        // (|a| components < edge, |b| < 2·edge): seven roundings of numbers <= 12·edge² and the input roundings
+        // (2·sqrt(3)·r_c·δ, δ <= 3·edge·2^-23), times four
+        const double margin = 4.0 * (8.0 * 12.0 * edge * edge + 8.0 * rcut * edge) / 16777216.0;
+        A.gate_rc2f = std::nextafterf((float)(rcut * rcut + margin), INFINITY);
+        A.rc_qq2 = rcut * rcut;
+        std::memcpy(&A.rcqq_bits, &A.rc_qq2, 8);
+        A.qq_negmask = 0;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                A.qq_tab[a * 3 + b] = h->q_site[a] * h->q_site[b];
+                if (A.qq_tab[a * 3 + b] < 0.0) A.qq_negmask |= 1u << (a * 3 + b);
+            }
+        A.lj_eps = h->lj[0].eps; A.lj_sig2 = h->lj[0].sig * h->lj[0].sig;
+        // −κ folded into the coefficients; DIRECT: also κ^2k, so the kernel runs Horner in r² itself
+        const bool direct = ep.ddeg > 0;
+        const int deg = direct ? ep.ddeg : ep.deg;
+        double k2k = 1.0;
+        for (int k = 0; k <= deg; ++k) {
+            A.pc[k] = direct ? -E.kappa * ep.a[k] * k2k : -E.kappa * ep.c[k];
+            k2k *= E.kappa * E.kappa;
+        }
+        A.pk2s = ep.kappa2 * ep.scale;
+        A.max_dev = reinterpret_cast<const double *>(h->d7_flags);
+        A.n_ovl = fl + 2; A.err_flag = fl + 3; A.ticket = fl + 5;
+        A.unit_partial = h->d7_unit_partial;
+        const int grid = (int)std::max(1LL, std::min<long long>((long long)h->v7_ctas_per_sm * h->sm_count, units));
+        launch_pairs_v7(deg, direct, grid, h->stream, A);
+        LAUNCH_CHECK();
+    }
+    if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
+    if (forked) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (E.rhok_external && E.rhok_done) CK(cudaStreamWaitEvent(h->stream, E.rhok_done, 0));
+    // ---- everything else in one launch
+    TailArgs T{};
+    T.unit_partial = h->d7_unit_partial; T.n_partial = units * 2 * V7_CONSUMERS;
+    T.rhok_partial = h->d_rhok_partial; T.rhok_blocks = rhok_blocks; T.nkvecs = ewald ? S.nkvecs : 0;
+    T.block_sums = h->d7_block_sums; T.done = fl + 6;
+    T.n_ovl = fl + 2; T.err_flag = fl + 3; T.max_count = h->d7_flags + 4;
+    T.vec = d_vec;
+    T.finish = finish ? 1 : 0; T.cfac = E.d_cfac; T.dst0 = dst0; T.dst1 = dst1;
+    T.host_out = h->d7_res; T.seq = ++h->res_seq;
+    k_eval_tail<<<TAIL_BLOCKS, TAIL_THREADS, 0, h->stream>>>(T); LAUNCH_CHECK();
+    if (h->tm.on) cudaEventRecord(h->tm.ev[6], h->stream);
+    h->last_fast = 7; h->last_mode = 0; h->last_ncd = G.ncd;
+    return MMC_OK;
+}
+
+// wait for the tail kernel of evaluation `res_seq` to publish its scalars in the mapped host slot
+int v7_wait(mmc_handle *h, double *hv)
+{
+    if (h->cfg.sync_mode == 1) CK(cudaStreamSynchronize(h->stream));
+    volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(h->h7_res + MMC_NSCAL);
+    unsigned spins = 0;
+    while (*flag != h->res_seq) {
+        _mm_pause();
+        if ((++spins & 0xfffu) == 0) {
+            cudaError_t q = cudaStreamQuery(h->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) { h->err = std::string("evaluation: ") + cudaGetErrorString(q); return MMC_ECUDA; }
+            if (q == cudaSuccess && *flag != h->res_seq) FAIL(MMC_ECUDA, "evaluation finished without publishing its result");
+        }
+    }
+    for (int i = 0; i < MMC_NSCAL; ++i) hv[i] = h->h7_res[i];
+    return MMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- general path
 // Leaves this rank's partial sums in d_vec: [0] Σlj_pot [1] Σlj_vir [2] Σcoul [3] #overlap
-// [MMC_NSCAL ..) ρ(k) partial (re,im).
+// [MMC_NSCAL ..) ρ(k) partial (re,im).  Cell lists + k_pairs_fast (3 sites) / k_pairs (any uniform topology), tile pairs
+// for boxes below 3 r_cut.
 int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
 {
-    const bool force_general = h->pair_level >= 3 || E.per_mol != nullptr;
+    const bool force_general = h->pair_level >= 2 || E.per_mol != nullptr;
     if (!h->uniform) FAIL(MMC_EINVAL, "pair kernel needs a uniform topology (internal)");
     const DevSystem &S = h->S;
     const int US = h->US;
     const bool want_qq = (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF);
-    const double rcmax = std::max(S.rc_lj, want_qq ? S.rc_qq : 0.0);
-    int ncd = (int)std::floor(E.box / rcmax);
-    if (ncd > 128) ncd = 128;
+    const int ncd = grid_cells(h, style, E.box);
     const bool cells = ncd >= 3;
     CK(cudaMemsetAsync(d_vec, 0, (MMC_NSCAL + 2 * (size_t)std::max(S.nkvecs, 1)) * sizeof(double), h->stream));
     if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
-    // The ρ(k) rebuild (RecipLong) depends on nothing the pair path produces when the box is unchanged (f == 1): it
-    // reads the resident sites in their own order and runs on the side stream while binning, gather and the pair
-    // kernel run here.  For a volume trial it needs the scaled sites and forks after the gather instead.
     const long long ns_all = S.n_sites;
     const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
-    bool rhok_forked = false;
-    // (small systems: the rebuild is a few µs of work, the fork/join events would cost more than they hide)
-    const bool rhok_side = h->overlap_rhok && !E.rhok_external && (long long)(rs1 - rs0) * S.nkvecs > 10000000LL;
-    auto fork_rhok_resident = [&]() -> int {
-        CK(cudaEventRecord(h->ev_fork, h->stream));
-        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        int rcr = rhok_launch(h, S.site, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL), h->side);
-        if (rcr) return rcr;
-        CK(cudaEventRecord(h->ev_join, h->side));
-        rhok_forked = true;
-        return MMC_OK;
-    };
-    if (style == MMC_STYLE_EWALD && rhok_side && h->overlap_rhok == 1 && E.f == 1.0) {
-        int rcr = fork_rhok_resident();
-        if (rcr) return rcr;
-    }
     const int tb = 256, gm = (S.n_mol + tb - 1) / tb;
     long long n_units;
     int zl_lo = 0, zl_cnt = 1 << 30;
@@ -227,11 +369,11 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         }
         bind_flags(h, ncell);
         CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * (8 + 2 * (size_t)ncell), h->stream));
-        // fractional COM coordinates are invariant under the volume scaling: bin the resident state
-        // a rank of a sharded evaluation reads the home cells of its unit range and their half-shell neighbours: z-layers
-        // [z(first home cell), z(last home cell) + 1]; only those are ordered and gathered (units are (cell, group) triples)
-        // Units are (cell, group) or (cell, slot) tuples, U per cell, dealt in contiguous ranges: for every U the first home
-        // cell of rank r is floor(ncell·r/world) and the last one is at most ceil(ncell·(r+1)/world) − 1.
+        // fractional COM coordinates are invariant under the volume scaling: bin the resident state.
+        // A rank of a sharded evaluation reads the home cells of its unit range and their half-shell neighbours: z-layers
+        // [z(first home cell), z(last home cell) + 1]; only those are ordered and gathered.  Units are (cell, slot) tuples,
+        // 14 per cell, dealt in contiguous ranges: the first home cell of rank r is floor(ncell·r/world) and the last one is
+        // at most ceil(ncell·(r+1)/world) − 1.
         zl_lo = 0; zl_cnt = ncd;
         if (E.world > 1 && E.f == 1.0) {
             const int c0 = (int)((long long)ncell * E.rank / E.world);
@@ -247,10 +389,6 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         k_cell_scan<<<1, 1024, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
         k_cell_fill<<<gm, tb, 0, h->stream>>>(C); LAUNCH_CHECK();
         k_cell_sort<<<(ncell * 32 + tb - 1) / tb, tb, 0, h->stream>>>(C, ncell); LAUNCH_CHECK();
-        if (style == MMC_STYLE_EWALD && rhok_side && h->overlap_rhok == 3 && E.f == 1.0) {   // fork after the (tiny, launch-bound) binning kernels
-            int rcr = fork_rhok_resident();
-            if (rcr) return rcr;
-        }
         n_units = 14LL * ncell;
         if (h->max_cell_cached < 0) {   // unknown density: one synchronous read-back, cached afterwards
             int mc = 0;
@@ -265,53 +403,12 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         const long long nt = (S.n_mol + PAIR_TILE - 1) / PAIR_TILE;
         n_units = nt * (nt + 1) / 2;
     }
-    // k_pairs_v6 reads the state as 96-byte rows + float gate coordinates (written by the same gather)
-    const bool want_rows = cells && US == 3 && h->pair_level == 0 && h->uniform_q && want_qq;
-    if (want_rows && !h->d_mrows) {
-        CK(cudaMalloc(&h->d_mrows, sizeof(double) * 12 * (size_t)S.n_mol));
-        CK(cudaMalloc(&h->d_gf, sizeof(float4) * (size_t)S.n_mol));
-    }
     GatherArgs G{S.com, S.site, cells ? h->d_perm : nullptr, S.n_mol, US, E.f, h->d_scom, h->d_ssite,
-                 reinterpret_cast<unsigned long long *>(h->d_maxdev), h->d_ovl,
-                 want_rows ? h->d_mrows : nullptr, want_rows ? h->d_gf : nullptr, h->d_cell_of, ncd, E.box / ncd,
+                 reinterpret_cast<unsigned long long *>(h->d_maxdev), h->d_ovl, nullptr, nullptr, h->d_cell_of, ncd, E.box / ncd,
                  zl_lo, std::min(zl_cnt, ncd)};
-    // Sites still arriving from the host (mmc_potential_host): the home cells are cut into z-layer windows; a window's gather and its
-    // share of the pair kernel start as soon as the chunk that completes its layers (+ one layer above, the half shell) has landed,
-    // while later chunks are still on the bus.  Which chunk that is comes from the cell of every molecule (known: the COMs are in).
-    int nwin = 1, win_need[4] = {0, 0, 0, 0};
-    auto win_z = [&](int w) { return (int)((long long)ncd * w / nwin); };
-    auto gather_window = [&](int w) -> int {          // layers not gathered by an earlier window: [zlo + (w > 0), zhi], zhi wraps to 0 for the last
-        const int lo = win_z(w) + (w > 0 ? 1 : 0), hi = std::min(win_z(w + 1), ncd - 1);
-        if (hi < lo) return MMC_OK;
-        GatherArgs Gw = G; Gw.zl_lo = lo; Gw.zl_cnt = hi - lo + 1;
-        k_gather<<<gm, tb, 0, h->stream>>>(Gw); LAUNCH_CHECK();
-        return MMC_OK;
-    };
-    if (E.chunk_ev && E.n_chunks > 1 && cells && want_rows && E.world == 1 && E.f == 1.0 && h->v6_dynamic && h->host_windows > 1 &&
-        ncd >= 4 * h->host_windows) {
-        nwin = std::min(4, h->host_windows);
-        if (!h->d_winneed) CK(cudaMalloc(&h->d_winneed, 4 * sizeof(int)));
-        CK(cudaMemsetAsync(h->d_winneed, 0, 4 * sizeof(int), h->stream));
-        k_window_need<<<gm, tb, 0, h->stream>>>(h->d_cell_of, S.n_mol, US, ncd, nwin, S.n_sites, E.n_chunks, h->d_winneed); LAUNCH_CHECK();
-        CK(cudaMemcpyAsync(win_need, h->d_winneed, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));          // ~0.15 ms into the call; the site chunks are in flight on the copy stream meanwhile
-        for (int w = 0; w < nwin; ++w) win_need[w] = std::max(0, std::min(win_need[w], E.n_chunks - 1));
-        for (int w = 1; w < nwin; ++w) win_need[w] = std::max(win_need[w], win_need[w - 1]);
-        CK(cudaStreamWaitEvent(h->stream, E.chunk_ev[win_need[0]], 0));
-        { int rcw = gather_window(0); if (rcw) return rcw; }
-    } else {
-        if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
-        k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
-    }
+    if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
+    k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
-    if (style == MMC_STYLE_EWALD && rhok_side && !rhok_forked) {      // volume trial: scaled, sorted sites
-        CK(cudaEventRecord(h->ev_fork, h->stream));
-        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        int rcr = rhok_launch(h, h->d_ssite, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL), h->side);
-        if (rcr) return rcr;
-        CK(cudaEventRecord(h->ev_join, h->side));
-        rhok_forked = true;
-    }
 
     PairArgs P{};
     P.com = h->d_scom; P.site = h->d_ssite; P.cell_start = h->d_start;
@@ -320,8 +417,6 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     P.L = E.box; P.rc_lj2 = S.rc_lj * S.rc_lj; P.rc_qq2 = S.rc_qq * S.rc_qq; P.kappa = E.kappa;
     P.want_lj = 1; P.want_qq = want_qq ? 1 : 0;
     P.nlj = (int)h->lj.size(); P.lj = h->d_lj;
-    for (int k = 0; k < 16; ++k) { P.lj_eps_tab[k] = 0.0; P.lj_sig_tab[k] = 0.0; }
-    if (US <= 4) for (const LJActive &e : h->lj) { P.lj_eps_tab[e.a * US + e.b] = e.eps; P.lj_sig_tab[e.a * US + e.b] = e.sig; }
     P.partial = h->d_pair_partial; P.ovl = h->d_ovl; P.n_ovl = h->d_novl; P.max_dev = h->d_maxdev;
     P.err_flag = h->d_errflag;
     P.per_mol = E.per_mol;
@@ -332,99 +427,13 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     P.ep = ErfPoly{};
     if (want_qq) get_erf_poly(h, E.kappa, S.rc_qq * S.rc_qq + 100, P.ep);
     const int max_cell = cells ? h->max_cell_cached : PAIR_TILE;
-    // the water kernels serve: 3 sites, LJ only on site pair (0,0), equal cut-offs, Coulomb on, polynomial erf, identical
-    // per-site charges in every molecule (they become launch constants)
-    const bool water = cells && US == 3 && !force_general && h->pair_level <= 1 && max_cell <= V3_ACAP && want_qq &&
-                       S.rc_lj == S.rc_qq && P.ep.deg > 0 && h->lj.size() == 1 && h->lj[0].a == 0 && h->lj[0].b == 0 && h->uniform_q;
-    const bool v6 = water && h->pair_level == 0 && want_rows;
-    const bool v5 = water && !v6;
-    if (nwin > 1 && !v6) {       // another kernel serves this state: it wants the whole gathered copy
-        if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));
-        k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
-        nwin = 1;
-    }
-    const int tile = (US == 3 && !force_general && !v5 && !v6) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
-    if (v5 || v6) n_units = (long long)V3_GROUPS * ncd * ncd * ncd;
-    if (v5 || v6) {
-        P.qq_negmask = 0;
-        for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) {
-                P.qq_tab[a * 3 + b] = h->q_site[a] * h->q_site[b];
-                if (P.qq_tab[a * 3 + b] < 0.0) P.qq_negmask |= 1u << (a * 3 + b);
-            }
-        // conservative FP32 gate: |d²_f32 - d²| <= 2*sqrt(3)*rc*delta + 3*delta² + 3*2^-23*rc², delta = 6*2^-24*edge
-        // (roundings to float of cell-local coordinates < edge, of their sum with the slot offset <= 2*edge, one
-        // float subtraction of <= 3*edge: 7 half-ulps of edge at most); 4x safety
-        const double edge = E.box / ncd, rc = S.rc_qq, delta = 8.0 * edge / 16777216.0;
-        const double margin = 4.0 * (2.0 * 1.7320508075688772 * rc * delta + 3.0 * delta * delta + 3.6e-7 * rc * rc);
-        P.gate_rc2f = std::nextafterf((float)(rc * rc + margin), INFINITY);
-    }
-    bool v5_direct = false;
-    int v5_deg = 0;
-    if (v5 || v6) {   // −κ folded into the coefficients; DIRECT: also κ^2k, so the kernel runs Horner in r² itself
-        v5_direct = P.ep.ddeg > 0;
-        v5_deg = v5_direct ? P.ep.ddeg : P.ep.deg;
-        double k2k = 1.0;
-        for (int k = 0; k <= v5_deg; ++k) {
-            P.pc[k] = v5_direct ? -E.kappa * P.ep.a[k] * k2k : -E.kappa * P.ep.c[k];
-            k2k *= E.kappa * E.kappa;
-        }
-        P.pk2s = P.ep.kappa2 * P.ep.scale;
-    }
+    const int tile = (US == 3 && !force_general) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
     P.unit_begin = n_units * E.rank / E.world;
     P.unit_end = n_units * (E.rank + 1) / E.world;
     const long long my_units = P.unit_end - P.unit_begin;
     int grid;
-    long long v6_units = 0;      // > 0: k_pairs_v6 ran with tickets and left per-(unit, warp) sums
     if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-    if (v5 || v6) {
-        {
-            const long long nslots = 14LL * ncd * ncd * ncd;
-            if (nslots > h->slots_cap) {
-                dfree(h->d_slots);
-                CK(cudaMalloc(&h->d_slots, sizeof(int4) * nslots));
-                h->slots_cap = nslots;
-            }
-            k_slots_build<<<(unsigned)((nslots + 255) / 256), 256, 0, h->stream>>>(P, h->d_slots, ncd * ncd * ncd);
-            LAUNCH_CHECK();
-            if (h->tm.on) cudaEventRecord(h->tm.ev[0], h->stream);
-        }
-        if (v6) {
-            grid = (int)std::max(1LL, std::min<long long>(h->v6_ctas_per_sm * h->sm_count, my_units));
-            V6Extra X{h->d_mrows, h->d_gf, nullptr, nullptr};
-            if (h->v6_dynamic && E.world == 1) {   // measured on config E: -2.3 % on one GPU, but +5..25 µs on a rank's share of a 2..8-rank
-                                                    // evaluation (few units per CTA: the greedy order ends on expensive units), so ranks keep the static deal
-                const size_t need = (size_t)my_units * V6_WARPS;
-                if (need > h->unit_partial_cap) {
-                    dfree(h->d_unit_partial);
-                    CK(cudaMalloc(&h->d_unit_partial, sizeof(double4) * need));
-                    h->unit_partial_cap = need;
-                }
-                X.ticket = reinterpret_cast<unsigned int *>(h->d_flags + 5);      // cleared with the flags at the start of the evaluation
-                X.unit_partial = h->d_unit_partial;
-                v6_units = my_units;
-            }
-            if (nwin > 1) {          // one launch per z-layer window, each as soon as its sites are in
-                const long long per_layer = (long long)V3_GROUPS * ncd * ncd;
-                for (int w = 0; w < nwin; ++w) {
-                    if (w > 0) {
-                        CK(cudaStreamWaitEvent(h->stream, E.chunk_ev[win_need[w]], 0));
-                        int rcw = gather_window(w); if (rcw) return rcw;
-                        CK(cudaMemsetAsync(X.ticket, 0, sizeof(unsigned int), h->stream));
-                    }
-                    PairArgs Pw = P;
-                    Pw.unit_begin = per_layer * win_z(w); Pw.unit_end = per_layer * win_z(w + 1);
-                    V6Extra Xw = X; Xw.unit_partial = X.unit_partial + (size_t)Pw.unit_begin * V6_WARPS;
-                    const int gw = (int)std::max(1LL, std::min<long long>(h->v6_ctas_per_sm * h->sm_count, Pw.unit_end - Pw.unit_begin));
-                    launch_pairs_v6(v5_deg, v5_direct, gw, h->stream, Pw, h->d_slots, Xw);
-                }
-            } else
-            launch_pairs_v6(v5_deg, v5_direct, grid, h->stream, P, h->d_slots, X);
-        } else {
-            grid = (int)std::max(1LL, std::min<long long>(4 * h->sm_count, my_units));
-            launch_pairs_v5(v5_deg, v5_direct, grid, h->stream, P, h->d_slots);
-        }
-    } else if (tile) {
+    if (tile) {
         if (n_units > h->units_cap) {
             dfree(h->d_units);
             CK(cudaMalloc(&h->d_units, sizeof(int4) * n_units));
@@ -450,22 +459,15 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     }
     LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
-    if (v6_units > 0) {          // fold the unit sums in unit order: 64 contiguous shares, then the usual final fold
-        grid = (int)std::min<long long>(64, h->pair_grid);
-        k_unit_fold<<<grid, 256, 0, h->stream>>>(h->d_unit_partial, v6_units * V6_WARPS, h->d_pair_partial); LAUNCH_CHECK();
-    }
     k_pair_reduce<<<1, 256, 0, h->stream>>>(h->d_pair_partial, grid, h->d_novl, h->d_maxcount, h->d_errflag, d_vec);
     LAUNCH_CHECK();
-    h->last_fast = v6 ? 6 : (v5 ? 5 : tile);
+    h->last_fast = tile;
     h->last_mode = cells ? 0 : 1;
     h->last_ncd = ncd;
-
     if (style == MMC_STYLE_EWALD && !E.rhok_external) {
-        if (rhok_forked) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        else {   // same stream: resident sites when the box is unchanged (a sharded rank gathers only its layers), scaled copy otherwise
-            int rc = rhok_launch(h, E.f == 1.0 ? S.site : h->d_ssite, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL));
-            if (rc) return rc;
-        }
+        // resident sites when the box is unchanged (a sharded rank gathers only its layers), scaled copy otherwise
+        int rc = rhok_launch(h, E.f == 1.0 ? S.site : h->d_ssite, rs0, rs1, E.box, reinterpret_cast<double2 *>(d_vec + MMC_NSCAL));
+        if (rc) return rc;
     }
     return MMC_OK;
 }
@@ -486,46 +488,12 @@ int overlap_row(mmc_handle *h, const EvalCtx &E, int sorted_index, double *row)
     return MMC_OK;
 }
 
-// d_vec holds the (already rank-summed) partials; computes E_recip on the device, brings the
-// scalars to the host and assembles Properties in the reference's order (energy.jl:972-1021).
-int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 *dst0, double2 *dst1,
-             mmc_properties *out)
+// Properties in the reference's order (energy.jl:972-1021) from the eight scalars of a (rank-summed) partial vector:
+// hv[0] Σlj_pot, [1] Σlj_vir, [2] Σcoul (overlap rows already removed), [4] E_recip un-scaled, [3] #overlapped molecules
+void assemble(mmc_handle *h, int style, const EvalCtx &E, double lj_pot, double lj_vir, double coul, double recip_raw,
+              long long novl, mmc_properties *out)
 {
     const DevSystem &S = h->S;
-    if (style == MMC_STYLE_EWALD) {
-        k_rhok_energy<<<1, RHOKE_BLOCK, 0, h->stream>>>(reinterpret_cast<const double2 *>(d_vec + MMC_NSCAL),
-                                                       E.d_cfac, S.nkvecs, dst0, dst1, d_vec + 4);
-        LAUNCH_CHECK();
-    }
-    CK(cudaMemcpyAsync(h->h_vec, d_vec, MMC_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (h->tm.on) cudaEventRecord(h->tm.ev[6], h->stream);
-    CK(cudaStreamSynchronize(h->stream));
-    if (E.world == 1) {
-        if (h->last_mode == 0) h->max_cell_cached = (int)h->h_vec[6];
-        if (h->h_vec[7] != 0.0) return 1;      // a cell outgrew the fast kernel's tile: caller re-runs
-    } else if (h->h_vec[7] != 0.0) {           // summed over ranks: every rank takes the same branch
-        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
-        h->max_cell_cached = -1;
-        return 1;                               // MMC_RETRY: caller repeats partial + all-reduce + finalize
-    }
-    double lj_pot = h->h_vec[0], lj_vir = h->h_vec[1], coul = h->h_vec[2];
-    const long long novl = (long long)h->h_vec[3];
-    const double recip_raw = h->h_vec[4];
-    if (novl > 0 && (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF)) {
-        // reference semantics: a molecule whose EwaldReal row hits the overlap rule contributes
-        // 0 for its whole row (ewalds.jl:359-360 inside energy.jl:991-1001): U - ½ Σ_flagged row_i
-        if (E.world > 1) FAIL(MMC_ESTATE, "overlap in a sharded evaluation: re-run unsharded (mmc_potential)");
-        std::vector<unsigned> fl(S.n_mol);
-        CK(cudaMemcpy(fl.data(), h->d_ovl, sizeof(unsigned) * S.n_mol, cudaMemcpyDeviceToHost));
-        for (int p = 0; p < S.n_mol; ++p)
-            if (fl[p]) {
-                double row;
-                int rc = overlap_row(h, E, p, &row);
-                if (rc) return rc;
-                coul -= row / 2;
-            }
-        h->cnt.overlap_events += novl;
-    }
     std::memset(out, 0, sizeof(*out));
     const double factor = S.factor;
     out->lj = lj_pot * 4;                       // Σ_i(4 pot_i)/2 over unique pairs
@@ -533,7 +501,6 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
     out->energy = out->lj;
     out->virial = vir_lj;
     out->overlaps = novl;
-    h->last_pairs = (long long)h->h_vec[5];
     if (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF) {
         const double totReal = coul * factor;   // (Σ_i row_i) * factor / 2
         out->real = totReal;
@@ -562,14 +529,123 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
             out->coulomb += out->wolf_const;
         }
     }
-    if (h->tm.on) {
-        cudaEventElapsedTime(&h->tm.ms[0], h->tm.ev[0], h->tm.ev[1]);
-        if (style == MMC_STYLE_EWALD) cudaEventElapsedTime(&h->tm.ms[1], h->tm.ev[2], h->tm.ev[3]);
-        cudaEventElapsedTime(&h->tm.ms[2], h->tm.ev[4], h->tm.ev[5]);
-        cudaEventElapsedTime(&h->tm.ms[3], h->tm.ev[4], h->tm.ev[6]);
-    }
+}
+
+void read_timings(mmc_handle *h, int style)
+{
+    if (!h->tm.on) return;
+    cudaEventElapsedTime(&h->tm.ms[0], h->tm.ev[0], h->tm.ev[1]);
+    if (style == MMC_STYLE_EWALD) cudaEventElapsedTime(&h->tm.ms[1], h->tm.ev[2], h->tm.ev[3]);
+    cudaEventElapsedTime(&h->tm.ms[2], h->tm.ev[4], h->tm.ev[5]);
+    cudaEventElapsedTime(&h->tm.ms[3], h->tm.ev[4], h->tm.ev[6]);
+}
+
+// v7, one rank: the tail kernel has done the device part; 1 = the kernel declined the state (caller escalates)
+int finish_v7(mmc_handle *h, int style, const EvalCtx &E, mmc_properties *out)
+{
+    double hv[MMC_NSCAL];
+    int rc = v7_wait(h, hv);
+    if (rc) return rc;
+    if (h->tm.on) { CK(cudaStreamSynchronize(h->stream)); if (style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side)); }
+    if (hv[7] != 0.0 || hv[3] != 0.0) return 1;
+    h->last_pairs = (long long)hv[5];
+    assemble(h, style, E, hv[0], hv[1], hv[2], hv[4], 0, out);
+    read_timings(h, style);
     h->cnt.full_energy_evals++;
     return MMC_OK;
+}
+
+int evaluate_unsharded(mmc_handle *h, int style, EvalCtx E, double2 *dst0, double2 *dst1, mmc_properties *out);
+
+// d_vec holds the (already rank-summed) partials; computes E_recip on the device, brings the
+// scalars to the host and assembles Properties in the reference's order (energy.jl:972-1021).
+// Returns 1 when the pair kernel that produced the partials declined the state (one rank: the caller escalates).
+int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 *dst0, double2 *dst1,
+             mmc_properties *out)
+{
+    const DevSystem &S = h->S;
+    if (style == MMC_STYLE_EWALD) {
+        k_rhok_energy<<<1, RHOKE_BLOCK, 0, h->stream>>>(reinterpret_cast<const double2 *>(d_vec + MMC_NSCAL),
+                                                       E.d_cfac, S.nkvecs, dst0, dst1, d_vec + 4);
+        LAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(h->h_vec, d_vec, MMC_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->tm.on && h->last_fast != 7) cudaEventRecord(h->tm.ev[6], h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->tm.on && style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side));
+    const bool coulomb = style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF;
+    const long long novl = (long long)h->h_vec[3];
+    if (E.world == 1) {
+        if (h->last_mode == 0 && h->last_fast != 7) h->max_cell_cached = (int)h->h_vec[6];
+        if (h->h_vec[7] != 0.0) return 1;      // a cell outgrew the kernel's tile: caller re-runs
+        if (h->last_fast == 7 && novl > 0) return 1;
+    } else if (h->h_vec[7] != 0.0 || (novl > 0 && coulomb)) {
+        // Summed over ranks, so every rank takes this branch together: a rank's pair kernel declined the state, or
+        // molecules overlap (ewalds.jl:359-360 zeroes whole rows, which needs a molecule's complete neighbourhood).  The
+        // state is replicated, so every rank evaluates the whole system on the general path and gets the same Properties:
+        // slow, rare, and no retry protocol leaks to the caller.
+        if (h->h_vec[7] != 0.0 || h->last_fast == 7) { if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)"); }
+        h->max_cell_cached = -1;
+        EvalCtx E1 = E;
+        E1.rank = 0; E1.world = 1; E1.wait_sites = nullptr; E1.rhok_external = false; E1.rhok_done = nullptr;
+        return evaluate_unsharded(h, style, E1, dst0, dst1, out);
+    }
+    double lj_pot = h->h_vec[0], lj_vir = h->h_vec[1], coul = h->h_vec[2];
+    const double recip_raw = h->h_vec[4];
+    if (novl > 0 && coulomb) {
+        // reference semantics: a molecule whose EwaldReal row hits the overlap rule contributes
+        // 0 for its whole row (ewalds.jl:359-360 inside energy.jl:991-1001): U - ½ Σ_flagged row_i
+        std::vector<unsigned> fl(S.n_mol);
+        CK(cudaMemcpy(fl.data(), h->d_ovl, sizeof(unsigned) * S.n_mol, cudaMemcpyDeviceToHost));
+        for (int p = 0; p < S.n_mol; ++p)
+            if (fl[p]) {
+                double row;
+                int rc = overlap_row(h, E, p, &row);
+                if (rc) return rc;
+                coul -= row / 2;
+            }
+        h->cnt.overlap_events += novl;
+    }
+    h->last_pairs = (long long)h->h_vec[5];
+    assemble(h, style, E, lj_pot, lj_vir, coul, recip_raw, novl, out);
+    read_timings(h, style);
+    h->cnt.full_energy_evals++;
+    return MMC_OK;
+}
+
+// One complete evaluation on this GPU alone: k_pairs_v7 when it serves the system, the general path otherwise; a kernel
+// that declines the state hands over to the next level.
+int evaluate_unsharded(mmc_handle *h, int style, EvalCtx E, double2 *dst0, double2 *dst1, mmc_properties *out)
+{
+    for (;;) {
+        ErfPoly ep{};
+        int rc;
+        if (v7_eligible(h, style, E, ep)) {
+            if ((rc = eval_v7(h, style, E, ep, h->d_vec, true, dst0, dst1))) return rc;
+            rc = finish_v7(h, style, E, out);
+        } else {
+            if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+            if (E.rhok_external && style == MMC_STYLE_EWALD) {       // mmc_potential_host: the chunks' ρ(k) partials, folded in CTA order
+                if (E.rhok_done) CK(cudaStreamWaitEvent(h->stream, E.rhok_done, 0));
+                k_rhok_reduce<<<(h->S.nkvecs + 31) / 32, dim3(32, 32), 0, h->stream>>>(h->d_rhok_partial, E.rhok_blocks, h->S.nkvecs,
+                                                                                      reinterpret_cast<double2 *>(h->d_vec + MMC_NSCAL));
+                LAUNCH_CHECK();
+            }
+            rc = finalize(h, style, E, h->d_vec, dst0, dst1, out);
+        }
+        if (rc != 1) return rc;
+        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        h->max_cell_cached = -1;
+        E.wait_sites = nullptr;                                       // the state is on the device by now
+    }
+}
+
+// this rank's share of a sharded evaluation, vector left in d_vec
+int evaluate_partial(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
+{
+    ErfPoly ep{};
+    if (v7_eligible(h, style, E, ep)) return eval_v7(h, style, E, ep, d_vec, false, nullptr, nullptr);
+    return eval_partials(h, style, E, d_vec);
 }
 
 // non-uniform topologies: literal Σ_i rows / 2 through the single-molecule kernel
@@ -659,7 +735,7 @@ int mmc_potential_partial(mmc_handle *h, int32_t style, double *d_partials)
     if (!h->uniform) FAIL(MMC_EINVAL, "sharded evaluation needs a uniform topology");
     if ((rc = ensure_vec(h))) return rc;
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
-    return eval_partials(h, style, E, d_partials);
+    return evaluate_partial(h, style, E, d_partials);
 }
 
 int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partials, mmc_properties *out)
@@ -765,7 +841,7 @@ int mmc_potential_sharded_begin(mmc_handle *h, int32_t style)
     { int rcf = flush_pending(h); if (rcf) return rcf; }
     if ((rc = ensure_vec(h))) return rc;
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
-    if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+    if ((rc = evaluate_partial(h, style, E, h->d_vec))) return rc;
     h->peer_epoch += 1;
     const PeerArgs P = peer_args(h);
     k_peer_push<<<h->cfg.world, 256, 0, h->stream>>>(P, h->d_vec);
@@ -774,7 +850,7 @@ int mmc_potential_sharded_begin(mmc_handle *h, int32_t style)
     return MMC_OK;
 }
 
-// wait for every rank's push, add the slots in rank order, finalise.  MMC_RETRY as mmc_potential_finalize.
+// wait for every rank's push, add the slots in rank order, finalise
 int mmc_potential_sharded_end(mmc_handle *h, mmc_properties *out)
 {
     if (!h || !out) return MMC_EINVAL;
@@ -792,16 +868,12 @@ int mmc_potential_sharded_end(mmc_handle *h, mmc_properties *out)
     return rc;
 }
 
-// all ranks call this together: begin + end, repeated while the pair kernel chain escalates (MMC_RETRY)
+// all ranks call this together: begin + end
 int mmc_potential_sharded(mmc_handle *h, int32_t style, mmc_properties *out)
 {
-    for (int attempt = 0; attempt < 8; ++attempt) {
-        int rc = mmc_potential_sharded_begin(h, style);
-        if (rc) return rc;
-        rc = mmc_potential_sharded_end(h, out);
-        if (rc != MMC_RETRY) return rc;
-    }
-    FAIL(MMC_ECUDA, "sharded potential did not converge on a pair kernel (internal)");
+    int rc = mmc_potential_sharded_begin(h, style);
+    if (rc) return rc;
+    return mmc_potential_sharded_end(h, out);
 }
 
 int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
@@ -825,13 +897,7 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
     if (!h->uniform) return potential_rows(h, style, out);
     if ((rc = ensure_vec(h))) return rc;
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, 0, 1};
-    if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
-    rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
-    while (rc == 1) {    // the chosen pair kernel declined this state (dense cell / wrapped molecules): next level
-        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
-        if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
-        rc = finalize(h, style, E, h->d_vec, h->S.rhok[0], h->S.rhok[1], out);
-    }
+    rc = evaluate_unsharded(h, style, E, h->S.rhok[0], h->S.rhok[1], out);
     if (style == MMC_STYLE_EWALD) h->new_valid = false;
     return rc;
 }
@@ -883,7 +949,7 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     if (!coords || !com || !out || style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "bad arguments");
     DevSystem &S = h->S;
     const int nchunk = h->host_chunks;
-    if (!h->uniform || h->cfg.world != 1 || S.n_sites < 64 * nchunk) {          // small or general systems: the plain sequence
+    if (!h->uniform || h->cfg.world != 1 || S.n_sites < 64 * nchunk || S.n_sites < 100000) {          // small or general systems: the plain sequence
         if ((rc = mmc_upload_positions(h, coords, com))) return rc;
         return mmc_potential(h, style, out);
     }
@@ -916,8 +982,7 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     }
     for (int c = 0; c < nchunk; ++c) {
         const int s0 = (int)((long long)S.n_sites * c / nchunk), s1 = (int)((long long)S.n_sites * (c + 1) / nchunk);
-        // the copy stream carries nothing but copies: a repack kernel in it would hold the next copy back whenever the SMs are
-        // taken by a window of the pair kernel (persistent CTAs).  Repack + ρ(k) partials of the chunk follow on the side stream.
+        // the copy stream carries nothing but copies; repack + ρ(k) partials of the chunk follow on the side stream
         CK(cudaMemcpyAsync(d_coords + 3 * (size_t)s0, coords + 3 * (size_t)s0, sizeof(double) * 3 * (size_t)(s1 - s0), cudaMemcpyHostToDevice, h->copy));
         CK(cudaEventRecord(h->ev_copy[c], h->copy));
         CK(cudaStreamWaitEvent(h->side, h->ev_copy[c], 0));
@@ -930,26 +995,13 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
         }
     }
     CK(cudaEventRecord(h->ev_join, h->side));
+    h->state_version++;                                         // new positions: the cell buckets are rebuilt
     EvalCtx E{1.0, S.box, S.kappa, S.cfac, 0, 1};
-    E.wait_sites = h->ev_sites; E.rhok_external = true;
-    cudaEvent_t chunk_events[8];
-    for (int c = 0; c < nchunk; ++c) chunk_events[c] = (c == nchunk - 1) ? h->ev_sites : h->ev_chunk[c];
-    E.chunk_ev = chunk_events; E.n_chunks = nchunk;
-    for (;;) {
-        if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
-        CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        if (ewald) {
-            k_rhok_reduce<<<(S.nkvecs + 31) / 32, dim3(32, 32), 0, h->stream>>>(h->d_rhok_partial, blocks, S.nkvecs,
-                                                                               reinterpret_cast<double2 *>(h->d_vec + MMC_NSCAL));
-            LAUNCH_CHECK();
-        }
-        CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        rc = finalize(h, style, E, h->d_vec, S.rhok[0], S.rhok[1], out);
-        if (rc != 1) break;
-        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
-        E.wait_sites = nullptr; E.chunk_ev = nullptr;            // the state is on the device now
-    }
+    E.wait_sites = h->ev_sites; E.rhok_external = true; E.rhok_blocks = blocks; E.rhok_done = h->ev_join;
+    CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    rc = evaluate_unsharded(h, style, E, S.rhok[0], S.rhok[1], out);
     if (rc < 0) return rc;
+    CK(cudaStreamSynchronize(h->stream));
     if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
     return rc;
 }
@@ -973,14 +1025,7 @@ int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t st
     }
     const double f = box_new / h->S.box;                                 // volumeChange.jl:62
     EvalCtx E{f, box_new, coul ? kappa_new : h->S.kappa, h->d_cfac_trial, 0, 1};
-    if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
-    rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
-    while (rc == 1) {
-        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
-        if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
-        rc = finalize(h, style, E, h->d_vec, h->d_rhok_trial, nullptr, out);
-    }
-    if (rc) return rc;
+    if ((rc = evaluate_unsharded(h, style, E, h->d_rhok_trial, nullptr, out))) return rc;
     h->vol_pending = true; h->vol_box = box_new; h->vol_kappa = E.kappa; h->vol_f = f; h->vol_style = style;
     return MMC_OK;
 }
@@ -993,6 +1038,7 @@ int mmc_volume_accept(mmc_handle *h)
     k_apply_scale<<<(h->S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->S, h->vol_f);
     LAUNCH_CHECK();
     h->S.box = h->vol_box;
+    h->state_version++;
     if (h->vol_style == MMC_STYLE_EWALD || h->vol_style == MMC_STYLE_WOLF) h->S.kappa = h->vol_kappa;
     if (h->vol_style == MMC_STYLE_EWALD) {
         std::swap(h->S.cfac, h->d_cfac_trial);

@@ -22,10 +22,8 @@ struct mmc_handle {
     bool own_stream = false;
     cudaStream_t side = nullptr;         // the ρ(k) rebuild of a full evaluation runs here, beside binning + pair kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sites = nullptr;
-    cudaStream_t copy = nullptr;         // mmc_potential_host: host->device chunks + repack; ρ(k) partials follow on `side`
+    cudaStream_t copy = nullptr;         // mmc_potential_host: host->device chunks; repack + ρ(k) partials follow on `side`
     cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int host_windows = 3;                // ... and z-layer windows the pair evaluation is cut into while they arrive (1: wait for all sites)
-    int *d_winneed = nullptr;
     cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int host_chunks = 6;                 // mmc_potential_host: pieces the site array is uploaded in (mmc_debug_set "host_chunks", 1..8)
     int overlap_rhok = 1;                // mmc_debug_set "overlap_rhok": 0 = everything on one stream
@@ -103,9 +101,7 @@ struct mmc_handle {
     int *d_cell_of = nullptr, *d_count = nullptr, *d_start = nullptr, *d_fill = nullptr, *d_perm = nullptr;
     int ncell_cap = 0;
     double4 *d_scom = nullptr, *d_ssite = nullptr;
-    double *d_mrows = nullptr;   // k_pairs_v6: cell-sorted state as rows of 12 doubles
     double *d_permol = nullptr, *d_permol_out = nullptr;   // mmc_energy_all: per-molecule rows (evaluation order) and the scaled output arrays
-    float4 *d_gf = nullptr;      //             and cell-local float COMs
     double4 *d_pair_partial = nullptr;
     int pair_grid = 0;
     unsigned int *d_ovl = nullptr, *d_novl = nullptr;
@@ -120,15 +116,24 @@ struct mmc_handle {
     int *d_maxcount = nullptr;
     int *d_flags = nullptr;      // [maxdev(2) | novl | errflag | maxcount | 3 spare | count(ncell) | fill(ncell)]
     int4 *d_units = nullptr;
-    int4 *d_slots = nullptr;
-    long long slots_cap = 0;
     int use_rhok_v2 = 1;
-    int v6_ctas_per_sm = 5;
-    int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v6, 1 k_pairs_v5, 2 k_pairs_fast, 3 general k_pairs
+    int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v7, 1 k_pairs_fast, 2 general k_pairs
                                  // (raised when a kernel declines the state)
-    int v6_dynamic = 1;          // k_pairs_v6 draws units by ticket (0: static round-robin deal)
-    double4 *d_unit_partial = nullptr;
-    size_t unit_partial_cap = 0;
+    // ---- k_pairs_v7 path (kernels_pairs_v7.cuh): ghost-extended cell grid in a fixed-capacity layout
+    int *d7_flags = nullptr;     // [8]: max |site-COM| (2 ints) | #overlap | err | max cell population | unit ticket | tail ticket | spare
+    int *d7_count = nullptr, *d7_bucket = nullptr, *d7_ecount = nullptr;
+    double *d7_rows = nullptr;
+    float4 *d7_gf = nullptr;
+    double4 *d7_unit_partial = nullptr, *d7_block_sums = nullptr;
+    int d7_ncd = 0;
+    size_t d7_partial_cap = 0;
+    double *h7_res = nullptr, *d7_res = nullptr;     // mapped pinned result slot [MMC_NSCAL + 1]: scalars + sequence number
+    unsigned long long res_seq = 0;
+    unsigned long long state_version = 1;           // bumped whenever resident positions change
+    unsigned long long bin_version = 0;             // state the buckets were built from (0: none)
+    int bin_ncd = 0, bin_z0 = -1, bin_z1 = -1;
+    int v7_ctas_per_sm = 4;
+    int v7_rhok_blocks = 0;                         // CTAs of the last ρ(k) partial launch
     int rhok_split = 1;          // ρ(k) rebuild: CTAs per resident slot (short CTAs let higher-priority kernels in between)
     int pair_floor = 0;          // lowest level the chain may start from (mmc_debug_set "pair_level": A/B tests)
     bool uniform_q = false;      // every molecule carries the charges of molecule 1 (per site index)
@@ -204,5 +209,5 @@ void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P);
 // mmc_eval.cu
 void eval_set_attributes();
 int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, double box, double2 *out, cudaStream_t st = nullptr,
-                int block0 = 0, int *nb_out = nullptr, int cap_blocks = 0);
+                int block0 = 0, int *nb_out = nullptr, int cap_blocks = 0, const double4 *com = nullptr, double f = 1.0);
 }  // namespace mmc_detail

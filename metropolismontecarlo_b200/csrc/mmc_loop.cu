@@ -24,6 +24,9 @@ namespace {
 
 struct UStream {
     const double *u; int64_t n, pos; bool dry;
+    // past the end of the caller's stream: `dry` is raised and the move in progress is abandoned by the loops below —
+    // it is rejected without being recorded, its counters are taken back and uniforms_used returns to the start of the
+    // move, so that a caller who refills the stream resumes exactly there (the returned 0.5 is never acted upon)
     double next() { if (pos >= n) { dry = true; return 0.5; } return u[pos++]; }
 };
 
@@ -92,6 +95,7 @@ extern "C" int mmc_loop_run(mmc_handle *h, const mmc_loop_params *p, double *com
     for (int64_t m = 0; m < n_moves; ++m) {
         const int i = (int)(m % n_mol);                  // sweep order i = 1..N (main.jl:490)
         const int2 mi = mol_of(h, i);
+        const int64_t pos_m = us.pos;                    // resume point if the stream runs dry inside this move
         double rnew[3] = {com[3 * i], com[3 * i + 1], com[3 * i + 2]};
         double ei[4];
         const double chose_move = us.next();             // main.jl:516
@@ -127,6 +131,10 @@ extern "C" int mmc_loop_run(mmc_handle *h, const mmc_loop_params *p, double *com
             ei[2] = rq[2] * old[0] + rq[3] * old[1] + rq[0] * old[2] - rq[1] * old[3];
             ei[3] = rq[3] * old[0] - rq[2] * old[1] + rq[1] * old[2] + rq[0] * old[3];
         } else { ret = 3; break; }                       // main.jl:539-541
+        if (us.dry) {                                    // not enough uniforms to draw this move: it never happened
+            if (is_trans) tr.attempt -= 1; else ro.attempt -= 1;
+            us.pos = pos_m; ret = 1; break;
+        }
         if (std::fabs(ei[0] * ei[0] + ei[1] * ei[1] + ei[2] * ei[2] + ei[3] * ei[3] - 1.0) > 1.e-6) { ret = 2; break; }
         double a[3][3];
         quat_to_matrix(ei, a);
@@ -146,8 +154,13 @@ extern "C" int mmc_loop_run(mmc_handle *h, const mmc_loop_params *p, double *com
         const bool overlap = r.overlap_old || r.overlap_new;
         const double deltaRecip = r.d_recip;             // already 0 on overlap / non-Ewald
         const double delta = (partial_new_e) - (partial_old_e) + deltaRecip;   // main.jl:593
-        if (overlap) st->n_overlap += 1;
         const bool acc = metropolis(delta / p->temperature, us) && !overlap;   // main.jl:598
+        if (us.dry) {                                    // Metropolis found the stream empty: reject, record nothing, resume at pos_m
+            if ((rc = mmc_reject(h))) return rc;
+            if (is_trans) tr.attempt -= 1; else ro.attempt -= 1;
+            us.pos = pos_m; ret = 1; break;
+        }
+        if (overlap) st->n_overlap += 1;
         if (acc) {
             st->total_energy += delta;
             st->total_virial += (partial_new_v - partial_old_v) + deltaRecip / 3;
@@ -161,7 +174,6 @@ extern "C" int mmc_loop_run(mmc_handle *h, const mmc_loop_params *p, double *com
         }
         if (accepted) accepted[m] = acc ? 1 : 0;
         if (delta_out) delta_out[m] = delta;
-        if (us.dry) { ret = 1; break; }
         if (p->adjust && i == n_mol - 1) {               // main.jl:645-651
             tr.d_max = dr_max; adjust_step(tr, box); dr_max = tr.d_max;
             ro.d_max = dphi_max; adjust_step(ro, box); dphi_max = ro.d_max;
@@ -294,6 +306,7 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     for (int m = 0; m < S.n_mol; ++m) { com[3 * m] = hc[m].x; com[3 * m + 1] = hc[m].y; com[3 * m + 2] = hc[m].z; }
     h->cur = o.cur;
     h->new_valid = false;
+    h->state_version++;
     if (std::getenv("MMC_CHAIN_DEBUG") && o.n_moves > 0)
         std::fprintf(stderr, "k_chain cycles/move: step0 %.0f  gate %.0f  compact %.0f  pairs %.0f  B4wait %.0f  decide %.0f\n",
                      (double)o.phase_cycles[0] / o.n_moves, (double)o.phase_cycles[1] / o.n_moves, (double)o.phase_cycles[2] / o.n_moves,
@@ -322,8 +335,10 @@ extern "C" int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_m
     int ret = 0, rc;
     for (int64_t m = 0; m < n_moves; ++m) {              // Monatomic/mainMonatomic.jl:373-413
         const int i = (int)(m % n);
+        const int64_t pos_m = us.pos;
         double rnew[3];
         const double z0 = us.next(), z1 = us.next(), z2 = us.next();
+        if (us.dry) { us.pos = pos_m; ret = 1; break; }  // not enough uniforms for this move: it never happened
         rnew[0] = r[3 * i] + (z0 - 0.5) * dr_max;
         rnew[1] = r[3 * i + 1] + (z1 - 0.5) * dr_max;
         rnew[2] = r[3 * i + 2] + (z2 - 0.5) * dr_max;
@@ -332,6 +347,10 @@ extern "C" int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_m
         if ((rc = mmc_trial_atom(h, i + 1, rnew, &t))) return rc;
         const double delta = t.lj_new - t.lj_old;
         const bool acc = metropolis(delta / temperature, us);
+        if (us.dry) {
+            if ((rc = mmc_reject(h))) return rc;
+            us.pos = pos_m; ret = 1; break;
+        }
         if (acc) {
             st->total_energy += delta;
             st->total_virial += (t.lj_vir_new - t.lj_vir_old);
@@ -341,7 +360,6 @@ extern "C" int mmc_loop_run_atoms(mmc_handle *h, double temperature, double dr_m
         } else if ((rc = mmc_reject(h))) return rc;
         if (accepted) accepted[m] = acc ? 1 : 0;
         if (delta_out) delta_out[m] = delta;
-        if (us.dry) { ret = 1; break; }
         st->n_moves = m + 1;
         st->trans_attempt += 1; st->trans_accept += acc ? 1 : 0;
     }

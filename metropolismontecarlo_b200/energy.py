@@ -337,7 +337,7 @@ class Engine:
     def last_eval_info(self):
         n, m, c, k = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
         self._ck(self.lib.mmc_last_eval_info(self.h, C.byref(n), C.byref(m), C.byref(c), C.byref(k)))
-        kern = {7: "k_pairs_v7", 6: "k_pairs_v6", 5: "k_pairs_v5", 64: "k_pairs_fast<64>", 128: "k_pairs_fast<128>", 0: "k_pairs"}.get(k.value, str(k.value))
+        kern = {7: "k_pairs_v7", 64: "k_pairs_fast<64>", 128: "k_pairs_fast<128>", 0: "k_pairs"}.get(k.value, str(k.value))
         return {"pairs_in_cutoff": n.value, "mode": ("cells", "tiles", "rows")[m.value] if m.value >= 0 else None,
                 "cells_per_dim": c.value, "pair_kernel": kern}
 

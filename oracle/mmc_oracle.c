@@ -568,6 +568,7 @@ int ora_loop(ora_system *s, ora_ewald *ew, const double *db, double *quat,
         double rm_old[3];
         memcpy(rm_old, s->com + 3 * (i - 1), sizeof(rm_old));                      /* :514 */
         memcpy(ra_old, s->coords + 3 * (fa - 1), sizeof(double) * 3 * npm);        /* :515 */
+        const int64_t pos_m = us.pos;   /* resume point if the caller's stream ends inside this move */
         double chose_move = urand(&us);                                            /* :516 */
         double ei[4], ai[9];
         int is_trans;
@@ -613,6 +614,14 @@ int ora_loop(ora_system *s, ora_ewald *ew, const double *db, double *quat,
         } else {
             rc = 3; st->n_moves = m; goto done;                                    /* :539-541 */
         }
+        if (us.dry) {
+            /* The reference's RNG never ends; a finite recorded stream can.  A move whose draws ran past the end never
+             * happened: state, counters and stream position go back to the start of the move (same rule in the engine's
+             * drivers, csrc/mmc_loop.cu and kernels_chain.cuh), so a caller who refills the stream resumes exactly here. */
+            memcpy(s->com + 3 * (i - 1), rm_old, sizeof(rm_old));
+            if (is_trans) trans.attempt -= 1; else rot.attempt -= 1;
+            us.pos = pos_m; rc = 1; st->n_moves = m; goto done;
+        }
         {   /* q_to_a aborts on |q·q-1| > 1e-6 (quaternions.jl:20-25) */
             double nrm = ei[0] * ei[0] + ei[1] * ei[1] + ei[2] * ei[2] + ei[3] * ei[3];
             if (fabs(nrm - 1.0) > 1.e-6) { rc = 2; st->n_moves = m; goto done; }
@@ -637,8 +646,15 @@ int ora_loop(ora_system *s, ora_ewald *ew, const double *db, double *quat,
         if (!overlap && p->style == 0)                                             /* :580 */
             deltaRecip = ora_RecipMove(box, ew, npm, ra_old, ra_new, s->charge + (fa - 1));
         double delta = (partial_new_e) - (partial_old_e) + deltaRecip;             /* :593 */
-        if (overlap) st->n_overlap += 1;
         int acc = (metropolis(delta / p->temperature, &us) && overlap == 0);       /* :598 */
+        if (us.dry) {   /* Metropolis found the stream empty: the move never happened (see above) */
+            memcpy(s->com + 3 * (i - 1), rm_old, sizeof(rm_old));
+            memcpy(s->coords + 3 * (fa - 1), ra_old, sizeof(double) * 3 * npm);
+            if (p->style == 0) ora_recip_rollback(ew);
+            if (is_trans) trans.attempt -= 1; else rot.attempt -= 1;
+            us.pos = pos_m; rc = 1; st->n_moves = m; goto done;
+        }
+        if (overlap) st->n_overlap += 1;
         if (acc) {
             st->total_energy += delta;
             st->total_virial += (partial_new_v - partial_old_v) + deltaRecip / 3;
@@ -653,7 +669,6 @@ int ora_loop(ora_system *s, ora_ewald *ew, const double *db, double *quat,
         }
         if (accepted) accepted[m] = (uint8_t)acc;
         if (delta_out) delta_out[m] = delta;
-        if (us.dry) { rc = 1; st->n_moves = m; goto done; }
         if (p->adjust && i == s->n_mol) {                                          /* :645-651 */
             trans.d_max = dr_max; adjust(&trans, box); dr_max = trans.d_max;
             rot.d_max = dphi_max; adjust(&rot, box); dphi_max = rot.d_max;
@@ -685,7 +700,9 @@ int ora_loop_atoms(int64_t n, double *r, const double *eps, const double *sig, d
         double eo, vo, en, vn, rold[3], rnew[3];
         ora_LJ_dU_atom(i, n, r, eps, sig, box, r_cut, &eo, &vo);
         memcpy(rold, r + 3 * (i - 1), sizeof(rold));
+        const int64_t pos_m = us.pos;
         double z0 = urand(&us), z1 = urand(&us), z2 = urand(&us);
+        if (us.dry) { us.pos = pos_m; rc = 1; st->n_moves = m; break; }   /* the move never happened (see ora_loop) */
         rnew[0] = rold[0] + (z0 - 0.5) * dr_max;
         rnew[1] = rold[1] + (z1 - 0.5) * dr_max;
         rnew[2] = rold[2] + (z2 - 0.5) * dr_max;
@@ -694,6 +711,7 @@ int ora_loop_atoms(int64_t n, double *r, const double *eps, const double *sig, d
         ora_LJ_dU_atom(i, n, r, eps, sig, box, r_cut, &en, &vn);
         double delta = en - eo;
         int acc = metropolis(delta / temperature, &us);
+        if (us.dry) { memcpy(r + 3 * (i - 1), rold, sizeof(rold)); us.pos = pos_m; rc = 1; st->n_moves = m; break; }
         if (acc) {
             st->total_energy += delta;
             st->total_virial += (vn - vo);
@@ -703,7 +721,6 @@ int ora_loop_atoms(int64_t n, double *r, const double *eps, const double *sig, d
         }
         if (accepted) accepted[m] = (uint8_t)acc;
         if (delta_out) delta_out[m] = delta;
-        if (us.dry) { rc = 1; st->n_moves = m; break; }
         st->n_moves = m + 1;
         st->trans_attempt += 1; st->trans_accept += acc;
     }

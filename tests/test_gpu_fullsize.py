@@ -36,7 +36,7 @@ def test_full_size_rows_and_totals_against_oracle(cfg_e):
     assert ms.n_sites == 768000 and abs(ms.box - 197.757) < 1e-2
     p = eng.potential("ewald")
     info = eng.last_eval_info()
-    assert info["mode"] == "cells" and info["cells_per_dim"] == 19 and info["pair_kernel"] == "k_pairs_v6"
+    assert info["mode"] == "cells" and info["cells_per_dim"] == 19 and info["pair_kernel"] == "k_pairs_v7"
     lj, vir, qq, ov = eng.energy_all("ewald")
     assert not ov.any() and p.overlaps == 0
     assert rel(lj.sum() / 2, p.lj) < 1e-10 and rel(qq.sum() / 2, p.real) < 1e-10
@@ -64,10 +64,10 @@ def test_full_size_rows_and_totals_against_oracle(cfg_e):
 def test_full_size_pair_kernels_agree(cfg_e):
     ms, eng = cfg_e
     ref = None
-    for level in (0, 1, 2, 3):
+    for level in (0, 1, 2):
         eng.debug_set("pair_level", level)
         p = eng.potential("ewald")
-        assert eng.last_eval_info()["pair_kernel"] == ("k_pairs_v6", "k_pairs_v5", "k_pairs_fast<64>", "k_pairs")[level]
+        assert eng.last_eval_info()["pair_kernel"] == ("k_pairs_v7", "k_pairs_fast<64>", "k_pairs")[level]
         if ref is None:
             ref = p
             assert eng.last_eval_info()["pairs_in_cutoff"] > 17_000_000
@@ -124,26 +124,24 @@ def test_full_size_volume_identity_and_rhok_delta(cfg_e):
     eng.upload_system(ms, 10.0, 10.0)
 
 
-def test_full_size_potential_host_windows(cfg_e):
-    """mmc_potential_host at full size: the pair evaluation is cut into z-layer windows that start while later site chunks
-    are still on the bus.  Same Properties as upload + potential() for the lattice order (chunks = z-slabs: windows really
-    overlap the copies), for a random molecule order (every window needs the last chunk), with 1..4 windows and 1..8 chunks."""
+def test_full_size_potential_host(cfg_e):
+    """mmc_potential_host at full size: COMs first (binning), sites in chunks with the rho(k) partials of each chunk computed as
+    it lands, gather + pair kernel when the last chunk is in.  Same Properties as upload + potential() for the lattice order and
+    for a random molecule order, with 1..8 chunks."""
     from metropolismontecarlo_b200.energy import water_engine
     ms, eng = cfg_e
     ref = eng.potential("ewald")
     fields = ("energy", "virial", "coulomb", "lj", "real", "recip", "self_")
-    for windows, chunks in ((4, 4), (1, 4), (4, 8), (3, 5), (2, 2), (4, 1)):
-        eng.debug_set("host_windows", windows)
+    for chunks in (4, 8, 5, 2, 1):
         eng.debug_set("host_chunks", chunks)
         for style in ("ewald", "wolf"):
             got = eng.potential_host(ms.coords, ms.com, style)
             want = ref if style == "ewald" else eng.potential("wolf")
             for f in fields:
-                assert rel(getattr(got, f), getattr(want, f)) < 1e-12, (windows, chunks, style, f)
+                assert rel(getattr(got, f), getattr(want, f)) < 1e-12, (chunks, style, f)
             assert got.overlaps == 0
-    eng.debug_set("host_windows", 3)
     eng.debug_set("host_chunks", 6)
-    # a random molecule order: same energy (to summation order), every window waits for the last chunk
+    # a random molecule order: same energy (to summation order)
     perm = np.random.default_rng(3).permutation(N_E)
     mp = ms.copy()
     mp.com = ms.com[perm].copy()

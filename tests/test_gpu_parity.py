@@ -327,7 +327,7 @@ def test_pair_kernel_variants_agree_with_oracle():
     want_pairs = npr_pairs_in_cutoff(ms.com, ms.box, 10.0)
     eng = water_engine(ms, 10.0)
     want_wolf = ora.potential_wolf(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
-    for level, name in ((0, "k_pairs_v6"), (1, "k_pairs_v5"), (2, "k_pairs_fast<64>"), (3, "k_pairs")):
+    for level, name in ((0, "k_pairs_v7"), (1, "k_pairs_fast<64>"), (2, "k_pairs")):
         eng.debug_set("pair_level", level)
         got = eng.potential("ewald")
         assert eng.last_eval_info()["pair_kernel"] == name, (level, eng.last_eval_info())
@@ -490,8 +490,8 @@ def test_tip3p_1000_molecules_reference_run():
     eng.close()
 
 
-def test_pairs_v6_two_pass_groups():
-    """k_pairs_v6's two-pass path: 3200 SPC/E molecules on the 15³ lattice give 4 cells of 11.5 Å per edge holding
+def test_pairs_v7_two_pass_groups():
+    """k_pairs_v7's two-pass path: 3200 SPC/E molecules on the 15³ lattice give 4 cells of 11.5 Å per edge holding
     27 … 64 molecules (3 or 4 lattice planes per cell and direction), so 5-slot groups of up to 288 molecules exceed the
     256-row B tile and are evaluated in two passes.  Totals and pair count against the oracle."""
     from metropolismontecarlo_b200.energy import water_engine
@@ -499,7 +499,7 @@ def test_pairs_v6_two_pass_groups():
     eng = water_engine(ms, 10.0)
     got = eng.potential("ewald")
     info = eng.last_eval_info()
-    assert info["pair_kernel"] == "k_pairs_v6" and info["cells_per_dim"] == 4, info
+    assert info["pair_kernel"] == "k_pairs_v7" and info["cells_per_dim"] == 4, info
     s = ora_system(ms)
     want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
     _check_props(got, want)
@@ -509,13 +509,13 @@ def test_pairs_v6_two_pass_groups():
 
 def test_pair_kernel_declines_dense_cells_with_stale_density():
     """A cell above 64 molecules that the cached density does not know about (positions re-sent with
-    mmc_upload_positions): k_pairs_v6 must decline cleanly (regression: its boundary fix-up ran on a declined unit)
+    mmc_upload_positions): k_pairs_v7 must decline cleanly (regression: its boundary fix-up ran on a declined unit)
     and the chain must end on a kernel that gives the oracle's answer."""
     from metropolismontecarlo_b200.energy import water_engine
     ms = systems.spce_lattice(4000)                 # 4 cells per edge, full cells hold exactly 64 molecules
     eng = water_engine(ms, 10.0)
     eng.potential("ewald")
-    assert eng.last_eval_info()["pair_kernel"] == "k_pairs_v6"
+    assert eng.last_eval_info()["pair_kernel"] == "k_pairs_v7"
     rng = np.random.default_rng(2)
     newcom = np.clip(ms.com + rng.uniform(-1.5, 1.5, ms.com.shape), 0.0, ms.box)
     ms2 = ms.copy()
@@ -528,12 +528,12 @@ def test_pair_kernel_declines_dense_cells_with_stale_density():
         eng.potential("ewald")
         eng.upload_positions(ms2.coords, ms2.com)
         got = eng.potential("ewald")
-        assert eng.last_eval_info()["pair_kernel"] != "k_pairs_v6"
+        assert eng.last_eval_info()["pair_kernel"] != "k_pairs_v7"
         _check_props(got, want)
     eng.close()
 
 
-def test_pairs_v6_sparse_box_with_empty_cells():
+def test_pairs_v7_sparse_box_with_empty_cells():
     """Low density: 6 cells per edge with a handful of molecules each and some empty ones (zero-size tiles), molecules
     clustered in one corner so that whole neighbour cells are empty."""
     from metropolismontecarlo_b200.energy import water_engine
@@ -547,7 +547,7 @@ def test_pairs_v6_sparse_box_with_empty_cells():
     eng = water_engine(ms, 10.0)
     got = eng.potential("ewald")
     info = eng.last_eval_info()
-    assert info["pair_kernel"] == "k_pairs_v6" and info["cells_per_dim"] >= 5, info
+    assert info["pair_kernel"] == "k_pairs_v7" and info["cells_per_dim"] >= 5, info
     s = ora_system(ms)
     want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
     assert info["pairs_in_cutoff"] == npr_pairs_in_cutoff(ms.com, ms.box, 10.0)

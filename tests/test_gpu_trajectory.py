@@ -152,23 +152,55 @@ def test_device_loop_matches_oracle_and_host_driver(style, sid, cluster):
 
 
 def test_device_loop_short_stream_and_small_system():
-    """Return code 1 when the uniform stream runs dry, exactly where the host driver stops; 100-molecule box."""
+    """The uniform stream ends inside a move (every draw position of the last moves is tried): return code 1, the move in
+    progress never happened — nothing committed or recorded, counters taken back, uniforms_used = position at the start
+    of that move — identically in the oracle, the host driver and the device block (no fabricated draw is ever
+    acted upon).  Resuming there with the rest of the stream reproduces the one-shot record.  100-molecule box."""
     from metropolismontecarlo_b200.energy import water_engine
     ms = systems.load_nist(1)
-    u = np.random.default_rng(5).random(1500)
-    outs = []
+    u = np.random.default_rng(5).random(4000)
+    prm = LoopParams(298.15, 0.3, 0.05, 0.5, 1.0, 0, 0)
+    full = {}
     for device in (False, True):
         eng = water_engine(ms, 9.0)
         g0 = eng.potential("ewald")
         com, quat = ms.com.copy(), ms.quat.copy()
-        rc, acc, delta, st = eng.loop_run(LoopParams(298.15, 0.3, 0.05, 0.5, 1.0, 0, 1), com, quat, ms.db, u, 2000,
-                                          g0.energy, g0.virial, device=device)
-        outs.append((rc, acc.copy(), st.n_moves, st.uniforms_used, st.n_accepted, com.copy()))
+        rc, acc, delta, st = eng.loop_run(prm, com, quat, ms.db, u, 300, g0.energy, g0.virial, device=device)
+        assert rc == 0
+        full[device] = (acc.copy(), com.copy(), quat.copy(), st.n_accepted)
         eng.close()
-    assert outs[0][0] == 1 and outs[1][0] == 1
-    assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3] == 1500 and outs[0][4] == outs[1][4]
-    assert np.array_equal(outs[0][1], outs[1][1])
-    assert np.abs(outs[0][5] - outs[1][5]).max() < 1e-12
+    assert np.array_equal(full[False][0], full[True][0])
+    for n_short in (1500, 1501, 1502, 1503, 1504, 1505, 1506, 3):
+        outs = []
+        s = ora_system(ms)
+        ew = ora_ewald(ms.box)
+        p0 = ora.potential_ewald(s, ew, 9.0, 9.0, ms.box)
+        q_o = ms.quat.copy()
+        oprm = ora.LoopParams(298.15, 0.3, 0.05, 0.5, 1.0, 9.0, 9.0, ms.box, 0, 0)
+        rc_o, acc_o, _, st_o = ora.loop(s, ew, ms.db, q_o, oprm, u[:n_short], 2000, p0.energy, p0.virial)
+        for device in (False, True):
+            eng = water_engine(ms, 9.0)
+            g0 = eng.potential("ewald")
+            com, quat = ms.com.copy(), ms.quat.copy()
+            rc, acc, delta, st = eng.loop_run(prm, com, quat, ms.db, u[:n_short], 2000, g0.energy, g0.virial, device=device)
+            outs.append((rc, acc.copy(), st.n_moves, st.uniforms_used, st.n_accepted, com.copy(), st.trans_attempt + st.rot_attempt))
+            assert rc == 1 and rc_o == 1
+            assert st.n_moves == st_o.n_moves and st.uniforms_used == st_o.uniforms_used <= n_short
+            assert st.n_accepted == st_o.n_accepted and np.array_equal(acc[:st.n_moves], acc_o[:st.n_moves])
+            assert st.trans_attempt == st_o.trans_attempt and st.rot_attempt == st_o.rot_attempt
+            assert st.trans_attempt + st.rot_attempt == st.n_moves
+            assert np.abs(com - s.com).max() < 1e-12
+            # the resident state is the state after n_moves complete moves: a fresh evaluation equals the running total
+            assert rel(eng.potential("ewald").energy, st.total_energy) < 1e-10
+            n_a = st.n_moves
+            if n_a < 300 and n_a % ms.n_mol == 0 and n_a > 0:       # resume at a sweep boundary with the rest of the stream
+                rc2, acc2, _, st2 = eng.loop_run(prm, com, quat, ms.db, u[st.uniforms_used:], 300 - n_a, st.total_energy,
+                                                 st.total_virial, device=device)
+                assert rc2 == 0 and np.array_equal(np.concatenate([acc[:n_a], acc2]), full[device][0])
+            eng.close()
+        assert outs[0][2:5] == outs[1][2:5] and outs[0][6] == outs[1][6]
+        assert np.array_equal(outs[0][1], outs[1][1])
+        assert np.abs(outs[0][5] - outs[1][5]).max() < 1e-12
 
 
 def _resite(ms, keep):

@@ -228,6 +228,51 @@ def test_loop_invariant_sum_of_deltas_equals_recompute():
     assert np.allclose(ew.sum_old, ew2.sum_old, rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("n_short", [700, 701, 702, 703, 704, 705])
+def test_loop_short_stream_resumes_exactly(n_short):
+    """A finite uniform stream that ends inside a move: the move never happened (state, counters, records untouched),
+    uniforms_used is the position at the start of that move, and resuming there with the rest of the stream gives the
+    record of a one-shot run.  (The reference's RNG is endless; this is the rule for recorded streams — ADVICE r1.)"""
+    ms = systems.load_nist(1)
+    prm = ora.LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 9.0, 9.0, ms.box, 0, 0)
+    u = np.random.default_rng(7).random(3000)
+
+    def fresh():
+        s, ew = ora_system(ms), ora_ewald(ms.box)
+        ora.RecipLong(ew, s.coords, s.charge, ms.box)
+        return s, ew, ms.quat.copy()
+    s1, ew1, q1 = fresh()
+    rc, acc1, del1, st1 = ora.loop(s1, ew1, ms.db, q1, prm, u, 400, 0.0, 0.0)
+    assert rc == 0 and st1.n_moves == 400
+    s2, ew2, q2 = fresh()
+    rc, acc2, del2, st2 = ora.loop(s2, ew2, ms.db, q2, prm, u[:n_short], 400, 0.0, 0.0)
+    assert rc == 1 and 0 < st2.n_moves < 400 and st2.uniforms_used <= n_short
+    n_a, used = st2.n_moves, st2.uniforms_used
+    assert st2.trans_attempt + st2.rot_attempt == n_a          # the abandoned move is not counted
+    # resume: molecules continue in sweep order, so the second block starts at molecule n_a % N; rotate the system view
+    rc, acc3, del3, st3 = _resume(ora, s2, ew2, ms, q2, prm, u[used:], 400 - n_a, n_a)
+    assert rc == 0
+    assert np.array_equal(np.concatenate([acc2[:n_a], acc3]), acc1)
+    # (the rotated molecule order changes the summation order of the j loop: deltas agree to rounding)
+    assert np.abs(np.concatenate([del2[:n_a], del3]) - del1).max() < 1e-9
+    assert np.array_equal(s2.coords, s1.coords) and np.array_equal(q2, q1)
+    assert st2.n_accepted + st3.n_accepted == st1.n_accepted
+
+
+def _resume(ora, s, ew, ms, quat, prm, u, n_moves, first):
+    """Continue a block of moves at move index `first` (sweep order i = first % N + 1): the oracle's Loop always starts at
+    molecule 1, so the molecules are rotated by `first` for the call and rotated back afterwards."""
+    n = ms.n_mol
+    k = first % n
+    roll = lambda a, per: np.roll(a.reshape(n, per, -1), -k, axis=0).reshape(a.shape).copy()
+    s.coords[:] = roll(s.coords, 3); s.com[:] = roll(s.com, 1); quat[:] = roll(quat, 1)
+    db = roll(ms.db, 3)
+    out = ora.loop(s, ew, db, quat, prm, u, n_moves, 0.0, 0.0)
+    unroll = lambda a, per: np.roll(a.reshape(n, per, -1), k, axis=0).reshape(a.shape).copy()
+    s.coords[:] = unroll(s.coords, 3); s.com[:] = unroll(s.com, 1); quat[:] = unroll(quat, 1)
+    return out
+
+
 # ---- the reference's random stream (Julia MersenneTwister = dSFMT-19937) -------------------
 
 def test_julia_rng_known_answers():
