@@ -95,8 +95,14 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites,
 int mmc_upload_positions(mmc_handle *h, const double *coords, const double *com);
 /* mmc_upload_positions + mmc_potential in one call with the host->device copies overlapped with the work that does
  * not need them yet (COMs first: cell binning; sites in chunks on a side stream, each fed to the rho(k) rebuild as it
- * lands; gather + pair kernel when the last chunk is in).  Host arrays in, Properties out. */
+ * lands; gather + pair kernel when the last chunk is in).  Host arrays in, Properties out.
+ * On a sharded handle (world > 1, peer exchange set up; all ranks call it together with the same arrays) the evaluation is
+ * domain-decomposed: a rank copies all COMs but only the blocks of the site array that hold molecules of its own slab of
+ * the cell grid (+ one layer, + its share of the sites for rho(k)); afterwards ONLY those are current on that GPU, and
+ * every entry point that needs the whole state returns MMC_ESTATE until mmc_upload_positions / mmc_upload_system.
+ * mmc_last_host_bytes: bytes the last mmc_potential_host copied host -> device on this rank. */
 int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, int32_t style, mmc_properties *out);
+int mmc_last_host_bytes(mmc_handle *h, int64_t *h2d_bytes);
 
 /* Monatomic/mainMonatomic.jl:140-146 Requirements(r, eps, sig, box, r_cut) */
 int mmc_upload_atoms(mmc_handle *h, int64_t n, const double *r, const double *eps_j,
@@ -106,6 +112,9 @@ int mmc_download_system(mmc_handle *h, double *coords, double *com);
 int mmc_download_atoms(mmc_handle *h, double *r);
 
 /* ---- k-space setup: Ewald/ewalds.jl:45-103 PrepareEwaldVariables ------------------------ */
+/* The tables belong to (kappa, box).  They survive mmc_upload_system / mmc_upload_positions; when a re-upload changes the
+ * box, cfac is rebuilt for the new box with the resident kappa and the resident rho(k) is cleared (the reference rebuilds
+ * both in PrepareEwaldVariables per box) — call mmc_ewald_prepare again for a new kappa (= alpha / box, main.jl:290). */
 int mmc_ewald_prepare(mmc_handle *h, double kappa, int32_t nk, int32_t k_sq_max,
                       double factor, int32_t *nkvecs);
 int mmc_get_kvectors(mmc_handle *h, int32_t *kxyz /* nkvecs x 3 */, double *cfac);
@@ -158,10 +167,9 @@ int mmc_partial_count(mmc_handle *h, int64_t *n_doubles);
 int mmc_potential_partial(mmc_handle *h, int32_t style, double *d_partials);
 int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partials,
                            mmc_properties *out);
-/* mmc_potential_finalize may return MMC_RETRY (1): the pair kernel chosen for the partial pass
- * declined the state (e.g. a cell denser than its tile); the library has already switched to the
- * next kernel on every rank — repeat mmc_potential_partial, the all-reduce and finalize. */
-#define MMC_RETRY 1
+/* (If a rank's pair kernel declined the state, or molecules overlap — ewalds.jl:359-360 zeroes whole rows, which needs a
+ * molecule's complete neighbourhood — every rank sees it in the summed vector and evaluates the whole (replicated) system
+ * itself on the general path: same Properties everywhere, slower, no retry protocol for the caller.) */
 
 /* ---- the same exchange over NVLink peer memory instead of a library all-reduce ------------ */
 /* Every rank owns an exchange buffer that its peers map through CUDA IPC (one process per GPU on one node).
@@ -275,11 +283,11 @@ int mmc_set_timing(mmc_handle *h, int32_t enabled);
 int mmc_last_timings(mmc_handle *h, float *ms4);
 /* what the last full-energy evaluation did: molecule pairs inside the cutoff (summed over ranks
  * after finalize), path taken (0 = cell list, 1 = tile pairs, 2 = per-molecule rows), cells per
- * box edge, and the pair kernel used (6 = k_pairs_v6, 5 = k_pairs_v5, 64/128 = k_pairs_fast tile, 0 = k_pairs) */
+ * box edge, and the pair kernel used (7 = k_pairs_v7, 64/128 = k_pairs_fast tile, 0 = k_pairs) */
 int mmc_last_eval_info(mmc_handle *h, int64_t *pairs_in_cutoff, int32_t *mode, int32_t *cells_per_dim,
                        int32_t *pair_kernel);
 /* test/profiling knobs. key "pair_level": first full-energy pair kernel the fallback chain may use
- * (0 = k_pairs_v6, 1 = k_pairs_v5, 2 = k_pairs_fast, 3 = general k_pairs); results are identical
+ * (0 = k_pairs_v7, 1 = k_pairs_fast, 2 = general k_pairs); results are identical
  * within rounding, only speed differs. */
 int mmc_debug_set(mmc_handle *h, const char *key, int64_t value);
 /* FP64 DFMA-chain microbenchmark: measured FP64 FMA throughput of the device [TFLOP/s] */

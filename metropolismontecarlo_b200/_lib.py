@@ -110,6 +110,7 @@ SIGNATURES = {
     "mmc_upload_positions": (C.c_int, [H, c_double_p, c_double_p]),
     "mmc_energy_all": (C.c_int, [H, C.c_int32, c_double_p, c_double_p, c_double_p, c_int32_p]),
     "mmc_potential_host": (C.c_int, [H, c_double_p, c_double_p, C.c_int32, C.POINTER(Properties)]),
+    "mmc_last_host_bytes": (C.c_int, [H, c_int64_p]),
     "mmc_loop_run": (C.c_int, [H, C.POINTER(LoopParams), c_double_p, c_double_p, c_double_p, c_double_p,
                                C.c_int64, C.c_int64, C.c_double, C.c_double, c_uint8_p, c_double_p,
                                C.POINTER(LoopStats)]),

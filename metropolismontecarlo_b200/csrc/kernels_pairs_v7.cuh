@@ -15,7 +15,8 @@
 //             pair kernel therefore has no periodic-wrap logic, no slot descriptors to build (a neighbour is `cell + const`)
 //             and nothing to fix up after a tile has landed.
 //   gate    = a lane OWNS B molecules (one per 32-wide chunk of the B tile, coordinates in registers) and walks the
-//             warp's A rows, which arrive by shared-memory broadcast as {−2a, r_c² − |a|²}:
+//             warp's A rows, which arrive by shared-memory broadcast as {−2a, r_c² − |a|²} (coordinates relative to the box centre,
+//             |·|² precomputed by the gather):
 //                 |a − b|² < r_c²   ⇔   |b|² − 2a·b < r_c² − |a|²          3 FFMA + 1 FSETP + 1 predicated LOP per test
 //             into a per-lane 16-bit row mask — no ballot, no popc, no store per test: 6 instructions per 32 tests
 //             instead of 26.  (FP32, conservative: the threshold carries the worst-case rounding error; the exact FP64
@@ -63,6 +64,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// (Measured: the poll loop is not what limits the kernel.  __nanosleep between polls and try_wait's suspend-time hint both
+// return after ~20 ns on this part and leave the kernel time unchanged; a polling warp yields its issue slot.)
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
     unsigned ok;
@@ -76,9 +79,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 #define V7_BLOCK (32 * (V7_CONSUMERS + 1))
 #define V7_CAP 64          // molecules per cell (fixed-capacity layout); a denser cell makes the path decline
 #define V7_BCAP 256        // rows of the B tile; a group with more neighbours is split into two sub-units
-#define V7_ROW 12
+#define V7_ROW 14          // doubles per stored molecule: 12 of payload {3 sites xyz, COM xyz} + 2 of padding.  The 112-byte stride is an
+                           // ODD number of 16-byte words, so the LDS.128 of eight consecutive rows hit eight different bank groups;
+                           // the 96-byte stride of v6 folds every fourth row onto the same banks (ncu: 63 % of the shared-memory
+                           // wavefronts of the first v7 build were conflict replays, the LSU pipe 80 % busy)
 #define V7_QCAP 1024       // queue entries per consumer warp
-#define V7_MAXCH (V7_BCAP / 32)
 
 constexpr size_t V7_SMEM = (size_t)(V7_CAP + V7_BCAP) * V7_ROW * sizeof(double) +        // rows: A | B
                            2 * (size_t)(V7_CAP + V7_BCAP) * sizeof(float4) +              // gate coordinates, two stages
@@ -100,6 +105,7 @@ struct Bin7Args {
     V7Grid G;
     int *count;            // [ncd³] (zeroed)
     int *bucket;           // [ncd³][V7_CAP]
+    unsigned char *need;   // optional [ceil(n_mol / 256)] (zeroed): set for every block of 256 molecules that holds one this rank reads
 };
 
 // one thread per molecule: cell of its COM, slot by arrival (k_gather7 orders the members afterwards)
@@ -112,6 +118,7 @@ static __global__ void k_bin7(Bin7Args A)
     const int cx = cell_coord(c.x, A.inv_cell, n), cy = cell_coord(c.y, A.inv_cell, n), cz = cell_coord(c.z, A.inv_cell, n);
     const bool needed = (cz >= A.G.z0 && cz <= A.G.z1) || (A.G.z1 == n && cz == 0);
     if (!needed) return;
+    if (A.need) A.need[m >> 8] = 1;
     const int id = cx + n * (cy + n * cz);
     const int pos = atomicAdd(&A.count[id], 1);
     if (pos < V7_CAP) A.bucket[(size_t)id * V7_CAP + pos] = m;
@@ -162,7 +169,7 @@ static __global__ void __launch_bounds__(256) k_gather7(Gather7Args A)
         const int v = t < 32 ? __shfl_sync(0xffffffffu, v0, t) : __shfl_sync(0xffffffffu, v1, t - 32);
         r0 += v < v0; r1 += v < v1;
     }
-    const double ox = (double)rx * G.edge, oy = (double)ry * G.edge, oz = (double)rz * G.edge;
+    const double hb = 0.5 * G.box_new;                    // gate coordinates are relative to the box centre
     double dev = 0.0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -182,7 +189,8 @@ static __global__ void __launch_bounds__(256) k_gather7(Gather7Args A)
         double2 *dst = reinterpret_cast<double2 *>(A.rows + ((size_t)e * V7_CAP + r) * V7_ROW);
 #pragma unroll
         for (int k = 0; k < 6; ++k) dst[k] = make_double2(v[2 * k], v[2 * k + 1]);
-        A.gf[(size_t)e * V7_CAP + r] = make_float4((float)(cnx - ox), (float)(cny - oy), (float)(cnz - oz), 0.f);
+        const float gx = (float)(v[9] - hb), gy = (float)(v[10] - hb), gz = (float)(v[11] - hb);
+        A.gf[(size_t)e * V7_CAP + r] = make_float4(gx, gy, gz, fmaf(gz, gz, fmaf(gy, gy, gx * gx)));
     }
     for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
     if (lane == 0) atomicMax(A.max_dev_bits, (unsigned long long)__double_as_longlong(dev));
@@ -206,7 +214,7 @@ struct V7Args {
     unsigned int *err_flag;
     unsigned int *n_ovl;
     unsigned int *ticket;          // zeroed before the launch
-    double4 *unit_partial;         // [units][2 sub-units][V7_CONSUMERS]
+    double4 *unit_partial;         // [units][V7_CONSUMERS]
 };
 
 // what the producer publishes per sub-unit (ring of four, guarded by the gate-coordinate barriers)
@@ -214,10 +222,9 @@ struct V7Desc {
     int valid;                     // 0: this CTA's unit sequence has ended
     int nA, nB, nsl;
     int self_n;                    // nA when slot 0 of this sub-unit is the home cell itself (keep q > p), else 0
-    int rot;                       // row rotation of the unit (spreads the remainder rows over the warps)
-    int boff[6];                   // first B row of slot k; entries from nsl on hold nB
-    float4 off[5];                 // slot offset of slot k in Å (FP32): gate coordinates are relative to the home cell
-    long long sub;                 // partial slot of this sub-unit: unit * 2 + pass
+    int rot;                       // rotation of the warps over the home cell's row blocks (spreads the short last block over the warps)
+    long long unit;                // partial slot of this sub-unit's unit
+    int first;                     // 1: first sub-unit of its unit (store the sums), 0: add to what is there
 };
 
 template <int DEG, bool DIRECT>
@@ -248,7 +255,6 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
     if (warp == V7_CONSUMERS) {
         // ======================================================================== producer warp
         const int n = A.G.ncd, EX = A.G.EX, EY = A.G.EY;
-        const float edge_f = (float)A.G.edge;
         long long u = blockIdx.x;
         unsigned tk_pending = 0;
         if (lane == 0) tk_pending = atomicAdd(A.ticket, 1u);       // one ticket is always in flight: drawn a unit ahead
@@ -267,11 +273,12 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
             const unsigned tk = __shfl_sync(FULL, tk_pending, 0);
             const long long u_next = (long long)gridDim.x + tk;
             if (lane == 0 && u_next < A.units) tk_pending = atomicAdd(A.ticket, 1u);
-            // both sub-unit slots of the unit start at zero (a unit is skipped when a tile is empty; most units have one pass)
-            if (lane < 2 * V7_CONSUMERS) A.unit_partial[(size_t)u * 2 * V7_CONSUMERS + lane] = make_double4(0.0, 0.0, 0.0, 0.0);
             const int nA = __shfl_sync(FULL, cnt, 5);
+            // a unit without work (an empty home cell or only empty neighbours) never reaches the consumers: its slots are zeroed here
+            const bool any_b = __any_sync(FULL, lane < nsl_all && cnt > 0);
+            if ((nA == 0 || !any_b) && lane < V7_CONSUMERS) A.unit_partial[(size_t)u * V7_CONSUMERS + lane] = make_double4(0.0, 0.0, 0.0, 0.0);
             int pass = 0;
-            for (int s_begin = 0; s_begin < nsl_all && nA > 0; ++pass) {
+            for (int s_begin = 0; s_begin < nsl_all && nA > 0;) {
                 int incl = (lane >= s_begin && lane < nsl_all) ? cnt : 0;          // inclusive prefix of the B counts from s_begin on
 #pragma unroll
                 for (int o = 1; o < 8; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
@@ -281,19 +288,12 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
                 if (nB > 0) {
                     const int sg = seq & 1;
                     V7Desc &D = s_desc[seq & 3];
-                    mbar_wait(&s_empty_gf[sg], ((seq >> 1) & 1u) ^ 1u);              // consumers are done gating sub-unit seq − 2
+                    mbar_wait(&s_empty_gf[sg], ((seq >> 1) & 1u) ^ 1u);         // consumers are done gating sub-unit seq − 2
                     const bool mine = lane >= s_begin && lane < se;
-                    if (mine) {
-                        const int k = lane - s_begin, s = sl0 + lane;
-                        D.boff[k] = incl - cnt;
-                        D.off[k] = make_float4((float)c_half_shell[s][0] * edge_f, (float)c_half_shell[s][1] * edge_f,
-                                               (float)c_half_shell[s][2] * edge_f, 0.f);
-                    }
-                    if (lane >= se - s_begin && lane < 6) D.boff[lane] = nB;
                     if (lane == 0) {
                         D.valid = 1; D.nA = nA; D.nB = nB; D.nsl = se - s_begin;
                         D.self_n = (g == 0 && s_begin == 0) ? nA : 0;
-                        D.rot = (int)(u & 3); D.sub = u * 2 + pass;
+                        D.rot = (int)(u & 3); D.unit = u; D.first = pass == 0 ? 1 : 0;
                     }
                     __syncwarp();
                     float4 *gfA = s_gf + sg * (V7_CAP + V7_BCAP), *gfB = gfA + V7_CAP;
@@ -308,7 +308,7 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
                     if (mine && cnt > 0)
                         bulk_g2s(s_rowB + (size_t)(incl - cnt) * V7_ROW, A.rows + (size_t)en * V7_CAP * V7_ROW, (unsigned)cnt * (V7_ROW * 8u), &s_full_rows);
                     if (lane == 5) bulk_g2s(s_rowA, A.rows + (size_t)e * V7_CAP * V7_ROW, (unsigned)nA * (V7_ROW * 8u), &s_full_rows);
-                    ++seq;
+                    ++seq; ++pass;
                 }
                 s_begin = se;
             }
@@ -394,113 +394,89 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
         const V7Desc &D = s_desc[seq & 3];
         if (!D.valid) break;
         const int nA = D.nA, nB = D.nB, self_n = D.self_n;
-        const int p0 = (warp + D.rot) & (V7_CONSUMERS - 1);
-        const int nr = nA > p0 ? (nA - p0 + V7_CONSUMERS - 1) / V7_CONSUMERS : 0;      // rows p0, p0+4, ... of the home cell
+        // warp w owns the contiguous rows [pb, pb + nr) of the home cell (blocks of ceil(nA / 4), rotated by unit)
+        const int nrw = (nA + V7_CONSUMERS - 1) / V7_CONSUMERS;
+        const int pb = ((warp + D.rot) & (V7_CONSUMERS - 1)) * nrw;
+        const int nr = max(0, min(nrw, nA - pb));
         const float4 *gfA = s_gf + sg * (V7_CAP + V7_BCAP), *gfB = gfA + V7_CAP;
         // ---- this warp's A rows as {−2a, r_c² − |a|²}; the tail of the table never passes
         if (lane < 16) {
             float4 t = make_float4(0.f, 0.f, 0.f, -INFINITY);
             if (lane < nr) {
-                const float4 a = gfA[p0 + V7_CONSUMERS * lane];
-                t = make_float4(-2.f * a.x, -2.f * a.y, -2.f * a.z, rc2f - fmaf(a.z, a.z, fmaf(a.y, a.y, a.x * a.x)));
+                const float4 a = gfA[pb + lane];
+                t = make_float4(-2.f * a.x, -2.f * a.y, -2.f * a.z, rc2f - a.w);
             }
             a2[lane] = t;
         }
         __syncwarp();
-        // ---- gate: lane owns B molecule t = 32 j + lane of every chunk j; 16-bit mask over the warp's rows
-        unsigned m[V7_MAXCH];
-        const int b1 = D.boff[1], b2 = D.boff[2], b3 = D.boff[3], b4 = D.boff[4];
-#pragma unroll
-        for (int j = 0; j < V7_MAXCH; ++j) {
-            m[j] = 0u;
-            if (32 * j < nB && nr > 0) {
+        const int nch = nr > 0 ? (nB + 31) >> 5 : 0;
+        const int nr4 = (nr + 3) & ~3;
+        bool rows_in = false, gf_released = false;
+        // Gate chunk after chunk (lane owns B molecule t = 32 j + lane; 16-bit mask over the warp's rows), each chunk's survivors
+        // appended to the queue behind those of the lanes below (one warp scan per chunk).  Normally the whole sub-unit is queued
+        // before the first round is evaluated; a sub-unit with more survivors than the queue holds is evaluated in several goes.
+        for (int j = 0;;) {
+            int tail = 0;
+            for (; j < nch; ++j) {
                 const int t = 32 * j + lane;
                 const bool valid = t < nB;
                 const float4 g = gfB[valid ? t : 0];
-                const int sl = (t >= b1) + (t >= b2) + (t >= b3) + (t >= b4);
-                const float4 o = D.off[sl];
-                const float bx = g.x + o.x, by = g.y + o.y, bz = g.z + o.z;
-                const float bw = valid ? fmaf(bz, bz, fmaf(by, by, bx * bx)) : INFINITY;
+                const float bx = g.x, by = g.y, bz = g.z;
+                const float bw = valid ? g.w : INFINITY;
                 unsigned mask = 0u;
+                for (int r4 = nr4 - 4; r4 >= 0; r4 -= 4) {          // four rows per step, highest rows first: mask = mask << 4 | nibble
+                    unsigned nib = 0u;
 #pragma unroll
-                for (int r4 = 0; r4 < 16; r4 += 4) {
-                    if (r4 < nr) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float4 a = a2[r4 + k];
-                            const float tt = fmaf(a.z, bz, fmaf(a.y, by, fmaf(a.x, bx, bw)));
-                            if (tt < a.w) mask |= 1u << (r4 + k);
-                        }
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 a = a2[r4 + k];
+                        const float tt = fmaf(a.z, bz, fmaf(a.y, by, fmaf(a.x, bx, bw)));
+                        if (tt < a.w) nib |= 1u << k;
                     }
+                    mask = (mask << 4) | nib;
                 }
-                if (t < self_n) {   // home cell against itself: keep q > p with p = p0 + 4 r  ⇔  r < ceil((t − p0) / 4)
-                    const int nv = t > p0 ? (t - p0 + V7_CONSUMERS - 1) / V7_CONSUMERS : 0;
-                    mask &= nv >= 16 ? 0xffffu : ((1u << nv) - 1u);
+                if (t < self_n) {
+                    // home cell against itself: every unordered pair {p, t} once, and about half of its pairs to every row
+                    // (so that the contiguous row blocks of the four warps carry equal work): row p < t takes the pair when
+                    // p + t is even, row p > t when p + t is odd.  p = pb + r.
+                    const int nv = t - pb;                          // rows r < nv are below t, r == nv is t itself
+                    const unsigned lo = nv >= 16 ? 0xffffu : (nv > 0 ? ((1u << nv) - 1u) : 0u);
+                    const unsigned hi = nv >= 15 ? 0u : (nv < 0 ? 0xffffu : (0xffffu << (nv + 1)) & 0xffffu);
+                    const unsigned even = ((pb + t) & 1) ? 0xaaaau : 0x5555u;      // rows r with pb + r + t even
+                    mask &= (lo & even) | (hi & ~even);
                 }
-                m[j] = mask;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty_gf[sg]);           // the producer may refill this gate stage
-        // ---- queue: every lane appends its own survivors behind those of the lanes below it
-        int cnt = 0;
+                const int cnt = __popc(mask);
+                int incl = cnt;
 #pragma unroll
-        for (int j = 0; j < V7_MAXCH; ++j) cnt += __popc(m[j]);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-        const int total = __shfl_sync(FULL, incl, 31);
-        if (total <= V7_QCAP) {
-            int base = incl - cnt;
-#pragma unroll
-            for (int j = 0; j < V7_MAXCH; ++j) {
-                if (32 * j < nB) {
-                    unsigned mm = m[j];
-                    const unsigned eb = ((unsigned)(32 * j + lane) << 6) | (unsigned)p0;
-                    while (mm) {
-                        const int r = __ffs(mm) - 1;
-                        mm &= mm - 1u;
-                        q[base++] = (unsigned short)(eb + (unsigned)(V7_CONSUMERS * r));
-                    }
+                for (int o2 = 1; o2 < 32; o2 <<= 1) { const int v = __shfl_up_sync(FULL, incl, o2); if (lane >= o2) incl += v; }
+                const int tot = __shfl_sync(FULL, incl, 31);
+                if (tail + tot > V7_QCAP) break;                     // no room: evaluate what is queued, then gate this chunk again
+                int base = tail + incl - cnt;
+                const unsigned eb = ((unsigned)t << 6) | (unsigned)pb;
+                while (mask) {
+                    const int r = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    q[base++] = (unsigned short)(eb + (unsigned)r);
                 }
+                tail += tot;
             }
             __syncwarp();
-            mbar_wait(&s_full_rows, seq & 1u);
-            for (int b = 0; b < total; b += 32) {
-                const bool have = b + lane < total;
+            if (j >= nch && !gf_released) { if (lane == 0) mbar_arrive(&s_empty_gf[sg]); gf_released = true; }   // the producer may refill this gate stage
+            if (!rows_in) { mbar_wait(&s_full_rows, seq & 1u); rows_in = true; }
+            for (int b = 0; b < tail; b += 32) {
+                const bool have = b + lane < tail;
                 consume(have ? q[b + lane] : 0u, have);
             }
-        } else {
-            // a unit with more survivors than the queue holds (far denser than a liquid): chunk by chunk
-            mbar_wait(&s_full_rows, seq & 1u);
-#pragma unroll
-            for (int j = 0; j < V7_MAXCH; ++j) {
-                if (32 * j < nB) {
-                    unsigned mm = m[j];
-                    const int c = __popc(mm);
-                    int ic = c;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, ic, o); if (lane >= o) ic += v; }
-                    const int tot = __shfl_sync(FULL, ic, 31);
-                    int base = ic - c;
-                    const unsigned eb = ((unsigned)(32 * j + lane) << 6) | (unsigned)p0;
-                    while (mm) {
-                        const int r = __ffs(mm) - 1;
-                        mm &= mm - 1u;
-                        q[base++] = (unsigned short)(eb + (unsigned)(V7_CONSUMERS * r));
-                    }
-                    __syncwarp();
-                    for (int b = 0; b < tot; b += 32) {
-                        const bool have = b + lane < tot;
-                        consume(have ? q[b + lane] : 0u, have);
-                    }
-                    __syncwarp();
-                }
-            }
+            __syncwarp();
+            if (j >= nch) break;
         }
         // ---- this sub-unit's sums, per warp, at a place that depends on the unit only (folded in unit order afterwards)
         const double w0 = warp_sum(acc_lj), w1 = warp_sum(acc_vir), w2 = warp_sum(acc_q);
-        if (lane == 0) A.unit_partial[(size_t)D.sub * V7_CONSUMERS + warp] = make_double4(w0, w1, w2, (double)my_pairs);
+        if (lane == 0) {
+            double4 *slot = A.unit_partial + (size_t)D.unit * V7_CONSUMERS + warp;
+            double4 v = make_double4(w0, w1, w2, (double)my_pairs);
+            if (!D.first) { const double4 o = *slot; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }   // (this lane wrote it a sub-unit ago)
+            *slot = v;
+        }
         acc_lj = 0.0; acc_vir = 0.0; acc_q = 0.0; my_pairs = 0;
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty_rows);             // the producer may refill the rows
@@ -514,7 +490,7 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
 // stores ρ(k) to the resident buffers (:600-601), and either publishes the scalars to the host (one rank) or pushes
 // this rank's vector into every peer's exchange buffer (sharded evaluation, kernels_peer.cuh).
 // ------------------------------------------------------------------------------------------------------------
-#define TAIL_BLOCKS 64
+#define TAIL_BLOCKS 128
 #define TAIL_THREADS 256
 
 struct TailArgs {
@@ -529,6 +505,9 @@ struct TailArgs {
     const double *cfac; double2 *dst0, *dst1;
     double *host_out;              // mapped pinned: [0..7] vec head, [8] sequence number (written last)
     unsigned long long seq;
+    // sharded evaluation: the last block stores the vector into slot `rank` of every rank's exchange buffer (kernels_peer.cuh)
+    int push;
+    PeerArgs peer;
 };
 
 static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_constant__ TailArgs A)
@@ -537,11 +516,19 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
     __shared__ double2 s_s[8][33];
     __shared__ int s_last;
     const int tid = threadIdx.x, b = blockIdx.x;
-    {   // pair sums: contiguous share, thread-strided, fixed tree
+    {   // pair sums: contiguous share; four independent running sums per thread (the loads are in flight together), fixed tree
         const long long per = (A.n_partial + gridDim.x - 1) / gridDim.x;
         const long long lo = per * b, hi = lo + per < A.n_partial ? lo + per : A.n_partial;
-        double v[4] = {0.0, 0.0, 0.0, 0.0};
-        for (long long i = lo + tid; i < hi; i += TAIL_THREADS) { const double4 p = A.unit_partial[i]; v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w; }
+        double v[4] = {0.0, 0.0, 0.0, 0.0}, w[4] = {0.0, 0.0, 0.0, 0.0};
+        long long i = lo + tid;
+        for (; i + TAIL_THREADS < hi; i += 2 * TAIL_THREADS) {
+            const double4 p = A.unit_partial[i], q = A.unit_partial[i + TAIL_THREADS];
+            v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
+            w[0] += q.x; w[1] += q.y; w[2] += q.z; w[3] += q.w;
+        }
+        if (i < hi) { const double4 p = A.unit_partial[i]; v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += w[k];
         block_sum<4, TAIL_THREADS>(v, s_red);
         if (tid == 0) A.block_sums[b] = make_double4(v[0], v[1], v[2], v[3]);
     }
@@ -549,9 +536,16 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
     for (int k0 = 32 * b; k0 < A.nkvecs; k0 += 32 * gridDim.x) {
         const int k = k0 + (tid & 31), sl = tid >> 5;
         const int c0 = (int)((long long)A.rhok_blocks * sl / 8), c1 = (int)((long long)A.rhok_blocks * (sl + 1) / 8);
-        double re = 0.0, im = 0.0;
-        if (k < A.nkvecs)
-            for (int c = c0; c < c1; ++c) { const double2 p = A.rhok_partial[(size_t)c * A.nkvecs + k]; re += p.x; im += p.y; }
+        double re = 0.0, im = 0.0, re2 = 0.0, im2 = 0.0;
+        if (k < A.nkvecs) {
+            int c = c0;
+            for (; c + 1 < c1; c += 2) {
+                const double2 p = A.rhok_partial[(size_t)c * A.nkvecs + k], q = A.rhok_partial[(size_t)(c + 1) * A.nkvecs + k];
+                re += p.x; im += p.y; re2 += q.x; im2 += q.y;
+            }
+            if (c < c1) { const double2 p = A.rhok_partial[(size_t)c * A.nkvecs + k]; re += p.x; im += p.y; }
+            re += re2; im += im2;
+        }
         __syncthreads();
         s_s[sl][tid & 31] = make_double2(re, im);
         __syncthreads();
@@ -580,16 +574,30 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
         }
         block_sum<1, TAIL_THREADS>(er, s_red);
     }
+    __shared__ double s_h[MMC_NSCAL];
     if (tid == 0) {
-        double h[MMC_NSCAL];
-        h[0] = v[0]; h[1] = v[1]; h[2] = v[2]; h[3] = (double)(*A.n_ovl); h[4] = er[0]; h[5] = v[3];
-        h[6] = (double)(*A.max_count); h[7] = (double)(*A.err_flag);
-        for (int i = 0; i < MMC_NSCAL; ++i) A.vec[i] = h[i];
+        s_h[0] = v[0]; s_h[1] = v[1]; s_h[2] = v[2]; s_h[3] = (double)(*A.n_ovl); s_h[4] = er[0]; s_h[5] = v[3];
+        s_h[6] = (double)(*A.max_count); s_h[7] = (double)(*A.err_flag);
+        for (int i = 0; i < MMC_NSCAL; ++i) A.vec[i] = s_h[i];
         if (A.finish && A.host_out) {
-            for (int i = 0; i < MMC_NSCAL; ++i) A.host_out[i] = h[i];
+            for (int i = 0; i < MMC_NSCAL; ++i) A.host_out[i] = s_h[i];
             __threadfence_system();
             *reinterpret_cast<volatile unsigned long long *>(A.host_out + MMC_NSCAL) = A.seq;
         }
         *A.done = 0u;                                     // ready for the next evaluation
+    }
+    if (A.push) {   // k_peer_push, by the block that holds the finished vector
+        __syncthreads();
+        const PeerArgs &P = A.peer;
+        for (int d = 0; d < P.world; ++d) {
+            double *dst = P.slot[d] + ((size_t)P.parity * P.world + P.rank) * P.nvec_cap;
+            for (int t = tid; t < P.nvec; t += TAIL_THREADS) dst[t] = t < MMC_NSCAL ? s_h[t] : __ldcg(&A.vec[t]);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < P.world) {
+            volatile unsigned long long *f = P.flag[tid] + (size_t)P.parity * P.world + P.rank;
+            *f = P.epoch;
+        }
     }
 }

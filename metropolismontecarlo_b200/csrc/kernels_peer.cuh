@@ -62,3 +62,53 @@ static __global__ void __launch_bounds__(256) k_peer_sum(const __grid_constant__
     }
     if (threadIdx.x == 0 && s_bad) *status = 1;
 }
+
+// k_peer_sum with the evaluation's own finalisation folded in (one launch after the exchange): the summed vector, then
+// E_recip = Σ cfac |ρ(k)|² (ewalds.jl:599), ρ(k) into the resident buffers (:600-601) and the scalars into the mapped host slot.
+struct PeerFinishArgs {
+    int nkvecs;                    // 0: no k-space
+    const double *cfac; double2 *dst0, *dst1;
+    double *host_out;              // mapped pinned: [0..7] summed scalars, [8] sequence number (written last), [9] status
+    unsigned long long seq;
+};
+
+static __global__ void __launch_bounds__(256) k_peer_sum_finish(const __grid_constant__ PeerArgs P, double *__restrict__ out,
+                                                                 const __grid_constant__ PeerFinishArgs F)
+{
+    __shared__ int s_bad;
+    __shared__ double s_red[8];
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    if (threadIdx.x < P.world) {
+        volatile unsigned long long *f = P.flag[P.rank] + (size_t)P.parity * P.world + threadIdx.x;
+        const long long t0 = clock64();
+        while (*f < P.epoch) {
+            __nanosleep(20);
+            if (clock64() - t0 > 20000000000LL) { s_bad = 1; break; }     // ≈10 s: a peer is gone
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    const volatile double *base = P.slot[P.rank] + (size_t)P.parity * P.world * P.nvec_cap;
+    double er[1] = {0.0};
+    for (int t = threadIdx.x; t < P.nvec; t += 256) {
+        double s = 0.0;
+        for (int q = 0; q < P.world; ++q) s += base[(size_t)q * P.nvec_cap + t];
+        out[t] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < F.nkvecs; k += 256) {
+        const double2 s = make_double2(out[MMC_NSCAL + 2 * k], out[MMC_NSCAL + 2 * k + 1]);
+        er[0] += F.cfac[k] * (s.x * s.x + s.y * s.y);
+        if (F.dst0) F.dst0[k] = s;
+        if (F.dst1) F.dst1[k] = s;
+    }
+    block_sum<1, 256>(er, s_red);
+    if (threadIdx.x == 0) {
+        out[4] = er[0];
+        for (int i = 0; i < MMC_NSCAL; ++i) F.host_out[i] = out[i];
+        F.host_out[MMC_NSCAL + 1] = s_bad ? 1.0 : 0.0;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(F.host_out + MMC_NSCAL) = F.seq;
+    }
+}

@@ -87,6 +87,16 @@ static __global__ void k_repack_sites(const double *coords, int s0, int s1, doub
     site[t] = s;
 }
 
+// sites of the molecule blocks (256 molecules each) a rank of a domain-decomposed evaluation has received
+static __global__ void k_repack_sites_blocks(const double *coords, const unsigned char *__restrict__ need, int US, int n_sites, double4 *site)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_sites || !need[(t / US) >> 8]) return;
+    double4 s = site[t];
+    s.x = coords[3 * (size_t)t]; s.y = coords[3 * (size_t)t + 1]; s.z = coords[3 * (size_t)t + 2];
+    site[t] = s;
+}
+
 // Σq and Σq² in two deterministic stages (EwaldSelf ewalds.jl:829-833, Wolf constants energy.jl:924-934)
 static __global__ void __launch_bounds__(256) k_charge_partial(const double4 *site, int n, double2 *part)
 {

@@ -27,7 +27,9 @@ void free_system(mmc_handle *h)
     dfree(h->d_rhok_partial); dfree(h->d_units);
     h->units_cap = 0;
     dfree(h->d7_flags); dfree(h->d7_count); dfree(h->d7_bucket); dfree(h->d7_ecount); dfree(h->d7_rows); dfree(h->d7_gf);
-    dfree(h->d7_unit_partial); dfree(h->d7_block_sums);
+    dfree(h->d7_unit_partial); dfree(h->d7_block_sums); dfree(h->d7_need);
+    if (h->h7_need) { cudaFreeHost(h->h7_need); h->h7_need = nullptr; }
+    h->need_cap = 0;
     h->d7_ncd = 0; h->d7_partial_cap = 0; h->bin_version = 0;
     h->max_cell_cached = -1;
     h->has_system = false;
@@ -184,8 +186,10 @@ void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P)
     P = Q;
 }
 
-int style_check(mmc_handle *h, int style)
+int style_check(mmc_handle *h, int style, bool need_full_state)
 {
+    if (need_full_state && h->partial_resident)
+        FAIL(MMC_ESTATE, "after mmc_potential_host on a sharded handle only this rank's slab of the sites is resident: mmc_upload_positions first");
     if (style == MMC_STYLE_LJ_ATOMS) {
         if (!h->has_atoms) FAIL(MMC_ESTATE, "no atomic system uploaded");
         return MMC_OK;
@@ -232,6 +236,8 @@ int launch_move_atom(mmc_handle *h, AtomArgs &A)
 int check_mol_index(mmc_handle *h, int64_t i)
 {
     if (!h->has_system) FAIL(MMC_ESTATE, "no molecular system uploaded");
+    if (h->partial_resident)
+        FAIL(MMC_ESTATE, "after mmc_potential_host on a sharded handle only this rank's slab of the sites is resident: mmc_upload_positions first");
     if (i < 1 || i > h->S.n_mol) FAIL(MMC_EINVAL, "molecule index out of range (1-based)");
     return MMC_OK;
 }
@@ -448,7 +454,7 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         for (int64_t m = 0; m < n_mol; ++m) h->h_mol[m] = make_int2((int)(first_atom[m] - 1), (int)(last_atom[m] - first_atom[m] + 1));
     }
     h->max_cell_cached = -1;
-    h->pair_level = h->pair_floor;
+    h->pair_level = h->pair_floor; h->v7_left_for_overlap = false;
     if (h->pend_kind == 1) h->pend_kind = 0;
     if (h->has_ewald) {
         get_erf_poly(h, S.kappa, rc_qq * rc_qq + 100, h->move_poly);
@@ -466,6 +472,7 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         }
     }
     h->has_system = true;
+    h->partial_resident = false;
     h->state_version++;
     h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
     return MMC_OK;
@@ -518,10 +525,11 @@ int mmc_upload_positions(mmc_handle *h, const double *coords, const double *com)
                                                                                   S.site, S.com, h->d_info);
     LAUNCH_CHECK();
     h->state_version++;
+    h->partial_resident = false;
     CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
-    h->pair_level = h->pair_floor;
+    h->pair_level = h->pair_floor; h->v7_left_for_overlap = false;
     if (h->pend_kind == 1) h->pend_kind = 0;
     h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
     return MMC_OK;

@@ -29,6 +29,8 @@ struct EvalCtx {
     double *per_mol = nullptr;          // mmc_energy_all: [n_mol x 3] per-molecule rows (general kernel, evaluation order)
     int rhok_blocks = 0;                // rhok_external: CTAs whose partials sit in d_rhok_partial ...
     cudaEvent_t rhok_done = nullptr;    //                ... once this event has fired
+    bool partial_state = false;         // domain-decomposed host evaluation: only this rank's slab is resident, so a fall-back to
+                                        // an unsharded evaluation is the caller's business (finalize_host returns 2)
 };
 
 }  // namespace
@@ -92,31 +94,40 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
 namespace {
 
 // k_pairs_fast instantiations: water (3 sites) x tile {64, 128} x padded polynomial degree
+#ifdef MMC_DEV_FEW_DEGS      // development builds: the degrees of configs A, D, E only (full list: 3x shorter compile)
+#define MMC_FOR_DEGS(X) X(0) X(16) X(20)
+#define MMC_FOR_POS_DEGS(X) X(16) X(20)
+#define MMC_FOR_DIRECT_DEGS(X) X(7)
+#else
 #define MMC_FOR_DEGS(X) X(0) X(8) X(12) X(16) X(20) X(24) X(32) X(44)
 #define MMC_FOR_POS_DEGS(X) X(8) X(12) X(16) X(20) X(24) X(32) X(44)
 #define MMC_FOR_DIRECT_DEGS(X) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
-void launch_pairs_fast(int tile, int deg, int grid, size_t smem, cudaStream_t st, const PairArgs &P)
+#endif
+// (false: no instantiation for this degree — the caller fails loudly instead of returning zeros)
+bool launch_pairs_fast(int tile, int deg, int grid, size_t smem, cudaStream_t st, const PairArgs &P)
 {
 #define X(D)                                                                                   \
     if (deg == D) {                                                                            \
         if (tile == 64) k_pairs_fast<3, 64, D><<<grid, PAIR_BLOCK, smem, st>>>(P);             \
         else k_pairs_fast<3, 128, D><<<grid, PAIR_BLOCK, smem, st>>>(P);                       \
-        return;                                                                                \
+        return true;                                                                           \
     }
     MMC_FOR_DEGS(X)
 #undef X
+    return false;
 }
-void launch_pairs_v7(int deg, bool direct, int grid, cudaStream_t st, const V7Args &A)
+bool launch_pairs_v7(int deg, bool direct, int grid, cudaStream_t st, const V7Args &A)
 {
     if (direct) {
-#define X(D) if (deg == D) { k_pairs_v7<D, true><<<grid, V7_BLOCK, V7_SMEM, st>>>(A); return; }
+#define X(D) if (deg == D) { k_pairs_v7<D, true><<<grid, V7_BLOCK, V7_SMEM, st>>>(A); return true; }
         MMC_FOR_DIRECT_DEGS(X)
 #undef X
     } else {
-#define X(D) if (deg == D) { k_pairs_v7<D, false><<<grid, V7_BLOCK, V7_SMEM, st>>>(A); return; }
+#define X(D) if (deg == D) { k_pairs_v7<D, false><<<grid, V7_BLOCK, V7_SMEM, st>>>(A); return true; }
         MMC_FOR_POS_DEGS(X)
 #undef X
     }
+    return false;
 }
 }  // namespace
 
@@ -190,6 +201,15 @@ void v7_slab(int ncd, int rank, int world, int &z0, int &z1)
     z1 = (int)((long long)ncd * (rank + 1) / world);
 }
 
+V7Grid v7_grid(const mmc_handle *h, int style, const EvalCtx &E)
+{
+    V7Grid G{};
+    G.ncd = grid_cells(h, style, E.box); G.EX = G.ncd + 2; G.EY = G.ncd + 2;
+    v7_slab(G.ncd, E.rank, E.world, G.z0, G.z1);
+    G.edge = E.box / G.ncd; G.box_new = E.box;
+    return G;
+}
+
 int v7_alloc(mmc_handle *h, const V7Grid &G, long long units)
 {
     if (!h->d7_flags) {
@@ -207,7 +227,7 @@ int v7_alloc(mmc_handle *h, const V7Grid &G, long long units)
         h->d7_ncd = G.ncd;
         h->bin_version = 0;
     }
-    const size_t need = (size_t)std::max(1LL, units) * 2 * V7_CONSUMERS;
+    const size_t need = (size_t)std::max(1LL, units) * V7_CONSUMERS;
     if (need > h->d7_partial_cap) {
         dfree(h->d7_unit_partial);
         CK(cudaMalloc(&h->d7_unit_partial, need * sizeof(double4)));
@@ -218,14 +238,12 @@ int v7_alloc(mmc_handle *h, const V7Grid &G, long long units)
 
 // Enqueues one evaluation on the v7 path and leaves this rank's partial-sum vector in d_vec.  finish: one rank — E_recip,
 // resident ρ(k) and the scalars in the mapped host slot come out of the same tail kernel.
-int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, double *d_vec, bool finish, double2 *dst0, double2 *dst1)
+int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, double *d_vec, bool finish, double2 *dst0, double2 *dst1,
+            const PeerArgs *push = nullptr)
 {
     const DevSystem &S = h->S;
     const bool ewald = style == MMC_STYLE_EWALD;
-    V7Grid G{};
-    G.ncd = grid_cells(h, style, E.box); G.EX = G.ncd + 2; G.EY = G.ncd + 2;
-    v7_slab(G.ncd, E.rank, E.world, G.z0, G.z1);
-    G.edge = E.box / G.ncd; G.box_new = E.box;
+    const V7Grid G = v7_grid(h, style, E);
     const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * (G.z1 - G.z0);
     int rc = v7_alloc(h, G, units);
     if (rc) return rc;
@@ -253,7 +271,7 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     const int tb = 256;
     if (h->bin_version != h->state_version || h->bin_ncd != G.ncd || h->bin_z0 != G.z0 || h->bin_z1 != G.z1) {
         CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)G.ncd * G.ncd * G.ncd, h->stream));
-        Bin7Args B{S.com, S.n_mol, (double)G.ncd / S.box, G, h->d7_count, h->d7_bucket};
+        Bin7Args B{S.com, S.n_mol, (double)G.ncd / S.box, G, h->d7_count, h->d7_bucket, nullptr};
         k_bin7<<<(S.n_mol + tb - 1) / tb, tb, 0, h->stream>>>(B); LAUNCH_CHECK();
         h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_z0 = G.z0; h->bin_z1 = G.z1;
     }
@@ -272,10 +290,11 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
         A.G = G; A.units = (int)units;
         A.rows = h->d7_rows; A.gf = h->d7_gf; A.ecount = h->d7_ecount;
         const double rcut = S.rc_qq, edge = G.edge;
-        // conservative FP32 gate in the dot form |b|² − 2a·b < r_c² − |a|² on coordinates relative to the home cell
-        // (|a| components < edge, |b| < 2·edge): seven roundings of numbers <= 12·edge² and the input roundings
-        // (2·sqrt(3)·r_c·δ, δ <= 3·edge·2^-23), times four
-        const double margin = 4.0 * (8.0 * 12.0 * edge * edge + 8.0 * rcut * edge) / 16777216.0;
+        // conservative FP32 gate in the dot form |b|² − 2a·b < r_c² − |a|² on coordinates relative to the box centre
+        // (components <= M = L/2 + edge, ghosts included): eight roundings of numbers <= 3M² and the input roundings
+        // (4·sqrt(3)·r_c·M·2^-24), times four.  Config E: 0.07 Å² on r_c² = 100, i.e. 0.1 % more survivors for the exact test.
+        const double M = 0.5 * E.box + edge;
+        const double margin = 4.0 * (8.0 * 3.0 * M * M + 7.0 * rcut * M) / 16777216.0;
         A.gate_rc2f = std::nextafterf((float)(rcut * rcut + margin), INFINITY);
         A.rc_qq2 = rcut * rcut;
         std::memcpy(&A.rcqq_bits, &A.rc_qq2, 8);
@@ -299,7 +318,7 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
         A.n_ovl = fl + 2; A.err_flag = fl + 3; A.ticket = fl + 5;
         A.unit_partial = h->d7_unit_partial;
         const int grid = (int)std::max(1LL, std::min<long long>((long long)h->v7_ctas_per_sm * h->sm_count, units));
-        launch_pairs_v7(deg, direct, grid, h->stream, A);
+        if (!launch_pairs_v7(deg, direct, grid, h->stream, A)) FAIL(MMC_ECUDA, "k_pairs_v7: no instantiation for this polynomial degree (internal)");
         LAUNCH_CHECK();
     }
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
@@ -307,13 +326,15 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     if (E.rhok_external && E.rhok_done) CK(cudaStreamWaitEvent(h->stream, E.rhok_done, 0));
     // ---- everything else in one launch
     TailArgs T{};
-    T.unit_partial = h->d7_unit_partial; T.n_partial = units * 2 * V7_CONSUMERS;
+    T.unit_partial = h->d7_unit_partial; T.n_partial = units * V7_CONSUMERS;
     T.rhok_partial = h->d_rhok_partial; T.rhok_blocks = rhok_blocks; T.nkvecs = ewald ? S.nkvecs : 0;
     T.block_sums = h->d7_block_sums; T.done = fl + 6;
     T.n_ovl = fl + 2; T.err_flag = fl + 3; T.max_count = h->d7_flags + 4;
     T.vec = d_vec;
     T.finish = finish ? 1 : 0; T.cfac = E.d_cfac; T.dst0 = dst0; T.dst1 = dst1;
-    T.host_out = h->d7_res; T.seq = ++h->res_seq;
+    T.host_out = h->d7_res; T.seq = finish ? ++h->res_seq : 0;
+    T.push = push ? 1 : 0;
+    if (push) T.peer = *push;
     k_eval_tail<<<TAIL_BLOCKS, TAIL_THREADS, 0, h->stream>>>(T); LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[6], h->stream);
     h->last_fast = 7; h->last_mode = 0; h->last_ncd = G.ncd;
@@ -446,7 +467,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         const size_t smem = 2 * (2 * (size_t)tile + 2 * (size_t)tile * US) * sizeof(double4) +
                             (size_t)tile * tile * sizeof(unsigned short);
         grid = (int)std::max(1LL, std::min<long long>((tile == 64 ? 4 : 2) * h->sm_count, my_units));
-        launch_pairs_fast(tile, P.ep.deg, grid, smem, h->stream, P);
+        if (!launch_pairs_fast(tile, P.ep.deg, grid, smem, h->stream, P)) FAIL(MMC_ECUDA, "k_pairs_fast: no instantiation for this polynomial degree (internal)");
     } else {
         const size_t smem = (2 * PAIR_TILE + 2 * PAIR_TILE * (size_t)US) * sizeof(double4) +
                             (size_t)PAIR_WARPS * PAIR_QCAP * sizeof(unsigned);
@@ -547,7 +568,8 @@ int finish_v7(mmc_handle *h, int style, const EvalCtx &E, mmc_properties *out)
     int rc = v7_wait(h, hv);
     if (rc) return rc;
     if (h->tm.on) { CK(cudaStreamSynchronize(h->stream)); if (style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side)); }
-    if (hv[7] != 0.0 || hv[3] != 0.0) return 1;
+    if (hv[7] != 0.0) return 1;
+    if (hv[3] != 0.0) { h->v7_left_for_overlap = true; return 1; }     // back to k_pairs_v7 once the overlaps are gone
     h->last_pairs = (long long)hv[5];
     assemble(h, style, E, hv[0], hv[1], hv[2], hv[4], 0, out);
     read_timings(h, style);
@@ -560,6 +582,8 @@ int evaluate_unsharded(mmc_handle *h, int style, EvalCtx E, double2 *dst0, doubl
 // d_vec holds the (already rank-summed) partials; computes E_recip on the device, brings the
 // scalars to the host and assembles Properties in the reference's order (energy.jl:972-1021).
 // Returns 1 when the pair kernel that produced the partials declined the state (one rank: the caller escalates).
+int finalize_host(mmc_handle *h, int style, const EvalCtx &E, const double *hv, double2 *dst0, double2 *dst1, mmc_properties *out);
+
 int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 *dst0, double2 *dst1,
              mmc_properties *out)
 {
@@ -573,25 +597,34 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
     if (h->tm.on && h->last_fast != 7) cudaEventRecord(h->tm.ev[6], h->stream);
     CK(cudaStreamSynchronize(h->stream));
     if (h->tm.on && style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side));
+    return finalize_host(h, style, E, h->h_vec, dst0, dst1, out);
+}
+
+// the host part: hv = the eight scalars of the (rank-summed) vector
+int finalize_host(mmc_handle *h, int style, const EvalCtx &E, const double *hv, double2 *dst0, double2 *dst1, mmc_properties *out)
+{
+    const DevSystem &S = h->S;
     const bool coulomb = style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF;
-    const long long novl = (long long)h->h_vec[3];
+    const long long novl = (long long)hv[3];
     if (E.world == 1) {
-        if (h->last_mode == 0 && h->last_fast != 7) h->max_cell_cached = (int)h->h_vec[6];
-        if (h->h_vec[7] != 0.0) return 1;      // a cell outgrew the kernel's tile: caller re-runs
+        if (h->last_mode == 0 && h->last_fast != 7) h->max_cell_cached = (int)hv[6];
+        if (hv[7] != 0.0) return 1;      // a cell outgrew the kernel's tile: caller re-runs
         if (h->last_fast == 7 && novl > 0) return 1;
-    } else if (h->h_vec[7] != 0.0 || (novl > 0 && coulomb)) {
+    } else if (hv[7] != 0.0 || (novl > 0 && coulomb)) {
         // Summed over ranks, so every rank takes this branch together: a rank's pair kernel declined the state, or
         // molecules overlap (ewalds.jl:359-360 zeroes whole rows, which needs a molecule's complete neighbourhood).  The
         // state is replicated, so every rank evaluates the whole system on the general path and gets the same Properties:
         // slow, rare, and no retry protocol leaks to the caller.
-        if (h->h_vec[7] != 0.0 || h->last_fast == 7) { if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)"); }
+        if (hv[7] != 0.0 || h->last_fast == 7) { if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)"); }
+        if (novl > 0 && hv[7] == 0.0) h->v7_left_for_overlap = true;
         h->max_cell_cached = -1;
+        if (E.partial_state) return 2;
         EvalCtx E1 = E;
         E1.rank = 0; E1.world = 1; E1.wait_sites = nullptr; E1.rhok_external = false; E1.rhok_done = nullptr;
         return evaluate_unsharded(h, style, E1, dst0, dst1, out);
     }
-    double lj_pot = h->h_vec[0], lj_vir = h->h_vec[1], coul = h->h_vec[2];
-    const double recip_raw = h->h_vec[4];
+    double lj_pot = hv[0], lj_vir = hv[1], coul = hv[2];
+    const double recip_raw = hv[4];
     if (novl > 0 && coulomb) {
         // reference semantics: a molecule whose EwaldReal row hits the overlap rule contributes
         // 0 for its whole row (ewalds.jl:359-360 inside energy.jl:991-1001): U - ½ Σ_flagged row_i
@@ -606,7 +639,8 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
             }
         h->cnt.overlap_events += novl;
     }
-    h->last_pairs = (long long)h->h_vec[5];
+    h->last_pairs = (long long)hv[5];
+    if (h->v7_left_for_overlap && novl == 0 && coulomb) { h->v7_left_for_overlap = false; h->pair_level = h->pair_floor; }
     assemble(h, style, E, lj_pot, lj_vir, coul, recip_raw, novl, out);
     read_timings(h, style);
     h->cnt.full_energy_evals++;
@@ -746,6 +780,10 @@ int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partial
     if (!d_partials || !out) FAIL(MMC_EINVAL, "null argument");
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
     rc = finalize(h, style, E, const_cast<double *>(d_partials), h->S.rhok[0], h->S.rhok[1], out);
+    if (rc == 1) {       // (world == 1) the pair kernel declined the state: next level, evaluated here
+        if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
+        rc = evaluate_unsharded(h, style, E, h->S.rhok[0], h->S.rhok[1], out);
+    }
     if (style == MMC_STYLE_EWALD) h->new_valid = false;
     return rc;
 }
@@ -827,6 +865,105 @@ static PeerArgs peer_args(mmc_handle *h)
     return P;
 }
 
+}  // extern "C"
+
+namespace {
+// mmc_potential_host on a sharded handle: DOMAIN DECOMPOSITION.  Rank r owns the z-slab [z0, z1) of the cell grid; it
+// receives all COMs (24 B per molecule: they decide who needs what), bins them, and then copies from the caller's site
+// array only the blocks of 256 molecules that hold a molecule of its slab, of the layer above it (the half shell) or of its
+// share of the sites for rho(k) — (1/world + 1/ncd) of the 72 B per molecule instead of all of it when the caller's order is
+// spatially coherent (a lattice start, a sorted restart), everything when it is not.  The partial vectors are exchanged over
+// NVLink as in mmc_potential_sharded.  Afterwards only those blocks are current on this GPU (partial_resident).
+int potential_host_sharded(mmc_handle *h, const double *coords, const double *com, int style, const ErfPoly &ep, mmc_properties *out)
+{
+    DevSystem &S = h->S;
+    int rc;
+    if ((rc = ensure_vec(h))) return rc;
+    h->pair_level = h->pair_floor;
+    if (h->pend_kind == 1) h->pend_kind = 0;
+    h->trial_pending = false; h->vol_pending = false; h->new_valid = false;
+    double *d_coords = reinterpret_cast<double *>(h->d_raw);
+    double *d_com = d_coords + 4 * (size_t)S.n_sites;
+    const bool ewald = style == MMC_STYLE_EWALD;
+    const int US = h->US;
+    const int nblk = (S.n_mol + 255) >> 8;
+    if (nblk > h->need_cap) {
+        dfree(h->d7_need);
+        if (h->h7_need) cudaFreeHost(h->h7_need);
+        CK(cudaMalloc(&h->d7_need, nblk));
+        CK(cudaHostAlloc((void **)&h->h7_need, nblk, cudaHostAllocDefault));
+        h->need_cap = nblk;
+    }
+    EvalCtx E{1.0, S.box, S.kappa, S.cfac, h->cfg.rank, h->cfg.world};
+    E.partial_state = true;
+    const V7Grid G = v7_grid(h, style, E);
+    const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * (G.z1 - G.z0);
+    if ((rc = v7_alloc(h, G, units))) return rc;
+    // ---- COMs, binning, and which molecule blocks this rank reads
+    CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * S.n_mol, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
+    k_repack_com<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(d_com, S.n_mol, S.box, S.com, h->d_info); LAUNCH_CHECK();
+    h->state_version++;
+    CK(cudaMemsetAsync(h->d7_need, 0, nblk, h->stream));
+    CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)G.ncd * G.ncd * G.ncd, h->stream));
+    Bin7Args B{S.com, S.n_mol, (double)G.ncd / S.box, G, h->d7_count, h->d7_bucket, h->d7_need};
+    k_bin7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(B); LAUNCH_CHECK();
+    h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_z0 = G.z0; h->bin_z1 = G.z1;
+    CK(cudaMemcpyAsync(h->h7_need, h->d7_need, nblk, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
+    // ---- this rank's share of the sites for rho(k) (by site index, as in the resident sharded evaluation)
+    const long long ns_all = S.n_sites;
+    const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
+    if (ewald)
+        for (int b = (rs0 / US) >> 8; b <= (((rs1 - 1) / US) >> 8) && b < nblk; ++b) h->h7_need[b] = 1;
+    // ---- copy the runs of needed blocks; the copy stream carries nothing but copies
+    CK(cudaStreamWaitEvent(h->copy, h->ev_fork, 0));
+    long long bytes = sizeof(double) * 3 * (long long)S.n_mol;
+    for (int b = 0; b < nblk;) {
+        if (!h->h7_need[b]) { ++b; continue; }
+        int e = b;
+        while (e < nblk && h->h7_need[e]) ++e;
+        const long long s0 = (long long)b * 256 * US, s1 = std::min<long long>((long long)e * 256 * US, S.n_sites);
+        CK(cudaMemcpyAsync(d_coords + 3 * s0, coords + 3 * s0, sizeof(double) * 3 * (size_t)(s1 - s0), cudaMemcpyHostToDevice, h->copy));
+        bytes += (long long)sizeof(double) * 3 * (s1 - s0);
+        b = e;
+    }
+    h->last_h2d_bytes = bytes;
+    CK(cudaMemcpyAsync(h->d7_need, h->h7_need, nblk, cudaMemcpyHostToDevice, h->copy));      // (with the rho(k) blocks added)
+    CK(cudaEventRecord(h->ev_copy[0], h->copy));
+    CK(cudaStreamWaitEvent(h->side, h->ev_copy[0], 0));
+    k_repack_sites_blocks<<<(S.n_sites + 255) / 256, 256, 0, h->side>>>(d_coords, h->d7_need, US, S.n_sites, S.site); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev_sites, h->side));
+    int blocks = 0;
+    if (ewald && (rc = rhok_launch(h, S.site, rs0, rs1, S.box, nullptr, h->side, 0, &blocks))) return rc;
+    CK(cudaEventRecord(h->ev_join, h->side));
+    h->partial_resident = true;
+    E.wait_sites = h->ev_sites; E.rhok_external = true; E.rhok_blocks = blocks; E.rhok_done = h->ev_join;
+    h->peer_epoch += 1;
+    const PeerArgs P = peer_args(h);
+    if ((rc = eval_v7(h, style, E, ep, h->d_vec, false, nullptr, nullptr, &P))) return rc;
+    PeerFinishArgs F{ewald ? S.nkvecs : 0, E.d_cfac, S.rhok[0], S.rhok[1], h->d7_res, ++h->res_seq};
+    k_peer_sum_finish<<<1, 256, 0, h->stream>>>(P, h->d_peer_total, F);
+    LAUNCH_CHECK();
+    double hv[MMC_NSCAL];
+    if ((rc = v7_wait(h, hv))) return rc;
+    if (h->h7_res[MMC_NSCAL + 1] != 0.0) FAIL(MMC_ENCCL, "peer exchange: a rank's partial sums did not arrive");
+    rc = finalize_host(h, style, E, hv, S.rhok[0], S.rhok[1], out);
+    if (rc == 2) {     // declined / overlapping molecules (every rank takes this branch): the whole state, one GPU, general path
+        if ((rc = mmc_upload_positions(h, coords, com))) return rc;
+        EvalCtx E1{1.0, S.box, S.kappa, S.cfac, 0, 1};
+        rc = evaluate_unsharded(h, style, E1, S.rhok[0], S.rhok[1], out);
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
 // this rank's partial sums, pushed into every rank's exchange buffer (asynchronous: returns after the launches)
 int mmc_potential_sharded_begin(mmc_handle *h, int32_t style)
 {
@@ -841,16 +978,21 @@ int mmc_potential_sharded_begin(mmc_handle *h, int32_t style)
     { int rcf = flush_pending(h); if (rcf) return rcf; }
     if ((rc = ensure_vec(h))) return rc;
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
-    if ((rc = evaluate_partial(h, style, E, h->d_vec))) return rc;
     h->peer_epoch += 1;
     const PeerArgs P = peer_args(h);
-    k_peer_push<<<h->cfg.world, 256, 0, h->stream>>>(P, h->d_vec);
-    LAUNCH_CHECK();
+    ErfPoly ep{};
+    if (v7_eligible(h, style, E, ep)) {          // the tail kernel of the evaluation pushes the vector itself
+        if ((rc = eval_v7(h, style, E, ep, h->d_vec, false, nullptr, nullptr, &P))) return rc;
+    } else {
+        if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
+        k_peer_push<<<h->cfg.world, 256, 0, h->stream>>>(P, h->d_vec);
+        LAUNCH_CHECK();
+    }
     h->sharded_pending = true; h->sharded_style = style;
     return MMC_OK;
 }
 
-// wait for every rank's push, add the slots in rank order, finalise
+// wait for every rank's push, add the slots in rank order, finalise (one launch; the scalars arrive in the mapped host slot)
 int mmc_potential_sharded_end(mmc_handle *h, mmc_properties *out)
 {
     if (!h || !out) return MMC_EINVAL;
@@ -858,13 +1000,18 @@ int mmc_potential_sharded_end(mmc_handle *h, mmc_properties *out)
     h->sharded_pending = false;
     const int style = h->sharded_style;
     const PeerArgs P = peer_args(h);
-    k_peer_sum<<<1, 256, 0, h->stream>>>(P, h->d_peer_total, h->d_peer_status);
-    LAUNCH_CHECK();
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
-    int rc = finalize(h, style, E, h->d_peer_total, h->S.rhok[0], h->S.rhok[1], out);
+    PeerFinishArgs F{style == MMC_STYLE_EWALD ? h->S.nkvecs : 0, E.d_cfac, h->S.rhok[0], h->S.rhok[1], h->d7_res, ++h->res_seq};
+    k_peer_sum_finish<<<1, 256, 0, h->stream>>>(P, h->d_peer_total, F);
+    LAUNCH_CHECK();
+    if (h->tm.on && h->last_fast != 7) cudaEventRecord(h->tm.ev[6], h->stream);
+    double hv[MMC_NSCAL];
+    int rc = v7_wait(h, hv);
+    if (rc) return rc;
+    if (h->tm.on) { CK(cudaStreamSynchronize(h->stream)); if (style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side)); }
+    if (h->h7_res[MMC_NSCAL + 1] != 0.0) FAIL(MMC_ENCCL, "peer exchange: a rank's partial sums did not arrive");
+    rc = finalize_host(h, style, E, hv, h->S.rhok[0], h->S.rhok[1], out);
     if (style == MMC_STYLE_EWALD) h->new_valid = false;
-    if (rc < 0) return rc;
-    if (*(volatile int *)h->h_peer_status) FAIL(MMC_ENCCL, "peer exchange: a rank's partial sums did not arrive");   // finalize synchronised the stream
     return rc;
 }
 
@@ -944,14 +1091,21 @@ int mmc_energy_all(mmc_handle *h, int32_t style, double *lj_pot, double *lj_vir,
 int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, int32_t style, mmc_properties *out)
 {
     if (!h) return MMC_EINVAL;
-    int rc = style_check(h, style);
+    int rc = style_check(h, style, false);
     if (rc) return rc;
     if (!coords || !com || !out || style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "bad arguments");
     DevSystem &S = h->S;
     const int nchunk = h->host_chunks;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->cfg.world > 1 && h->peer_ready == h->cfg.world && S.n_sites >= 100000) {       // all ranks call this together
+        EvalCtx Ed{1.0, S.box, S.kappa, S.cfac, h->cfg.rank, h->cfg.world};
+        ErfPoly ep{};
+        h->pair_level = h->pair_floor;
+        if (v7_eligible(h, style, Ed, ep)) return potential_host_sharded(h, coords, com, style, ep, out);
+    }
     if (!h->uniform || h->cfg.world != 1 || S.n_sites < 64 * nchunk || S.n_sites < 100000) {          // small or general systems: the plain sequence
         if ((rc = mmc_upload_positions(h, coords, com))) return rc;
-        return mmc_potential(h, style, out);
+        return h->cfg.world > 1 && h->peer_ready == h->cfg.world ? mmc_potential_sharded(h, style, out) : mmc_potential(h, style, out);
     }
     CK(cudaSetDevice(h->cfg.device));
     if ((rc = ensure_vec(h))) return rc;
@@ -996,6 +1150,8 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     }
     CK(cudaEventRecord(h->ev_join, h->side));
     h->state_version++;                                         // new positions: the cell buckets are rebuilt
+    h->partial_resident = false;
+    h->last_h2d_bytes = (long long)sizeof(double) * 3 * ((long long)S.n_sites + S.n_mol);
     EvalCtx E{1.0, S.box, S.kappa, S.cfac, 0, 1};
     E.wait_sites = h->ev_sites; E.rhok_external = true; E.rhok_blocks = blocks; E.rhok_done = h->ev_join;
     CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1004,6 +1160,13 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
     return rc;
+}
+
+int mmc_last_host_bytes(mmc_handle *h, int64_t *h2d_bytes)
+{
+    if (!h || !h2d_bytes) return MMC_EINVAL;
+    *h2d_bytes = h->last_h2d_bytes;
+    return MMC_OK;
 }
 
 int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t style, mmc_properties *out)

@@ -133,6 +133,11 @@ struct mmc_handle {
     unsigned long long bin_version = 0;             // state the buckets were built from (0: none)
     int bin_ncd = 0, bin_z0 = -1, bin_z1 = -1;
     int v7_ctas_per_sm = 4;
+    unsigned char *d7_need = nullptr, *h7_need = nullptr;     // domain-decomposed host evaluation: molecule blocks this rank reads
+    int need_cap = 0;
+    bool partial_resident = false;                  // after it only those blocks' sites are current on this GPU
+    long long last_h2d_bytes = 0;                   // bytes the last mmc_potential_host moved host -> device on this rank
+    bool v7_left_for_overlap = false;               // k_pairs_v7 handed the state over because molecules overlapped
     int v7_rhok_blocks = 0;                         // CTAs of the last ρ(k) partial launch
     int rhok_split = 1;          // ρ(k) rebuild: CTAs per resident slot (short CTAs let higher-priority kernels in between)
     int pair_floor = 0;          // lowest level the chain may start from (mmc_debug_set "pair_level": A/B tests)
@@ -203,7 +208,7 @@ int ensure_vec(mmc_handle *h);
 int move_tiles(const mmc_handle *h);
 int flush_pending(mmc_handle *h);
 int launch_move_on(mmc_handle *h, const DevSystem &sys, MoveArgs &A, const ErfPoly &poly, bool carry_commit);
-int style_check(mmc_handle *h, int style);
+int style_check(mmc_handle *h, int style, bool need_full_state = true);
 void fill_cfac(const std::vector<int32_t> &kxyz, double kappa, double box, std::vector<double> &cfac);
 void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P);
 // mmc_eval.cu

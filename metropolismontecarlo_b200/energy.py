@@ -91,6 +91,12 @@ class Engine:
         self._ck(self.lib.mmc_potential_host(self.h, _dp(coords), _dp(com), _style(style), C.byref(out)))
         return out
 
+    def last_host_bytes(self) -> int:
+        """Bytes the last potential_host copied host -> device on this rank."""
+        n = C.c_int64()
+        self._ck(self.lib.mmc_last_host_bytes(self.h, C.byref(n)))
+        return n.value
+
     def upload_atoms(self, at: AtomicSystem):
         r = np.ascontiguousarray(at.r, dtype=np.float64)
         e = np.ascontiguousarray(at.eps, dtype=np.float64)
@@ -223,10 +229,9 @@ class Engine:
         self._ck(self.lib.mmc_potential_partial(self.h, _style(style), C.c_void_p(d_partials_ptr)))
 
     def potential_finalize(self, style, d_partials_ptr: int):
-        """Returns Properties, or None when the library asks for the partial pass to be repeated (MMC_RETRY)."""
         out = Properties()
-        rc = self._ck(self.lib.mmc_potential_finalize(self.h, _style(style), C.c_void_p(d_partials_ptr), C.byref(out)))
-        return None if rc == 1 else out
+        self._ck(self.lib.mmc_potential_finalize(self.h, _style(style), C.c_void_p(d_partials_ptr), C.byref(out)))
+        return out
 
     # ---- the sharded evaluation with the exchange over NVLink peer memory (include/mmc_b200.h mmc_peer_*)
     def peer_export(self) -> bytes:
@@ -251,8 +256,8 @@ class Engine:
 
     def potential_sharded_end(self):
         out = Properties()
-        rc = self._ck(self.lib.mmc_potential_sharded_end(self.h, C.byref(out)))
-        return None if rc == 1 else out
+        self._ck(self.lib.mmc_potential_sharded_end(self.h, C.byref(out)))
+        return out
 
     def potential_sharded(self, style) -> Properties:
         out = Properties()

@@ -14,7 +14,7 @@ NSCAL = 8
 
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous share [lo, hi) of n items for `rank` — the same integer formula the library uses
-    for pair units and for sites (mmc_api.cu: n * rank / world)."""
+    for cell layers and for sites (mmc_eval.cu: n * rank / world)."""
     return n * rank // world, n * (rank + 1) // world
 
 
@@ -25,15 +25,11 @@ def partial_len(nkvecs: int) -> int:
 def sharded_potential(eng, style, vec, world: int, group=None):
     """partial → all-reduce (NCCL over NVLink when vec is a CUDA tensor) → finalize.
     `vec` must live on the stream the engine was created with."""
-    for _ in range(4):
-        eng.potential_partial(style, vec.data_ptr())
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(vec, group=group)
-        props = eng.potential_finalize(style, vec.data_ptr())
-        if props is not None:                  # None: MMC_RETRY, every rank switched to the next pair kernel
-            return props
-    raise RuntimeError("sharded potential did not converge on a pair kernel")
+    eng.potential_partial(style, vec.data_ptr())
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(vec, group=group)
+    return eng.potential_finalize(style, vec.data_ptr())
 
 
 def setup_peer_exchange(eng, world: int, group=None):

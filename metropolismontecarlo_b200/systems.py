@@ -295,3 +295,30 @@ def lj_lattice(n: int, rho: float = 0.75, r_cut: float = 2.5) -> AtomicSystem:
     """Config C: InitCubicGrid at rho*, ε=σ=1 (Monatomic/mainMonatomic.jl:343-356)."""
     r, L = init_cubic_grid(n, rho)
     return AtomicSystem(np.ascontiguousarray(r), np.ones(n), np.ones(n), float(L), float(r_cut))
+
+
+def water_ion_mixture(n_mol: int, n_ions: int, rho: float = 0.033101144, seed: int = 11234) -> MolecularSystem:
+    """A mixed topology (what the reference reads from Ewald/topol.top + mea.pdb style inputs: molecules with different site
+    counts, firstAtom/lastAtom per molecule, Ewald/energy.jl:219-226): SPC/E water with `n_ions` of the molecules replaced by
+    single-site ions of alternating charge ±1 e at the molecule's COM.  Three LJ types (O, H, ion; Lorentz-Berthelot mixing as
+    Ewald/structs.jl:342-346, ion: σ = 2.35 Å, ε/k_B = 65 K)."""
+    w = spce_lattice(n_mol, rho, seed)
+    ion_of = np.zeros(n_mol, dtype=bool)
+    ion_of[np.linspace(0, n_mol - 1, n_ions).astype(int)] = True
+    coords, charge, atype, first, last, db = [], [], [], [], [], []
+    sign = 1.0
+    for m in range(n_mol):
+        first.append(len(charge) + 1)
+        if ion_of[m]:
+            coords.append(w.com[m]); charge.append(sign); atype.append(3); db.append(np.zeros(3))
+            sign = -sign
+        else:
+            for a in range(3):
+                coords.append(w.coords[3 * m + a]); charge.append(w.charge[3 * m + a]); atype.append(w.atype[3 * m + a]); db.append(w.db[3 * m + a])
+        last.append(len(charge))
+    e = np.array([SPCE_EPS_O, 0.0, 65.0]); sg = np.array([SPCE_SIGMA_O, 0.0, 2.35])
+    eps = np.sqrt(np.outer(e, e)); sig = 0.5 * (sg[:, None] + sg[None, :])
+    quat = w.quat.copy()
+    quat[ion_of] = np.array([1.0, 0.0, 0.0, 0.0])
+    return MolecularSystem(np.array(coords), np.array(charge), np.array(atype, dtype=np.int64), np.array(first, dtype=np.int64),
+                           np.array(last, dtype=np.int64), w.com.copy(), eps, sig, w.box, np.array(db), quat)

@@ -15,7 +15,7 @@ import pytest
 
 from metropolismontecarlo_b200 import systems
 from oracle import oracle as ora
-from tests.util import ora_ewald, ora_system, rel
+from tests.util import ora_ewald, ora_system, rel  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
@@ -91,7 +91,6 @@ def test_full_size_sharded_sum_equals_unsharded(cfg_e):
     torch.cuda.synchronize()
     total = torch.stack(bufs).sum(0)
     got = engs[3].potential_finalize("ewald", total.clone().data_ptr())
-    assert got is not None
     for f in ("energy", "virial", "coulomb", "lj", "real", "recip", "self_"):
         assert rel(getattr(got, f), getattr(ref, f)) < 1e-11, f
     for e in engs:
@@ -154,3 +153,64 @@ def test_full_size_potential_host(cfg_e):
     for f in fields:
         assert rel(getattr(got, f), getattr(want, f)) < 1e-12, f
     e2.close()
+
+
+def test_config_e_against_full_oracle_golden(cfg_e):
+    """mmc_potential's Properties at config E against ONE full run of the oracle's O(N²) potential() on the same inputs
+    (tests/golden/config_e_properties.json, written by tests/golden/make_config_e.py).  1e-10 relative."""
+    import json
+    from pathlib import Path
+    g = json.loads((Path(__file__).resolve().parent / "golden" / "config_e_properties.json").read_text())
+    ms, eng = cfg_e
+    assert g["n_molecules"] == ms.n_mol and g["box"] == ms.box and g["kappa"] == systems.ALPHA / ms.box
+    p = eng.potential("ewald")
+    assert eng.last_eval_info()["pair_kernel"] == "k_pairs_v7"
+    for f in ("energy", "virial", "coulomb", "lj", "real", "recip", "self_"):
+        assert rel(getattr(p, f), g["ewald"][f]) < 1e-10, (f, getattr(p, f), g["ewald"][f])
+    assert p.overlaps == g["ewald"]["overlaps"] == 0
+    w = eng.potential("wolf")
+    for f in ("energy", "virial", "coulomb", "lj", "real", "wolf_const"):
+        assert rel(getattr(w, f), g["wolf"][f]) < 1e-10, (f, getattr(w, f), g["wolf"][f])
+    for level in (1, 2):                              # the general kernels against the same golden
+        eng.debug_set("pair_level", level)
+        q = eng.potential("ewald")
+        for f in ("energy", "virial", "lj", "real"):
+            assert rel(getattr(q, f), g["ewald"][f]) < 1e-10, (level, f)
+    eng.debug_set("pair_level", 0)
+
+
+def test_config_c_32000_atoms_against_oracle():
+    """Config C at its stated size (BASELINE.json: monatomic LJ, 32 000 atoms, rho* = 0.75, r_cut = 2.5, T* = 1, dr_max = L/30;
+    Monatomic/mainMonatomic.jl:227-289, 373-413): LJ_ΔU rows for sampled atoms, potential(), and a 10⁴-move trajectory through
+    the per-move protocol AND the block-of-moves kernel against the oracle's loop on the reference's own random stream
+    (identical accept/reject record, deltas, final positions)."""
+    from metropolismontecarlo_b200.energy import Engine, julia_rand
+    at = systems.lj_lattice(32000, 0.75, 2.5)
+    assert at.n == 32000 and abs(at.box - 34.9432) < 1e-3
+    rng = np.random.default_rng(11234)
+    at.r[:] = (at.r + rng.normal(0, 0.05, at.r.shape)) % at.box          # off the perfect lattice: a generic configuration
+    eng = Engine()
+    eng.upload_atoms(at)
+    sample = np.unique(np.concatenate([[1, 2, 31999, 32000], rng.integers(1, 32001, 64)]))
+    for i in sample:
+        e, v = eng.LJ_ΔU(int(i))
+        e0, v0 = ora.LJ_dU_atom(int(i), at.r, at.eps, at.sig, at.box, at.r_cut)
+        assert rel(e, e0) < 1e-12 and rel(v, v0) < 1e-12, i
+    p = eng.potential("atoms")
+    e0, v0 = ora.potential_atoms(at.r, at.eps, at.sig, at.box, at.r_cut, 16)
+    assert rel(p.energy, e0) < 1e-11 and rel(p.virial, v0) < 1e-11
+    n_moves = 10_000
+    u = julia_rand(11234, 5 * n_moves)
+    r_o = at.r.copy()
+    rc_o, acc_o, del_o, st_o = ora.loop_atoms(r_o, at.eps, at.sig, at.box, at.r_cut, 1.0, at.box / 30, u, n_moves, e0, v0)
+    assert rc_o == 0 and 0 < st_o.n_accepted < n_moves
+    for device in (False, True):
+        eng.upload_atoms(at)
+        r_g = at.r.copy()
+        rc_g, acc_g, del_g, st_g = eng.loop_run_atoms(1.0, at.box / 30, r_g, u, n_moves, p.energy, p.virial, device=device)
+        assert rc_g == 0 and np.array_equal(acc_g, acc_o), device
+        assert st_g.uniforms_used == st_o.uniforms_used and st_g.n_accepted == st_o.n_accepted
+        assert np.abs(del_g - del_o).max() < 1e-10 * max(1.0, np.abs(del_o).max())
+        assert np.abs(r_g - r_o).max() < 1e-12 and np.abs(eng.download_atoms() - r_o).max() < 1e-12
+        assert rel(st_g.total_energy, st_o.total_energy) < 1e-10
+    eng.close()

@@ -26,7 +26,7 @@ def _worker(rank, world, port, out):
     from metropolismontecarlo_b200.sharding import setup_peer_exchange, sharded_potential
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    ms = systems.spce_lattice(8000)
+    ms = systems.spce_lattice(40000)
     eng = Engine(device=rank, rank=rank, world=world, stream=stream.cuda_stream)
     eng.upload_system(ms, 10.0, 10.0)
     eng.PrepareEwaldVariables(systems.ALPHA / ms.box)
@@ -38,6 +38,10 @@ def _worker(rank, world, port, out):
     vec = torch.zeros(eng.partial_count(), dtype=torch.float64, device=dev)
     q = sharded_potential(eng, "ewald", vec, world)  # the NCCL form of the same evaluation
     res.append((q.energy, q.virial, q.recip, q.real))
+    for _ in range(2):                               # the domain-decomposed host-array form (each rank copies its slab only)
+        d = eng.potential_host(ms.coords, ms.com, "ewald")
+        res.append((d.energy, d.virial, d.recip, d.real))
+    res.append((float(eng.last_host_bytes()), 0.0, 0.0, 0.0))
     np.save(f"{out}.{rank}.npy", np.array(res))
     dist.barrier()
     eng.close()
@@ -57,10 +61,14 @@ def test_peer_exchange_two_processes(tmp_path):
     r0, r1 = np.load(out + ".0.npy"), np.load(out + ".1.npy")
     assert np.array_equal(r0[:3], r1[:3])            # bit-identical totals on both ranks, every repetition
     assert np.array_equal(r0[0], r0[1]) and np.array_equal(r0[0], r0[2])
-    ms = systems.spce_lattice(8000)
+    ms = systems.spce_lattice(40000)
     eng = water_engine(ms, 10.0)
     want = eng.potential("ewald")
     eng.close()
     for k, w in enumerate((want.energy, want.virial, want.recip, want.real)):
         assert abs(r0[0][k] - w) <= 1e-12 * abs(w)
         assert abs(r0[3][k] - w) <= 1e-12 * abs(w)   # NCCL form agrees too
+        assert abs(r0[4][k] - w) <= 1e-12 * abs(w) and abs(r0[5][k] - w) <= 1e-12 * abs(w)   # and the domain-decomposed host form
+    assert np.array_equal(r0[4:6], r1[4:6])
+    full = 24 * (ms.n_sites + ms.n_mol)
+    assert max(r0[6][0], r1[6][0]) < 0.85 * full     # each rank copied its slab, not the whole site array

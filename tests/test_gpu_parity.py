@@ -54,6 +54,67 @@ def test_single_molecule_all_i(c750):
     print("worst single-molecule rel err", worst)
 
 
+def test_single_molecule_rows_against_independent_pin(c750):
+    """The engine's LJ_poly_ΔU(i) / EwaldReal(i) for all 750 molecules against the 40-digit mpmath evaluation of the Julia
+    formulas (tests/golden/realspace_pin_coord750.npz, tests/golden/make_realspace_pin.py) — a pin that does not pass through
+    the C oracle.  Per-move kernel (mmc_lj_mol / mmc_ewald_real) and the all-rows evaluation (mmc_energy_all)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "realspace_pin_coord750.npz")
+    ms, eng = c750
+    lj = np.empty(750); vir = np.empty(750); qq = np.empty(750)
+    for i in range(1, 751):
+        lj[i - 1], vir[i - 1] = eng.LJ_poly_ΔU(i)
+        qq[i - 1], ov = eng.EwaldReal(i)
+        assert ov == bool(g["overlap"][i - 1])
+    for got, want in ((lj, g["lj_pot"]), (vir, g["lj_vir"]), (qq, g["qq_pot"])):
+        scale = np.maximum(np.abs(want), 0.02 * np.abs(want).max())
+        assert (np.abs(got - want) / scale).max() < 1e-12
+    lj2, vir2, qq2, ov2 = eng.energy_all("ewald")
+    for got, want in ((lj2, g["lj_pot"]), (vir2, g["lj_vir"]), (qq2 / systems.FACTOR, g["qq_pot"])):
+        scale = np.maximum(np.abs(want), 0.02 * np.abs(want).max())
+        assert (np.abs(got - want) / scale).max() < 1e-11
+    p = eng.potential("ewald")
+    assert rel(p.lj, g["lj_pot"].sum() / 2) < 1e-12 and rel(p.real, g["qq_pot"].sum() / 2 * systems.FACTOR) < 1e-11
+
+
+def test_reupload_with_a_new_box_rebuilds_cfac():
+    """the k-space tables survive mmc_upload_system, so a re-upload with a different box must rebuild cfac
+    (2π·exp(−b k²)/k²/L with b = 1/(4κ²L²), ewalds.jl:52,78-83) for the new box and drop the resident rho(k)."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.load_nist(1)
+    eng = water_engine(ms, 9.0)
+    kappa = systems.ALPHA / ms.box
+    eng.potential("ewald")
+    ms2 = ms.copy()
+    f = 1.04
+    ms2.box = ms.box * f
+    ms2.com = ms.com * f
+    ms2.coords = ms.coords + np.repeat(ms2.com - ms.com, 3, axis=0)
+    for n_sites_change in (False, True):
+        if n_sites_change:                       # a different molecule count takes the re-allocating branch of the upload
+            keep = ms2.n_mol - 3
+            ms2 = systems.MolecularSystem(ms2.coords[:3 * keep].copy(), ms2.charge[:3 * keep].copy(), ms2.atype[:3 * keep].copy(),
+                                          ms2.first_atom[:keep].copy(), ms2.last_atom[:keep].copy(), ms2.com[:keep].copy(),
+                                          ms2.eps, ms2.sig, ms2.box, ms2.db[:3 * keep].copy(), ms2.quat[:keep].copy())
+        eng.upload_system(ms2, 9.0, 9.0)
+        ew = ora.Ewald(kappa, systems.NK, systems.K_SQ_MAX, systems.FACTOR, ms2.box)      # same kappa, new box
+        k, c = eng.kvectors()
+        assert np.allclose(c, ew.cfac, rtol=1e-15, atol=0)
+        old, new = eng.rhok()
+        assert not old.any() and not new.any()
+        want = ora.potential_ewald(ora_system(ms2), ew, 9.0, 9.0, ms2.box)
+        got = eng.potential("ewald")
+        _check_props(got, want)
+        e0 = ora.RecipLong(ew, ms2.coords, ms2.charge, ms2.box)
+        assert rel(eng.RecipLong(), e0) < 1e-11
+        i = 7
+        sl = slice(3 * (i - 1), 3 * i)
+        t = eng.trial_move(i, ms2.com[i - 1] + 0.1, ms2.coords[sl] + 0.1, "ewald")
+        assert abs(t.d_recip - ora.RecipMove(ms2.box, ew, ms2.coords[sl], ms2.coords[sl] + 0.1, ms2.charge[sl])) < 1e-9 * max(1.0, abs(t.d_recip))
+        eng.reject()
+    eng.close()
+
+
 def test_recip_long_and_self(c750):
     ms, eng = c750
     ew = ora_ewald(ms.box)
@@ -262,18 +323,14 @@ def test_sharded_partials_sum_to_unsharded(c750):
         engs = [water_engine(ms, 10.0, rank=r, world=world) for r in range(world)]
         n = engs[0].partial_count()
         bufs = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in range(world)]
-        for attempt in range(4):
-            for e, b in zip(engs, bufs):
-                e.potential_partial("ewald", b.data_ptr())
-            torch.cuda.synchronize()
-            total = torch.stack(bufs).sum(0)
-            props = []
-            for e in engs:
-                buf = total.clone()
-                props.append(e.potential_finalize("ewald", buf.data_ptr()))
-            assert all(p is None for p in props) or all(p is not None for p in props)
-            if props[0] is not None:
-                break
+        for e, b in zip(engs, bufs):
+            e.potential_partial("ewald", b.data_ptr())
+        torch.cuda.synchronize()
+        total = torch.stack(bufs).sum(0)
+        props = []
+        for e in engs:      # (coord750 has molecules wrapped across the box: k_pairs_v7 declines, every rank sees it in the
+            buf = total.clone()     # summed vector and evaluates the replicated state on the general path — no retry protocol)
+            props.append(e.potential_finalize("ewald", buf.data_ptr()))
         for e, p in zip(engs, props):
             _check_props(p, ref, 1e-12)
             old, _ = e.rhok()
@@ -312,26 +369,31 @@ def npr_pairs_in_cutoff(com, box, rc):
     return tot
 
 
-def test_pair_kernel_variants_agree_with_oracle():
-    """Every pair kernel (v3 water kernel, k_pairs_fast tiles, general k_pairs) on a disordered box:
-    2197 SPC/E molecules, lattice COMs displaced by up to 1.2 Å, so cells are unevenly filled."""
+@pytest.mark.parametrize("amp", [0.35, 1.2])
+def test_pair_kernel_variants_agree_with_oracle(amp):
+    """Every pair kernel (k_pairs_v7, k_pairs_fast tiles, general k_pairs) on a disordered box: 2197 SPC/E molecules, lattice
+    COMs displaced by up to `amp` Å, so cells are unevenly filled.  amp = 1.2 Å makes 59 molecules overlap (ewalds.jl:359-360
+    zeroes their whole rows): k_pairs_v7 must detect that and hand the state to the general path, which implements the rule."""
     from metropolismontecarlo_b200.energy import water_engine
     ms = systems.spce_lattice(2197)
     rng = np.random.default_rng(9)
-    d = rng.uniform(-1.2, 1.2, ms.com.shape)
+    d = rng.uniform(-amp, amp, ms.com.shape)
     newcom = np.clip(ms.com + d, 0.0, ms.box)
     ms.coords = ms.coords + np.repeat(newcom - ms.com, 3, axis=0)
     ms.com = newcom
     s = ora_system(ms)
     want = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
+    assert (want.overlaps > 0) == (amp > 1.0)
     want_pairs = npr_pairs_in_cutoff(ms.com, ms.box, 10.0)
     eng = water_engine(ms, 10.0)
     want_wolf = ora.potential_wolf(s, ora_ewald(ms.box), 10.0, 10.0, ms.box, 8)
-    for level, name in ((0, "k_pairs_v7"), (1, "k_pairs_fast<64>"), (2, "k_pairs")):
+    for level, name in ((0, "k_pairs_v7" if want.overlaps == 0 else "k_pairs_fast<64>"), (1, "k_pairs_fast<64>"), (2, "k_pairs")):
+        eng.upload_system(ms, 10.0, 10.0)              # (an upload resets the kernel chain to the requested level)
         eng.debug_set("pair_level", level)
         got = eng.potential("ewald")
         assert eng.last_eval_info()["pair_kernel"] == name, (level, eng.last_eval_info())
         assert eng.last_eval_info()["pairs_in_cutoff"] == want_pairs
+        assert got.overlaps == want.overlaps
         _check_props(got, want)
         _check_props(eng.potential("wolf"), want_wolf)
     eng.debug_set("pair_level", 0)
@@ -437,13 +499,9 @@ def test_peer_exchange_emulated_ranks(c750):
                 e.peer_import_ptr(r, o.peer_buffer())
         want = ref if msx is ms else None
         for rep in range(3):
-            for attempt in range(8):
-                for e in engs:
-                    e.potential_sharded_begin("ewald")
-                props = [e.potential_sharded_end() for e in engs]
-                assert all(p is None for p in props) or all(p is not None for p in props)
-                if props[0] is not None:
-                    break
+            for e in engs:
+                e.potential_sharded_begin("ewald")
+            props = [e.potential_sharded_end() for e in engs]
             if want is None:
                 single = water_engine(msx, 10.0)
                 want = single.potential("ewald")
@@ -540,7 +598,8 @@ def test_pairs_v7_sparse_box_with_empty_cells():
     ms = systems.spce_lattice(600, rho=0.0025)
     rng = np.random.default_rng(8)
     newcom = ms.com.copy()
-    newcom[:200] = rng.uniform(0.0, 0.3 * ms.box, (200, 3))       # a dense corner ...
+    g = np.stack(np.meshgrid(*(np.arange(6),) * 3, indexing="ij"), -1).reshape(-1, 3)[:200]
+    newcom[:200] = 0.5 + 3.2 * g + rng.uniform(-0.2, 0.2, (200, 3))   # a dense corner (3.2 Å grid: no overlapping molecules) ...
     newcom[200:] = np.clip(ms.com[200:] + rng.uniform(-2, 2, (400, 3)), 0.0, ms.box)
     ms.coords = ms.coords + np.repeat(newcom - ms.com, 3, axis=0)
     ms.com = newcom
@@ -711,3 +770,93 @@ def test_host_register_pins_caller_arrays():
     with pytest.raises(MMCError):
         host_unregister(com)
     eng.close()
+
+
+def test_mixed_topology_water_and_ions():
+    """A non-uniform system (3-site SPC/E + 1-site ions, three LJ types; the reference's routines take per-molecule
+    firstAtom/lastAtom, Ewald/energy.jl:219-226) through mmc_potential (Ewald, Wolf, LJ), the single-molecule entry points,
+    mmc_trial_move and a block of moves of mmc_loop_run, all against the oracle."""
+    from metropolismontecarlo_b200.energy import LoopParams, julia_rand, water_engine
+    ms = systems.water_ion_mixture(512, 40)
+    assert ms.n_sites == 3 * 472 + 40 and ms.eps.shape == (3, 3)
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    eng = water_engine(ms, 10.0)
+    for style, want in (("ewald", ora.potential_ewald(s, ew, 10.0, 10.0, ms.box, 8)), ("wolf", ora.potential_wolf(s, ew, 10.0, 10.0, ms.box, 8))):
+        got = eng.potential(style)
+        _check_props(got, want)
+        assert got.overlaps == want.overlaps
+    kappa = systems.ALPHA / ms.box
+    for i in (1, 2, 13, 14, 256, 511, 512):
+        e, v = eng.LJ_poly_ΔU(i)
+        e0, v0 = ora.LJ_poly_dU(i, s, 10.0, ms.box)
+        p, ov = eng.EwaldReal(i)
+        p0, ov0 = ora.EwaldReal(i, s, kappa, 10.0, ms.box)
+        assert rel(e, e0) < 1e-11 and abs(v - v0) < 1e-10 * max(1.0, abs(v0), abs(e0)) and rel(p, p0) < 1e-10 and ov == ov0, i
+    # a block of moves through the per-move protocol (ions: translations; rotations act on a single site at the COM)
+    p0 = ora.potential_ewald(s, ew, 10.0, 10.0, ms.box, 8)
+    g0 = eng.potential("ewald")
+    u = julia_rand(11234, 8 * 1500)
+    q_o = ms.quat.copy()
+    prm = ora.LoopParams(298.15, 0.3, 0.05, 0.5, 1.0, 10.0, 10.0, ms.box, 0, 1)
+    rc_o, acc_o, del_o, st_o = ora.loop(s, ew, ms.db, q_o, prm, u, 1500, p0.energy, p0.virial)
+    com, quat = ms.com.copy(), ms.quat.copy()
+    rc_g, acc_g, del_g, st_g = eng.loop_run(LoopParams(298.15, 0.3, 0.05, 0.5, 1.0, 0, 1), com, quat, ms.db, u, 1500, g0.energy, g0.virial)
+    assert rc_o == 0 and rc_g == 0 and np.array_equal(acc_g, acc_o) and st_g.uniforms_used == st_o.uniforms_used
+    assert np.abs(del_g - del_o).max() < 1e-9 * max(1.0, np.abs(del_o).max())
+    assert np.abs(com - s.com).max() < 1e-12
+    fresh = eng.potential("ewald")
+    assert rel(st_g.total_energy, fresh.energy) < 1e-9
+    eng.close()
+
+
+@pytest.mark.parametrize("world,order", [(2, "lattice"), (4, "lattice"), (3, "random")])
+def test_domain_decomposed_host_evaluation_emulated_ranks(world, order):
+    """mmc_potential_host on sharded handles (ranks emulated as threads of one process on one GPU): every rank copies all COMs
+    but only the site blocks of its own slab of the cell grid (+ one layer, + its rho(k) share) — less than the whole array for
+    the lattice order, all of it for a random order — and every rank returns the Properties of the unsharded evaluation,
+    bit-identical across ranks.  Afterwards the state is only partially resident: entry points that need all of it refuse."""
+    import threading
+    from metropolismontecarlo_b200.energy import MMCError, water_engine
+    ms = systems.spce_lattice(40000)
+    if order == "random":
+        perm = np.random.default_rng(4).permutation(ms.n_mol)
+        ms.com = ms.com[perm].copy()
+        ms.coords = ms.coords.reshape(-1, 3, 3)[perm].reshape(-1, 3).copy()
+    single = water_engine(ms, 10.0)
+    want = single.potential("ewald")
+    want_w = single.potential("wolf")
+    assert single.last_eval_info()["pair_kernel"] == "k_pairs_v7"
+    single.close()
+    engs = [water_engine(ms, 10.0, rank=r, world=world) for r in range(world)]
+    for e in engs:
+        e.peer_export()
+    for e in engs:
+        for r, o in enumerate(engs):
+            e.peer_import_ptr(r, o.peer_buffer())
+    full = 24 * (ms.n_sites + ms.n_mol)
+    for style, ref in (("ewald", want), ("wolf", want_w), ("ewald", want)):
+        res = [None] * world
+
+        def run(r):
+            res[r] = engs[r].potential_host(ms.coords, ms.com, style)
+        th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=120)
+        assert all(p is not None for p in res)
+        for p in res:
+            _check_props(p, ref, 1e-12)
+            assert p.energy == res[0].energy and p.recip == res[0].recip and p.real == res[0].real
+        got = [e.last_host_bytes() for e in engs]
+        if order == "lattice":
+            assert max(got) < 0.85 * full and all(g >= 24 * ms.n_mol for g in got), (got, full)
+        else:
+            assert max(got) <= full
+    with pytest.raises(MMCError):
+        engs[0].potential("ewald")                      # only a slab of the sites is resident
+    engs[0].upload_positions(ms.coords, ms.com)
+    _check_props(engs[0].potential("ewald"), want, 1e-12)
+    for e in engs:
+        e.close()

@@ -197,6 +197,35 @@ def test_potential_coord750_reference_semantics():
     assert rel(w.virial, p.virial - (p.real + p.recip + p.self_) / 3.0) < 1e-9
 
 
+def test_realspace_rows_against_independent_40_digit_pin():
+    """The oracle's LJ_poly_ΔU(i) and EwaldReal(i) for ALL 750 molecules of coord750 against tests/golden/
+    realspace_pin_coord750.npz: a 40-digit mpmath evaluation written from the Julia source (COM gate, per-site minimum image,
+    +100 window, overlap early return; tests/golden/make_realspace_pin.py), i.e. the exact value of the reference's formula on
+    these float64 inputs.  This pins the real-space erfc and LJ rows — which the reference itself holds no golden numbers
+    for — independently of the C restatement.  1e-13 relative to each row's own magnitude (rows are sums of ~10³ terms of
+    mixed sign; the closest COM-gate call in the file is 4e-6 relative, so no float64 decision can differ)."""
+    g = np.load(Path(__file__).resolve().parent / "golden" / "realspace_pin_coord750.npz")
+    assert float(g["closest_gate_rel"]) > 1e-9 and float(g["closest_overlap_abs"]) > 1e-6
+    ms = systems.load_nist(4)
+    s = ora_system(ms)
+    kappa = systems.ALPHA / ms.box
+    assert kappa == float(g["kappa"]) and ms.box == float(g["box"])
+    lj = np.empty(750); vir = np.empty(750); qq = np.empty(750)
+    for i in range(1, 751):
+        lj[i - 1], vir[i - 1] = ora.LJ_poly_dU(i, s, 10.0, ms.box)
+        qq[i - 1], ov = ora.EwaldReal(i, s, kappa, 10.0, ms.box)
+        assert ov == bool(g["overlap"][i - 1])
+    # a row is a sum of ~1000 terms of mixed sign: compare on the scale of the terms (Σ|term| ~ 50x the typical |row|)
+    for got, want in ((lj, g["lj_pot"]), (vir, g["lj_vir"]), (qq, g["qq_pot"])):
+        scale = np.maximum(np.abs(want), 0.02 * np.abs(want).max())
+        assert (np.abs(got - want) / scale).max() < 1e-13
+    # totals of potential(): Σ rows / 2
+    assert rel(lj.sum() / 2, g["lj_pot"].sum() / 2) < 1e-13
+    assert rel(qq.sum() / 2, g["qq_pot"].sum() / 2) < 1e-12
+    p = ora.potential_ewald(s, ora_ewald(ms.box), 10.0, 10.0, ms.box)
+    assert rel(p.lj, g["lj_pot"].sum() / 2) < 1e-13 and rel(p.real, g["qq_pot"].sum() / 2 * systems.FACTOR) < 1e-12
+
+
 def test_monatomic_potential_vs_numpy():
     at = systems.lj_lattice(343, 0.75, 2.5)
     rng = np.random.default_rng(5)
