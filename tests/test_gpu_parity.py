@@ -91,11 +91,13 @@ def test_reupload_with_a_new_box_rebuilds_cfac():
     ms2.com = ms.com * f
     ms2.coords = ms.coords + np.repeat(ms2.com - ms.com, 3, axis=0)
     for n_sites_change in (False, True):
-        if n_sites_change:                       # a different molecule count takes the re-allocating branch of the upload
-            keep = ms2.n_mol - 3
-            ms2 = systems.MolecularSystem(ms2.coords[:3 * keep].copy(), ms2.charge[:3 * keep].copy(), ms2.atype[:3 * keep].copy(),
-                                          ms2.first_atom[:keep].copy(), ms2.last_atom[:keep].copy(), ms2.com[:keep].copy(),
-                                          ms2.eps, ms2.sig, ms2.box, ms2.db[:3 * keep].copy(), ms2.quat[:keep].copy())
+        if n_sites_change:                       # a different molecule count takes the re-allocating branch of the upload,
+            keep = ms2.n_mol - 3                 # and the box changes once more
+            g = 0.98
+            com2 = ms2.com[:keep] * g
+            ms2 = systems.MolecularSystem(ms2.coords[:3 * keep] + np.repeat(com2 - ms2.com[:keep], 3, axis=0), ms2.charge[:3 * keep].copy(),
+                                          ms2.atype[:3 * keep].copy(), ms2.first_atom[:keep].copy(), ms2.last_atom[:keep].copy(), com2,
+                                          ms2.eps, ms2.sig, ms2.box * g, ms2.db[:3 * keep].copy(), ms2.quat[:keep].copy())
         eng.upload_system(ms2, 9.0, 9.0)
         ew = ora.Ewald(kappa, systems.NK, systems.K_SQ_MAX, systems.FACTOR, ms2.box)      # same kappa, new box
         k, c = eng.kvectors()
