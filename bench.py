@@ -32,10 +32,17 @@ UNIT = "evals/s"
 N_MOL_E = 256_000
 RC = 10.0
 FLOP_PER_PAIR = 624          # 9 x 67 + 21 per in-cutoff water-water pair
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on config E at N=1, from the
-# `ncu --set full` capture summarised in profiles/r01_v6_ncu_full_pairs_and_rhok.txt (a profiler number is never
-# taken inside bench.py; the algorithmic bytes are the 35 MB of state, read once)
-NCU_DRAM_BYTES = {"k_pairs_v6": 30271488, "k_pairs_v5": 34369280, "k_pairs_v4": 34369280}
+FLOP_PER_SITE_K = 14         # rho(k) rebuild, 14 flop per (site, k) + 168 per site + 6 per k
+# From the committed `ncu --set full` capture of the same command line (profiles/r02_ncu_full_eval_kernels.txt): DRAM bytes of ONE
+# launch (dram__bytes_read.sum + dram__bytes_write.sum) and the executed-instruction counters.  A profiler number is never taken
+# inside bench.py; these are the capture's values, quoted so that the line carries them, and only for the configuration the
+# capture was made on (config E, one GPU).  Algorithmic bytes: 43 MB of rows + gate coordinates read once (L2-resident).
+NCU_CAPTURE = {
+    "k_pairs_v7": {"dram_bytes": 44416512, "fp64_pipe_busy_pct": 49.1, "issue_slots_busy_pct": 60.9, "fp64_instructions_per_pair": 203,
+                   "warp_instructions": 312.2e6, "source": "profiles/r02_ncu_full_eval_kernels.txt"},
+    "k_rhok_pairs": {"dram_bytes": 24606720, "fp64_pipe_busy_pct": 55.1, "issue_slots_busy_pct": 39.6,
+                     "source": "profiles/r02_ncu_full_eval_kernels.txt"},
+}
 
 
 def workload_config(n_mol):
@@ -44,9 +51,11 @@ def workload_config(n_mol):
                     "rho=0.033101144 A^-3 with random quaternions (seed 11234); full Ewald potential(): "
                     "r_cut=10 A COM cutoff, kappa=5.6/L, nk=5, k^2<27 (337 k-vectors)",
         "n_molecules": n_mol,
-        "l2": "flushed between timed steps (256 MiB device write); state itself (35 MB) is L2-sized",
-        "sharding": "pair work units (cell pairs) and rho(k) sites split per rank; the 682-double partial vectors are exchanged "
-                    "peer to peer over NVLink (CUDA IPC buffers, k_peer_push/k_peer_sum) or, with --collective nccl, by one all-reduce",
+        "l2": "flushed before every timed evaluation (256 MiB device write); state itself (35 MB) is L2-sized",
+        "step": "one step = --evals-per-step evaluations (default 10), each timed with CUDA events on the launching stream",
+        "sharding": "z-slabs of the cell grid (pair work) and rho(k) sites split per rank; the 682-double partial vectors are exchanged "
+                    "peer to peer over NVLink (CUDA IPC buffers; the evaluation's tail kernel pushes, k_peer_sum_finish sums) or, with "
+                    "--collective nccl, by one all-reduce",
     }
 
 
@@ -157,7 +166,7 @@ def run_reference(args, rank):
     emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(ms.n_mol),
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(workload_config(ms.n_mol), evals_per_step=args.evals_per_step),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sample_wall_s": wall,
@@ -211,7 +220,7 @@ def moves_benchmarks(n_moves=10_000):
                                                    u, n_moves, p0.energy, p0.virial, device=True)
         dt_dev = time.perf_counter() - t0
         assert np.array_equal(acc, acc_d), "device block of moves diverged from the per-move protocol"
-        out[name] = {"moves_per_s": n_moves / dt, "us_per_move": 1e6 * dt / n_moves, "accepted": int(st.n_accepted),
+        out[name] = {"moves_per_s": n_moves / dt, "us_per_move": 1e6 * dt / n_moves, "accepted": int(st.n_accepted), "_acc_sum": int(acc_d.sum()),
                      "gpu_launches": int(launches), "cpu_port_moves_per_s_1core": n_cpu / dtc,
                      "flop_per_move": 2.1e5 if sid == 0 else 1.75e5,
                      "block_offload": {"moves_per_s": n_moves / dt_dev, "us_per_move": 1e6 * dt_dev / n_moves,
@@ -334,6 +343,55 @@ def replica_moves(local_rank, world, dev, n_moves=10_000):
                     "uniforms H2D + results D2H inside the timed region, max over ranks"}
 
 
+def replicas_one_gpu(n_rep=15, n_moves=10_000, cluster=8):
+    """Per-move paths do not shard, and one chain uses 8 of the 148 SMs (k_chains: one 8-CTA cluster).  So ONE GPU runs R
+    independent replicas of config A at once: R handles, R streams, R host threads (what R Julia processes sharing a GPU would
+    do); aggregate moves/s = R x n_moves / wall time of the slowest.  Replica 0 runs the stream of the single-chain leg and must
+    give the same accept/reject record."""
+    import threading
+    from metropolismontecarlo_b200 import systems
+    from metropolismontecarlo_b200.energy import LoopParams, water_engine
+    ms = systems.load_nist(4)
+    prm = LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 0, 1)
+    engs = [water_engine(ms, RC) for _ in range(n_rep)]
+    for e in engs:
+        e.debug_set("chain_cluster", cluster)
+    us = [np.random.default_rng(11234).random(8 * n_moves) if r == 0 else np.random.default_rng(11234 + r).random(8 * n_moves) for r in range(n_rep)]
+    out = [None] * n_rep
+    walls = []
+    for rep in range(3):                       # first round untimed (kernel load, buffer allocation)
+        p0s = []
+        for e in engs:
+            e.upload_system(ms, RC, RC)
+            p0s.append(e.potential("ewald"))
+        start = threading.Barrier(n_rep + 1)
+
+        def run(r):
+            com, quat = ms.com.copy(), ms.quat.copy()
+            start.wait()
+            out[r] = engs[r].loop_run(prm, com, quat, ms.db, us[r], n_moves, p0s[r].energy, p0s[r].virial, device=True)
+        th = [threading.Thread(target=run, args=(r,)) for r in range(n_rep)]
+        for t in th:
+            t.start()
+        start.wait()
+        t0 = time.perf_counter()
+        for t in th:
+            t.join()
+        if rep > 0:
+            walls.append(time.perf_counter() - t0)
+    for r in range(n_rep):
+        fresh = engs[r].potential("ewald")
+        assert out[r][0] == 0 and abs(out[r][3].total_energy - fresh.energy) <= 1e-9 * abs(fresh.energy)
+    acc0 = out[0][1].copy()
+    for e in engs:
+        e.close()
+    best = min(walls)
+    return {"moves_per_s": n_rep * n_moves / best, "replicas": n_rep, "us_per_move_per_replica": 1e6 * best / n_moves,
+            "sms_per_chain": cluster,
+            "what": f"config A, {n_rep} independent chains on ONE GPU (k_chains: a {cluster}-SM cluster each), one host thread and one "
+                    "stream per chain; uniforms H2D + results D2H inside the timed region"}, acc0
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -376,7 +434,9 @@ def run_ours(args, rank, world, local_rank):
             args.collective = "nccl"
 
     def step():
-        if p2p:    # partial -> each rank stores its 682 doubles into every peer's buffer over NVLink -> ordered sum -> finalize
+        if world == 1:
+            return eng.potential("ewald")
+        if p2p:    # partial -> the tail kernel stores the 682 doubles into every peer's buffer over NVLink -> ordered sum -> Properties
             return eng.potential_sharded("ewald")
         # partial -> NCCL all-reduce over NVLink (8 scalars + 337 complex rho(k)) -> finalize
         return sharded_potential(eng, "ewald", vec, world)
@@ -388,19 +448,26 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         props = step()
-    fp64_peak = eng.measure_fp64_peak() if rank == 0 else 0.0
+    fp64_peak, peak_clock = (0.0, None)
+    if rank == 0:
+        cs = ClockSampler(local_rank)
+        cs.start()
+        fp64_peak = eng.measure_fp64_peak()
+        peak_clock = cs.stop()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     eng.set_timing(True)
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    inner = max(1, args.evals_per_step)
+    n_ev = args.steps * inner
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
     l0 = eng.counters().kernel_launches
     pair_ms, rhok_ms = [], []
     barrier()
     if sampler:
         sampler.start()
-    for k in range(args.steps):
-        flush.fill_(k & 0xff)                          # evict the 126 MB L2 between timed steps
+    for k in range(n_ev):
+        flush.fill_(k & 0xff)                          # evict the 126 MB L2 before every timed evaluation
         ev0[k].record()
         props = step()
         ev1[k].record()
@@ -410,14 +477,15 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = eng.counters().kernel_launches - l0
-    # the dominant kernel alone (rho(k) rebuild NOT running beside it), outside the timed region: explains `roofline`
+    # the two big kernels alone (rho(k) rebuild NOT running beside the pair kernel), outside the timed region: explains `roofline`
     eng.debug_set("overlap_rhok", 0)
-    iso = []
-    for _ in range(5):
+    iso, iso_r = [], []
+    for _ in range(7):
         step()
         iso.append(eng.last_timings()["pairs_ms"])
+        iso_r.append(eng.last_timings()["rhok_ms"])
     eng.debug_set("overlap_rhok", 1)
-    pair_ms_isolated = float(np.median(iso))
+    pair_ms_isolated, rhok_ms_isolated = float(np.median(iso)), float(np.median(iso_r))
     eng.set_timing(False)
     total_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -425,34 +493,37 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)       # max over ranks, device-timed
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = 1e3 / ms_per_step
+    value = 1e3 * inner / ms_per_step
     info = eng.last_eval_info()
+    # sharded == unsharded, outside the timed region: every rank evaluates the whole (replicated) system itself once
+    sharded_rel = None
+    if world > 1:
+        whole = eng.potential("ewald")
+        sharded_rel = max(abs(getattr(props, f) - getattr(whole, f)) / abs(getattr(whole, f)) for f in ("energy", "virial", "lj", "real", "recip"))
+        assert sharded_rel < 1e-11, f"sharded evaluation differs from the unsharded one: {sharded_rel}"
 
-    # ---- e2e: host arrays in, host scalars out, every step (upload + evaluate).  The inputs are the
-    # reference's own array layouts held in PINNED host memory; the library DMAs them as they are.
+    # ---- e2e: host arrays in, host scalars out, every step.  The inputs are the reference's own array layouts (pointer(soa.coords),
+    # pointer(moa.COM)) in PINNED host memory; mmc_potential_host DMAs them as they are.  One rank: copies overlapped with binning and
+    # the rho(k) rebuild.  N ranks: domain decomposition — a rank copies all COMs but only the site blocks of its slab of the cell grid.
     ms_pin = ms.copy()
-    for name in ("coords", "charge", "atype", "first_atom", "last_atom", "com"):
+    for name in ("coords", "com"):
         setattr(ms_pin, name, torch.from_numpy(np.ascontiguousarray(getattr(ms, name))).pin_memory().numpy())
-    def e2e_step():        # what changes between evaluations are the positions: coordinates + COMs from pinned host memory
-        if world == 1:     # one call, copies overlapped with binning and the rho(k) rebuild (mmc_potential_host)
-            return eng.potential_host(ms_pin.coords, ms_pin.com, "ewald")
-        eng.upload_positions(ms_pin.coords, ms_pin.com)
-        return step()
-    for _ in range(2):
-        e2e_step()
+    for _ in range(3):
+        p2 = eng.potential_host(ms_pin.coords, ms_pin.com, "ewald")
+    h2d = eng.last_host_bytes()
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(3, min(args.steps, 10))
+    n_e2e = max(10, min(n_ev, 50))
     for _ in range(n_e2e):
-        p2 = e2e_step()
+        p2 = eng.potential_host(ms_pin.coords, ms_pin.com, "ewald")
     barrier()
     e2e_s = (time.perf_counter() - t0) / n_e2e
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([e2e_s, float(h2d)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    h2d = ms.n_sites * 24 + ms.n_mol * 24
+    e2e_s, h2d_max = float(t[0].item()), int(t[1].item())
     assert abs(p2.energy - props.energy) <= 1e-12 * abs(props.energy)
+    eng.upload_positions(ms.coords, ms.com)            # (a sharded handle holds only its slab after potential_host)
 
     replicas = replica_moves(local_rank, world, dev) if (world > 1 and not args.no_moves) else None
     if rank == 0:
@@ -461,29 +532,45 @@ def run_ours(args, rank, world, local_rank):
         # algorithmic FP64 flops of the dominant kernel for THIS rank's share of the pairs
         alg_flops = FLOP_PER_PAIR * pairs / world
         achieved = alg_flops / t_pair / 1e12
+        nk = eng.nkvecs
+        rhok_flops = (FLOP_PER_SITE_K * nk + 168) * ms.n_sites / world + 6 * nk
+        t_rhok = float(np.mean(rhok_ms)) * 1e-3
+        cap = NCU_CAPTURE.get(info["pair_kernel"]) if (world == 1 and ms.n_mol == N_MOL_E) else None
+        cap_r = NCU_CAPTURE.get("k_rhok_pairs") if (world == 1 and ms.n_mol == N_MOL_E) else None
+        peak_src = ("live DFMA-chain probe on this GPU before the timed region (MEASURED_PEAKS.json has no FP64 figure); nominal "
+                    "148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(ms.n_mol),
+            "config": dict(workload_config(ms.n_mol), evals_per_step=inner),
+            "ms_per_eval": ms_per_step / inner,
             "energy_per_molecule_K": props.energy / ms.n_mol,
+            "sharded_vs_unsharded_rel": sharded_rel,
             "pairs_in_cutoff": pairs, "path": info["mode"], "cells_per_dim": info["cells_per_dim"],
             "kernel_ms": {"pairs": float(np.mean(pair_ms)), "rhok_rebuild": float(np.mean(rhok_ms))},
             "roofline": {"bound": "fp64", "kernel": info["pair_kernel"], "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                         "peak_source": "live DFMA-chain probe on this GPU (MEASURED_PEAKS.json has no FP64 figure); "
-                                        "nominal 37.2 TFLOP/s at 1965 MHz",
+                         "peak_source": peak_src, "peak_probe_clocks": peak_clock,
                          "algorithmic_flop_per_launch": alg_flops,
                          "note": "achieved/frac are in situ (timed region, rho(k) rebuild running beside the pair kernel on a side stream)",
                          "isolated": {"ms": pair_ms_isolated, "achieved": alg_flops / (pair_ms_isolated * 1e-3) / 1e12,
                                       "frac": (alg_flops / (pair_ms_isolated * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None},
-                         "executed": {"fp64_instructions_per_pair": 204, "fp64_pipe_busy_pct": 41.6, "issue_slots_busy_pct": 64.4,
-                                      "source": "ncu --set full, profiles/r01_v6c_ncu_full_pairs_tickets.txt (static, not re-measured per run)"},
-                         "traffic": NCU_DRAM_BYTES.get(info["pair_kernel"]) if world == 1 and ms.n_mol == N_MOL_E else None,
-                         "traffic_unit": "bytes of DRAM per launch (ncu, profiles/r01_v6c_ncu_full_pairs_tickets.txt)"},
-            "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
-                    "what": "N=1: mmc_potential_host (pinned host soa.coords + moa.COM in, Properties out, copies overlapped with compute); "
-                            "N>1: mmc_upload_positions + sharded potential"},
+                         "executed": cap,
+                         "traffic": cap["dram_bytes"] if cap else None,
+                         "traffic_unit": "bytes of DRAM per launch (ncu capture named in `executed.source`; null when this run is not the captured configuration)"},
+            "roofline_rhok": {"bound": "fp64", "kernel": "k_rhok_pairs", "achieved": rhok_flops / t_rhok / 1e12 if t_rhok > 0 else None,
+                              "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": (rhok_flops / t_rhok / 1e12 / fp64_peak) if (fp64_peak and t_rhok > 0) else None,
+                              "algorithmic_flop_per_launch": rhok_flops,
+                              "isolated": {"ms": rhok_ms_isolated,
+                                           "frac": (rhok_flops / (rhok_ms_isolated * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and rhok_ms_isolated > 0) else None},
+                              "executed": cap_r, "traffic": cap_r["dram_bytes"] if cap_r else None},
+            "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_max, "d2h_bytes_per_step": 72,
+                    "evaluations_timed": n_e2e,
+                    "what": "mmc_potential_host: pinned host soa.coords + moa.COM in, Properties out, wall clock, max over ranks.  N=1: all "
+                            "24.6 MB, copies overlapped with binning and the rho(k) rebuild.  N>1: domain decomposition, every rank copies all "
+                            "COMs and only the site blocks of its slab of the cell grid (h2d_bytes_per_step = the largest rank's bytes)"},
             "gpu_launches": int(launches) * world,
             "collective": (args.collective if world > 1 else None),
             "clocks": clocks,
@@ -500,6 +587,15 @@ def run_ours(args, rank, world, local_rank):
                           "linearly; Julia is not installed, so this is the C restatement of the reference algorithm"}
             if not args.no_moves:
                 line["moves"] = moves_benchmarks()
+                line["moves"]["B_spce750_wolf"].pop("_acc_sum", None)
+                try:
+                    rep, acc0 = replicas_one_gpu(15, 10_000, 8)
+                    rep["same_record_as_single_chain"] = bool(line["moves"]["A_spce750_ewald"].pop("_acc_sum") == int(acc0.sum()))
+                    line["moves"]["A_spce750_ewald"]["replicas_one_gpu"] = rep
+                    line["moves"]["A_spce750_ewald"]["replicas_one_gpu_2sm"] = replicas_one_gpu(64, 10_000, 2)[0]
+                except Exception as e:           # (never lose the line to the optional leg)
+                    line["moves"]["A_spce750_ewald"]["replicas_one_gpu"] = {"error": str(e)}
+                line["moves"]["A_spce750_ewald"].pop("_acc_sum", None)
         if replicas is not None:
             line["moves"] = {"A_spce750_ewald_replicas": replicas}
         emit(line)
@@ -536,6 +632,8 @@ def _main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--molecules", type=int, default=N_MOL_E)
+    ap.add_argument("--evals-per-step", dest="evals_per_step", type=int, default=10,
+                    help="evaluations per step (each preceded by an L2 flush and timed with its own pair of CUDA events)")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="exchange of the partial sums at N > 1: NVLink peer-memory kernels (default) or an NCCL all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -20,6 +20,25 @@
 
 using namespace mmc_detail;
 
+#include <map>
+#include <mutex>
+namespace {
+// cudaFuncSetAttribute on a kernel that has launches in flight makes the driver wait for them: with one call per block of
+// moves, chains of different handles (streams) ran one after the other (measured: 16 replicas on one GPU at 2x the rate of one).
+// The opt-in shared-memory size is therefore raised once per kernel and only when a launch needs more than what is set.
+cudaError_t ensure_smem_optin(const void *func, int bytes)
+{
+    static std::mutex mtx;
+    static std::map<const void *, int> set;
+    std::lock_guard<std::mutex> g(mtx);
+    auto it = set.find(func);
+    if (it != set.end() && it->second >= bytes) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) set[func] = bytes;
+    return e;
+}
+}  // namespace
+
 namespace {
 
 struct UStream {
@@ -256,7 +275,7 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
 #define MMC_CHAIN_LAUNCH(SS, DD)                                                                                     \
     if (C > 1) {                                                                                                     \
         auto kern = sliced ? k_chains<SS, DD, true> : k_chains<SS, DD, false>;                                        \
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+        CK(ensure_smem_optin((const void *)kern, (int)smem));                      \
         cudaLaunchConfig_t lc{};                                                                                     \
         lc.gridDim = dim3(C); lc.blockDim = dim3(CHAINC_THREADS); lc.dynamicSmemBytes = smem; lc.stream = h->stream; \
         cudaLaunchAttribute at[1];                                                                                   \
@@ -265,7 +284,7 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
         lc.attrs = at; lc.numAttrs = 1;                                                                              \
         CK(cudaLaunchKernelEx(&lc, kern, h->S, A, h->move_poly));                                                    \
     } else {                                                                                                         \
-        CK(cudaFuncSetAttribute(k_chain<SS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        CK(ensure_smem_optin((const void *)k_chain<SS, DD>, (int)smem));           \
         k_chain<SS, DD><<<1, CHAIN_THREADS, smem, h->stream>>>(h->S, A, h->move_poly);                               \
     }
     const int deg = A.style_qq ? h->move_poly.deg : 0;
@@ -410,8 +429,11 @@ extern "C" int mmc_loop_run_atoms_device(mmc_handle *h, double temperature, doub
         A.gate_rc2f = std::nextafterf((float)(rcut * rcut + margin), INFINITY);
     }
     A.uniforms = d; A.delta = d + off_delta; A.out = reinterpret_cast<ChainOut *>(d + off_out); A.accepted = d_acc;
-    CK(cudaFuncSetAttribute(k_chain_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (C > 8 && cudaFuncSetAttribute(k_chain_atoms, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    CK(ensure_smem_optin((const void *)k_chain_atoms, (int)smem));
+    static int nonportable_ok = -1;          // (set once: see ensure_smem_optin)
+    if (C > 8 && nonportable_ok < 0)
+        nonportable_ok = cudaFuncSetAttribute(k_chain_atoms, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 1 : 0;
+    if (C > 8 && !nonportable_ok) {
         cudaGetLastError();
         C = CHAINC_MAXC;
     }

@@ -299,3 +299,42 @@ def test_device_loop_config_d_4000_molecules():
     assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][2] == outs[1][2] and abs(outs[0][3] - outs[1][3]) < 1e-12
     assert np.abs(outs[0][1] - outs[1][1]).max() < 1e-6 * max(1.0, np.abs(outs[0][1]).max())
     assert np.abs(outs[0][4] - outs[1][4]).max() < 1e-11 and np.abs(outs[0][5] - outs[1][5]).max() < 1e-11
+
+
+def test_concurrent_replicas_on_one_gpu_match_their_oracle_runs():
+    """Per-move paths do not shard (replicas only), and one chain uses 8 of 148 SMs: several independent chains run
+    at once on ONE GPU (one handle, stream and host thread each).  Every replica's accept/reject record, stream consumption and
+    final COMs must equal the oracle's Loop() on that replica's own uniform stream."""
+    import threading
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.load_nist(4)
+    n_rep, n_moves = 6, 3000
+    us = [julia_rand(11234 + r, 8 * n_moves) for r in range(n_rep)]
+    engs = [water_engine(ms, 10.0) for _ in range(n_rep)]
+    p0 = [e.potential("ewald") for e in engs]
+    res = [None] * n_rep
+
+    def run(r):
+        com, quat = ms.com.copy(), ms.quat.copy()
+        out = engs[r].loop_run(LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 0, 1), com, quat, ms.db, us[r], n_moves,
+                               p0[r].energy, p0[r].virial, device=True)
+        res[r] = (out, com)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(n_rep)]
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join(timeout=300)
+    for r in range(n_rep):
+        s = ora_system(ms)
+        ew = ora_ewald(ms.box)
+        w0 = ora.potential_ewald(s, ew, 10.0, 10.0, ms.box)
+        prm = ora.LoopParams(298.15, 0.316555789, 0.05, 0.5, 1.0, 10.0, 10.0, ms.box, 0, 1)
+        rc_o, acc_o, del_o, st_o = ora.loop(s, ew, ms.db, ms.quat.copy(), prm, us[r], n_moves, w0.energy, w0.virial)
+        (rc_g, acc_g, del_g, st_g), com = res[r]
+        assert rc_g == 0 and rc_o == 0 and np.array_equal(acc_g, acc_o), r
+        assert st_g.uniforms_used == st_o.uniforms_used and st_g.n_accepted == st_o.n_accepted
+        assert np.abs(com - s.com).max() < 1e-12
+        assert rel(st_g.total_energy, engs[r].potential("ewald").energy) < 1e-9
+    assert len({tuple(res[r][0][1][:200]) for r in range(n_rep)}) == n_rep       # different streams, different records
+    for e in engs:
+        e.close()
