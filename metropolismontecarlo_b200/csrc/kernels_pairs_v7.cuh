@@ -92,10 +92,23 @@ constexpr size_t V7_SMEM = (size_t)(V7_CAP + V7_BCAP) * V7_ROW * sizeof(double) 
 // ---- extended grid: real cell (cx, cy, cz) is extended cell (cx+1, cy+1, cz); ghosts at x,y = 0 / ncd+1 and z = ncd
 struct V7Grid {
     int ncd, EX, EY;       // EX = EY = ncd + 2; extended layers ez = 0 .. ncd
-    int z0, z1;            // this rank's home layers [z0, z1); it reads layers z0 .. z1 (z1 == ncd: the ghost of layer 0)
+    int rank, world;
+    // This rank's home cells are the contiguous range [range[rank], range[rank + 1]) of the real cells in (z, y, x) order —
+    // k_partition7 cuts the order into `world` ranges of equal estimated pair work from the cell populations, on the device,
+    // identically on every rank.  (One rank: {0, ncd³}.)
+    const int *range;
     double edge;           // box_new / ncd
     double box_new;
 };
+// extended row (ez * EY + ey) of a real cell index, and which extended rows a rank with home cells [c0, c1) reads: the rows
+// of its home cells and the next one (slots (·,0,0), (·,+1,0)), and the three rows around them one layer up (slots (·,−1..+1,+1))
+__device__ __forceinline__ int v7_ext_row(const V7Grid &G, int c) { const int n = G.ncd; return (c / (n * n)) * G.EY + ((c / n) % n) + 1; }
+__device__ __forceinline__ bool v7_row_needed(const V7Grid &G, int R, int c0, int c1)
+{
+    if (c1 <= c0) return false;
+    const int Ra = v7_ext_row(G, c0), Rb = v7_ext_row(G, c1 - 1);
+    return (R >= Ra && R <= Rb + 1) || (R >= Ra + G.EY - 1 && R <= Rb + G.EY + 1);
+}
 __host__ __device__ __forceinline__ int v7_ext_cells(const V7Grid &G) { return G.EX * G.EY * (G.ncd + 1); }
 
 struct Bin7Args {
@@ -105,7 +118,7 @@ struct Bin7Args {
     V7Grid G;
     int *count;            // [ncd³] (zeroed)
     int *bucket;           // [ncd³][V7_CAP]
-    unsigned char *need;   // optional [ceil(n_mol / 256)] (zeroed): set for every block of 256 molecules that holds one this rank reads
+    int *cell_of;          // optional [n_mol]: the molecule's cell (k_need7)
 };
 
 // one thread per molecule: cell of its COM, slot by arrival (k_gather7 orders the members afterwards)
@@ -116,12 +129,76 @@ static __global__ void k_bin7(Bin7Args A)
     const double4 c = A.com[m];
     const int n = A.G.ncd;
     const int cx = cell_coord(c.x, A.inv_cell, n), cy = cell_coord(c.y, A.inv_cell, n), cz = cell_coord(c.z, A.inv_cell, n);
-    const bool needed = (cz >= A.G.z0 && cz <= A.G.z1) || (A.G.z1 == n && cz == 0);
-    if (!needed) return;
-    if (A.need) A.need[m >> 8] = 1;
     const int id = cx + n * (cy + n * cz);
+    if (A.cell_of) A.cell_of[m] = id;
     const int pos = atomicAdd(&A.count[id], 1);
     if (pos < V7_CAP) A.bucket[(size_t)id * V7_CAP + pos] = m;
+}
+
+// Cuts the (z, y, x) order of the cells into `world` contiguous ranges of equal estimated pair work: the work of home cell c is
+// n_c · (n_c + Σ populations of its 13 half-shell neighbours) — the gate tests, to which the survivors are proportional at uniform
+// density.  One CTA; deterministic, so every rank computes the same boundaries from the same (replicated) COMs.
+static __global__ void __launch_bounds__(1024) k_partition7(const int *__restrict__ count, int n, int world, int *range)
+{
+    __shared__ unsigned long long s_part[1024];
+    __shared__ unsigned long long s_total;
+    const int tid = threadIdx.x, ncell = n * n * n;
+    const int per = (ncell + 1023) / 1024;
+    const int lo = min(ncell, tid * per), hi = min(ncell, lo + per);
+    auto cost = [&](int c) -> unsigned long long {
+        const int cx = c % n, cy = (c / n) % n, cz = c / (n * n);
+        const int nc = min(count[c], V7_CAP);
+        int nb = 0;
+        for (int s = 0; s < 14; ++s) {
+            int x = cx + c_half_shell[s][0], y = cy + c_half_shell[s][1], z = cz + c_half_shell[s][2];
+            x = x < 0 ? x + n : (x >= n ? x - n : x); y = y < 0 ? y + n : (y >= n ? y - n : y); z = z >= n ? z - n : z;
+            nb += min(count[x + n * (y + n * z)], V7_CAP);
+        }
+        return (unsigned long long)nc * nb + 64ull;     // (+ a constant per cell: the per-unit overhead of nearly empty cells)
+    };
+    unsigned long long mine = 0;
+    for (int c = lo; c < hi; ++c) mine += cost(c);
+    s_part[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (int t = 0; t < 1024; ++t) { const unsigned long long v = s_part[t]; s_part[t] = run; run += v; }
+        s_total = run;
+        range[0] = 0; range[world] = ncell;
+    }
+    __syncthreads();
+    // boundary r is the first cell whose prefix reaches total · r / world: found by the thread whose share contains it
+    unsigned long long run = s_part[tid];
+    for (int c = lo; c < hi; ++c) {
+        const unsigned long long nxt = run + cost(c);
+        for (int r = 1; r < world; ++r) {
+            const unsigned long long target = s_total / world * r;
+            if (run < target && nxt >= target) range[r] = c + 1;
+        }
+        run = nxt;
+    }
+}
+
+// domain-decomposed host evaluation: which blocks of 256 molecules hold a molecule this rank reads (its home range, the
+// half shell around it, the ghost images included)
+static __global__ void k_need7(const int *__restrict__ cell_of, int n_mol, V7Grid G, unsigned char *need)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mol) return;
+    const int c0 = G.range[G.rank], c1 = G.range[G.rank + 1];
+    const int n = G.ncd, c = cell_of[m];
+    const int cy = (c / n) % n, cz = c / (n * n);
+    bool nd = false;
+    // the molecule's rows in the extended grid: its own, the y-ghost (cy = 0 -> row n+1, cy = n-1 -> row 0), the z-ghost layer n
+#pragma unroll
+    for (int gz = 0; gz < 2; ++gz) {
+        if (gz == 1 && cz != 0) continue;
+        const int ez = gz ? n : cz;
+        nd |= v7_row_needed(G, ez * G.EY + cy + 1, c0, c1);
+        if (cy == 0) nd |= v7_row_needed(G, ez * G.EY + n + 1, c0, c1);
+        if (cy == n - 1) nd |= v7_row_needed(G, ez * G.EY + 0, c0, c1);
+    }
+    if (nd) need[m >> 8] = 1;
 }
 
 struct Gather7Args {
@@ -146,11 +223,11 @@ static __global__ void __launch_bounds__(256) k_gather7(Gather7Args A)
     const int wcell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const V7Grid &G = A.G;
     const int per_layer = G.EX * G.EY;
-    const int n_layers = G.z1 - G.z0 + 1;
-    if (wcell >= per_layer * n_layers) return;
-    const int ez = G.z0 + wcell / per_layer, rem = wcell - (wcell / per_layer) * per_layer;
+    if (wcell >= per_layer * (G.ncd + 1)) return;
+    const int ez = wcell / per_layer, rem = wcell - ez * per_layer;
     const int ey = rem / G.EX, ex = rem - ey * G.EX;
-    const int e = ex + G.EX * (ey + G.EY * ez);
+    if (G.world > 1 && !v7_row_needed(G, ez * G.EY + ey, G.range[G.rank], G.range[G.rank + 1])) return;
+    const int e = wcell;
     const int n = G.ncd;
     int rx = ex - 1, ry = ey - 1, rz = ez;
     double shx = 0.0, shy = 0.0, shz = 0.0;
@@ -197,8 +274,7 @@ static __global__ void __launch_bounds__(256) k_gather7(Gather7Args A)
 }
 
 struct V7Args {
-    V7Grid G;
-    int units;                     // 3 groups x ncd² x (z1 − z0) home cells
+    V7Grid G;                      // units = 3 groups x the home cells [G.range[rank], G.range[rank + 1])
     const double *rows;
     const float4 *gf;
     const int *ecount;
@@ -255,14 +331,17 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
     if (warp == V7_CONSUMERS) {
         // ======================================================================== producer warp
         const int n = A.G.ncd, EX = A.G.EX, EY = A.G.EY;
+        const int c_first = A.G.range[A.G.rank];
+        const long long n_units = (long long)V3_GROUPS * (A.G.range[A.G.rank + 1] - c_first);
         long long u = blockIdx.x;
         unsigned tk_pending = 0;
         if (lane == 0) tk_pending = atomicAdd(A.ticket, 1u);       // one ticket is always in flight: drawn a unit ahead
         unsigned seq = 0;
-        while (u < A.units) {
+        while (u < n_units) {
             const int ci = (int)(u / V3_GROUPS), g = (int)(u - (long long)ci * V3_GROUPS);
-            const int lz = ci / (n * n), r2 = ci - lz * n * n, cy = r2 / n, cx = r2 - cy * n;
-            const int e = (cx + 1) + EX * ((cy + 1) + EY * (A.G.z0 + lz));
+            const int c = c_first + ci;
+            const int cz = c / (n * n), r2 = c - cz * n * n, cy = r2 / n, cx = r2 - cy * n;
+            const int e = (cx + 1) + EX * ((cy + 1) + EY * cz);
             const int sl0 = c_v3_group_begin[g], nsl_all = c_v3_group_begin[g + 1] - sl0;
             int en = e, cnt = 0;
             if (lane < nsl_all) {
@@ -272,7 +351,7 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
             } else if (lane == 5) cnt = A.ecount[e];
             const unsigned tk = __shfl_sync(FULL, tk_pending, 0);
             const long long u_next = (long long)gridDim.x + tk;
-            if (lane == 0 && u_next < A.units) tk_pending = atomicAdd(A.ticket, 1u);
+            if (lane == 0 && u_next < n_units) tk_pending = atomicAdd(A.ticket, 1u);
             const int nA = __shfl_sync(FULL, cnt, 5);
             // a unit without work (an empty home cell or only empty neighbours) never reaches the consumers: its slots are zeroed here
             const bool any_b = __any_sync(FULL, lane < nsl_all && cnt > 0);
@@ -494,7 +573,8 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
 #define TAIL_THREADS 256
 
 struct TailArgs {
-    const double4 *unit_partial; long long n_partial;   // pair sums
+    const double4 *unit_partial;   // pair sums [units][V7_CONSUMERS], units = 3 x (range[rank + 1] − range[rank])
+    const int *range; int rank;
     const double2 *rhok_partial; int rhok_blocks, nkvecs;   // ρ(k) partials [rhok_blocks][nkvecs] (nkvecs == 0: no k-space)
     double4 *block_sums;           // [TAIL_BLOCKS]
     unsigned int *done;            // ticket of the tail blocks (zeroed)
@@ -517,8 +597,9 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
     __shared__ int s_last;
     const int tid = threadIdx.x, b = blockIdx.x;
     {   // pair sums: contiguous share; four independent running sums per thread (the loads are in flight together), fixed tree
-        const long long per = (A.n_partial + gridDim.x - 1) / gridDim.x;
-        const long long lo = per * b, hi = lo + per < A.n_partial ? lo + per : A.n_partial;
+        const long long n_partial = (long long)V3_GROUPS * V7_CONSUMERS * (A.range[A.rank + 1] - A.range[A.rank]);
+        const long long per = (n_partial + gridDim.x - 1) / gridDim.x;
+        const long long lo = per * b < n_partial ? per * b : n_partial, hi = lo + per < n_partial ? lo + per : n_partial;
         double v[4] = {0.0, 0.0, 0.0, 0.0}, w[4] = {0.0, 0.0, 0.0, 0.0};
         long long i = lo + tid;
         for (; i + TAIL_THREADS < hi; i += 2 * TAIL_THREADS) {

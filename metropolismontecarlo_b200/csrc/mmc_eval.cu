@@ -193,29 +193,26 @@ bool v7_eligible(mmc_handle *h, int style, const EvalCtx &E, ErfPoly &ep)
     return ep.deg > 0;
 }
 
-// this rank's home layers of the cell grid: contiguous z-slabs (every rank bins, gathers and reads only its slab + the
-// layer above it)
-void v7_slab(int ncd, int rank, int world, int &z0, int &z1)
-{
-    z0 = (int)((long long)ncd * rank / world);
-    z1 = (int)((long long)ncd * (rank + 1) / world);
-}
-
 V7Grid v7_grid(const mmc_handle *h, int style, const EvalCtx &E)
 {
     V7Grid G{};
     G.ncd = grid_cells(h, style, E.box); G.EX = G.ncd + 2; G.EY = G.ncd + 2;
-    v7_slab(G.ncd, E.rank, E.world, G.z0, G.z1);
+    G.rank = E.rank; G.world = E.world;
+    G.range = h->d7_range + (E.world > 1 ? 2 : 0);      // [0, 1]: the whole grid (one rank); [2 ..]: the partition of a sharded evaluation
     G.edge = E.box / G.ncd; G.box_new = E.box;
     return G;
 }
 
-int v7_alloc(mmc_handle *h, const V7Grid &G, long long units)
+int v7_alloc(mmc_handle *h, int ncd, int EXY)
 {
     if (!h->d7_flags) {
         CK(cudaMalloc(&h->d7_flags, 8 * sizeof(int)));
         CK(cudaMalloc(&h->d7_block_sums, TAIL_BLOCKS * sizeof(double4)));
+        CK(cudaMalloc(&h->d7_range, (2 + MMC_PEER_MAX + 1) * sizeof(int)));
     }
+    V7Grid G{};
+    G.ncd = ncd; G.EX = EXY; G.EY = EXY;
+    const long long units = (long long)V3_GROUPS * ncd * ncd * ncd;
     if (G.ncd != h->d7_ncd) {
         dfree(h->d7_count); dfree(h->d7_bucket); dfree(h->d7_ecount); dfree(h->d7_rows); dfree(h->d7_gf);
         const size_t ncell = (size_t)G.ncd * G.ncd * G.ncd, next = (size_t)v7_ext_cells(G);
@@ -226,6 +223,8 @@ int v7_alloc(mmc_handle *h, const V7Grid &G, long long units)
         CK(cudaMalloc(&h->d7_gf, next * V7_CAP * sizeof(float4)));
         h->d7_ncd = G.ncd;
         h->bin_version = 0;
+        const int whole[2] = {0, (int)ncell};
+        CK(cudaMemcpyAsync(h->d7_range, whole, sizeof(whole), cudaMemcpyHostToDevice, h->stream));
     }
     const size_t need = (size_t)std::max(1LL, units) * V7_CONSUMERS;
     if (need > h->d7_partial_cap) {
@@ -243,10 +242,9 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
 {
     const DevSystem &S = h->S;
     const bool ewald = style == MMC_STYLE_EWALD;
-    const V7Grid G = v7_grid(h, style, E);
-    const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * (G.z1 - G.z0);
-    int rc = v7_alloc(h, G, units);
+    int rc = v7_alloc(h, grid_cells(h, style, E.box), grid_cells(h, style, E.box) + 2);
     if (rc) return rc;
+    const V7Grid G = v7_grid(h, style, E);
     if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
     // ---- ρ(k) rebuild (RecipLong, ewalds.jl:538-604) of this rank's share of the sites: depends on nothing the pair path
     // produces (a volume trial scales the resident sites inside the kernel), so it runs beside it on the side stream
@@ -269,25 +267,29 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     // e.g. by consecutive volume trials) and the gather into the extended grid
     CK(cudaMemsetAsync(h->d7_flags, 0, 8 * sizeof(int), h->stream));
     const int tb = 256;
-    if (h->bin_version != h->state_version || h->bin_ncd != G.ncd || h->bin_z0 != G.z0 || h->bin_z1 != G.z1) {
+    if (h->bin_version != h->state_version || h->bin_ncd != G.ncd || h->bin_world != E.world) {
         CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)G.ncd * G.ncd * G.ncd, h->stream));
         Bin7Args B{S.com, S.n_mol, (double)G.ncd / S.box, G, h->d7_count, h->d7_bucket, nullptr};
         k_bin7<<<(S.n_mol + tb - 1) / tb, tb, 0, h->stream>>>(B); LAUNCH_CHECK();
-        h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_z0 = G.z0; h->bin_z1 = G.z1;
+        if (E.world > 1) {       // the ranks' home ranges: equal estimated pair work, from the cell populations
+            k_partition7<<<1, 1024, 0, h->stream>>>(h->d7_count, G.ncd, E.world, h->d7_range + 2); LAUNCH_CHECK();
+        }
+        h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_world = E.world;
     }
     if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
     unsigned int *fl = reinterpret_cast<unsigned int *>(h->d7_flags);
     {
         Gather7Args A{S.com, S.site, h->d7_count, h->d7_bucket, G, E.f, h->d7_rows, h->d7_gf, h->d7_ecount,
                       reinterpret_cast<unsigned long long *>(h->d7_flags), fl + 3, h->d7_flags + 4};
-        const int warps = G.EX * G.EY * (G.z1 - G.z0 + 1);
+        const int warps = G.EX * G.EY * (G.ncd + 1);
         k_gather7<<<(warps + 7) / 8, 256, 0, h->stream>>>(A); LAUNCH_CHECK();
     }
     if (h->tm.on) { cudaEventRecord(h->tm.ev[5], h->stream); cudaEventRecord(h->tm.ev[0], h->stream); }
     // ---- pairs
-    if (units > 0) {
+    {
+        const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * G.ncd / E.world + 1;      // (about: the grid size only)
         V7Args A{};
-        A.G = G; A.units = (int)units;
+        A.G = G;
         A.rows = h->d7_rows; A.gf = h->d7_gf; A.ecount = h->d7_ecount;
         const double rcut = S.rc_qq, edge = G.edge;
         // conservative FP32 gate in the dot form |b|² − 2a·b < r_c² − |a|² on coordinates relative to the box centre
@@ -326,7 +328,7 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     if (E.rhok_external && E.rhok_done) CK(cudaStreamWaitEvent(h->stream, E.rhok_done, 0));
     // ---- everything else in one launch
     TailArgs T{};
-    T.unit_partial = h->d7_unit_partial; T.n_partial = units * V7_CONSUMERS;
+    T.unit_partial = h->d7_unit_partial; T.range = G.range; T.rank = E.rank;
     T.rhok_partial = h->d_rhok_partial; T.rhok_blocks = rhok_blocks; T.nkvecs = ewald ? S.nkvecs : 0;
     T.block_sums = h->d7_block_sums; T.done = fl + 6;
     T.n_ovl = fl + 2; T.err_flag = fl + 3; T.max_count = h->d7_flags + 4;
@@ -896,9 +898,8 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     }
     EvalCtx E{1.0, S.box, S.kappa, S.cfac, h->cfg.rank, h->cfg.world};
     E.partial_state = true;
+    if ((rc = v7_alloc(h, grid_cells(h, style, E.box), grid_cells(h, style, E.box) + 2))) return rc;
     const V7Grid G = v7_grid(h, style, E);
-    const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * (G.z1 - G.z0);
-    if ((rc = v7_alloc(h, G, units))) return rc;
     // ---- COMs, binning, and which molecule blocks this rank reads
     CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * S.n_mol, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
@@ -906,9 +907,11 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     h->state_version++;
     CK(cudaMemsetAsync(h->d7_need, 0, nblk, h->stream));
     CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)G.ncd * G.ncd * G.ncd, h->stream));
-    Bin7Args B{S.com, S.n_mol, (double)G.ncd / S.box, G, h->d7_count, h->d7_bucket, h->d7_need};
+    Bin7Args B{S.com, S.n_mol, (double)G.ncd / S.box, G, h->d7_count, h->d7_bucket, h->d_cell_of};
     k_bin7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(B); LAUNCH_CHECK();
-    h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_z0 = G.z0; h->bin_z1 = G.z1;
+    k_partition7<<<1, 1024, 0, h->stream>>>(h->d7_count, G.ncd, E.world, h->d7_range + 2); LAUNCH_CHECK();
+    k_need7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->d_cell_of, S.n_mol, G, h->d7_need); LAUNCH_CHECK();
+    h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_world = E.world;
     CK(cudaMemcpyAsync(h->h7_need, h->d7_need, nblk, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaEventRecord(h->ev_fork, h->stream));

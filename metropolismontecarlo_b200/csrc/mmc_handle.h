@@ -131,7 +131,8 @@ struct mmc_handle {
     unsigned long long res_seq = 0;
     unsigned long long state_version = 1;           // bumped whenever resident positions change
     unsigned long long bin_version = 0;             // state the buckets were built from (0: none)
-    int bin_ncd = 0, bin_z0 = -1, bin_z1 = -1;
+    int bin_ncd = 0, bin_world = 0;
+    int *d7_range = nullptr;                        // [0,1] = {0, ncd³}; [2 .. 2+world] = home-cell boundaries of the ranks (k_partition7)
     int v7_ctas_per_sm = 4;
     unsigned char *d7_need = nullptr, *h7_need = nullptr;     // domain-decomposed host evaluation: molecule blocks this rank reads
     int need_cap = 0;
