@@ -63,6 +63,7 @@ typedef struct {
     double lj, real, recip, self_;
     double wolf_const;      /* (prefactor - prefactor2)*factor, energy.jl:924-934 */
     int64_t overlaps;       /* molecules whose EwaldReal row hit the overlap rule */
+    double intra;           /* intramolecular Ewald correction; 0 unless mmc_set_intramolecular is on (not in the reference) */
 } mmc_properties;
 
 /* result of one fused trial move: exactly the numbers Loop() gets from its five calls */
@@ -120,6 +121,15 @@ int mmc_ewald_prepare(mmc_handle *h, double kappa, int32_t nk, int32_t k_sq_max,
 int mmc_get_kvectors(mmc_handle *h, int32_t *kxyz /* nkvecs x 3 */, double *cfac);
 /* ewald.sumQExpOld / sumQExpNew (re,im interleaved); either pointer may be NULL */
 int mmc_get_rhok(mmc_handle *h, double *sum_old, double *sum_new);
+
+/* Opt-in (default off = the reference's semantics): add the intramolecular correction of the Ewald sum,
+ *     E_intra = -factor * sum_molecules sum_{a<b in molecule} q_a q_b erf(kappa r_ab) / r_ab,
+ * to the EWALD energies of mmc_potential*, mmc_potential_host and mmc_volume_trial (energy, coulomb, virial += E_intra/3 like the
+ * other Coulomb terms, and Properties.intra).  The reference omits it (Ewald/energy.jl:1008-1021 adds the reciprocal and the
+ * self term only); because kappa = alpha/L changes with the box, NPT volume moves need it for physically meaningful energies
+ * (SURVEY 8-f4).  Rigid-body trial moves leave it unchanged, so the per-move entry points do not carry it; neither does
+ * mmc_potential_host on a sharded handle (only a slab of the sites is resident there). */
+int mmc_set_intramolecular(mmc_handle *h, int32_t enabled);
 
 /* ---- per-function drop-ins (molecules) ------------------------------------------------- */
 /* Ewald/energy.jl:209-290  LJ_poly_ΔU(i, moa, soa, vdwTable, r_cut, box) -> (4 pot, 24 vir/3) */

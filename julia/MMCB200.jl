@@ -1,8 +1,11 @@
 # MMCB200.jl — Julia binding of libmmc_b200.so (include/mmc_b200.h) for the reference driver
 # (BradenDKelly/MetropolisMonteCarlo, Ewald/main.jl).  UNTESTED HERE: Julia is not installed in
 # the build image; the same C ABI is exercised through Python ctypes (metropolismontecarlo_b200/
-# _lib.py) by the parity tests.  Memory layouts are the reference's own (SURVEY.md A.6): pointers
-# to soa.coords / moa.COM (Vector{SVector{3,Float64}}) are passed as Ptr{Float64} with no copy.
+# _lib.py) by the parity tests.  Memory layouts are the reference's own (SURVEY.md A.6): soa.coords /
+# moa.COM (Vector{SVector{3,Float64}}) go through with no copy.  Array arguments are declared Ptr{Cvoid} and
+# the ARRAYS (not a) are handed to ccall: Base.cconvert then keeps them rooted for the duration of
+# the call (no GC.@preserve needed) and accepts any element type, SVector included; a single SVector (a COM)
+# travels as Ref(x), which unsafe_convert(Ptr{Cvoid}, ::RefValue) supports for isbits types.
 module MMCB200
 
 const LIB = get(ENV, "MMC_B200_LIB", "libmmc_b200")
@@ -16,7 +19,8 @@ mutable struct Props            # mmc_properties  (Properties of Ewald/auxillary
     energy::Cdouble; virial::Cdouble; coulomb::Cdouble
     lj::Cdouble; real::Cdouble; recip::Cdouble; self::Cdouble; wolf_const::Cdouble
     overlaps::Int64
-    Props() = new(0, 0, 0, 0, 0, 0, 0, 0, 0)
+    intra::Cdouble              # intramolecular correction, 0 unless set_intramolecular!(e, true)
+    Props() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
 end
 
 mutable struct TrialResult      # mmc_trial_result
@@ -48,11 +52,11 @@ destroy(e::Engine) = ccall((:mmc_destroy, LIB), Cint, (Ptr{Cvoid},), e.h)
 function upload!(e::Engine, soa, moa, vdwTable, box, rc_lj, rc_qq)
     nt = size(vdwTable.ϵᵢⱼ, 1)
     check(e, ccall((:mmc_upload_system, LIB), Cint,
-        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
-         Cint, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cdouble),
-        e.h, length(moa), length(soa), pointer(soa.coords), pointer(soa.charge), pointer(soa.atype),
-        pointer(moa.firstAtom), pointer(moa.lastAtom), pointer(moa.COM), nt,
-        pointer(vdwTable.ϵᵢⱼ), pointer(vdwTable.σᵢⱼ), box, rc_lj, rc_qq))
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+         Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cdouble),
+        e.h, length(moa), length(soa), soa.coords, soa.charge, soa.atype,
+        moa.firstAtom, moa.lastAtom, moa.COM, nt,
+        vdwTable.ϵᵢⱼ, vdwTable.σᵢⱼ, box, rc_lj, rc_qq))
 end
 
 # PrepareEwaldVariables(ewald, box)  — Ewald/ewalds.jl:45-103
@@ -80,8 +84,8 @@ end
 # RecipMove(box, ewald, r_old, r_new, q)  — Ewald/ewalds.jl:718-826
 function RecipMove(e::Engine, r_old::Vector, r_new::Vector, q::Vector{Float64})
     d = Ref{Cdouble}(0)
-    check(e, ccall((:mmc_recip_move, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ref{Cdouble}),
-                   e.h, pointer(r_old), pointer(r_new), pointer(q), length(q), d))
+    check(e, ccall((:mmc_recip_move, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{Cdouble}),
+                   e.h, r_old, r_new, q, length(q), d))
     d[]
 end
 recip_commit!(e::Engine) = check(e, ccall((:mmc_recip_commit, LIB), Cint, (Ptr{Cvoid},), e.h))     # main.jl:621
@@ -89,30 +93,33 @@ recip_rollback!(e::Engine) = check(e, ccall((:mmc_recip_rollback, LIB), Cint, (P
 
 # in-place writes of main.jl:527,552 / 623-624
 set_molecule!(e::Engine, i::Int, com, sites::Vector) =
-    check(e, ccall((:mmc_set_molecule, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), e.h, i, Ref(com), pointer(sites)))
+    check(e, ccall((:mmc_set_molecule, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}), e.h, i, Ref(com), sites))
 
 # page-lock long-lived host arrays (soa.coords, moa.COM) once, so uploads from them are true asynchronous DMA at full PCIe rate
-host_register(a::Array) = ccall((:mmc_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), pointer(a), sizeof(a)) == 0 ||
+host_register(a::Array) = ccall((:mmc_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), a, sizeof(a)) == 0 ||
     error("mmc_host_register failed")
-host_unregister(a::Array) = ccall((:mmc_host_unregister, LIB), Cint, (Ptr{Cvoid},), pointer(a)) == 0 ||
+host_unregister(a::Array) = ccall((:mmc_host_unregister, LIB), Cint, (Ptr{Cvoid},), a) == 0 ||
     error("mmc_host_unregister failed")
 
-# all positions at once (bulk form of set_molecule!): pointer(soa.coords), pointer(moa.COM)
+# all positions at once (bulk form of set_molecule!): soa.coords, moa.COM
 upload_positions!(e::Engine, coords, com) =
-    check(e, ccall((:mmc_upload_positions, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), e.h, pointer(coords), pointer(com)))
+    check(e, ccall((:mmc_upload_positions, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), e.h, coords, com))
 
 # host arrays in, Properties out: upload_positions! + potential with the copies overlapped with compute
 function potential_host(e::Engine, coords, com, style::Cint = EWALD)
     p = Props()
-    check(e, ccall((:mmc_potential_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ref{Props}),
-                   e.h, pointer(coords), pointer(com), style, p))
+    check(e, ccall((:mmc_potential_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{Props}),
+                   e.h, coords, com, style, p))
     p
 end
+
+# opt-in intramolecular Ewald correction (the reference omits it, Ewald/energy.jl:1008-1021); Props.intra carries it
+set_intramolecular!(e::Engine, on::Bool) = check(e, ccall((:mmc_set_intramolecular, LIB), Cint, (Ptr{Cvoid}, Cint), e.h, on ? 1 : 0))
 
 # LJ_poly_ΔU(i, …) and EwaldShort(i, …)[1] for every molecule i from one evaluation (the rows potential() sums)
 function energy_all(e::Engine, n_mol::Integer, style::Cint = EWALD)
     lj = Vector{Float64}(undef, n_mol); vir = similar(lj); qq = similar(lj); ov = Vector{Int32}(undef, n_mol)
-    check(e, ccall((:mmc_energy_all, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+    check(e, ccall((:mmc_energy_all, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
                    e.h, style, lj, vir, qq, ov))
     lj, vir, qq, ov
 end
@@ -127,8 +134,8 @@ end
 # fused fast path: the five calls of Loop (main.jl:491-590) in one launch
 function trial_move(e::Engine, i::Int, com_new, sites_new::Vector, style::Cint = EWALD)
     r = TrialResult()
-    check(e, ccall((:mmc_trial_move, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Ref{TrialResult}),
-                   e.h, i, Ref(com_new), pointer(sites_new), style, r))
+    check(e, ccall((:mmc_trial_move, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{TrialResult}),
+                   e.h, i, Ref(com_new), sites_new, style, r))
     r
 end
 accept!(e::Engine) = check(e, ccall((:mmc_accept, LIB), Cint, (Ptr{Cvoid},), e.h))
@@ -146,11 +153,11 @@ volume_reject!(e::Engine) = check(e, ccall((:mmc_volume_reject, LIB), Cint, (Ptr
 # sharded full energy with the exchange over NVLink peer memory (one process per GPU; include/mmc_b200.h mmc_peer_*)
 function peer_export(e::Engine)
     hd = Vector{UInt8}(undef, 64)
-    check(e, ccall((:mmc_peer_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), e.h, hd))
+    check(e, ccall((:mmc_peer_export, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), e.h, hd))
     hd
 end
 peer_import!(e::Engine, rank::Integer, hd::Vector{UInt8}) =
-    check(e, ccall((:mmc_peer_import, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}), e.h, rank, hd))
+    check(e, ccall((:mmc_peer_import, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), e.h, rank, hd))
 function potential_sharded(e::Engine, style::Cint = EWALD)
     p = Props()
     check(e, ccall((:mmc_potential_sharded, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Props}), e.h, style, p))
@@ -175,9 +182,9 @@ function loop_run_device!(e::Engine, p::LoopParams, com, quat, db, u::Vector{Flo
                           accepted::Vector{UInt8} = Vector{UInt8}(undef, n_moves), delta::Vector{Float64} = Vector{Float64}(undef, n_moves))
     st = LoopStats()
     rc = ccall((:mmc_loop_run_device, LIB), Cint,
-               (Ptr{Cvoid}, Ref{LoopParams}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Cdouble, Cdouble,
-                Ptr{UInt8}, Ptr{Float64}, Ref{LoopStats}),
-               e.h, p, pointer(com), pointer(quat), pointer(db), pointer(u), length(u), n_moves, e0, v0, pointer(accepted), pointer(delta), st)
+               (Ptr{Cvoid}, Ref{LoopParams}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cdouble, Cdouble,
+                Ptr{Cvoid}, Ptr{Cvoid}, Ref{LoopStats}),
+               e.h, p, com, quat, db, u, length(u), n_moves, e0, v0, accepted, delta, st)
     rc < 0 && check(e, rc)          # 1 = stream ran dry, 2 = quaternion-norm error (quaternions.jl:22-25), 3 = no move selected
     st, accepted, delta, rc
 end

@@ -29,7 +29,7 @@ class Config(C.Structure):
 class Properties(C.Structure):
     _fields_ = [("energy", C.c_double), ("virial", C.c_double), ("coulomb", C.c_double),
                 ("lj", C.c_double), ("real", C.c_double), ("recip", C.c_double),
-                ("self_", C.c_double), ("wolf_const", C.c_double), ("overlaps", C.c_int64)]
+                ("self_", C.c_double), ("wolf_const", C.c_double), ("overlaps", C.c_int64), ("intra", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -124,6 +124,7 @@ SIGNATURES = {
     "mmc_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mmc_host_unregister": (C.c_int, [C.c_void_p]),
     "mmc_julia_rand": (C.c_int, [C.c_uint64, C.c_int64, c_double_p, C.c_int64]),
+    "mmc_set_intramolecular": (C.c_int, [H, C.c_int32]),
     "mmc_get_counters": (C.c_int, [H, C.POINTER(Counters)]),
     "mmc_set_timing": (C.c_int, [H, C.c_int32]),
     "mmc_last_timings": (C.c_int, [H, c_float_p]),

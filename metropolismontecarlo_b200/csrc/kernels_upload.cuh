@@ -135,3 +135,37 @@ static __global__ void k_window_need(const int *__restrict__ cell_of, int n_mol,
         if ((z >= zlo && z < zhi) || z == zhi % ncd) atomicMax(&need[w], c);
     }
 }
+
+// Intramolecular Ewald correction (opt-in, not in the reference): Σ_mol Σ_{a<b} q_a q_b erf(κ r_ab)/r_ab, un-scaled, in two
+// deterministic stages like the charge sums.  r_ab is the plain separation (a rigid shift of the molecule — volume scaling,
+// periodic wrapping of the COM — does not change it).
+static __global__ void __launch_bounds__(256) k_intra_partial(const double4 *site, const int2 *mol, int n_mol, double kappa, double *part)
+{
+    __shared__ double s_red[8];
+    double acc[1] = {0.0};
+    for (int m = blockIdx.x * 256 + threadIdx.x; m < n_mol; m += gridDim.x * 256) {
+        const int2 mi = mol[m];
+        double e = 0.0;
+        for (int a = 0; a < mi.y; ++a) {
+            const double4 sa = site[mi.x + a];
+            for (int b = a + 1; b < mi.y; ++b) {
+                const double4 sb = site[mi.x + b];
+                const double dx = sb.x - sa.x, dy = sb.y - sa.y, dz = sb.z - sa.z;
+                const double r = sqrt(dx * dx + dy * dy + dz * dz);
+                e += sa.w * sb.w * erf(kappa * r) / r;
+            }
+        }
+        acc[0] += e;
+    }
+    block_sum<1, 256>(acc, s_red);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc[0];
+}
+
+static __global__ void __launch_bounds__(256) k_intra_final(const double *part, int nb, double *out)
+{
+    __shared__ double s_red[8];
+    double acc[1] = {0.0};
+    for (int l = threadIdx.x; l < nb; l += 256) acc[0] += part[l];
+    block_sum<1, 256>(acc, s_red);
+    if (threadIdx.x == 0) out[0] = acc[0];
+}

@@ -17,7 +17,7 @@ std::string g_create_error;
 void free_system(mmc_handle *h)
 {
     dfree(h->S.site); dfree(h->S.com); dfree(h->S.mol); dfree(h->S.atype);
-    dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums); dfree(h->d_raw); dfree(h->d_info); dfree(h->d_qpart);
+    dfree(h->d_intra); dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums); dfree(h->d_raw); dfree(h->d_info); dfree(h->d_qpart);
     h->raw_bytes = 0; h->cap_mol = 0; h->cap_sites = 0;
     dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
     h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
@@ -199,6 +199,18 @@ int style_check(mmc_handle *h, int style, bool need_full_state)
     if (!h->has_system) FAIL(MMC_ESTATE, "no molecular system uploaded");
     if ((style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF) && !h->has_ewald)
         FAIL(MMC_ESTATE, "mmc_ewald_prepare has not been called");
+    return MMC_OK;
+}
+
+// Σ_mol Σ_{a<b} q_a q_b erf(κ r_ab)/r_ab on the resident state (one small evaluation: n_mol threads)
+int intra_energy(mmc_handle *h, double kappa, double *e_unscaled)
+{
+    if (!h->d_intra) CK(cudaMalloc(&h->d_intra, 257 * sizeof(double)));
+    const int nb = std::max(1, std::min(256, (h->S.n_mol + 255) / 256));
+    k_intra_partial<<<nb, 256, 0, h->stream>>>(h->S.site, h->S.mol, h->S.n_mol, kappa, h->d_intra); LAUNCH_CHECK();
+    k_intra_final<<<1, 256, 0, h->stream>>>(h->d_intra, nb, h->d_intra + 256); LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(e_unscaled, h->d_intra + 256, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return MMC_OK;
 }
 
@@ -843,6 +855,13 @@ int mmc_reject(mmc_handle *h)
     if (!h) return MMC_EINVAL;
     if (!h->trial_pending) FAIL(MMC_ESTATE, "mmc_reject without a pending trial move");
     h->trial_pending = false; h->new_valid = false;    // main.jl:623-628: resident state was never touched
+    return MMC_OK;
+}
+
+int mmc_set_intramolecular(mmc_handle *h, int32_t enabled)
+{
+    if (!h) return MMC_EINVAL;
+    h->intramolecular = enabled ? 1 : 0;
     return MMC_OK;
 }
 

@@ -513,8 +513,8 @@ int overlap_row(mmc_handle *h, const EvalCtx &E, int sorted_index, double *row)
 
 // Properties in the reference's order (energy.jl:972-1021) from the eight scalars of a (rank-summed) partial vector:
 // hv[0] Σlj_pot, [1] Σlj_vir, [2] Σcoul (overlap rows already removed), [4] E_recip un-scaled, [3] #overlapped molecules
-void assemble(mmc_handle *h, int style, const EvalCtx &E, double lj_pot, double lj_vir, double coul, double recip_raw,
-              long long novl, mmc_properties *out)
+int assemble(mmc_handle *h, int style, const EvalCtx &E, double lj_pot, double lj_vir, double coul, double recip_raw,
+             long long novl, mmc_properties *out)
 {
     const DevSystem &S = h->S;
     std::memset(out, 0, sizeof(*out));
@@ -541,6 +541,15 @@ void assemble(mmc_handle *h, int style, const EvalCtx &E, double lj_pot, double 
             out->energy += selfEnergy;
             out->coulomb += selfEnergy;
             out->virial += selfEnergy / 3.0;
+            if (h->intramolecular && !E.partial_state) {      // opt-in, not in the reference (include/mmc_b200.h: mmc_set_intramolecular)
+                double raw = 0.0;
+                int rc = intra_energy(h, E.kappa, &raw);
+                if (rc) return rc;
+                out->intra = -raw * factor;
+                out->energy += out->intra;
+                out->coulomb += out->intra;
+                out->virial += out->intra / 3.0;
+            }
         } else {
             // energy.jl:924-934 with Σ_iΣ_j q_i q_j = (Σq)² in closed form; r_cut = LJ_rcut (:874)
             const double r_cut = S.rc_lj;
@@ -552,6 +561,7 @@ void assemble(mmc_handle *h, int style, const EvalCtx &E, double lj_pot, double 
             out->coulomb += out->wolf_const;
         }
     }
+    return MMC_OK;
 }
 
 void read_timings(mmc_handle *h, int style)
@@ -573,7 +583,7 @@ int finish_v7(mmc_handle *h, int style, const EvalCtx &E, mmc_properties *out)
     if (hv[7] != 0.0) return 1;
     if (hv[3] != 0.0) { h->v7_left_for_overlap = true; return 1; }     // back to k_pairs_v7 once the overlaps are gone
     h->last_pairs = (long long)hv[5];
-    assemble(h, style, E, hv[0], hv[1], hv[2], hv[4], 0, out);
+    if ((rc = assemble(h, style, E, hv[0], hv[1], hv[2], hv[4], 0, out))) return rc;
     read_timings(h, style);
     h->cnt.full_energy_evals++;
     return MMC_OK;
@@ -643,7 +653,7 @@ int finalize_host(mmc_handle *h, int style, const EvalCtx &E, const double *hv, 
     }
     h->last_pairs = (long long)hv[5];
     if (h->v7_left_for_overlap && novl == 0 && coulomb) { h->v7_left_for_overlap = false; h->pair_level = h->pair_floor; }
-    assemble(h, style, E, lj_pot, lj_vir, coul, recip_raw, novl, out);
+    { int rca = assemble(h, style, E, lj_pot, lj_vir, coul, recip_raw, novl, out); if (rca) return rca; }
     read_timings(h, style);
     h->cnt.full_energy_evals++;
     return MMC_OK;
@@ -721,6 +731,11 @@ int potential_rows(mmc_handle *h, int style, mmc_properties *out)
             const double selfEnergy = -S.kappa * h->sum_q2 / std::sqrt(M_PI) * S.factor;
             out->self_ = selfEnergy; out->energy += selfEnergy; out->coulomb += selfEnergy;
             out->virial += selfEnergy / 3.0;
+            if (h->intramolecular) {
+                double raw = 0.0;
+                if ((rc = intra_energy(h, S.kappa, &raw))) return rc;
+                out->intra = -raw * S.factor; out->energy += out->intra; out->coulomb += out->intra; out->virial += out->intra / 3.0;
+            }
             h->new_valid = false;
         } else {
             const double ec = std::erfc(S.kappa * S.rc_lj);

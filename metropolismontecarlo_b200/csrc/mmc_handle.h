@@ -138,6 +138,8 @@ struct mmc_handle {
     int need_cap = 0;
     bool partial_resident = false;                  // after it only those blocks' sites are current on this GPU
     long long last_h2d_bytes = 0;                   // bytes the last mmc_potential_host moved host -> device on this rank
+    int intramolecular = 0;                         // mmc_set_intramolecular
+    double *d_intra = nullptr;                      // [256 partials | result]
     bool v7_left_for_overlap = false;               // k_pairs_v7 handed the state over because molecules overlapped
     int v7_rhok_blocks = 0;                         // CTAs of the last ρ(k) partial launch
     int rhok_split = 1;          // ρ(k) rebuild: CTAs per resident slot (short CTAs let higher-priority kernels in between)
@@ -210,6 +212,7 @@ int move_tiles(const mmc_handle *h);
 int flush_pending(mmc_handle *h);
 int launch_move_on(mmc_handle *h, const DevSystem &sys, MoveArgs &A, const ErfPoly &poly, bool carry_commit);
 int style_check(mmc_handle *h, int style, bool need_full_state = true);
+int intra_energy(mmc_handle *h, double kappa, double *e_unscaled);
 void fill_cfac(const std::vector<int32_t> &kxyz, double kappa, double box, std::vector<double> &cfac);
 void get_erf_poly(mmc_handle *h, double kappa, double r2_max, ErfPoly &P);
 // mmc_eval.cu

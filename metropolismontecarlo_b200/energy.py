@@ -325,6 +325,10 @@ class Engine:
                                                   acc.ctypes.data_as(_lib.c_uint8_p), _dp(delta), C.byref(st)))
         return rc, acc, delta, st
 
+    def set_intramolecular(self, on: bool):
+        """Opt-in intramolecular Ewald correction (mmc_set_intramolecular; the reference omits it, energy.jl:1008-1021)."""
+        self._ck(self.lib.mmc_set_intramolecular(self.h, int(on)))
+
     # ---- instrumentation
     def counters(self) -> Counters:
         c = Counters()

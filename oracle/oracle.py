@@ -187,6 +187,14 @@ def EwaldShort(i, s: System, ew: Ewald, qq_rcut, box):
     return e.value, v.value, bool(ov.value)
 
 
+def EwaldIntra(s: System, kappa, factor):
+    """Intramolecular correction (not in the reference; twin of the engine's opt-in flag): -factor Σ_mol Σ_{a<b} q_a q_b erf(κ r)/r."""
+    cs = s.c()
+    f = lib().ora_EwaldIntra
+    f.restype = C.c_double
+    return f(C.byref(cs), C.c_double(kappa), C.c_double(factor))
+
+
 def RecipLong(ew: Ewald, r, q, box):
     r = np.ascontiguousarray(r, dtype=np.float64)
     q = np.ascontiguousarray(q, dtype=np.float64)

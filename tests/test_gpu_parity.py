@@ -862,3 +862,34 @@ def test_domain_decomposed_host_evaluation_emulated_ranks(world, order):
     _check_props(engs[0].potential("ewald"), want, 1e-12)
     for e in engs:
         e.close()
+
+
+def test_intramolecular_correction_is_opt_in():
+    """the intramolecular Ewald correction the reference omits (Ewald/energy.jl:1008-1021), as an opt-in flag.
+    Default off = the reference's Properties; on: Properties.intra = −factor Σ_mol Σ_{a<b} q_a q_b erf(κ r)/r (oracle twin
+    ora_EwaldIntra), added to energy / coulomb and, like the other Coulomb terms, /3 to the virial — for potential() on the v7
+    path, the general path, a mixed topology, and a volume trial (κ = α/L' changes with the box)."""
+    from metropolismontecarlo_b200.energy import water_engine
+    for ms in (systems.spce_lattice(4000), systems.load_nist(4), systems.water_ion_mixture(512, 40)):
+        eng = water_engine(ms, 10.0)
+        s = ora_system(ms)
+        kappa = systems.ALPHA / ms.box
+        ref = eng.potential("ewald")
+        assert ref.intra == 0.0
+        eng.set_intramolecular(True)
+        got = eng.potential("ewald")
+        want = ora.EwaldIntra(s, kappa, systems.FACTOR)
+        assert want < 0 and rel(got.intra, want) < 1e-12
+        assert rel(got.energy, ref.energy + want) < 1e-12 and rel(got.coulomb, ref.coulomb + want) < 1e-12
+        assert rel(got.virial, ref.virial + want / 3) < 1e-12
+        for f in ("lj", "real", "recip", "self_"):
+            assert getattr(got, f) == getattr(ref, f)
+        assert eng.potential("wolf").intra == 0.0           # an Ewald-sum term only
+        if ms.n_mol == 4000:
+            L2 = ms.box * 1.02
+            v = eng.volume_trial(L2, systems.ALPHA / L2, "ewald")
+            eng.volume_reject()
+            assert rel(v.intra, ora.EwaldIntra(s, systems.ALPHA / L2, systems.FACTOR)) < 1e-12      # rigid shift: same r_ab, new κ
+        eng.set_intramolecular(False)
+        assert eng.potential("ewald").energy == ref.energy
+        eng.close()
