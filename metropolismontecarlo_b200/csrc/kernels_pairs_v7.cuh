@@ -179,6 +179,34 @@ static __global__ void __launch_bounds__(1024) k_partition7(const int *__restric
     }
 }
 
+// mmc_potential_host on one GPU, windowed: the home cells are cut into `nwin` contiguous ranges (range[0 .. nwin]) that are
+// gathered and evaluated one after the other while later site chunks are still on the bus; need[w] = the last chunk (sites
+// [n_sites·c/n_chunks, n_sites·(c+1)/n_chunks)) that holds a molecule window w reads.
+static __global__ void k_window_need7(const int *__restrict__ cell_of, int n_mol, int US, int n_sites, int n_chunks, V7Grid G, int nwin, int *need)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mol) return;
+    const int n = G.ncd, c = cell_of[m];
+    const int cy = (c / n) % n, cz = c / (n * n);
+    const long long last_site = (long long)m * US + US - 1;
+    int ch = (int)(last_site * n_chunks / n_sites);
+    while (ch + 1 < n_chunks && (long long)n_sites * (ch + 1) / n_chunks <= last_site) ++ch;
+    while (ch > 0 && (long long)n_sites * ch / n_chunks > last_site) --ch;
+    for (int w = 0; w < nwin; ++w) {
+        const int c0 = G.range[w], c1 = G.range[w + 1];
+        bool nd = false;
+#pragma unroll
+        for (int gz = 0; gz < 2; ++gz) {
+            if (gz == 1 && cz != 0) continue;
+            const int ez = gz ? n : cz;
+            nd |= v7_row_needed(G, ez * G.EY + cy + 1, c0, c1);
+            if (cy == 0) nd |= v7_row_needed(G, ez * G.EY + n + 1, c0, c1);
+            if (cy == n - 1) nd |= v7_row_needed(G, ez * G.EY + 0, c0, c1);
+        }
+        if (nd) atomicMax(&need[w], ch);
+    }
+}
+
 // domain-decomposed host evaluation: which blocks of 256 molecules hold a molecule this rank reads (its home range, the
 // half shell around it, the ghost images included)
 static __global__ void k_need7(const int *__restrict__ cell_of, int n_mol, V7Grid G, unsigned char *need)
@@ -290,7 +318,7 @@ struct V7Args {
     unsigned int *err_flag;
     unsigned int *n_ovl;
     unsigned int *ticket;          // zeroed before the launch
-    double4 *unit_partial;         // [units][V7_CONSUMERS]
+    double4 *unit_partial;         // [3 ncd³][V7_CONSUMERS], indexed by the GLOBAL unit 3·cell + group
 };
 
 // what the producer publishes per sub-unit (ring of four, guarded by the gate-coordinate barriers)
@@ -355,7 +383,8 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
             const int nA = __shfl_sync(FULL, cnt, 5);
             // a unit without work (an empty home cell or only empty neighbours) never reaches the consumers: its slots are zeroed here
             const bool any_b = __any_sync(FULL, lane < nsl_all && cnt > 0);
-            if ((nA == 0 || !any_b) && lane < V7_CONSUMERS) A.unit_partial[(size_t)u * V7_CONSUMERS + lane] = make_double4(0.0, 0.0, 0.0, 0.0);
+            const long long ug = (long long)V3_GROUPS * c_first + u;            // global unit
+            if ((nA == 0 || !any_b) && lane < V7_CONSUMERS) A.unit_partial[(size_t)ug * V7_CONSUMERS + lane] = make_double4(0.0, 0.0, 0.0, 0.0);
             int pass = 0;
             for (int s_begin = 0; s_begin < nsl_all && nA > 0;) {
                 int incl = (lane >= s_begin && lane < nsl_all) ? cnt : 0;          // inclusive prefix of the B counts from s_begin on
@@ -372,7 +401,7 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
                     if (lane == 0) {
                         D.valid = 1; D.nA = nA; D.nB = nB; D.nsl = se - s_begin;
                         D.self_n = (g == 0 && s_begin == 0) ? nA : 0;
-                        D.rot = (int)(u & 3); D.unit = u; D.first = pass == 0 ? 1 : 0;
+                        D.rot = (int)(u & 3); D.unit = ug; D.first = pass == 0 ? 1 : 0;
                     }
                     __syncwarp();
                     float4 *gfA = s_gf + sg * (V7_CAP + V7_BCAP), *gfB = gfA + V7_CAP;
@@ -597,9 +626,9 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
     __shared__ int s_last;
     const int tid = threadIdx.x, b = blockIdx.x;
     {   // pair sums: contiguous share; four independent running sums per thread (the loads are in flight together), fixed tree
-        const long long n_partial = (long long)V3_GROUPS * V7_CONSUMERS * (A.range[A.rank + 1] - A.range[A.rank]);
-        const long long per = (n_partial + gridDim.x - 1) / gridDim.x;
-        const long long lo = per * b < n_partial ? per * b : n_partial, hi = lo + per < n_partial ? lo + per : n_partial;
+        const long long p0 = (long long)V3_GROUPS * V7_CONSUMERS * A.range[A.rank], p1 = (long long)V3_GROUPS * V7_CONSUMERS * A.range[A.rank + 1];
+        const long long per = (p1 - p0 + gridDim.x - 1) / gridDim.x;
+        const long long lo = p0 + per * b < p1 ? p0 + per * b : p1, hi = lo + per < p1 ? lo + per : p1;
         double v[4] = {0.0, 0.0, 0.0, 0.0}, w[4] = {0.0, 0.0, 0.0, 0.0};
         long long i = lo + tid;
         for (; i + TAIL_THREADS < hi; i += 2 * TAIL_THREADS) {

@@ -137,9 +137,9 @@ static __global__ void k_window_need(const int *__restrict__ cell_of, int n_mol,
 }
 
 // Intramolecular Ewald correction (opt-in, not in the reference): Σ_mol Σ_{a<b} q_a q_b erf(κ r_ab)/r_ab, un-scaled, in two
-// deterministic stages like the charge sums.  r_ab is the plain separation (a rigid shift of the molecule — volume scaling,
-// periodic wrapping of the COM — does not change it).
-static __global__ void __launch_bounds__(256) k_intra_partial(const double4 *site, const int2 *mol, int n_mol, double kappa, double *part)
+// deterministic stages like the charge sums.  r_ab by the reference's minimum image in the RESIDENT box (a rigid shift of the
+// molecule — the volume scaling of a trial — does not change it).
+static __global__ void __launch_bounds__(256) k_intra_partial(const double4 *site, const int2 *mol, int n_mol, double kappa, double box, double *part)
 {
     __shared__ double s_red[8];
     double acc[1] = {0.0};
@@ -150,7 +150,7 @@ static __global__ void __launch_bounds__(256) k_intra_partial(const double4 *sit
             const double4 sa = site[mi.x + a];
             for (int b = a + 1; b < mi.y; ++b) {
                 const double4 sb = site[mi.x + b];
-                const double dx = sb.x - sa.x, dy = sb.y - sa.y, dz = sb.z - sa.z;
+                const double dx = min_image(sa.x, sb.x, box), dy = min_image(sa.y, sb.y, box), dz = min_image(sa.z, sb.z, box);
                 const double r = sqrt(dx * dx + dy * dy + dz * dz);
                 e += sa.w * sb.w * erf(kappa * r) / r;
             }

@@ -207,7 +207,7 @@ int intra_energy(mmc_handle *h, double kappa, double *e_unscaled)
 {
     if (!h->d_intra) CK(cudaMalloc(&h->d_intra, 257 * sizeof(double)));
     const int nb = std::max(1, std::min(256, (h->S.n_mol + 255) / 256));
-    k_intra_partial<<<nb, 256, 0, h->stream>>>(h->S.site, h->S.mol, h->S.n_mol, kappa, h->d_intra); LAUNCH_CHECK();
+    k_intra_partial<<<nb, 256, 0, h->stream>>>(h->S.site, h->S.mol, h->S.n_mol, kappa, h->S.box, h->d_intra); LAUNCH_CHECK();
     k_intra_final<<<1, 256, 0, h->stream>>>(h->d_intra, nb, h->d_intra + 256); LAUNCH_CHECK();
     CK(cudaMemcpyAsync(e_unscaled, h->d_intra + 256, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -322,6 +322,12 @@ int mmc_create(const mmc_config *cfg, mmc_handle **out)
     if ((e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_sites, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return fail("copy stream", e);
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if ((e = cudaStreamCreateWithPriority(&h->rk, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return fail("rk stream", e);
+    }
+    if ((e = cudaEventCreateWithFlags(&h->ev_rk, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     for (auto &ev : h->ev_chunk)
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     for (auto &ev : h->ev_copy)
@@ -349,6 +355,8 @@ int mmc_destroy(mmc_handle *h)
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_sites) cudaEventDestroy(h->ev_sites);
     if (h->copy) { cudaStreamSynchronize(h->copy); cudaStreamDestroy(h->copy); }
+    if (h->rk) { cudaStreamSynchronize(h->rk); cudaStreamDestroy(h->rk); }
+    if (h->ev_rk) cudaEventDestroy(h->ev_rk);
     for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->ev_copy) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -904,6 +912,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     if (k == "chain_cluster_atoms") { h->chain_cluster_atoms = (int)value; return MMC_OK; }
     if (k == "chain_cluster") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
+    if (k == "host_windows") { if (value < 1 || value > 4) FAIL(MMC_EINVAL, "host_windows must be 1..4"); h->host_windows = (int)value; return MMC_OK; }
     if (k == "v7_ctas_per_sm") { if (value < 1 || value > 4) FAIL(MMC_EINVAL, "v7_ctas_per_sm must be 1..4"); h->v7_ctas_per_sm = (int)value; return MMC_OK; }
     if (k == "host_chunks") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "host_chunks must be 1..8"); h->host_chunks = (int)value; return MMC_OK; }
     if (k == "rhok_split") {

@@ -29,6 +29,8 @@ struct EvalCtx {
     double *per_mol = nullptr;          // mmc_energy_all: [n_mol x 3] per-molecule rows (general kernel, evaluation order)
     int rhok_blocks = 0;                // rhok_external: CTAs whose partials sit in d_rhok_partial ...
     cudaEvent_t rhok_done = nullptr;    //                ... once this event has fired
+    int n_windows = 1;                  // mmc_potential_host, one GPU: home-cell windows evaluated as their sites arrive ...
+    const cudaEvent_t *win_wait = nullptr;   //                      ... each after this event
     bool partial_state = false;         // domain-decomposed host evaluation: only this rank's slab is resident, so a fall-back to
                                         // an unsharded evaluation is the caller's business (finalize_host returns 2)
 };
@@ -206,9 +208,9 @@ V7Grid v7_grid(const mmc_handle *h, int style, const EvalCtx &E)
 int v7_alloc(mmc_handle *h, int ncd, int EXY)
 {
     if (!h->d7_flags) {
-        CK(cudaMalloc(&h->d7_flags, 8 * sizeof(int)));
+        CK(cudaMalloc(&h->d7_flags, 16 * sizeof(int)));
         CK(cudaMalloc(&h->d7_block_sums, TAIL_BLOCKS * sizeof(double4)));
-        CK(cudaMalloc(&h->d7_range, (2 + MMC_PEER_MAX + 1) * sizeof(int)));
+        CK(cudaMalloc(&h->d7_range, 32 * sizeof(int)));
     }
     V7Grid G{};
     G.ncd = ncd; G.EX = EXY; G.EY = EXY;
@@ -234,6 +236,29 @@ int v7_alloc(mmc_handle *h, int ncd, int EXY)
     }
     return MMC_OK;
 }
+
+// MMC_TRACE_HOST=1: a timeline of mmc_potential_host (timing events on every stream, printed when the call returns)
+struct HostTrace {
+    bool on = false;
+    int n = 0;
+    cudaEvent_t ev[48] = {};
+    const char *name[48] = {};
+    void mark(cudaStream_t st, const char *what)
+    {
+        if (!on || n >= 48) return;
+        if (!ev[n]) cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], st);
+        name[n++] = what;
+    }
+    void dump()
+    {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        for (int i = 1; i < n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[i]); std::fprintf(stderr, "  %8.3f ms  %s\n", ms, name[i]); }
+        n = 0;
+    }
+};
+HostTrace g_trace;
 
 // Enqueues one evaluation on the v7 path and leaves this rank's partial-sum vector in d_vec.  finish: one rank — E_recip,
 // resident ρ(k) and the scalars in the mapped host slot come out of the same tail kernel.
@@ -265,7 +290,7 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     }
     // ---- binning (fractional COM coordinates do not change with the box: the buckets of an unchanged state are reused,
     // e.g. by consecutive volume trials) and the gather into the extended grid
-    CK(cudaMemsetAsync(h->d7_flags, 0, 8 * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d7_flags, 0, 16 * sizeof(int), h->stream));
     const int tb = 256;
     if (h->bin_version != h->state_version || h->bin_ncd != G.ncd || h->bin_world != E.world) {
         CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)G.ncd * G.ncd * G.ncd, h->stream));
@@ -278,19 +303,8 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     }
     if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
     unsigned int *fl = reinterpret_cast<unsigned int *>(h->d7_flags);
+    V7Args A{};
     {
-        Gather7Args A{S.com, S.site, h->d7_count, h->d7_bucket, G, E.f, h->d7_rows, h->d7_gf, h->d7_ecount,
-                      reinterpret_cast<unsigned long long *>(h->d7_flags), fl + 3, h->d7_flags + 4};
-        const int warps = G.EX * G.EY * (G.ncd + 1);
-        k_gather7<<<(warps + 7) / 8, 256, 0, h->stream>>>(A); LAUNCH_CHECK();
-    }
-    if (h->tm.on) { cudaEventRecord(h->tm.ev[5], h->stream); cudaEventRecord(h->tm.ev[0], h->stream); }
-    // ---- pairs
-    {
-        const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * G.ncd / E.world + 1;      // (about: the grid size only)
-        V7Args A{};
-        A.G = G;
-        A.rows = h->d7_rows; A.gf = h->d7_gf; A.ecount = h->d7_ecount;
         const double rcut = S.rc_qq, edge = G.edge;
         // conservative FP32 gate in the dot form |b|² − 2a·b < r_c² − |a|² on coordinates relative to the box centre
         // (components <= M = L/2 + edge, ghosts included): eight roundings of numbers <= 3M² and the input roundings
@@ -307,21 +321,41 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
                 if (A.qq_tab[a * 3 + b] < 0.0) A.qq_negmask |= 1u << (a * 3 + b);
             }
         A.lj_eps = h->lj[0].eps; A.lj_sig2 = h->lj[0].sig * h->lj[0].sig;
-        // −κ folded into the coefficients; DIRECT: also κ^2k, so the kernel runs Horner in r² itself
-        const bool direct = ep.ddeg > 0;
-        const int deg = direct ? ep.ddeg : ep.deg;
+    }
+    // −κ folded into the coefficients; DIRECT: also κ^2k, so the kernel runs Horner in r² itself
+    const bool direct = ep.ddeg > 0;
+    const int deg = direct ? ep.ddeg : ep.deg;
+    {
         double k2k = 1.0;
         for (int k = 0; k <= deg; ++k) {
             A.pc[k] = direct ? -E.kappa * ep.a[k] * k2k : -E.kappa * ep.c[k];
             k2k *= E.kappa * E.kappa;
         }
         A.pk2s = ep.kappa2 * ep.scale;
-        A.max_dev = reinterpret_cast<const double *>(h->d7_flags);
-        A.n_ovl = fl + 2; A.err_flag = fl + 3; A.ticket = fl + 5;
-        A.unit_partial = h->d7_unit_partial;
+    }
+    A.rows = h->d7_rows; A.gf = h->d7_gf; A.ecount = h->d7_ecount;
+    A.max_dev = reinterpret_cast<const double *>(h->d7_flags);
+    A.n_ovl = fl + 2; A.err_flag = fl + 3;
+    A.unit_partial = h->d7_unit_partial;
+    const int nwin = (E.world == 1 && E.n_windows > 1) ? E.n_windows : 1;
+    for (int w = 0; w < nwin; ++w) {
+        V7Grid Gw = G;
+        if (nwin > 1) {          // a window is a "rank" of the window partition: same kernels, same range mechanism
+            Gw.range = h->d7_range + 16; Gw.rank = w; Gw.world = nwin;
+            if (E.win_wait) CK(cudaStreamWaitEvent(h->stream, E.win_wait[w], 0));
+        }
+        Gather7Args Ga{S.com, S.site, h->d7_count, h->d7_bucket, Gw, E.f, h->d7_rows, h->d7_gf, h->d7_ecount,
+                       reinterpret_cast<unsigned long long *>(h->d7_flags), fl + 3, h->d7_flags + 4};
+        const int warps = G.EX * G.EY * (G.ncd + 1);
+        k_gather7<<<(warps + 7) / 8, 256, 0, h->stream>>>(Ga); LAUNCH_CHECK();
+        g_trace.mark(h->stream, "window gathered");
+        if (w == 0 && h->tm.on) { cudaEventRecord(h->tm.ev[5], h->stream); cudaEventRecord(h->tm.ev[0], h->stream); }
+        A.G = Gw; A.ticket = fl + 8 + w;
+        const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * G.ncd / (E.world * nwin) + 1;      // (about: the grid size only)
         const int grid = (int)std::max(1LL, std::min<long long>((long long)h->v7_ctas_per_sm * h->sm_count, units));
         if (!launch_pairs_v7(deg, direct, grid, h->stream, A)) FAIL(MMC_ECUDA, "k_pairs_v7: no instantiation for this polynomial degree (internal)");
         LAUNCH_CHECK();
+        g_trace.mark(h->stream, "window pairs done");
     }
     if (h->tm.on) cudaEventRecord(h->tm.ev[1], h->stream);
     if (forked) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
@@ -682,7 +716,8 @@ int evaluate_unsharded(mmc_handle *h, int style, EvalCtx E, double2 *dst0, doubl
         if (rc != 1) return rc;
         if (!escalate_pair_level(h)) FAIL(MMC_ECUDA, "pair kernel fallback chain exhausted (internal)");
         h->max_cell_cached = -1;
-        E.wait_sites = nullptr;                                       // the state is on the device by now
+        if (E.n_windows > 1 || E.wait_sites) { CK(cudaStreamSynchronize(h->side)); CK(cudaStreamSynchronize(h->rk)); }
+        E.wait_sites = nullptr; E.n_windows = 1; E.win_wait = nullptr;      // the state is on the device by now
     }
 }
 
@@ -1125,7 +1160,6 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
         if ((rc = mmc_upload_positions(h, coords, com))) return rc;
         return h->cfg.world > 1 && h->peer_ready == h->cfg.world ? mmc_potential_sharded(h, style, out) : mmc_potential(h, style, out);
     }
-    CK(cudaSetDevice(h->cfg.device));
     if ((rc = ensure_vec(h))) return rc;
     h->pair_level = h->pair_floor;
     if (h->pend_kind == 1) h->pend_kind = 0;
@@ -1133,47 +1167,97 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     double *d_coords = reinterpret_cast<double *>(h->d_raw);
     double *d_com = d_coords + 4 * (size_t)S.n_sites;
     const bool ewald = style == MMC_STYLE_EWALD;
-    // main stream: COMs
+    EvalCtx E{1.0, S.box, S.kappa, S.cfac, 0, 1};
+    ErfPoly ep{};
+    const int ncd = grid_cells(h, style, S.box);
+    const int nwin = (h->host_windows > 1 && v7_eligible(h, style, E, ep) && ncd >= 2 * h->host_windows) ? h->host_windows : 1;
+    g_trace.on = std::getenv("MMC_TRACE_HOST") != nullptr;
+    g_trace.mark(h->stream, "start");
+    // ---- main stream: COMs first (the cell binning needs nothing else; issued before the site chunks so that it is not queued
+    // behind them in the host->device copy engine)
     CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * S.n_mol, cudaMemcpyHostToDevice, h->stream));
+    g_trace.mark(h->stream, "COM copy done");
     CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
     k_repack_com<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(d_com, S.n_mol, S.box, S.com, h->d_info); LAUNCH_CHECK();
-    CK(cudaEventRecord(h->ev_fork, h->stream));
-    // copy stream: site chunks, each repacked as it lands; side stream: (Ewald) ρ(k) partials of a chunk as soon as it is in
-    CK(cudaStreamWaitEvent(h->copy, h->ev_fork, 0));
-    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    // ---- copy stream: the site array in chunks, nothing but copies (they follow the COMs through the copy engine; nothing of
+    // this call has to be waited for: the previous evaluation has returned); side stream: each chunk repacked as it lands — its
+    // stream order makes ev_chunk[c] mean "chunks 0..c are resident"; rk stream: (Ewald) the chunk's ρ(k) partials.
     int blocks = 0, cap = 0;
     if (ewald) {   // blocks a chunk needs (same formula as rhok_launch), to size the partial buffer once
         const bool v2 = h->n_kpairs <= 32 && S.nk <= 6 && h->use_rhok_v2;
         const int ck = v2 ? RHOK2_SITES : RHOK_SITES;
         for (int c = 0; c < nchunk; ++c) {
             const int n = (int)((long long)S.n_sites * (c + 1) / nchunk) - (int)((long long)S.n_sites * c / nchunk);
-            int per = std::max(2 * ck, (n + 2 * h->sm_count - 1) / (2 * h->sm_count));
+            const int waves = 2 * h->sm_count * std::max(1, h->rhok_split);
+            int per = std::max(2 * ck, (n + waves - 1) / waves);
             per = (per + ck - 1) / ck * ck;
             cap += std::max(1, (n + per - 1) / per);
         }
     }
     for (int c = 0; c < nchunk; ++c) {
         const int s0 = (int)((long long)S.n_sites * c / nchunk), s1 = (int)((long long)S.n_sites * (c + 1) / nchunk);
-        // the copy stream carries nothing but copies; repack + ρ(k) partials of the chunk follow on the side stream
         CK(cudaMemcpyAsync(d_coords + 3 * (size_t)s0, coords + 3 * (size_t)s0, sizeof(double) * 3 * (size_t)(s1 - s0), cudaMemcpyHostToDevice, h->copy));
         CK(cudaEventRecord(h->ev_copy[c], h->copy));
+        g_trace.mark(h->copy, "chunk copy done");
         CK(cudaStreamWaitEvent(h->side, h->ev_copy[c], 0));
         k_repack_sites<<<(s1 - s0 + 255) / 256, 256, 0, h->side>>>(d_coords, s0, s1, S.site); LAUNCH_CHECK();
-        CK(cudaEventRecord(c == nchunk - 1 ? h->ev_sites : h->ev_chunk[c], h->side));
+        g_trace.mark(h->side, "chunk repacked");
+        cudaEvent_t evc = c == nchunk - 1 ? h->ev_sites : h->ev_chunk[c];
+        CK(cudaEventRecord(evc, h->side));
         if (ewald) {
             int nb = 0;
-            if ((rc = rhok_launch(h, S.site, s0, s1, S.box, nullptr, h->side, blocks, &nb, cap))) return rc;
+            CK(cudaStreamWaitEvent(h->rk, evc, 0));
+            if ((rc = rhok_launch(h, S.site, s0, s1, S.box, nullptr, h->rk, blocks, &nb, cap))) return rc;
+            g_trace.mark(h->rk, "chunk rho(k) partial done");
             blocks += nb;
         }
     }
-    CK(cudaEventRecord(h->ev_join, h->side));
+    CK(cudaEventRecord(h->ev_join, ewald ? h->rk : h->side));
     h->state_version++;                                         // new positions: the cell buckets are rebuilt
     h->partial_resident = false;
     h->last_h2d_bytes = (long long)sizeof(double) * 3 * ((long long)S.n_sites + S.n_mol);
-    EvalCtx E{1.0, S.box, S.kappa, S.cfac, 0, 1};
-    E.wait_sites = h->ev_sites; E.rhok_external = true; E.rhok_blocks = blocks; E.rhok_done = h->ev_join;
     CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    E.rhok_external = true; E.rhok_blocks = blocks; E.rhok_done = h->ev_join;
+    cudaEvent_t win_ev[4];
+    if (nwin > 1) {
+        // The home cells are cut into nwin contiguous ranges; a window's gather and its pair kernel start as soon as the chunk
+        // that completes the rows it reads has landed, while later chunks are still on the bus.  Which chunk that is follows
+        // from the cell of every molecule — known now: the COMs are in.  (A spatially coherent order — a lattice start, a sorted
+        // restart — lets the windows start early; for a random order every window needs the last chunk.)
+        if ((rc = v7_alloc(h, ncd, ncd + 2))) return rc;
+        const V7Grid G = v7_grid(h, style, E);
+        const int ncell = ncd * ncd * ncd;
+        if (h->win_ncd != ncd || h->win_n != nwin) {
+            int wr[8];
+            for (int w = 0; w <= nwin; ++w) wr[w] = (int)((long long)ncell * w / nwin);
+            CK(cudaMemcpyAsync(h->d7_range + 16, wr, sizeof(int) * (nwin + 1), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            h->win_ncd = ncd; h->win_n = nwin;
+        }
+        CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)ncell, h->stream));
+        Bin7Args B{S.com, S.n_mol, (double)ncd / S.box, G, h->d7_count, h->d7_bucket, h->d_cell_of};
+        k_bin7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(B); LAUNCH_CHECK();
+        h->bin_version = h->state_version; h->bin_ncd = ncd; h->bin_world = 1;
+        CK(cudaMemsetAsync(h->d7_range + 24, 0, 4 * sizeof(int), h->stream));
+        V7Grid Gw = G; Gw.range = h->d7_range + 16; Gw.world = nwin;
+        k_window_need7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->d_cell_of, S.n_mol, h->US, S.n_sites, nchunk, Gw, nwin, h->d7_range + 24); LAUNCH_CHECK();
+        int need[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(need, h->d7_range + 24, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        g_trace.mark(h->stream, "binned, window needs known");
+        CK(cudaStreamSynchronize(h->stream));          // ~0.15 ms into the call; the site chunks are in flight on the copy stream meanwhile
+        for (int w = 0; w < nwin; ++w) {
+            int c = std::max(0, std::min(need[w], nchunk - 1));
+            if (w > 0) c = std::max(c, std::max(0, std::min(need[w - 1], nchunk - 1)));
+            need[w] = c;
+            win_ev[w] = (c == nchunk - 1) ? h->ev_sites : h->ev_chunk[c];
+        }
+        E.n_windows = nwin; E.win_wait = win_ev;
+    } else {
+        E.wait_sites = h->ev_sites;
+    }
     rc = evaluate_unsharded(h, style, E, S.rhok[0], S.rhok[1], out);
+    g_trace.mark(h->stream, "result published");
+    g_trace.dump();
     if (rc < 0) return rc;
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");

@@ -22,9 +22,14 @@ struct mmc_handle {
     bool own_stream = false;
     cudaStream_t side = nullptr;         // the ρ(k) rebuild of a full evaluation runs here, beside binning + pair kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sites = nullptr;
-    cudaStream_t copy = nullptr;         // mmc_potential_host: host->device chunks; repack + ρ(k) partials follow on `side`
+    cudaStream_t copy = nullptr;         // mmc_potential_host: host->device chunks (nothing else); repack follows on `side`,
+    cudaStream_t rk = nullptr;           //                     the chunks' ρ(k) partials on `rk` (they cannot co-reside with the pair kernel
+                                         //                     and must not hold back the "chunk resident" events behind them)
+    cudaEvent_t ev_rk = nullptr;
     cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int host_windows = 3;                // mmc_potential_host, one GPU: home-cell windows evaluated as their sites arrive (1: wait for all sites)
+    int win_ncd = 0, win_n = 0;
     int host_chunks = 6;                 // mmc_potential_host: pieces the site array is uploaded in (mmc_debug_set "host_chunks", 1..8)
     int overlap_rhok = 1;                // mmc_debug_set "overlap_rhok": 0 = everything on one stream
     std::string err;

@@ -304,17 +304,17 @@ double ora_EwaldSelf(const ora_ewald *ew, int64_t n, const double *q)
 /* NOT in the reference (Ewald/energy.jl:1008-1021 adds recip + self and nothing else): the intramolecular correction of the
  * Ewald sum, E_intra = -factor * sum_molecules sum_{a<b in molecule} q_a q_b erf(kappa r_ab) / r_ab, which removes the
  * interaction of a site with the screening clouds of its own molecule's sites that the k-space term contains.  Twin of the
- * engine's opt-in mmc_set_intramolecular; r_ab is the plain (un-wrapped) separation: a molecule's sites are
- * kept together by the reference (only COMs are wrapped, boundaries.jl:16-26). */
-double ora_EwaldIntra(const ora_system *s, double kappa, double factor)
+ * engine's opt-in mmc_set_intramolecular; r_ab by the reference's own minimum image (vector1D), so a molecule
+ * stored across the periodic boundary (the NIST files) is handled like one stored whole. */
+double ora_EwaldIntraBox(const ora_system *s, double kappa, double factor, double box)
 {
     double tot = 0.0;
     for (int64_t m = 0; m < s->n_mol; ++m) {
         double e = 0.0;
         for (int64_t a = s->first_atom[m] - 1; a < s->last_atom[m]; ++a)
             for (int64_t b = a + 1; b < s->last_atom[m]; ++b) {
-                const double dx = s->coords[3 * b] - s->coords[3 * a], dy = s->coords[3 * b + 1] - s->coords[3 * a + 1],
-                             dz = s->coords[3 * b + 2] - s->coords[3 * a + 2];
+                const double dx = ora_vector1D(s->coords[3 * a], s->coords[3 * b], box), dy = ora_vector1D(s->coords[3 * a + 1], s->coords[3 * b + 1], box),
+                             dz = ora_vector1D(s->coords[3 * a + 2], s->coords[3 * b + 2], box);
                 const double r = sqrt(dx * dx + dy * dy + dz * dz);
                 e += s->charge[a] * s->charge[b] * erf(kappa * r) / r;
             }

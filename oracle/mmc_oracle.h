@@ -77,7 +77,7 @@ double ora_RecipLong(ora_ewald *ew, int64_t n, const double *r, const double *q,
 double ora_RecipMove(double box, ora_ewald *ew, int64_t n, const double *r_old,
                      const double *r_new, const double *q);
 double ora_EwaldSelf(const ora_ewald *ew, int64_t n, const double *q);
-double ora_EwaldIntra(const ora_system *s, double kappa, double factor);
+double ora_EwaldIntraBox(const ora_system *s, double kappa, double factor, double box);
 void ora_recip_commit(ora_ewald *ew);    /* Ewald/main.jl:621 */
 void ora_recip_rollback(ora_ewald *ew);  /* Ewald/main.jl:628 */
 

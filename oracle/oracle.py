@@ -187,12 +187,13 @@ def EwaldShort(i, s: System, ew: Ewald, qq_rcut, box):
     return e.value, v.value, bool(ov.value)
 
 
-def EwaldIntra(s: System, kappa, factor):
-    """Intramolecular correction (not in the reference; twin of the engine's opt-in flag): -factor Σ_mol Σ_{a<b} q_a q_b erf(κ r)/r."""
+def EwaldIntra(s: System, kappa, factor, box):
+    """Intramolecular correction (not in the reference; twin of the engine's opt-in flag): -factor Σ_mol Σ_{a<b} q_a q_b erf(κ r)/r,
+    r by the reference's minimum image."""
     cs = s.c()
-    f = lib().ora_EwaldIntra
+    f = lib().ora_EwaldIntraBox
     f.restype = C.c_double
-    return f(C.byref(cs), C.c_double(kappa), C.c_double(factor))
+    return f(C.byref(cs), C.c_double(kappa), C.c_double(factor), C.c_double(box))
 
 
 def RecipLong(ew: Ewald, r, q, box):

@@ -125,20 +125,23 @@ def test_full_size_volume_identity_and_rhok_delta(cfg_e):
 
 def test_full_size_potential_host(cfg_e):
     """mmc_potential_host at full size: COMs first (binning), sites in chunks with the rho(k) partials of each chunk computed as
-    it lands, gather + pair kernel when the last chunk is in.  Same Properties as upload + potential() for the lattice order and
-    for a random molecule order, with 1..8 chunks."""
+    it lands, the home cells cut into windows that are gathered and evaluated while later chunks are still on the bus.  Same
+    Properties as upload + potential() for the lattice order (windows really start early) and for a random molecule order (every
+    window needs the last chunk), with 1..4 windows and 1..8 chunks."""
     from metropolismontecarlo_b200.energy import water_engine
     ms, eng = cfg_e
     ref = eng.potential("ewald")
     fields = ("energy", "virial", "coulomb", "lj", "real", "recip", "self_")
-    for chunks in (4, 8, 5, 2, 1):
+    for windows, chunks in ((4, 8), (1, 4), (4, 4), (3, 5), (2, 2), (4, 1)):
+        eng.debug_set("host_windows", windows)
         eng.debug_set("host_chunks", chunks)
         for style in ("ewald", "wolf"):
             got = eng.potential_host(ms.coords, ms.com, style)
             want = ref if style == "ewald" else eng.potential("wolf")
             for f in fields:
-                assert rel(getattr(got, f), getattr(want, f)) < 1e-12, (chunks, style, f)
+                assert rel(getattr(got, f), getattr(want, f)) < 1e-12, (windows, chunks, style, f)
             assert got.overlaps == 0
+    eng.debug_set("host_windows", 3)
     eng.debug_set("host_chunks", 6)
     # a random molecule order: same energy (to summation order)
     perm = np.random.default_rng(3).permutation(N_E)

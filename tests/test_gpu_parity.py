@@ -878,10 +878,11 @@ def test_intramolecular_correction_is_opt_in():
         assert ref.intra == 0.0
         eng.set_intramolecular(True)
         got = eng.potential("ewald")
-        want = ora.EwaldIntra(s, kappa, systems.FACTOR)
-        assert want < 0 and rel(got.intra, want) < 1e-12
-        assert rel(got.energy, ref.energy + want) < 1e-12 and rel(got.coulomb, ref.coulomb + want) < 1e-12
-        assert rel(got.virial, ref.virial + want / 3) < 1e-12
+        want = ora.EwaldIntra(s, kappa, systems.FACTOR, ms.box)
+        assert want > 0 and rel(got.intra, want) < 1e-12       # (q_O q_H < 0 dominates: the correction raises the energy)
+        # (E_intra nearly cancels E_self: compare on the scale of the terms)
+        assert abs(got.energy - (ref.energy + want)) < 1e-12 * abs(ref.energy) and abs(got.coulomb - (ref.coulomb + want)) < 1e-12 * abs(ref.coulomb)
+        assert abs(got.virial - (ref.virial + want / 3)) < 1e-12 * max(abs(ref.virial), abs(want))
         for f in ("lj", "real", "recip", "self_"):
             assert getattr(got, f) == getattr(ref, f)
         assert eng.potential("wolf").intra == 0.0           # an Ewald-sum term only
@@ -889,7 +890,7 @@ def test_intramolecular_correction_is_opt_in():
             L2 = ms.box * 1.02
             v = eng.volume_trial(L2, systems.ALPHA / L2, "ewald")
             eng.volume_reject()
-            assert rel(v.intra, ora.EwaldIntra(s, systems.ALPHA / L2, systems.FACTOR)) < 1e-12      # rigid shift: same r_ab, new κ
+            assert rel(v.intra, ora.EwaldIntra(s, systems.ALPHA / L2, systems.FACTOR, ms.box)) < 1e-12      # rigid shift: same r_ab, new κ
         eng.set_intramolecular(False)
         assert eng.potential("ewald").energy == ref.energy
         eng.close()
