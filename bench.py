@@ -343,6 +343,32 @@ def replica_moves(local_rank, world, dev, n_moves=10_000):
                     "uniforms H2D + results D2H inside the timed region, max over ranks"}
 
 
+def e2_large_k(ms, fp64_peak):
+    """SURVEY 8d "E2" (labelled extension): config E with a converged k-space sum — kappa = 0.32 /A (kappa r_cut = 3.2), nk = 12,
+    k^2 < 145: 3796 k-vectors instead of the reference's 337 — through k_rhok_big."""
+    from metropolismontecarlo_b200.energy import Engine
+    eng = Engine()
+    eng.upload_system(ms, RC, RC)
+    nkv = eng.PrepareEwaldVariables(0.32, 12, 145)
+    eng.set_timing(True)
+    eng.debug_set("overlap_rhok", 0)
+    rows = []
+    for _ in range(8):
+        t0 = time.perf_counter()
+        p = eng.potential("ewald")
+        w = time.perf_counter() - t0
+        t = eng.last_timings()
+        rows.append((t["pairs_ms"], t["rhok_ms"], 1e3 * w))
+    r = np.median(np.array(rows[2:]), axis=0)
+    flops = (FLOP_PER_SITE_K * nkv + 168) * ms.n_sites + 6 * nkv
+    eng.close()
+    return {"what": "extension, not a reference configuration: kappa = 0.32 /A (kappa r_cut = 3.2), nk = 12, k^2 < 145", "k_vectors": nkv,
+            "evals_per_s": 1e3 / r[2], "ms_per_eval_wall": float(r[2]), "kernel_ms": {"pairs": float(r[0]), "rhok_rebuild": float(r[1])},
+            "rhok_kernel": "k_rhok_big", "rhok_algorithmic_tflops": flops / (r[1] * 1e-3) / 1e12,
+            "rhok_frac_of_fp64_peak": (flops / (r[1] * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
+            "energy_per_molecule_K": p.energy / ms.n_mol}
+
+
 def replicas_one_gpu(n_rep=15, n_moves=10_000, cluster=8):
     """Per-move paths do not shard, and one chain uses 8 of the 148 SMs (k_chains: one 8-CTA cluster).  So ONE GPU runs R
     independent replicas of config A at once: R handles, R streams, R host threads (what R Julia processes sharing a GPU would
@@ -598,6 +624,11 @@ def run_ours(args, rank, world, local_rank):
                 line["moves"]["A_spce750_ewald"].pop("_acc_sum", None)
         if replicas is not None:
             line["moves"] = {"A_spce750_ewald_replicas": replicas}
+        if world == 1 and ms.n_mol == N_MOL_E and not args.no_moves:
+            try:
+                line["e2_large_k"] = e2_large_k(ms, fp64_peak)
+            except Exception as e:
+                line["e2_large_k"] = {"error": str(e)}
         emit(line)
     eng.close()
     if world > 1:

@@ -6,9 +6,9 @@
 // Decomposition: sites are split over CTAs (and over ranks when sharded); inside a CTA the
 // sites stream through shared memory in sub-chunks whose per-site tables (q·e^{ikx}, e^{iky},
 // e^{ikz}, k = 0..nk; negative k by conjugation, ewalds.jl:566-567,581-582) are built by the
-// same recurrence the reference uses; every thread owns KPT k-vectors and keeps their complex
-// accumulators in registers.  Per-CTA partial sums go to HBM and are folded in CTA order by
-// k_rhok_reduce, so the result is deterministic.  FP64 accumulation throughout.
+// same recurrence the reference uses; a lane owns one (kx, |ky|) pair and keeps the accumulators of
+// its kz values in registers (k_rhok_pairs for nk <= 6, k_rhok_big beyond).  Per-CTA partial sums go
+// to HBM and are folded in CTA order, so the result is deterministic.  FP64 accumulation throughout.
 #pragma once
 #include "mmc_common.cuh"
 
@@ -40,68 +40,6 @@ __device__ __forceinline__ double rhok_coord(const double4 &s, int d, const doub
         x = x + (f * cd - cd);
     }
     return x;
-}
-
-template <int KPT>
-static __global__ void __launch_bounds__(RHOK_BLOCK) k_rhok_partial(RhokArgs A)
-{
-    __shared__ cplx s_e[RHOK_SITES][3][MMC_MAX_NK + 1];
-    const int tid = threadIdx.x;
-    const int c0 = A.s_begin + blockIdx.x * A.per_block;
-    const int c1 = min(A.s_end, c0 + A.per_block);
-    const double twopi = 2.0 * 3.141592653589793;
-    int kx[KPT], ky[KPT], kz[KPT];
-    bool ny[KPT], nz[KPT];
-    double are[KPT], aim[KPT];
-#pragma unroll
-    for (int u = 0; u < KPT; ++u) {
-        const int k = tid + u * RHOK_BLOCK;
-        int4 kv = make_int4(0, 0, 0, 0);
-        if (k < A.nkvecs) kv = A.kvec[k];
-        kx[u] = kv.x; ky[u] = abs(kv.y); kz[u] = abs(kv.z);
-        ny[u] = kv.y < 0; nz[u] = kv.z < 0;
-        are[u] = 0.0; aim[u] = 0.0;
-    }
-    for (int base = c0; base < c1; base += RHOK_SITES) {
-        __syncthreads();
-        if (tid < RHOK_SITES * 3) {
-            const int l = tid / 3, d = tid - 3 * l;
-            double x = 0.0, q = 0.0;
-            if (base + l < c1) {
-                const double4 s = A.site[base + l];
-                x = rhok_coord(s, d, A.com, A.f, A.US, base + l);
-                q = s.w;
-            }
-            const double sc = (d == 0) ? q : 1.0;      // charge folded into the x table: (q*ex)*ey*ez
-            cplx e1;
-            sincos(twopi * x / A.box, &e1.im, &e1.re);  // ewalds.jl:561-564
-            cplx e; e.re = 1.0; e.im = 0.0;
-            cplx st; st.re = sc * e.re; st.im = sc * e.im;
-            s_e[l][d][0] = st;
-            e = e1;
-            for (int k = 1; k <= A.nk; ++k) {
-                st.re = sc * e.re; st.im = sc * e.im;
-                s_e[l][d][k] = st;
-                e = cmul(e, e1);                         // ewalds.jl:573-575
-            }
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int l = 0; l < RHOK_SITES; ++l) {
-#pragma unroll
-            for (int u = 0; u < KPT; ++u) {
-                const cplx t = cmul(cmul(s_e[l][0][kx[u]], cconj_if(s_e[l][1][ky[u]], ny[u])),
-                                    cconj_if(s_e[l][2][kz[u]], nz[u]));
-                are[u] += t.re;
-                aim[u] += t.im;
-            }
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < KPT; ++u) {
-        const int k = tid + u * RHOK_BLOCK;
-        if (k < A.nkvecs) A.partial[(size_t)blockIdx.x * A.nkvecs + k] = make_double2(are[u], aim[u]);
-    }
 }
 
 // ρ(k) = Σ_b partial[b][k] → out[k].  blockDim = (32 k, 32 slices): each slice folds a contiguous 1/32 of the
@@ -264,6 +202,126 @@ static __global__ void __launch_bounds__(RHOK2_BLOCK, 2) k_rhok_pairs(Rhok2Args 
     for (int kz = 1; kz <= NK; ++kz) {
         const double *a = acc + 4 + 8 * (kz - 1);
         put(+1, +1, kz, a[0] - a[1], a[2] + a[3]);
+        put(+1, -1, kz, a[0] + a[1], a[3] - a[2]);
+        if (ky > 0) {
+            put(-1, +1, kz, a[4] - a[5], a[6] + a[7]);
+            put(-1, -1, kz, a[4] + a[5], a[7] - a[6]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_rhok_big — the (kx, |ky|)-per-lane register blocking of k_rhok_pairs for LARGE k-sets (nk up to 16: a converged
+// Ewald sum at κ·r_cut ≈ 3.2 needs nk ≈ 12, 3.6 k k-vectors; SURVEY §8d "E2").  The (nk+1)² pairs no longer fit one
+// warp-width and the 8·nk accumulators no longer fit the register file, so the k-set is cut into COMBOS = (tile of 32
+// pairs) x (tile of RHOKB_ZT kz values): one combo per warp, accumulators in registers (4 + 8·ZT doubles), every warp of
+// the CTA walks ALL sites of the CTA's chunk (the e^{ik·r} tables of a sub-chunk are built once, cooperatively, by the
+// reference's recurrence, ewalds.jl:556-585, and read by all eight combos).  gridDim.y covers the combos in groups of eight;
+// CTAs of different y rebuild the tables of the same sites — 3 sincos + 3·nk complex products per site against
+// 8 x 32 x (8·ZT + 8) DFMA: under 2 %.  A CTA writes complete per-chunk partials for ITS k-vectors only, so the partial
+// array [chunk][k] is the same as k_rhok_pairs' and the same tail folds it.  Sharding by k-RANGES (north star: "k-vector
+// ranges split per GPU") is a range of combo groups per rank: every rank then sums all sites for its k-vectors, and the
+// vectors the ranks exchange have disjoint support.
+// ------------------------------------------------------------------------------------------
+#define RHOKB_BLOCK 256
+#define RHOKB_WARPS (RHOKB_BLOCK / 32)
+#define RHOKB_SITES 64     // sites per sub-chunk: tables in dynamic shared memory, 64 x 3 x ((nk+1)|1) x 16 B (40 KB at nk = 12)
+#define RHOKB_ZT 6
+#define MMC_MAX_NK_FULL 16     // the full-energy k-space path (per-move kernels: MMC_MAX_NK)
+
+struct RhokBigArgs {
+    const double4 *site;
+    int s_begin, s_end, per_block;
+    int nk, nkvecs;
+    const int *kindex;           // [(nk+1) x (2nk+1) x (2nk+1)] index of (kx, ky, kz) in the k list or -1
+    double box;
+    double2 *partial;            // [gridDim.x][nkvecs]
+    const double4 *com;          // volume trial on the resident state (NULL: sites as they are), as RhokArgs
+    double f;
+    int US;
+    int n_ptiles, n_ztiles;      // combos = n_ptiles x n_ztiles; combo c = pt * n_ztiles + zt
+    int group_begin;             // first combo group of this launch (k-range sharding: a rank's share of the groups)
+};
+
+static __global__ void __launch_bounds__(RHOKB_BLOCK, 2) k_rhok_big(const __grid_constant__ RhokBigArgs A)
+{
+    constexpr int ZT = RHOKB_ZT;
+    constexpr int NACC = 4 + 8 * ZT;
+    extern __shared__ __align__(16) double2 s_tab[];        // [RHOKB_SITES][3][TS], TS = (nk+1)|1 (odd: conflict-free row builds)
+    const int TS = (A.nk + 1) | 1;
+    auto s_t = [&](int l, int d, int k) -> double2 & { return s_tab[(l * 3 + d) * TS + k]; };
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = A.s_begin + blockIdx.x * A.per_block;
+    const int c1 = min(A.s_end, c0 + A.per_block);
+    const double twopi = 2.0 * 3.141592653589793;
+    const int NK = A.nk, W1 = NK + 1;
+    const int combo = (A.group_begin + blockIdx.y) * RHOKB_WARPS + warp;
+    const bool live = combo < A.n_ptiles * A.n_ztiles;
+    const int pt = live ? combo / A.n_ztiles : 0, zt = live ? combo - pt * A.n_ztiles : 0;
+    const int pi = pt * 32 + lane;
+    const bool lane_on = live && pi < W1 * W1;
+    const int kx = lane_on ? pi / W1 : 0, ky = lane_on ? pi - (pi / W1) * W1 : 0;
+    const int kz0 = zt * ZT + 1;                 // this tile's kz = kz0 .. kz0 + ZT − 1 (kz = 0 rides with tile 0)
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+    for (int base = c0; base < c1; base += RHOKB_SITES) {
+        __syncthreads();
+        if (tid < RHOKB_SITES * 3) {
+            const int l = tid / 3, d = tid - 3 * l;
+            double x = 0.0, q = 0.0;
+            if (base + l < c1) {
+                const double4 s = A.site[base + l];
+                x = rhok_coord(s, d, A.com, A.f, A.US, base + l);
+                q = s.w;
+            }
+            const double sc = (d == 0) ? q : 1.0;      // charge folded into the x table: (q·e_x)·e_y·e_z, ewalds.jl:592-596
+            cplx e1;
+            sincos(twopi * x / A.box, &e1.im, &e1.re);  // ewalds.jl:561-564
+            s_t(l, d, 0) = make_double2(sc, 0.0);
+            cplx e = e1;
+            for (int k = 1; k <= NK; ++k) {
+                s_t(l, d, k) = make_double2(sc * e.re, sc * e.im);
+                e = cmul(e, e1);                         // ewalds.jl:573-575
+            }
+        }
+        __syncthreads();
+        if (!live) continue;
+#pragma unroll 2
+        for (int l = 0; l < RHOKB_SITES; ++l) {
+            const double2 ex = s_t(l, 0, kx), ey = s_t(l, 1, ky);
+            const double p1 = ex.x * ey.x, p2 = ex.y * ey.y, p3 = ex.y * ey.x, p4 = ex.x * ey.y;
+            const double ur = p1 - p2, ui = p3 + p4, vr = p1 + p2, vi = p3 - p4;
+            acc[0] += ur; acc[1] += ui; acc[2] += vr; acc[3] += vi;       // kz = 0 (used by tile 0 only)
+#pragma unroll
+            for (int z = 0; z < ZT; ++z) {
+                if (kz0 + z <= NK) {                                       // uniform
+                    const double2 ez = s_t(l, 2, kz0 + z);                 // same address in every lane: broadcast
+                    double *a = acc + 4 + 8 * z;
+                    a[0] = fma(ur, ez.x, a[0]); a[1] = fma(ui, ez.y, a[1]); a[2] = fma(ur, ez.y, a[2]); a[3] = fma(ui, ez.x, a[3]);
+                    a[4] = fma(vr, ez.x, a[4]); a[5] = fma(vi, ez.y, a[5]); a[6] = fma(vr, ez.y, a[6]); a[7] = fma(vi, ez.x, a[7]);
+                }
+            }
+        }
+    }
+    if (!lane_on) return;
+    const int W = 2 * NK + 1;
+    double2 *out = A.partial + (size_t)blockIdx.x * A.nkvecs;
+    auto put = [&](int sy, int sz, int kz, double re, double im) {
+        const int idx = A.kindex[(kx * W + (sy * ky + NK)) * W + (sz * kz + NK)];
+        if (idx >= 0) out[idx] = make_double2(re, im);
+    };
+    if (zt == 0) {
+        put(+1, +1, 0, acc[0], acc[1]);
+        if (ky > 0) put(-1, +1, 0, acc[2], acc[3]);
+    }
+#pragma unroll
+    for (int z = 0; z < ZT; ++z) {
+        const int kz = kz0 + z;
+        if (kz > NK) break;
+        const double *a = acc + 4 + 8 * z;
+        put(+1, +1, kz, a[0] - a[1], a[2] + a[3]);      // negative k by conjugation, ewalds.jl:566-567
         put(+1, -1, kz, a[0] + a[1], a[3] - a[2]);
         if (ky > 0) {
             put(-1, +1, kz, a[4] - a[5], a[6] + a[7]);

@@ -585,7 +585,7 @@ int mmc_ewald_prepare(mmc_handle *h, double kappa, int32_t nk, int32_t k_sq_max,
 {
     if (!h) return MMC_EINVAL;
     if (!h->has_system) FAIL(MMC_ESTATE, "upload the system before mmc_ewald_prepare (cfac depends on the box)");
-    if (!(kappa > 0) || nk < 1 || nk > MMC_MAX_NK || k_sq_max < 2) FAIL(MMC_EINVAL, "bad Ewald parameters (1 <= nk <= 8)");
+    if (!(kappa > 0) || nk < 1 || nk > 16 || k_sq_max < 2) FAIL(MMC_EINVAL, "bad Ewald parameters (1 <= nk <= 16)");
     CK(cudaSetDevice(h->cfg.device));
     free_ewald(h);
     fill_kvectors(nk, k_sq_max, h->kxyz);
@@ -717,6 +717,7 @@ int mmc_recip_move(mmc_handle *h, const double *r_old, const double *r_new, cons
     if (!h) return MMC_EINVAL;
     if (!h->has_system || !h->has_ewald) FAIL(MMC_ESTATE, "system and Ewald tables required");
     if (!r_old || !r_new || !q || n < 1 || n > MMC_MAX_SITES) FAIL(MMC_EINVAL, "bad arguments (1 <= n <= 16)");
+    if (h->S.nk > MMC_MAX_NK) FAIL(MMC_EINVAL, "the per-move k-space kernels are sized for nk <= 8 (the full-energy path takes nk <= 16)");
     MoveArgs A{};
     A.i = 0; A.n_cfg = 0; A.tiles = 0; A.cur = h->cur;
     A.recip_blocks = (h->S.nkvecs + MOVE_BLOCK - 1) / MOVE_BLOCK;
@@ -790,6 +791,7 @@ int mmc_trial_move(mmc_handle *h, int64_t i, const double com_new[3], const doub
     if (rc) return rc;
     if ((rc = style_check(h, style))) return rc;
     if (style == MMC_STYLE_LJ_ATOMS || !com_new || !sites_new || !out) FAIL(MMC_EINVAL, "bad arguments");
+    if (style == MMC_STYLE_EWALD && h->S.nk > MMC_MAX_NK) FAIL(MMC_EINVAL, "the per-move k-space kernels are sized for nk <= 8 (the full-energy path takes nk <= 16)");
     MoveArgs &A = h->last;
     A = MoveArgs{};
     A.i = (int)(i - 1); A.n_cfg = 2; A.tiles = move_tiles(h);
@@ -912,6 +914,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     if (k == "chain_cluster_atoms") { h->chain_cluster_atoms = (int)value; return MMC_OK; }
     if (k == "chain_cluster") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
+    if (k == "rhok_kshard") { h->rhok_kshard = value != 0; return MMC_OK; }
     if (k == "host_windows") { if (value < 1 || value > 4) FAIL(MMC_EINVAL, "host_windows must be 1..4"); h->host_windows = (int)value; return MMC_OK; }
     if (k == "v7_ctas_per_sm") { if (value < 1 || value > 4) FAIL(MMC_EINVAL, "v7_ctas_per_sm must be 1..4"); h->v7_ctas_per_sm = (int)value; return MMC_OK; }
     if (k == "host_chunks") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "host_chunks must be 1..8"); h->host_chunks = (int)value; return MMC_OK; }

@@ -47,8 +47,18 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
     const int n = s_end - s_begin;
     const int nkv = h->S.nkvecs;
     const bool v2 = h->n_kpairs <= 32 && h->S.nk <= 6 && h->use_rhok_v2;
-    const int chunk = v2 ? RHOK2_SITES : RHOK_SITES;
-    const int waves = 2 * h->sm_count * std::max(1, h->rhok_split);
+    const bool big = !v2;                       // large k-sets: combos of (32 pairs) x (6 kz) per warp, k_rhok_big
+    const int chunk = v2 ? RHOK2_SITES : RHOKB_SITES;
+    const int W1 = h->S.nk + 1;
+    const int n_ptiles = (W1 * W1 + 31) / 32, n_ztiles = std::max(1, (h->S.nk + RHOKB_ZT - 1) / RHOKB_ZT);
+    const int n_groups = (n_ptiles * n_ztiles + RHOKB_WARPS - 1) / RHOKB_WARPS;
+    int g0 = 0, g1 = n_groups;
+    if (big && h->rhok_kshard && h->cfg.world > 1 && com == nullptr && s_begin == 0 && s_end == h->S.n_sites) {
+        // k-RANGE sharding (north star): this rank sums ALL sites for its share of the combo groups
+        g0 = (int)((long long)n_groups * h->cfg.rank / h->cfg.world);
+        g1 = (int)((long long)n_groups * (h->cfg.rank + 1) / h->cfg.world);
+    }
+    const int waves = std::max(1, 2 * h->sm_count * std::max(1, h->rhok_split) / (big ? std::max(1, g1 - g0) : 1));
     int per = std::max(2 * chunk, (n + waves - 1) / waves);
     per = (per + chunk - 1) / chunk * chunk;
     const int nb = std::max(1, (n + per - 1) / per);
@@ -74,13 +84,12 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
             default: k_rhok_pairs<6><<<nb, RHOK2_BLOCK, 0, st>>>(R); break;
         }
     } else {
-        RhokArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->S.kvec, box, part, com, f, US};
-        const int kpt = (nkv + RHOK_BLOCK - 1) / RHOK_BLOCK;
-        if (kpt <= 1) k_rhok_partial<1><<<nb, RHOK_BLOCK, 0, st>>>(R);
-        else if (kpt <= 2) k_rhok_partial<2><<<nb, RHOK_BLOCK, 0, st>>>(R);
-        else if (kpt <= 4) k_rhok_partial<4><<<nb, RHOK_BLOCK, 0, st>>>(R);
-        else if (kpt <= 8) k_rhok_partial<8><<<nb, RHOK_BLOCK, 0, st>>>(R);
-        else FAIL(MMC_EINVAL, "too many k-vectors for the rebuild kernel (nk too large)");
+        if (h->S.nk > MMC_MAX_NK_FULL) FAIL(MMC_EINVAL, "nk too large for the rebuild kernel (<= 16)");
+        // every CTA writes only its own k-vectors: the others of this launch's k-share must read as zero
+        if (g1 - g0 < n_groups) CK(cudaMemsetAsync(part, 0, (size_t)nb * nkv * sizeof(double2), st));
+        RhokBigArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->d_kindex, box, part, com, f, US, n_ptiles, n_ztiles, g0};
+        const size_t smem = (size_t)RHOKB_SITES * 3 * ((h->S.nk + 1) | 1) * sizeof(double2);
+        if (g1 > g0) k_rhok_big<<<dim3(nb, g1 - g0), RHOKB_BLOCK, smem, st>>>(R);
     }
     LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[3], st);
@@ -139,6 +148,7 @@ void mmc_detail::eval_set_attributes()
     cudaFuncSetAttribute(k_pairs<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_pairs<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_pairs<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_rhok_big, cudaFuncAttributeMaxDynamicSharedMemorySize, RHOKB_SITES * 3 * 17 * (int)sizeof(double2));
 #define X(D) cudaFuncSetAttribute(k_pairs_v7<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V7_SMEM);
     MMC_FOR_DIRECT_DEGS(X)
 #undef X
@@ -171,6 +181,13 @@ bool escalate_pair_level(mmc_handle *h)
 {
     h->pair_level += 1;
     return h->pair_level <= 2;
+}
+
+// sharded ρ(k) by k-ranges instead of sites (large k-sets only; mmc_debug_set "rhok_kshard")
+bool kshard_on(const mmc_handle *h, const EvalCtx &E)
+{
+    const bool v2 = h->n_kpairs <= 32 && h->S.nk <= 6 && h->use_rhok_v2;
+    return h->rhok_kshard && !v2 && E.world > 1 && !E.rhok_external && E.f == 1.0;
 }
 
 int grid_cells(const mmc_handle *h, int style, double box)
@@ -274,7 +291,8 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     // ---- ρ(k) rebuild (RecipLong, ewalds.jl:538-604) of this rank's share of the sites: depends on nothing the pair path
     // produces (a volume trial scales the resident sites inside the kernel), so it runs beside it on the side stream
     const long long ns_all = S.n_sites;
-    const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
+    int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
+    if (kshard_on(h, E)) { rs0 = 0; rs1 = (int)ns_all; }       // k-range sharding: all sites, this rank's k-vectors (rhok_launch)
     int rhok_blocks = E.rhok_blocks;
     bool forked = false;
     if (ewald && !E.rhok_external) {
@@ -411,7 +429,8 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     CK(cudaMemsetAsync(d_vec, 0, (MMC_NSCAL + 2 * (size_t)std::max(S.nkvecs, 1)) * sizeof(double), h->stream));
     if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
     const long long ns_all = S.n_sites;
-    const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
+    int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
+    if (kshard_on(h, E) && E.f == 1.0) { rs0 = 0; rs1 = (int)ns_all; }
     const int tb = 256, gm = (S.n_mol + tb - 1) / tb;
     long long n_units;
     int zl_lo = 0, zl_cnt = 1 << 30;
@@ -849,7 +868,7 @@ int mmc_peer_export(mmc_handle *h, void *handle64)
     if (h->cfg.world < 1 || h->cfg.world > MMC_PEER_MAX) FAIL(MMC_EINVAL, "peer exchange supports up to 8 ranks");
     CK(cudaSetDevice(h->cfg.device));
     if (!h->d_peer_buf) {
-        h->peer_nvec_cap = MMC_NSCAL + 2 * 4096;
+        h->peer_nvec_cap = MMC_NSCAL + 2 * 16384;      // (nk = 16, k² < 257: 8.6 k k-vectors)
         const size_t doubles = peer_flag_offset_doubles(h) + 2 * (size_t)h->cfg.world;
         CK(cudaMalloc(&h->d_peer_buf, doubles * sizeof(double)));
         CK(cudaMemset(h->d_peer_buf, 0, doubles * sizeof(double)));
@@ -1185,7 +1204,7 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     int blocks = 0, cap = 0;
     if (ewald) {   // blocks a chunk needs (same formula as rhok_launch), to size the partial buffer once
         const bool v2 = h->n_kpairs <= 32 && S.nk <= 6 && h->use_rhok_v2;
-        const int ck = v2 ? RHOK2_SITES : RHOK_SITES;
+        const int ck = v2 ? RHOK2_SITES : RHOKB_SITES;
         for (int c = 0; c < nchunk; ++c) {
             const int n = (int)((long long)S.n_sites * (c + 1) / nchunk) - (int)((long long)S.n_sites * c / nchunk);
             const int waves = 2 * h->sm_count * std::max(1, h->rhok_split);

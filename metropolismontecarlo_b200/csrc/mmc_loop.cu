@@ -224,6 +224,7 @@ extern "C" int mmc_loop_run_device(mmc_handle *h, const mmc_loop_params *p, doub
     const DevSystem &S = h->S;
     if (!(S.rc_lj < S.box / 2)) FAIL(MMC_EINVAL, "r_cut must be < box/2 (Ewald/main.jl:483)");
     if (!h->uniform || h->US < 1 || h->US > 4) FAIL(MMC_EINVAL, "device loop needs a uniform topology with 1..4 sites per molecule");
+    if (p->style == MMC_STYLE_EWALD && S.nk > MMC_MAX_NK) FAIL(MMC_EINVAL, "the per-move k-space kernels are sized for nk <= 8");
     const bool recip = p->style == MMC_STYLE_EWALD;
     int dev = 0, max_optin = 0;
     CK(cudaGetDevice(&dev));

@@ -894,3 +894,69 @@ def test_intramolecular_correction_is_opt_in():
         eng.set_intramolecular(False)
         assert eng.potential("ewald").energy == ref.energy
         eng.close()
+
+
+@pytest.mark.parametrize("nk,k_sq_max", [(12, 145), (7, 50), (16, 257)])
+def test_large_k_sets_rebuild_and_k_range_sharding(nk, k_sq_max):
+    """SURVEY §8d "E2" / north star "k-vector ranges split per GPU": ρ(k) rebuilds beyond the reference's nk = 5 (a converged
+    Ewald sum at κ·r_cut ≈ 3.2 needs nk ≈ 12: 3.6 k k-vectors) through k_rhok_big — RecipLong energy and every ρ(k) element
+    against the oracle (Ewald/ewalds.jl:538-604, whose arithmetic is general in nk), the full potential(), a volume trial (the
+    kernel scales the resident sites itself), and the sharded evaluation with the k-space work split by SITES and by K-RANGES
+    (emulated ranks), both equal to the unsharded one."""
+    from metropolismontecarlo_b200.energy import Engine, MMCError
+    ms = systems.spce_lattice(4000)
+    kappa = 0.32
+    ew = ora.Ewald(kappa, nk, k_sq_max, systems.FACTOR, ms.box)
+    eng = Engine()
+    eng.upload_system(ms, 10.0, 10.0)
+    n = eng.PrepareEwaldVariables(kappa, nk, k_sq_max)
+    assert n == ew.nkvecs and (nk != 12 or n > 3000)
+    k, c = eng.kvectors()
+    assert np.array_equal(k, ew.kxyz) and np.allclose(c, ew.cfac, rtol=1e-14, atol=0)
+    e0 = ora.RecipLong(ew, ms.coords, ms.charge, ms.box)
+    assert rel(eng.RecipLong(), e0) < 1e-11
+    old, new = eng.rhok()
+    want_rho = ew.sum_new[:, 0] + 1j * ew.sum_new[:, 1]
+    assert np.abs(old - want_rho).max() < 1e-12 * 0.8476 * ms.n_sites and np.array_equal(old, new)
+    s = ora_system(ms)
+    want = ora.potential_ewald(s, ora.Ewald(kappa, nk, k_sq_max, systems.FACTOR, ms.box), 10.0, 10.0, ms.box, 8)
+    got = eng.potential("ewald")
+    _check_props(got, want)
+    # volume trial == a fresh engine on the scaled configuration (volumeChange.jl:62-80)
+    L2 = ms.box * 1.015
+    v = eng.volume_trial(L2, kappa, "ewald")
+    eng.volume_reject()
+    ms2 = ms.copy()
+    ms2.box = L2
+    ms2.com = ms.com * (L2 / ms.box)
+    ms2.coords = ms.coords + np.repeat(ms2.com - ms.com, 3, axis=0)
+    want2 = ora.potential_ewald(ora_system(ms2), ora.Ewald(kappa, nk, k_sq_max, systems.FACTOR, L2), 10.0, 10.0, L2, 8)
+    _check_props(v, want2)
+    if nk > 8:          # the per-move kernels are sized for nk <= 8 and say so
+        with pytest.raises(MMCError):
+            eng.trial_move(1, ms.com[0], ms.coords[:3], "ewald")
+    eng.close()
+    for world, kshard in ((2, 0), (3, 1), (4, 1)):
+        engs = []
+        for r in range(world):
+            e = Engine(rank=r, world=world)
+            e.upload_system(ms, 10.0, 10.0)
+            e.PrepareEwaldVariables(kappa, nk, k_sq_max)
+            e.debug_set("rhok_kshard", kshard)
+            engs.append(e)
+        for e in engs:
+            e.peer_export()
+        for e in engs:
+            for r, o in enumerate(engs):
+                e.peer_import_ptr(r, o.peer_buffer())
+        for rep in range(2):
+            for e in engs:
+                e.potential_sharded_begin("ewald")
+            props = [e.potential_sharded_end() for e in engs]
+            for p in props:
+                _check_props(p, want, 1e-11)
+                assert p.energy == props[0].energy and p.recip == props[0].recip
+        r0, _ = engs[-1].rhok()
+        assert np.abs(r0 - want_rho).max() < 1e-12 * 0.8476 * ms.n_sites
+        for e in engs:
+            e.close()
