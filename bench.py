@@ -439,6 +439,8 @@ def run_ours(args, rank, world, local_rank):
     ms = systems.spce_lattice(args.molecules)
     eng.upload_system(ms, RC, RC)
     eng.PrepareEwaldVariables(systems.ALPHA / ms.box)
+    if args.overlap_rhok >= 0:
+        eng.debug_set("overlap_rhok", args.overlap_rhok)
     nvec = eng.partial_count()
     vec = torch.zeros(nvec, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -510,7 +512,7 @@ def run_ours(args, rank, world, local_rank):
         step()
         iso.append(eng.last_timings()["pairs_ms"])
         iso_r.append(eng.last_timings()["rhok_ms"])
-    eng.debug_set("overlap_rhok", 1)
+    eng.debug_set("overlap_rhok", args.overlap_rhok if args.overlap_rhok >= 0 else 1)
     pair_ms_isolated, rhok_ms_isolated = float(np.median(iso)), float(np.median(iso_r))
     eng.set_timing(False)
     total_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
@@ -560,7 +562,6 @@ def run_ours(args, rank, world, local_rank):
         achieved = alg_flops / t_pair / 1e12
         nk = eng.nkvecs
         rhok_flops = (FLOP_PER_SITE_K * nk + 168) * ms.n_sites / world + 6 * nk
-        t_rhok = float(np.mean(rhok_ms)) * 1e-3
         cap = NCU_CAPTURE.get(info["pair_kernel"]) if (world == 1 and ms.n_mol == N_MOL_E) else None
         cap_r = NCU_CAPTURE.get("k_rhok_pairs") if (world == 1 and ms.n_mol == N_MOL_E) else None
         peak_src = ("live DFMA-chain probe on this GPU before the timed region (MEASURED_PEAKS.json has no FP64 figure); nominal "
@@ -579,18 +580,22 @@ def run_ours(args, rank, world, local_rank):
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "peak_source": peak_src, "peak_probe_clocks": peak_clock,
                          "algorithmic_flop_per_launch": alg_flops,
-                         "note": "achieved/frac are in situ (timed region, rho(k) rebuild running beside the pair kernel on a side stream)",
+                         "note": "achieved/frac are in situ (timed region; the rho(k) rebuild is queued behind the pair kernel on a low-priority stream "
+                                 "and fills the SMs as the ticket queue drains)",
                          "isolated": {"ms": pair_ms_isolated, "achieved": alg_flops / (pair_ms_isolated * 1e-3) / 1e12,
                                       "frac": (alg_flops / (pair_ms_isolated * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None},
                          "executed": cap,
                          "traffic": cap["dram_bytes"] if cap else None,
                          "traffic_unit": "bytes of DRAM per launch (ncu capture named in `executed.source`; null when this run is not the captured configuration)"},
-            "roofline_rhok": {"bound": "fp64", "kernel": "k_rhok_pairs", "achieved": rhok_flops / t_rhok / 1e12 if t_rhok > 0 else None,
+            "roofline_rhok": {"bound": "fp64", "kernel": "k_rhok_pairs",
+                              "achieved": rhok_flops / (rhok_ms_isolated * 1e-3) / 1e12 if rhok_ms_isolated > 0 else None,
                               "peak": fp64_peak, "unit": "TFLOP/s",
-                              "frac": (rhok_flops / t_rhok / 1e12 / fp64_peak) if (fp64_peak and t_rhok > 0) else None,
+                              "frac": (rhok_flops / (rhok_ms_isolated * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and rhok_ms_isolated > 0) else None,
                               "algorithmic_flop_per_launch": rhok_flops,
-                              "isolated": {"ms": rhok_ms_isolated,
-                                           "frac": (rhok_flops / (rhok_ms_isolated * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and rhok_ms_isolated > 0) else None},
+                              "note": "kernel timed alone (rho(k) rebuild before the pair path on the same stream, outside the timed region): in the timed "
+                                      "region it is queued behind the pair kernel on a low-priority stream and fills the SMs as the pair kernel's ticket "
+                                      "queue drains, so its in-situ event time (kernel_ms.rhok_rebuild) contains the wait for the pair kernel",
+                              "in_situ_ms": float(np.mean(rhok_ms)),
                               "executed": cap_r, "traffic": cap_r["dram_bytes"] if cap_r else None},
             "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_max, "d2h_bytes_per_step": 72,
                     "evaluations_timed": n_e2e,
@@ -667,6 +672,7 @@ def _main():
                     help="evaluations per step (each preceded by an L2 flush and timed with its own pair of CUDA events)")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="exchange of the partial sums at N > 1: NVLink peer-memory kernels (default) or an NCCL all-reduce")
+    ap.add_argument("--overlap-rhok", dest="overlap_rhok", type=int, default=-1, help="placement of the rho(k) rebuild (library default when < 0)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-moves", action="store_true", help="skip the moves/s legs (configs A/B/C)")
     args = ap.parse_args()

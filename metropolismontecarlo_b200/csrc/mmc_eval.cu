@@ -289,23 +289,36 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     const V7Grid G = v7_grid(h, style, E);
     if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
     // ---- ρ(k) rebuild (RecipLong, ewalds.jl:538-604) of this rank's share of the sites: depends on nothing the pair path
-    // produces (a volume trial scales the resident sites inside the kernel), so it runs beside it on the side stream
+    // produces (a volume trial scales the resident sites inside the kernel).  overlap_rhok: 0 = on this stream before the pair
+    // path; 1 = on the low-priority side stream, made eligible TOGETHER with the pair kernel (after the gather): the persistent
+    // pair CTAs take the SMs first and the rebuild's CTAs (128 registers x 256 threads, they cannot co-reside with four pair
+    // CTAs) fill the SMs as the ticket queue drains — the rebuild hides the pair kernel's tail instead of slowing its bulk;
+    // 2 = side stream from the start of the evaluation (round 1's placement: both kernels run 20 % slower side by side).
     const long long ns_all = S.n_sites;
     int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
     if (kshard_on(h, E)) { rs0 = 0; rs1 = (int)ns_all; }       // k-range sharding: all sites, this rank's k-vectors (rhok_launch)
     int rhok_blocks = E.rhok_blocks;
     bool forked = false;
-    if (ewald && !E.rhok_external) {
-        const bool side = h->overlap_rhok && (long long)(rs1 - rs0) * S.nkvecs > 10000000LL;
-        cudaStream_t st = side ? h->side : h->stream;
+    const bool rhok_here = ewald && !E.rhok_external;
+    const bool rhok_side = rhok_here && h->overlap_rhok && (long long)(rs1 - rs0) * S.nkvecs > 10000000LL;
+    // (overlap_rhok == 1 additionally runs the first rhok_early_pct % of the sites at once: the binning and the gather are
+    //  latency-bound and leave the SMs nearly idle for ~35 us, which is about that share of the rebuild)
+    const bool split = rhok_side && h->overlap_rhok == 1 && h->rhok_early_pct > 0 && !kshard_on(h, E);
+    const int rsm = split ? rs0 + (int)((long long)(rs1 - rs0) * h->rhok_early_pct / 100) / 64 * 64 : rs0;
+    int blocks_early = 0;
+    auto launch_rhok = [&](bool side, int a, int b, int block0, int *nb) -> int {
         if (side) {
             CK(cudaEventRecord(h->ev_fork, h->stream));
             CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         }
-        rc = rhok_launch(h, S.site, rs0, rs1, E.box, nullptr, st, 0, &rhok_blocks, 0, E.f == 1.0 ? nullptr : S.com, E.f);
-        if (rc) return rc;
+        int rcr = rhok_launch(h, S.site, a, b, E.box, nullptr, side ? h->side : h->stream, block0, nb, 4 * h->sm_count * std::max(1, h->rhok_split) + 8,
+                              E.f == 1.0 ? nullptr : S.com, E.f);
+        if (rcr) return rcr;
         if (side) { CK(cudaEventRecord(h->ev_join, h->side)); forked = true; }
-    }
+        return MMC_OK;
+    };
+    if (rhok_here && (!rhok_side || h->overlap_rhok == 2) && (rc = launch_rhok(rhok_side, rs0, rs1, 0, &rhok_blocks))) return rc;
+    if (split && rsm > rs0 && (rc = launch_rhok(true, rs0, rsm, 0, &blocks_early))) return rc;
     // ---- binning (fractional COM coordinates do not change with the box: the buckets of an unchanged state are reused,
     // e.g. by consecutive volume trials) and the gather into the extended grid
     CK(cudaMemsetAsync(h->d7_flags, 0, 16 * sizeof(int), h->stream));
@@ -367,6 +380,11 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
         const int warps = G.EX * G.EY * (G.ncd + 1);
         k_gather7<<<(warps + 7) / 8, 256, 0, h->stream>>>(Ga); LAUNCH_CHECK();
         g_trace.mark(h->stream, "window gathered");
+        if (w == 0 && rhok_side && h->overlap_rhok == 1) {
+            int nb_late = 0;
+            if ((rc = launch_rhok(true, rsm, rs1, blocks_early, &nb_late))) return rc;
+            rhok_blocks = blocks_early + nb_late;
+        }
         if (w == 0 && h->tm.on) { cudaEventRecord(h->tm.ev[5], h->stream); cudaEventRecord(h->tm.ev[0], h->stream); }
         A.G = Gw; A.ticket = fl + 8 + w;
         const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * G.ncd / (E.world * nwin) + 1;      // (about: the grid size only)

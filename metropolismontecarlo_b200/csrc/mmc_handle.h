@@ -122,6 +122,7 @@ struct mmc_handle {
     int *d_flags = nullptr;      // [maxdev(2) | novl | errflag | maxcount | 3 spare | count(ncell) | fill(ncell)]
     int4 *d_units = nullptr;
     int use_rhok_v2 = 1;
+    int rhok_early_pct = 0;      // overlap_rhok == 1: share of the sites whose ρ(k) partials run beside binning + gather
     int rhok_kshard = 0;         // sharded ρ(k) rebuild of a large k-set: 1 = split the k-vectors (combo groups) per rank, 0 = the sites
     int pair_level = 0;          // first pair kernel allowed: 0 k_pairs_v7, 1 k_pairs_fast, 2 general k_pairs
                                  // (raised when a kernel declines the state)
