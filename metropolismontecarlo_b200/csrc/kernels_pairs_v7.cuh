@@ -605,6 +605,7 @@ struct TailArgs {
     const double4 *unit_partial;   // pair sums [units][V7_CONSUMERS], units = 3 x (range[rank + 1] − range[rank])
     const int *range; int rank;
     const double2 *rhok_partial; int rhok_blocks, nkvecs;   // ρ(k) partials [rhok_blocks][nkvecs] (nkvecs == 0: no k-space)
+    double2 *rhok_scratch;         // [16][nkvecs] slice sums
     double4 *block_sums;           // [TAIL_BLOCKS]
     unsigned int *done;            // ticket of the tail blocks (zeroed)
     const unsigned int *n_ovl, *err_flag; const int *max_count;
@@ -642,10 +643,16 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
         block_sum<4, TAIL_THREADS>(v, s_red);
         if (tid == 0) A.block_sums[b] = make_double4(v[0], v[1], v[2], v[3]);
     }
-    // ρ(k): block b owns k-vectors [32 b, 32 b + 32); 8 slices of the CTA partials per k, added in slice order
-    for (int k0 = 32 * b; k0 < A.nkvecs; k0 += 32 * gridDim.x) {
-        const int k = k0 + (tid & 31), sl = tid >> 5;
-        const int c0 = (int)((long long)A.rhok_blocks * sl / 8), c1 = (int)((long long)A.rhok_blocks * (sl + 1) / 8);
+    // ρ(k) partials [rhok_blocks][nkvecs]: the blocks form a (k-group of 32) x (slice of the CTA partials) grid — every thread
+    // adds a handful of partials (the kernel is pure load latency: the more loads in flight, the better), a block folds its eight
+    // sub-slices in order into scratch[slice][k], and the last block adds the slices in slice order.  Deterministic.
+    const int n_groups = (A.nkvecs + 31) / 32;
+    const int n_slices = n_groups > 0 ? max(1, min(16, (int)gridDim.x / n_groups)) : 1;
+    for (int w = b; w < n_groups * n_slices; w += gridDim.x) {
+        const int kg = w % n_groups, sl = w / n_groups;
+        const int k = 32 * kg + (tid & 31), sub = tid >> 5;
+        const int s0 = (int)((long long)A.rhok_blocks * sl / n_slices), s1 = (int)((long long)A.rhok_blocks * (sl + 1) / n_slices);
+        const int c0 = s0 + (int)((long long)(s1 - s0) * sub / 8), c1 = s0 + (int)((long long)(s1 - s0) * (sub + 1) / 8);
         double re = 0.0, im = 0.0, re2 = 0.0, im2 = 0.0;
         if (k < A.nkvecs) {
             int c = c0;
@@ -657,12 +664,12 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
             re += re2; im += im2;
         }
         __syncthreads();
-        s_s[sl][tid & 31] = make_double2(re, im);
+        s_s[sub][tid & 31] = make_double2(re, im);
         __syncthreads();
-        if (sl == 0 && k < A.nkvecs) {
+        if (sub == 0 && k < A.nkvecs) {
             double2 t = s_s[0][tid];
             for (int j = 1; j < 8; ++j) { t.x += s_s[j][tid].x; t.y += s_s[j][tid].y; }
-            A.vec[MMC_NSCAL + 2 * k] = t.x; A.vec[MMC_NSCAL + 2 * k + 1] = t.y;
+            A.rhok_scratch[(size_t)sl * A.nkvecs + k] = t;
         }
     }
     __threadfence();
@@ -675,15 +682,17 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
     if (tid < (int)gridDim.x) { const double4 p = ldcg4(&A.block_sums[tid]); v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; }
     block_sum<4, TAIL_THREADS>(v, s_red);
     double er[1] = {0.0};
-    if (A.finish && A.nkvecs > 0) {
-        for (int k = tid; k < A.nkvecs; k += TAIL_THREADS) {
-            const double2 s = make_double2(__ldcg(&A.vec[MMC_NSCAL + 2 * k]), __ldcg(&A.vec[MMC_NSCAL + 2 * k + 1]));
+    for (int k = tid; k < A.nkvecs; k += TAIL_THREADS) {
+        double2 s = __ldcg(&A.rhok_scratch[k]);
+        for (int j = 1; j < n_slices; ++j) { const double2 t = __ldcg(&A.rhok_scratch[(size_t)j * A.nkvecs + k]); s.x += t.x; s.y += t.y; }
+        A.vec[MMC_NSCAL + 2 * k] = s.x; A.vec[MMC_NSCAL + 2 * k + 1] = s.y;
+        if (A.finish) {
             er[0] += A.cfac[k] * (s.x * s.x + s.y * s.y);
             if (A.dst0) A.dst0[k] = s;
             if (A.dst1) A.dst1[k] = s;
         }
-        block_sum<1, TAIL_THREADS>(er, s_red);
     }
+    if (A.finish && A.nkvecs > 0) block_sum<1, TAIL_THREADS>(er, s_red);
     __shared__ double s_h[MMC_NSCAL];
     if (tid == 0) {
         s_h[0] = v[0]; s_h[1] = v[1]; s_h[2] = v[2]; s_h[3] = (double)(*A.n_ovl); s_h[4] = er[0]; s_h[5] = v[3];
@@ -701,7 +710,7 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
         const PeerArgs &P = A.peer;
         for (int d = 0; d < P.world; ++d) {
             double *dst = P.slot[d] + ((size_t)P.parity * P.world + P.rank) * P.nvec_cap;
-            for (int t = tid; t < P.nvec; t += TAIL_THREADS) dst[t] = t < MMC_NSCAL ? s_h[t] : __ldcg(&A.vec[t]);
+            for (int t = tid; t < P.nvec; t += TAIL_THREADS) dst[t] = t < MMC_NSCAL ? s_h[t] : A.vec[t];
         }
         __threadfence_system();
         __syncthreads();

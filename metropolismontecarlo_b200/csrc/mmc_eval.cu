@@ -400,6 +400,12 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     TailArgs T{};
     T.unit_partial = h->d7_unit_partial; T.range = G.range; T.rank = E.rank;
     T.rhok_partial = h->d_rhok_partial; T.rhok_blocks = rhok_blocks; T.nkvecs = ewald ? S.nkvecs : 0;
+    if (ewald && (size_t)S.nkvecs > h->d7_scratch_cap) {
+        dfree(h->d7_rhok_scratch);
+        CK(cudaMalloc(&h->d7_rhok_scratch, sizeof(double2) * 16 * (size_t)S.nkvecs));
+        h->d7_scratch_cap = (size_t)S.nkvecs;
+    }
+    T.rhok_scratch = h->d7_rhok_scratch;
     T.block_sums = h->d7_block_sums; T.done = fl + 6;
     T.n_ovl = fl + 2; T.err_flag = fl + 3; T.max_count = h->d7_flags + 4;
     T.vec = d_vec;

@@ -139,6 +139,8 @@ struct mmc_handle {
     unsigned long long state_version = 1;           // bumped whenever resident positions change
     unsigned long long bin_version = 0;             // state the buckets were built from (0: none)
     int bin_ncd = 0, bin_world = 0;
+    double2 *d7_rhok_scratch = nullptr;             // [16][nkvecs] slice sums of the ρ(k) partials (k_eval_tail)
+    size_t d7_scratch_cap = 0;
     int *d7_range = nullptr;                        // [0,1] = {0, ncd³}; [2 .. 2+world] = home-cell boundaries of the ranks (k_partition7)
     int v7_ctas_per_sm = 4;
     unsigned char *d7_need = nullptr, *h7_need = nullptr;     // domain-decomposed host evaluation: molecule blocks this rank reads

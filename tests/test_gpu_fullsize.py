@@ -64,17 +64,20 @@ def test_full_size_rows_and_totals_against_oracle(cfg_e):
 def test_full_size_pair_kernels_agree(cfg_e):
     ms, eng = cfg_e
     ref = None
-    for level in (0, 1, 2):
-        eng.debug_set("pair_level", level)
-        p = eng.potential("ewald")
-        assert eng.last_eval_info()["pair_kernel"] == ("k_pairs_v7", "k_pairs_fast<64>", "k_pairs")[level]
-        if ref is None:
-            ref = p
-            assert eng.last_eval_info()["pairs_in_cutoff"] > 17_000_000
-        else:
-            assert rel(p.lj, ref.lj) < 1e-11 and rel(p.real, ref.real) < 1e-11 and rel(p.virial, ref.virial) < 1e-11, level
-            assert p.recip == ref.recip
-    eng.debug_set("pair_level", 0)
+    try:
+        for level in (0, 1, 2):
+            eng.debug_set("pair_level", level)
+            p = eng.potential("ewald")
+            assert eng.last_eval_info()["pair_kernel"] == ("k_pairs_v7", "k_pairs_fast<64>", "k_pairs")[level]
+            if ref is None:
+                ref = p
+                assert eng.last_eval_info()["pairs_in_cutoff"] > 17_000_000
+            else:
+                assert rel(p.lj, ref.lj) < 1e-11 and rel(p.real, ref.real) < 1e-11 and rel(p.virial, ref.virial) < 1e-11, level
+                # the v7 tail folds the rho(k) CTA partials in (slice, sub-slice) order, the legacy k_rhok_reduce in CTA order
+                assert rel(p.recip, ref.recip) < 1e-13
+    finally:
+        eng.debug_set("pair_level", 0)
 
 
 def test_full_size_sharded_sum_equals_unsharded(cfg_e):
