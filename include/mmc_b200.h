@@ -159,14 +159,17 @@ int mmc_set_atom(mmc_handle *h, int64_t i, const double r[3]);
 
 /* ---- full-system energy: potential(...) ------------------------------------------------ */
 /* Ewald/energy.jl:946-1032 (EWALD), :864-943 (WOLF), Monatomic/mainMonatomic.jl:275-289 (LJ_ATOMS).
- * EWALD also rebuilds S(k) into both buffers like RecipLong does. Unsharded handles only. */
+ * EWALD also rebuilds S(k) into both buffers like RecipLong does. Unsharded handles only.
+ * Any topology the reference's firstAtom/lastAtom tables can describe with <= 16 sites per molecule (Ewald/energy.jl:219-226):
+ * rigid three-site water takes the k_pairs_v7 pipeline, other uniform molecules k_pairs_fast / k_pairs, and mixtures of
+ * different molecules k_pairs on an evaluation copy padded to the largest molecule (LJ by the active type pairs). */
 int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out);
 
 /* LJ_poly_ΔU(i) (Ewald/energy.jl:209-290) and EwaldShort(i) (Ewald/ewalds.jl:892-910) for EVERY molecule i from one
  * evaluation — the rows that potential() sums at energy.jl:966-1001, kept per molecule.  Arrays of n_mol
  * entries in molecule order, any of them may be NULL: lj_pot[i] = 4·pot, lj_vir[i] = 24·vir/3, coul[i] = pot·factor
- * (0 with overlap[i] = 1 when the overlap rule of ewalds.jl:359 fires for molecule i; coul is 0 for LJ_ONLY).  Uniform
- * topologies, unsharded handles.  Row sums are accumulated with FP64 atomics: equal to the per-i calls to ~1e-13 relative. */
+ * (0 with overlap[i] = 1 when the overlap rule of ewalds.jl:359 fires for molecule i; coul is 0 for LJ_ONLY).  Any
+ * topology, unsharded handles.  Row sums are accumulated with FP64 atomics: equal to the per-i calls to ~1e-13 relative. */
 int mmc_energy_all(mmc_handle *h, int32_t style, double *lj_pot, double *lj_vir, double *coul, int32_t *overlap);
 
 /* sharded variant (world > 1): each rank evaluates its share of the molecule-pair work and of

@@ -53,6 +53,9 @@ struct PairArgs {
     double pc[MMC_ERF_MAXDEG + 1];   // v5: −κ·(coefficients), in r² (DIRECT, κ^2k folded) or in s = pk2s·r² − 1
     double pk2s;               // v5: σ κ²
     double *per_mol;           // k_pairs<ST, true>: [n_mol x 3] per-molecule rows {Σlj_pot, Σlj_vir, Σcoul} (index space of `com`)
+    // mixed topologies (k_pairs<0, *> only): every molecule padded to S site slots, stype[m*S + a] = 0-based LJ type of the
+    // slot or −1 for padding; `lj` then lists the active TYPE pairs (a, b = types) instead of site-slot pairs
+    const signed char *stype;
 };
 
 // ---- one Coulomb site pair: q_a q_b erfc(κ r)/r with the overlap rule (ewalds.jl:359-367).
@@ -100,13 +103,22 @@ static __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_con
     double4 *s_siteA = s_comB + PAIR_TILE;
     double4 *s_siteB = s_siteA + PAIR_TILE * S;
     unsigned int *s_queue = reinterpret_cast<unsigned int *>(s_siteB + PAIR_TILE * S);
+    const bool mix = (ST == 0) && A.stype != nullptr;
+    signed char *s_typeA = reinterpret_cast<signed char *>(s_queue + PAIR_WARPS * PAIR_QCAP);     // mix only (the host sizes smem)
+    signed char *s_typeB = s_typeA + PAIR_TILE * S;
     __shared__ LJActive s_lj[64];
     __shared__ double s_red[4 * PAIR_WARPS];
+    __shared__ double2 s_tab[MMC_MAX_TYPES * MMC_MAX_TYPES];   // mix: {eps, sig} by type pair, eps = 0 for the inactive ones
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned int *q = s_queue + warp * PAIR_QCAP;
     const int nlj = min(A.nlj, 64);
     if (tid < nlj) s_lj[tid] = A.lj[tid];
+    if (mix) {
+        if (tid < MMC_MAX_TYPES * MMC_MAX_TYPES) s_tab[tid] = make_double2(0.0, 0.0);
+        __syncthreads();
+        if (tid < nlj) s_tab[A.lj[tid].a * MMC_MAX_TYPES + A.lj[tid].b] = make_double2(A.lj[tid].eps, A.lj[tid].sig);
+    }
     const double L = A.L;
     const bool cells = (A.mode == 0);
     double rcmax = sqrt(fmax(A.rc_lj2, A.rc_qq2));
@@ -158,6 +170,10 @@ static __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_con
                 for (int t = tid; t < nB; t += PAIR_BLOCK) s_comB[t] = A.com[b0 + t];
                 for (int t = tid; t < nA * S; t += PAIR_BLOCK) s_siteA[t] = A.site[(size_t)a0 * S + t];
                 for (int t = tid; t < nB * S; t += PAIR_BLOCK) s_siteB[t] = A.site[(size_t)b0 * S + t];
+                if (mix) {
+                    for (int t = tid; t < nA * S; t += PAIR_BLOCK) s_typeA[t] = A.stype[(size_t)a0 * S + t];
+                    for (int t = tid; t < nB * S; t += PAIR_BLOCK) s_typeB[t] = A.stype[(size_t)b0 * S + t];
+                }
                 __syncthreads();
                 // ---- (a) COM gate, warp-private ordered compaction
                 int npairs = 0;
@@ -197,6 +213,7 @@ static __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_con
                         if (!(e & (2u << 16))) continue;
                         const int p = e & 255u, qi = (e >> 8) & 255u;
                         const int a = ab / S, b = ab - a * S;
+                        if (mix && (s_typeA[p * S + a] < 0 || s_typeB[qi * S + b] < 0)) continue;      // padding slot
                         const double4 sa = s_siteA[p * S + a], sb = s_siteB[qi * S + b];
                         double dx, dy, dz;
                         if (fast) {
@@ -220,13 +237,23 @@ static __global__ void __launch_bounds__(PAIR_BLOCK, 2) k_pairs(const __grid_con
                 }
                 // ---- (c) LJ: only the site-type combinations with ε_ij > 0.001 (energy.jl:270)
                 if (A.want_lj) {
-                    const int items = npairs * nlj;
+                    const int per = mix ? SS : nlj;       // mixed: every slot pair, resolved through the type table
+                    const int items = npairs * per;
                     for (int w = lane; w < items; w += 32) {
-                        const int pr = w / nlj, li = w - pr * nlj;
+                        const int pr = w / per, li = w - pr * per;
                         const unsigned e = q[pr];
                         if (!(e & (1u << 16))) continue;
                         const int p = e & 255u, qi = (e >> 8) & 255u;
-                        const LJActive lj = s_lj[li];
+                        LJActive lj;
+                        if (mix) {
+                            lj.a = li / S; lj.b = li - lj.a * S;
+                            const int ta = s_typeA[p * S + lj.a], tb = s_typeB[qi * S + lj.b];
+                            if (ta < 0 || tb < 0) continue;
+                            const double2 es = s_tab[ta * MMC_MAX_TYPES + tb];
+                            if (es.x == 0.0) continue;                                  // ε_ij <= 0.001 (energy.jl:270)
+                            lj.eps = es.x; lj.sig = es.y;
+                        } else
+                            lj = s_lj[li];
                         const double4 sa = s_siteA[p * S + lj.a], sb = s_siteB[qi * S + lj.b];
                         const double4 ca = s_comA[p], cb = s_comB[qi];
                         double dx, dy, dz, rx, ry, rz;
@@ -640,6 +667,11 @@ struct GatherArgs {
     int ncd;
     double edge;            // box_new / ncd
     int zl_lo, zl_cnt;      // cell mode: gather only molecules whose cell lies in z-layers [zl_lo, zl_lo + zl_cnt) (mod ncd)
+    // mixed topologies: molecule m owns sites [mol[m].x, mol[m].x + mol[m].y); the copy is padded to S slots per molecule,
+    // padding = {scaled COM, q = 0}, stype = −1
+    const int2 *mol;
+    const int *atype;
+    signed char *stype;
 };
 
 // cell-sorted copy of the state; for a volume trial the COMs are scaled by f and the sites
@@ -664,8 +696,15 @@ static __global__ void k_gather(GatherArgs A)
     cn.x = A.f * c.x; cn.y = A.f * c.y; cn.z = A.f * c.z;
     const double chx = cn.x - c.x, chy = cn.y - c.y, chz = cn.z - c.z;
     A.scom[p] = cn;
+    const int2 mi = A.mol ? A.mol[m] : make_int2(m * A.S, A.S);
     for (int a = 0; a < A.S; ++a) {
-        double4 s = A.site[(size_t)m * A.S + a];
+        if (a >= mi.y) {
+            A.ssite[(size_t)p * A.S + a] = make_double4(cn.x, cn.y, cn.z, 0.0);
+            A.stype[(size_t)p * A.S + a] = (signed char)-1;
+            continue;
+        }
+        double4 s = A.site[(size_t)mi.x + a];
+        if (A.stype) A.stype[(size_t)p * A.S + a] = (signed char)A.atype[mi.x + a];
         dev = fmax(dev, fmax(fabs(s.x - c.x), fmax(fabs(s.y - c.y), fabs(s.z - c.z))));
         s.x = s.x + chx; s.y = s.y + chy; s.z = s.z + chz;
         A.ssite[(size_t)p * A.S + a] = s;

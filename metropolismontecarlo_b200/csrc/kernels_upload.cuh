@@ -169,3 +169,10 @@ static __global__ void __launch_bounds__(256) k_intra_final(const double *part, 
     block_sum<1, 256>(acc, s_red);
     if (threadIdx.x == 0) out[0] = acc[0];
 }
+
+// {m·S, S} for every molecule: the molecule table of a copy padded to S slots per molecule (mixed topologies)
+static __global__ void k_mol_packed(int2 *mol, int n_mol, int S)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n_mol) mol[m] = make_int2(m * S, S);
+}

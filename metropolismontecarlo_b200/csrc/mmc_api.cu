@@ -17,7 +17,7 @@ std::string g_create_error;
 void free_system(mmc_handle *h)
 {
     dfree(h->S.site); dfree(h->S.com); dfree(h->S.mol); dfree(h->S.atype);
-    dfree(h->d_intra); dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums); dfree(h->d_raw); dfree(h->d_info); dfree(h->d_qpart);
+    dfree(h->d_intra); dfree(h->d_stype); dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums); dfree(h->d_raw); dfree(h->d_info); dfree(h->d_qpart);
     h->raw_bytes = 0; h->cap_mol = 0; h->cap_sites = 0;
     dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
     h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
@@ -402,6 +402,7 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         CK(cudaMalloc(&h->d_perm, sizeof(int) * n_mol));
         CK(cudaMalloc(&h->d_scom, sizeof(double4) * n_mol));
         CK(cudaMalloc(&h->d_ssite, sizeof(double4) * n_sites));
+        h->ssite_cap = (size_t)n_sites;
         h->pair_grid = 5 * h->sm_count;
         CK(cudaMalloc(&h->d_pair_partial, sizeof(double4) * h->pair_grid));
         CK(cudaMalloc(&h->d_ovl, sizeof(unsigned) * n_mol));
@@ -460,6 +461,26 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
     if (h->lj.size() > 64) uniform = false;
     h->uniform = uniform; h->US = uniform ? US : 0;
     S.uni = h->US;
+    // any other topology (molecules of different size or type sequence, ≤ 16 sites each): the cell path works on a copy padded
+    // to max_sites slots per molecule and resolves LJ through the active TYPE pairs
+    h->mixed = !uniform; h->ES = uniform ? US : S.max_sites;
+    if (h->mixed) {
+        h->lj.clear();
+        for (int ta = 0; ta < n_types; ++ta)
+            for (int tb = 0; tb < n_types; ++tb)
+                if (eps[ta + tb * n_types] > 0.001) h->lj.push_back(LJActive{ta, tb, eps[ta + tb * n_types], sig[ta + tb * n_types]});
+        const size_t need = (size_t)n_mol * h->ES;
+        if (need > h->ssite_cap) {
+            dfree(h->d_ssite);
+            CK(cudaMalloc(&h->d_ssite, sizeof(double4) * need));
+            h->ssite_cap = need;
+        }
+        dfree(h->d_stype);
+        CK(cudaMalloc(&h->d_stype, need));
+        k_mol_packed<<<(unsigned)((n_mol + 255) / 256), 256, 0, h->stream>>>(h->d_mol_uniform, (int)n_mol, h->ES); LAUNCH_CHECK();
+        if (!h->lj.empty())
+            CK(cudaMemcpyAsync(h->d_lj, h->lj.data(), sizeof(LJActive) * h->lj.size(), cudaMemcpyHostToDevice, h->stream));
+    }
     h->h_mol.clear();
     if (uniform) {
         if (realloc_needed || true) {
@@ -924,8 +945,8 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
         h->rhok_split = (int)value;
         return MMC_OK;
     }
-    if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v7, 1 fast, 2 general)
-        if (value < 0 || value > 2) FAIL(MMC_EINVAL, "pair_level must be 0..2");
+    if (k == "pair_level") {                 // first pair kernel the fallback chain may use (0 v7, 1 fast, 2 general; 3: mmc_potential as Σ_i rows / 2 via k_move)
+        if (value < 0 || value > 3) FAIL(MMC_EINVAL, "pair_level must be 0..3");
         h->pair_floor = (int)value; h->pair_level = (int)value;
         return MMC_OK;
     }

@@ -444,15 +444,16 @@ int v7_wait(mmc_handle *h, double *hv)
 int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
 {
     const bool force_general = h->pair_level >= 2 || E.per_mol != nullptr;
-    if (!h->uniform) FAIL(MMC_EINVAL, "pair kernel needs a uniform topology (internal)");
     const DevSystem &S = h->S;
-    const int US = h->US;
+    const int US = h->ES;
+    if (US < 1 || US > MMC_MAX_SITES) FAIL(MMC_EINVAL, "pair kernel: 1..16 sites per molecule (internal)");
     const bool want_qq = (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF);
     const int ncd = grid_cells(h, style, E.box);
     const bool cells = ncd >= 3;
     CK(cudaMemsetAsync(d_vec, 0, (MMC_NSCAL + 2 * (size_t)std::max(S.nkvecs, 1)) * sizeof(double), h->stream));
     if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
-    const long long ns_all = S.n_sites;
+    // ρ(k) reads the resident sites, or — for a volume trial — the scaled copy (padded slots of a mixed topology carry q = 0)
+    const long long ns_all = (E.f != 1.0 && h->mixed) ? (long long)S.n_mol * US : S.n_sites;
     int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
     if (kshard_on(h, E) && E.f == 1.0) { rs0 = 0; rs1 = (int)ns_all; }
     const int tb = 256, gm = (S.n_mol + tb - 1) / tb;
@@ -505,7 +506,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     }
     GatherArgs G{S.com, S.site, cells ? h->d_perm : nullptr, S.n_mol, US, E.f, h->d_scom, h->d_ssite,
                  reinterpret_cast<unsigned long long *>(h->d_maxdev), h->d_ovl, nullptr, nullptr, h->d_cell_of, ncd, E.box / ncd,
-                 zl_lo, std::min(zl_cnt, ncd)};
+                 zl_lo, std::min(zl_cnt, ncd), h->mixed ? S.mol : nullptr, h->mixed ? S.atype : nullptr, h->mixed ? h->d_stype : nullptr};
     if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
     k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
@@ -520,6 +521,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     P.partial = h->d_pair_partial; P.ovl = h->d_ovl; P.n_ovl = h->d_novl; P.max_dev = h->d_maxdev;
     P.err_flag = h->d_errflag;
     P.per_mol = E.per_mol;
+    P.stype = h->mixed ? h->d_stype : nullptr;
     P.rclj_bits = 0; P.rcqq_bits = 0; P.cutlj_bits = 0; P.cutqq_bits = 0;
     { double v;
       v = P.rc_lj2; std::memcpy(&P.rclj_bits, &v, 8); v = P.rc_qq2; std::memcpy(&P.rcqq_bits, &v, 8);
@@ -527,7 +529,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     P.ep = ErfPoly{};
     if (want_qq) get_erf_poly(h, E.kappa, S.rc_qq * S.rc_qq + 100, P.ep);
     const int max_cell = cells ? h->max_cell_cached : PAIR_TILE;
-    const int tile = (US == 3 && !force_general) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
+    const int tile = (US == 3 && !force_general && !h->mixed) ? (max_cell <= 64 ? 64 : (max_cell <= 128 ? 128 : 0)) : 0;
     P.unit_begin = n_units * E.rank / E.world;
     P.unit_end = n_units * (E.rank + 1) / E.world;
     const long long my_units = P.unit_end - P.unit_begin;
@@ -549,9 +551,12 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
         if (!launch_pairs_fast(tile, P.ep.deg, grid, smem, h->stream, P)) FAIL(MMC_ECUDA, "k_pairs_fast: no instantiation for this polynomial degree (internal)");
     } else {
         const size_t smem = (2 * PAIR_TILE + 2 * PAIR_TILE * (size_t)US) * sizeof(double4) +
-                            (size_t)PAIR_WARPS * PAIR_QCAP * sizeof(unsigned);
+                            (size_t)PAIR_WARPS * PAIR_QCAP * sizeof(unsigned) + (h->mixed ? 2 * PAIR_TILE * (size_t)US : 0);
         grid = (int)std::max(1LL, std::min<long long>(2 * h->sm_count, my_units));
-        if (P.per_mol) {
+        if (h->mixed) {
+            if (P.per_mol) k_pairs<0, true><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+            else k_pairs<0, false><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
+        } else if (P.per_mol) {
             if (US == 3) k_pairs<3, true><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
             else k_pairs<0, true><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
         } else if (US == 3) k_pairs<3, false><<<grid, PAIR_BLOCK, smem, h->stream>>>(P);
@@ -772,7 +777,7 @@ int evaluate_partial(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     return eval_partials(h, style, E, d_vec);
 }
 
-// non-uniform topologies: literal Σ_i rows / 2 through the single-molecule kernel
+// debug (pair_level 3): literal Σ_i rows / 2 through the single-molecule kernel, any topology — N launches
 int potential_rows(mmc_handle *h, int style, mmc_properties *out)
 {
     const DevSystem &S = h->S;
@@ -861,7 +866,6 @@ int mmc_potential_partial(mmc_handle *h, int32_t style, double *d_partials)
     if (rc) return rc;
     { int rcf = flush_pending(h); if (rcf) return rcf; }
     if (style == MMC_STYLE_LJ_ATOMS || !d_partials) FAIL(MMC_EINVAL, "sharded evaluation is for molecular systems");
-    if (!h->uniform) FAIL(MMC_EINVAL, "sharded evaluation needs a uniform topology");
     if ((rc = ensure_vec(h))) return rc;
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
     return evaluate_partial(h, style, E, d_partials);
@@ -1067,7 +1071,6 @@ int mmc_potential_sharded_begin(mmc_handle *h, int32_t style)
     int rc = style_check(h, style);
     if (rc) return rc;
     if (style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "sharded evaluation is for molecular systems");
-    if (!h->uniform) FAIL(MMC_EINVAL, "sharded evaluation needs a uniform topology");
     if (h->peer_ready != h->cfg.world) FAIL(MMC_ESTATE, "peer exchange not set up: mmc_peer_export / mmc_peer_import for every rank");
     if (h->sharded_pending) FAIL(MMC_ESTATE, "mmc_potential_sharded_end has not been called");
     if ((size_t)(MMC_NSCAL + 2 * std::max(h->S.nkvecs, 1)) > h->peer_nvec_cap) FAIL(MMC_EINVAL, "too many k-vectors for the exchange buffer");
@@ -1137,7 +1140,7 @@ int mmc_potential(mmc_handle *h, int32_t style, mmc_properties *out)
         h->cnt.full_energy_evals++;
         return MMC_OK;
     }
-    if (!h->uniform) return potential_rows(h, style, out);
+    if (h->pair_level >= 3) return potential_rows(h, style, out);        // debug: the literal Σ_i rows / 2 through k_move
     if ((rc = ensure_vec(h))) return rc;
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, 0, 1};
     rc = evaluate_unsharded(h, style, E, h->S.rhok[0], h->S.rhok[1], out);
@@ -1153,7 +1156,6 @@ int mmc_energy_all(mmc_handle *h, int32_t style, double *lj_pot, double *lj_vir,
     int rc = style_check(h, style);
     if (rc) return rc;
     if (style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "mmc_energy_all is for molecular systems");
-    if (!h->uniform) FAIL(MMC_EINVAL, "mmc_energy_all needs a uniform topology");
     { int rcf = flush_pending(h); if (rcf) return rcf; }
     if ((rc = ensure_vec(h))) return rc;
     const DevSystem &S = h->S;
@@ -1322,7 +1324,6 @@ int mmc_volume_trial(mmc_handle *h, double box_new, double kappa_new, int32_t st
     { int rcf = flush_pending(h); if (rcf) return rcf; }
     if (style == MMC_STYLE_LJ_ATOMS) FAIL(MMC_EINVAL, "volume trial is implemented for molecular systems");
     if (!out || !(box_new > 0)) FAIL(MMC_EINVAL, "bad arguments");
-    if (!h->uniform) FAIL(MMC_EINVAL, "volume trial needs a uniform topology");
     if ((rc = ensure_vec(h))) return rc;
     const bool coul = (style == MMC_STYLE_EWALD || style == MMC_STYLE_WOLF);
     if (coul && !(kappa_new > 0)) FAIL(MMC_EINVAL, "kappa_new must be positive");

@@ -46,6 +46,10 @@ struct mmc_handle {
     struct UploadResult { int info[4]; double qs[2]; } *h_up = nullptr;   // pinned
     bool uniform = false;        // every molecule: same site count, same type sequence, packed
     int US = 0;                  // uniform sites per molecule
+    bool mixed = false;          // molecules of different size / type sequence: the cell path evaluates a copy padded to ES slots
+    int ES = 0;                  // site slots per molecule of the evaluation copy (US, or max_sites when mixed)
+    signed char *d_stype = nullptr;   // mixed: LJ type per slot of the evaluation copy (−1 = padding)
+    size_t ssite_cap = 0;        // capacity of d_ssite in sites
     std::vector<LJActive> lj;
     LJActive *d_lj = nullptr;
     int2 *d_mol_uniform = nullptr;

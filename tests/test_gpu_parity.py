@@ -812,6 +812,64 @@ def test_mixed_topology_water_and_ions():
     eng.close()
 
 
+@pytest.mark.parametrize("n_mol,n_ions", [(4096, 300), (512, 40)])
+def test_mixed_topology_on_the_pair_kernels(n_mol, n_ions):
+    """a non-uniform topology (3-site water + 1-site ions, three LJ types) is evaluated by the cell / tile
+    pair kernel k_pairs on a copy padded to max_sites slots per molecule (LJ resolved through the active type pairs) instead of
+    N k_move launches.  4096 molecules: cell mode (4³ cells); 512: tile mode (box < 3 r_cut).  Against the oracle's potential(),
+    the literal Σ_i rows / 2 (debug pair_level 3), mmc_energy_all against the per-molecule calls, a volume trial against the
+    scaled recompute, and the sharded partials (2 and 3 emulated ranks) against the unsharded evaluation."""
+    import torch
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.water_ion_mixture(n_mol, n_ions)
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    eng = water_engine(ms, 10.0)
+    wants = {"ewald": ora.potential_ewald(s, ew, 10.0, 10.0, ms.box, 8), "wolf": ora.potential_wolf(s, ew, 10.0, 10.0, ms.box, 8)}
+    for style, want in wants.items():
+        got = eng.potential(style)
+        info = eng.last_eval_info()
+        assert info["pair_kernel"] == "k_pairs" and info["mode"] == ("cells" if n_mol == 4096 else "tiles"), info
+        _check_props(got, want)
+        assert got.overlaps == want.overlaps == 0
+    got = eng.potential("ewald")
+    eng.debug_set("pair_level", 3)
+    rows = eng.potential("ewald")
+    eng.debug_set("pair_level", 0)
+    _check_props(got, rows, 1e-11)
+    lj = eng.potential("lj")
+    assert rel(lj.energy, wants["ewald"].lj) < 1e-11
+    # every molecule's rows from the one pass, ions included
+    ljr, virr, qqr, ovr = eng.energy_all("ewald")
+    assert not ovr.any()
+    for i in (1, 2, 14, 15, n_mol // 2, n_mol):
+        e0, v0 = ora.LJ_poly_dU(i, s, 10.0, ms.box)
+        c0, _, ov0 = ora.EwaldShort(i, s, ew, 10.0, ms.box)
+        assert not ov0 and rel(ljr[i - 1], e0) < 1e-11 and abs(virr[i - 1] - v0) < 1e-10 * max(1.0, abs(v0), abs(e0)) and rel(qqr[i - 1], c0) < 1e-10, i
+    assert rel(ljr.sum() / 2, got.lj) < 1e-11 and rel(qqr.sum() / 2, got.real) < 1e-11
+    # volume trial: COMs scaled, sites shifted rigidly, κ = α/L'
+    box_new = ms.box * 1.01
+    s2 = ora_system(ms)
+    ora.volume_scale(s2, ms.box, box_new)
+    w2 = ora.potential_ewald(s2, ora.Ewald(systems.ALPHA / box_new, 5, 27, systems.FACTOR, box_new), 10.0, 10.0, box_new, 8)
+    _check_props(eng.volume_trial(box_new, systems.ALPHA / box_new, "ewald"), w2)
+    eng.volume_reject()
+    assert eng.potential("ewald").energy == got.energy
+    # sharded: partial vectors of R ranks summed = the unsharded evaluation
+    for world in (2, 3):
+        engs = [water_engine(ms, 10.0, rank=r, world=world) for r in range(world)]
+        n = engs[0].partial_count()
+        bufs = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in range(world)]
+        for e, b in zip(engs, bufs):
+            e.potential_partial("ewald", b.data_ptr())
+        torch.cuda.synchronize()
+        total = torch.stack(bufs).sum(0)
+        for e in engs:
+            _check_props(e.potential_finalize("ewald", total.clone().data_ptr()), got, 1e-12)
+            e.close()
+    eng.close()
+
+
 @pytest.mark.parametrize("world,order", [(2, "lattice"), (4, "lattice"), (3, "random")])
 def test_domain_decomposed_host_evaluation_emulated_ranks(world, order):
     """mmc_potential_host on sharded handles (ranks emulated as threads of one process on one GPU): every rank copies all COMs
