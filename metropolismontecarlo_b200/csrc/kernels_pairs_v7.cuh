@@ -179,6 +179,65 @@ static __global__ void __launch_bounds__(1024) k_partition7(const int *__restric
     }
 }
 
+// Order in which the persistent pair CTAs draw the units of one segment (a rank's or a window's home range): most expensive
+// first, so that the last tickets are the cheap units and the CTAs finish together (cell populations on the lattice start range
+// from 27 to 64, unit costs over a factor of five; in lattice order the slowest CTA ends one big unit after the others).
+// Cost of unit (c, g) = n_c · Σ populations of the group's cells (half of n_c for the home cell itself).  Counting sort on 1024
+// cost classes; the order inside a class is arbitrary — every unit writes its own partial slot, so results do not depend on it.
+// One CTA per segment: segment s = blockIdx.x + seg0 holds the cells [range[s], range[s + 1]); order[3·range[s] + t] = global unit.
+static __global__ void __launch_bounds__(1024) k_order7(const int *__restrict__ count, int n, const int *__restrict__ range, int seg0, int *__restrict__ order)
+{
+    __shared__ unsigned s_hist[1024];
+    __shared__ unsigned s_max;
+    const int tid = threadIdx.x, seg = blockIdx.x + seg0;
+    const int c0 = range[seg], c1 = range[seg + 1];
+    const int u0 = V3_GROUPS * c0, nu = V3_GROUPS * (c1 - c0);
+    auto cost = [&](int ug) -> unsigned {
+        const int c = ug / V3_GROUPS, g = ug - c * V3_GROUPS;
+        const int cx = c % n, cy = (c / n) % n, cz = c / (n * n);
+        const int nc = min(count[c], V7_CAP);
+        int nb2 = 0;                                            // twice the partner count
+        for (int s = c_v3_group_begin[g]; s < c_v3_group_begin[g + 1]; ++s) {
+            int x = cx + c_half_shell[s][0], y = cy + c_half_shell[s][1], z = cz + c_half_shell[s][2];
+            x = x < 0 ? x + n : (x >= n ? x - n : x); y = y < 0 ? y + n : (y >= n ? y - n : y); z = z >= n ? z - n : z;
+            const int k = min(count[x + n * (y + n * z)], V7_CAP);
+            nb2 += s == 0 ? k : 2 * k;
+        }
+        return (unsigned)(nc * nb2);
+    };
+    s_hist[tid] = 0u;
+    if (tid == 0) s_max = 1u;
+    __syncthreads();
+    unsigned mx = 0;
+    for (int t = tid; t < nu; t += 1024) mx = max(mx, cost(u0 + t));
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+    const unsigned cmax = s_max;
+    auto cls = [&](unsigned cst) -> int { return 1023 - (int)((unsigned long long)cst * 1023ull / cmax); };   // 0 = most expensive
+    for (int t = tid; t < nu; t += 1024) atomicAdd(&s_hist[cls(cost(u0 + t))], 1u);
+    __syncthreads();
+    // exclusive scan of the 1024 class sizes (one value per thread: warp scans + the 32 warp totals)
+    __shared__ unsigned s_wsum[32];
+    const unsigned mine = s_hist[tid];
+    unsigned incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+    if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        unsigned w = s_wsum[tid], wi = w;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, wi, o); if (tid >= o) wi += v; }
+        s_wsum[tid] = wi - w;
+    }
+    __syncthreads();
+    s_hist[tid] = s_wsum[tid >> 5] + incl - mine;
+    __syncthreads();
+    for (int t = tid; t < nu; t += 1024) {
+        const unsigned pos = atomicAdd(&s_hist[cls(cost(u0 + t))], 1u);
+        order[u0 + pos] = u0 + t;
+    }
+}
+
 // mmc_potential_host on one GPU, windowed: the home cells are cut into `nwin` contiguous ranges (range[0 .. nwin]) that are
 // gathered and evaluated one after the other while later site chunks are still on the bus; need[w] = the last chunk (sites
 // [n_sites·c/n_chunks, n_sites·(c+1)/n_chunks)) that holds a molecule window w reads.
@@ -318,6 +377,7 @@ struct V7Args {
     unsigned int *err_flag;
     unsigned int *n_ovl;
     unsigned int *ticket;          // zeroed before the launch
+    const int *order;              // [3 ncd³] k_order7: the t-th unit this rank draws is order[3·range[rank] + t] (global unit id)
     double4 *unit_partial;         // [3 ncd³][V7_CONSUMERS], indexed by the GLOBAL unit 3·cell + group
 };
 
@@ -366,8 +426,8 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
         if (lane == 0) tk_pending = atomicAdd(A.ticket, 1u);       // one ticket is always in flight: drawn a unit ahead
         unsigned seq = 0;
         while (u < n_units) {
-            const int ci = (int)(u / V3_GROUPS), g = (int)(u - (long long)ci * V3_GROUPS);
-            const int c = c_first + ci;
+            const long long ug = A.order[(long long)V3_GROUPS * c_first + u];            // global unit
+            const int c = (int)(ug / V3_GROUPS), g = (int)(ug - (long long)c * V3_GROUPS);
             const int cz = c / (n * n), r2 = c - cz * n * n, cy = r2 / n, cx = r2 - cy * n;
             const int e = (cx + 1) + EX * ((cy + 1) + EY * cz);
             const int sl0 = c_v3_group_begin[g], nsl_all = c_v3_group_begin[g + 1] - sl0;
@@ -383,7 +443,6 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
             const int nA = __shfl_sync(FULL, cnt, 5);
             // a unit without work (an empty home cell or only empty neighbours) never reaches the consumers: its slots are zeroed here
             const bool any_b = __any_sync(FULL, lane < nsl_all && cnt > 0);
-            const long long ug = (long long)V3_GROUPS * c_first + u;            // global unit
             if ((nA == 0 || !any_b) && lane < V7_CONSUMERS) A.unit_partial[(size_t)ug * V7_CONSUMERS + lane] = make_double4(0.0, 0.0, 0.0, 0.0);
             int pass = 0;
             for (int s_begin = 0; s_begin < nsl_all && nA > 0;) {
@@ -401,7 +460,7 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
                     if (lane == 0) {
                         D.valid = 1; D.nA = nA; D.nB = nB; D.nsl = se - s_begin;
                         D.self_n = (g == 0 && s_begin == 0) ? nA : 0;
-                        D.rot = (int)(u & 3); D.unit = ug; D.first = pass == 0 ? 1 : 0;
+                        D.rot = (int)(ug & 3); D.unit = ug; D.first = pass == 0 ? 1 : 0;
                     }
                     __syncwarp();
                     float4 *gfA = s_gf + sg * (V7_CAP + V7_BCAP), *gfB = gfA + V7_CAP;

@@ -27,7 +27,7 @@ void free_system(mmc_handle *h)
     dfree(h->d_rhok_partial); dfree(h->d_units);
     h->units_cap = 0;
     dfree(h->d7_flags); dfree(h->d7_count); dfree(h->d7_bucket); dfree(h->d7_ecount); dfree(h->d7_rows); dfree(h->d7_gf);
-    dfree(h->d7_unit_partial); dfree(h->d7_block_sums); dfree(h->d7_need); dfree(h->d7_range); dfree(h->d7_rhok_scratch); h->d7_scratch_cap = 0;
+    dfree(h->d7_unit_partial); dfree(h->d7_order); dfree(h->d7_block_sums); dfree(h->d7_need); dfree(h->d7_range); dfree(h->d7_rhok_scratch); h->d7_scratch_cap = 0;
     if (h->h7_need) { cudaFreeHost(h->h7_need); h->h7_need = nullptr; }
     h->need_cap = 0;
     h->d7_ncd = 0; h->d7_partial_cap = 0; h->bin_version = 0;

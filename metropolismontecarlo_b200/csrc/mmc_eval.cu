@@ -247,9 +247,11 @@ int v7_alloc(mmc_handle *h, int ncd, int EXY)
     }
     const size_t need = (size_t)std::max(1LL, units) * V7_CONSUMERS;
     if (need > h->d7_partial_cap) {
-        dfree(h->d7_unit_partial);
+        dfree(h->d7_unit_partial); dfree(h->d7_order);
         CK(cudaMalloc(&h->d7_unit_partial, need * sizeof(double4)));
+        CK(cudaMalloc(&h->d7_order, (size_t)std::max(1LL, units) * sizeof(int)));
         h->d7_partial_cap = need;
+        h->bin_version = 0;
     }
     return MMC_OK;
 }
@@ -330,6 +332,7 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
         if (E.world > 1) {       // the ranks' home ranges: equal estimated pair work, from the cell populations
             k_partition7<<<1, 1024, 0, h->stream>>>(h->d7_count, G.ncd, E.world, h->d7_range + 2); LAUNCH_CHECK();
         }
+        k_order7<<<1, 1024, 0, h->stream>>>(h->d7_count, G.ncd, G.range, G.rank, h->d7_order); LAUNCH_CHECK();
         h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_world = E.world;
     }
     if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
@@ -367,7 +370,7 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     A.rows = h->d7_rows; A.gf = h->d7_gf; A.ecount = h->d7_ecount;
     A.max_dev = reinterpret_cast<const double *>(h->d7_flags);
     A.n_ovl = fl + 2; A.err_flag = fl + 3;
-    A.unit_partial = h->d7_unit_partial;
+    A.unit_partial = h->d7_unit_partial; A.order = h->d7_order;
     const int nwin = (E.world == 1 && E.n_windows > 1) ? E.n_windows : 1;
     for (int w = 0; w < nwin; ++w) {
         V7Grid Gw = G;
@@ -1007,6 +1010,7 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     Bin7Args B{S.com, S.n_mol, (double)G.ncd / S.box, G, h->d7_count, h->d7_bucket, h->d_cell_of};
     k_bin7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(B); LAUNCH_CHECK();
     k_partition7<<<1, 1024, 0, h->stream>>>(h->d7_count, G.ncd, E.world, h->d7_range + 2); LAUNCH_CHECK();
+    k_order7<<<1, 1024, 0, h->stream>>>(h->d7_count, G.ncd, G.range, G.rank, h->d7_order); LAUNCH_CHECK();
     k_need7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->d_cell_of, S.n_mol, G, h->d7_need); LAUNCH_CHECK();
     h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_world = E.world;
     CK(cudaMemcpyAsync(h->h7_need, h->d7_need, nblk, cudaMemcpyDeviceToHost, h->stream));
@@ -1285,6 +1289,7 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
         h->bin_version = h->state_version; h->bin_ncd = ncd; h->bin_world = 1;
         CK(cudaMemsetAsync(h->d7_range + 24, 0, 4 * sizeof(int), h->stream));
         V7Grid Gw = G; Gw.range = h->d7_range + 16; Gw.world = nwin;
+        k_order7<<<nwin, 1024, 0, h->stream>>>(h->d7_count, ncd, Gw.range, 0, h->d7_order); LAUNCH_CHECK();
         k_window_need7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->d_cell_of, S.n_mol, h->US, S.n_sites, nchunk, Gw, nwin, h->d7_range + 24); LAUNCH_CHECK();
         int need[4] = {0, 0, 0, 0};
         CK(cudaMemcpyAsync(need, h->d7_range + 24, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

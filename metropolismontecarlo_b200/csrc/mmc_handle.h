@@ -136,6 +136,7 @@ struct mmc_handle {
     double *d7_rows = nullptr;
     float4 *d7_gf = nullptr;
     double4 *d7_unit_partial = nullptr, *d7_block_sums = nullptr;
+    int *d7_order = nullptr;                        // [3 ncd³] k_order7: draw order of the units, expensive first
     int d7_ncd = 0;
     size_t d7_partial_cap = 0;
     double *h7_res = nullptr, *d7_res = nullptr;     // mapped pinned result slot [MMC_NSCAL + 1]: scalars + sequence number
