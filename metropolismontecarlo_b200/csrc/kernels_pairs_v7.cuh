@@ -422,8 +422,6 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
         const int c_first = A.G.range[A.G.rank];
         const long long n_units = (long long)V3_GROUPS * (A.G.range[A.G.rank + 1] - c_first);
         long long u = blockIdx.x;
-        unsigned tk_pending = 0;
-        if (lane == 0) tk_pending = atomicAdd(A.ticket, 1u);       // one ticket is always in flight: drawn a unit ahead
         unsigned seq = 0;
         while (u < n_units) {
             const long long ug = A.order[(long long)V3_GROUPS * c_first + u];            // global unit
@@ -437,9 +435,6 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
                 en = e + c_half_shell[s][0] + EX * (c_half_shell[s][1] + EY * c_half_shell[s][2]);
                 cnt = A.ecount[en];
             } else if (lane == 5) cnt = A.ecount[e];
-            const unsigned tk = __shfl_sync(FULL, tk_pending, 0);
-            const long long u_next = (long long)gridDim.x + tk;
-            if (lane == 0 && u_next < n_units) tk_pending = atomicAdd(A.ticket, 1u);
             const int nA = __shfl_sync(FULL, cnt, 5);
             // a unit without work (an empty home cell or only empty neighbours) never reaches the consumers: its slots are zeroed here
             const bool any_b = __any_sync(FULL, lane < nsl_all && cnt > 0);
@@ -479,7 +474,12 @@ static __global__ void __launch_bounds__(V7_BLOCK, 4) k_pairs_v7(const __grid_co
                 }
                 s_begin = se;
             }
-            u = u_next;
+            // the next unit is claimed only now — when this one's rows are on their way, i.e. the consumers are a whole unit
+            // behind: a ticket drawn further ahead is a unit another CTA cannot take when the queue runs dry (sharded ranks
+            // have four units per CTA; three claimed ahead left SMs idle for a third of the kernel)
+            unsigned tk = 0;
+            if (lane == 0) tk = atomicAdd(A.ticket, 1u);
+            u = (long long)gridDim.x + __shfl_sync(FULL, tk, 0);
         }
         // end marker
         const int sg = seq & 1;
