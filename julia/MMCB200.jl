@@ -113,6 +113,17 @@ function potential_host(e::Engine, coords, com, style::Cint = EWALD)
     p
 end
 
+# bytes the last potential_host copied host -> device on this rank (a sharded engine copies only its slab's site blocks)
+function last_host_bytes(e::Engine)
+    n = Ref{Int64}(0)
+    check(e, ccall((:mmc_last_host_bytes, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}), e.h, n))
+    n[]
+end
+
+# tuning / debugging switches (include/mmc_b200.h mmc_debug_set), e.g. debug_set(e, "rhok_kshard", 1)
+debug_set(e::Engine, key::AbstractString, value::Integer) =
+    check(e, ccall((:mmc_debug_set, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), e.h, key, value))
+
 # opt-in intramolecular Ewald correction (the reference omits it, Ewald/energy.jl:1008-1021); Props.intra carries it
 set_intramolecular!(e::Engine, on::Bool) = check(e, ccall((:mmc_set_intramolecular, LIB), Cint, (Ptr{Cvoid}, Cint), e.h, on ? 1 : 0))
 

@@ -10,6 +10,7 @@
 // its kz values in registers (k_rhok_pairs for nk <= 6, k_rhok_big beyond).  Per-CTA partial sums go
 // to HBM and are folded in CTA order, so the result is deterministic.  FP64 accumulation throughout.
 #pragma once
+#include <type_traits>
 #include "mmc_common.cuh"
 
 #define RHOK_BLOCK 384
@@ -226,7 +227,7 @@ static __global__ void __launch_bounds__(RHOK2_BLOCK, 2) k_rhok_pairs(Rhok2Args 
 #define RHOKB_BLOCK 256
 #define RHOKB_WARPS (RHOKB_BLOCK / 32)
 #define RHOKB_SITES 64     // sites per sub-chunk: tables in dynamic shared memory, 64 x 3 x ((nk+1)|1) x 16 B (40 KB at nk = 12)
-#define RHOKB_ZT 6
+#define RHOKB_ZT_MAX 5      // kz values per combo: 4 or 5, whichever wastes less (six need 52 accumulators: spills at 128 registers)
 #define MMC_MAX_NK_FULL 16     // the full-energy k-space path (per-move kernels: MMC_MAX_NK)
 
 struct RhokBigArgs {
@@ -239,13 +240,15 @@ struct RhokBigArgs {
     const double4 *com;          // volume trial on the resident state (NULL: sites as they are), as RhokArgs
     double f;
     int US;
-    int n_ptiles, n_ztiles;      // combos = n_ptiles x n_ztiles; combo c = pt * n_ztiles + zt
+    const int2 *pairs; int npairs;       // (kx, |ky|) pairs that own a k-vector, sorted by kx² + ky²
+    const int2 *combos; int n_combos;    // {pair tile, kz tile} combos that hold at least one k-vector
     int group_begin;             // first combo group of this launch (k-range sharding: a rank's share of the groups)
 };
 
-static __global__ void __launch_bounds__(RHOKB_BLOCK, 2) k_rhok_big(const __grid_constant__ RhokBigArgs A)
+// blockDim.x = 32 x (warps per CTA, <= 8): the host picks the warp count that divides the combos evenly over gridDim.y
+template <int ZT>
+__device__ __forceinline__ void rhok_big_body(const RhokBigArgs &A)
 {
-    constexpr int ZT = RHOKB_ZT;
     constexpr int NACC = 4 + 8 * ZT;
     extern __shared__ __align__(16) double2 s_tab[];        // [RHOKB_SITES][3][TS], TS = (nk+1)|1 (odd: conflict-free row builds)
     const int TS = (A.nk + 1) | 1;
@@ -254,13 +257,15 @@ static __global__ void __launch_bounds__(RHOKB_BLOCK, 2) k_rhok_big(const __grid
     const int c0 = A.s_begin + blockIdx.x * A.per_block;
     const int c1 = min(A.s_end, c0 + A.per_block);
     const double twopi = 2.0 * 3.141592653589793;
-    const int NK = A.nk, W1 = NK + 1;
-    const int combo = (A.group_begin + blockIdx.y) * RHOKB_WARPS + warp;
-    const bool live = combo < A.n_ptiles * A.n_ztiles;
-    const int pt = live ? combo / A.n_ztiles : 0, zt = live ? combo - pt * A.n_ztiles : 0;
+    const int NK = A.nk;
+    const int combo = (A.group_begin + blockIdx.y) * (int)(blockDim.x >> 5) + warp;
+    const bool live = combo < A.n_combos;
+    const int2 cb = live ? A.combos[combo] : make_int2(0, 0);
+    const int pt = cb.x, zt = cb.y;
     const int pi = pt * 32 + lane;
-    const bool lane_on = live && pi < W1 * W1;
-    const int kx = lane_on ? pi / W1 : 0, ky = lane_on ? pi - (pi / W1) * W1 : 0;
+    const bool lane_on = live && pi < A.npairs;
+    const int2 pr = A.pairs[lane_on ? pi : 0];
+    const int kx = pr.x, ky = pr.y;
     const int kz0 = zt * ZT + 1;                 // this tile's kz = kz0 .. kz0 + ZT − 1 (kz = 0 rides with tile 0)
     double acc[NACC];
 #pragma unroll
@@ -268,8 +273,8 @@ static __global__ void __launch_bounds__(RHOKB_BLOCK, 2) k_rhok_big(const __grid
 
     for (int base = c0; base < c1; base += RHOKB_SITES) {
         __syncthreads();
-        if (tid < RHOKB_SITES * 3) {
-            const int l = tid / 3, d = tid - 3 * l;
+        for (int t = tid; t < RHOKB_SITES * 3; t += blockDim.x) {
+            const int l = t / 3, d = t - 3 * l;
             double x = 0.0, q = 0.0;
             if (base + l < c1) {
                 const double4 s = A.site[base + l];
@@ -288,22 +293,29 @@ static __global__ void __launch_bounds__(RHOKB_BLOCK, 2) k_rhok_big(const __grid
         }
         __syncthreads();
         if (!live) continue;
+        // row pointers advanced per site (the lambda's index arithmetic was 40 % of the loop's instructions)
+        const double2 *px = s_tab + kx, *py = s_tab + TS + ky, *pz = s_tab + 2 * TS + kz0;
+        const int nz = min(ZT, NK - kz0 + 1);
+        auto sweep = [&](auto full_tag) {                                  // FULL: all ZT kz of this tile exist (no predicates in the loop)
+            constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll 2
-        for (int l = 0; l < RHOKB_SITES; ++l) {
-            const double2 ex = s_t(l, 0, kx), ey = s_t(l, 1, ky);
-            const double p1 = ex.x * ey.x, p2 = ex.y * ey.y, p3 = ex.y * ey.x, p4 = ex.x * ey.y;
-            const double ur = p1 - p2, ui = p3 + p4, vr = p1 + p2, vi = p3 - p4;
-            acc[0] += ur; acc[1] += ui; acc[2] += vr; acc[3] += vi;       // kz = 0 (used by tile 0 only)
+            for (int l = 0; l < RHOKB_SITES; ++l, px += 3 * TS, py += 3 * TS, pz += 3 * TS) {
+                const double2 ex = *px, ey = *py;
+                const double p1 = ex.x * ey.x, p2 = ex.y * ey.y, p3 = ex.y * ey.x, p4 = ex.x * ey.y;
+                const double ur = p1 - p2, ui = p3 + p4, vr = p1 + p2, vi = p3 - p4;
+                if (zt == 0) { acc[0] += ur; acc[1] += ui; acc[2] += vr; acc[3] += vi; }      // kz = 0 rides with tile 0 (uniform)
 #pragma unroll
-            for (int z = 0; z < ZT; ++z) {
-                if (kz0 + z <= NK) {                                       // uniform
-                    const double2 ez = s_t(l, 2, kz0 + z);                 // same address in every lane: broadcast
-                    double *a = acc + 4 + 8 * z;
-                    a[0] = fma(ur, ez.x, a[0]); a[1] = fma(ui, ez.y, a[1]); a[2] = fma(ur, ez.y, a[2]); a[3] = fma(ui, ez.x, a[3]);
-                    a[4] = fma(vr, ez.x, a[4]); a[5] = fma(vi, ez.y, a[5]); a[6] = fma(vr, ez.y, a[6]); a[7] = fma(vi, ez.x, a[7]);
+                for (int z = 0; z < ZT; ++z) {
+                    if (FULL || z < nz) {                                      // uniform
+                        const double2 ez = pz[z];                              // same address in every lane: broadcast
+                        double *a = acc + 4 + 8 * z;
+                        a[0] = fma(ur, ez.x, a[0]); a[1] = fma(ui, ez.y, a[1]); a[2] = fma(ur, ez.y, a[2]); a[3] = fma(ui, ez.x, a[3]);
+                        a[4] = fma(vr, ez.x, a[4]); a[5] = fma(vi, ez.y, a[5]); a[6] = fma(vr, ez.y, a[6]); a[7] = fma(vi, ez.x, a[7]);
+                    }
                 }
             }
-        }
+        };
+        if (nz == ZT) sweep(std::true_type{}); else sweep(std::false_type{});
     }
     if (!lane_on) return;
     const int W = 2 * NK + 1;
@@ -329,3 +341,7 @@ static __global__ void __launch_bounds__(RHOKB_BLOCK, 2) k_rhok_big(const __grid
         }
     }
 }
+
+// blockDim.x = 128 or 256 (registers are allocated per four warps): four or two CTAs per SM
+template <int ZT>
+static __global__ void __launch_bounds__(256, 2) k_rhok_big(const __grid_constant__ RhokBigArgs A) { rhok_big_body<ZT>(A); }

@@ -38,7 +38,7 @@ void free_system(mmc_handle *h)
 void free_ewald(mmc_handle *h)
 {
     dfree(h->S.kvec); dfree(h->S.cfac); dfree(h->S.rhok[0]); dfree(h->S.rhok[1]);
-    dfree(h->d_rhok_trial); dfree(h->d_cfac_trial); dfree(h->d_vec); dfree(h->d_kpairs); dfree(h->d_kindex);
+    dfree(h->d_rhok_trial); dfree(h->d_cfac_trial); dfree(h->d_vec); dfree(h->d_kpairs); dfree(h->d_kcombos); dfree(h->d_kindex);
     if (h->h_vec) cudaFreeHost(h->h_vec);
     h->h_vec = nullptr;
     h->has_ewald = false;
@@ -635,11 +635,37 @@ int mmc_ewald_prepare(mmc_handle *h, double kappa, int32_t nk, int32_t k_sq_max,
             kindex[((size_t)kx * W + (ky + nk)) * W + (kz + nk)] = i;
             used[(size_t)kx * (nk + 1) + std::abs(ky)] = 1;
         }
+        // sorted by kx² + ky² (stable): a tile of 32 consecutive pairs then shares its largest useful kz, and k_rhok_big
+        // skips the (pair tile, kz tile) combos that hold no k-vector at all
         std::vector<int2> kp;
+        std::vector<int> kzmax((size_t)(nk + 1) * (nk + 1), 0);
+        for (int i = 0; i < n; ++i) {
+            int &m = kzmax[(size_t)h->kxyz[3 * i] * (nk + 1) + std::abs(h->kxyz[3 * i + 1])];
+            m = std::max(m, std::abs(h->kxyz[3 * i + 2]));
+        }
         for (int kx = 0; kx <= nk; ++kx)
             for (int ky = 0; ky <= nk; ++ky)
                 if (used[(size_t)kx * (nk + 1) + ky]) kp.push_back(make_int2(kx, ky));
+        std::stable_sort(kp.begin(), kp.end(), [](const int2 &p, const int2 &q) { return p.x * p.x + p.y * p.y < q.x * q.x + q.y * q.y; });
         h->n_kpairs = (int)kp.size();
+        {   // combos for ZT = 4 and 5 kz values per warp: the cheaper list wins (per combo and site: 8 + 8·ZT DFMA slots)
+            std::vector<int2> best; int best_zt = 4; long long best_cost = -1;
+            for (int zt = 4; zt <= 5; ++zt) {
+                std::vector<int2> cb;
+                for (int pt = 0; pt * 32 < (int)kp.size(); ++pt) {
+                    int mz = 0;
+                    for (int j = pt * 32; j < std::min((int)kp.size(), pt * 32 + 32); ++j) mz = std::max(mz, kzmax[(size_t)kp[j].x * (nk + 1) + kp[j].y]);
+                    const int nzt = std::max(1, (mz + zt - 1) / zt);          // (tile 0 of a pair tile also carries kz = 0)
+                    for (int z = 0; z < nzt; ++z) cb.push_back(make_int2(pt, z));
+                }
+                const long long cost = (long long)cb.size() * (8 + 8 * zt);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cb; best_zt = zt; }
+            }
+            h->k_zt = best_zt; h->n_kcombos = (int)best.size();
+            dfree(h->d_kcombos);
+            CK(cudaMalloc(&h->d_kcombos, sizeof(int2) * best.size()));
+            CK(cudaMemcpyAsync(h->d_kcombos, best.data(), sizeof(int2) * best.size(), cudaMemcpyHostToDevice, h->stream));
+        }
         CK(cudaMalloc(&h->d_kpairs, sizeof(int2) * kp.size()));
         CK(cudaMalloc(&h->d_kindex, sizeof(int) * kindex.size()));
         CK(cudaMemcpyAsync(h->d_kpairs, kp.data(), sizeof(int2) * kp.size(), cudaMemcpyHostToDevice, h->stream));

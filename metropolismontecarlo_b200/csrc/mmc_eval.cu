@@ -47,18 +47,24 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
     const int n = s_end - s_begin;
     const int nkv = h->S.nkvecs;
     const bool v2 = h->n_kpairs <= 32 && h->S.nk <= 6 && h->use_rhok_v2;
-    const bool big = !v2;                       // large k-sets: combos of (32 pairs) x (6 kz) per warp, k_rhok_big
+    const bool big = !v2;                       // large k-sets: combos of (32 pairs) x (4 or 5 kz) per warp, k_rhok_big
     const int chunk = v2 ? RHOK2_SITES : RHOKB_SITES;
     const int W1 = h->S.nk + 1;
-    const int n_ptiles = (W1 * W1 + 31) / 32, n_ztiles = std::max(1, (h->S.nk + RHOKB_ZT - 1) / RHOKB_ZT);
-    const int n_groups = (n_ptiles * n_ztiles + RHOKB_WARPS - 1) / RHOKB_WARPS;
+    // combos of (32 (kx,|ky|) pairs) x (ZT kz values) that hold k-vectors (list built by mmc_ewald_prepare); warps per CTA: four or
+    // eight (registers are allocated per four warps), whichever costs less — dead warps in the last CTA row against one more
+    // rebuild of the e^{ik·r} tables per row (≈ 1200 warp instructions per 64 sites; a warp spends 64 x (12 + 8·ZT) on them)
+    const int ZT = h->k_zt, n_combos = h->n_kcombos;
+    auto row_cost = [&](int w) { return (long long)((n_combos + w - 1) / w) * (w * 64LL * (12 + 8 * ZT) + 1200); };
+    const int big_warps = row_cost(4) <= row_cost(8) ? 4 : 8;
+    const int n_groups = (n_combos + big_warps - 1) / big_warps;
     int g0 = 0, g1 = n_groups;
     if (big && h->rhok_kshard && h->cfg.world > 1 && com == nullptr && s_begin == 0 && s_end == h->S.n_sites) {
         // k-RANGE sharding (north star): this rank sums ALL sites for its share of the combo groups
         g0 = (int)((long long)n_groups * h->cfg.rank / h->cfg.world);
         g1 = (int)((long long)n_groups * (h->cfg.rank + 1) / h->cfg.world);
     }
-    const int waves = std::max(1, 2 * h->sm_count * std::max(1, h->rhok_split) / (big ? std::max(1, g1 - g0) : 1));
+    const int resident = (big && big_warps == 4) ? 4 : 2;          // CTAs per SM
+    const int waves = std::max(1, resident * h->sm_count * std::max(1, h->rhok_split) / (big ? std::max(1, g1 - g0) : 1));
     int per = std::max(2 * chunk, (n + waves - 1) / waves);
     per = (per + chunk - 1) / chunk * chunk;
     const int nb = std::max(1, (n + per - 1) / per);
@@ -87,9 +93,13 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
         if (h->S.nk > MMC_MAX_NK_FULL) FAIL(MMC_EINVAL, "nk too large for the rebuild kernel (<= 16)");
         // every CTA writes only its own k-vectors: the others of this launch's k-share must read as zero
         if (g1 - g0 < n_groups) CK(cudaMemsetAsync(part, 0, (size_t)nb * nkv * sizeof(double2), st));
-        RhokBigArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->d_kindex, box, part, com, f, US, n_ptiles, n_ztiles, g0};
+        RhokBigArgs R{site, s_begin, s_end, per, h->S.nk, nkv, h->d_kindex, box, part, com, f, US, h->d_kpairs, h->n_kpairs, h->d_kcombos, n_combos, g0};
         const size_t smem = (size_t)RHOKB_SITES * 3 * ((h->S.nk + 1) | 1) * sizeof(double2);
-        if (g1 > g0) k_rhok_big<<<dim3(nb, g1 - g0), RHOKB_BLOCK, smem, st>>>(R);
+        if (g1 > g0) {
+            const dim3 grid(nb, g1 - g0);
+            if (ZT == 4) k_rhok_big<4><<<grid, 32 * big_warps, smem, st>>>(R);
+            else k_rhok_big<5><<<grid, 32 * big_warps, smem, st>>>(R);
+        }
     }
     LAUNCH_CHECK();
     if (h->tm.on) cudaEventRecord(h->tm.ev[3], st);
@@ -148,7 +158,11 @@ void mmc_detail::eval_set_attributes()
     cudaFuncSetAttribute(k_pairs<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_pairs<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_pairs<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_rhok_big, cudaFuncAttributeMaxDynamicSharedMemorySize, RHOKB_SITES * 3 * 17 * (int)sizeof(double2));
+    const int big_smem = RHOKB_SITES * 3 * 17 * (int)sizeof(double2);
+    cudaFuncSetAttribute(k_rhok_big<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem);
+    cudaFuncSetAttribute(k_rhok_big<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem);
+    cudaFuncSetAttribute(k_rhok_big<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // four CTAs x 41 KB
+    cudaFuncSetAttribute(k_rhok_big<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #define X(D) cudaFuncSetAttribute(k_pairs_v7<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V7_SMEM);
     MMC_FOR_DIRECT_DEGS(X)
 #undef X

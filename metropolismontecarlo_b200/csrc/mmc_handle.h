@@ -67,6 +67,7 @@ struct mmc_handle {
     int2 *d_kpairs = nullptr;
     int *d_kindex = nullptr;
     int n_kpairs = 0;
+    int2 *d_kcombos = nullptr; int n_kcombos = 0, k_zt = 4;   // k_rhok_big: (pair tile, kz tile) combos that hold k-vectors; kz per tile
     double *d_cfac_trial = nullptr;
     std::vector<double> cfac_trial;
 
