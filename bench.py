@@ -366,6 +366,9 @@ def e2_large_k(ms, fp64_peak):
             "evals_per_s": 1e3 / r[2], "ms_per_eval_wall": float(r[2]), "kernel_ms": {"pairs": float(r[0]), "rhok_rebuild": float(r[1])},
             "rhok_kernel": "k_rhok_big", "rhok_algorithmic_tflops": flops / (r[1] * 1e-3) / 1e12,
             "rhok_frac_of_fp64_peak": (flops / (r[1] * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
+            "rhok_note": "algorithmic = the reference's 14 flop per (site, k) (SURVEY 8d); the kernel forms e^{i(kx x +- ky y)} once per (kx, |ky|) "
+                         "and gets the four sign combinations of (ky, kz) from 8 DFMA, i.e. it executes ~4 flop per (site, k), so the algorithmic "
+                         "rate may exceed the DFMA peak; executed: FP64 pipe 63 % busy (profiles/r02_ncu_rhok_big.txt)",
             "energy_per_molecule_K": p.energy / ms.n_mol}
 
 
