@@ -291,7 +291,9 @@ typedef struct {
 int mmc_get_counters(mmc_handle *h, mmc_counters *out);
 /* device times [ms] of the most recent full-energy evaluation, measured with CUDA events on the
  * handle's stream when timing is enabled: ms4[0] pair kernel, ms4[1] rho(k) rebuild kernel,
- * ms4[2] binning + gather, ms4[3] whole evaluation up to the result copy */
+ * ms4[2] binning + gather, ms4[3] whole evaluation up to the result copy.  enabled = 1: every phase (the events and the
+ * stream synchronisations they need cost ~35 us per evaluation); enabled = 2: the pair kernel only (two event records, no
+ * synchronisation: what bench.py leaves on inside its timed region) */
 int mmc_set_timing(mmc_handle *h, int32_t enabled);
 int mmc_last_timings(mmc_handle *h, float *ms4);
 /* what the last full-energy evaluation did: molecule pairs inside the cutoff (summed over ranks

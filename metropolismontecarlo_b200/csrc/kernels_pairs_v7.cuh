@@ -677,6 +677,10 @@ struct TailArgs {
     // sharded evaluation: the last block stores the vector into slot `rank` of every rank's exchange buffer (kernels_peer.cuh)
     int push;
     PeerArgs peer;
+    // ... and then waits for every rank's vector, adds them in rank order and finishes (k_peer_sum_finish's body)
+    int peer_finish;
+    PeerFinishArgs fin;
+    double *fin_out;               // [nvec] the summed vector
 };
 
 static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_constant__ TailArgs A)
@@ -776,6 +780,10 @@ static __global__ void __launch_bounds__(TAIL_THREADS) k_eval_tail(const __grid_
         if (tid < P.world) {
             volatile unsigned long long *f = P.flag[tid] + (size_t)P.parity * P.world + P.rank;
             *f = P.epoch;
+        }
+        if (A.peer_finish) {
+            __syncthreads();
+            peer_sum_finish_block(P, A.fin_out, A.fin);
         }
     }
 }

@@ -72,8 +72,8 @@ struct PeerFinishArgs {
     unsigned long long seq;
 };
 
-static __global__ void __launch_bounds__(256) k_peer_sum_finish(const __grid_constant__ PeerArgs P, double *__restrict__ out,
-                                                                 const __grid_constant__ PeerFinishArgs F)
+// (body shared with k_eval_tail, whose last block runs it right after its own push: one launch less per sharded evaluation)
+__device__ __forceinline__ void peer_sum_finish_block(const PeerArgs &P, double *__restrict__ out, const PeerFinishArgs &F)
 {
     __shared__ int s_bad;
     __shared__ double s_red[8];
@@ -111,4 +111,10 @@ static __global__ void __launch_bounds__(256) k_peer_sum_finish(const __grid_con
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long *>(F.host_out + MMC_NSCAL) = F.seq;
     }
+}
+
+static __global__ void __launch_bounds__(256) k_peer_sum_finish(const __grid_constant__ PeerArgs P, double *__restrict__ out,
+                                                                 const __grid_constant__ PeerFinishArgs F)
+{
+    peer_sum_finish_block(P, out, F);
 }

@@ -932,7 +932,7 @@ int mmc_get_counters(mmc_handle *h, mmc_counters *out)
 int mmc_set_timing(mmc_handle *h, int32_t enabled)
 {
     if (!h) return MMC_EINVAL;
-    h->tm.on = enabled != 0;
+    h->tm.on = enabled == 2 ? 2 : (enabled != 0 ? 1 : 0);
     return MMC_OK;
 }
 

@@ -78,7 +78,7 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
     }
     double2 *part = h->d_rhok_partial + (size_t)block0 * nkv;
     const int US = h->US > 0 ? h->US : 1;
-    if (h->tm.on) cudaEventRecord(h->tm.ev[2], st);
+    if (h->tm.full()) cudaEventRecord(h->tm.ev[2], st);
     if (v2) {
         Rhok2Args R{site, s_begin, s_end, per, nkv, h->n_kpairs, h->d_kpairs, h->d_kindex, box, part, com, f, US};
         switch (h->S.nk) {
@@ -102,7 +102,7 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
         }
     }
     LAUNCH_CHECK();
-    if (h->tm.on) cudaEventRecord(h->tm.ev[3], st);
+    if (h->tm.full()) cudaEventRecord(h->tm.ev[3], st);
     if (out) {
         k_rhok_reduce<<<(nkv + 31) / 32, dim3(32, 32), 0, st>>>(h->d_rhok_partial, nb, nkv, out);
         LAUNCH_CHECK();
@@ -296,14 +296,14 @@ HostTrace g_trace;
 // Enqueues one evaluation on the v7 path and leaves this rank's partial-sum vector in d_vec.  finish: one rank — E_recip,
 // resident ρ(k) and the scalars in the mapped host slot come out of the same tail kernel.
 int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, double *d_vec, bool finish, double2 *dst0, double2 *dst1,
-            const PeerArgs *push = nullptr)
+            const PeerArgs *push = nullptr, const PeerFinishArgs *fin = nullptr)
 {
     const DevSystem &S = h->S;
     const bool ewald = style == MMC_STYLE_EWALD;
     int rc = v7_alloc(h, grid_cells(h, style, E.box), grid_cells(h, style, E.box) + 2);
     if (rc) return rc;
     const V7Grid G = v7_grid(h, style, E);
-    if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
+    if (h->tm.full()) cudaEventRecord(h->tm.ev[4], h->stream);
     // ---- ρ(k) rebuild (RecipLong, ewalds.jl:538-604) of this rank's share of the sites: depends on nothing the pair path
     // produces (a volume trial scales the resident sites inside the kernel).  overlap_rhok: 0 = on this stream before the pair
     // path; 1 = on the low-priority side stream, made eligible TOGETHER with the pair kernel (after the gather): the persistent
@@ -402,7 +402,7 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
             if ((rc = launch_rhok(true, rsm, rs1, blocks_early, &nb_late))) return rc;
             rhok_blocks = blocks_early + nb_late;
         }
-        if (w == 0 && h->tm.on) { cudaEventRecord(h->tm.ev[5], h->stream); cudaEventRecord(h->tm.ev[0], h->stream); }
+        if (w == 0 && h->tm.on) { if (h->tm.full()) cudaEventRecord(h->tm.ev[5], h->stream); cudaEventRecord(h->tm.ev[0], h->stream); }
         A.G = Gw; A.ticket = fl + 8 + w;
         const long long units = (long long)V3_GROUPS * G.ncd * G.ncd * G.ncd / (E.world * nwin) + 1;      // (about: the grid size only)
         const int grid = (int)std::max(1LL, std::min<long long>((long long)h->v7_ctas_per_sm * h->sm_count, units));
@@ -430,8 +430,10 @@ int eval_v7(mmc_handle *h, int style, const EvalCtx &E, const ErfPoly &ep, doubl
     T.host_out = h->d7_res; T.seq = finish ? ++h->res_seq : 0;
     T.push = push ? 1 : 0;
     if (push) T.peer = *push;
+    T.peer_finish = (push && fin) ? 1 : 0;
+    if (push && fin) { T.fin = *fin; T.fin_out = h->d_peer_total; }
     k_eval_tail<<<TAIL_BLOCKS, TAIL_THREADS, 0, h->stream>>>(T); LAUNCH_CHECK();
-    if (h->tm.on) cudaEventRecord(h->tm.ev[6], h->stream);
+    if (h->tm.full()) cudaEventRecord(h->tm.ev[6], h->stream);
     h->last_fast = 7; h->last_mode = 0; h->last_ncd = G.ncd;
     return MMC_OK;
 }
@@ -468,7 +470,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
     const int ncd = grid_cells(h, style, E.box);
     const bool cells = ncd >= 3;
     CK(cudaMemsetAsync(d_vec, 0, (MMC_NSCAL + 2 * (size_t)std::max(S.nkvecs, 1)) * sizeof(double), h->stream));
-    if (h->tm.on) cudaEventRecord(h->tm.ev[4], h->stream);
+    if (h->tm.full()) cudaEventRecord(h->tm.ev[4], h->stream);
     // ρ(k) reads the resident sites, or — for a volume trial — the scaled copy (padded slots of a mixed topology carry q = 0)
     const long long ns_all = (E.f != 1.0 && h->mixed) ? (long long)S.n_mol * US : S.n_sites;
     int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
@@ -526,7 +528,7 @@ int eval_partials(mmc_handle *h, int style, const EvalCtx &E, double *d_vec)
                  zl_lo, std::min(zl_cnt, ncd), h->mixed ? S.mol : nullptr, h->mixed ? S.atype : nullptr, h->mixed ? h->d_stype : nullptr};
     if (E.wait_sites) CK(cudaStreamWaitEvent(h->stream, E.wait_sites, 0));      // binning needed the COMs only; the gather needs the sites
     k_gather<<<gm, tb, 0, h->stream>>>(G); LAUNCH_CHECK();
-    if (h->tm.on) cudaEventRecord(h->tm.ev[5], h->stream);
+    if (h->tm.full()) cudaEventRecord(h->tm.ev[5], h->stream);
 
     PairArgs P{};
     P.com = h->d_scom; P.site = h->d_ssite; P.cell_start = h->d_start;
@@ -667,6 +669,7 @@ void read_timings(mmc_handle *h, int style)
 {
     if (!h->tm.on) return;
     cudaEventElapsedTime(&h->tm.ms[0], h->tm.ev[0], h->tm.ev[1]);
+    if (!h->tm.full()) return;
     if (style == MMC_STYLE_EWALD) cudaEventElapsedTime(&h->tm.ms[1], h->tm.ev[2], h->tm.ev[3]);
     cudaEventElapsedTime(&h->tm.ms[2], h->tm.ev[4], h->tm.ev[5]);
     cudaEventElapsedTime(&h->tm.ms[3], h->tm.ev[4], h->tm.ev[6]);
@@ -678,7 +681,7 @@ int finish_v7(mmc_handle *h, int style, const EvalCtx &E, mmc_properties *out)
     double hv[MMC_NSCAL];
     int rc = v7_wait(h, hv);
     if (rc) return rc;
-    if (h->tm.on) { CK(cudaStreamSynchronize(h->stream)); if (style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side)); }
+    if (h->tm.full()) { CK(cudaStreamSynchronize(h->stream)); if (style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side)); }
     if (hv[7] != 0.0) return 1;
     if (hv[3] != 0.0) { h->v7_left_for_overlap = true; return 1; }     // back to k_pairs_v7 once the overlaps are gone
     h->last_pairs = (long long)hv[5];
@@ -705,9 +708,9 @@ int finalize(mmc_handle *h, int style, const EvalCtx &E, double *d_vec, double2 
         LAUNCH_CHECK();
     }
     CK(cudaMemcpyAsync(h->h_vec, d_vec, MMC_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (h->tm.on && h->last_fast != 7) cudaEventRecord(h->tm.ev[6], h->stream);
+    if (h->tm.full() && h->last_fast != 7) cudaEventRecord(h->tm.ev[6], h->stream);
     CK(cudaStreamSynchronize(h->stream));
-    if (h->tm.on && style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side));
+    if (h->tm.full() && style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side));
     return finalize_host(h, style, E, h->h_vec, dst0, dst1, out);
 }
 
@@ -1062,10 +1065,8 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     E.wait_sites = h->ev_sites; E.rhok_external = true; E.rhok_blocks = blocks; E.rhok_done = h->ev_join;
     h->peer_epoch += 1;
     const PeerArgs P = peer_args(h);
-    if ((rc = eval_v7(h, style, E, ep, h->d_vec, false, nullptr, nullptr, &P))) return rc;
-    PeerFinishArgs F{ewald ? S.nkvecs : 0, E.d_cfac, S.rhok[0], S.rhok[1], h->d7_res, ++h->res_seq};
-    k_peer_sum_finish<<<1, 256, 0, h->stream>>>(P, h->d_peer_total, F);
-    LAUNCH_CHECK();
+    const PeerFinishArgs F{ewald ? S.nkvecs : 0, E.d_cfac, S.rhok[0], S.rhok[1], h->d7_res, ++h->res_seq};
+    if ((rc = eval_v7(h, style, E, ep, h->d_vec, false, nullptr, nullptr, &P, &F))) return rc;      // push + sum + finish in the tail
     double hv[MMC_NSCAL];
     if ((rc = v7_wait(h, hv))) return rc;
     if (h->h7_res[MMC_NSCAL + 1] != 0.0) FAIL(MMC_ENCCL, "peer exchange: a rank's partial sums did not arrive");
@@ -1098,8 +1099,11 @@ int mmc_potential_sharded_begin(mmc_handle *h, int32_t style)
     h->peer_epoch += 1;
     const PeerArgs P = peer_args(h);
     ErfPoly ep{};
-    if (v7_eligible(h, style, E, ep)) {          // the tail kernel of the evaluation pushes the vector itself
-        if ((rc = eval_v7(h, style, E, ep, h->d_vec, false, nullptr, nullptr, &P))) return rc;
+    h->sharded_fused = false;
+    if (v7_eligible(h, style, E, ep)) {          // the tail kernel of the evaluation pushes the vector itself, waits for the peers' and finishes
+        const PeerFinishArgs F{style == MMC_STYLE_EWALD ? h->S.nkvecs : 0, E.d_cfac, h->S.rhok[0], h->S.rhok[1], h->d7_res, ++h->res_seq};
+        if ((rc = eval_v7(h, style, E, ep, h->d_vec, false, nullptr, nullptr, &P, &F))) return rc;
+        h->sharded_fused = true;
     } else {
         if ((rc = eval_partials(h, style, E, h->d_vec))) return rc;
         k_peer_push<<<h->cfg.world, 256, 0, h->stream>>>(P, h->d_vec);
@@ -1118,14 +1122,16 @@ int mmc_potential_sharded_end(mmc_handle *h, mmc_properties *out)
     const int style = h->sharded_style;
     const PeerArgs P = peer_args(h);
     EvalCtx E{1.0, h->S.box, h->S.kappa, h->S.cfac, h->cfg.rank, h->cfg.world};
-    PeerFinishArgs F{style == MMC_STYLE_EWALD ? h->S.nkvecs : 0, E.d_cfac, h->S.rhok[0], h->S.rhok[1], h->d7_res, ++h->res_seq};
-    k_peer_sum_finish<<<1, 256, 0, h->stream>>>(P, h->d_peer_total, F);
-    LAUNCH_CHECK();
-    if (h->tm.on && h->last_fast != 7) cudaEventRecord(h->tm.ev[6], h->stream);
+    if (!h->sharded_fused) {
+        PeerFinishArgs F{style == MMC_STYLE_EWALD ? h->S.nkvecs : 0, E.d_cfac, h->S.rhok[0], h->S.rhok[1], h->d7_res, ++h->res_seq};
+        k_peer_sum_finish<<<1, 256, 0, h->stream>>>(P, h->d_peer_total, F);
+        LAUNCH_CHECK();
+    }
+    if (h->tm.full() && h->last_fast != 7) cudaEventRecord(h->tm.ev[6], h->stream);
     double hv[MMC_NSCAL];
     int rc = v7_wait(h, hv);
     if (rc) return rc;
-    if (h->tm.on) { CK(cudaStreamSynchronize(h->stream)); if (style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side)); }
+    if (h->tm.full()) { CK(cudaStreamSynchronize(h->stream)); if (style == MMC_STYLE_EWALD) CK(cudaStreamSynchronize(h->side)); }
     if (h->h7_res[MMC_NSCAL + 1] != 0.0) FAIL(MMC_ENCCL, "peer exchange: a rank's partial sums did not arrive");
     rc = finalize_host(h, style, E, hv, h->S.rhok[0], h->S.rhok[1], out);
     if (style == MMC_STYLE_EWALD) h->new_valid = false;

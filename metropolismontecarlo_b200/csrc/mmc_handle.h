@@ -14,7 +14,7 @@
 
 // host-side fold of one move launch: exactly the numbers Loop() gets from its calls
 struct MoveOut { double lj_pot[2], lj_vir[2], qq[2], d_recip; int overlap[2]; };
-struct Timers { cudaEvent_t ev[8]; bool on = false; float ms[4] = {0, 0, 0, 0}; };
+struct Timers { cudaEvent_t ev[8]; int on = 0; float ms[4] = {0, 0, 0, 0}; bool full() const { return on == 1; } };   // on: 0 off, 1 every phase, 2 pair kernel only
 
 struct mmc_handle {
     mmc_config cfg{};
@@ -137,6 +137,7 @@ struct mmc_handle {
     double *d7_rows = nullptr;
     float4 *d7_gf = nullptr;
     double4 *d7_unit_partial = nullptr, *d7_block_sums = nullptr;
+    bool sharded_fused = false;                     // the pending sharded evaluation finishes inside its own tail kernel
     int *d7_order = nullptr;                        // [3 ncd³] k_order7: draw order of the units, expensive first
     int d7_ncd = 0;
     size_t d7_partial_cap = 0;

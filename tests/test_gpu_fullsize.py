@@ -220,3 +220,38 @@ def test_config_c_32000_atoms_against_oracle():
         assert np.abs(r_g - r_o).max() < 1e-12 and np.abs(eng.download_atoms() - r_o).max() < 1e-12
         assert rel(st_g.total_energy, st_o.total_energy) < 1e-10
     eng.close()
+
+
+def test_mixed_topology_at_full_size():
+    """A 256 000-molecule water + ion mixture (2000 single-site ions, three LJ types; 764 000 sites) through the cell-list
+    pair kernel on the padded evaluation copy: totals = Σ_i rows / 2, sampled rows (ions and waters) against the oracle's
+    O(N) per-molecule functions, RecipLong and EwaldSelf against the oracle, and a volume trial at f = 1 == potential()."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.water_ion_mixture(N_E, 2000)
+    assert ms.n_sites == 3 * (N_E - 2000) + 2000
+    eng = water_engine(ms, 10.0)
+    p = eng.potential("ewald")
+    info = eng.last_eval_info()
+    assert info["mode"] == "cells" and info["pair_kernel"] == "k_pairs" and p.overlaps == 0
+    lj, vir, qq, ov = eng.energy_all("ewald")
+    assert not ov.any()
+    assert rel(lj.sum() / 2, p.lj) < 1e-10 and rel(qq.sum() / 2, p.real) < 1e-10
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    ions = np.flatnonzero(ms.last_atom == ms.first_atom) + 1
+    assert len(ions) == 2000
+    rng = np.random.default_rng(5)
+    sample = np.unique(np.concatenate([[1, N_E], ions[:6], ions[-3:], rng.integers(1, N_E + 1, 20)]))
+    for i in sample:
+        e0, v0 = ora.LJ_poly_dU(int(i), s, 10.0, ms.box)
+        c0, _, ov0 = ora.EwaldShort(int(i), s, ew, 10.0, ms.box)
+        assert not ov0
+        assert rel(lj[i - 1], e0) < 1e-10 and rel(qq[i - 1], c0) < 1e-10, i
+        assert abs(vir[i - 1] - v0) < 1e-10 * max(1.0, abs(v0), abs(e0)), i
+    assert rel(p.recip, ora.RecipLong(ew, ms.coords, ms.charge, ms.box) * systems.FACTOR) < 1e-10
+    assert rel(p.self_, ora.EwaldSelf(ew, ms.charge)) < 1e-10
+    v = eng.volume_trial(ms.box, systems.ALPHA / ms.box, "ewald")
+    eng.volume_reject()
+    for f in ("energy", "virial", "lj", "real", "recip"):
+        assert rel(getattr(v, f), getattr(p, f)) < 1e-12, f
+    eng.close()

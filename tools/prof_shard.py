@@ -26,4 +26,16 @@ for ov in (0, 1):
             rows.append((t["pairs_ms"], t["rhok_ms"], t["bin_gather_ms"], t["total_ms"]))
         r = np.median(np.array(rows[3:]), axis=0)
         print(f"world {world} rank {rank} overlap {ov} ctas/SM {ctas}: pairs {r[0]*1e3:6.1f} us  rhok {r[1]*1e3:6.1f}  bin+gather {r[2]*1e3:6.1f}  total(dev) {r[3]*1e3:6.1f} us", flush=True)
+eng.debug_set("overlap_rhok", 1); eng.debug_set("v7_ctas_per_sm", 4)
+for pct in (0, 30, 50, 70):
+    eng.debug_set("rhok_early_pct", pct)
+    rows = []
+    for k in range(12):
+        flush.fill_(k); torch.cuda.synchronize()
+        eng.potential_partial("ewald", vec.data_ptr())
+        eng.potential_finalize("ewald", vec.data_ptr())
+        t = eng.last_timings()
+        rows.append((t["pairs_ms"], t["rhok_ms"], t["bin_gather_ms"], t["total_ms"]))
+    r = np.median(np.array(rows[3:]), axis=0)
+    print(f"world {world} rank {rank} rhok_early_pct {pct}: pairs {r[0]*1e3:6.1f} us  total(dev) {r[3]*1e3:6.1f} us", flush=True)
 eng.close()
