@@ -158,14 +158,21 @@ static __global__ void __launch_bounds__(1024) k_partition7(const int *__restric
     };
     unsigned long long mine = 0;
     for (int c = lo; c < hi; ++c) mine += cost(c);
-    s_part[tid] = mine;
+    // exclusive prefix over the 1024 threads: warp scans + the 32 warp totals (a serial scan by one thread was 16 us of the 40)
+    __shared__ unsigned long long s_wsum[32];
+    unsigned long long incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+    if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long run = 0;
-        for (int t = 0; t < 1024; ++t) { const unsigned long long v = s_part[t]; s_part[t] = run; run += v; }
-        s_total = run;
-        range[0] = 0; range[world] = ncell;
+    if (tid < 32) {
+        const unsigned long long w = s_wsum[tid];
+        unsigned long long wi = w;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o); if (tid >= o) wi += v; }
+        s_wsum[tid] = wi - w;
+        if (tid == 31) { s_total = wi; range[0] = 0; range[world] = ncell; }
     }
+    __syncthreads();
+    s_part[tid] = s_wsum[tid >> 5] + incl - mine;
     __syncthreads();
     // boundary r is the first cell whose prefix reaches total · r / world: found by the thread whose share contains it
     unsigned long long run = s_part[tid];
@@ -188,7 +195,6 @@ static __global__ void __launch_bounds__(1024) k_partition7(const int *__restric
 static __global__ void __launch_bounds__(1024) k_order7(const int *__restrict__ count, int n, const int *__restrict__ range, int seg0, int *__restrict__ order)
 {
     __shared__ unsigned s_hist[1024];
-    __shared__ unsigned s_max;
     const int tid = threadIdx.x, seg = blockIdx.x + seg0;
     const int c0 = range[seg], c1 = range[seg + 1];
     const int u0 = V3_GROUPS * c0, nu = V3_GROUPS * (c1 - c0);
@@ -206,15 +212,9 @@ static __global__ void __launch_bounds__(1024) k_order7(const int *__restrict__ 
         return (unsigned)(nc * nb2);
     };
     s_hist[tid] = 0u;
-    if (tid == 0) s_max = 1u;
     __syncthreads();
-    unsigned mx = 0;
-    for (int t = tid; t < nu; t += 1024) mx = max(mx, cost(u0 + t));
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((tid & 31) == 0) atomicMax(&s_max, mx);
-    __syncthreads();
-    const unsigned cmax = s_max;
-    auto cls = [&](unsigned cst) -> int { return 1023 - (int)((unsigned long long)cst * 1023ull / cmax); };   // 0 = most expensive
+    // classes on the absolute scale (cost <= 64 · 2 · 5 · 64): no pass for the maximum
+    auto cls = [&](unsigned cst) -> int { return 1023 - (int)min(1023u, cst / 40u); };   // 0 = most expensive
     for (int t = tid; t < nu; t += 1024) atomicAdd(&s_hist[cls(cost(u0 + t))], 1u);
     __syncthreads();
     // exclusive scan of the 1024 class sizes (one value per thread: warp scans + the 32 warp totals)

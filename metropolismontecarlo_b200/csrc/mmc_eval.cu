@@ -1018,7 +1018,37 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     if ((rc = v7_alloc(h, grid_cells(h, style, E.box), grid_cells(h, style, E.box) + 2))) return rc;
     const V7Grid G = v7_grid(h, style, E);
     // ---- COMs, binning, and which molecule blocks this rank reads
+    g_trace.on = std::getenv("MMC_TRACE_HOST") != nullptr && h->cfg.rank == 0;
+    g_trace.mark(h->stream, "start");
     CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * S.n_mol, cudaMemcpyHostToDevice, h->stream));
+    g_trace.mark(h->stream, "COM copy done");
+    // copies the runs of molecule blocks that `want` selects (the copy stream carries nothing but copies); returns the bytes
+    auto copy_runs = [&](auto want) -> long long {
+        long long nbytes = 0;
+        for (int b = 0; b < nblk;) {
+            if (!want(b)) { ++b; continue; }
+            int e2 = b;
+            while (e2 < nblk && want(e2)) ++e2;
+            const long long s0 = (long long)b * 256 * US, s1 = std::min<long long>((long long)e2 * 256 * US, S.n_sites);
+            if (cudaMemcpyAsync(d_coords + 3 * s0, coords + 3 * s0, sizeof(double) * 3 * (size_t)(s1 - s0), cudaMemcpyHostToDevice, h->copy) != cudaSuccess) return -1;
+            nbytes += (long long)sizeof(double) * 3 * (s1 - s0);
+            b = e2;
+        }
+        return nbytes;
+    };
+    // Which blocks this rank reads is known only after the binning — but it changes slowly from one evaluation to the next (a
+    // Monte Carlo move displaces one molecule by a fraction of an Å), so the blocks the PREVIOUS call needed start crossing the
+    // bus right behind the COMs, while the binning kernels run; whatever turns out to be missing afterwards is copied then.
+    const bool spec = (int)h->need_prev.size() == nblk && h->need_prev_world == E.world;
+    long long bytes = sizeof(double) * 3 * (long long)S.n_mol;
+    if (spec) {
+        CK(cudaEventRecord(h->ev_copy[1], h->stream));
+        CK(cudaStreamWaitEvent(h->copy, h->ev_copy[1], 0));       // behind the COMs, not beside them: the binning waits for those
+        const long long nb = copy_runs([&](int b) { return h->need_prev[b] != 0; });
+        if (nb < 0) FAIL(MMC_ECUDA, "cudaMemcpyAsync (site blocks)");
+        bytes += nb;
+        g_trace.mark(h->copy, "site blocks of the previous call's slab copied");
+    }
     CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
     k_repack_com<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(d_com, S.n_mol, S.box, S.com, h->d_info); LAUNCH_CHECK();
     h->state_version++;
@@ -1033,6 +1063,7 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     CK(cudaMemcpyAsync(h->h7_need, h->d7_need, nblk, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaEventRecord(h->ev_fork, h->stream));
+    g_trace.mark(h->stream, "binned, partitioned, needs on the host");
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
     // ---- this rank's share of the sites for rho(k) (by site index, as in the resident sharded evaluation)
@@ -1040,27 +1071,30 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     const int rs0 = (int)(ns_all * E.rank / E.world), rs1 = (int)(ns_all * (E.rank + 1) / E.world);
     if (ewald)
         for (int b = (rs0 / US) >> 8; b <= (((rs1 - 1) / US) >> 8) && b < nblk; ++b) h->h7_need[b] = 1;
-    // ---- copy the runs of needed blocks; the copy stream carries nothing but copies
+    // ---- copy the runs of needed blocks (those the speculative copy did not bring)
     CK(cudaStreamWaitEvent(h->copy, h->ev_fork, 0));
-    long long bytes = sizeof(double) * 3 * (long long)S.n_mol;
-    for (int b = 0; b < nblk;) {
-        if (!h->h7_need[b]) { ++b; continue; }
-        int e = b;
-        while (e < nblk && h->h7_need[e]) ++e;
-        const long long s0 = (long long)b * 256 * US, s1 = std::min<long long>((long long)e * 256 * US, S.n_sites);
-        CK(cudaMemcpyAsync(d_coords + 3 * s0, coords + 3 * s0, sizeof(double) * 3 * (size_t)(s1 - s0), cudaMemcpyHostToDevice, h->copy));
-        bytes += (long long)sizeof(double) * 3 * (s1 - s0);
-        b = e;
+    {
+        const long long nb = spec ? copy_runs([&](int b) { return h->h7_need[b] && !h->need_prev[b]; }) : copy_runs([&](int b) { return h->h7_need[b] != 0; });
+        if (nb < 0) FAIL(MMC_ECUDA, "cudaMemcpyAsync (site blocks)");
+        bytes += nb;
+    }
+    if (spec) {      // next call's guess = this call's needs; the repack below takes every block that was copied
+        for (int b = 0; b < nblk; ++b) { const unsigned char now = h->h7_need[b]; h->h7_need[b] = now | h->need_prev[b]; h->need_prev[b] = now; }
+    } else {
+        h->need_prev.assign(h->h7_need, h->h7_need + nblk);
+        h->need_prev_world = E.world;
     }
     h->last_h2d_bytes = bytes;
     CK(cudaMemcpyAsync(h->d7_need, h->h7_need, nblk, cudaMemcpyHostToDevice, h->copy));      // (with the rho(k) blocks added)
     CK(cudaEventRecord(h->ev_copy[0], h->copy));
+    g_trace.mark(h->copy, "site blocks copied");
     CK(cudaStreamWaitEvent(h->side, h->ev_copy[0], 0));
     k_repack_sites_blocks<<<(S.n_sites + 255) / 256, 256, 0, h->side>>>(d_coords, h->d7_need, US, S.n_sites, S.site); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev_sites, h->side));
     int blocks = 0;
     if (ewald && (rc = rhok_launch(h, S.site, rs0, rs1, S.box, nullptr, h->side, 0, &blocks))) return rc;
     CK(cudaEventRecord(h->ev_join, h->side));
+    g_trace.mark(h->side, "rho(k) partials done");
     h->partial_resident = true;
     E.wait_sites = h->ev_sites; E.rhok_external = true; E.rhok_blocks = blocks; E.rhok_done = h->ev_join;
     h->peer_epoch += 1;
@@ -1069,6 +1103,8 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     if ((rc = eval_v7(h, style, E, ep, h->d_vec, false, nullptr, nullptr, &P, &F))) return rc;      // push + sum + finish in the tail
     double hv[MMC_NSCAL];
     if ((rc = v7_wait(h, hv))) return rc;
+    g_trace.mark(h->stream, "tail: pushed, peers summed, result published");
+    g_trace.dump();
     if (h->h7_res[MMC_NSCAL + 1] != 0.0) FAIL(MMC_ENCCL, "peer exchange: a rank's partial sums did not arrive");
     rc = finalize_host(h, style, E, hv, S.rhok[0], S.rhok[1], out);
     if (rc == 2) {     // declined / overlapping molecules (every rank takes this branch): the whole state, one GPU, general path

@@ -152,6 +152,8 @@ struct mmc_handle {
     int v7_ctas_per_sm = 4;
     unsigned char *d7_need = nullptr, *h7_need = nullptr;     // domain-decomposed host evaluation: molecule blocks this rank reads
     int need_cap = 0;
+    std::vector<unsigned char> need_prev;     // the blocks the previous domain-decomposed call needed (copied speculatively by the next one)
+    int need_prev_world = 0;
     bool partial_resident = false;                  // after it only those blocks' sites are current on this GPU
     long long last_h2d_bytes = 0;                   // bytes the last mmc_potential_host moved host -> device on this rank
     int intramolecular = 0;                         // mmc_set_intramolecular

@@ -916,6 +916,25 @@ def test_domain_decomposed_host_evaluation_emulated_ranks(world, order):
             assert max(got) <= full
     with pytest.raises(MMCError):
         engs[0].potential("ewald")                      # only a slab of the sites is resident
+    # a DIFFERENT state in the next call (the molecules re-ordered: the same energy, other blocks): the site blocks of the previous
+    # call's slab are copied speculatively behind the COMs, the missing ones after the binning — same Properties
+    perm2 = np.roll(np.arange(ms.n_mol), ms.n_mol // 3)
+    com2 = ms.com[perm2].copy()
+    coords2 = ms.coords.reshape(-1, 3, 3)[perm2].reshape(-1, 3).copy()
+    for _ in range(2):
+        res = [None] * world
+
+        def run2(r):
+            res[r] = engs[r].potential_host(coords2, com2, "ewald")
+        th = [threading.Thread(target=run2, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=120)
+        assert all(p is not None for p in res)
+        for p in res:
+            _check_props(p, want, 1e-11)
+            assert p.energy == res[0].energy
     engs[0].upload_positions(ms.coords, ms.com)
     _check_props(engs[0].potential("ewald"), want, 1e-12)
     for e in engs:
