@@ -118,3 +118,64 @@ static __global__ void __launch_bounds__(256) k_peer_sum_finish(const __grid_con
 {
     peer_sum_finish_block(P, out, F);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// COM all-gather for the domain-decomposed host evaluation: every rank needs ALL centres of mass to bin and partition
+// identically, but only 1/world of them has to cross ITS PCIe link — rank r copies its slice of the caller's COM array into
+// the staging area of its own exchange buffer, publishes "slice r of call e is there" into every rank's flag array
+// (k_com_publish, after the copy in stream order), and k_repack_com_gather builds the resident COM array reading slice q
+// from rank q's staging area over NVLink (plain loads from peer memory) once flag q shows call e.  A rank overwrites its
+// slice for call e + 1 only after it has the result of call e, which needs every rank's partial vector of call e, which every
+// rank pushes after its own gather kernel — so no reader can still be on the old slice: no double buffering.
+// ------------------------------------------------------------------------------------------------------------
+struct ComGatherArgs {
+    const double *stage[MMC_PEER_MAX];        // raw [3 x n_mol] staging areas of all ranks (only slice q of stage[q] is current)
+    unsigned long long *flag[MMC_PEER_MAX];   // flag[q] + r: rank q's copy of "rank r's slice is in place" (epoch)
+    unsigned long long epoch;
+    int world, rank, n_mol;
+    double box;
+    double4 *dcom;
+    int *info;
+};
+
+__host__ __device__ __forceinline__ int com_slice_begin(int n_mol, int world, int q) { return (int)((long long)n_mol * q / world); }
+
+static __global__ void k_com_publish(ComGatherArgs A)
+{
+    __threadfence_system();
+    if ((int)threadIdx.x < A.world) {
+        volatile unsigned long long *f = A.flag[threadIdx.x] + A.rank;
+        *f = A.epoch;
+    }
+}
+
+static __global__ void __launch_bounds__(256) k_repack_com_gather(const __grid_constant__ ComGatherArgs A)
+{
+    __shared__ int s_bad;
+    const int t0 = blockIdx.x * 256, t = t0 + threadIdx.x;
+    auto owner = [&](int m) {
+        int q = (int)((long long)m * A.world / A.n_mol);
+        while (q > 0 && m < com_slice_begin(A.n_mol, A.world, q)) --q;
+        while (q + 1 < A.world && m >= com_slice_begin(A.n_mol, A.world, q + 1)) ++q;
+        return q;
+    };
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    const int q_lo = owner(min(t0, A.n_mol - 1)), q_hi = owner(min(t0 + 255, A.n_mol - 1));
+    if ((int)threadIdx.x <= q_hi - q_lo) {           // this block's one or two source slices
+        volatile unsigned long long *f = A.flag[A.rank] + (q_lo + threadIdx.x);
+        const long long c0 = clock64();
+        while (*f < A.epoch) {
+            __nanosleep(20);
+            if (clock64() - c0 > 20000000000LL) { s_bad = 1; break; }     // ≈10 s: a peer is gone
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (s_bad) { if (threadIdx.x == 0) atomicOr(&A.info[0], REPACK_PEER_TIMEOUT); return; }
+    if (t >= A.n_mol) return;
+    const double *src = A.stage[owner(t)] + 3 * (size_t)t;
+    const double x = __ldcg(src), y = __ldcg(src + 1), z = __ldcg(src + 2);
+    if (!(x >= 0.0 && x <= A.box && y >= 0.0 && y <= A.box && z >= 0.0 && z <= A.box)) atomicOr(&A.info[0], REPACK_COM_OUTSIDE);
+    A.dcom[t] = make_double4(x, y, z, 0.0);
+}

@@ -17,7 +17,6 @@ struct RepackArgs {
     int *info;     // [0] error bits, [1] max sites per molecule, [2] non-uniform flag, [3] charges differ between molecules
 };
 
-enum { REPACK_BAD_ATYPE = 1, REPACK_BAD_RANGE = 2, REPACK_TOO_MANY_SITES = 4, REPACK_COM_OUTSIDE = 8 };
 
 static __global__ void k_repack(RepackArgs A)
 {

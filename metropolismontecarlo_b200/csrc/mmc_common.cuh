@@ -37,6 +37,9 @@ struct DevSystem {
     double2 *rhok[2];
 };
 
+// bits of the upload kernels' validation word (kernels_upload.cuh, kernels_peer.cuh)
+enum { REPACK_BAD_ATYPE = 1, REPACK_BAD_RANGE = 2, REPACK_TOO_MANY_SITES = 4, REPACK_COM_OUTSIDE = 8, REPACK_PEER_TIMEOUT = 16 };
+
 // LJ-active site pair (a, b) of the uniform molecule (eps_ab > 0.001, Ewald/energy.jl:270)
 struct LJActive { int a, b; double eps, sig; };
 

@@ -908,7 +908,12 @@ int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partial
 }
 
 // ---- sharded evaluation with the exchange over NVLink peer memory (kernels_peer.cuh) ----------------------
+// exchange buffer (doubles): [2][world][nvec_cap] vector slots | [2][world] epoch flags | header: COM staging capacity (molecules)
+// | [world] COM-slice flags | [3 x capacity] COM staging area (raw layout of moa.COM)
 static size_t peer_flag_offset_doubles(const mmc_handle *h) { return 2 * (size_t)h->cfg.world * h->peer_nvec_cap; }
+static size_t peer_hdr_offset_doubles(const mmc_handle *h) { return peer_flag_offset_doubles(h) + 2 * (size_t)h->cfg.world; }
+static size_t peer_comflag_offset_doubles(const mmc_handle *h) { return peer_hdr_offset_doubles(h) + 1; }
+static size_t peer_stage_offset_doubles(const mmc_handle *h) { return peer_comflag_offset_doubles(h) + MMC_PEER_MAX; }
 
 int mmc_peer_export(mmc_handle *h, void *handle64)
 {
@@ -917,9 +922,13 @@ int mmc_peer_export(mmc_handle *h, void *handle64)
     CK(cudaSetDevice(h->cfg.device));
     if (!h->d_peer_buf) {
         h->peer_nvec_cap = MMC_NSCAL + 2 * 16384;      // (nk = 16, k² < 257: 8.6 k k-vectors)
-        const size_t doubles = peer_flag_offset_doubles(h) + 2 * (size_t)h->cfg.world;
+        // a system uploaded before the export sizes the COM staging area (the all-gather of mmc_potential_host, kernels_peer.cuh)
+        const unsigned long long stage_cap = h->has_system ? (unsigned long long)h->S.n_mol : 0ull;
+        const size_t doubles = peer_stage_offset_doubles(h) + 3 * (size_t)stage_cap;
         CK(cudaMalloc(&h->d_peer_buf, doubles * sizeof(double)));
         CK(cudaMemset(h->d_peer_buf, 0, doubles * sizeof(double)));
+        CK(cudaMemcpy(h->d_peer_buf + peer_hdr_offset_doubles(h), &stage_cap, sizeof(stage_cap), cudaMemcpyHostToDevice));
+        h->peer_stage_cap = stage_cap;
         CK(cudaMalloc(&h->d_peer_total, h->peer_nvec_cap * sizeof(double)));
         CK(cudaHostAlloc((void **)&h->h_peer_status, sizeof(int), cudaHostAllocMapped));
         *h->h_peer_status = 0;
@@ -947,6 +956,11 @@ int mmc_peer_import(mmc_handle *h, int32_t peer_rank, const void *handle64)
     CK(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
     h->peer_base[peer_rank] = p; h->peer_opened[peer_rank] = true;
     h->peer_ready += 1;
+    {   // every rank ends with the same staging capacity: the smallest one
+        unsigned long long cap = 0;
+        CK(cudaMemcpy(&cap, reinterpret_cast<double *>(p) + peer_hdr_offset_doubles(h), sizeof(cap), cudaMemcpyDeviceToHost));
+        h->peer_stage_cap = std::min(h->peer_stage_cap, cap);
+    }
     return MMC_OK;
 }
 
@@ -959,6 +973,11 @@ int mmc_peer_import_ptr(mmc_handle *h, int32_t peer_rank, void *peer_buffer)
     if (peer_rank == h->cfg.rank || h->peer_base[peer_rank]) return MMC_OK;
     h->peer_base[peer_rank] = peer_buffer;
     h->peer_ready += 1;
+    {
+        unsigned long long cap = 0;
+        CK(cudaMemcpy(&cap, reinterpret_cast<double *>(peer_buffer) + peer_hdr_offset_doubles(h), sizeof(cap), cudaMemcpyDeviceToHost));
+        h->peer_stage_cap = std::min(h->peer_stage_cap, cap);
+    }
     return MMC_OK;
 }
 
@@ -1020,7 +1039,20 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     // ---- COMs, binning, and which molecule blocks this rank reads
     g_trace.on = std::getenv("MMC_TRACE_HOST") != nullptr && h->cfg.rank == 0;
     g_trace.mark(h->stream, "start");
-    CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * S.n_mol, cudaMemcpyHostToDevice, h->stream));
+    // all ranks hold the same system and the same (smallest) staging capacity, so they take the same branch
+    const bool com_gather = h->com_allgather && h->peer_stage_cap >= (unsigned long long)S.n_mol && S.n_mol >= E.world;
+    ComGatherArgs CG{};
+    if (com_gather) {      // 1/world of the COMs over this rank's PCIe link, the rest over NVLink (k_repack_com_gather below)
+        const int m0 = com_slice_begin(S.n_mol, E.world, E.rank), m1 = com_slice_begin(S.n_mol, E.world, E.rank + 1);
+        double *stage = h->d_peer_buf + peer_stage_offset_doubles(h);
+        CK(cudaMemcpyAsync(stage + 3 * (size_t)m0, com + 3 * (size_t)m0, sizeof(double) * 3 * (size_t)(m1 - m0), cudaMemcpyHostToDevice, h->stream));
+        for (int q = 0; q < E.world; ++q) {
+            CG.stage[q] = reinterpret_cast<double *>(h->peer_base[q]) + peer_stage_offset_doubles(h);
+            CG.flag[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(h->peer_base[q]) + peer_comflag_offset_doubles(h));
+        }
+        CG.epoch = ++h->com_epoch; CG.world = E.world; CG.rank = E.rank; CG.n_mol = S.n_mol; CG.box = S.box; CG.dcom = S.com; CG.info = h->d_info;
+    } else
+        CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * S.n_mol, cudaMemcpyHostToDevice, h->stream));
     g_trace.mark(h->stream, "COM copy done");
     // copies the runs of molecule blocks that `want` selects (the copy stream carries nothing but copies); returns the bytes
     auto copy_runs = [&](auto want) -> long long {
@@ -1040,7 +1072,8 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     // Monte Carlo move displaces one molecule by a fraction of an Å), so the blocks the PREVIOUS call needed start crossing the
     // bus right behind the COMs, while the binning kernels run; whatever turns out to be missing afterwards is copied then.
     const bool spec = (int)h->need_prev.size() == nblk && h->need_prev_world == E.world;
-    long long bytes = sizeof(double) * 3 * (long long)S.n_mol;
+    long long bytes = com_gather ? (long long)sizeof(double) * 3 * (com_slice_begin(S.n_mol, E.world, E.rank + 1) - com_slice_begin(S.n_mol, E.world, E.rank))
+                                 : (long long)sizeof(double) * 3 * S.n_mol;
     if (spec) {
         CK(cudaEventRecord(h->ev_copy[1], h->stream));
         CK(cudaStreamWaitEvent(h->copy, h->ev_copy[1], 0));       // behind the COMs, not beside them: the binning waits for those
@@ -1050,7 +1083,13 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
         g_trace.mark(h->copy, "site blocks of the previous call's slab copied");
     }
     CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
-    k_repack_com<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(d_com, S.n_mol, S.box, S.com, h->d_info); LAUNCH_CHECK();
+    if (com_gather) {
+        k_com_publish<<<1, 32, 0, h->stream>>>(CG); LAUNCH_CHECK();
+        k_repack_com_gather<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(CG); LAUNCH_CHECK();
+        g_trace.mark(h->stream, "COMs gathered over NVLink");
+    } else {
+        k_repack_com<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(d_com, S.n_mol, S.box, S.com, h->d_info); LAUNCH_CHECK();
+    }
     h->state_version++;
     CK(cudaMemsetAsync(h->d7_need, 0, nblk, h->stream));
     CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)G.ncd * G.ncd * G.ncd, h->stream));
@@ -1065,6 +1104,7 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     CK(cudaEventRecord(h->ev_fork, h->stream));
     g_trace.mark(h->stream, "binned, partitioned, needs on the host");
     CK(cudaStreamSynchronize(h->stream));
+    if (h->h_up->info[0] & REPACK_PEER_TIMEOUT) FAIL(MMC_ENCCL, "COM all-gather: a rank's slice did not arrive");
     if (h->h_up->info[0] & REPACK_COM_OUTSIDE) FAIL(MMC_EINVAL, "a COM lies outside [0, box] (the reference's PBC keeps COMs inside)");
     // ---- this rank's share of the sites for rho(k) (by site index, as in the resident sharded evaluation)
     const long long ns_all = S.n_sites;

@@ -85,6 +85,9 @@ struct mmc_handle {
     bool peer_opened[MMC_PEER_MAX] = {false};     // opened through cudaIpcOpenMemHandle (to be closed)
     int peer_ready = 0;                           // number of imported ranks
     unsigned long long peer_epoch = 0;
+    unsigned long long peer_stage_cap = 0;        // COM staging capacity (molecules) every rank has: the smallest one
+    unsigned long long com_epoch = 0;
+    int com_allgather = 1;                        // mmc_debug_set "com_allgather": 0 = every rank copies all COMs itself
     double *d_peer_total = nullptr;               // summed vector
     int *h_peer_status = nullptr;                 // mapped pinned host word written by k_peer_sum (no extra copy to read it)
     int *d_peer_status = nullptr;                 // its device alias
