@@ -444,6 +444,9 @@ def run_ours(args, rank, world, local_rank):
     eng.PrepareEwaldVariables(systems.ALPHA / ms.box)
     if args.overlap_rhok >= 0:
         eng.debug_set("overlap_rhok", args.overlap_rhok)
+    for kv in args.debug:                           # library tuning switches for experiments: --debug key=value
+        k_, v_ = kv.split("=")
+        eng.debug_set(k_, int(v_))
     nvec = eng.partial_count()
     vec = torch.zeros(nvec, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -682,6 +685,7 @@ def _main():
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="exchange of the partial sums at N > 1: NVLink peer-memory kernels (default) or an NCCL all-reduce")
     ap.add_argument("--overlap-rhok", dest="overlap_rhok", type=int, default=-1, help="placement of the rho(k) rebuild (library default when < 0)")
+    ap.add_argument("--debug", action="append", default=[], help="mmc_debug_set key=value (experiments)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-moves", action="store_true", help="skip the moves/s legs (configs A/B/C)")
     args = ap.parse_args()

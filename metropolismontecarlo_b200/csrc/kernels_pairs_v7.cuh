@@ -138,7 +138,7 @@ static __global__ void k_bin7(Bin7Args A)
 // Cuts the (z, y, x) order of the cells into `world` contiguous ranges of equal estimated pair work: the work of home cell c is
 // n_c · (n_c + Σ populations of its 13 half-shell neighbours) — the gate tests, to which the survivors are proportional at uniform
 // density.  One CTA; deterministic, so every rank computes the same boundaries from the same (replicated) COMs.
-static __global__ void __launch_bounds__(1024) k_partition7(const int *__restrict__ count, int n, int world, int *range)
+__device__ __forceinline__ void partition7_body(const int *__restrict__ count, int n, int world, int *range)
 {
     __shared__ unsigned long long s_part[1024];
     __shared__ unsigned long long s_total;
@@ -192,11 +192,11 @@ static __global__ void __launch_bounds__(1024) k_partition7(const int *__restric
 // Cost of unit (c, g) = n_c · Σ populations of the group's cells (half of n_c for the home cell itself).  Counting sort on 1024
 // cost classes; the order inside a class is arbitrary — every unit writes its own partial slot, so results do not depend on it.
 // One CTA per segment: segment s = blockIdx.x + seg0 holds the cells [range[s], range[s + 1]); order[3·range[s] + t] = global unit.
-static __global__ void __launch_bounds__(1024) k_order7(const int *__restrict__ count, int n, const int *__restrict__ range, int seg0, int *__restrict__ order)
+__device__ __forceinline__ void order7_body(const int *__restrict__ count, int n, const int *range, int seg, int *__restrict__ order)
 {
     __shared__ unsigned s_hist[1024];
-    const int tid = threadIdx.x, seg = blockIdx.x + seg0;
-    const int c0 = range[seg], c1 = range[seg + 1];
+    const int tid = threadIdx.x;
+    const int c0 = __ldcg(range + seg), c1 = __ldcg(range + seg + 1);
     const int u0 = V3_GROUPS * c0, nu = V3_GROUPS * (c1 - c0);
     auto cost = [&](int ug) -> unsigned {
         const int c = ug / V3_GROUPS, g = ug - c * V3_GROUPS;
@@ -236,6 +236,23 @@ static __global__ void __launch_bounds__(1024) k_order7(const int *__restrict__ 
         const unsigned pos = atomicAdd(&s_hist[cls(cost(u0 + t))], 1u);
         order[u0 + pos] = u0 + t;
     }
+}
+
+static __global__ void __launch_bounds__(1024) k_partition7(const int *__restrict__ count, int n, int world, int *range)
+{
+    partition7_body(count, n, world, range);
+}
+static __global__ void __launch_bounds__(1024) k_order7(const int *__restrict__ count, int n, const int *__restrict__ range, int seg0, int *__restrict__ order)
+{
+    order7_body(count, n, range, blockIdx.x + seg0, order);
+}
+// both in one launch (one CTA): the ranks' ranges, then the draw order of this rank's units
+static __global__ void __launch_bounds__(1024) k_partition_order7(const int *__restrict__ count, int n, int world, int *range, int rank, int *__restrict__ order)
+{
+    partition7_body(count, n, world, range);
+    __threadfence();
+    __syncthreads();
+    order7_body(count, n, range, rank, order);
 }
 
 // mmc_potential_host on one GPU, windowed: the home cells are cut into `nwin` contiguous ranges (range[0 .. nwin]) that are

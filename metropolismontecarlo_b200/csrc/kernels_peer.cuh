@@ -136,46 +136,75 @@ struct ComGatherArgs {
     double box;
     double4 *dcom;
     int *info;
+    unsigned int *zero_words; int n_zero_words;    // k_com_wait clears these (the block-need flags)
+    int *zero_count; int n_zero_count;             // k_repack_com_gather clears these (the cell populations, before k_bin7)
 };
 
-__host__ __device__ __forceinline__ int com_slice_begin(int n_mol, int world, int q) { return (int)((long long)n_mol * q / world); }
+// slices begin on multiples of 256 molecules: a block of the gather kernel has one source rank and its 6 KB chunk is 16-byte aligned
+__host__ __device__ __forceinline__ int com_slice_begin(int n_mol, int world, int q)
+{
+    return q >= world ? n_mol : (int)((long long)n_mol * q / world) / 256 * 256;
+}
 
+// (the slice was written by a host->device copy that completed earlier in this stream: nothing of this kernel's to fence)
 static __global__ void k_com_publish(ComGatherArgs A)
 {
-    __threadfence_system();
     if ((int)threadIdx.x < A.world) {
         volatile unsigned long long *f = A.flag[threadIdx.x] + A.rank;
         *f = A.epoch;
     }
 }
 
-static __global__ void __launch_bounds__(256) k_repack_com_gather(const __grid_constant__ ComGatherArgs A)
+// waits (one thread per rank) until every rank's slice of this call is in place; the gather kernel behind it in the stream needs
+// no flag and no fence of its own (with a system-scope fence in each of its 1000 blocks it took 140 us whenever this GPU's PCIe
+// link was busy with the site copies — the fence's round trip queues behind the DMA traffic — against 25 us on an idle link)
+static __global__ void k_com_wait(ComGatherArgs A)
 {
-    __shared__ int s_bad;
-    const int t0 = blockIdx.x * 256, t = t0 + threadIdx.x;
-    auto owner = [&](int m) {
-        int q = (int)((long long)m * A.world / A.n_mol);
-        while (q > 0 && m < com_slice_begin(A.n_mol, A.world, q)) --q;
-        while (q + 1 < A.world && m >= com_slice_begin(A.n_mol, A.world, q + 1)) ++q;
-        return q;
-    };
-    if (threadIdx.x == 0) s_bad = 0;
+    // (also clears what the kernels behind it accumulate into: the validation word and the block-need flags — two memsets less)
+    if (threadIdx.x < 4) A.info[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < A.n_zero_words; i += blockDim.x) A.zero_words[i] = 0u;
     __syncthreads();
-    const int q_lo = owner(min(t0, A.n_mol - 1)), q_hi = owner(min(t0 + 255, A.n_mol - 1));
-    if ((int)threadIdx.x <= q_hi - q_lo) {           // this block's one or two source slices
-        volatile unsigned long long *f = A.flag[A.rank] + (q_lo + threadIdx.x);
+    if ((int)threadIdx.x < A.world) {
+        volatile unsigned long long *f = A.flag[A.rank] + threadIdx.x;
         const long long c0 = clock64();
         while (*f < A.epoch) {
             __nanosleep(20);
-            if (clock64() - c0 > 20000000000LL) { s_bad = 1; break; }     // ≈10 s: a peer is gone
+            if (clock64() - c0 > 20000000000LL) { atomicOr(&A.info[0], REPACK_PEER_TIMEOUT); break; }     // ≈10 s: a peer is gone
         }
     }
-    __syncthreads();
     __threadfence_system();
-    if (s_bad) { if (threadIdx.x == 0) atomicOr(&A.info[0], REPACK_PEER_TIMEOUT); return; }
+}
+
+// one block = 256 molecules = 768 doubles of the raw array: read as 384 16-byte loads from the owner's staging area (peer memory:
+// 8-byte loads at a 24-byte stride cost three sectors per sector used), turned through shared memory
+static __global__ void __launch_bounds__(256) k_repack_com_gather(const __grid_constant__ ComGatherArgs A)
+{
+    __shared__ double2 s_raw[384];
+    const int t0 = blockIdx.x * 256, t = t0 + threadIdx.x;
+    for (int i = t; i < A.n_zero_count; i += gridDim.x * 256) A.zero_count[i] = 0;
+    int q = (int)((long long)t0 * A.world / A.n_mol);
+    while (q > 0 && t0 < com_slice_begin(A.n_mol, A.world, q)) --q;
+    while (q + 1 < A.world && t0 >= com_slice_begin(A.n_mol, A.world, q + 1)) ++q;
+    const double *src = A.stage[q] + 3 * (size_t)t0;
+    const int nd = 3 * min(256, A.n_mol - t0);            // doubles of this block's chunk
+    for (int i = threadIdx.x; 2 * i < nd; i += 256) {
+        if (2 * i + 1 < nd) s_raw[i] = __ldcg(reinterpret_cast<const double2 *>(src) + i);
+        else s_raw[i] = make_double2(__ldcg(src + 2 * i), 0.0);
+    }
+    __syncthreads();
     if (t >= A.n_mol) return;
-    const double *src = A.stage[owner(t)] + 3 * (size_t)t;
-    const double x = __ldcg(src), y = __ldcg(src + 1), z = __ldcg(src + 2);
+    const double *r = reinterpret_cast<const double *>(s_raw) + 3 * threadIdx.x;
+    const double x = r[0], y = r[1], z = r[2];
     if (!(x >= 0.0 && x <= A.box && y >= 0.0 && y <= A.box && z >= 0.0 && z <= A.box)) atomicOr(&A.info[0], REPACK_COM_OUTSIDE);
     A.dcom[t] = make_double4(x, y, z, 0.0);
+}
+
+// small results to the host through MAPPED pinned memory instead of a device->host copy: a copy would queue in the copy engine
+// behind the host->device site copies another stream has in flight (mmc_potential_host), and the host waits for exactly these bytes
+static __global__ void k_bytes_to_host(const unsigned char *__restrict__ src, int n, const int *__restrict__ info, int n_info,
+                                       unsigned char *h_dst, int *h_info)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) h_dst[i] = src[i];
+    if ((int)threadIdx.x < n_info) h_info[threadIdx.x] = info[threadIdx.x];
+    __threadfence_system();
 }

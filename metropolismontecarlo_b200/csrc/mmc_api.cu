@@ -408,7 +408,10 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
         CK(cudaMalloc(&h->d_ovl, sizeof(unsigned) * n_mol));
         h->ncell_cap = 0; h->rhok_grid_cap = 0;
         h->cap_mol = (int)n_mol; h->cap_sites = (int)n_sites;
-        if (!h->h_up) CK(cudaHostAlloc((void **)&h->h_up, sizeof(*h->h_up), cudaHostAllocDefault));
+        if (!h->h_up) {
+            CK(cudaHostAlloc((void **)&h->h_up, sizeof(*h->h_up), cudaHostAllocMapped));
+            CK(cudaHostGetDevicePointer((void **)&h->d_up, h->h_up, 0));
+        }
     }
     h->has_system = false;
     // ---- DMA the caller's arrays as they are (pinned sources go at full PCIe rate), repack on the device
@@ -960,6 +963,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     const std::string k(key);
     if (k == "chain_cluster_atoms") { h->chain_cluster_atoms = (int)value; return MMC_OK; }
     if (k == "chain_cluster") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
+    if (k == "dd_speculate") { h->dd_speculate = value != 0; return MMC_OK; }
     if (k == "com_allgather") { h->com_allgather = value != 0; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather
     if (k == "rhok_early_pct") { if (value < 0 || value > 90) FAIL(MMC_EINVAL, "rhok_early_pct must be 0..90"); h->rhok_early_pct = (int)value; return MMC_OK; }

@@ -912,7 +912,7 @@ int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partial
 // | [world] COM-slice flags | [3 x capacity] COM staging area (raw layout of moa.COM)
 static size_t peer_flag_offset_doubles(const mmc_handle *h) { return 2 * (size_t)h->cfg.world * h->peer_nvec_cap; }
 static size_t peer_hdr_offset_doubles(const mmc_handle *h) { return peer_flag_offset_doubles(h) + 2 * (size_t)h->cfg.world; }
-static size_t peer_comflag_offset_doubles(const mmc_handle *h) { return peer_hdr_offset_doubles(h) + 1; }
+static size_t peer_comflag_offset_doubles(const mmc_handle *h) { return peer_hdr_offset_doubles(h) + 2; }    // (+2: the staging area stays 16-byte aligned)
 static size_t peer_stage_offset_doubles(const mmc_handle *h) { return peer_comflag_offset_doubles(h) + MMC_PEER_MAX; }
 
 int mmc_peer_export(mmc_handle *h, void *handle64)
@@ -1028,8 +1028,9 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     if (nblk > h->need_cap) {
         dfree(h->d7_need);
         if (h->h7_need) cudaFreeHost(h->h7_need);
-        CK(cudaMalloc(&h->d7_need, nblk));
-        CK(cudaHostAlloc((void **)&h->h7_need, nblk, cudaHostAllocDefault));
+        CK(cudaMalloc(&h->d7_need, (nblk + 3) / 4 * 4));
+        CK(cudaHostAlloc((void **)&h->h7_need, nblk, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void **)&h->d7_need_host, h->h7_need, 0));
         h->need_cap = nblk;
     }
     EvalCtx E{1.0, S.box, S.kappa, S.cfac, h->cfg.rank, h->cfg.world};
@@ -1051,8 +1052,14 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
             CG.flag[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(h->peer_base[q]) + peer_comflag_offset_doubles(h));
         }
         CG.epoch = ++h->com_epoch; CG.world = E.world; CG.rank = E.rank; CG.n_mol = S.n_mol; CG.box = S.box; CG.dcom = S.com; CG.info = h->d_info;
-    } else
+        CG.zero_words = reinterpret_cast<unsigned int *>(h->d7_need); CG.n_zero_words = (nblk + 3) / 4;
+        CG.zero_count = h->d7_count; CG.n_zero_count = G.ncd * G.ncd * G.ncd;
+        CK(cudaEventRecord(h->ev_copy[1], h->stream));
+        k_com_publish<<<1, 32, 0, h->stream>>>(CG); LAUNCH_CHECK();       // the peers wait for this: out first (the host is the
+    } else {                                                               // bottleneck of this call's first 100 us)
         CK(cudaMemcpyAsync(d_com, com, sizeof(double) * 3 * S.n_mol, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaEventRecord(h->ev_copy[1], h->stream));
+    }
     g_trace.mark(h->stream, "COM copy done");
     // copies the runs of molecule blocks that `want` selects (the copy stream carries nothing but copies); returns the bytes
     auto copy_runs = [&](auto want) -> long long {
@@ -1071,36 +1078,33 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     // Which blocks this rank reads is known only after the binning — but it changes slowly from one evaluation to the next (a
     // Monte Carlo move displaces one molecule by a fraction of an Å), so the blocks the PREVIOUS call needed start crossing the
     // bus right behind the COMs, while the binning kernels run; whatever turns out to be missing afterwards is copied then.
-    const bool spec = (int)h->need_prev.size() == nblk && h->need_prev_world == E.world;
+    const bool spec = (int)h->need_prev.size() == nblk && h->need_prev_world == E.world && h->dd_speculate;
     long long bytes = com_gather ? (long long)sizeof(double) * 3 * (com_slice_begin(S.n_mol, E.world, E.rank + 1) - com_slice_begin(S.n_mol, E.world, E.rank))
                                  : (long long)sizeof(double) * 3 * S.n_mol;
     if (spec) {
-        CK(cudaEventRecord(h->ev_copy[1], h->stream));
         CK(cudaStreamWaitEvent(h->copy, h->ev_copy[1], 0));       // behind the COMs, not beside them: the binning waits for those
         const long long nb = copy_runs([&](int b) { return h->need_prev[b] != 0; });
         if (nb < 0) FAIL(MMC_ECUDA, "cudaMemcpyAsync (site blocks)");
         bytes += nb;
         g_trace.mark(h->copy, "site blocks of the previous call's slab copied");
     }
-    CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
     if (com_gather) {
-        k_com_publish<<<1, 32, 0, h->stream>>>(CG); LAUNCH_CHECK();
-        k_repack_com_gather<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(CG); LAUNCH_CHECK();
+        k_com_wait<<<1, 256, 0, h->stream>>>(CG); LAUNCH_CHECK();           // (+ clears the validation word and the need flags)
+        k_repack_com_gather<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(CG); LAUNCH_CHECK();     // (+ clears the cell populations)
         g_trace.mark(h->stream, "COMs gathered over NVLink");
     } else {
+        CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
         k_repack_com<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(d_com, S.n_mol, S.box, S.com, h->d_info); LAUNCH_CHECK();
+        CK(cudaMemsetAsync(h->d7_need, 0, nblk, h->stream));
+        CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)G.ncd * G.ncd * G.ncd, h->stream));
     }
     h->state_version++;
-    CK(cudaMemsetAsync(h->d7_need, 0, nblk, h->stream));
-    CK(cudaMemsetAsync(h->d7_count, 0, sizeof(int) * (size_t)G.ncd * G.ncd * G.ncd, h->stream));
     Bin7Args B{S.com, S.n_mol, (double)G.ncd / S.box, G, h->d7_count, h->d7_bucket, h->d_cell_of};
     k_bin7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(B); LAUNCH_CHECK();
-    k_partition7<<<1, 1024, 0, h->stream>>>(h->d7_count, G.ncd, E.world, h->d7_range + 2); LAUNCH_CHECK();
-    k_order7<<<1, 1024, 0, h->stream>>>(h->d7_count, G.ncd, G.range, G.rank, h->d7_order); LAUNCH_CHECK();
+    k_partition_order7<<<1, 1024, 0, h->stream>>>(h->d7_count, G.ncd, E.world, h->d7_range + 2, G.rank, h->d7_order); LAUNCH_CHECK();
     k_need7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->d_cell_of, S.n_mol, G, h->d7_need); LAUNCH_CHECK();
     h->bin_version = h->state_version; h->bin_ncd = G.ncd; h->bin_world = E.world;
-    CK(cudaMemcpyAsync(h->h7_need, h->d7_need, nblk, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    k_bytes_to_host<<<1, 256, 0, h->stream>>>(h->d7_need, nblk, h->d_info, 4, h->d7_need_host, h->d_up->info); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev_fork, h->stream));
     g_trace.mark(h->stream, "binned, partitioned, needs on the host");
     CK(cudaStreamSynchronize(h->stream));
@@ -1361,7 +1365,8 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     h->state_version++;                                         // new positions: the cell buckets are rebuilt
     h->partial_resident = false;
     h->last_h2d_bytes = (long long)sizeof(double) * 3 * ((long long)S.n_sites + S.n_mol);
-    CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    // (a device->host COPY here would queue in the copy engine behind the site chunks and hold this stream back with it)
+    k_bytes_to_host<<<1, 32, 0, h->stream>>>(nullptr, 0, h->d_info, 4, nullptr, h->d_up->info); LAUNCH_CHECK();
     E.rhok_external = true; E.rhok_blocks = blocks; E.rhok_done = h->ev_join;
     cudaEvent_t win_ev[4];
     if (nwin > 1) {
@@ -1387,10 +1392,10 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
         V7Grid Gw = G; Gw.range = h->d7_range + 16; Gw.world = nwin;
         k_order7<<<nwin, 1024, 0, h->stream>>>(h->d7_count, ncd, Gw.range, 0, h->d7_order); LAUNCH_CHECK();
         k_window_need7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->d_cell_of, S.n_mol, h->US, S.n_sites, nchunk, Gw, nwin, h->d7_range + 24); LAUNCH_CHECK();
-        int need[4] = {0, 0, 0, 0};
-        CK(cudaMemcpyAsync(need, h->d7_range + 24, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        k_bytes_to_host<<<1, 32, 0, h->stream>>>(nullptr, 0, h->d7_range + 24, 4, nullptr, h->d_up->win_need); LAUNCH_CHECK();
         g_trace.mark(h->stream, "binned, window needs known");
         CK(cudaStreamSynchronize(h->stream));          // ~0.15 ms into the call; the site chunks are in flight on the copy stream meanwhile
+        int need[4] = {h->h_up->win_need[0], h->h_up->win_need[1], h->h_up->win_need[2], h->h_up->win_need[3]};
         for (int w = 0; w < nwin; ++w) {
             int c = std::max(0, std::min(need[w], nchunk - 1));
             if (w > 0) c = std::max(c, std::max(0, std::min(need[w - 1], nchunk - 1)));

@@ -43,7 +43,8 @@ struct mmc_handle {
     int cap_mol = 0, cap_sites = 0;     // sizes the resident buffers were allocated for
     int *d_info = nullptr;
     double2 *d_qpart = nullptr;
-    struct UploadResult { int info[4]; double qs[2]; } *h_up = nullptr;   // pinned
+    struct UploadResult { int info[4]; double qs[2]; int win_need[4]; } *h_up = nullptr;   // pinned (mapped: kernels write it directly)
+    UploadResult *d_up = nullptr;     // its device alias
     bool uniform = false;        // every molecule: same site count, same type sequence, packed
     int US = 0;                  // uniform sites per molecule
     bool mixed = false;          // molecules of different size / type sequence: the cell path evaluates a copy padded to ES slots
@@ -87,6 +88,7 @@ struct mmc_handle {
     unsigned long long peer_epoch = 0;
     unsigned long long peer_stage_cap = 0;        // COM staging capacity (molecules) every rank has: the smallest one
     unsigned long long com_epoch = 0;
+    int dd_speculate = 1;                         // mmc_debug_set "dd_speculate": 0 = no speculative site-block copy
     int com_allgather = 1;                        // mmc_debug_set "com_allgather": 0 = every rank copies all COMs itself
     double *d_peer_total = nullptr;               // summed vector
     int *h_peer_status = nullptr;                 // mapped pinned host word written by k_peer_sum (no extra copy to read it)
@@ -153,6 +155,7 @@ struct mmc_handle {
     size_t d7_scratch_cap = 0;
     int *d7_range = nullptr;                        // [0,1] = {0, ncd³}; [2 .. 2+world] = home-cell boundaries of the ranks (k_partition7)
     int v7_ctas_per_sm = 4;
+    unsigned char *d7_need_host = nullptr;                    // device alias of h7_need (mapped pinned)
     unsigned char *d7_need = nullptr, *h7_need = nullptr;     // domain-decomposed host evaluation: molecule blocks this rank reads
     int need_cap = 0;
     std::vector<unsigned char> need_prev;     // the blocks the previous domain-decomposed call needed (copied speculatively by the next one)
