@@ -196,9 +196,8 @@ int mmc_potential_finalize(mmc_handle *h, int32_t style, const double *d_partial
  * Export AFTER mmc_upload_system: the buffer then also holds a staging area for the centres of mass, and mmc_potential_host
  * on the sharded handles copies only 1/world of the COM array over each rank's PCIe link — the other slices are read from
  * the peers' staging areas over NVLink (k_repack_com_gather).  Exported earlier, every rank copies all COMs itself.
- * (Ranks emulated in ONE process share a CUDA context: a rank that is still allocating — cudaMalloc waits for the device —
- * cannot publish while another rank's kernel already spins on its flag; run one evaluation with
- * mmc_debug_set("com_allgather", 0) first.  One process per GPU has no such coupling.) */
+ * (Ranks emulated in ONE process — mmc_peer_import_ptr — always copy all COMs themselves: the all-gather's kernels spin on the
+ * peers' flags early in the call, which deadlocks streams that share one CUDA context.  One process per GPU has no such coupling.) */
 int mmc_peer_export(mmc_handle *h, void *ipc_handle_64_bytes);
 int mmc_peer_import(mmc_handle *h, int32_t peer_rank, const void *ipc_handle_64_bytes);
 int mmc_peer_import_ptr(mmc_handle *h, int32_t peer_rank, void *peer_buffer);

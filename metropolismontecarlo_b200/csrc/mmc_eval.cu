@@ -973,6 +973,7 @@ int mmc_peer_import_ptr(mmc_handle *h, int32_t peer_rank, void *peer_buffer)
     if (peer_rank == h->cfg.rank || h->peer_base[peer_rank]) return MMC_OK;
     h->peer_base[peer_rank] = peer_buffer;
     h->peer_ready += 1;
+    h->peer_same_process = true;      // emulated ranks: streams of ONE context — no kernel may spin on a peer early in the call
     {
         unsigned long long cap = 0;
         CK(cudaMemcpy(&cap, reinterpret_cast<double *>(peer_buffer) + peer_hdr_offset_doubles(h), sizeof(cap), cudaMemcpyDeviceToHost));
@@ -1041,7 +1042,7 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     g_trace.on = std::getenv("MMC_TRACE_HOST") != nullptr && h->cfg.rank == 0;
     g_trace.mark(h->stream, "start");
     // all ranks hold the same system and the same (smallest) staging capacity, so they take the same branch
-    const bool com_gather = h->com_allgather && h->peer_stage_cap >= (unsigned long long)S.n_mol && S.n_mol >= E.world;
+    const bool com_gather = h->com_allgather && !h->peer_same_process && h->peer_stage_cap >= (unsigned long long)S.n_mol && S.n_mol >= E.world;
     ComGatherArgs CG{};
     if (com_gather) {      // 1/world of the COMs over this rank's PCIe link, the rest over NVLink (k_repack_com_gather below)
         const int m0 = com_slice_begin(S.n_mol, E.world, E.rank), m1 = com_slice_begin(S.n_mol, E.world, E.rank + 1);

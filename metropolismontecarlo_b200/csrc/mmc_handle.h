@@ -88,6 +88,7 @@ struct mmc_handle {
     unsigned long long peer_epoch = 0;
     unsigned long long peer_stage_cap = 0;        // COM staging capacity (molecules) every rank has: the smallest one
     unsigned long long com_epoch = 0;
+    bool peer_same_process = false;               // peers imported by pointer (ranks emulated in one process)
     int dd_speculate = 1;                         // mmc_debug_set "dd_speculate": 0 = no speculative site-block copy
     int com_allgather = 1;                        // mmc_debug_set "com_allgather": 0 = every rank copies all COMs itself
     double *d_peer_total = nullptr;               // summed vector

@@ -41,7 +41,17 @@ def _worker(rank, world, port, out):
     for _ in range(2):                               # the domain-decomposed host-array form (each rank copies its slab only)
         d = eng.potential_host(ms.coords, ms.com, "ewald")
         res.append((d.energy, d.virial, d.recip, d.real))
-    res.append((float(eng.last_host_bytes()), 0.0, 0.0, 0.0))
+    b_gather = float(eng.last_host_bytes())
+    # a different state (the molecules re-ordered: the same energy): the previous call's site blocks go speculatively, the rest after
+    perm = np.roll(np.arange(ms.n_mol), ms.n_mol // 3)
+    d = eng.potential_host(ms.coords.reshape(-1, 3, 3)[perm].reshape(-1, 3).copy(), ms.com[perm].copy(), "ewald")
+    res.append((d.energy, d.virial, d.recip, d.real))
+    eng.debug_set("com_allgather", 0)                # every rank copies all COMs itself (both ranks switch together)
+    d = eng.potential_host(ms.coords, ms.com, "ewald")
+    res.append((d.energy, d.virial, d.recip, d.real))
+    d = eng.potential_host(ms.coords, ms.com, "ewald")
+    res.append((d.energy, d.virial, d.recip, d.real))
+    res.append((b_gather, float(eng.last_host_bytes()), 0.0, 0.0))
     np.save(f"{out}.{rank}.npy", np.array(res))
     dist.barrier()
     eng.close()
@@ -69,6 +79,12 @@ def test_peer_exchange_two_processes(tmp_path):
         assert abs(r0[0][k] - w) <= 1e-12 * abs(w)
         assert abs(r0[3][k] - w) <= 1e-12 * abs(w)   # NCCL form agrees too
         assert abs(r0[4][k] - w) <= 1e-12 * abs(w) and abs(r0[5][k] - w) <= 1e-12 * abs(w)   # and the domain-decomposed host form
-    assert np.array_equal(r0[4:6], r1[4:6])
+    assert np.array_equal(r0[4:9], r1[4:9])
+    for j in (6, 7, 8):                              # re-ordered state; COMs copied by every rank instead of gathered over NVLink
+        for k, w in enumerate((want.energy, want.virial, want.recip, want.real)):
+            assert abs(r0[j][k] - w) <= 1e-11 * abs(w), (j, k)
     full = 24 * (ms.n_sites + ms.n_mol)
-    assert max(r0[6][0], r1[6][0]) < 0.85 * full     # each rank copied its slab, not the whole site array
+    assert max(r0[9][1], r1[9][1]) < 0.85 * full     # each rank copied its slab, not the whole site array
+    # with the all-gather a rank copies only its slice of the COMs (slices begin on multiples of 256 molecules)
+    cut = ms.n_mol // 2 // 256 * 256
+    assert r0[9][1] - r0[9][0] == 24 * (ms.n_mol - cut) and r1[9][1] - r1[9][0] == 24 * cut
