@@ -53,9 +53,9 @@ def workload_config(n_mol):
         "n_molecules": n_mol,
         "l2": "flushed before every timed evaluation (256 MiB device write); state itself (35 MB) is L2-sized",
         "step": "one step = --evals-per-step evaluations (default 10), each timed with CUDA events on the launching stream",
-        "sharding": "z-slabs of the cell grid (pair work) and rho(k) sites split per rank; the 682-double partial vectors are exchanged "
-                    "peer to peer over NVLink (CUDA IPC buffers; the evaluation's tail kernel pushes, k_peer_sum_finish sums) or, with "
-                    "--collective nccl, by one all-reduce",
+        "sharding": "contiguous cost-balanced ranges of the cell grid (pair work) and rho(k) sites split per rank; the 682-double partial "
+                    "vectors are exchanged peer to peer over NVLink (CUDA IPC buffers; the evaluation's tail kernel pushes its vector, waits "
+                    "for the peers', adds them in rank order and finishes) or, with --collective nccl, by one all-reduce",
     }
 
 
@@ -548,7 +548,9 @@ def run_ours(args, rank, world, local_rank):
     ms_pin = ms.copy()
     for name in ("coords", "com"):
         setattr(ms_pin, name, torch.from_numpy(np.ascontiguousarray(getattr(ms, name))).pin_memory().numpy())
-    for _ in range(3):
+    # (warm-up: W steps of evals_per_step calls like the device-timed leg — the first few dozen copies out of a freshly pinned
+    #  buffer run at 60-70 % of the link's rate on some boxes, tools/prof_e2e_ab.py)
+    for _ in range(max(args.warmup, 3) * inner):
         p2 = eng.potential_host(ms_pin.coords, ms_pin.com, "ewald")
     h2d = eng.last_host_bytes()
     barrier()

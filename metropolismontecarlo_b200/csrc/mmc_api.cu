@@ -963,6 +963,7 @@ int mmc_debug_set(mmc_handle *h, const char *key, int64_t value)
     const std::string k(key);
     if (k == "chain_cluster_atoms") { h->chain_cluster_atoms = (int)value; return MMC_OK; }
     if (k == "chain_cluster") { if (value < 1 || value > 8) FAIL(MMC_EINVAL, "chain_cluster must be 1..8"); h->chain_cluster = (int)value; return MMC_OK; }
+    if (k == "host_mailbox") { h->host_mailbox = value != 0; return MMC_OK; }
     if (k == "dd_speculate") { h->dd_speculate = value != 0; return MMC_OK; }
     if (k == "com_allgather") { h->com_allgather = value != 0; return MMC_OK; }
     if (k == "overlap_rhok") { h->overlap_rhok = (int)value; return MMC_OK; }   // 0: one stream, 1: fork at the start, 2: fork after the gather

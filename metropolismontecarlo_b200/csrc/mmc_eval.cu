@@ -1367,7 +1367,8 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
     h->partial_resident = false;
     h->last_h2d_bytes = (long long)sizeof(double) * 3 * ((long long)S.n_sites + S.n_mol);
     // (a device->host COPY here would queue in the copy engine behind the site chunks and hold this stream back with it)
-    k_bytes_to_host<<<1, 32, 0, h->stream>>>(nullptr, 0, h->d_info, 4, nullptr, h->d_up->info); LAUNCH_CHECK();
+    if (h->host_mailbox) { k_bytes_to_host<<<1, 32, 0, h->stream>>>(nullptr, 0, h->d_info, 4, nullptr, h->d_up->info); LAUNCH_CHECK(); }
+    else CK(cudaMemcpyAsync(h->h_up->info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     E.rhok_external = true; E.rhok_blocks = blocks; E.rhok_done = h->ev_join;
     cudaEvent_t win_ev[4];
     if (nwin > 1) {
@@ -1393,7 +1394,8 @@ int mmc_potential_host(mmc_handle *h, const double *coords, const double *com, i
         V7Grid Gw = G; Gw.range = h->d7_range + 16; Gw.world = nwin;
         k_order7<<<nwin, 1024, 0, h->stream>>>(h->d7_count, ncd, Gw.range, 0, h->d7_order); LAUNCH_CHECK();
         k_window_need7<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(h->d_cell_of, S.n_mol, h->US, S.n_sites, nchunk, Gw, nwin, h->d7_range + 24); LAUNCH_CHECK();
-        k_bytes_to_host<<<1, 32, 0, h->stream>>>(nullptr, 0, h->d7_range + 24, 4, nullptr, h->d_up->win_need); LAUNCH_CHECK();
+        if (h->host_mailbox) { k_bytes_to_host<<<1, 32, 0, h->stream>>>(nullptr, 0, h->d7_range + 24, 4, nullptr, h->d_up->win_need); LAUNCH_CHECK(); }
+        else CK(cudaMemcpyAsync(h->h_up->win_need, h->d7_range + 24, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         g_trace.mark(h->stream, "binned, window needs known");
         CK(cudaStreamSynchronize(h->stream));          // ~0.15 ms into the call; the site chunks are in flight on the copy stream meanwhile
         int need[4] = {h->h_up->win_need[0], h->h_up->win_need[1], h->h_up->win_need[2], h->h_up->win_need[3]};

@@ -89,6 +89,7 @@ struct mmc_handle {
     unsigned long long peer_stage_cap = 0;        // COM staging capacity (molecules) every rank has: the smallest one
     unsigned long long com_epoch = 0;
     bool peer_same_process = false;               // peers imported by pointer (ranks emulated in one process)
+    int host_mailbox = 1;                         // mmc_debug_set "host_mailbox": small results through mapped memory (1) or device->host copies (0)
     int dd_speculate = 1;                         // mmc_debug_set "dd_speculate": 0 = no speculative site-block copy
     int com_allgather = 1;                        // mmc_debug_set "com_allgather": 0 = every rank copies all COMs itself
     double *d_peer_total = nullptr;               // summed vector
