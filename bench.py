@@ -38,9 +38,9 @@ FLOP_PER_SITE_K = 14         # rho(k) rebuild, 14 flop per (si
 # inside bench.py; these are the capture's values, quoted so that the line carries them, and only for the configuration the
 # capture was made on (config E, one GPU).  Algorithmic bytes: 43 MB of rows + gate coordinates read once (L2-resident).
 NCU_CAPTURE = {
-    "k_pairs_v7": {"dram_bytes": 44416512, "fp64_pipe_busy_pct": 49.1, "issue_slots_busy_pct": 60.9, "fp64_instructions_per_pair": 203,
-                   "warp_instructions": 312.2e6, "source": "profiles/r02_ncu_full_eval_kernels.txt"},
-    "k_rhok_pairs": {"dram_bytes": 24606720, "fp64_pipe_busy_pct": 55.1, "issue_slots_busy_pct": 39.6,
+    "k_pairs_v7": {"dram_bytes": 44249856, "fp64_pipe_busy_pct": 49.4, "issue_slots_busy_pct": 61.4, "fp64_instructions_per_pair": 203,
+                   "warp_instructions": 312.8e6, "source": "profiles/r02_ncu_full_eval_kernels.txt"},
+    "k_rhok_pairs": {"dram_bytes": 24606976, "fp64_pipe_busy_pct": 54.8, "issue_slots_busy_pct": 39.6,
                      "source": "profiles/r02_ncu_full_eval_kernels.txt"},
 }
 
