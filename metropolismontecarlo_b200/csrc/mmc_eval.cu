@@ -1082,6 +1082,12 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
     const bool spec = (int)h->need_prev.size() == nblk && h->need_prev_world == E.world && h->dd_speculate;
     long long bytes = com_gather ? (long long)sizeof(double) * 3 * (com_slice_begin(S.n_mol, E.world, E.rank + 1) - com_slice_begin(S.n_mol, E.world, E.rank))
                                  : (long long)sizeof(double) * 3 * S.n_mol;
+    // (host order = priority order: the gather first — two launches — then the speculative copies, then the binning kernels)
+    if (com_gather) {
+        k_com_wait<<<1, 256, 0, h->stream>>>(CG); LAUNCH_CHECK();           // (+ clears the validation word and the need flags)
+        k_repack_com_gather<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(CG); LAUNCH_CHECK();     // (+ clears the cell populations)
+        g_trace.mark(h->stream, "COMs gathered over NVLink");
+    }
     if (spec) {
         CK(cudaStreamWaitEvent(h->copy, h->ev_copy[1], 0));       // behind the COMs, not beside them: the binning waits for those
         const long long nb = copy_runs([&](int b) { return h->need_prev[b] != 0; });
@@ -1089,11 +1095,7 @@ int potential_host_sharded(mmc_handle *h, const double *coords, const double *co
         bytes += nb;
         g_trace.mark(h->copy, "site blocks of the previous call's slab copied");
     }
-    if (com_gather) {
-        k_com_wait<<<1, 256, 0, h->stream>>>(CG); LAUNCH_CHECK();           // (+ clears the validation word and the need flags)
-        k_repack_com_gather<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(CG); LAUNCH_CHECK();     // (+ clears the cell populations)
-        g_trace.mark(h->stream, "COMs gathered over NVLink");
-    } else {
+    if (!com_gather) {
         CK(cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
         k_repack_com<<<(S.n_mol + 255) / 256, 256, 0, h->stream>>>(d_com, S.n_mol, S.box, S.com, h->d_info); LAUNCH_CHECK();
         CK(cudaMemsetAsync(h->d7_need, 0, nblk, h->stream));
