@@ -17,7 +17,7 @@ std::string g_create_error;
 void free_system(mmc_handle *h)
 {
     dfree(h->S.site); dfree(h->S.com); dfree(h->S.mol); dfree(h->S.atype);
-    dfree(h->d_intra); dfree(h->d_stype); dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums); dfree(h->d_raw); dfree(h->d_info); dfree(h->d_qpart);
+    dfree(h->d_intra); dfree(h->d_stype); dfree(h->d_atype_pad); dfree(h->d_lj); dfree(h->d_mol_uniform); dfree(h->d_qsums); dfree(h->d_raw); dfree(h->d_info); dfree(h->d_qpart);
     h->raw_bytes = 0; h->cap_mol = 0; h->cap_sites = 0;
     dfree(h->d_cell_of); dfree(h->d_start); dfree(h->d_perm); dfree(h->d_flags);
     h->d_count = h->d_fill = nullptr; h->d_maxcount = nullptr; h->d_novl = h->d_errflag = nullptr; h->d_maxdev = nullptr;
@@ -123,7 +123,7 @@ int launch_move_on(mmc_handle *h, const DevSystem &sys, MoveArgs &A, const ErfPo
         std::memcpy(A.commit_site, h->pend_site, sizeof(double) * 3 * h->pend_ns);
         h->pend_kind = 0;                       // this launch writes it back
     }
-    { const int2 mi = (&sys == &h->S) ? mol_of(h, A.i) : make_int2(A.i * h->US, h->US); A.i_first = mi.x; A.i_ns = mi.y; }
+    { const int2 mi = (&sys == &h->S) ? mol_of(h, A.i) : make_int2(A.i * h->ES, h->ES)      /* the evaluation copy: ES slots per molecule */; A.i_first = mi.x; A.i_ns = mi.y; }
     const int blocks = A.n_cfg * A.tiles + A.recip_blocks;
     if (blocks <= 0 || blocks > h->max_slots) FAIL(MMC_EINVAL, "bad move launch size");
     if (sys.max_sites <= 3) k_move<3><<<blocks, MOVE_BLOCK, 0, h->stream>>>(sys, A, poly, h->W);
@@ -478,8 +478,10 @@ int mmc_upload_system(mmc_handle *h, int64_t n_mol, int64_t n_sites, const doubl
             CK(cudaMalloc(&h->d_ssite, sizeof(double4) * need));
             h->ssite_cap = need;
         }
-        dfree(h->d_stype);
+        dfree(h->d_stype); dfree(h->d_atype_pad);
         CK(cudaMalloc(&h->d_stype, need));
+        CK(cudaMalloc(&h->d_atype_pad, need * sizeof(int)));       // types of the padded copy as k_move wants them (Coulomb rows only: all 0)
+        CK(cudaMemsetAsync(h->d_atype_pad, 0, need * sizeof(int), h->stream));
         k_mol_packed<<<(unsigned)((n_mol + 255) / 256), 256, 0, h->stream>>>(h->d_mol_uniform, (int)n_mol, h->ES); LAUNCH_CHECK();
         if (!h->lj.empty())
             CK(cudaMemcpyAsync(h->d_lj, h->lj.data(), sizeof(LJActive) * h->lj.size(), cudaMemcpyHostToDevice, h->stream));

@@ -602,6 +602,9 @@ int overlap_row(mmc_handle *h, const EvalCtx &E, int sorted_index, double *row)
     ErfPoly poly{};                      // rare path: plain erfc()
     DevSystem V = h->S;
     V.site = h->d_ssite; V.com = h->d_scom; V.mol = h->d_mol_uniform;
+    if (h->mixed) {      // the padded copy is a uniform system of ES-slot molecules (padding: q = 0 — contributes nothing, overlaps nothing)
+        V.uni = h->ES; V.max_sites = h->ES; V.n_sites = V.n_mol * h->ES; V.atype = h->d_atype_pad;
+    }
     V.box = E.box; V.kappa = E.kappa;
     MoveArgs A{};
     A.i = sorted_index; A.n_cfg = 1; A.tiles = move_tiles(h); A.recip_blocks = 0;

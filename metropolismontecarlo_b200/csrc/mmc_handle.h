@@ -49,6 +49,7 @@ struct mmc_handle {
     int US = 0;                  // uniform sites per molecule
     bool mixed = false;          // molecules of different size / type sequence: the cell path evaluates a copy padded to ES slots
     int ES = 0;                  // site slots per molecule of the evaluation copy (US, or max_sites when mixed)
+    int *d_atype_pad = nullptr;       // mixed: [n_mol x ES] zeros — the type array the overlap rows' k_move indexes on the padded copy
     signed char *d_stype = nullptr;   // mixed: LJ type per slot of the evaluation copy (−1 = padding)
     size_t ssite_cap = 0;        // capacity of d_ssite in sites
     std::vector<LJActive> lj;

@@ -870,6 +870,44 @@ def test_mixed_topology_on_the_pair_kernels(n_mol, n_ions):
     eng.close()
 
 
+@pytest.mark.parametrize("n_mol,n_ions", [(4096, 300), (512, 40)])
+def test_mixed_topology_overlap_rule(n_mol, n_ions):
+    """The overlap rule (ewalds.jl:359-360: r² < 0.5 with q_a q_b < 0 zeroes the molecule's whole real-space row) on a mixed
+    topology: an anion moved onto a cation, and a water hydrogen onto an anion — potential() (cell mode and tile mode, padded
+    evaluation copy + overlap rows through k_move) and mmc_energy_all against the oracle."""
+    from metropolismontecarlo_b200.energy import water_engine
+    ms = systems.water_ion_mixture(n_mol, n_ions)
+    ions = np.flatnonzero(ms.last_atom == ms.first_atom)
+    a, b = ions[0], ions[1]                                   # charges +1, −1
+    assert ms.charge[ms.first_atom[a] - 1] * ms.charge[ms.first_atom[b] - 1] < 0
+    new_b = np.clip(ms.com[a] + np.array([0.3, 0.2, 0.0]), 0.0, ms.box)
+    ms.coords[ms.first_atom[b] - 1] = new_b
+    ms.com[b] = new_b
+    c = ions[3]                                               # an anion; bring a water's first H onto it
+    w = next(m for m in range(n_mol) if ms.last_atom[m] - ms.first_atom[m] == 2 and abs(m - c) > 5)
+    fa = ms.first_atom[w] - 1
+    shift = (ms.coords[ms.first_atom[c] - 1] + np.array([0.0, 0.25, 0.1])) - ms.coords[fa + 1]
+    ms.coords[fa:fa + 3] += shift
+    ms.com[w] = np.clip(ms.com[w] + shift, 0.0, ms.box)
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    want = ora.potential_ewald(s, ew, 10.0, 10.0, ms.box, 8)
+    assert want.overlaps >= 4
+    eng = water_engine(ms, 10.0)
+    got = eng.potential("ewald")
+    assert eng.last_eval_info()["pair_kernel"] == "k_pairs"
+    _check_props(got, want)
+    assert got.overlaps == want.overlaps
+    lj, vir, qq, ov = eng.energy_all("ewald")
+    for i in (a + 1, b + 1, c + 1, w + 1, 1, n_mol):
+        c0, _, ov0 = ora.EwaldShort(int(i), s, ew, 10.0, ms.box)
+        e0, _ = ora.LJ_poly_dU(int(i), s, 10.0, ms.box)
+        assert bool(ov[i - 1]) == bool(ov0) and (rel(qq[i - 1], c0) < 1e-10 if c0 != 0 else qq[i - 1] == 0.0), i
+        assert rel(lj[i - 1], e0) < 1e-10, i
+    assert ov[a] and ov[b] and ov[c] and ov[w]
+    eng.close()
+
+
 @pytest.mark.parametrize("world,order", [(2, "lattice"), (4, "lattice"), (3, "random")])
 def test_domain_decomposed_host_evaluation_emulated_ranks(world, order):
     """mmc_potential_host on sharded handles (ranks emulated as threads of one process on one GPU): every rank copies all COMs
