@@ -6,7 +6,7 @@ properties of the path plus every oracle piece that is O(N) or O(n_s · NK):
     O(N) scan, energy.jl:209-290, ewalds.jl:293-376), and Σ_i rows / 2 == potential()'s LJ and real-space terms
     (energy.jl:966-1001) — together these pin the pair part of the full evaluation to the oracle;
   * RecipLong and EwaldSelf against the oracle directly (ewalds.jl:538-604, 829-833);
-  * all six pair kernels (v6 … general) agree; sharded partial sums over 8 emulated ranks == unsharded;
+  * the three pair kernels (k_pairs_v7, k_pairs_fast, k_pairs) agree; sharded partial sums over 8 emulated ranks == unsharded;
   * a volume trial at f = 1 reproduces potential(); ρ(k) after delta updates == a fresh rebuild.
 Tolerance 1e-10 relative (north star), stated per assertion.
 """
