@@ -30,3 +30,34 @@ r = at.r.copy()
 rc, acc, delta, st = eng.loop_run_atoms(1.0, at.box / 100, r, u, 300, g0.energy, g0.virial, device=True)
 print("atoms chain", rc, st.n_accepted)
 eng.close()
+# ---- round 2: mixed topologies (padded copy, overlap rows), all-molecule rows, large k-sets, sharded partials, host path
+ms = systems.water_ion_mixture(4096, 300)
+ions = np.flatnonzero(ms.last_atom == ms.first_atom)
+b = ions[1]
+ms.coords[ms.first_atom[b] - 1] = ms.com[b] = np.clip(ms.com[ions[0]] + np.array([0.3, 0.2, 0.0]), 0.0, ms.box)
+eng = water_engine(ms, 10.0)
+p = eng.potential("ewald")
+print("mixed:", eng.last_eval_info(), p.overlaps)
+eng.energy_all("ewald")
+v = eng.volume_trial(ms.box * 1.01, systems.ALPHA / (ms.box * 1.01), "ewald")
+eng.volume_reject()
+eng.set_intramolecular(True); eng.potential("ewald"); eng.set_intramolecular(False)
+eng.close()
+ms = systems.spce_lattice(4000)
+eng = Engine()
+eng.upload_system(ms, 10.0, 10.0)
+for nk, k2 in ((12, 145), (7, 50)):
+    eng.PrepareEwaldVariables(0.32, nk, k2)
+    print("large k:", nk, eng.potential("ewald").recip)
+eng.close()
+import torch
+for r in range(2):
+    e = water_engine(ms, 10.0, rank=r, world=2)
+    vec = torch.zeros(e.partial_count(), dtype=torch.float64, device="cuda")
+    e.potential_partial("ewald", vec.data_ptr())
+    torch.cuda.synchronize()
+    e.close()
+ms = systems.spce_lattice(40000)
+eng = water_engine(ms, 10.0)
+print("host path:", eng.potential_host(ms.coords, ms.com, "ewald").energy)
+eng.close()
