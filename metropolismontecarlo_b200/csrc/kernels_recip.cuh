@@ -100,7 +100,7 @@ k_rhok_energy(const double2 *rho, const double *cfac, int nkvecs, double2 *dst0,
 // are folded in CTA order by k_rhok_reduce as before (deterministic).
 // ------------------------------------------------------------------------------------------
 #define RHOK2_BLOCK 256
-#define RHOK2_SITES 64
+#define RHOK2_SITES 80     // sites per sub-chunk: 3 x 80 = 240 table rows, one per thread in a single pass, ten sites per warp
 
 struct Rhok2Args {
     const double4 *site;
@@ -135,8 +135,8 @@ static __global__ void __launch_bounds__(RHOK2_BLOCK, 2) k_rhok_pairs(Rhok2Args 
 
     for (int base = c0; base < c1; base += RHOK2_SITES) {
         __syncthreads();
-        if (tid < RHOK2_SITES * 3) {
-            const int l = tid / 3, d = tid - 3 * l;
+        for (int t = tid; t < RHOK2_SITES * 3; t += RHOK2_BLOCK) {
+            const int l = t / 3, d = t - 3 * l;
             double x = 0.0, q = 0.0;
             if (base + l < c1) {
                 const double4 s = A.site[base + l];
