@@ -49,7 +49,6 @@ int rhok_launch(mmc_handle *h, const double4 *site, int s_begin, int s_end, doub
     const bool v2 = h->n_kpairs <= 32 && h->S.nk <= 6 && h->use_rhok_v2;
     const bool big = !v2;                       // large k-sets: combos of (32 pairs) x (4 or 5 kz) per warp, k_rhok_big
     const int chunk = v2 ? RHOK2_SITES : RHOKB_SITES;
-    const int W1 = h->S.nk + 1;
     // combos of (32 (kx,|ky|) pairs) x (ZT kz values) that hold k-vectors (list built by mmc_ewald_prepare); warps per CTA: four or
     // eight (registers are allocated per four warps), whichever costs less — dead warps in the last CTA row against one more
     // rebuild of the e^{ik·r} tables per row (≈ 1200 warp instructions per 64 sites; a warp spends 64 x (12 + 8·ZT) on them)
