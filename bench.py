@@ -129,7 +129,8 @@ def cpu_full_energy_sample(ms, n_rows, site_frac, threads):
     s = ora.System(ms.coords, ms.charge, ms.atype, ms.first_atom, ms.last_atom, ms.com, ms.eps, ms.sig)
     kappa = systems.ALPHA / ms.box
     rng = np.random.default_rng(1)
-    i0 = int(rng.integers(0, ms.n_mol - n_rows))
+    n_rows = min(n_rows, ms.n_mol)
+    i0 = int(rng.integers(0, ms.n_mol - n_rows)) if ms.n_mol > n_rows else 0
     t0 = time.perf_counter()
     ora.potential_rows(s, kappa, RC, RC, ms.box, i0, i0 + n_rows, threads)
     t_rows = time.perf_counter() - t0

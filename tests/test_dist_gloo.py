@@ -72,3 +72,24 @@ def test_two_rank_partials_allreduce_to_unsharded(tmp_path):
     assert np.abs(S - want).max() < 1e-11
     e_recip = float((ew.cfac * (S.real ** 2 + S.imag ** 2)).sum()) * ew.factor
     assert abs(e_recip - p.recip) < 1e-11 * abs(p.recip)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (CPU only: the oracle port on a bounded sample) prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--molecules", "4000", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "full_ewald_energy_evals_per_sec" and d["value"] > 0 and d["steps"] == 2
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
