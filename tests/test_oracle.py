@@ -384,3 +384,42 @@ def test_tip3p_lattice_is_rigid_and_neutral():
     s = ora_system(ms)
     e = ora.potential_ewald(s, ora_ewald(ms.box), 9.0, 9.0, ms.box, 2)
     assert np.isfinite(e.energy) and e.lj != 0.0
+
+
+def test_closed_form_terms_against_40_digit_arithmetic():
+    """The terms of potential() that are closed forms of the charges — Wolf's two constants (Ewald/energy.jl:925-934), EwaldSelf
+    (Ewald/ewalds.jl:829-833) — and the opt-in intramolecular correction, evaluated in 40-digit mpmath arithmetic on the float64
+    inputs of coord750 (erfc, erf, sqrt(pi) from mpmath, not from libm): pins what the NIST energies and the row pin leave open."""
+    mpmath = pytest.importorskip("mpmath")
+    from mpmath import mp, mpf
+    mp.dps = 40
+    ms = systems.load_nist(4)
+    s = ora_system(ms)
+    ew = ora_ewald(ms.box)
+    kappa, factor, rc = mpf(float(ew.kappa)), mpf(float(ew.factor)), mpf(10.0)
+    q = [mpf(float(v)) for v in ms.charge]
+    sq, sq2 = sum(q), sum(v * v for v in q)
+    # prefactor = −Σ_i Σ_j q_i q_j erfc(κ r_c)/r_c ;  prefactor2 = (erfc(κ r_c)/(2 r_c) + κ/√π) Σ q²
+    wolf = (-(sq * sq) * mpmath.erfc(kappa * rc) / rc - (mpmath.erfc(kappa * rc) / 2 / rc + kappa / mpmath.sqrt(mpmath.pi)) * sq2) * factor
+    w = ora.potential_wolf(s, ew, 10.0, 10.0, ms.box, n_threads=4)
+    assert abs(mpf(w.wolf_const) - wolf) < mpf(1e-12) * abs(wolf)
+    self_ = -kappa / mpmath.sqrt(mpmath.pi) * sq2 * factor
+    assert abs(mpf(ora.EwaldSelf(ew, ms.charge)) - self_) < mpf(1e-13) * abs(self_)
+    # −factor Σ_mol Σ_{a<b} q_a q_b erf(κ r_ab)/r_ab, r_ab by the reference's minimum image (the NIST files store wrapped molecules)
+    def v1d(c1, c2, box):
+        if c1 < c2:
+            return (c2 - c1) if (c2 - c1) < (c1 - c2 + box) else (c2 - c1 - box)
+        return (c2 - c1) if (c1 - c2) < (c2 - c1 + box) else (c2 - c1 + box)
+    box = mpf(float(ms.box))
+    xyz = [[mpf(float(v)) for v in row] for row in ms.coords]
+    intra = mpf(0)
+    for m in range(ms.n_mol):
+        a0, a1 = int(ms.first_atom[m]) - 1, int(ms.last_atom[m])
+        for a in range(a0, a1):
+            for b in range(a + 1, a1):
+                d = [v1d(xyz[a][k], xyz[b][k], box) for k in range(3)]
+                r = mpmath.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+                intra += q[a] * q[b] * mpmath.erf(kappa * r) / r
+    intra *= -factor
+    got = ora.EwaldIntra(s, float(ew.kappa), float(ew.factor), ms.box)
+    assert got > 0 and abs(mpf(got) - intra) < mpf(1e-12) * abs(intra)
