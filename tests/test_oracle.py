@@ -423,3 +423,36 @@ def test_closed_form_terms_against_40_digit_arithmetic():
     intra *= -factor
     got = ora.EwaldIntra(s, float(ew.kappa), float(ew.factor), ms.box)
     assert got > 0 and abs(mpf(got) - intra) < mpf(1e-12) * abs(intra)
+
+
+def test_recip_long_against_30_digit_arithmetic():
+    """RecipLong (Ewald/ewalds.jl:538-604) and the cfac table of PrepareEwaldVariables (:45-103) on the smallest NIST box (100
+    molecules, L = 20 Å): every ρ(k) = Σ_l q_l e^{i 2π k·r_l / L} and E = Σ_k cfac_k |ρ(k)|² in 30-digit mpmath arithmetic with
+    direct exponentials — the exact value of the formula the reference evaluates by recurrence in float64."""
+    mpmath = pytest.importorskip("mpmath")
+    from mpmath import mp, mpf
+    mp.dps = 30
+    ms = systems.load_nist(1)
+    ew = ora_ewald(ms.box)
+    got_e = ora.RecipLong(ew, ms.coords, ms.charge, ms.box)
+    L, kappa = mpf(float(ms.box)), mpf(float(ew.kappa))
+    b = 1 / (4 * kappa * kappa * L * L)
+    twopi = 2 * mpmath.pi
+    q = [mpf(float(v)) for v in ms.charge]
+    ph = [[twopi * mpf(float(v)) / L for v in row] for row in ms.coords]
+    # e^{i k x} for k = -5..5 per site and axis, from one exponential each (exact to 30 digits)
+    tab = [[[mpmath.expj(k * p) for k in range(-5, 6)] for p in row] for row in ph]
+    energy, worst = mpf(0), mpf(0)
+    kx_ky_kz = [(kx, ky, kz) for kx in range(0, 6) for ky in range(-5, 6) for kz in range(-5, 6) if 0 < kx * kx + ky * ky + kz * kz < 27]
+    assert len(kx_ky_kz) == ew.nkvecs
+    qsum = sum(abs(v) for v in q)
+    for i, (kx, ky, kz) in enumerate(kx_ky_kz):
+        term = sum(q[l] * tab[l][0][kx + 5] * tab[l][1][ky + 5] * tab[l][2][kz + 5] for l in range(len(q)))
+        k_sq = kx * kx + ky * ky + kz * kz
+        kr_sq = twopi * twopi * k_sq
+        cfac = twopi * mpmath.exp(-b * kr_sq) / kr_sq / L * (2 if kx > 0 else 1)
+        energy += cfac * (term.real * term.real + term.imag * term.imag)
+        worst = max(worst, abs(mpf(float(ew.sum_new[i, 0])) - term.real), abs(mpf(float(ew.sum_new[i, 1])) - term.imag))
+        assert abs(mpf(float(ew.cfac[i])) - cfac) < mpf(1e-14) * cfac
+    assert worst < mpf(1e-13) * qsum
+    assert abs(mpf(got_e) - energy) < mpf(1e-12) * energy
