@@ -443,6 +443,7 @@ def test_recip_long_against_30_digit_arithmetic():
     # e^{i k x} for k = -5..5 per site and axis, from one exponential each (exact to 30 digits)
     tab = [[[mpmath.expj(k * p) for k in range(-5, 6)] for p in row] for row in ph]
     energy, worst = mpf(0), mpf(0)
+    terms = []
     kx_ky_kz = [(kx, ky, kz) for kx in range(0, 6) for ky in range(-5, 6) for kz in range(-5, 6) if 0 < kx * kx + ky * ky + kz * kz < 27]
     assert len(kx_ky_kz) == ew.nkvecs
     qsum = sum(abs(v) for v in q)
@@ -451,8 +452,22 @@ def test_recip_long_against_30_digit_arithmetic():
         k_sq = kx * kx + ky * ky + kz * kz
         kr_sq = twopi * twopi * k_sq
         cfac = twopi * mpmath.exp(-b * kr_sq) / kr_sq / L * (2 if kx > 0 else 1)
+        terms.append((term, cfac))
         energy += cfac * (term.real * term.real + term.imag * term.imag)
         worst = max(worst, abs(mpf(float(ew.sum_new[i, 0])) - term.real), abs(mpf(float(ew.sum_new[i, 1])) - term.imag))
         assert abs(mpf(float(ew.cfac[i])) - cfac) < mpf(1e-14) * cfac
     assert worst < mpf(1e-13) * qsum
     assert abs(mpf(got_e) - energy) < mpf(1e-12) * energy
+    # RecipMove (ewalds.jl:718-826) for a rigid displacement of molecule 7: Σ_k cfac (|ρ_new|² − |ρ_old|²) · factor, ρ_new = ρ_old + Δ
+    sl = slice(int(ms.first_atom[6]) - 1, int(ms.last_atom[6]))
+    r_old = ms.coords[sl].copy()
+    r_new = r_old + np.array([0.21, -0.13, 0.08])
+    got_d = ora.RecipMove(ms.box, ew, r_old, r_new, ms.charge[sl])
+    def e3(r, kx, ky, kz):
+        return mpmath.expj(twopi * (kx * mpf(float(r[0])) + ky * mpf(float(r[1])) + kz * mpf(float(r[2]))) / L)
+    delta = mpf(0)
+    for (kx, ky, kz), (term, cfac) in zip(kx_ky_kz, terms):
+        new = term + sum(mpf(float(qa)) * (e3(rn, kx, ky, kz) - e3(ro, kx, ky, kz)) for qa, ro, rn in zip(ms.charge[sl], r_old, r_new))
+        delta += cfac * ((new.real * new.real + new.imag * new.imag) - (term.real * term.real + term.imag * term.imag))
+    delta *= mpf(float(ew.factor))
+    assert abs(mpf(got_d) - delta) < mpf(1e-10) * max(abs(delta), mpf(1))
